@@ -1,0 +1,232 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE ITSELF.
+
+Run only in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference package imports ``timm.models.layers.trunc_normal_``; timm is not installed and there
+is no network, so a 3-line shim is written to a temp dir and put on sys.path.
+Each fixture holds: the config, the module state_dict (float32), the input (float32), optional
+padding mask / noise, and the reference output computed with the module in float64 on those values.
+The reference ships no golden vectors of its own for this path, so these ARE the pins.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import tempfile
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = '/root/reference/efficient-attention'
+
+
+def _import_reference():
+    shim = tempfile.mkdtemp(prefix='timm_shim_')
+    os.makedirs(os.path.join(shim, 'timm', 'models'))
+    open(os.path.join(shim, 'timm', '__init__.py'), 'w').close()
+    open(os.path.join(shim, 'timm', 'models', '__init__.py'), 'w').close()
+    with open(os.path.join(shim, 'timm', 'models', 'layers.py'), 'w') as f:
+        f.write('from torch.nn.init import trunc_normal_\n')
+    sys.path.insert(0, shim)
+    sys.path.insert(0, REF)
+    import efficient_attention as ref  # noqa
+    assert ref.__file__.startswith(REF), ref.__file__
+    return ref
+
+
+def _lively_init(module, seed):
+    """Replace the reference's near-zero init (std .02 => uniform softmax everywhere) by weights that
+    give logits of order 1, so that masking / bias / softmax mistakes are visible in the output."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in module.named_parameters():
+        with torch.no_grad():
+            if name.endswith('relative_attention_bias.weight') or 'bias_table' in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.7)
+            elif p.dim() == 2:
+                p.copy_(torch.randn(p.shape, generator=g) * (1.3 / math.sqrt(p.shape[1])))
+            elif name.endswith('.weight'):           # LayerNorm gain
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))
+            else:                                    # any bias
+                p.copy_(0.2 * torch.randn(p.shape, generator=g))
+
+
+def _save(name, cfg, module, arrays):
+    sd = {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+    out = {f'sd::{k}': v for k, v in sd.items()}
+    out.update({k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in arrays.items() if v is not None})
+    out['cfg'] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print(f'{name:28s} {os.path.getsize(path) / 1024:8.1f} KiB  y {tuple(arrays["y"].shape)}')
+
+
+def _run(module, fn, train_seed=None):
+    """Run in float64; in training mode seed the global RNG so the noise can be re-derived."""
+    module = module.double()
+    if train_seed is None:
+        module.eval()
+    else:
+        module.train()
+        torch.manual_seed(train_seed)
+    with torch.no_grad():
+        return fn(module)
+
+
+def _noise(seed, shape):
+    torch.manual_seed(seed)
+    return torch.randn(shape, dtype=torch.float64)
+
+
+def gen_eva(ref, name, *, B, shape, dim, heads, window, landmarks, attn_2d, overlap=False, use_rpe=False,
+            use_t5=False, adaptive='default', mask_tail=None, train_seed=None, seed=0):
+    cfg = dict(kind='eva', dim=dim, num_heads=heads, window_size=window, num_landmarks=landmarks, attn_2d=attn_2d,
+               overlap_window=overlap, use_rpe=use_rpe, use_t5_rpe=use_t5, adaptive_proj=adaptive, qkv_bias=True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = ref.AttentionFactory.build_attention('eva', dict(
+            dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, use_rpe=use_rpe,
+            window_size=window, attn_2d=attn_2d, overlap_window=overlap, adaptive_proj=adaptive,
+            num_landmarks=landmarks, use_t5_rpe=use_t5))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    mask = None
+    if mask_tail is not None:
+        n = int(np.prod(shape))
+        mask = torch.zeros(B, n, dtype=torch.bool)
+        for b, t in enumerate(mask_tail):
+            if t:
+                mask[b, n - t:] = True
+    y = _run(m, lambda mod: mod(x.double(), mask), train_seed)
+    noise = None
+    if train_seed is not None:
+        n_pad = int(np.prod(shape)) if attn_2d else int(math.ceil(np.prod(shape) / window) * window)
+        chunk = int(math.sqrt(n_pad // landmarks)) if attn_2d else n_pad // landmarks
+        ext = max(1, window // 2) if overlap else 0
+        n_chunks = (shape[0] // chunk) * (shape[1] // chunk) if attn_2d else n_pad // chunk
+        noise = _noise(train_seed, (B, heads, n_chunks, dim // heads))
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, noise=noise, y=y))
+
+
+def gen_local(ref, name, *, kind, B, shape, dim, heads, window=4, attn_2d=False, overlap=False, use_rpe=False,
+              mask_tail=None, seed=0):
+    cfg = dict(kind=kind, dim=dim, num_heads=heads, window_size=window, attn_2d=attn_2d, overlap_window=overlap,
+               use_rpe=use_rpe, qkv_bias=True)
+    args = dict(dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False)
+    if kind == 'local':
+        args.update(use_rpe=use_rpe, window_size=window, attn_2d=attn_2d, overlap_window=overlap)
+    m = ref.AttentionFactory.build_attention(kind, args)
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    mask = None
+    if mask_tail is not None:
+        n = int(np.prod(shape))
+        mask = torch.zeros(B, n, dtype=torch.bool)
+        for b, t in enumerate(mask_tail):
+            if t:
+                mask[b, n - t:] = True
+    y = _run(m, lambda mod: mod(x.double(), mask))
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, y=y))
+
+
+def gen_lara(ref, name, *, B, shape, dim, heads, landmarks, proposal_gen, mis_type='mis-opt', alpha=1.0,
+             antithetic=False, multisample=False, mask_tail=None, train_seed=None, seed=0):
+    cfg = dict(kind='lara', dim=dim, num_heads=heads, num_landmarks=landmarks, proposal_gen=proposal_gen,
+               mis_type=mis_type, alpha_coeff=alpha, use_antithetics=antithetic, use_multisample=multisample,
+               pool_module_type='light', qkv_bias=True)
+    m = ref.AttentionFactory.build_attention('lara', dict(
+        dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, num_landmarks=landmarks,
+        kernel_size=None, proposal_gen=proposal_gen, use_antithetics=antithetic, use_multisample=multisample,
+        pool_module_type='light', mis_type=mis_type, alpha_coeff=alpha))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    mask = None
+    if mask_tail is not None:
+        n = int(np.prod(shape))
+        mask = torch.zeros(B, n, dtype=torch.bool)
+        for b, t in enumerate(mask_tail):
+            if t:
+                mask[b, n - t:] = True
+    y = _run(m, lambda mod: mod(x.double(), mask), train_seed)
+    noise = None
+    if train_seed is not None:
+        n = int(np.prod(shape))
+        s = min(landmarks, n) if len(shape) == 1 else int(math.sqrt(landmarks)) ** 2
+        noise = _noise(train_seed, (B, heads, 2 * s if multisample else s, dim // heads))
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, noise=noise, y=y))
+
+
+def gen_causal(ref, name, *, T, B, dim, heads, window, chunk_size=None, num_chunks=None, causal=True, use_t5=True,
+               overlap=False, adaptive='qk', mask_tail=None, train_seed=None, seed=0):
+    cfg = dict(kind='causal_eva', embed_dim=dim, num_heads=heads, window_size=window, chunk_size=chunk_size,
+               num_chunks=num_chunks, causal=causal, use_t5_rpe=use_t5, overlap_window=overlap, adaptive_proj=adaptive)
+    m = ref.CausalEVAttention(embed_dim=dim, num_heads=heads, self_attention=True, attn_args=Namespace(
+        adaptive_proj=adaptive, num_chunks=num_chunks, chunk_size=chunk_size, causal=causal, use_t5_rpe=use_t5,
+        window_size=window, overlap_window=overlap))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(T, B, dim, generator=g)
+    mask = None
+    if mask_tail is not None:
+        mask = torch.zeros(B, T, dtype=torch.bool)
+        for b, t in enumerate(mask_tail):
+            if t:
+                mask[b, T - t:] = True
+    y = _run(m, lambda mod: mod(x.double(), x.double(), x.double(), key_padding_mask=mask)[0], train_seed)
+    noise = None
+    if train_seed is not None:
+        n_pad = int(math.ceil(T / window) * window)
+        cs = chunk_size if chunk_size is not None else n_pad // num_chunks
+        noise = _noise(train_seed, (B, heads, n_pad // cs, dim // heads))
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, noise=noise, y=y))
+
+
+def main():
+    argparse.ArgumentParser(description=__doc__).parse_args()
+    ref = _import_reference()
+    torch.set_num_threads(8)
+    # --- EVA (eva.py) ---
+    # BASELINE config c1, exact shape
+    gen_eva(ref, 'eva_c1', B=2, shape=(14, 14), dim=192, heads=3, window=7, landmarks=49, attn_2d=True, use_rpe=True)
+    # c3 geometry (28x28, chunk 4x4) at reduced width
+    gen_eva(ref, 'eva_c3_geom', B=1, shape=(28, 28), dim=128, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, seed=3)
+    gen_eva(ref, 'eva_2d_overlap', B=2, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, overlap=True, use_rpe=True, seed=5)
+    gen_eva(ref, 'eva_2d_train', B=2, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, train_seed=11, seed=7)
+    gen_eva(ref, 'eva_2d_noln', B=1, shape=(8, 8), dim=64, heads=2, window=4, landmarks=16, attn_2d=True, adaptive='no-ln', seed=9)
+    gen_eva(ref, 'eva_2d_none', B=1, shape=(8, 8), dim=64, heads=2, window=4, landmarks=16, attn_2d=True, adaptive='none', seed=13)
+    gen_eva(ref, 'eva_2d_t5', B=1, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, use_t5=True, seed=14)
+    gen_eva(ref, 'eva_1d_t5_mask', B=3, shape=(50,), dim=64, heads=2, window=8, landmarks=7, attn_2d=False, overlap=True, use_t5=True, mask_tail=[0, 5, 17], seed=15)
+    gen_eva(ref, 'eva_1d_rpe', B=2, shape=(48,), dim=64, heads=4, window=8, landmarks=6, attn_2d=False, use_rpe=True, mask_tail=[3, 0], seed=17)
+    gen_eva(ref, 'eva_1d_train', B=2, shape=(45,), dim=64, heads=2, window=6, landmarks=8, attn_2d=False, overlap=True, train_seed=21, seed=19)
+    # --- softmax / local (abstract_attention.py, local_attention.py) ---
+    gen_local(ref, 'softmax_mask', kind='softmax', B=2, shape=(37,), dim=64, heads=2, mask_tail=[0, 9], seed=23)
+    gen_local(ref, 'local_2d_rpe', kind='local', B=2, shape=(8, 8), dim=64, heads=2, window=4, attn_2d=True, overlap=True, use_rpe=True, seed=25)
+    gen_local(ref, 'local_1d_mask', kind='local', B=2, shape=(30,), dim=64, heads=2, window=8, overlap=True, use_rpe=True, mask_tail=[4, 0], seed=27)
+    # --- LARA (lara.py) ---
+    gen_lara(ref, 'lara_c4_geom', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', seed=29)
+    gen_lara(ref, 'lara_2d_pool_bh', B=1, shape=(10, 12), dim=64, heads=2, landmarks=16, proposal_gen='pool', mis_type='mis-bh', seed=31)
+    gen_lara(ref, 'lara_2d_vmixed_biased', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='pool-vmixed', mis_type='mis-biased', seed=33)
+    gen_lara(ref, 'lara_2d_noparam', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='no-param-pool', alpha=0.5, seed=35)
+    gen_lara(ref, 'lara_2d_train_anti', B=1, shape=(14, 14), dim=64, heads=2, landmarks=49, proposal_gen='pool-mixed', antithetic=True, train_seed=41, seed=37)
+    gen_lara(ref, 'lara_2d_train_multi', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='pool', multisample=True, train_seed=43, seed=39)
+    gen_lara(ref, 'lara_1d_uneven_mask', B=2, shape=(61,), dim=64, heads=2, landmarks=8, proposal_gen='adaptive-1d', mask_tail=[0, 6], seed=45)
+    gen_lara(ref, 'lara_1d_even', B=2, shape=(64,), dim=64, heads=2, landmarks=8, proposal_gen='adaptive-1d', mis_type='mis-bh', train_seed=47, seed=49)
+    # --- causal EVA (causal_eva.py) ---
+    # the reference's own self-check configuration (causal_eva.py:916-950), shortened sequence
+    gen_causal(ref, 'causal_selfcheck', T=128, B=2, dim=128, heads=8, window=64, chunk_size=16, seed=51)
+    gen_causal(ref, 'causal_c5_geom', T=96, B=2, dim=128, heads=2, window=32, chunk_size=32, seed=53)
+    gen_causal(ref, 'causal_overlap_mask', T=75, B=3, dim=64, heads=2, window=16, chunk_size=8, overlap=True, mask_tail=[0, 7, 30], seed=55)
+    gen_causal(ref, 'causal_numchunks_train', T=64, B=2, dim=64, heads=2, window=16, num_chunks=8, use_t5=False, adaptive='no-ln', train_seed=61, seed=57)
+    gen_causal(ref, 'noncausal_flag', T=64, B=1, dim=64, heads=2, window=16, chunk_size=8, causal=False, overlap=True, seed=59)
+
+
+if __name__ == '__main__':
+    main()
