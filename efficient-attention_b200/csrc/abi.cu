@@ -1,0 +1,258 @@
+// C ABI of libeva_sm100.so (see include/eva_sm100.h).  Validates arguments, builds the internal
+// geometry and enqueues kernels on the caller's stream.  Never throws, never allocates device memory.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(EVA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int ipow(int b, int e) { return e == 2 ? b * b : b; }
+
+int make_geo(const EvaGeometry* in, eva::Geo* g) {
+  if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");
+  if (in->batch <= 0 || in->heads <= 0 || in->tokens <= 0) return fail(EVA_ERR_INVALID, "batch/heads/tokens must be positive");
+  if (in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
+    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (32, 64, 128)", in->head_dim);
+  if (in->dims != 1 && in->dims != 2) return fail(EVA_ERR_INVALID, "dims must be 1 or 2");
+  if (in->io_dtype < EVA_F32 || in->io_dtype > EVA_BF16) return fail(EVA_ERR_INVALID, "unknown io_dtype %d", in->io_dtype);
+  if (in->window <= 0 || in->ext < 0 || in->chunk < 0 || in->chunk_ext < 0) return fail(EVA_ERR_INVALID, "window must be > 0; ext/chunk >= 0");
+  g->B = in->batch; g->H = in->heads; g->N = in->tokens; g->D = in->head_dim;
+  g->dims = in->dims;
+  g->window = in->window; g->ext = in->ext; g->left_only = in->halo_left_only ? 1 : 0;
+  g->chunk = in->chunk; g->chunk_ext = in->chunk_ext;
+  g->causal = in->causal ? 1 : 0; g->mask_queries = in->mask_queries ? 1 : 0;
+  g->mask_fill = in->mask_is_neg_inf ? -INFINITY : eva::kMaskVal;
+  if (in->dims == 2) {
+    if (in->grid_h <= 0 || in->grid_w <= 0 || in->grid_h * in->grid_w != in->tokens)
+      return fail(EVA_ERR_INVALID, "grid %dx%d does not cover %d tokens", in->grid_h, in->grid_w, in->tokens);
+    if (in->grid_h % in->window || in->grid_w % in->window)
+      return fail(EVA_ERR_INVALID, "grid %dx%d not divisible by window %d (eva.py:124-126)", in->grid_h, in->grid_w, in->window);
+    if (in->causal || in->halo_left_only) return fail(EVA_ERR_INVALID, "causal / left-only halos are 1-D only");
+    g->gh = in->grid_h; g->gw = in->grid_w;
+    g->n_windows = (g->gh / g->window) * (g->gw / g->window);
+    g->L = g->window * g->window;
+    g->J = ipow(g->window + 2 * g->ext, 2);
+    if (g->chunk > 0) {
+      if (g->chunk_ext == 0 && (g->gh % g->chunk || g->gw % g->chunk))
+        return fail(EVA_ERR_INVALID, "grid not divisible by chunk %d", g->chunk);
+      g->n_chunks = (g->gh / g->chunk) * (g->gw / g->chunk);
+      g->Jc = ipow(g->chunk + 2 * g->chunk_ext, 2);
+    }
+  } else {
+    if (in->tokens % in->window) return fail(EVA_ERR_INVALID, "tokens %d not a multiple of window %d (pad first)", in->tokens, in->window);
+    g->gh = 1; g->gw = in->tokens;
+    g->n_windows = g->N / g->window;
+    g->L = g->window;
+    g->J = g->window + g->ext + (g->left_only ? 0 : g->ext);
+    if (g->chunk > 0) {
+      if (g->chunk_ext == 0 && g->N % g->chunk) return fail(EVA_ERR_INVALID, "tokens %d not divisible by chunk %d", g->N, g->chunk);
+      g->n_chunks = g->N / g->chunk;
+      g->Jc = g->chunk + g->chunk_ext + (g->left_only ? 0 : g->chunk_ext);
+    }
+  }
+  if (g->chunk == 0) { g->n_chunks = 0; g->Jc = 0; }
+  if (g->chunk > 0 && g->n_chunks <= 0) return fail(EVA_ERR_INVALID, "geometry yields no chunks");
+  return EVA_OK;
+}
+
+int make_view(const EvaHeadsView* in, const char* name, eva::View* v) {
+  if (!in || !in->ptr) return fail(EVA_ERR_INVALID, "%s view is NULL", name);
+  if ((reinterpret_cast<uintptr_t>(in->ptr) & 15u) != 0) return fail(EVA_ERR_INVALID, "%s pointer not 16-byte aligned", name);
+  if (in->stride_b % 8 || in->stride_n % 8 || in->stride_h % 8)
+    return fail(EVA_ERR_INVALID, "%s strides must be multiples of 8 elements", name);
+  v->ptr = in->ptr; v->sb = in->stride_b; v->sn = in->stride_n; v->sh = in->stride_h;
+  return EVA_OK;
+}
+
+int check_ada(const EvaAdaptive* a) {
+  if (!a) return fail(EVA_ERR_INVALID, "adaptive parameters are NULL");
+  if (!a->w_k || !a->b_k) return fail(EVA_ERR_INVALID, "adaptive_mu_k Linear is required (eva.py:79-98)");
+  if (a->w_q && !a->b_q) return fail(EVA_ERR_INVALID, "adaptive_mu_q bias missing");
+  if ((a->ln_gain_k && !a->ln_bias_k) || (a->ln_gain_q && !a->ln_bias_q)) return fail(EVA_ERR_INVALID, "LayerNorm gain without bias");
+  return EVA_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+int eva_sm100_abi_version(void) { return EVA_SM100_ABI_VERSION; }
+
+const char* eva_last_error(void) { return g_err; }
+
+int eva_num_chunks(const EvaGeometry* gin) {
+  eva::Geo g{};
+  const int rc = make_geo(gin, &g);
+  return rc != EVA_OK ? rc : g.n_chunks;
+}
+
+int eva_chunk_stats(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                    const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
+                    float* k_bar, float* beta, void* stream) {
+  eva::Geo g{};
+  eva::View vq, vk, vv;
+  int rc;
+  if ((rc = make_geo(gin, &g)) || (rc = make_view(q, "q", &vq)) || (rc = make_view(k, "k", &vk)) ||
+      (rc = make_view(v, "v", &vv)) || (rc = check_ada(ada)))
+    return rc;
+  if (g.n_chunks == 0) return fail(EVA_ERR_INVALID, "chunk == 0: nothing to compute");
+  if (!k_bar || !beta) return fail(EVA_ERR_INVALID, "k_bar / beta output is NULL");
+  const cudaError_t e = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, k_bar, beta,
+                                                reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_chunk_stats");
+}
+
+int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                         const uint8_t* pad_mask, const float* k_bar, const float* beta,
+                         const float* bias, int64_t bias_stride_h, void* out, void* stream) {
+  eva::Geo g{};
+  eva::View vq, vk, vv;
+  int rc;
+  if ((rc = make_geo(gin, &g)) || (rc = make_view(q, "q", &vq)) || (rc = make_view(k, "k", &vk)) ||
+      (rc = make_view(v, "v", &vv)))
+    return rc;
+  if (g.n_chunks > 0 && (!k_bar || !beta)) return fail(EVA_ERR_INVALID, "k_bar / beta required when chunk > 0");
+  if (!out) return fail(EVA_ERR_INVALID, "out is NULL");
+  if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
+    return fail(EVA_ERR_INVALID, "bias_stride_h must be 0 or L*J = %d", g.L * g.J);
+  const cudaError_t e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias,
+                                                bias_stride_h, out, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_window_attention");
+}
+
+int eva_forward_workspace_bytes(const EvaGeometry* gin, size_t* bytes) {
+  eva::Geo g{};
+  const int rc = make_geo(gin, &g);
+  if (rc) return rc;
+  if (!bytes) return fail(EVA_ERR_INVALID, "bytes is NULL");
+  const size_t stats = align256((size_t)g.B * g.H * g.n_chunks * g.D * sizeof(float));
+  *bytes = 2 * stats + align256(eva::fused_workspace_bytes(g));
+  return EVA_OK;
+}
+
+int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
+                const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,
+                int32_t* path_taken, void* stream) {
+  eva::Geo g{};
+  eva::View vq, vk, vv;
+  int rc;
+  if ((rc = make_geo(gin, &g)) || (rc = make_view(q, "q", &vq)) || (rc = make_view(k, "k", &vk)) ||
+      (rc = make_view(v, "v", &vv)) || (rc = check_ada(ada)))
+    return rc;
+  if (g.n_chunks == 0) return fail(EVA_ERR_INVALID, "eva_forward needs chunk > 0 (use eva_window_attention)");
+  if (!out || !workspace) return fail(EVA_ERR_INVALID, "out / workspace is NULL");
+  if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
+    return fail(EVA_ERR_INVALID, "bias_stride_h must be 0 or L*J = %d", g.L * g.J);
+  size_t need = 0;
+  eva_forward_workspace_bytes(gin, &need);
+  if (workspace_bytes < need) return fail(EVA_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(EVA_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t stats = align256((size_t)g.B * g.H * g.n_chunks * g.D * sizeof(float));
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* k_bar = reinterpret_cast<float*>(ws);
+  float* beta = reinterpret_cast<float*>(ws + stats);
+  if (eva::fused_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, bias, bias_stride_h)) {
+    const char* msg = "";
+    const cudaError_t e = eva::launch_fused(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out,
+                                            ws + 2 * stats, st, &msg);
+    if (path_taken) *path_taken = 1;
+    if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(fused): %s: %s", msg, cudaGetErrorString(e));
+    return EVA_OK;
+  }
+  if (path_taken) *path_taken = 0;
+  cudaError_t e = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, k_bar, beta, st);
+  if (e != cudaSuccess) return cuda_fail(e, "eva_forward(chunk_stats)");
+  e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out, st);
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_forward(window_attention)");
+}
+
+// ---------------------------------------------------------------------------------------------
+static int make_lara_geo(const LaraGeometry* in, eva::LaraGeo* g) {
+  if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");
+  if (in->batch <= 0 || in->heads <= 0 || in->tokens <= 0 || in->landmarks <= 0) return fail(EVA_ERR_INVALID, "batch/heads/tokens/landmarks must be positive");
+  if (in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
+    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (32, 64, 128)", in->head_dim);
+  if (in->io_dtype < EVA_F32 || in->io_dtype > EVA_BF16) return fail(EVA_ERR_INVALID, "unknown io_dtype %d", in->io_dtype);
+  if (in->mis_type < LARA_MIS_OPT || in->mis_type > LARA_MIS_BIASED) return fail(EVA_ERR_INVALID, "unknown mis_type");
+  if (in->sample_mode < LARA_SAMPLE_SINGLE || in->sample_mode > LARA_SAMPLE_MULTI) return fail(EVA_ERR_INVALID, "unknown sample_mode");
+  g->B = in->batch; g->H = in->heads; g->N = in->tokens; g->D = in->head_dim;
+  g->dims = in->dims; g->gh = in->grid_h; g->gw = in->grid_w;
+  g->C = in->landmarks;
+  g->side = 0;
+  if (in->dims == 2) {
+    if (in->grid_h * in->grid_w != in->tokens) return fail(EVA_ERR_INVALID, "grid does not cover tokens");
+    int side = 1;
+    while ((side + 1) * (side + 1) <= in->landmarks) ++side;
+    if (side * side != in->landmarks) return fail(EVA_ERR_INVALID, "2-D landmarks must be a square number");
+    if (side > in->grid_h || side > in->grid_w) return fail(EVA_ERR_INVALID, "more landmarks per side than grid cells");
+    if (in->per_token_proj) return fail(EVA_ERR_INVALID, "'adaptive-1d' proposals are 1-D only");
+    g->side = side;
+  } else if (in->dims == 1) {
+    if (in->landmarks > in->tokens) return fail(EVA_ERR_INVALID, "1-D landmarks must be <= tokens (pass min(num_landmarks, tokens))");
+    if (in->mixed) return fail(EVA_ERR_INVALID, "landmark mixing is 2-D only (lara.py:157)");
+  } else {
+    return fail(EVA_ERR_INVALID, "dims must be 1 or 2");
+  }
+  g->S = in->sample_mode == LARA_SAMPLE_SINGLE ? g->C : 2 * g->C;
+  g->per_token_proj = in->per_token_proj ? 1 : 0;
+  g->mixed = in->mixed; g->mis_type = in->mis_type; g->sample_mode = in->sample_mode;
+  g->zero_padded = in->zero_padded ? 1 : 0;
+  g->alpha_coeff = in->alpha_coeff;
+  return EVA_OK;
+}
+
+int lara_forward_workspace_bytes(const LaraGeometry* gin, size_t* bytes) {
+  eva::LaraGeo g{};
+  const int rc = make_lara_geo(gin, &g);
+  if (rc) return rc;
+  if (!bytes) return fail(EVA_ERR_INVALID, "bytes is NULL");
+  *bytes = eva::lara_workspace_bytes(g);
+  return EVA_OK;
+}
+
+int lara_forward(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                 const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
+                 void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  eva::LaraGeo g{};
+  eva::View vq, vk, vv;
+  int rc;
+  if ((rc = make_lara_geo(gin, &g)) || (rc = make_view(q, "q", &vq)) || (rc = make_view(k, "k", &vk)) ||
+      (rc = make_view(v, "v", &vv)))
+    return rc;
+  if (!proj) return fail(EVA_ERR_INVALID, "proj is NULL (pass a zeroed struct for 'no-param-pool')");
+  if (proj->w_q && (!proj->w_k || !proj->b_q || !proj->b_k || !proj->ln_gain_q || !proj->ln_gain_k || !proj->ln_bias_q || !proj->ln_bias_k))
+    return fail(EVA_ERR_INVALID, "q_bar_gen / k_bar_gen need Linear and LayerNorm parameters for both sides");
+  if (g.per_token_proj && !proj->w_q) return fail(EVA_ERR_INVALID, "'adaptive-1d' needs projection parameters");
+  if (!noise && g.sample_mode != LARA_SAMPLE_SINGLE) return fail(EVA_ERR_INVALID, "sample_mode without noise");
+  if (!out || !workspace) return fail(EVA_ERR_INVALID, "out / workspace is NULL");
+  if (workspace_bytes < eva::lara_workspace_bytes(g)) return fail(EVA_ERR_INVALID, "workspace too small");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(EVA_ERR_INVALID, "workspace must be 256-byte aligned");
+  const cudaError_t e = eva::launch_lara(g, gin->io_dtype, vq, vk, vv, pad_mask, *proj, noise, out, workspace,
+                                         reinterpret_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(EVA_ERR_UNSUPPORTED, "landmarks x head_dim too large for one CTA's shared memory");
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "lara_forward");
+}
+
+}  // extern "C"

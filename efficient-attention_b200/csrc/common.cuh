@@ -1,0 +1,96 @@
+// Shared device helpers for libeva_sm100 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eva_sm100.h"
+
+namespace eva {
+
+constexpr float kMaskVal = -5.0e4f;  // eva.py:139
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kNegInf = -INFINITY;
+
+// ---- io-type helpers: everything is computed in fp32, T is only the HBM format ----------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8 consecutive elements (16-byte aligned for 2-byte types, 32-byte span for float)
+template <typename T> __device__ __forceinline__ void load8(const T* p, float* o);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* o) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float* o) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* o) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// exp(x) for x <= 0 (softmax terms); exp(-inf) = 0
+__device__ __forceinline__ float exp_nonpos(float x) { return exp2f(x * kLog2e); }
+
+// ---- strided q/k/v view ------------------------------------------------------------------------
+struct View {
+  const void* ptr;
+  long long sb, sn, sh;
+  template <typename T> __device__ __forceinline__ const T* row(int b, int n, int h) const {
+    return reinterpret_cast<const T*>(ptr) + (long long)b * sb + (long long)n * sn + (long long)h * sh;
+  }
+};
+
+// ---- window / chunk geometry -------------------------------------------------------------------
+struct Geo {
+  int B, H, N, D;
+  int dims, gh, gw;
+  int window, ext, left_only;
+  int chunk, chunk_ext;
+  int causal, mask_queries;
+  int n_windows, L, J;    // queries per window, local keys per window
+  int n_chunks, Jc;       // chunk keys, tokens per chunk (incl. halo)
+  float mask_fill;        // -5e4, or -inf for the dense softmax baseline
+};
+
+// token id of slot `slot` of group `grp` (edge `size`, halo `ext`), -1 when off the sequence.
+// 2-D: groups row-major over the grid, slots row-major inside the (size+2ext)^2 box
+// (attn_utils.py:172-210).  1-D: slot 0 is `ext` tokens left of the group start (attn_utils.py:155-166).
+__device__ __forceinline__ int group_token(const Geo& g, int grp, int slot, int size, int ext) {
+  if (g.dims == 2) {
+    const int t = size + 2 * ext;
+    const int ngx = g.gw / size;
+    const int y = (grp / ngx) * size - ext + slot / t;
+    const int x = (grp % ngx) * size - ext + slot % t;
+    return (y >= 0 && y < g.gh && x >= 0 && x < g.gw) ? y * g.gw + x : -1;
+  }
+  const int p = grp * size - ext + slot;
+  return (p >= 0 && p < g.N) ? p : -1;
+}
+
+}  // namespace eva

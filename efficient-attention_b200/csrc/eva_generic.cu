@@ -1,0 +1,363 @@
+// Generic (any geometry) EVA kernels: fp32 math on CUDA cores, T only the HBM format.
+// These cover every configuration the reference accepts (1-D / 2-D, halos, padding masks, causal,
+// chunk-less local / dense attention, head_dim 32/64/128); the fused tcgen05/TMA kernel in
+// eva_fused_sm100.cu takes over for the geometries it is specialised for.
+//
+//   chunk_stats_kernel    eva.py:155-196, causal_eva.py:676-719
+//   window_attn_kernel    eva.py:200-227, causal_eva.py:722-783, local_attention.py:134-182,
+//                         abstract_attention.py:115-133
+#include "common.cuh"
+#include "launch.h"
+
+namespace eva {
+
+// ------------------------------------------------------------------------------------------------
+// Stage A: one warp per (batch, head, chunk).  Lane l owns features l, l+32, ...
+// ------------------------------------------------------------------------------------------------
+template <int DPL>
+__device__ __forceinline__ void warp_linear(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                            const float (&x)[DPL], float (&y)[DPL], int lane) {
+  constexpr int D = 32 * DPL;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) y[i] = bias ? __ldg(bias + lane + 32 * i) : 0.f;
+#pragma unroll
+  for (int ii = 0; ii < DPL; ++ii) {
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float m = __shfl_sync(0xffffffffu, x[ii], jj);
+      const float* wrow = Wt + (jj + 32 * ii) * D + lane;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) y[i] = fmaf(wrow[32 * i], m, y[i]);
+    }
+  }
+}
+
+template <int DPL>
+__device__ __forceinline__ void warp_layer_norm(float (&y)[DPL], const float* __restrict__ gain,
+                                                const float* __restrict__ bias, float eps, int lane) {
+  constexpr int D = 32 * DPL;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) s += y[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) { const float c = y[i] - mean; v = fmaf(c, c, v); }
+  const float inv = 1.0f / sqrtf(warp_sum(v) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) y[i] = (y[i] - mean) * inv * __ldg(gain + lane + 32 * i) + __ldg(bias + lane + 32 * i);
+}
+
+template <typename T, int DPL>
+__global__ void __launch_bounds__(256)
+chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                   const EvaAdaptive ada, const float* __restrict__ noise, float* __restrict__ kbar_out,
+                   float* __restrict__ beta_out) {
+  constexpr int D = 32 * DPL;
+  extern __shared__ float sm[];
+  float* WtK = sm;
+  float* WtQ = sm + D * D;
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int e = idx / D, i = idx % D;  // W[e][i] -> Wt[i][e]
+    WtK[i * D + e] = __ldg(ada.w_k + idx);
+    if (ada.w_q) WtQ[i * D + e] = __ldg(ada.w_q + idx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float scale = rsqrtf((float)D);
+  const float inv_cnt = 1.0f / (float)g.Jc;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  for (long long wg = (long long)blockIdx.x * wpb + warp; wg < total; wg += (long long)gridDim.x * wpb) {
+    const int c = (int)(wg % g.n_chunks);
+    const int h = (int)((wg / g.n_chunks) % g.H);
+    const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+    // pass 1: chunk means; padded / off-sequence slots count as zeros in the denominator (eva.py:174-180)
+    float sq[DPL], sk[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) sq[i] = sk[i] = 0.f;
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;
+      const T* qr = q.row<T>(b, tok, h);
+      const T* kr = k.row<T>(b, tok, h);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) { sq[i] += to_f32(qr[lane + 32 * i]); sk[i] += to_f32(kr[lane + 32 * i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { sq[i] *= inv_cnt; sk[i] *= inv_cnt; }
+    float kb[DPL], om[DPL];
+    warp_linear<DPL>(WtK, ada.b_k, sk, kb, lane);
+    if (ada.ln_gain_k) warp_layer_norm<DPL>(kb, ada.ln_gain_k, ada.ln_bias_k, ada.ln_eps, lane);
+    if (ada.w_q) {
+      float qb[DPL];
+      warp_linear<DPL>(WtQ, ada.b_q, sq, qb, lane);
+      if (ada.ln_gain_q) warp_layer_norm<DPL>(qb, ada.ln_gain_q, ada.ln_bias_q, ada.ln_eps, lane);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) om[i] = ada.mu_coeff * (qb[i] + kb[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) om[i] = 0.f;
+    }
+    const long long obase = wg * D;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+      if (noise) om[i] += __ldg(noise + obase + lane + 32 * i);
+      kbar_out[obase + lane + 32 * i] = kb[i];
+    }
+    // pass 2: beta = softmax_j(prm(k_j, omega)) . v_j, online over the chunk's slots (eva.py:192-196)
+    float m = kNegInf, l = 0.f, acc[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      const bool dead = tok < 0 || (mask && mask[(long long)b * g.N + tok]);
+      float lg = kMaskVal, vv[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) vv[i] = 0.f;
+      if (!dead) {
+        const T* kr = k.row<T>(b, tok, h);
+        const T* vr = v.row<T>(b, tok, h);
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+          const float kk = to_f32(kr[lane + 32 * i]);
+          part = fmaf(kk, om[i] - 0.5f * kk, part);
+          vv[i] = to_f32(vr[lane + 32 * i]);
+        }
+        lg = scale * warp_sum(part);
+      }
+      const float mn = fmaxf(m, lg);
+      const float corr = exp_nonpos(m - mn), p = exp_nonpos(lg - mn);
+      l = fmaf(l, corr, p);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc[i] = fmaf(acc[i], corr, p * vv[i]);
+      m = mn;
+    }
+    const float inv_l = 1.0f / l;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) beta_out[obase + lane + 32 * i] = acc[i] * inv_l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage B: CTA = (batch*head, window, block of 16 query rows); keys = local window slots followed by
+// the chunk keys (k_bar / beta); key tiles of 32 staged in smem, online softmax per query row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRows = 16;   // query rows per CTA (4 per warp)
+constexpr int kRpw = 4;
+constexpr int kKt = 32;     // keys per tile
+
+template <typename T, int DPL>
+__global__ void __launch_bounds__(128)
+window_attn_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                   const float* __restrict__ kbar, const float* __restrict__ beta,
+                   const float* __restrict__ bias, const long long bias_sh, T* __restrict__ out) {
+  constexpr int D = 32 * DPL;
+  constexpr int DP = D + 1;
+  extern __shared__ float sm[];
+  float* Qs = sm;                       // [kRows][D], pre-scaled
+  float* Ks = Qs + kRows * D;           // [kKt][DP]
+  float* Vs = Ks + kKt * DP;            // [kKt][DP]
+  float* Ps = Vs + kKt * DP;            // [4][kRpw][kKt]
+  int* kflag = reinterpret_cast<int*>(Ps + 4 * kRpw * kKt);  // [kKt] 0 live, 1 masked, 2 absent
+  int* qtok = kflag + kKt;              // [kRows] token id or -1
+  int* qpad = qtok + kRows;             // [kRows]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb = blockIdx.x, win = blockIdx.y;
+  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
+  const float scale = rsqrtf((float)D);
+  const int n_keys = g.J + g.n_chunks;
+
+  if (tid < kRows) {
+    const int li = rb * kRows + tid;
+    const int tok = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+    qtok[tid] = tok;
+    qpad[tid] = (tok >= 0 && mask) ? (int)mask[(long long)b * g.N + tok] : 0;
+  }
+  for (int idx = tid; idx < kRows * (D / 8); idx += blockDim.x) {
+    const int r = idx / (D / 8), part = idx % (D / 8);
+    const int li = rb * kRows + r;
+    const int tok = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+    float f[8];
+    if (tok >= 0) load8<T>(q.row<T>(b, tok, h) + part * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Qs[r * D + part * 8 + i] = tok >= 0 ? f[i] * scale : 0.f;
+  }
+
+  float m[kRpw], l[kRpw], o[kRpw][DPL];
+#pragma unroll
+  for (int r = 0; r < kRpw; ++r) {
+    m[r] = kNegInf; l[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) o[r][i] = 0.f;
+  }
+
+  for (int kt0 = 0; kt0 < n_keys; kt0 += kKt) {
+    __syncthreads();  // previous tile fully consumed (and Qs/qtok visible on the first pass)
+    for (int idx = tid; idx < kKt * (D / 8); idx += blockDim.x) {
+      const int j = idx / (D / 8), part = idx % (D / 8);
+      const int gj = kt0 + j;
+      float fk[8], fv[8];
+      int flag = 0;
+      bool have = false;
+      if (gj < g.J) {
+        const int tok = group_token(g, win, gj, g.window, g.ext);
+        if (tok >= 0) {
+          load8<T>(k.row<T>(b, tok, h) + part * 8, fk);
+          load8<T>(v.row<T>(b, tok, h) + part * 8, fv);
+          have = true;
+          flag = (mask && mask[(long long)b * g.N + tok]) ? 1 : 0;
+        } else {
+          flag = 1;  // halo outside the sequence: zero key/value, masked logit (pad_val=1)
+        }
+      } else if (gj < n_keys) {
+        const long long base = (((long long)b * g.H + h) * g.n_chunks + (gj - g.J)) * D + part * 8;
+        load8<float>(kbar + base, fk);
+        load8<float>(beta + base, fv);
+        have = true;
+      } else {
+        flag = 2;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        Ks[j * DP + part * 8 + i] = have ? fk[i] : 0.f;
+        Vs[j * DP + part * 8 + i] = have ? fv[i] : 0.f;
+      }
+      if (part == 0) kflag[j] = flag;
+    }
+    __syncthreads();
+
+    // logits: lane = key, 4 rows of this warp share each K read
+    float s[kRpw];
+#pragma unroll
+    for (int r = 0; r < kRpw; ++r) s[r] = 0.f;
+    const float* krow = Ks + lane * DP;
+    const float* qrow = Qs + (warp * kRpw) * D;
+#pragma unroll 8
+    for (int e = 0; e < D; ++e) {
+      const float kk = krow[e];
+#pragma unroll
+      for (int r = 0; r < kRpw; ++r) s[r] = fmaf(qrow[r * D + e], kk, s[r]);
+    }
+    const int gj = kt0 + lane;
+    const int flag = kflag[lane];
+#pragma unroll
+    for (int r = 0; r < kRpw; ++r) {
+      const int row = warp * kRpw + r;
+      const int li = rb * kRows + row;
+      const int tq = qtok[row];
+      if (tq < 0) continue;  // warp-uniform: row does not exist
+      float sv = s[r];
+      if (flag == 2) {
+        sv = kNegInf;
+      } else if (gj < g.J) {
+        if (bias) sv += __ldg(bias + (long long)h * bias_sh + (long long)li * g.J + gj);
+        const bool dead = flag == 1 || (g.mask_queries && qpad[row]);
+        if (dead) sv = g.mask_fill;
+        if (g.causal && gj > li + g.ext) sv = kMaskVal;
+      } else {
+        if (g.causal && (gj - g.J) >= tq / g.chunk) sv = kMaskVal;
+      }
+      const float mt = warp_max(sv);
+      const float mn = fmaxf(m[r], mt);
+      float corr = 1.f, p = 0.f;
+      if (mn != kNegInf) { corr = exp_nonpos(m[r] - mn); p = exp_nonpos(sv - mn); }
+      l[r] = fmaf(l[r], corr, warp_sum(p));
+      m[r] = mn;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[r][i] *= corr;
+      Ps[(warp * kRpw + r) * kKt + lane] = p;
+    }
+    __syncwarp();
+    // PV: lane owns features lane + 32 i
+    const float* prow = Ps + (warp * kRpw) * kKt;
+#pragma unroll 4
+    for (int j = 0; j < kKt; ++j) {
+      float vv[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) vv[i] = Vs[j * DP + lane + 32 * i];
+#pragma unroll
+      for (int r = 0; r < kRpw; ++r) {
+        const float p = prow[r * kKt + j];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) o[r][i] = fmaf(p, vv[i], o[r][i]);
+      }
+    }
+    __syncwarp();
+  }
+
+#pragma unroll
+  for (int r = 0; r < kRpw; ++r) {
+    const int tq = qtok[warp * kRpw + r];
+    if (tq < 0) continue;
+    const float inv = 1.0f / l[r];
+    T* orow = out + ((long long)b * g.N + tq) * ((long long)g.H * D) + (long long)h * D;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) orow[lane + 32 * i] = from_f32<T>(o[r][i] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DPL>
+static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View& k, const View& v,
+                                        const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
+                                        float* kbar, float* beta, cudaStream_t st) {
+  constexpr int D = 32 * DPL;
+  const size_t smem = 2 * (size_t)D * D * sizeof(float);
+  auto kern = chunk_stats_kernel<T, DPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  const int wpb = 8;
+  long long blocks = (total + wpb - 1) / wpb;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;  // grid-stride beyond 16 CTAs per SM
+  kern<<<(unsigned)blocks, wpb * 32, smem, st>>>(g, q, k, v, mask, ada, noise, kbar, beta);
+  return cudaGetLastError();
+}
+
+template <typename T, int DPL>
+static cudaError_t launch_window_attn_t(const Geo& g, const View& q, const View& k, const View& v,
+                                        const uint8_t* mask, const float* kbar, const float* beta,
+                                        const float* bias, long long bias_sh, void* out, cudaStream_t st) {
+  constexpr int D = 32 * DPL;
+  const size_t smem = (size_t)(kRows * D + 2 * kKt * (D + 1) + 4 * kRpw * kKt) * sizeof(float) +
+                      (size_t)(kKt + 2 * kRows) * sizeof(int);
+  auto kern = window_attn_kernel<T, DPL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((g.L + kRows - 1) / kRows, g.n_windows, g.B * g.H);
+  kern<<<grid, 128, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<T*>(out));
+  return cudaGetLastError();
+}
+
+#define EVA_DISPATCH(FN, ...)                                                             \
+  switch (io_dtype * 8 + g.D / 32) {                                                      \
+    case EVA_F32 * 8 + 1: return FN<float, 1>(__VA_ARGS__);                               \
+    case EVA_F32 * 8 + 2: return FN<float, 2>(__VA_ARGS__);                               \
+    case EVA_F32 * 8 + 4: return FN<float, 4>(__VA_ARGS__);                               \
+    case EVA_F16 * 8 + 1: return FN<__half, 1>(__VA_ARGS__);                              \
+    case EVA_F16 * 8 + 2: return FN<__half, 2>(__VA_ARGS__);                              \
+    case EVA_F16 * 8 + 4: return FN<__half, 4>(__VA_ARGS__);                              \
+    case EVA_BF16 * 8 + 1: return FN<__nv_bfloat16, 1>(__VA_ARGS__);                      \
+    case EVA_BF16 * 8 + 2: return FN<__nv_bfloat16, 2>(__VA_ARGS__);                      \
+    case EVA_BF16 * 8 + 4: return FN<__nv_bfloat16, 4>(__VA_ARGS__);                      \
+    default: return cudaErrorInvalidValue;                                                \
+  }
+
+cudaError_t launch_chunk_stats(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                               const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
+                               float* kbar, float* beta, cudaStream_t st) {
+  EVA_DISPATCH(launch_chunk_stats_t, g, q, k, v, mask, ada, noise, kbar, beta, st)
+}
+
+cudaError_t launch_window_attn(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                               const uint8_t* mask, const float* kbar, const float* beta,
+                               const float* bias, long long bias_sh, void* out, cudaStream_t st) {
+  if (g.D / 32 != 1 && g.D / 32 != 2 && g.D / 32 != 4) return cudaErrorInvalidValue;
+  EVA_DISPATCH(launch_window_attn_t, g, q, k, v, mask, kbar, beta, bias, bias_sh, out, st)
+}
+
+}  // namespace eva

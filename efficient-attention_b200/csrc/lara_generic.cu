@@ -1,0 +1,548 @@
+// LARA (LinearRA) forward core, generic CUDA-core implementation: fp32 math, T = HBM format.
+//
+//   lara_landmark_kernel   lara.py:84-175 + 182-198 + the [S,C] proposal statistics of :221-236
+//   lara_stats_kernel      lara.py:202-211 (kv statistics, lse of phi(k)) and :222-223 (lse of t_nc)
+//   lara_out_kernel        lara.py:201, 214-246 (phi(q), MIS weights, self-normalised combine)
+//
+// Workspace per (batch, head), float32:
+//   qbar[C,D] mu[C,D] omega[S,D] kv[S,D] lp[S] bh[S] lse_k[S] lse_t[C]
+#include <math.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace eva {
+
+struct LaraWs {
+  float *qbar, *mu, *omega, *kv, *lp, *bh, *lse_k, *lse_t;
+};
+
+__host__ __device__ inline size_t lara_ws_floats_per_bh(int C, int S, int D) {
+  return (size_t)(2 * C + 2 * S) * D + 3 * (size_t)S + C;
+}
+__host__ __device__ inline LaraWs lara_ws_at(float* base, long long bh, int C, int S, int D) {
+  float* p = base + bh * (long long)lara_ws_floats_per_bh(C, S, D);
+  LaraWs w;
+  w.qbar = p; p += (size_t)C * D;
+  w.mu = p; p += (size_t)C * D;
+  w.omega = p; p += (size_t)S * D;
+  w.kv = p; p += (size_t)S * D;
+  w.lp = p; p += S;
+  w.bh = p; p += S;
+  w.lse_k = p; p += S;
+  w.lse_t = p;
+  return w;
+}
+
+__device__ __forceinline__ void bin_of(int i, int n_in, int n_out, int& lo, int& hi) {
+  // AdaptiveAvgPool bins: [floor(i*n_in/n_out), ceil((i+1)*n_in/n_out))
+  lo = (i * n_in) / n_out;
+  hi = ((i + 1) * n_in + n_out - 1) / n_out;
+}
+
+template <int DPL>
+__device__ __forceinline__ void warp_linear_ln(const float* Wt, const EvaAdaptive& p, bool q_side,
+                                               const float (&x)[DPL], float (&y)[DPL], int lane) {
+  constexpr int D = 32 * DPL;
+  const float* bias = q_side ? p.b_q : p.b_k;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) y[i] = bias ? __ldg(bias + lane + 32 * i) : 0.f;
+#pragma unroll
+  for (int ii = 0; ii < DPL; ++ii) {
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
+      const float m = __shfl_sync(0xffffffffu, x[ii], jj);
+      const float* wrow = Wt + (jj + 32 * ii) * D + lane;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) y[i] = fmaf(wrow[32 * i], m, y[i]);
+    }
+  }
+  const float* gain = q_side ? p.ln_gain_q : p.ln_gain_k;
+  const float* lb = q_side ? p.ln_bias_q : p.ln_bias_k;
+  if (gain) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) s += y[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { const float c = y[i] - mean; v = fmaf(c, c, v); }
+    const float inv = 1.0f / sqrtf(warp_sum(v) * (1.0f / D) + p.ln_eps);
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) y[i] = (y[i] - mean) * inv * __ldg(gain + lane + 32 * i) + __ldg(lb + lane + 32 * i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1: landmarks + proposal statistics.  One CTA per (batch, head).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DPL>
+__global__ void __launch_bounds__(256)
+lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                     const EvaAdaptive proj, const float* __restrict__ noise, float* __restrict__ ws_base) {
+  constexpr int D = 32 * DPL, DP = D + 1;
+  extern __shared__ float sm[];
+  const int C = g.C, S = g.S;
+  float* qb = sm;                  // [C][DP]  q landmarks, later mu
+  float* kb = qb + C * DP;         // [C][DP]
+  float* vb = kb + C * DP;         // [C][DP]  (vmixed)
+  float* kb2 = vb + C * DP;        // [C][DP]  mixed k landmarks
+  float* om = kb2 + C * DP;        // [S][DP]
+  float* Wt = om + S * DP;         // [D][D]
+  float* rowbuf = Wt + D * D;      // [8][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / g.H, h = blockIdx.x % g.H;
+  const float scale = rsqrtf((float)D);
+  const LaraWs ws = lara_ws_at(ws_base, blockIdx.x, C, S, D);
+  const bool has_proj = proj.w_q != nullptr;
+
+  for (int side = 0; side < 3; ++side) {  // 0: q, 1: k, 2: v (only for '-vmixed')
+    if (side == 2 && g.mixed != 2) break;
+    const bool per_tok = g.per_token_proj && side < 2;
+    if (has_proj && side < 2) {
+      __syncthreads();
+      const float* W = side == 0 ? proj.w_q : proj.w_k;
+      for (int idx = tid; idx < D * D; idx += blockDim.x) Wt[(idx % D) * D + idx / D] = __ldg(W + idx);
+      __syncthreads();
+    }
+    const View& src = side == 0 ? q : (side == 1 ? k : v);
+    float* dst = side == 0 ? qb : (side == 1 ? kb : vb);
+    for (int c = warp; c < C; c += 8) {
+      float acc[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+      int y0 = 0, y1 = 1, x0, x1;
+      if (g.dims == 2) {
+        bin_of(c / g.side, g.gh, g.side, y0, y1);
+        bin_of(c % g.side, g.gw, g.side, x0, x1);
+      } else if (g.N <= C) {
+        x0 = c; x1 = c + 1;
+      } else if (g.N % C == 0) {
+        x0 = c * (g.N / C); x1 = x0 + g.N / C;
+      } else {
+        const int seg = g.N / C, n_short = (seg + 1) * C - g.N;  // lara.py:111-124
+        if (c < n_short) { x0 = c * seg; x1 = x0 + seg; }
+        else { x0 = n_short * seg + (c - n_short) * (seg + 1); x1 = x0 + seg + 1; }
+      }
+      const int width = g.dims == 2 ? g.gw : 0;
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          const int tok = y * width + x;
+          float xv[DPL];
+          const bool zero = g.zero_padded && mask && mask[(long long)b * g.N + tok];
+          const T* r = src.row<T>(b, tok, h);
+#pragma unroll
+          for (int i = 0; i < DPL; ++i) xv[i] = zero ? 0.f : to_f32(r[lane + 32 * i]);
+          if (per_tok) {
+            float yv[DPL];
+            warp_linear_ln<DPL>(Wt, proj, side == 0, xv, yv, lane);
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) acc[i] += yv[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) acc[i] += xv[i];
+          }
+        }
+      const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+      float mean[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) mean[i] = acc[i] * inv;
+      if (has_proj && !g.per_token_proj && side < 2 && g.dims == 2) {
+        float yv[DPL];
+        warp_linear_ln<DPL>(Wt, proj, side == 0, mean, yv, lane);
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) mean[i] = yv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) dst[c * DP + lane + 32 * i] = mean[i];
+    }
+  }
+  __syncthreads();
+
+  // landmark mixing: k_bar <- softmax(scale k_bar k_bar^T [+ log|v_bar|]) k_bar  (lara.py:157-174)
+  float* kfin = kb;
+  if (g.mixed) {
+    float* pr = rowbuf + warp * C;
+    for (int p = warp; p < C; p += 8) {
+      float mx = kNegInf;
+      for (int c = lane; c < C; c += 32) {
+        float s = 0.f;
+        for (int e = 0; e < D; ++e) s = fmaf(kb[p * DP + e], kb[c * DP + e], s);
+        s *= scale;
+        if (g.mixed == 2) {
+          float n2 = 0.f;
+          for (int e = 0; e < D; ++e) n2 = fmaf(vb[c * DP + e], vb[c * DP + e], n2);
+          s += logf(sqrtf(n2) + 1e-4f);
+        }
+        pr[c] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int c = lane; c < C; c += 32) { const float e_ = exp_nonpos(pr[c] - mx); pr[c] = e_; sum += e_; }
+      sum = warp_sum(sum);
+      __syncwarp();
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) a = fmaf(pr[c], kb[c * DP + lane + 32 * i], a);
+        kb2[p * DP + lane + 32 * i] = a * inv;
+      }
+      __syncwarp();
+    }
+    kfin = kb2;
+    __syncthreads();
+  }
+
+  // q_bar -> workspace; mu = q_bar + k_bar (lara.py:182); omega = proposal samples (lara.py:188-198)
+  for (int idx = tid; idx < C * D; idx += blockDim.x) {
+    const int c = idx / D, e = idx % D;
+    const float qv = qb[c * DP + e];
+    const float m = qv + kfin[c * DP + e];
+    ws.qbar[idx] = qv;
+    ws.mu[idx] = m;
+    qb[c * DP + e] = m;  // qb now holds mu
+  }
+  __syncthreads();
+  const float* nz = noise ? noise + (long long)blockIdx.x * (g.sample_mode == LARA_SAMPLE_ANTITHETIC ? C : S) * D : nullptr;
+  for (int idx = tid; idx < S * D; idx += blockDim.x) {
+    const int s = idx / D, e = idx % D;
+    float o = qb[(s % C) * DP + e];
+    if (nz) {
+      if (g.sample_mode == LARA_SAMPLE_ANTITHETIC) o += (s < C ? 1.f : -1.f) * __ldg(nz + (s % C) * D + e);
+      else o += __ldg(nz + idx);
+    }
+    om[s * DP + e] = o;
+    ws.omega[idx] = o;
+  }
+  __syncthreads();
+
+  // proposal statistics over Lm[s][c] = prm(mu_c, omega_s)   (lara.py:215,228-236)
+  const float log_rep = logf((float)(S / C));
+  float* pr = rowbuf + warp * C;
+  for (int s = warp; s < S; s += 8) {
+    float mx = kNegInf;
+    for (int c = lane; c < C; c += 32) {
+      float dot = 0.f, n2 = 0.f;
+      for (int e = 0; e < D; ++e) {
+        const float m = qb[c * DP + e];
+        dot = fmaf(om[s * DP + e], m, dot);
+        n2 = fmaf(m, m, n2);
+      }
+      const float lv = scale * (dot - 0.5f * n2);
+      pr[c] = lv;
+      mx = fmaxf(mx, lv);
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += exp_nonpos(pr[c] - mx);
+    const float lse = mx + logf(warp_sum(sum));
+    if (lane == 0) {
+      if (g.mis_type == LARA_MIS_OPT) {
+        const float lp = pr[s % C];
+        ws.lp[s] = lp;
+        ws.bh[s] = expf(lp - (lse + log_rep));
+      } else {
+        ws.lp[s] = lse;
+        ws.bh[s] = 0.f;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L2: rows x all tokens with online softmax.  blockIdx.x < kv_blocks: rows = omega samples, keys = k,
+// values = v  -> kv[s], lse_k[s].  Otherwise (mis-opt): rows = q_bar landmarks, keys = q -> lse_t[c].
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DPL>
+__global__ void __launch_bounds__(128)
+lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                  float* __restrict__ ws_base, const int kv_blocks) {
+  constexpr int D = 32 * DPL, DP = D + 1;
+  constexpr int ROWS = 16, RPW = 4, KT = 32;
+  extern __shared__ float sm[];
+  float* Rs = sm;                 // [ROWS][D]
+  float* Ks = Rs + ROWS * D;      // [KT][DP]
+  float* Vs = Ks + KT * DP;       // [KT][DP]
+  float* Ps = Vs + KT * DP;       // [4][RPW][KT]
+  int* kflag = reinterpret_cast<int*>(Ps + 4 * RPW * KT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
+  const LaraWs ws = lara_ws_at(ws_base, blockIdx.z, g.C, g.S, D);
+  const bool kv_mode = (int)blockIdx.x < kv_blocks;
+  const int rb = kv_mode ? blockIdx.x : blockIdx.x - kv_blocks;
+  const int n_rows = kv_mode ? g.S : g.C;
+  const float* rows = kv_mode ? ws.omega : ws.qbar;
+  const View& keys = kv_mode ? k : q;
+  const float scale = rsqrtf((float)D);
+
+  for (int idx = tid; idx < ROWS * D; idx += blockDim.x) {
+    const int r = idx / D, row = rb * ROWS + r;
+    Rs[idx] = row < n_rows ? rows[(long long)row * D + idx % D] : 0.f;
+  }
+  float m[RPW], l[RPW], o[RPW][DPL];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    m[r] = kNegInf; l[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) o[r][i] = 0.f;
+  }
+  for (int kt0 = 0; kt0 < g.N; kt0 += KT) {
+    __syncthreads();
+    for (int idx = tid; idx < KT * (D / 8); idx += blockDim.x) {
+      const int j = idx / (D / 8), part = idx % (D / 8);
+      const int tok = kt0 + j;
+      float fk[8], fv[8];
+      int flag = 2;
+      bool have = false;
+      if (tok < g.N) {
+        const bool padded = mask && mask[(long long)b * g.N + tok];
+        flag = (padded && kv_mode) ? 1 : 0;
+        if (!(padded && g.zero_padded)) {
+          load8<T>(keys.row<T>(b, tok, h) + part * 8, fk);
+          if (kv_mode) load8<T>(v.row<T>(b, tok, h) + part * 8, fv);
+          have = true;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        Ks[j * DP + part * 8 + i] = have ? fk[i] : 0.f;
+        Vs[j * DP + part * 8 + i] = (have && kv_mode) ? fv[i] : 0.f;
+      }
+      if (part == 0) kflag[j] = flag;
+    }
+    __syncthreads();
+    float s[RPW], n2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) s[r] = 0.f;
+    const float* krow = Ks + lane * DP;
+    const float* rrow = Rs + (warp * RPW) * D;
+#pragma unroll 8
+    for (int e = 0; e < D; ++e) {
+      const float kk = krow[e];
+      n2 = fmaf(kk, kk, n2);
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) s[r] = fmaf(rrow[r * D + e], kk, s[r]);
+    }
+    const int flag = kflag[lane];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      float sv = kv_mode ? scale * (s[r] - 0.5f * n2) : scale * s[r];
+      if (flag != 0) sv = kNegInf;  // absent, or padded key of phi(k) (lara.py:204-208)
+      const float mt = warp_max(sv);
+      const float mn = fmaxf(m[r], mt);
+      float corr = 1.f, p = 0.f;
+      if (mn != kNegInf) { corr = exp_nonpos(m[r] - mn); p = exp_nonpos(sv - mn); }
+      l[r] = fmaf(l[r], corr, warp_sum(p));
+      m[r] = mn;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[r][i] *= corr;
+      Ps[(warp * RPW + r) * KT + lane] = p;
+    }
+    __syncwarp();
+    if (kv_mode) {
+      const float* prow = Ps + (warp * RPW) * KT;
+#pragma unroll 4
+      for (int j = 0; j < KT; ++j) {
+        float vv[DPL];
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) vv[i] = Vs[j * DP + lane + 32 * i];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const float p = prow[r * KT + j];
+#pragma unroll
+          for (int i = 0; i < DPL; ++i) o[r][i] = fmaf(p, vv[i], o[r][i]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = rb * ROWS + warp * RPW + r;
+    if (row >= n_rows) continue;
+    const float lse = m[r] + logf(l[r]);
+    if (kv_mode) {
+      const float inv = 1.0f / l[r];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) ws.kv[(long long)row * D + lane + 32 * i] = o[r][i] * inv;
+      if (lane == 0) ws.lse_k[row] = lse;
+    } else if (lane == 0) {
+      ws.lse_t[row] = lse;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L3: per token.  CTA stages omega, q_bar|mu, kv and the per-sample constants; one warp per token.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLaraTokPerCta = 64;
+
+template <typename T, int DPL>
+__global__ void __launch_bounds__(256)
+lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask, const float* __restrict__ ws_base,
+                T* __restrict__ out) {
+  constexpr int D = 32 * DPL, DP = D + 1;
+  extern __shared__ float sm[];
+  const int C = g.C, S = g.S;
+  float* om = sm;               // [S][DP]
+  float* aux = om + S * DP;     // [C][DP]  q_bar (mis-opt) or mu (mis-biased)
+  float* kvs = aux + C * DP;    // [S][DP]
+  float* cst = kvs + S * DP;    // [S]  lse_k - lp
+  float* bhs = cst + S;         // [S]
+  float* lset = bhs + S;        // [C]
+  float* qv = lset + C;         // [8][D]
+  float* wv = qv + 8 * D;       // [8][S]
+  float* tb = wv + 8 * S;       // [8][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
+  const LaraWs ws = lara_ws_at(const_cast<float*>(ws_base), blockIdx.z, C, S, D);
+  const float scale = rsqrtf((float)D);
+  const float* auxsrc = g.mis_type == LARA_MIS_OPT ? ws.qbar : ws.mu;
+  for (int idx = tid; idx < S * D; idx += blockDim.x) {
+    om[(idx / D) * DP + idx % D] = ws.omega[idx];
+    kvs[(idx / D) * DP + idx % D] = ws.kv[idx];
+  }
+  for (int idx = tid; idx < C * D; idx += blockDim.x) aux[(idx / D) * DP + idx % D] = auxsrc[idx];
+  for (int s = tid; s < S; s += blockDim.x) { cst[s] = ws.lse_k[s] - ws.lp[s]; bhs[s] = ws.bh[s]; }
+  for (int c = tid; c < C; c += blockDim.x) lset[c] = ws.lse_t[c];
+  __syncthreads();
+
+  float* myq = qv + warp * D;
+  float* myw = wv + warp * S;
+  float* myt = tb + warp * C;
+  const int t_end = min(g.N, (int)(blockIdx.x + 1) * kLaraTokPerCta);
+  for (int tok = blockIdx.x * kLaraTokPerCta + warp; tok < t_end; tok += 8) {
+    const bool zero = g.zero_padded && mask && mask[(long long)b * g.N + tok];
+    const T* qr = q.row<T>(b, tok, h);
+    float n2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+      const float x = zero ? 0.f : to_f32(qr[lane + 32 * i]);
+      myq[lane + 32 * i] = x;
+      n2 = fmaf(x, x, n2);
+    }
+    n2 = warp_sum(n2);
+    __syncwarp();
+    float mean_t = 0.f;
+    if (g.mis_type == LARA_MIS_OPT) {
+      float acc = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        float d_ = 0.f;
+        for (int e = 0; e < D; ++e) d_ = fmaf(aux[c * DP + e], myq[e], d_);
+        const float t = expf(scale * d_ - lset[c]);
+        myt[c] = t;
+        acc += t;
+      }
+      mean_t = warp_sum(acc) / (float)C;
+      __syncwarp();
+    }
+    float mx = kNegInf;
+    for (int s = lane; s < S; s += 32) {
+      float d_ = 0.f;
+      for (int e = 0; e < D; ++e) d_ = fmaf(om[s * DP + e], myq[e], d_);
+      const float A = scale * (d_ - 0.5f * n2);
+      float log_alpha = 0.f;
+      if (g.mis_type == LARA_MIS_OPT) {
+        const float alpha = bhs[s] + g.alpha_coeff * (myt[s % C] - mean_t);
+        log_alpha = logf(fmaxf(alpha, 1e-8f));
+      } else if (g.mis_type == LARA_MIS_BIASED) {
+        float dm = 0.f;
+        for (int e = 0; e < D; ++e) dm = fmaf(aux[(s % C) * DP + e], myq[e], dm);
+        log_alpha = scale * dm;
+      }
+      const float lw = log_alpha + A + cst[s];
+      myw[s] = lw;
+      mx = fmaxf(mx, lw);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < S; s += 32) { const float e_ = exp_nonpos(myw[s] - mx); myw[s] = e_; sum += e_; }
+    const float inv = 1.0f / warp_sum(sum);
+    __syncwarp();
+    float o[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float w = myw[s];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[i] = fmaf(w, kvs[s * DP + lane + 32 * i], o[i]);
+    }
+    T* orow = out + ((long long)b * g.N + tok) * ((long long)g.H * D) + (long long)h * D;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) orow[lane + 32 * i] = from_f32<T>(o[i] * inv);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t landmark_smem(const LaraGeo& g) {
+  const int DP = g.D + 1;
+  return ((size_t)(4 * g.C + g.S) * DP + (size_t)g.D * g.D + 8 * (size_t)g.C) * sizeof(float);
+}
+static size_t out_smem(const LaraGeo& g) {
+  const int DP = g.D + 1;
+  return ((size_t)(2 * g.S + g.C) * DP + 2 * (size_t)g.S + g.C + 8 * (size_t)(g.D + g.S + g.C)) * sizeof(float);
+}
+
+size_t lara_workspace_bytes(const LaraGeo& g) {
+  const size_t per = lara_ws_floats_per_bh(g.C, g.S, g.D);
+  return (((size_t)g.B * g.H * per * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+template <typename T, int DPL>
+static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k, const View& v, const uint8_t* mask,
+                                 const EvaAdaptive& proj, const float* noise, void* out, void* workspace,
+                                 cudaStream_t st) {
+  constexpr int D = 32 * DPL;
+  float* ws = reinterpret_cast<float*>(workspace);
+  const size_t sm1 = landmark_smem(g), sm3 = out_smem(g);
+  if (sm1 > 227 * 1024 || sm3 > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e;
+  {
+    auto kern = lara_landmark_kernel<T, DPL>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+    kern<<<g.B * g.H, 256, sm1, st>>>(g, q, k, v, mask, proj, noise, ws);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    auto kern = lara_stats_kernel<T, DPL>;
+    const size_t sm2 = (size_t)(16 * D + 2 * 32 * (D + 1) + 4 * 4 * 32) * sizeof(float) + 32 * sizeof(int);
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)) != cudaSuccess) return e;
+    const int kv_blocks = (g.S + 15) / 16;
+    const int t_blocks = g.mis_type == LARA_MIS_OPT ? (g.C + 15) / 16 : 0;
+    dim3 grid(kv_blocks + t_blocks, 1, g.B * g.H);
+    kern<<<grid, 128, sm2, st>>>(g, q, k, v, mask, ws, kv_blocks);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    auto kern = lara_out_kernel<T, DPL>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
+    dim3 grid((g.N + kLaraTokPerCta - 1) / kLaraTokPerCta, 1, g.B * g.H);
+    kern<<<grid, 256, sm3, st>>>(g, q, mask, ws, reinterpret_cast<T*>(out));
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
+                        const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
+                        void* workspace, cudaStream_t st) {
+  switch (io_dtype * 8 + g.D / 32) {
+    case EVA_F32 * 8 + 1: return launch_lara_t<float, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 8 + 2: return launch_lara_t<float, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 8 + 4: return launch_lara_t<float, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 8 + 1: return launch_lara_t<__half, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 8 + 2: return launch_lara_t<__half, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 8 + 4: return launch_lara_t<__half, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 8 + 1: return launch_lara_t<__nv_bfloat16, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 8 + 2: return launch_lara_t<__nv_bfloat16, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 8 + 4: return launch_lara_t<__nv_bfloat16, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace eva

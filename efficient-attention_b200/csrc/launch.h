@@ -1,0 +1,41 @@
+// Internal C++ launch interface between the C ABI (abi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eva_sm100.h"
+#include "common.cuh"
+
+namespace eva {
+
+cudaError_t launch_chunk_stats(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                               const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
+                               float* kbar, float* beta, cudaStream_t st);
+
+cudaError_t launch_window_attn(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                               const uint8_t* mask, const float* kbar, const float* beta,
+                               const float* bias, long long bias_sh, void* out, cudaStream_t st);
+
+// Fused tcgen05/TMA path (eva_fused_sm100.cu).  `supported` says whether the geometry qualifies.
+bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                     const uint8_t* mask, const EvaAdaptive& ada, const float* bias, long long bias_sh);
+size_t fused_workspace_bytes(const Geo& g);
+// returns cudaSuccess, or an error with *msg describing it
+cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
+                         const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,
+                         void* out, void* workspace, cudaStream_t st, const char** msg);
+
+// LARA (lara_generic.cu)
+struct LaraGeo {
+  int B, H, N, D;
+  int dims, gh, gw;
+  int C, S, side;          // landmarks, samples, landmarks per grid side (2-D)
+  int per_token_proj, mixed, mis_type, sample_mode, zero_padded;
+  float alpha_coeff;
+};
+size_t lara_workspace_bytes(const LaraGeo& g);
+cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
+                        const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
+                        void* workspace, cudaStream_t st);
+
+}  // namespace eva

@@ -1,0 +1,232 @@
+"""ctypes binding of libeva_sm100.so (C ABI declared in include/eva_sm100.h).
+
+Raw device pointers, sizes and the current CUDA stream go across; no torch types.  There is no CPU
+or eager fallback: if the library is missing or a tensor is not on a CUDA device the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libeva_sm100.so')
+
+EVA_F32, EVA_F16, EVA_BF16 = 0, 1, 2
+_DTYPES = {torch.float32: EVA_F32, torch.float16: EVA_F16, torch.bfloat16: EVA_BF16}
+LARA_MIS = {'mis-opt': 0, 'mis-bh': 1, 'mis-biased': 2}
+LARA_SAMPLE_SINGLE, LARA_SAMPLE_ANTITHETIC, LARA_SAMPLE_MULTI = 0, 1, 2
+
+
+class EvaHeadsView(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('stride_b', ctypes.c_int64), ('stride_n', ctypes.c_int64),
+                ('stride_h', ctypes.c_int64)]
+
+
+class EvaGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        'batch', 'heads', 'tokens', 'head_dim', 'dims', 'grid_h', 'grid_w', 'window', 'ext', 'halo_left_only',
+        'chunk', 'chunk_ext', 'causal', 'mask_queries', 'mask_is_neg_inf', 'io_dtype')]
+
+
+class EvaAdaptive(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('w_q', 'b_q', 'ln_gain_q', 'ln_bias_q', 'w_k', 'b_k', 'ln_gain_k',
+                                               'ln_bias_k')] + [('mu_coeff', ctypes.c_float), ('ln_eps', ctypes.c_float)]
+
+
+class LaraGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        'batch', 'heads', 'tokens', 'head_dim', 'dims', 'grid_h', 'grid_w', 'landmarks', 'per_token_proj', 'mixed',
+        'mis_type', 'sample_mode', 'zero_padded', 'io_dtype')] + [('alpha_coeff', ctypes.c_float)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+class EvaKernelError(RuntimeError):
+    """A libeva_sm100 entry point returned a non-zero status."""
+
+
+def load():
+    """Load (once) and return the shared library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python efficient-attention_b200/build.py` '
+                '(nvcc, sm_100a). There is no CPU / eager fallback for this package.')
+        lib = ctypes.CDLL(LIB_PATH)
+        P, I64, SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
+        G, V, A, LG = ctypes.POINTER(EvaGeometry), ctypes.POINTER(EvaHeadsView), ctypes.POINTER(EvaAdaptive), ctypes.POINTER(LaraGeometry)
+        lib.eva_sm100_abi_version.restype = ctypes.c_int
+        lib.eva_last_error.restype = ctypes.c_char_p
+        lib.eva_num_chunks.argtypes = [G]
+        lib.eva_chunk_stats.argtypes = [G, V, V, V, P, A, P, P, P, P]
+        lib.eva_window_attention.argtypes = [G, V, V, V, P, P, P, P, I64, P, P]
+        lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
+        lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
+        lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
+        lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
+        for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
+                   'eva_forward', 'lara_forward_workspace_bytes', 'lara_forward'):
+            getattr(lib, fn).restype = ctypes.c_int
+        if lib.eva_sm100_abi_version() != 1:
+            raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
+        _lib = lib
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EvaKernelError(f'{what} failed ({rc}): {load().eva_last_error().decode()}')
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('efficient_attention (B200 build) needs CUDA tensors: there is no CPU fallback')
+
+
+def io_dtype(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f'unsupported activation dtype {t.dtype} (float32, float16, bfloat16)') from None
+
+
+def heads_view(t):
+    """t: [B, N, H, D] view (any strides, D contiguous) -> EvaHeadsView."""
+    assert t.dim() == 4 and t.stride(3) == 1, 'expected a [B, N, H, D] view with contiguous D'
+    return EvaHeadsView(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff, ln_eps=1e-5):
+    """Returns (struct, keepalive list of float32 tensors)."""
+    keep = [_f32(t) for t in (wq, bq, gq, betq, wk, bk, gk, betk)]
+    s = EvaAdaptive(*[None if t is None else t.data_ptr() for t in keep], mu_coeff, ln_eps)
+    return s, keep
+
+
+def _mask_u8(mask, B, N):
+    if mask is None:
+        return None
+    m = mask.reshape(B, N).to(torch.bool).to(torch.uint8).contiguous()
+    return m
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def eva_geometry(q, *, seq_shape, window, ext, chunk, chunk_ext, causal=False, halo_left_only=False,
+                 mask_queries=False, mask_is_neg_inf=False):
+    B, N, H, D = q.shape
+    two_d = len(seq_shape) == 2
+    return EvaGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N,
+                       window, ext, int(halo_left_only), chunk, chunk_ext, int(causal), int(mask_queries),
+                       int(mask_is_neg_inf), io_dtype(q))
+
+
+def num_chunks(geom):
+    n = load().eva_num_chunks(ctypes.byref(geom))
+    if n < 0:
+        _check(n, 'eva_num_chunks')
+    return n
+
+
+def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, return_path=False):
+    """q,k,v: [B,N,H,D] views.  Returns out [B,N,H*D] (same dtype)."""
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, noise, bias)
+    B, N, H, D = q.shape
+    ada_s, keep = ada
+    mask = _mask_u8(pad_mask, B, N)
+    noise = _f32(noise)
+    bias = _f32(bias)
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.eva_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'eva_forward_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
+    path = ctypes.c_int32(-1)
+    bias_sh = 0 if bias is None or bias.shape[0] == 1 else bias.shape[1] * bias.shape[2]
+    with torch.cuda.device(q.device):
+        rc = lib.eva_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                             ctypes.byref(heads_view(v)), _ptr(mask), ctypes.byref(ada_s), _ptr(noise), _ptr(bias),
+                             bias_sh, _ptr(out), _ptr(ws), ws.numel(), ctypes.byref(path), _stream(q.device))
+    _check(rc, 'eva_forward')
+    del keep
+    return (out, path.value) if return_path else out
+
+
+def eva_chunk_stats(q, k, v, geom, ada, *, pad_mask=None, noise=None):
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, noise)
+    B, N, H, D = q.shape
+    C = num_chunks(geom)
+    ada_s, keep = ada
+    mask = _mask_u8(pad_mask, B, N)
+    noise = _f32(noise)
+    k_bar = torch.empty(B, H, C, D, dtype=torch.float32, device=q.device)
+    beta = torch.empty_like(k_bar)
+    with torch.cuda.device(q.device):
+        rc = lib.eva_chunk_stats(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                 ctypes.byref(heads_view(v)), _ptr(mask), ctypes.byref(ada_s), _ptr(noise),
+                                 _ptr(k_bar), _ptr(beta), _stream(q.device))
+    _check(rc, 'eva_chunk_stats')
+    del keep
+    return k_bar, beta
+
+
+def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None, bias=None):
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, k_bar, beta, bias)
+    B, N, H, D = q.shape
+    mask = _mask_u8(pad_mask, B, N)
+    bias = _f32(bias)
+    k_bar, beta = _f32(k_bar), _f32(beta)
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    bias_sh = 0 if bias is None or bias.shape[0] == 1 else bias.shape[1] * bias.shape[2]
+    with torch.cuda.device(q.device):
+        rc = lib.eva_window_attention(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                      ctypes.byref(heads_view(v)), _ptr(mask), _ptr(k_bar), _ptr(beta), _ptr(bias),
+                                      bias_sh, _ptr(out), _stream(q.device))
+    _check(rc, 'eva_window_attention')
+    return out
+
+
+def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded,
+                 alpha_coeff, proj, pad_mask=None, noise=None):
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, noise)
+    B, N, H, D = q.shape
+    two_d = len(seq_shape) == 2
+    geom = LaraGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N,
+                        landmarks, int(per_token_proj), int(mixed), LARA_MIS[mis_type], sample_mode, int(zero_padded),
+                        io_dtype(q), float(alpha_coeff))
+    proj_s, keep = proj
+    mask = _mask_u8(pad_mask, B, N)
+    noise = _f32(noise)
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.lara_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'lara_forward_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.lara_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                              ctypes.byref(heads_view(v)), _ptr(mask), ctypes.byref(proj_s), _ptr(noise), _ptr(out),
+                              _ptr(ws), ws.numel(), _stream(q.device))
+    _check(rc, 'lara_forward')
+    del keep
+    return out

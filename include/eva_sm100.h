@@ -1,0 +1,149 @@
+/* eva_sm100.h -- C ABI of libeva_sm100.so: the B200 (sm_100a) EVA / LARA / causal-EVA attention
+ * forward core.
+ *
+ * The reference (HKUNLP/efficient-attention) is pure Python/PyTorch and has no native boundary of
+ * its own; the seam is cut just below `module.forward`: everything between `proj_and_split_heads`
+ * and the output projection.  Each entry point names the reference code it replaces:
+ *
+ *   eva_chunk_stats        eva.py:155-196          causal_eva.py:676-719   (chunk pooling, adaptive
+ *                                                  Linear+LayerNorm, phi-projection, beta)
+ *   eva_window_attention   eva.py:200-227          causal_eva.py:722-783   (local + chunk logits, one
+ *                          local_attention.py:134-182   abstract_attention.py:115-133   joint softmax, PV)
+ *   eva_forward            eva.py:151-227 as one call (selects the fused sm_100a tcgen05/TMA kernel
+ *                          when the geometry allows, else the two generic stages)
+ *   lara_landmarks         lara.py:84-175          (landmark pooling, Linear+LN, mixing, proposal stats)
+ *   lara_forward           lara.py:201-246         (phi-projections, kv statistics, MIS weights, SNIS)
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative errno-style code; it never throws, never
+ *     calls exit(), never allocates or frees device memory and never synchronises the device;
+ *   - all buffers are caller-owned device memory (the Python host side hands out PyTorch tensors);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
+ *   - the library is re-entrant across streams and devices; the only process-global state is a
+ *     per-device cache of function attributes / tensor maps guarded by a mutex, and a thread-local
+ *     last-error string;
+ *   - q, k, v are described as strided views [batch, tokens, heads, head_dim] with head_dim
+ *     contiguous, so both the packed `qkv` Linear output ([B,N,3,h,d], abstract_attention.py:72-78)
+ *     and separate q/k/v projections (causal_eva.py:511-536) are consumed without a permute copy;
+ *   - the output is written as [batch, tokens, heads*head_dim] contiguous, which is what the
+ *     output projection consumes (eva.py:228, causal_eva.py:784).
+ */
+#ifndef EVA_SM100_H_
+#define EVA_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVA_SM100_ABI_VERSION 1
+
+enum EvaDtype { EVA_F32 = 0, EVA_F16 = 1, EVA_BF16 = 2 };
+
+enum EvaStatus {
+  EVA_OK = 0,
+  EVA_ERR_INVALID = -22,      /* EINVAL: malformed geometry / null pointer / misaligned view   */
+  EVA_ERR_UNSUPPORTED = -95,  /* EOPNOTSUPP: legal in the reference but not built here         */
+  EVA_ERR_CUDA = -5           /* EIO: a CUDA runtime/driver call failed (see eva_last_error)   */
+};
+
+/* One of q / k / v: element (b, n, h, e) lives at ptr[b*stride_b + n*stride_n + h*stride_h + e].
+ * Strides are in elements. ptr must be 16-byte aligned and strides multiples of 8 elements. */
+typedef struct EvaHeadsView {
+  const void* ptr;
+  int64_t stride_b, stride_n, stride_h;
+} EvaHeadsView;
+
+/* Geometry of one EVA-style forward (eva.py:119-165, causal_eva.py:353-365,676-690). */
+typedef struct EvaGeometry {
+  int32_t batch, heads, tokens, head_dim; /* tokens = padded sequence length N               */
+  int32_t dims;                           /* 1 (sequence) or 2 (token grid)                   */
+  int32_t grid_h, grid_w;                 /* dims==2: grid_h*grid_w == tokens                 */
+  int32_t window;                         /* local window edge w (tokens % w == 0 / grid % w) */
+  int32_t ext;                            /* halo ("ext_size") of the local windows           */
+  int32_t halo_left_only;                 /* 1: causal_window_1d_partition (causal_eva.py:102)*/
+  int32_t chunk;                          /* chunk edge (rf_win_size); 0 = no chunk keys      */
+  int32_t chunk_ext;                      /* halo of the chunks (== ext in EVA, 0 in causal)  */
+  int32_t causal;                         /* triu masks of causal_eva.py:725-739,765-771      */
+  int32_t mask_queries;                   /* local logits of padded queries masked too        */
+  int32_t mask_is_neg_inf;                /* 1: padded keys get -inf (softmax baseline),
+                                             0: -5e4 (eva.py:139)                             */
+  int32_t io_dtype;                       /* EvaDtype of q, k, v and out                      */
+} EvaGeometry;
+
+/* adaptive_mu_q / adaptive_mu_k = Linear(d,d) [+ LayerNorm(d)] shared by all heads
+ * (eva.py:78-98, causal_eva.py:381-396). float32, row-major [out,in].
+ * w_q == NULL: adaptive_proj == 'none' (mu = 0).  ln_gain_* == NULL: no LayerNorm ('no-ln'). */
+typedef struct EvaAdaptive {
+  const float *w_q, *b_q, *ln_gain_q, *ln_bias_q;
+  const float *w_k, *b_k, *ln_gain_k, *ln_bias_k;
+  float mu_coeff; /* 0.5 in EVA (eva.py:182), 1.0 in causal EVA (causal_eva.py:708) */
+  float ln_eps;   /* 1e-5 */
+} EvaAdaptive;
+
+int eva_sm100_abi_version(void);
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* eva_last_error(void);
+/* Number of chunks the geometry produces (C_n), or a negative status. */
+int eva_num_chunks(const EvaGeometry* g);
+
+/* k_bar, beta: float32 [batch, heads, C_n, head_dim].  pad_mask: [batch, tokens] bytes, nonzero =
+ * padding, may be NULL.  noise: float32 [batch, heads, C_n, head_dim] or NULL (eval mode). */
+int eva_chunk_stats(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                    const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
+                    float* k_bar, float* beta, void* stream);
+
+/* bias: float32 [bias_heads, L, J] added to the local logits (already scaled), NULL for none;
+ * bias_stride_h = L*J, or 0 when one table is shared by all heads (causal T5 bias).
+ * k_bar / beta may be NULL iff g->chunk == 0 (pure local / dense softmax attention).
+ * out: io_dtype [batch, tokens, heads*head_dim]. */
+int eva_window_attention(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                         const uint8_t* pad_mask, const float* k_bar, const float* beta,
+                         const float* bias, int64_t bias_stride_h, void* out, void* stream);
+
+/* Bytes of scratch eva_forward needs (k_bar + beta + fast-path staging); 256-byte aligned. */
+int eva_forward_workspace_bytes(const EvaGeometry* g, size_t* bytes);
+
+/* Both stages in one call.  *path_taken (optional) receives 1 when the fused sm_100a kernel ran,
+ * 0 when the generic two-stage path ran. */
+int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
+                const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,
+                int32_t* path_taken, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LARA (lara.py).  Landmarks are the pooled q/k summaries; samples S = landmarks C, or 2C with
+ * antithetic / multi-sample proposals at training time (lara.py:188-198). */
+enum LaraMis { LARA_MIS_OPT = 0, LARA_MIS_BH = 1, LARA_MIS_BIASED = 2 };
+enum LaraSample { LARA_SAMPLE_SINGLE = 0, LARA_SAMPLE_ANTITHETIC = 1, LARA_SAMPLE_MULTI = 2 };
+
+typedef struct LaraGeometry {
+  int32_t batch, heads, tokens, head_dim;
+  int32_t dims;             /* 2: AdaptiveAvgPool2d landmarks (lara.py:129-175); 1: segment means (lara.py:84-127) */
+  int32_t grid_h, grid_w;
+  int32_t landmarks;        /* C: dims==2 -> int(sqrt(num_landmarks))^2 ; dims==1 -> min(num_landmarks, tokens) */
+  int32_t per_token_proj;   /* 1: 'adaptive-1d' (Linear+LN on every token before pooling)   */
+  int32_t mixed;            /* 0 none, 1 '-mixed', 2 '-vmixed' (lara.py:157-174)            */
+  int32_t mis_type;         /* LaraMis                                                      */
+  int32_t sample_mode;      /* LaraSample (only meaningful when noise != NULL)              */
+  int32_t zero_padded;      /* 1: q,k,v of padded tokens are treated as 0 (1-D path, lara.py:87-91) */
+  int32_t io_dtype;
+  float alpha_coeff;
+} LaraGeometry;
+
+/* Scratch for lara_forward. */
+int lara_forward_workspace_bytes(const LaraGeometry* g, size_t* bytes);
+
+/* proj: the q_bar_gen / k_bar_gen Linear(+LayerNorm) parameters in an EvaAdaptive (w_q == NULL for
+ * 'no-param-pool'; mu_coeff ignored).  noise: float32 [batch, heads, S or C (antithetic), head_dim]
+ * or NULL.  out: io_dtype [batch, tokens, heads*head_dim]. */
+int lara_forward(const LaraGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                 const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
+                 void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVA_SM100_H_ */

@@ -1,0 +1,145 @@
+"""CPU tests of the drop-in boundary: plugin surface, argparse plumbing, checkpoint compatibility,
+host-side index logic, the C-ABI export list and loud failure without CUDA.  (`-m "not gpu"`)"""
+import argparse
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, golden_names, load_golden
+from helpers import build_module
+from oracle import eva_oracle as O
+
+import efficient_attention as ea
+from efficient_attention import _abi
+from efficient_attention.attn_utils import pad_to_multiple, t5_bucket_table
+
+
+def test_registry_names_and_errors():
+    assert set(ea.AttentionFactory.attn_dict) == {'softmax', 'local', 'lara', 'eva', 'causal_eva'}
+    with pytest.raises(KeyError):
+        ea.AttentionFactory.build_attention('nope', {})
+    with pytest.raises(TypeError):
+        ea.AttentionFactory.build_attention('eva', dict(dim=64, num_heads=2, bogus=1))
+
+
+def test_eva_cli_namespace_matches_reference_probe():
+    # the namespace the DeiT EVA command line produces
+    p = argparse.ArgumentParser()
+    ea.AttentionFactory.add_attn_specific_args(p, 'eva')
+    a = p.parse_args(['--use-rpe', '--window-size', '7', '--attn-2d'], namespace=ea.NestedNamespace())
+    assert vars(a.attn_args) == dict(fp32=False, use_rpe=True, window_size=7, attn_2d=True, overlap_window=False,
+                                     adaptive_proj='default', num_landmarks=49, use_t5_rpe=False)
+
+
+def test_prefixed_arguments_land_in_named_struct():
+    p = argparse.ArgumentParser()
+    ea.AttentionFactory.add_attn_specific_args(p, 'eva', struct_name='attn_args_encoder', prefix='encoder-attn')
+    ea.AttentionFactory.add_attn_specific_args(p, 'causal_eva', struct_name='attn_args_decoder', prefix='decoder-attn')
+    a = p.parse_args(['--encoder-attn-window-size', '8', '--decoder-attn-chunk-size', '16', '--decoder-attn-causal'],
+                     namespace=ea.NestedNamespace())
+    assert a.attn_args_encoder.window_size == 8 and a.attn_args_encoder.num_landmarks == 49
+    assert a.attn_args_decoder.chunk_size == 16 and a.attn_args_decoder.causal is True
+    assert a.attn_args_decoder.window_size == 4
+
+
+def test_lara_cli_defaults():
+    p = argparse.ArgumentParser()
+    ea.AttentionFactory.add_attn_specific_args(p, 'lara')
+    a = p.parse_args([], namespace=ea.NestedNamespace())
+    assert vars(a.attn_args) == dict(fp32=False, num_landmarks=49, kernel_size=None, pool_module_type='light',
+                                     mis_type='mis-opt', proposal_gen='pool', use_antithetics=False,
+                                     use_multisample=False, alpha_coeff=1.0)
+
+
+def test_remove_argument():
+    p = argparse.ArgumentParser()
+    p.add_argument('--foo', default=1)
+    p.add_argument('--bar', default=2)
+    ea.remove_argument(p, '--foo')
+    assert vars(p.parse_args([])) == {'bar': 2}
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_reference_checkpoints_load_strict(name):
+    """state_dict keys / shapes are part of the boundary."""
+    cfg, sd, _ = load_golden(name, dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd, strict=True)
+    if 'relative_position_index' in sd:   # our index formula == the reference's buffer
+        fresh = build_module(cfg)
+        assert torch.equal(fresh.relative_position_index, sd['relative_position_index'])
+
+
+def test_param_counts_match_survey():
+    from argparse import Namespace
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        eva = ea.AttentionFactory.build_attention('eva', dict(dim=192, num_heads=3, use_rpe=True, window_size=7, attn_2d=True))
+    lara = ea.AttentionFactory.build_attention('lara', dict(dim=384, num_heads=6, proposal_gen='pool-mixed'))
+    causal = ea.CausalEVAttention(512, 8, self_attention=True, attn_args=Namespace(
+        adaptive_proj='qk', num_chunks=None, chunk_size=256, causal=True, use_t5_rpe=True, window_size=256,
+        overlap_window=False))
+    count = lambda m: sum(p.numel() for p in m.parameters())
+    assert (count(eva), count(lara), count(causal)) == (157091, 599936, 1059264)
+
+
+def test_pad_to_multiple():
+    x = torch.ones(2, 10, 4)
+    y, m = pad_to_multiple(x, 8, dim=-2, create_mask=True)
+    assert y.shape == (2, 16, 4) and m.shape == (2, 16) and m[:, 10:].all() and not m[:, :10].any()
+    assert y[:, 10:].abs().sum() == 0
+    y2, m2 = pad_to_multiple(torch.ones(2, 16, 4), 8, dim=-2, create_mask=True)
+    assert y2.shape == (2, 16, 4) and not m2.any()
+    km = pad_to_multiple(torch.zeros(2, 10, dtype=torch.bool), 8, dim=-1, value=True)
+    assert km.shape == (2, 16) and km[:, 10:].all()
+
+
+@pytest.mark.parametrize('causal', [False, True])
+@pytest.mark.parametrize('geom', [(49, 49, 16, 7), (8, 12, 16, 12), (256, 256, 64, 256), (16, 32, 16, 32)])
+def test_t5_bucket_table_matches_oracle(geom, causal):
+    L, J, nb, md = geom
+    rel = torch.arange(J).view(1, J) - torch.arange(L).view(L, 1)
+    assert torch.equal(t5_bucket_table(L, J, causal, nb, md), O.t5_bucket(rel, causal, nb, md))
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'eva_sm100.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(?:int|const char\s*\*)\s+((?:eva|lara)_\w+)\s*\(', header))
+    assert {'eva_forward', 'eva_chunk_stats', 'eva_window_attention', 'lara_forward', 'eva_last_error'} <= declared
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert _abi.load().eva_sm100_abi_version() == 1
+
+
+def test_cabi_rejects_bad_geometry_without_touching_the_gpu():
+    lib = _abi.load()
+    g = _abi.EvaGeometry(2, 3, 196, 64, 2, 14, 14, 5, 0, 0, 2, 0, 0, 0, 0, _abi.EVA_F16)  # 14 % 5 != 0
+    assert lib.eva_num_chunks(ctypes.byref(g)) == -22
+    assert b'window' in lib.eva_last_error()
+    g = _abi.EvaGeometry(2, 3, 196, 48, 2, 14, 14, 7, 0, 0, 2, 0, 0, 0, 0, _abi.EVA_F16)  # head_dim 48
+    assert lib.eva_num_chunks(ctypes.byref(g)) == -95
+    g = _abi.EvaGeometry(2, 3, 784, 64, 2, 28, 28, 7, 0, 0, 4, 0, 0, 0, 0, _abi.EVA_F16)
+    assert lib.eva_num_chunks(ctypes.byref(g)) == 49
+
+
+def test_no_cpu_fallback():
+    cfg, sd, a = load_golden('eva_2d_noln', dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.eval()(a['x'])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'efficient-attention_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('SURVEY', ''), os.path.join(dirpath, f)

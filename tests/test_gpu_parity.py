@@ -1,0 +1,231 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI (ctypes) and through the
+drop-in modules, against the golden fixtures and the CPU oracle on identical inputs.
+
+Tolerances (relative L2 per output tensor, reference evaluated in float64):
+  float32 I/O                      <= 2e-5   (fp32 math on both sides of the softmax)
+  float16 I/O, core only           <= 1e-3   (north_star tolerance; output rounding alone is ~2e-4)
+  bfloat16 I/O, core only          <= 6e-3   (bf16 output store alone costs ~1.7e-3; reported, not the target)
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_l2
+from helpers import build_module, run_module
+from oracle import eva_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 2e-5
+TOL_F16 = 1e-3
+TOL_BF16 = 6e-3
+
+
+def _dev():
+    return torch.device('cuda', 0)
+
+
+def _rand_ada(d, g, ln=True):
+    wq, wk = torch.randn(d, d, generator=g) / math.sqrt(d), torch.randn(d, d, generator=g) / math.sqrt(d)
+    bq, bk = 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    if not ln:
+        return dict(wq=wq, bq=bq, gq=None, betq=None, wk=wk, bk=bk, gk=None, betk=None)
+    return dict(wq=wq, bq=bq, gq=1 + 0.1 * torch.randn(d, generator=g), betq=0.1 * torch.randn(d, generator=g),
+                wk=wk, bk=bk, gk=1 + 0.1 * torch.randn(d, generator=g), betk=0.1 * torch.randn(d, generator=g))
+
+
+def _abi_ada(p, dev, mu_coeff):
+    from efficient_attention import _abi
+    mv = lambda t: None if t is None else t.to(dev)
+    return _abi.adaptive(mv(p['wq']), mv(p['bq']), mv(p['gq']), mv(p['betq']), mv(p['wk']), mv(p['bk']),
+                         mv(p['gk']), mv(p['betk']), mu_coeff=mu_coeff)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', golden_names())
+def test_module_matches_reference_golden_fp32(name):
+    cfg, sd, a = load_golden(name, dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    m = m.to(_dev())
+    m.train(a['noise'] is not None)
+    y = run_module(m, cfg, a, _dev(), torch.float32)
+    assert y.shape == a['y'].shape
+    err = rel_l2(y.cpu(), a['y'])
+    assert err < TOL_F32, (name, err)
+
+
+# ---------------------------------------------------------------------------------------------
+CORE_CASES = {
+    # name: (B, H, seq_shape, d, window, ext, chunk)
+    'c1_14x14': (2, 3, (14, 14), 64, 7, 0, 2),
+    'c3_28x28': (2, 3, (28, 28), 64, 7, 0, 4),
+    'pvt_d32_56x56': (1, 2, (56, 56), 32, 7, 0, 8),
+    'overlap_14x14': (1, 2, (14, 14), 64, 7, 3, 2),
+    'seq_1d_d128': (2, 2, (96,), 128, 16, 8, 12),
+}
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, TOL_F32), (torch.float16, TOL_F16), (torch.bfloat16, TOL_BF16)])
+@pytest.mark.parametrize('case', sorted(CORE_CASES))
+def test_eva_core_through_cabi_vs_oracle(case, dtype, tol):
+    from efficient_attention import _abi
+    B, H, shape, d, w, ext, chunk = CORE_CASES[case]
+    N = math.prod(shape)
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.2).to(dtype)        # quantise once; both sides see the same values
+    two_d = len(shape) == 2
+    L = w * w if two_d else w
+    J = (w + 2 * ext) ** 2 if two_d else w + 2 * ext
+    bias = 0.5 * torch.randn(H, L, J, generator=g)
+    ada = _rand_ada(d, g)
+    mask = None
+    if not two_d:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[1, N - 10:] = True
+    q64, k64, v64 = (qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3))
+    want, kbar_w, beta_w = O.eva_core(q64, k64, v64, seq_shape=shape, window=w, ext=ext, chunk=chunk, chunk_ext=ext,
+                                      **{k_: (v_.double() if v_ is not None else None) for k_, v_ in ada.items()},
+                                      mu_coeff=0.5, pad_mask=mask, bias=bias.double(), return_stats=True)
+    dev = _dev()
+    qkv_d = qkv.to(dev)
+    q, k, v = qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=shape, window=w, ext=ext, chunk=chunk, chunk_ext=ext)
+    ada_s = _abi_ada(ada, dev, 0.5)
+    mask_d = mask.to(dev) if mask is not None else None
+    # stage A alone
+    kbar, beta = _abi.eva_chunk_stats(q, k, v, geom, ada_s, pad_mask=mask_d)
+    assert rel_l2(kbar.cpu(), kbar_w) < 2e-5 and rel_l2(beta.cpu(), beta_w) < 2e-5
+    # stage B alone, fed with the oracle's statistics
+    out_b = _abi.eva_window_attention(q, k, v, geom, k_bar=kbar_w.float().to(dev), beta=beta_w.float().to(dev),
+                                      pad_mask=mask_d, bias=bias.to(dev))
+    # both stages in one call
+    out, path = _abi.eva_forward(q, k, v, geom, ada_s, pad_mask=mask_d, bias=bias.to(dev), return_path=True)
+    want_flat = want.permute(0, 2, 1, 3).reshape(B, N, H * d)
+    for name, o in (('stage_b', out_b), ('forward', out)):
+        err = rel_l2(o.cpu(), want_flat)
+        assert err < tol, (case, dtype, name, path, err)
+
+
+def test_c5_causal_layer_full_shape_fp32():
+    """BASELINE config c5 at full size: T=4096, B=2, C=512, h=8, window=chunk=256, causal, T5 bias."""
+    from argparse import Namespace
+    import efficient_attention as ea
+    torch.manual_seed(3)
+    m = ea.CausalEVAttention(512, 8, self_attention=True, attn_args=Namespace(
+        adaptive_proj='qk', num_chunks=None, chunk_size=256, causal=True, use_t5_rpe=True, window_size=256,
+        overlap_window=False)).eval()
+    with torch.no_grad():
+        m.rel_pos_bias.relative_attention_bias.weight.normal_(0, 0.5)
+    x = torch.randn(4096, 2, 512)
+    cfg = dict(num_heads=8, window_size=256, overlap_window=False, chunk_size=256, num_chunks=None, causal=True,
+               use_t5_rpe=True, adaptive_proj='qk')
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    want = O.causal_eva_forward(sd, cfg, x.double())
+    with torch.no_grad():
+        got = m.to(_dev())(x.to(_dev()), None, None)[0]
+    assert rel_l2(got.cpu(), want) < TOL_F32
+
+
+def test_c4_lara_layer_full_shape_fp32():
+    """BASELINE config c4 at full width: C=384, h=6, 14x14, 49 landmarks, pool-mixed, mis-opt."""
+    import efficient_attention as ea
+    torch.manual_seed(4)
+    m = ea.AttentionFactory.build_attention('lara', dict(dim=384, num_heads=6, num_landmarks=49,
+                                                         proposal_gen='pool-mixed', mis_type='mis-opt')).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 1.0 / math.sqrt(p.shape[1]))
+    x = torch.randn(4, 14, 14, 384)
+    cfg = dict(num_heads=6, num_landmarks=49, proposal_gen='pool-mixed', mis_type='mis-opt', alpha_coeff=1.0)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    want = O.lara_forward(sd, cfg, x.double())
+    with torch.no_grad():
+        got = m.to(_dev())(x.to(_dev()))
+    assert rel_l2(got.cpu(), want) < TOL_F32
+
+
+# ---- size-independent properties at the benchmark's shape --------------------------------------
+def _bench_layer(dtype):
+    import bench
+    return bench.build_layer(_dev(), dtype)
+
+
+def test_batch_permutation_equivariance_and_determinism_fp16():
+    m = _bench_layer(torch.float16)
+    torch.manual_seed(5)
+    x = torch.randn(64, 28, 28, 192, device=_dev(), dtype=torch.float16)
+    perm = torch.randperm(64, device=_dev())
+    with torch.no_grad():
+        y1, y2, yp = m(x), m(x), m(x[perm])
+    assert torch.equal(y1, y2)                     # run-to-run bitwise deterministic
+    assert torch.equal(y1[perm], yp)               # every (batch, head) is an independent unit
+
+
+def test_head_independence_fp32():
+    """Heads only meet in qkv / proj; with identity proj, perturbing head 0's input slice of the qkv
+    output must leave the other heads' core outputs bit-identical."""
+    from efficient_attention import _abi
+    torch.manual_seed(6)
+    dev = _dev()
+    g = torch.Generator().manual_seed(6)
+    qkv = torch.randn(2, 196, 3, 3, 64, generator=g).to(dev)
+    ada = _abi_ada(_rand_ada(64, g), dev, 0.5)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+    o1 = _abi.eva_forward(q, k, v, geom, ada).view(2, 196, 3, 64)
+    qkv2 = qkv.clone()
+    qkv2[:, :, :, 0] += 1.0
+    o2 = _abi.eva_forward(qkv2[:, :, 0], qkv2[:, :, 1], qkv2[:, :, 2], geom, ada).view(2, 196, 3, 64)
+    assert torch.equal(o1[:, :, 1:], o2[:, :, 1:]) and not torch.equal(o1[:, :, 0], o2[:, :, 0])
+
+
+def test_padding_invariance_1d():
+    """Appending masked tokens that fill whole extra windows must not change the valid outputs' local
+    part; with chunk keys present the chunk partition changes, so compare pure local attention."""
+    cfg, sd, a = load_golden('local_1d_mask', dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    m = m.to(_dev()).eval()
+    x = a['x'].to(_dev())
+    with torch.no_grad():
+        y = m(x, None)
+        x_long = torch.cat([x, torch.randn(2, 16, x.shape[-1], device=_dev())], 1)
+        mask = torch.zeros(2, x_long.shape[1], dtype=torch.bool, device=_dev())
+        mask[:, x.shape[1]:] = True
+        y_long = m(x_long, mask)
+    # tokens 0..23 live in windows whose halo never reaches the appended region (window 8, halo 4)
+    assert rel_l2(y_long[:, :24].cpu(), y[:, :24].cpu()) < 1e-6
+
+
+def test_causal_consistency_on_gpu():
+    """causal_eva.py:916-950 on the device: a prefix's outputs equal the full sequence's."""
+    cfg, sd, a = load_golden('causal_selfcheck', dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    m = m.to(_dev()).eval()
+    x = a['x'].to(_dev())
+    with torch.no_grad():
+        full = m(x, None, None)[0]
+        for t in (26, 64, 65, 100):
+            part = m(x[:t], None, None)[0]
+            assert torch.allclose(part[25], full[25], atol=2e-5, rtol=0), t
+
+
+def test_cabi_error_paths_on_device():
+    from efficient_attention import _abi
+    dev = _dev()
+    qkv = torch.randn(1, 196, 3, 2, 64, device=dev)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+    g = torch.Generator().manual_seed(0)
+    ada = _abi_ada(_rand_ada(64, g), dev, 0.5)
+    with pytest.raises(_abi.EvaKernelError, match='bias_stride_h'):
+        _abi.eva_forward(q, k, v, geom, ada, bias=torch.zeros(2, 49, 48, device=dev))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _abi.eva_forward(q.cpu(), k.cpu(), v.cpu(), geom, ada)
+    misaligned = torch.randn(1, 196, 3, 2, 66, device=dev)[..., 1:65]
+    with pytest.raises(AssertionError):
+        _abi.heads_view(misaligned[:, :, 0].transpose(2, 3))
