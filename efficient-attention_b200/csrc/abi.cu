@@ -28,8 +28,8 @@ int ipow(int b, int e) { return e == 2 ? b * b : b; }
 int make_geo(const EvaGeometry* in, eva::Geo* g) {
   if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");
   if (in->batch <= 0 || in->heads <= 0 || in->tokens <= 0) return fail(EVA_ERR_INVALID, "batch/heads/tokens must be positive");
-  if (in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
-    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (32, 64, 128)", in->head_dim);
+  if (in->head_dim != 16 && in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
+    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (16, 32, 64, 128)", in->head_dim);
   if (in->dims != 1 && in->dims != 2) return fail(EVA_ERR_INVALID, "dims must be 1 or 2");
   if (in->io_dtype < EVA_F32 || in->io_dtype > EVA_BF16) return fail(EVA_ERR_INVALID, "unknown io_dtype %d", in->io_dtype);
   if (in->window <= 0 || in->ext < 0 || in->chunk < 0 || in->chunk_ext < 0) return fail(EVA_ERR_INVALID, "window must be > 0; ext/chunk >= 0");
@@ -191,8 +191,8 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
 static int make_lara_geo(const LaraGeometry* in, eva::LaraGeo* g) {
   if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");
   if (in->batch <= 0 || in->heads <= 0 || in->tokens <= 0 || in->landmarks <= 0) return fail(EVA_ERR_INVALID, "batch/heads/tokens/landmarks must be positive");
-  if (in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
-    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (32, 64, 128)", in->head_dim);
+  if (in->head_dim != 16 && in->head_dim != 32 && in->head_dim != 64 && in->head_dim != 128)
+    return fail(EVA_ERR_UNSUPPORTED, "head_dim %d not built (16, 32, 64, 128)", in->head_dim);
   if (in->io_dtype < EVA_F32 || in->io_dtype > EVA_BF16) return fail(EVA_ERR_INVALID, "unknown io_dtype %d", in->io_dtype);
   if (in->mis_type < LARA_MIS_OPT || in->mis_type > LARA_MIS_BIASED) return fail(EVA_ERR_INVALID, "unknown mis_type");
   if (in->sample_mode < LARA_SAMPLE_SINGLE || in->sample_mode > LARA_SAMPLE_MULTI) return fail(EVA_ERR_INVALID, "unknown sample_mode");

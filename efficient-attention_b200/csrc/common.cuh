@@ -57,6 +57,49 @@ __device__ __forceinline__ float warp_max(float v) {
 // exp(x) for x <= 0 (softmax terms); exp(-inf) = 0
 __device__ __forceinline__ float exp_nonpos(float x) { return exp2f(x * kLog2e); }
 
+// ---- warp-per-row helpers: lane l owns features l, l+32, ... of a D-vector (D = 16, 32, 64, 128) ----
+template <int D> struct Feat {
+  static constexpr int kPerLane = (D + 31) / 32;
+  static __device__ __forceinline__ bool has(int lane, int i) { return (D % 32 == 0) || (lane + 32 * i < D); }
+};
+
+// y = W x + b with W^T staged in shared memory as Wt[in][out]
+template <int D>
+__device__ __forceinline__ void warp_linear(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                            const float (&x)[Feat<D>::kPerLane], float (&y)[Feat<D>::kPerLane], int lane) {
+  constexpr int DPL = Feat<D>::kPerLane;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) y[i] = (bias && Feat<D>::has(lane, i)) ? __ldg(bias + lane + 32 * i) : 0.f;
+#pragma unroll
+  for (int ii = 0; ii < DPL; ++ii) {
+#pragma unroll 8
+    for (int jj = 0; jj < (D < 32 ? D : 32); ++jj) {
+      const float m = __shfl_sync(0xffffffffu, x[ii], jj);
+      const float* wrow = Wt + (jj + 32 * ii) * D + lane;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) y[i] = fmaf(wrow[32 * i], m, y[i]);
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void warp_layer_norm(float (&y)[Feat<D>::kPerLane], const float* __restrict__ gain,
+                                                const float* __restrict__ bias, float eps, int lane) {
+  constexpr int DPL = Feat<D>::kPerLane;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) s += Feat<D>::has(lane, i) ? y[i] : 0.f;
+  const float mean = warp_sum(s) * (1.0f / D);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) { const float c = Feat<D>::has(lane, i) ? y[i] - mean : 0.f; v = fmaf(c, c, v); }
+  const float inv = 1.0f / sqrtf(warp_sum(v) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < DPL; ++i)
+    if (Feat<D>::has(lane, i)) y[i] = (y[i] - mean) * inv * __ldg(gain + lane + 32 * i) + __ldg(bias + lane + 32 * i);
+}
+
 // ---- strided q/k/v view ------------------------------------------------------------------------
 struct View {
   const void* ptr;

@@ -14,46 +14,12 @@ namespace eva {
 // ------------------------------------------------------------------------------------------------
 // Stage A: one warp per (batch, head, chunk).  Lane l owns features l, l+32, ...
 // ------------------------------------------------------------------------------------------------
-template <int DPL>
-__device__ __forceinline__ void warp_linear(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                            const float (&x)[DPL], float (&y)[DPL], int lane) {
-  constexpr int D = 32 * DPL;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) y[i] = bias ? __ldg(bias + lane + 32 * i) : 0.f;
-#pragma unroll
-  for (int ii = 0; ii < DPL; ++ii) {
-#pragma unroll 8
-    for (int jj = 0; jj < 32; ++jj) {
-      const float m = __shfl_sync(0xffffffffu, x[ii], jj);
-      const float* wrow = Wt + (jj + 32 * ii) * D + lane;
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) y[i] = fmaf(wrow[32 * i], m, y[i]);
-    }
-  }
-}
-
-template <int DPL>
-__device__ __forceinline__ void warp_layer_norm(float (&y)[DPL], const float* __restrict__ gain,
-                                                const float* __restrict__ bias, float eps, int lane) {
-  constexpr int D = 32 * DPL;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) s += y[i];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float v = 0.f;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) { const float c = y[i] - mean; v = fmaf(c, c, v); }
-  const float inv = 1.0f / sqrtf(warp_sum(v) * (1.0f / D) + eps);
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) y[i] = (y[i] - mean) * inv * __ldg(gain + lane + 32 * i) + __ldg(bias + lane + 32 * i);
-}
-
-template <typename T, int DPL>
+template <typename T, int D>
 __global__ void __launch_bounds__(256)
 chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
                    const EvaAdaptive ada, const float* __restrict__ noise, float* __restrict__ kbar_out,
                    float* __restrict__ beta_out) {
-  constexpr int D = 32 * DPL;
+  constexpr int DPL = Feat<D>::kPerLane;
   extern __shared__ float sm[];
   float* WtK = sm;
   float* WtQ = sm + D * D;
@@ -81,17 +47,18 @@ chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const 
       const T* qr = q.row<T>(b, tok, h);
       const T* kr = k.row<T>(b, tok, h);
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) { sq[i] += to_f32(qr[lane + 32 * i]); sk[i] += to_f32(kr[lane + 32 * i]); }
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) { sq[i] += to_f32(qr[lane + 32 * i]); sk[i] += to_f32(kr[lane + 32 * i]); }
     }
 #pragma unroll
     for (int i = 0; i < DPL; ++i) { sq[i] *= inv_cnt; sk[i] *= inv_cnt; }
     float kb[DPL], om[DPL];
-    warp_linear<DPL>(WtK, ada.b_k, sk, kb, lane);
-    if (ada.ln_gain_k) warp_layer_norm<DPL>(kb, ada.ln_gain_k, ada.ln_bias_k, ada.ln_eps, lane);
+    warp_linear<D>(WtK, ada.b_k, sk, kb, lane);
+    if (ada.ln_gain_k) warp_layer_norm<D>(kb, ada.ln_gain_k, ada.ln_bias_k, ada.ln_eps, lane);
     if (ada.w_q) {
       float qb[DPL];
-      warp_linear<DPL>(WtQ, ada.b_q, sq, qb, lane);
-      if (ada.ln_gain_q) warp_layer_norm<DPL>(qb, ada.ln_gain_q, ada.ln_bias_q, ada.ln_eps, lane);
+      warp_linear<D>(WtQ, ada.b_q, sq, qb, lane);
+      if (ada.ln_gain_q) warp_layer_norm<D>(qb, ada.ln_gain_q, ada.ln_bias_q, ada.ln_eps, lane);
 #pragma unroll
       for (int i = 0; i < DPL; ++i) om[i] = ada.mu_coeff * (qb[i] + kb[i]);
     } else {
@@ -101,6 +68,7 @@ chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const 
     const long long obase = wg * D;
 #pragma unroll
     for (int i = 0; i < DPL; ++i) {
+      if (!Feat<D>::has(lane, i)) continue;
       if (noise) om[i] += __ldg(noise + obase + lane + 32 * i);
       kbar_out[obase + lane + 32 * i] = kb[i];
     }
@@ -120,6 +88,7 @@ chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const 
         float part = 0.f;
 #pragma unroll
         for (int i = 0; i < DPL; ++i) {
+          if (!Feat<D>::has(lane, i)) continue;
           const float kk = to_f32(kr[lane + 32 * i]);
           part = fmaf(kk, om[i] - 0.5f * kk, part);
           vv[i] = to_f32(vr[lane + 32 * i]);
@@ -135,7 +104,8 @@ chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const 
     }
     const float inv_l = 1.0f / l;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) beta_out[obase + lane + 32 * i] = acc[i] * inv_l;
+    for (int i = 0; i < DPL; ++i)
+      if (Feat<D>::has(lane, i)) beta_out[obase + lane + 32 * i] = acc[i] * inv_l;
   }
 }
 
@@ -147,12 +117,12 @@ constexpr int kRows = 16;   // query rows per CTA (4 per warp)
 constexpr int kRpw = 4;
 constexpr int kKt = 32;     // keys per tile
 
-template <typename T, int DPL>
+template <typename T, int D>
 __global__ void __launch_bounds__(128)
 window_attn_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
                    const float* __restrict__ kbar, const float* __restrict__ beta,
                    const float* __restrict__ bias, const long long bias_sh, T* __restrict__ out) {
-  constexpr int D = 32 * DPL;
+  constexpr int DPL = Feat<D>::kPerLane;
   constexpr int DP = D + 1;
   extern __shared__ float sm[];
   float* Qs = sm;                       // [kRows][D], pre-scaled
@@ -276,7 +246,7 @@ window_attn_kernel(const Geo g, const View q, const View k, const View v, const 
     for (int j = 0; j < kKt; ++j) {
       float vv[DPL];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) vv[i] = Vs[j * DP + lane + 32 * i];
+      for (int i = 0; i < DPL; ++i) vv[i] = Feat<D>::has(lane, i) ? Vs[j * DP + lane + 32 * i] : 0.f;
 #pragma unroll
       for (int r = 0; r < kRpw; ++r) {
         const float p = prow[r * kKt + j];
@@ -294,20 +264,21 @@ window_attn_kernel(const Geo g, const View q, const View k, const View v, const 
     const float inv = 1.0f / l[r];
     T* orow = out + ((long long)b * g.N + tq) * ((long long)g.H * D) + (long long)h * D;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) orow[lane + 32 * i] = from_f32<T>(o[r][i] * inv);
+    for (int i = 0; i < DPL; ++i)
+      if (Feat<D>::has(lane, i)) orow[lane + 32 * i] = from_f32<T>(o[r][i] * inv);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-template <typename T, int DPL>
+template <typename T, int D>
 static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View& k, const View& v,
                                         const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
                                         float* kbar, float* beta, cudaStream_t st) {
-  constexpr int D = 32 * DPL;
+  constexpr int DPL = Feat<D>::kPerLane;
   const size_t smem = 2 * (size_t)D * D * sizeof(float);
-  auto kern = chunk_stats_kernel<T, DPL>;
+  auto kern = chunk_stats_kernel<T, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long total = (long long)g.B * g.H * g.n_chunks;
@@ -318,14 +289,14 @@ static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View&
   return cudaGetLastError();
 }
 
-template <typename T, int DPL>
+template <typename T, int D>
 static cudaError_t launch_window_attn_t(const Geo& g, const View& q, const View& k, const View& v,
                                         const uint8_t* mask, const float* kbar, const float* beta,
                                         const float* bias, long long bias_sh, void* out, cudaStream_t st) {
-  constexpr int D = 32 * DPL;
+  constexpr int DPL = Feat<D>::kPerLane;
   const size_t smem = (size_t)(kRows * D + 2 * kKt * (D + 1) + 4 * kRpw * kKt) * sizeof(float) +
                       (size_t)(kKt + 2 * kRows) * sizeof(int);
-  auto kern = window_attn_kernel<T, DPL>;
+  auto kern = window_attn_kernel<T, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((g.L + kRows - 1) / kRows, g.n_windows, g.B * g.H);
@@ -334,16 +305,19 @@ static cudaError_t launch_window_attn_t(const Geo& g, const View& q, const View&
 }
 
 #define EVA_DISPATCH(FN, ...)                                                             \
-  switch (io_dtype * 8 + g.D / 32) {                                                      \
-    case EVA_F32 * 8 + 1: return FN<float, 1>(__VA_ARGS__);                               \
-    case EVA_F32 * 8 + 2: return FN<float, 2>(__VA_ARGS__);                               \
-    case EVA_F32 * 8 + 4: return FN<float, 4>(__VA_ARGS__);                               \
-    case EVA_F16 * 8 + 1: return FN<__half, 1>(__VA_ARGS__);                              \
-    case EVA_F16 * 8 + 2: return FN<__half, 2>(__VA_ARGS__);                              \
-    case EVA_F16 * 8 + 4: return FN<__half, 4>(__VA_ARGS__);                              \
-    case EVA_BF16 * 8 + 1: return FN<__nv_bfloat16, 1>(__VA_ARGS__);                      \
-    case EVA_BF16 * 8 + 2: return FN<__nv_bfloat16, 2>(__VA_ARGS__);                      \
-    case EVA_BF16 * 8 + 4: return FN<__nv_bfloat16, 4>(__VA_ARGS__);                      \
+  switch (io_dtype * 256 + g.D) {                                                         \
+    case EVA_F32 * 256 + 16: return FN<float, 16>(__VA_ARGS__);                           \
+    case EVA_F32 * 256 + 32: return FN<float, 32>(__VA_ARGS__);                           \
+    case EVA_F32 * 256 + 64: return FN<float, 64>(__VA_ARGS__);                           \
+    case EVA_F32 * 256 + 128: return FN<float, 128>(__VA_ARGS__);                         \
+    case EVA_F16 * 256 + 16: return FN<__half, 16>(__VA_ARGS__);                          \
+    case EVA_F16 * 256 + 32: return FN<__half, 32>(__VA_ARGS__);                          \
+    case EVA_F16 * 256 + 64: return FN<__half, 64>(__VA_ARGS__);                          \
+    case EVA_F16 * 256 + 128: return FN<__half, 128>(__VA_ARGS__);                        \
+    case EVA_BF16 * 256 + 16: return FN<__nv_bfloat16, 16>(__VA_ARGS__);                  \
+    case EVA_BF16 * 256 + 32: return FN<__nv_bfloat16, 32>(__VA_ARGS__);                  \
+    case EVA_BF16 * 256 + 64: return FN<__nv_bfloat16, 64>(__VA_ARGS__);                  \
+    case EVA_BF16 * 256 + 128: return FN<__nv_bfloat16, 128>(__VA_ARGS__);                \
     default: return cudaErrorInvalidValue;                                                \
   }
 
@@ -356,7 +330,6 @@ cudaError_t launch_chunk_stats(const Geo& g, int io_dtype, const View& q, const 
 cudaError_t launch_window_attn(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                                const uint8_t* mask, const float* kbar, const float* beta,
                                const float* bias, long long bias_sh, void* out, cudaStream_t st) {
-  if (g.D / 32 != 1 && g.D / 32 != 2 && g.D / 32 != 4) return cudaErrorInvalidValue;
   EVA_DISPATCH(launch_window_attn_t, g, q, k, v, mask, kbar, beta, bias, bias_sh, out, st)
 }
 

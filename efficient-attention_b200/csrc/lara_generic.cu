@@ -40,47 +40,22 @@ __device__ __forceinline__ void bin_of(int i, int n_in, int n_out, int& lo, int&
   hi = ((i + 1) * n_in + n_out - 1) / n_out;
 }
 
-template <int DPL>
+template <int D>
 __device__ __forceinline__ void warp_linear_ln(const float* Wt, const EvaAdaptive& p, bool q_side,
-                                               const float (&x)[DPL], float (&y)[DPL], int lane) {
-  constexpr int D = 32 * DPL;
-  const float* bias = q_side ? p.b_q : p.b_k;
-#pragma unroll
-  for (int i = 0; i < DPL; ++i) y[i] = bias ? __ldg(bias + lane + 32 * i) : 0.f;
-#pragma unroll
-  for (int ii = 0; ii < DPL; ++ii) {
-#pragma unroll 8
-    for (int jj = 0; jj < 32; ++jj) {
-      const float m = __shfl_sync(0xffffffffu, x[ii], jj);
-      const float* wrow = Wt + (jj + 32 * ii) * D + lane;
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) y[i] = fmaf(wrow[32 * i], m, y[i]);
-    }
-  }
+                                               const float (&x)[Feat<D>::kPerLane], float (&y)[Feat<D>::kPerLane], int lane) {
+  warp_linear<D>(Wt, q_side ? p.b_q : p.b_k, x, y, lane);
   const float* gain = q_side ? p.ln_gain_q : p.ln_gain_k;
-  const float* lb = q_side ? p.ln_bias_q : p.ln_bias_k;
-  if (gain) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) s += y[i];
-    const float mean = warp_sum(s) * (1.0f / D);
-    float v = 0.f;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) { const float c = y[i] - mean; v = fmaf(c, c, v); }
-    const float inv = 1.0f / sqrtf(warp_sum(v) * (1.0f / D) + p.ln_eps);
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) y[i] = (y[i] - mean) * inv * __ldg(gain + lane + 32 * i) + __ldg(lb + lane + 32 * i);
-  }
+  if (gain) warp_layer_norm<D>(y, gain, q_side ? p.ln_bias_q : p.ln_bias_k, p.ln_eps, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
 // L1: landmarks + proposal statistics.  One CTA per (batch, head).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int DPL>
+template <typename T, int D>
 __global__ void __launch_bounds__(256)
 lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
                      const EvaAdaptive proj, const float* __restrict__ noise, float* __restrict__ ws_base) {
-  constexpr int D = 32 * DPL, DP = D + 1;
+  constexpr int DPL = Feat<D>::kPerLane, DP = D + 1;
   extern __shared__ float sm[];
   const int C = g.C, S = g.S;
   float* qb = sm;                  // [C][DP]  q landmarks, later mu
@@ -132,10 +107,10 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
           const bool zero = g.zero_padded && mask && mask[(long long)b * g.N + tok];
           const T* r = src.row<T>(b, tok, h);
 #pragma unroll
-          for (int i = 0; i < DPL; ++i) xv[i] = zero ? 0.f : to_f32(r[lane + 32 * i]);
+          for (int i = 0; i < DPL; ++i) xv[i] = (zero || !Feat<D>::has(lane, i)) ? 0.f : to_f32(r[lane + 32 * i]);
           if (per_tok) {
             float yv[DPL];
-            warp_linear_ln<DPL>(Wt, proj, side == 0, xv, yv, lane);
+            warp_linear_ln<D>(Wt, proj, side == 0, xv, yv, lane);
 #pragma unroll
             for (int i = 0; i < DPL; ++i) acc[i] += yv[i];
           } else {
@@ -149,12 +124,13 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
       for (int i = 0; i < DPL; ++i) mean[i] = acc[i] * inv;
       if (has_proj && !g.per_token_proj && side < 2 && g.dims == 2) {
         float yv[DPL];
-        warp_linear_ln<DPL>(Wt, proj, side == 0, mean, yv, lane);
+        warp_linear_ln<D>(Wt, proj, side == 0, mean, yv, lane);
 #pragma unroll
         for (int i = 0; i < DPL; ++i) mean[i] = yv[i];
       }
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) dst[c * DP + lane + 32 * i] = mean[i];
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) dst[c * DP + lane + 32 * i] = mean[i];
     }
   }
   __syncthreads();
@@ -185,6 +161,7 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
       const float inv = 1.0f / sum;
 #pragma unroll
       for (int i = 0; i < DPL; ++i) {
+        if (!Feat<D>::has(lane, i)) continue;
         float a = 0.f;
         for (int c = 0; c < C; ++c) a = fmaf(pr[c], kb[c * DP + lane + 32 * i], a);
         kb2[p * DP + lane + 32 * i] = a * inv;
@@ -257,11 +234,11 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
 // L2: rows x all tokens with online softmax.  blockIdx.x < kv_blocks: rows = omega samples, keys = k,
 // values = v  -> kv[s], lse_k[s].  Otherwise (mis-opt): rows = q_bar landmarks, keys = q -> lse_t[c].
 // ------------------------------------------------------------------------------------------------
-template <typename T, int DPL>
+template <typename T, int D>
 __global__ void __launch_bounds__(128)
 lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
                   float* __restrict__ ws_base, const int kv_blocks) {
-  constexpr int D = 32 * DPL, DP = D + 1;
+  constexpr int DPL = Feat<D>::kPerLane, DP = D + 1;
   constexpr int ROWS = 16, RPW = 4, KT = 32;
   extern __shared__ float sm[];
   float* Rs = sm;                 // [ROWS][D]
@@ -349,7 +326,7 @@ lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, con
       for (int j = 0; j < KT; ++j) {
         float vv[DPL];
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) vv[i] = Vs[j * DP + lane + 32 * i];
+        for (int i = 0; i < DPL; ++i) vv[i] = Feat<D>::has(lane, i) ? Vs[j * DP + lane + 32 * i] : 0.f;
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
           const float p = prow[r * KT + j];
@@ -368,7 +345,8 @@ lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, con
     if (kv_mode) {
       const float inv = 1.0f / l[r];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) ws.kv[(long long)row * D + lane + 32 * i] = o[r][i] * inv;
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) ws.kv[(long long)row * D + lane + 32 * i] = o[r][i] * inv;
       if (lane == 0) ws.lse_k[row] = lse;
     } else if (lane == 0) {
       ws.lse_t[row] = lse;
@@ -381,11 +359,11 @@ lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, con
 // ------------------------------------------------------------------------------------------------
 constexpr int kLaraTokPerCta = 64;
 
-template <typename T, int DPL>
+template <typename T, int D>
 __global__ void __launch_bounds__(256)
 lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask, const float* __restrict__ ws_base,
                 T* __restrict__ out) {
-  constexpr int D = 32 * DPL, DP = D + 1;
+  constexpr int DPL = Feat<D>::kPerLane, DP = D + 1;
   extern __shared__ float sm[];
   const int C = g.C, S = g.S;
   float* om = sm;               // [S][DP]
@@ -421,6 +399,7 @@ lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask,
     float n2 = 0.f;
 #pragma unroll
     for (int i = 0; i < DPL; ++i) {
+      if (!Feat<D>::has(lane, i)) continue;
       const float x = zero ? 0.f : to_f32(qr[lane + 32 * i]);
       myq[lane + 32 * i] = x;
       n2 = fmaf(x, x, n2);
@@ -469,11 +448,13 @@ lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask,
     for (int s = 0; s < S; ++s) {
       const float w = myw[s];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) o[i] = fmaf(w, kvs[s * DP + lane + 32 * i], o[i]);
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) o[i] = fmaf(w, kvs[s * DP + lane + 32 * i], o[i]);
     }
     T* orow = out + ((long long)b * g.N + tok) * ((long long)g.H * D) + (long long)h * D;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) orow[lane + 32 * i] = from_f32<T>(o[i] * inv);
+    for (int i = 0; i < DPL; ++i)
+      if (Feat<D>::has(lane, i)) orow[lane + 32 * i] = from_f32<T>(o[i] * inv);
     __syncwarp();
   }
 }
@@ -493,23 +474,22 @@ size_t lara_workspace_bytes(const LaraGeo& g) {
   return (((size_t)g.B * g.H * per * sizeof(float)) + 255) & ~(size_t)255;
 }
 
-template <typename T, int DPL>
+template <typename T, int D>
 static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k, const View& v, const uint8_t* mask,
                                  const EvaAdaptive& proj, const float* noise, void* out, void* workspace,
                                  cudaStream_t st) {
-  constexpr int D = 32 * DPL;
   float* ws = reinterpret_cast<float*>(workspace);
   const size_t sm1 = landmark_smem(g), sm3 = out_smem(g);
   if (sm1 > 227 * 1024 || sm3 > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   {
-    auto kern = lara_landmark_kernel<T, DPL>;
+    auto kern = lara_landmark_kernel<T, D>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
     kern<<<g.B * g.H, 256, sm1, st>>>(g, q, k, v, mask, proj, noise, ws);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    auto kern = lara_stats_kernel<T, DPL>;
+    auto kern = lara_stats_kernel<T, D>;
     const size_t sm2 = (size_t)(16 * D + 2 * 32 * (D + 1) + 4 * 4 * 32) * sizeof(float) + 32 * sizeof(int);
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)) != cudaSuccess) return e;
     const int kv_blocks = (g.S + 15) / 16;
@@ -519,7 +499,7 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    auto kern = lara_out_kernel<T, DPL>;
+    auto kern = lara_out_kernel<T, D>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
     dim3 grid((g.N + kLaraTokPerCta - 1) / kLaraTokPerCta, 1, g.B * g.H);
     kern<<<grid, 256, sm3, st>>>(g, q, mask, ws, reinterpret_cast<T*>(out));
@@ -531,16 +511,19 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
 cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
                         const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
                         void* workspace, cudaStream_t st) {
-  switch (io_dtype * 8 + g.D / 32) {
-    case EVA_F32 * 8 + 1: return launch_lara_t<float, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F32 * 8 + 2: return launch_lara_t<float, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F32 * 8 + 4: return launch_lara_t<float, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 8 + 1: return launch_lara_t<__half, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 8 + 2: return launch_lara_t<__half, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 8 + 4: return launch_lara_t<__half, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 8 + 1: return launch_lara_t<__nv_bfloat16, 1>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 8 + 2: return launch_lara_t<__nv_bfloat16, 2>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 8 + 4: return launch_lara_t<__nv_bfloat16, 4>(g, q, k, v, mask, proj, noise, out, workspace, st);
+  switch (io_dtype * 256 + g.D) {
+    case EVA_F32 * 256 + 16: return launch_lara_t<float, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 256 + 32: return launch_lara_t<float, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 256 + 64: return launch_lara_t<float, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 256 + 128: return launch_lara_t<float, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 256 + 16: return launch_lara_t<__half, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 256 + 32: return launch_lara_t<__half, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 256 + 64: return launch_lara_t<__half, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F16 * 256 + 128: return launch_lara_t<__half, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 256 + 16: return launch_lara_t<__nv_bfloat16, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 256 + 32: return launch_lara_t<__nv_bfloat16, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 256 + 64: return launch_lara_t<__nv_bfloat16, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_BF16 * 256 + 128: return launch_lara_t<__nv_bfloat16, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
     default: return cudaErrorInvalidValue;
   }
 }
