@@ -254,7 +254,7 @@ def run_ours(args):
             'e2e': {'value': tokens_per_step * Ke / (e2e_ms * 1e-3), 'unit': 'tokens/s',
                     'h2d_bytes_per_step': x_host.numel() * elem, 'd2h_bytes_per_step': y_host.numel() * elem,
                     'steps': Ke, 'what': 'EVA.forward(x): H2D x, qkv Linear, attention core, proj Linear, D2H y'},
-            'gpu_launches': K * (1 if path == 1 else 2),
+            'gpu_launches': K * 2,  # fused: weight-pack + fused kernel; generic: chunk_stats + window_attn
             'clocks': clk.summary(),
         }
         if world == 1 and not args.no_cpu:

@@ -1,19 +1,21 @@
-// Fused EVA forward for sm_100a: one persistent kernel does, per (batch, head) work item,
-//   phase A  chunk pooling -> adaptive Linear (tcgen05.mma) -> LayerNorm -> k_bar, omega -> beta     (eva.py:155-196)
-//   phase B  per pair of windows: S = Q [K_w ; k_bar]^T (tcgen05.mma, operands landed by TMA),
-//            joint row softmax in registers (TMEM -> RF), P back to TMEM, O = P [V_w ; beta] (tcgen05.mma,
-//            A operand from TMEM), normalise, store                                                   (eva.py:200-227)
-// q/k/v are read from HBM once (phase A); the window tiles of phase B are TMA loads that hit L2 because
-// the same CTA just streamed that (batch, head).  Geometry: 2-D grid, no halo, head_dim 64, window w with
-// L = w*w <= 64 queries, CN <= 64 chunks, fp16 / bf16 I/O, no padding mask.
+// Fused EVA forward for sm_100a (v2): one persistent kernel; per (batch, head) work item everything runs
+// off TMA tiles and tcgen05 MMAs, the CUDA cores only do LayerNorm, |k|^2, two small softmaxes and packing.
 //
-// CTA = 6 warps: warps 0-3 compute (thread t <-> TMEM lane t <-> query row t of the pair tile),
-// warp 4 = TMA producer, warp 5 = MMA issuer.  Two CTAs are resident per SM (256 TMEM columns and
-// ~103 KB shared memory each) so that one CTA's softmax overlaps the other's loads and MMAs.
+//   pass 1   chunk means:      [feat x chunk]   = Q_r^T . Pool^T, K_r^T . Pool^T       (M=64 MMAs, A MN-major)
+//            adaptive Linear:  [chunk x feat]   = [mq ; mk] . [W_q ; W_k]^T            (M=128 MMA) -> LayerNorm
+//            -> k_bar tile, omega tile                                                  (eva.py:155-190)
+//   pass 2   phi-logits:       [token x chunk]  = K_r . Omega_r^T                      (M=128 MMA)
+//            16-token softmax per chunk (SIMT) -> P tile;  beta^T = V_r^T . P^T         (M=64 MMA)
+//            -> beta tile                                                               (eva.py:192-196)
+//   phase B  per pair of windows: S = Q [K_w ; k_bar]^T, joint row softmax (TMEM -> RF), P -> TMEM,
+//            O = P [V_w ; beta] (A operand from TMEM), normalise, store                 (eva.py:200-227)
 //
-// Pair tile (M = 128): rows 0..L-1 = window a, rows 64..64+L-1 = window b.  K/V tile (112 rows for L=49):
-// rows 0..L-1 = window a, rows LP8..LP8+L-1 = window b (LP8 = L rounded up to 8).  S columns:
-// [0,2*LP8) local logits (the off-diagonal blocks are computed and ignored), [2*LP8, 2*LP8+64) chunk logits.
+// q/k/v reach the SM only through TMA: chunk-row boxes (pass 1: q,k from HBM; pass 2: k from L2, v prefetched
+// into L2 during pass 1) and window boxes (phase B, L2 hits).  All tiles travel through one ring of four
+// 16-KB shared-memory slots with full/free mbarriers; the means tile of the Linear step borrows a ring slot.
+//
+// CTA = 6 warps: warps 0-3 compute (thread t <-> TMEM lane t), warp 4 = TMA producer, warp 5 = MMA issuer.
+// Two CTAs per SM (256 TMEM columns, ~105 KB shared memory each).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -32,16 +34,21 @@ constexpr int kD = 64;
 constexpr int kThreads = 192;
 constexpr int kComputeThreads = 128;
 constexpr uint32_t kTmemCols = 256;
+constexpr int kSlots = 4;
+constexpr int kSlotBytes = 16384;
 
-enum Bar { kQkFull = 0, kVFull, kQkFree, kVFree, kSFull, kPFull, kOFull, kOFree, kAFull, kLinFull, kStatsFull, kNumBars };
+enum Bar {
+  kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
+  kD2Full0, kD2Full1, kP2Full0, kP2Full1, kP2Free0, kP2Free1, kBetaFull, kStatsFull,
+  kSFull, kPFull, kOFull, kOFree, kNumBars
+};
 
 struct Params {
   int B, H, N, gh, gw;
   int nwx, n_windows, n_pairs;   // windows per grid row, total, pairs per item
-  int chunk, ncx, Jc;            // chunk edge, chunks per grid row, tokens per chunk
   int items;
-  View q, k, v;
-  const float *w_q, *b_q, *g_q, *beta_q, *w_k, *b_k, *g_k, *beta_k;
+  const float *b_q, *g_q, *beta_q, *b_k, *g_k, *beta_k;
+  int has_q;                     // 0: adaptive_proj == 'none' (mu = 0)
   float mu_coeff, ln_eps;
   const float* noise;
   const float* bias;
@@ -49,29 +56,42 @@ struct Params {
   void* out;
 };
 
-template <int L, int CN> struct Layout {
+template <int W, int GW, int CH, int NR> struct Cfg {
+  static constexpr int L = W * W;
   static constexpr int LP8 = (L + 7) & ~7;
-  static constexpr int LS = L | 1;  // bias row stride (odd: conflict-free across rows)
-  static constexpr int kQ = 0;                                  // [128][128 B]
-  static constexpr int kK = kQ + 128 * 128;                     // [2*LP8][128 B]
-  static constexpr int kV = kK + 2 * LP8 * 128;
-  static constexpr int kKbar = kV + 2 * LP8 * 128;              // [64][128 B]
-  static constexpr int kBeta = kKbar + 64 * 128;                // [64][128 B]
-  static constexpr int kA = kBeta + 64 * 128;                   // [128][128 B] chunk means (fp16); later omega fp32 [CN][65]
-  static constexpr int kZeroEnd = kA + 128 * 128;
-  static constexpr int kW = kZeroEnd;                           // [128][128 B] adaptive weights (fp16)
-  static constexpr int kBias = kW + 128 * 128;                  // [L][LS] fp32, pre-multiplied by log2(e)
-  static constexpr int kBars = (kBias + L * LS * 4 + 127) & ~127;
+  static constexpr int LS = L | 1;              // bias row stride (odd: conflict-free across rows)
+  static constexpr int NCX = GW / CH;           // chunks per chunk-row
+  static constexpr int CN = NR * NCX;           // chunks per item
+  static constexpr int TOK = GW * CH;           // tokens per chunk-row
+  static constexpr int KS = (TOK + 15) / 16;    // k-steps over the tokens of a chunk-row
+  static constexpr int KBLK = (TOK + 63) / 64;  // 64-token K blocks of the Pool / P2 tiles
+  static constexpr int JC = CH * CH;
+  static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOK <= 128 && L <= 64 && CN <= 64, "geometry");
+  // shared memory map (bytes from the 1024-aligned base)
+  static constexpr int kSlot = 0;
+  static constexpr int kKbar = kSlots * kSlotBytes;    // [64][128 B]  k_bar, row = chunk c
+  static constexpr int kBeta = kKbar + 8192;           // [64][128 B]  beta,  row = chunk c
+  static constexpr int kOm = kBeta + 8192;             // [64][128 B]  omega, row = 8r + cx
+  static constexpr int kPool = kOm + 8192;             // KBLK x [8][128 B] pooling weights (constant)
+  static constexpr int kP2 = kPool + KBLK * 1024;      // 2 x KBLK x [8][128 B] chunk softmax weights
+  static constexpr int kZeroEnd = kP2 + 2 * KBLK * 1024;
+  static constexpr int kBias = kZeroEnd;               // [L][LS] fp32, x log2(e)
+  static constexpr int kLbuf = (kBias + L * LS * 4 + 15) & ~15;   // 2 x [128] fp32 logit exchange
+  static constexpr int kBars = (kLbuf + 2 * 128 * 4 + 7) & ~7;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemPtr + 16;
-  static constexpr int kDynamic = kBytes + 1024;                // slack for 1024-B alignment of the base
-  static_assert(CN * 65 * 4 <= 128 * 128, "omega staging must fit in the means tile");
-  static_assert(kK % 1024 == 0 && kV % 1024 == 0 && kKbar % 1024 == 0 && kBeta % 1024 == 0 && kA % 1024 == 0 && kW % 1024 == 0,
-                "UMMA tiles must be 1024-byte aligned");
-  static_assert(2 * LP8 + 64 + 64 <= (int)kTmemCols, "TMEM column budget");
-  static_assert((2 * LP8) % 16 == 0, "local S width must be a multiple of 16");
+  static constexpr int kDynamic = kBytes + 1024;
+  static_assert(kDynamic <= 115712, "two CTAs per SM need <= 113 KB each");
+  static_assert(CN * 65 * 4 <= kSlotBytes, "k_bar staging must fit in the borrowed slot");
   // TMEM columns
+  static constexpr uint32_t cPoolQ = 0, cPoolK = 64;   // pass 1: [feat x (8r+cx)]
+  static constexpr uint32_t cLin = 0;                  // Linear: [chunk-row x 128]
+  static constexpr uint32_t cBetaT = 0;                // pass 2: [feat x (8r+cx)]
+  static constexpr uint32_t cD2 = 224;                 // pass 2: 2 x [token x 16]
   static constexpr uint32_t cSloc = 0, cSrfa = 2 * LP8, cO = 2 * LP8 + 64, cPloc = 0, cPrfa = LP8;
+  static_assert(2 * LP8 + 128 <= 256 && (2 * LP8) % 16 == 0, "TMEM budget");
+  // loads per item, in ring order
+  static constexpr int nAt = 2 * NR, nW = 2 * NR + 1, nPass2 = 2 * NR + 2, nPairs = 4 * NR + 2;
 };
 
 template <typename T> struct IoFmt;
@@ -81,6 +101,8 @@ template <> struct IoFmt<__half> {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
   }
+  static __device__ __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+  static __device__ __forceinline__ uint16_t one(float a) { return __half_as_ushort(__float2half_rn(a)); }
 };
 template <> struct IoFmt<__nv_bfloat16> {
   static constexpr uint32_t kUmma = ptx::kFmtBF16;
@@ -88,24 +110,26 @@ template <> struct IoFmt<__nv_bfloat16> {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
   }
+  static __device__ __forceinline__ float2 unpack2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+  static __device__ __forceinline__ uint16_t one(float a) { return __bfloat16_as_ushort(__float2bfloat16_rn(a)); }
 };
-__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
+__device__ __forceinline__ uint16_t f16_bits(float a) { return __half_as_ushort(__float2half_rn(a)); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// N consecutive TMEM columns -> registers, N decomposed into x16 / x1 loads (compile time)
+// N consecutive TMEM columns -> registers (x16 / x8 / x1 pieces, compile time)
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 #pragma unroll
   for (int g = 0; g < N / 16; ++g) ptx::tmem_ld16(taddr + 16 * g, r + 16 * g);
+  constexpr int done = (N / 16) * 16;
+  if constexpr ((N % 16) >= 8) ptx::tmem_ld8(taddr + done, r + done);
+  constexpr int done2 = done + (((N % 16) >= 8) ? 8 : 0);
 #pragma unroll
-  for (int j = (N / 16) * 16; j < N; ++j) ptx::tmem_ld1(taddr + j, r[j]);
+  for (int j = done2; j < N; ++j) ptx::tmem_ld1(taddr + j, r[j]);
 }
 // registers -> N consecutive TMEM columns, N a multiple of 4
 template <int N>
@@ -118,64 +142,68 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r) 
   if constexpr ((N % 8) >= 4) { ptx::tmem_st4(taddr + done, r + done); done += 4; }
 }
 
-// 16-byte store of 8 packed 16-bit values into row `row`, 16-byte chunk `chunk` of a 128-byte-swizzled tile
-__device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+// byte offset of 16-bit element (row, col) inside a [rows][64] tile with 128-byte swizzle
+__device__ __forceinline__ int tile_off(int row, int col) {
+  return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
+// byte offset of 16-bit element (row n < 8, token t) in a K-major [8][TOK] tile made of 64-token blocks
+__device__ __forceinline__ int ktile_off(int n, int t) { return (t >> 6) * 1024 + tile_off(n, t & 63); }
 
-template <typename T, int W, int CN>
+__device__ __forceinline__ uint32_t slot_of(uint32_t n) { return n & (kSlots - 1); }
+__device__ __forceinline__ uint32_t par_of(uint32_t n) { return (n >> 2) & 1u; }
+
+template <typename T, int W, int GW, int CH, int NR>
 __global__ void __launch_bounds__(kThreads, 2)
-eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, const Params p) {
-  constexpr int L = W * W;
-  using Lay = Layout<L, CN>;
-  constexpr int LP8 = Lay::LP8, LS = Lay::LS;
+eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant__ CUtensorMap tw_k,
+                 const __grid_constant__ CUtensorMap tw_v, const __grid_constant__ CUtensorMap tr_q,
+                 const __grid_constant__ CUtensorMap tr_k, const __grid_constant__ CUtensorMap tr_v,
+                 const __grid_constant__ CUtensorMap t_w, const Params p) {
+  using C = Cfg<W, GW, CH, NR>;
+  constexpr int L = C::L, LP8 = C::LP8, LS = C::LS, CN = C::CN, NCX = C::NCX, TOK = C::TOK, KS = C::KS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Qt = sm + Lay::kQ;
-  uint8_t* Kt = sm + Lay::kK;
-  uint8_t* Vt = sm + Lay::kV;
-  uint8_t* KBt = sm + Lay::kKbar;
-  uint8_t* BTt = sm + Lay::kBeta;
-  uint8_t* At = sm + Lay::kA;
-  uint8_t* Wt = sm + Lay::kW;
-  float* omega = reinterpret_cast<float*>(At);           // [CN][65], valid after the Linear MMA has consumed At
-  float* bias2 = reinterpret_cast<float*>(sm + Lay::kBias);
-  const uint32_t bars = ptx::smem_u32(sm + Lay::kBars);
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + Lay::kTmemPtr);
+  uint8_t* KBt = sm + C::kKbar;
+  uint8_t* BTt = sm + C::kBeta;
+  uint8_t* OMt = sm + C::kOm;
+  uint8_t* PoolT = sm + C::kPool;
+  uint8_t* P2t = sm + C::kP2;
+  float* bias2 = reinterpret_cast<float*>(sm + C::kBias);
+  float* lbuf = reinterpret_cast<float*>(sm + C::kLbuf);
+  const uint32_t bars = ptx::smem_u32(sm + C::kBars);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + C::kTmemPtr);
   auto bar = [&](int i) { return bars + 8u * i; };
+  auto slot_ptr = [&](uint32_t s) { return sm + C::kSlot + s * kSlotBytes; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_per_item = C::nPairs + 3 * p.n_pairs;
 
   // ---- one-time setup --------------------------------------------------------------------------
-  for (int i = tid; i < Lay::kZeroEnd / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
-  for (int idx = tid; idx < 128 * 8; idx += kThreads) {   // W tile: rows 0-63 = W_q, 64-127 = W_k, fp16
-    const int row = idx >> 3, ch = idx & 7;
-    const float* src = row < 64 ? p.w_q : p.w_k;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (src) {
-      float f[8];
-      load8<float>(src + (row & 63) * 64 + ch * 8, f);
-      v = make_uint4(pack2_f16(f[0], f[1]), pack2_f16(f[2], f[3]), pack2_f16(f[4], f[5]), pack2_f16(f[6], f[7]));
-    }
-    st_tile_chunk(Wt, row, ch, v);
-  }
+  for (int i = tid; i < C::kZeroEnd / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int t = tid; t < TOK; t += kThreads)   // Pool^T[n][t] = 1/Jc for the chunk column n that owns token t
+    *reinterpret_cast<uint16_t*>(PoolT + ktile_off((t % GW) / CH, t)) = IoFmt<T>::one(1.0f / C::JC);
   if (warp == 4 && lane == 0) {
-    ptx::mbar_init(bar(kQkFull), 1);
-    ptx::mbar_init(bar(kVFull), 1);
-    ptx::mbar_init(bar(kQkFree), 1);
-    ptx::mbar_init(bar(kVFree), 1);
+    for (int s = 0; s < kSlots; ++s) { ptx::mbar_init(bar(kFull0 + s), 1); ptx::mbar_init(bar(kFree0 + s), 1); }
+    ptx::mbar_init(bar(kPoolFull), 1);
+    ptx::mbar_init(bar(kAFull), kComputeThreads);
+    ptx::mbar_init(bar(kLinFull), 1);
+    ptx::mbar_init(bar(kOmFull), kComputeThreads);
+    ptx::mbar_init(bar(kD2Full0), 1);
+    ptx::mbar_init(bar(kD2Full1), 1);
+    ptx::mbar_init(bar(kP2Full0), kComputeThreads);
+    ptx::mbar_init(bar(kP2Full1), kComputeThreads);
+    ptx::mbar_init(bar(kP2Free0), 1);
+    ptx::mbar_init(bar(kP2Free1), 1);
+    ptx::mbar_init(bar(kBetaFull), 1);
+    ptx::mbar_init(bar(kStatsFull), kComputeThreads);
     ptx::mbar_init(bar(kSFull), 1);
     ptx::mbar_init(bar(kPFull), kComputeThreads);
     ptx::mbar_init(bar(kOFull), 1);
     ptx::mbar_init(bar(kOFree), kComputeThreads);
-    ptx::mbar_init(bar(kAFull), kComputeThreads);
-    ptx::mbar_init(bar(kLinFull), 1);
-    ptx::mbar_init(bar(kStatsFull), kComputeThreads);
     ptx::fence_mbar_init();
-    ptx::prefetch_tmap(&tm_q);
-    ptx::prefetch_tmap(&tm_k);
-    ptx::prefetch_tmap(&tm_v);
+    ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
+    ptx::prefetch_tmap(&tr_q); ptx::prefetch_tmap(&tr_k); ptx::prefetch_tmap(&tr_v);
+    ptx::prefetch_tmap(&t_w);
   }
   if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), kTmemCols);
   ptx::fence_proxy_async_smem();
@@ -187,26 +215,49 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 4) {
     // =================================== TMA producer ==========================================
     if (lane == 0) {
-      uint32_t np = 0;
+      uint32_t n = 0;
+      auto acquire = [&](uint32_t bytes) -> uint32_t {   // returns the slot; arms its full barrier
+        const uint32_t s = slot_of(n);
+        ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
+        ++n;
+        return s;
+      };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int b = item / p.H, h = item % p.H;
-        for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
+        for (int r = 0; r < NR; ++r) {                   // pass 1: q, k chunk-rows (first touch: HBM)
+          uint32_t s = acquire(TOK * 128);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          s = acquire(TOK * 128);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          ptx::tma_prefetch_5d(&tr_v, 0, h, 0, r * CH, b);   // v is first needed in pass 2: warm L2 now
+        }
+        ++n;                                             // slot borrowed by the compute warps for the means tile
+        {
+          const uint32_t s = acquire(128 * 128);
+          ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
+        }
+        for (int r = 0; r < NR; ++r) {                   // pass 2: k (L2), v (L2 after the prefetch)
+          uint32_t s = acquire(TOK * 128);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          s = acquire(TOK * 128);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b);
+        }
+        for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: window pairs (L2)
           const int w0 = 2 * pr, w1 = w0 + 1;
           const bool two = w1 < p.n_windows;
           const int x0 = (w0 % p.nwx) * W, y0 = (w0 / p.nwx) * W;
           const int x1 = (w1 % p.nwx) * W, y1 = (w1 / p.nwx) * W;
-          ptx::mbar_wait(bar(kQkFree), (np & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(bar(kQkFull), (two ? 4u : 2u) * L * 128u);
-          ptx::tma_load_5d(ptx::smem_u32(Qt), &tm_q, bar(kQkFull), 0, h, x0, y0, b);
-          ptx::tma_load_5d(ptx::smem_u32(Kt), &tm_k, bar(kQkFull), 0, h, x0, y0, b);
-          if (two) {
-            ptx::tma_load_5d(ptx::smem_u32(Qt + 64 * 128), &tm_q, bar(kQkFull), 0, h, x1, y1, b);
-            ptx::tma_load_5d(ptx::smem_u32(Kt + LP8 * 128), &tm_k, bar(kQkFull), 0, h, x1, y1, b);
-          }
-          ptx::mbar_wait(bar(kVFree), (np & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(bar(kVFull), (two ? 2u : 1u) * L * 128u);
-          ptx::tma_load_5d(ptx::smem_u32(Vt), &tm_v, bar(kVFull), 0, h, x0, y0, b);
-          if (two) ptx::tma_load_5d(ptx::smem_u32(Vt + LP8 * 128), &tm_v, bar(kVFull), 0, h, x1, y1, b);
+          const uint32_t bytes = (two ? 2u : 1u) * L * 128u;
+          uint32_t s = acquire(bytes);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b);
+          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b);
+          s = acquire(bytes);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b);
+          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b);
+          s = acquire(bytes);
+          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b);
+          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b);
         }
       }
     }
@@ -214,106 +265,167 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // =================================== MMA issuer ============================================
     if (lane == 0) {
       constexpr uint32_t fmt = IoFmt<T>::kUmma;
+      constexpr uint32_t id_pool = ptx::umma_idesc(fmt, fmt, 1, 0, 64, 8);      // A MN-major (feat), B K-major
       constexpr uint32_t id_lin = ptx::umma_idesc(ptx::kFmtF16, ptx::kFmtF16, 0, 0, 128, 128);
+      constexpr uint32_t id_d2 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 16);
       constexpr uint32_t id_sl = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 2 * LP8);
       constexpr uint32_t id_sr = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
       constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
-      const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(Qt)), dK = ptx::umma_desc_sw128(ptx::smem_u32(Kt));
-      const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(Vt)), dKB = ptx::umma_desc_sw128(ptx::smem_u32(KBt));
-      const uint64_t dBT = ptx::umma_desc_sw128(ptx::smem_u32(BTt)), dA = ptx::umma_desc_sw128(ptx::smem_u32(At));
-      const uint64_t dW = ptx::umma_desc_sw128(ptx::smem_u32(Wt));
-      uint32_t ni = 0, np = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni) {
-        // adaptive Linear for all chunks at once: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used)
-        ptx::mbar_wait(bar(kAFull), ni & 1);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem, dA + 2 * ks, dW + 2 * ks, id_lin, ks > 0);
-        ptx::umma_commit(bar(kLinFull));
-        ptx::mbar_wait(bar(kStatsFull), ni & 1);
-        ptx::tc_fence_after();
-        for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
-          ptx::mbar_wait(bar(kQkFull), np & 1);
+      const uint64_t dSlot0 = ptx::umma_desc_sw128(ptx::smem_u32(slot_ptr(0)));
+      auto dSlot = [&](uint32_t s) { return dSlot0 + (uint64_t)(s * (kSlotBytes >> 4)); };
+      const uint64_t dKB = ptx::umma_desc_sw128(ptx::smem_u32(KBt)), dBT = ptx::umma_desc_sw128(ptx::smem_u32(BTt));
+      const uint64_t dOM = ptx::umma_desc_sw128(ptx::smem_u32(OMt)), dPool = ptx::umma_desc_sw128(ptx::smem_u32(PoolT));
+      const uint64_t dP2 = ptx::umma_desc_sw128(ptx::smem_u32(P2t));
+      // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
+      auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
+      uint32_t nb = 0, ni = 0, np = 0, par_p2 = 0;   // par_p2: bit b = parity of the next P2Full[b] wait
+      auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); };
+      auto free_slot = [&](uint32_t n) { ptx::umma_commit(bar(kFree0 + slot_of(n))); };
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
+        // ---- pass 1: chunk means ------------------------------------------------------------
+        for (int r = 0; r < NR; ++r) {
+          const uint32_t nq = nb + 2 * r, nk = nq + 1;
+          wait_full(nq);
+          wait_full(nk);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + Lay::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+          for (int ks = 0; ks < KS; ++ks)
+            ptx::umma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + Lay::cSrfa, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
+          for (int ks = 0; ks < KS; ++ks)
+            ptx::umma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+          free_slot(nq);
+          free_slot(nk);
+        }
+        ptx::umma_commit(bar(kPoolFull));
+        // ---- adaptive Linear: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used) ----------
+        ptx::mbar_wait(bar(kAFull), ni & 1);
+        // the borrowed slot was filled by the compute warps, not by TMA: complete its `full` phase by hand
+        // so that the slot's phase count keeps matching the ring counter
+        ptx::mbar_arrive(bar(kFull0 + slot_of(nb + C::nAt)));
+        wait_full(nb + C::nW);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
+        ptx::umma_commit(bar(kLinFull));
+        free_slot(nb + C::nW);
+        ptx::mbar_wait(bar(kOmFull), ni & 1);      // omega / k_bar tiles written, staging in the borrowed slot dead
+        free_slot(nb + C::nAt);
+        ptx::tc_fence_after();
+        // ---- pass 2: logits one row ahead of beta ------------------------------------------------
+        auto issue_d2 = [&](int r) {
+          const uint32_t nk = nb + C::nPass2 + 2 * r;
+          wait_full(nk);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_ss(tmem + C::cD2 + 16 * (r & 1), dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
+          ptx::umma_commit(bar(kD2Full0 + (r & 1)));
+        };
+        issue_d2(0);
+        for (int r = 0; r < NR; ++r) {
+          if (r + 1 < NR) issue_d2(r + 1);
+          const uint32_t nk = nb + C::nPass2 + 2 * r, nv = nk + 1;
+          ptx::mbar_wait(bar(kP2Full0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
+          par_p2 ^= 1u << (r & 1);
+          wait_full(nv);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+            ptx::umma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
+                         dP2 + (uint64_t)((r & 1) * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
+          ptx::umma_commit(bar(kP2Free0 + (r & 1)));
+          free_slot(nk);
+          free_slot(nv);
+        }
+        ptx::umma_commit(bar(kBetaFull));
+        ptx::mbar_wait(bar(kStatsFull), ni & 1);
+        ptx::tc_fence_after();
+        // ---- phase B --------------------------------------------------------------------------------
+        for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
+          const uint32_t nq = nb + C::nPairs + 3 * pr, nk = nq + 1, nv = nq + 2;
+          wait_full(nq);
+          wait_full(nk);
+          ptx::tc_fence_after();
+          const uint64_t dQ = dSlot(slot_of(nq)), dK = dSlot(slot_of(nk)), dV = dSlot(slot_of(nv));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + C::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + C::cSrfa, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
           ptx::umma_commit(bar(kSFull));
-          ptx::umma_commit(bar(kQkFree));
+          free_slot(nq);
+          free_slot(nk);
           ptx::mbar_wait(bar(kPFull), np & 1);
-          ptx::mbar_wait(bar(kVFull), np & 1);
+          wait_full(nv);
           ptx::mbar_wait(bar(kOFree), (np & 1) ^ 1);
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2 * LP8 / 16; ++ks)
-            ptx::umma_ts(tmem + Lay::cO, tmem + Lay::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+            ptx::umma_ts(tmem + C::cO, tmem + C::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_ts(tmem + Lay::cO, tmem + Lay::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
+            ptx::umma_ts(tmem + C::cO, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
           ptx::umma_commit(bar(kOFull));
-          ptx::umma_commit(bar(kVFree));
+          free_slot(nv);
         }
       }
     }
   } else {
     // =================================== compute warps ==========================================
-    const int ws = tid >> 6;           // which window of the pair this row belongs to (warp-uniform)
-    const int i = tid & 63;            // query slot inside the window (valid if < L)
-    const int ic = i < L ? i : L - 1;  // clamped, for shared-memory reads of idle rows
+    const int ws = tid >> 6;           // phase B: which window of the pair this row belongs to (warp-uniform)
+    const int i = tid & 63;            // phase B: query slot inside the window (valid if < L)
+    const int ic = i < L ? i : L - 1;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const int oct = lane & 7, slot = lane >> 3;
-    const float scale = 0.125f;                      // head_dim 64
+    const float scale = 0.125f;        // head_dim 64
     const float scale_log2 = scale * kLog2e;
-    const float inv_cnt = 1.0f / (float)p.Jc;
     T* const out = reinterpret_cast<T*>(p.out);
-    uint32_t ni = 0, np = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni) {
+    // pass 1 / beta readback: lanes 0-15 of each warp hold feature 16*warp + lane of an M=64 accumulator
+    const int feat = 16 * warp + (lane & 15);
+    const bool feat_lane = lane < 16;
+    // pass 2: token of the chunk-row owned by this thread
+    const int tcx = (tid % GW) / CH;
+    const bool tok_ok = tid < TOK;
+    uint32_t nb = 0, ni = 0, np = 0, par_d2 = 0, par_p2f = 3;   // bit b = parity of the next wait on buffer b
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
       const int b = item / p.H, h = item % p.H;
       // ---- per-head bias table (x log2 e) ------------------------------------------------------
       for (int idx = tid; idx < L * L; idx += kComputeThreads) {
         const int r = idx / L, c = idx % L;
         bias2[r * LS + c] = p.bias ? __ldg(p.bias + (long long)h * p.bias_sh + idx) * kLog2e : 0.f;
       }
-      // ---- A1: chunk means of q and k -> fp16 tile rows c (q) and 64+c (k) ----------------------
-      for (int c = warp; c < CN; c += 4) {
-        const int ty0 = (c / p.ncx) * p.chunk, tx0 = (c % p.ncx) * p.chunk;
-        float aq[8], ak[8];
+      // ---- pass 1 readback: means^T (TMEM) -> fp16 means tile [chunk][feat] in the borrowed slot -----
+      const uint32_t nat = nb + C::nAt;
+      uint8_t* At = slot_ptr(slot_of(nat));
+      float* stage = reinterpret_cast<float*>(At);    // [CN][65] fp32 k_bar, valid after the Linear MMA
+      ptx::mbar_wait(bar(kFree0 + slot_of(nat)), par_of(nat) ^ 1);
+      ptx::mbar_wait(bar(kPoolFull), ni & 1);
+      ptx::tc_fence_after();
+      {
+        float mq[8 * NR], mk[8 * NR];
+        tmem_ld_cols<8 * NR>(trow + C::cPoolQ, reinterpret_cast<uint32_t*>(mq));
+        tmem_ld_cols<8 * NR>(trow + C::cPoolK, reinterpret_cast<uint32_t*>(mk));
+        ptx::tmem_ld_wait();
+        if (feat_lane) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) aq[e] = ak[e] = 0.f;
-        for (int t0 = 0; t0 < p.Jc; t0 += 4) {
-          const int t = t0 + slot;
-          if (t < p.Jc) {
-            const int tok = (ty0 + t / p.chunk) * p.gw + tx0 + t % p.chunk;
-            float fq[8], fk[8];
-            load8<T>(p.q.row<T>(b, tok, h) + oct * 8, fq);
-            load8<T>(p.k.row<T>(b, tok, h) + oct * 8, fk);
+          for (int r = 0; r < NR; ++r)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { aq[e] += fq[e]; ak[e] += fk[e]; }
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], 8);
-          aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], 16);
-          ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 8);
-          ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], 16);
-          aq[e] *= inv_cnt;
-          ak[e] *= inv_cnt;
-        }
-        if (slot == 0) {
-          st_tile_chunk(At, c, oct, make_uint4(pack2_f16(aq[0], aq[1]), pack2_f16(aq[2], aq[3]), pack2_f16(aq[4], aq[5]), pack2_f16(aq[6], aq[7])));
-          st_tile_chunk(At, 64 + c, oct, make_uint4(pack2_f16(ak[0], ak[1]), pack2_f16(ak[2], ak[3]), pack2_f16(ak[4], ak[5]), pack2_f16(ak[6], ak[7])));
+            for (int cx = 0; cx < NCX; ++cx) {
+              const int c = r * NCX + cx;
+              *reinterpret_cast<uint16_t*>(At + tile_off(c, feat)) = f16_bits(mq[8 * r + cx]);
+              *reinterpret_cast<uint16_t*>(At + tile_off(64 + c, feat)) = f16_bits(mk[8 * r + cx]);
+            }
         }
       }
       ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kAFull));
       // ---- Linear result -> bias, LayerNorm; rows 0-63 = q side, rows 64-127 = k side ------------
       ptx::mbar_wait(bar(kLinFull), ni & 1);
       ptx::tc_fence_after();
       {
         float y[64];
-        tmem_ld_cols<64>(trow + (ws ? 64u : 0u), reinterpret_cast<uint32_t*>(y));
+        tmem_ld_cols<64>(trow + C::cLin + (ws ? 64u : 0u), reinterpret_cast<uint32_t*>(y));
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         const float* lb = ws ? p.b_k : p.b_q;
@@ -339,78 +451,92 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (ws == 1 && valid) {   // k side: k_bar tile (B operand of the chunk logits) + fp32 copy for mu
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            st_tile_chunk(KBt, i, ch, make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
-                                                  IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7])));
+            *reinterpret_cast<uint4*>(KBt + i * 128 + ((ch ^ (i & 7)) << 4)) =
+                make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
+                           IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7]));
 #pragma unroll
-          for (int e = 0; e < 64; ++e) omega[i * 65 + e] = y[e];
+          for (int e = 0; e < 64; ++e) stage[i * 65 + e] = y[e];
         }
         ptx::named_bar_sync(1, kComputeThreads);
-        if (ws == 0 && valid) {   // q side: omega = mu_coeff (q_bar + k_bar) [+ noise]   (eva.py:182-190)
+        if (ws == 0 && valid) {   // q side: omega = mu_coeff (q_bar + k_bar) [+ noise] -> omega tile row 8r+cx
           const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * CN + i) * 64 : nullptr;
+          const int orow = 8 * (i / NCX) + i % NCX;
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            float o = p.w_q ? p.mu_coeff * (y[e] + omega[i * 65 + e]) : 0.f;
-            if (nz) o += __ldg(nz + e);
-            omega[i * 65 + e] = o;
+          for (int ch = 0; ch < 8; ++ch) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              o[e] = p.has_q ? p.mu_coeff * (y[8 * ch + e] + stage[i * 65 + 8 * ch + e]) : 0.f;
+              if (nz) o[e] += __ldg(nz + 8 * ch + e);
+            }
+            *reinterpret_cast<uint4*>(OMt + orow * 128 + ((ch ^ (orow & 7)) << 4)) =
+                make_uint4(IoFmt<T>::pack2(o[0], o[1]), IoFmt<T>::pack2(o[2], o[3]), IoFmt<T>::pack2(o[4], o[5]), IoFmt<T>::pack2(o[6], o[7]));
           }
         }
-        ptx::named_bar_sync(1, kComputeThreads);
       }
-      // ---- A2: beta_c = softmax_j(prm(k_j, omega_c)) . v_j  -> beta tile --------------------------
-      for (int c = warp; c < CN; c += 4) {
-        const int ty0 = (c / p.ncx) * p.chunk, tx0 = (c % p.ncx) * p.chunk;
-        float om[8], acc[8];
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bar(kOmFull));
+      // ---- pass 2: per chunk-row, p_t = softmax over the 16 tokens of my chunk -> P2 tile ------------
+      for (int r = 0; r < NR; ++r) {
+        const uint32_t nk = nb + C::nPass2 + 2 * r;
+        const uint8_t* Kr = slot_ptr(slot_of(nk));
+        ptx::mbar_wait(bar(kFull0 + slot_of(nk)), par_of(nk));
+        float n2 = 0.f;
+        if (tok_ok) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { om[e] = omega[c * 65 + oct * 8 + e]; acc[e] = 0.f; }
-        float m = kNegInf, l = 0.f;
-        for (int t0 = 0; t0 < p.Jc; t0 += 4) {
-          const int t = t0 + slot;
-          float lg = kNegInf, fv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) fv[e] = 0.f;
-          if (t < p.Jc) {
-            const int tok = (ty0 + t / p.chunk) * p.gw + tx0 + t % p.chunk;
-            float fk[8];
-            load8<T>(p.k.row<T>(b, tok, h) + oct * 8, fk);
-            load8<T>(p.v.row<T>(b, tok, h) + oct * 8, fv);
-            float part = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) part = fmaf(fk[e], om[e] - 0.5f * fk[e], part);
-            lg = part;
-          }
-          // the 8 lanes of a token slot hold partial dot products (invalid slots carry -inf in all 8)
-          float tot = (t < p.Jc) ? lg : 0.f;
-          tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-          tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-          tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-          lg = (t < p.Jc) ? tot * scale : kNegInf;
-          const float mn = fmaxf(m, lg);
-          if (mn != kNegInf) {
-            const float corr = ex2((m - mn) * kLog2e), pj = ex2((lg - mn) * kLog2e);
-            l = fmaf(l, corr, pj);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(acc[e], corr, pj * fv[e]);
-            m = mn;
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(Kr + tid * 128 + ((ch ^ (tid & 7)) << 4));
+            const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
+            n2 = fmaf(a.x, a.x, n2); n2 = fmaf(a.y, a.y, n2); n2 = fmaf(b2.x, b2.x, n2); n2 = fmaf(b2.y, b2.y, n2);
+            n2 = fmaf(c2.x, c2.x, n2); n2 = fmaf(c2.y, c2.y, n2); n2 = fmaf(d2.x, d2.x, n2); n2 = fmaf(d2.y, d2.y, n2);
           }
         }
-        // merge the 4 token slots
-        float mg = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-        mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 16));
-        const float f = (m == kNegInf) ? 0.f : ex2((m - mg) * kLog2e);
-        l *= f;
-        l += __shfl_xor_sync(0xffffffffu, l, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 16);
-        const float inv_l = 1.0f / l;
+        ptx::mbar_wait(bar(kD2Full0 + (r & 1)), (par_d2 >> (r & 1)) & 1);
+        par_d2 ^= 1u << (r & 1);
+        ptx::tc_fence_after();
+        float dd[8];
+        ptx::tmem_ld8(trow + C::cD2 + 16 * (r & 1), reinterpret_cast<uint32_t*>(dd));
+        ptx::tmem_ld_wait();
+        float dsel = dd[0];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[e] *= f;
-          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-          acc[e] *= inv_l;
+        for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? dd[c] : dsel;
+        const float lg = tok_ok ? scale_log2 * (dsel - 0.5f * n2) : kNegInf;   // log2 units
+        float* lb_ = lbuf + (r & 1) * 128;
+        lb_[tid] = lg;
+        ptx::named_bar_sync(1, kComputeThreads);
+        float mx = kNegInf;
+        const int t0 = tcx * CH;
+#pragma unroll
+        for (int yy = 0; yy < CH; ++yy)
+#pragma unroll
+          for (int xx = 0; xx < CH; ++xx) mx = fmaxf(mx, lb_[tok_ok ? yy * GW + t0 + xx : 0]);
+        float sum = 0.f;
+#pragma unroll
+        for (int yy = 0; yy < CH; ++yy)
+#pragma unroll
+          for (int xx = 0; xx < CH; ++xx) sum += ex2(lb_[tok_ok ? yy * GW + t0 + xx : 0] - mx);
+        const float pt = ex2(lg - mx) / sum;
+        ptx::mbar_wait(bar(kP2Free0 + (r & 1)), (par_p2f >> (r & 1)) & 1);
+        par_p2f ^= 1u << (r & 1);
+        if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + (r & 1) * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(kP2Full0 + (r & 1)));
+      }
+      // ---- beta^T (TMEM) -> beta tile [chunk][feat] -------------------------------------------------
+      ptx::mbar_wait(bar(kBetaFull), ni & 1);
+      ptx::tc_fence_after();
+      {
+        float bt[8 * NR];
+        tmem_ld_cols<8 * NR>(trow + C::cBetaT, reinterpret_cast<uint32_t*>(bt));
+        ptx::tmem_ld_wait();
+        if (feat_lane) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int cx = 0; cx < NCX; ++cx)
+              *reinterpret_cast<uint16_t*>(BTt + tile_off(r * NCX + cx, feat)) = IoFmt<T>::one(bt[8 * r + cx]);
         }
-        if (slot == 0)
-          st_tile_chunk(BTt, c, oct, make_uint4(IoFmt<T>::pack2(acc[0], acc[1]), IoFmt<T>::pack2(acc[2], acc[3]),
-                                                 IoFmt<T>::pack2(acc[4], acc[5]), IoFmt<T>::pack2(acc[6], acc[7])));
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
@@ -423,8 +549,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         ptx::mbar_wait(bar(kSFull), np & 1);
         ptx::tc_fence_after();
         float sl[L], sr[CN];
-        tmem_ld_cols<L>(trow + Lay::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
-        tmem_ld_cols<CN>(trow + Lay::cSrfa, reinterpret_cast<uint32_t*>(sr));
+        tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
+        tmem_ld_cols<CN>(trow + C::cSrfa, reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
         const float* brow = bias2 + ic * LS;
         float mx = kNegInf;
@@ -450,9 +576,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           prf[j] = IoFmt<T>::pack2(a, c2);
         }
         // P (16-bit, two per column) overwrites the S columns this thread has finished reading
-        tmem_st_cols<LP8 / 2>(trow + Lay::cPloc + (uint32_t)(ws * (LP8 / 2)), pl);
-        tmem_st_cols<LP8 / 2>(trow + Lay::cPloc + (uint32_t)((1 - ws) * (LP8 / 2)), zeros);
-        tmem_st_cols<32>(trow + Lay::cPrfa, prf);
+        tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)(ws * (LP8 / 2)), pl);
+        tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)((1 - ws) * (LP8 / 2)), zeros);
+        tmem_st_cols<32>(trow + C::cPrfa, prf);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kPFull));
@@ -460,7 +586,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         ptx::mbar_wait(bar(kOFull), np & 1);
         ptx::tc_fence_after();
         float o[64];
-        tmem_ld_cols<64>(trow + Lay::cO, reinterpret_cast<uint32_t*>(o));
+        tmem_ld_cols<64>(trow + C::cO, reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kOFree));
@@ -483,6 +609,15 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 5) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
+// [W_q ; W_k] (fp32 [64][64] each, row-major [out][in]) -> fp16 [128][64] in the workspace
+__global__ void pack_adaptive_weights(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * 64) return;
+  const int row = idx >> 6, col = idx & 63;
+  const float* src = row < 64 ? wq : wk;
+  dst[idx] = __float2half_rn(src ? src[(row & 63) * 64 + col] : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -499,18 +634,30 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// [B, gh, gw, H, 64] view (strides from the caller's q/k/v view) with a (w x w x 64) box, 128-B swizzle
-static bool make_window_map(CUtensorMap* tm, const View& v, const Geo& g, int io_dtype) {
+// [B, gh, gw, H, 64] view (strides from the caller's q/k/v view) with a (box_h x box_w x 64) box, 128-B swizzle
+static bool make_box_map(CUtensorMap* tm, const View& v, const Geo& g, int io_dtype, int box_w, int box_h) {
   auto enc = get_encode();
   if (!enc) return false;
   const cuuint64_t dims[5] = {64, (cuuint64_t)g.H, (cuuint64_t)g.gw, (cuuint64_t)g.gh, (cuuint64_t)g.B};
   const cuuint64_t strides[4] = {(cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2, (cuuint64_t)v.sn * g.gw * 2, (cuuint64_t)v.sb * 2};
-  const cuuint32_t box[5] = {64, 1, (cuuint32_t)g.window, (cuuint32_t)g.window, 1};
+  const cuuint32_t box[5] = {64, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = enc(tm, io_dtype == EVA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
                          const_cast<void*>(v.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+static bool make_weight_map(CUtensorMap* tm, const void* w16) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {64, 128};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w16), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int sm_count() {
@@ -523,32 +670,37 @@ static int sm_count() {
   return n > 0 ? n : 148;
 }
 
-template <typename T, int W, int CN>
+template <typename T, int W, int GW, int CH, int NR>
 static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
-                            const float* noise, const float* bias, long long bias_sh, void* out, cudaStream_t st,
-                            const char** msg) {
-  using Lay = Layout<W * W, CN>;
-  CUtensorMap tq, tk, tv;
-  const int io = sizeof(T) == 2 && std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
-  if (!make_window_map(&tq, q, g, io) || !make_window_map(&tk, k, g, io) || !make_window_map(&tv, v, g, io)) {
+                            const float* noise, const float* bias, long long bias_sh, void* out, void* workspace,
+                            cudaStream_t st, const char** msg) {
+  using C = Cfg<W, GW, CH, NR>;
+  constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
+  __half* w16 = reinterpret_cast<__half*>(workspace);
+  pack_adaptive_weights<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *msg = "pack_adaptive_weights launch"; return e; }
+  CUtensorMap twq, twk, twv, trq, trk, trv, tw;
+  if (!make_box_map(&twq, q, g, io, W, W) || !make_box_map(&twk, k, g, io, W, W) || !make_box_map(&twv, v, g, io, W, W) ||
+      !make_box_map(&trq, q, g, io, GW, CH) || !make_box_map(&trk, k, g, io, GW, CH) || !make_box_map(&trv, v, g, io, GW, CH) ||
+      !make_weight_map(&tw, w16)) {
     *msg = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
   Params p{};
   p.B = g.B; p.H = g.H; p.N = g.N; p.gh = g.gh; p.gw = g.gw;
   p.nwx = g.gw / g.window; p.n_windows = g.n_windows; p.n_pairs = (g.n_windows + 1) / 2;
-  p.chunk = g.chunk; p.ncx = g.gw / g.chunk; p.Jc = g.Jc;
   p.items = g.B * g.H;
-  p.q = q; p.k = k; p.v = v;
-  p.w_q = ada.w_q; p.b_q = ada.b_q; p.g_q = ada.ln_gain_q; p.beta_q = ada.ln_bias_q;
-  p.w_k = ada.w_k; p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
+  p.b_q = ada.b_q; p.g_q = ada.ln_gain_q; p.beta_q = ada.ln_bias_q;
+  p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
+  p.has_q = ada.w_q != nullptr;
   p.mu_coeff = ada.mu_coeff; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias = bias; p.bias_sh = bias_sh; p.out = out;
-  auto kern = eva_fused_kernel<T, W, CN>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay::kDynamic);
+  auto kern = eva_fused_kernel<T, W, GW, CH, NR>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
   const int grid = p.items < 2 * sm_count() ? p.items : 2 * sm_count();
-  kern<<<grid, kThreads, Lay::kDynamic, st>>>(tq, tk, tv, p);
+  kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, p);
   *msg = "kernel launch";
   return cudaGetLastError();
 }
@@ -564,14 +716,22 @@ static bool fused_disabled() {
   return v == 1;
 }
 
+// geometry families the fused kernel is instantiated for: window 7, 49 chunks on a 28-wide (chunk 4) or
+// 14-wide (chunk 2) grid -- DeiT-tiny/small p8 and p16 (BASELINE configs c2, c3)
+static int fused_variant(const Geo& g) {
+  if (g.window != 7 || g.n_chunks != 49) return 0;
+  if (g.gw == 28 && g.gh == 28 && g.chunk == 4) return 1;
+  if (g.gw == 14 && g.gh == 14 && g.chunk == 2) return 2;
+  return 0;
+}
+
 bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                      const EvaAdaptive& ada, const float* bias, long long bias_sh) {
   (void)ada; (void)bias; (void)bias_sh;
   if (fused_disabled()) return false;
   if (g.dims != 2 || g.ext != 0 || g.chunk_ext != 0 || g.causal || g.D != 64 || mask != nullptr) return false;
   if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
-  if (g.window != 7 || g.n_chunks != 49 || g.chunk <= 0) return false;
-  if (g.gw % g.chunk || g.gh % g.chunk) return false;
+  if (fused_variant(g) == 0) return false;
   for (const View* x : {&q, &k, &v}) {
     if (x->sh * 2 % 16 || x->sn * 2 % 16 || x->sb * 2 % 16) return false;
     if (x->sh <= 0 || x->sn <= 0 || x->sb <= 0) return false;
@@ -579,14 +739,18 @@ bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, c
   return fused::get_encode() != nullptr;
 }
 
-size_t fused_workspace_bytes(const Geo&) { return 0; }
+size_t fused_workspace_bytes(const Geo&) { return 128 * 64 * sizeof(__half); }
 
 cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                          const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,
                          void* out, void* workspace, cudaStream_t st, const char** msg) {
-  (void)workspace;
-  if (io_dtype == EVA_F16) return fused::launch_t<__half, 7, 49>(g, q, k, v, ada, noise, bias, bias_sh, out, st, msg);
-  return fused::launch_t<__nv_bfloat16, 7, 49>(g, q, k, v, ada, noise, bias, bias_sh, out, st, msg);
+  const int var = fused_variant(g);
+  if (io_dtype == EVA_F16) {
+    if (var == 1) return fused::launch_t<__half, 7, 28, 4, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+    return fused::launch_t<__half, 7, 14, 2, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  }
+  if (var == 1) return fused::launch_t<__nv_bfloat16, 7, 28, 4, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  return fused::launch_t<__nv_bfloat16, 7, 14, 2, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
 }
 
 }  // namespace eva
