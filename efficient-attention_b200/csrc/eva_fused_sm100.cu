@@ -40,7 +40,7 @@ constexpr int kSlotBytes = 16384;
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
   kD2Full0, kD2Full1, kP2Full0, kP2Full1, kP2Free0, kP2Free1, kBetaFull, kStatsFull,
-  kSFull, kPFull, kOFull, kOFree, kNumBars
+  kSFull, kPFull, kOFull, kOFree, kBiasFull, kBiasFree, kNumBars
 };
 
 struct Params {
@@ -51,9 +51,9 @@ struct Params {
   int has_q;                     // 0: adaptive_proj == 'none' (mu = 0)
   float mu_coeff, ln_eps;
   const float* noise;
-  const float* bias;
-  long long bias_sh;
+  const float* bias2;            // [H][kBiasSlab/4] fp32 bias x log2(e), row stride LS (packed by pack_params), or NULL
   void* out;
+  int trace;
 };
 
 template <int W, int GW, int CH, int NR> struct Cfg {
@@ -72,12 +72,17 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int kKbar = kSlots * kSlotBytes;    // [64][128 B]  k_bar, row = chunk c
   static constexpr int kBeta = kKbar + 8192;           // [64][128 B]  beta,  row = chunk c
   static constexpr int kOm = kBeta + 8192;             // [64][128 B]  omega, row = 8r + cx
-  static constexpr int kPool = kOm + 8192;             // KBLK x [8][128 B] pooling weights (constant)
-  static constexpr int kP2 = kPool + KBLK * 1024;      // 2 x KBLK x [8][128 B] chunk softmax weights
-  static constexpr int kZeroEnd = kP2 + 2 * KBLK * 1024;
-  static constexpr int kBias = kZeroEnd;               // [L][LS] fp32, x log2(e)
-  static constexpr int kLbuf = (kBias + L * LS * 4 + 15) & ~15;   // 2 x [128] fp32 logit exchange
-  static constexpr int kBars = (kLbuf + 2 * 128 * 4 + 7) & ~7;
+  static constexpr int kLbuf = kOm + 8192;             // 2 x [128] fp32 logit exchange
+  // phase B re-uses [kOm, kP2) as the output staging: window a at +0, window b at +LP8*128 (swizzled rows)
+  static constexpr int kOStage = kOm;
+  static constexpr int kOStageEnd = kOStage + LP8 * 128 + L * 128;
+  static constexpr int kP2 = ((kLbuf + 1024 > kOStageEnd ? kLbuf + 1024 : kOStageEnd) + 1023) & ~1023;   // 2 x KBLK x [8][128 B]
+  static constexpr int kPool = kP2 + 2 * KBLK * 1024;  // KBLK x [8][128 B] pooling weights (constant)
+  static constexpr int kBias = kPool + KBLK * 1024;    // [L][LS] fp32, x log2(e)
+  static constexpr int kBiasSlab = (L * LS * 4 + 15) & ~15;
+  static constexpr int kZeroEnd = kBias + kBiasSlab;
+  static constexpr int kLn = kZeroEnd;                 // [6][64] fp32: b_q, gain_q, beta_q, b_k, gain_k, beta_k
+  static constexpr int kBars = (kLn + 6 * 64 * 4 + 7) & ~7;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemPtr + 16;
   static constexpr int kDynamic = kBytes + 1024;
@@ -152,16 +157,28 @@ __device__ __forceinline__ int ktile_off(int n, int t) { return (t >> 6) * 1024 
 __device__ __forceinline__ uint32_t slot_of(uint32_t n) { return n & (kSlots - 1); }
 __device__ __forceinline__ uint32_t par_of(uint32_t n) { return (n >> 2) & 1u; }
 
+// optional phase trace of CTA 0 (EVA_SM100_TRACE=1): [0] compute thread 0, [1] MMA thread; pairs (event, clock64)
+constexpr int kTraceLen = 8192;
+__device__ unsigned long long g_trace[2][kTraceLen];
+struct Tracer {
+  unsigned long long* buf;
+  int n;
+  __device__ __forceinline__ void operator()(int ev) {
+    if (buf && n + 2 <= kTraceLen) { buf[n] = (unsigned long long)ev; buf[n + 1] = (unsigned long long)clock64(); n += 2; }
+  }
+};
+
 template <typename T, int W, int GW, int CH, int NR>
 __global__ void __launch_bounds__(kThreads, 2)
 eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant__ CUtensorMap tw_k,
                  const __grid_constant__ CUtensorMap tw_v, const __grid_constant__ CUtensorMap tr_q,
                  const __grid_constant__ CUtensorMap tr_k, const __grid_constant__ CUtensorMap tr_v,
-                 const __grid_constant__ CUtensorMap t_w, const Params p) {
+                 const __grid_constant__ CUtensorMap t_w, const __grid_constant__ CUtensorMap t_o, const Params p) {
   using C = Cfg<W, GW, CH, NR>;
   constexpr int L = C::L, LP8 = C::LP8, LS = C::LS, CN = C::CN, NCX = C::NCX, TOK = C::TOK, KS = C::KS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by offset arithmetic (not by integer round trip) so the compiler keeps the shared address space
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* KBt = sm + C::kKbar;
   uint8_t* BTt = sm + C::kBeta;
   uint8_t* OMt = sm + C::kOm;
@@ -182,6 +199,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   __syncthreads();
   for (int t = tid; t < TOK; t += kThreads)   // Pool^T[n][t] = 1/Jc for the chunk column n that owns token t
     *reinterpret_cast<uint16_t*>(PoolT + ktile_off((t % GW) / CH, t)) = IoFmt<T>::one(1.0f / C::JC);
+  {
+    float* ln = reinterpret_cast<float*>(sm + C::kLn);
+    const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
+    for (int idx = tid; idx < 6 * 64; idx += kThreads) ln[idx] = src[idx >> 6] ? __ldg(src[idx >> 6] + (idx & 63)) : 0.f;
+  }
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < kSlots; ++s) { ptx::mbar_init(bar(kFull0 + s), 1); ptx::mbar_init(bar(kFree0 + s), 1); }
     ptx::mbar_init(bar(kPoolFull), 1);
@@ -200,10 +222,13 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kPFull), kComputeThreads);
     ptx::mbar_init(bar(kOFull), 1);
     ptx::mbar_init(bar(kOFree), kComputeThreads);
+    ptx::mbar_init(bar(kBiasFull), 1);
+    ptx::mbar_init(bar(kBiasFree), kComputeThreads);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
     ptx::prefetch_tmap(&tr_q); ptx::prefetch_tmap(&tr_k); ptx::prefetch_tmap(&tr_v);
     ptx::prefetch_tmap(&t_w);
+    ptx::prefetch_tmap(&t_o);
   }
   if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), kTmemCols);
   ptx::fence_proxy_async_smem();
@@ -215,7 +240,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   if (warp == 4) {
     // =================================== TMA producer ==========================================
     if (lane == 0) {
-      uint32_t n = 0;
+      uint32_t n = 0, ni = 0;
+      const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
       auto acquire = [&](uint32_t bytes) -> uint32_t {   // returns the slot; arms its full barrier
         const uint32_t s = slot_of(n);
         ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
@@ -223,14 +249,20 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ++n;
         return s;
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni) {
         const int b = item / p.H, h = item % p.H;
         for (int r = 0; r < NR; ++r) {                   // pass 1: q, k chunk-rows (first touch: HBM)
           uint32_t s = acquire(TOK * 128);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           s = acquire(TOK * 128);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b);
-          ptx::tma_prefetch_5d(&tr_v, 0, h, 0, r * CH, b);   // v is first needed in pass 2: warm L2 now
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
+        }
+        if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
+          ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(bar(kBiasFull), C::kBiasSlab);
+          ptx::bulk_load(ptx::smem_u32(sm + C::kBias), reinterpret_cast<const uint8_t*>(p.bias2) + (size_t)h * C::kBiasSlab,
+                         C::kBiasSlab, bar(kBiasFull));
         }
         ++n;                                             // slot borrowed by the compute warps for the means tile
         {
@@ -239,9 +271,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         }
         for (int r = 0; r < NR; ++r) {                   // pass 2: k (L2), v (L2 after the prefetch)
           uint32_t s = acquire(TOK * 128);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           s = acquire(TOK * 128);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b);
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
         }
         for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: window pairs (L2)
           const int w0 = 2 * pr, w1 = w0 + 1;
@@ -249,15 +281,15 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const int x0 = (w0 % p.nwx) * W, y0 = (w0 / p.nwx) * W;
           const int x1 = (w1 % p.nwx) * W, y1 = (w1 / p.nwx) * W;
           const uint32_t bytes = (two ? 2u : 1u) * L * 128u;
-          uint32_t s = acquire(bytes);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b);
-          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b);
+          uint32_t s = acquire(bytes);                   // last use of these lines: let L2 drop them first
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b, stream);
           s = acquire(bytes);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b);
-          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b);
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b, stream);
           s = acquire(bytes);
-          ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b);
-          if (two) ptx::tma_load_5d(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b);
+          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b, stream);
         }
       }
     }
@@ -279,10 +311,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
       auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
       uint32_t nb = 0, ni = 0, np = 0, par_p2 = 0;   // par_p2: bit b = parity of the next P2Full[b] wait
+      Tracer tr{(p.trace && blockIdx.x == 0) ? g_trace[1] : nullptr, 0};
       auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); };
       auto free_slot = [&](uint32_t n) { ptx::umma_commit(bar(kFree0 + slot_of(n))); };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         // ---- pass 1: chunk means ------------------------------------------------------------
+        tr(101);
         for (int r = 0; r < NR; ++r) {
           const uint32_t nq = nb + 2 * r, nk = nq + 1;
           wait_full(nq);
@@ -298,6 +332,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           free_slot(nk);
         }
         ptx::umma_commit(bar(kPoolFull));
+        tr(102);
         // ---- adaptive Linear: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used) ----------
         ptx::mbar_wait(bar(kAFull), ni & 1);
         // the borrowed slot was filled by the compute warps, not by TMA: complete its `full` phase by hand
@@ -309,8 +344,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         for (int ks = 0; ks < 4; ++ks)
           ptx::umma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
         ptx::umma_commit(bar(kLinFull));
+        tr(103);
         free_slot(nb + C::nW);
-        ptx::mbar_wait(bar(kOmFull), ni & 1);      // omega / k_bar tiles written, staging in the borrowed slot dead
+        ptx::mbar_wait(bar(kOmFull), ni & 1);
+        tr(104);      // omega / k_bar tiles written, staging in the borrowed slot dead
         free_slot(nb + C::nAt);
         ptx::tc_fence_after();
         // ---- pass 2: logits one row ahead of beta ------------------------------------------------
@@ -329,6 +366,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const uint32_t nk = nb + C::nPass2 + 2 * r, nv = nk + 1;
           ptx::mbar_wait(bar(kP2Full0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
           par_p2 ^= 1u << (r & 1);
+          free_slot(nk);   // K_r: its logits MMA is done and the compute warps have read it (they arrived on P2Full)
           wait_full(nv);
           ptx::tc_fence_after();
 #pragma unroll
@@ -336,11 +374,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             ptx::umma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
                          dP2 + (uint64_t)((r & 1) * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
           ptx::umma_commit(bar(kP2Free0 + (r & 1)));
-          free_slot(nk);
           free_slot(nv);
+          tr(110 + r);
         }
         ptx::umma_commit(bar(kBetaFull));
         ptx::mbar_wait(bar(kStatsFull), ni & 1);
+        tr(120);
         ptx::tc_fence_after();
         // ---- phase B --------------------------------------------------------------------------------
         for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
@@ -356,6 +395,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           ptx::umma_commit(bar(kSFull));
           free_slot(nq);
           free_slot(nk);
+          tr(130 + 2 * pr);
           ptx::mbar_wait(bar(kPFull), np & 1);
           wait_full(nv);
           ptx::mbar_wait(bar(kOFree), (np & 1) ^ 1);
@@ -368,8 +408,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             ptx::umma_ts(tmem + C::cO, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
           ptx::umma_commit(bar(kOFull));
           free_slot(nv);
+          tr(131 + 2 * pr);
         }
       }
+      if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
     }
   } else {
     // =================================== compute warps ==========================================
@@ -379,21 +421,18 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const float scale = 0.125f;        // head_dim 64
     const float scale_log2 = scale * kLog2e;
-    T* const out = reinterpret_cast<T*>(p.out);
     // pass 1 / beta readback: lanes 0-15 of each warp hold feature 16*warp + lane of an M=64 accumulator
     const int feat = 16 * warp + (lane & 15);
     const bool feat_lane = lane < 16;
     // pass 2: token of the chunk-row owned by this thread
     const int tcx = (tid % GW) / CH;
     const bool tok_ok = tid < TOK;
-    uint32_t nb = 0, ni = 0, np = 0, par_d2 = 0, par_p2f = 3;   // bit b = parity of the next wait on buffer b
+    uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0, par_d2 = 0, par_p2f = 3;   // bit b = parity of the next wait on buffer b
+    uint8_t* const ostage = sm + C::kOStage;
+    Tracer tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
       const int b = item / p.H, h = item % p.H;
-      // ---- per-head bias table (x log2 e) ------------------------------------------------------
-      for (int idx = tid; idx < L * L; idx += kComputeThreads) {
-        const int r = idx / L, c = idx % L;
-        bias2[r * LS + c] = p.bias ? __ldg(p.bias + (long long)h * p.bias_sh + idx) * kLog2e : 0.f;
-      }
+      tr(1);
       // ---- pass 1 readback: means^T (TMEM) -> fp16 means tile [chunk][feat] in the borrowed slot -----
       const uint32_t nat = nb + C::nAt;
       uint8_t* At = slot_ptr(slot_of(nat));
@@ -401,6 +440,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::mbar_wait(bar(kFree0 + slot_of(nat)), par_of(nat) ^ 1);
       ptx::mbar_wait(bar(kPoolFull), ni & 1);
       ptx::tc_fence_after();
+      tr(2);
       {
         float mq[8 * NR], mk[8 * NR];
         tmem_ld_cols<8 * NR>(trow + C::cPoolQ, reinterpret_cast<uint32_t*>(mq));
@@ -420,33 +460,50 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kAFull));
+      tr(3);
       // ---- Linear result -> bias, LayerNorm; rows 0-63 = q side, rows 64-127 = k side ------------
       ptx::mbar_wait(bar(kLinFull), ni & 1);
       ptx::tc_fence_after();
+      tr(4);
       {
         float y[64];
         tmem_ld_cols<64>(trow + C::cLin + (ws ? 64u : 0u), reinterpret_cast<uint32_t*>(y));
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        const float* lb = ws ? p.b_k : p.b_q;
-        const float* gain = ws ? p.g_k : p.g_q;
-        const float* lnb = ws ? p.beta_k : p.beta_q;
-        if (lb) {
+        tr(240);
+        const float* lnp = reinterpret_cast<const float*>(sm + C::kLn) + (ws ? 192 : 0);   // bias | gain | beta
+        const bool has_lin_bias = ws ? (p.b_k != nullptr) : (p.b_q != nullptr);
+        const bool has_ln = ws ? (p.g_k != nullptr) : (p.g_q != nullptr);
+        if (has_lin_bias) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e) y[e] += __ldg(lb + e);
+          for (int e4 = 0; e4 < 16; ++e4) {
+            const float4 bb = *reinterpret_cast<const float4*>(lnp + 4 * e4);
+            y[4 * e4] += bb.x; y[4 * e4 + 1] += bb.y; y[4 * e4 + 2] += bb.z; y[4 * e4 + 3] += bb.w;
+          }
         }
-        if (gain) {
-          float s = 0.f;
+        if (has_ln) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 64; ++e) s += y[e];
-          const float mean = s * (1.0f / 64);
-          float var = 0.f;
+          for (int e = 0; e < 64; e += 4) { s0 += y[e]; s1 += y[e + 1]; s2 += y[e + 2]; s3 += y[e + 3]; }
+          const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64);
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 64; ++e) { const float d_ = y[e] - mean; var = fmaf(d_, d_, var); }
-          const float inv = 1.0f / sqrtf(var * (1.0f / 64) + p.ln_eps);
+          for (int e = 0; e < 64; e += 4) {
+            const float d0 = y[e] - mean, d1 = y[e + 1] - mean, d2_ = y[e + 2] - mean, d3 = y[e + 3] - mean;
+            v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2_, d2_, v2); v3 = fmaf(d3, d3, v3);
+          }
+          const float inv = 1.0f / sqrtf(((v0 + v1) + (v2 + v3)) * (1.0f / 64) + p.ln_eps);
 #pragma unroll
-          for (int e = 0; e < 64; ++e) y[e] = (y[e] - mean) * inv * __ldg(gain + e) + __ldg(lnb + e);
+          for (int e4 = 0; e4 < 16; ++e4) {
+            const float4 gg = *reinterpret_cast<const float4*>(lnp + 64 + 4 * e4);
+            const float4 bb = *reinterpret_cast<const float4*>(lnp + 128 + 4 * e4);
+            y[4 * e4] = (y[4 * e4] - mean) * inv * gg.x + bb.x;
+            y[4 * e4 + 1] = (y[4 * e4 + 1] - mean) * inv * gg.y + bb.y;
+            y[4 * e4 + 2] = (y[4 * e4 + 2] - mean) * inv * gg.z + bb.z;
+            y[4 * e4 + 3] = (y[4 * e4 + 3] - mean) * inv * gg.w + bb.w;
+          }
         }
+        tr(241);
         const bool valid = i < CN;
         if (ws == 1 && valid) {   // k side: k_bar tile (B operand of the chunk logits) + fp32 copy for mu
 #pragma unroll
@@ -457,7 +514,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 64; ++e) stage[i * 65 + e] = y[e];
         }
+        tr(242);
         ptx::named_bar_sync(1, kComputeThreads);
+        tr(243);
         if (ws == 0 && valid) {   // q side: omega = mu_coeff (q_bar + k_bar) [+ noise] -> omega tile row 8r+cx
           const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * CN + i) * 64 : nullptr;
           const int orow = 8 * (i / NCX) + i % NCX;
@@ -476,6 +535,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar(kOmFull));
+      tr(5);
       // ---- pass 2: per chunk-row, p_t = softmax over the 16 tokens of my chunk -> P2 tile ------------
       for (int r = 0; r < NR; ++r) {
         const uint32_t nk = nb + C::nPass2 + 2 * r;
@@ -522,10 +582,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kP2Full0 + (r & 1)));
+        tr(10 + r);
       }
       // ---- beta^T (TMEM) -> beta tile [chunk][feat] -------------------------------------------------
       ptx::mbar_wait(bar(kBetaFull), ni & 1);
       ptx::tc_fence_after();
+      tr(20);
       {
         float bt[8 * NR];
         tmem_ld_cols<8 * NR>(trow + C::cBetaT, reinterpret_cast<uint32_t*>(bt));
@@ -541,30 +603,43 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kStatsFull));
+      tr(21);
+      if (p.bias2) ptx::mbar_wait(bar(kBiasFull), ni & 1);
 
-      // ---- phase B: pairs of windows ----------------------------------------------------------------
-      for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
-        const int wi = 2 * pr + ws;
-        const bool valid = i < L && wi < p.n_windows;
-        ptx::mbar_wait(bar(kSFull), np & 1);
+      // ---- phase B: pairs of windows; softmax of pair p+1 is done before the epilogue of pair p so that
+      //      the PV MMA of pair p and the S MMA of pair p+1 run under SIMT work ---------------------------
+      auto softmax_pair = [&](int pr) -> float {
+        ptx::mbar_wait(bar(kSFull), np_s & 1);
         ptx::tc_fence_after();
+        tr(30 + 4 * pr);
         float sl[L], sr[CN];
         tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
         tmem_ld_cols<CN>(trow + C::cSrfa, reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
+        if (pr == 1) tr(250);
         const float* brow = bias2 + ic * LS;
-        float mx = kNegInf;
+        float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
-        for (int j = 0; j < L; ++j) { sl[j] = fmaf(sl[j], scale_log2, brow[j]); mx = fmaxf(mx, sl[j]); }
+        for (int j = 0; j < L; ++j) {
+          sl[j] = fmaf(sl[j], scale_log2, brow[j]);
+          if ((j & 3) == 0) m0 = fmaxf(m0, sl[j]); else if ((j & 3) == 1) m1 = fmaxf(m1, sl[j]);
+          else if ((j & 3) == 2) m2 = fmaxf(m2, sl[j]); else m3 = fmaxf(m3, sl[j]);
+        }
 #pragma unroll
-        for (int c = 0; c < CN; ++c) { sr[c] *= scale_log2; mx = fmaxf(mx, sr[c]); }
-        float sum = 0.f;
+        for (int c = 0; c < CN; ++c) {
+          sr[c] *= scale_log2;
+          if ((c & 3) == 0) m0 = fmaxf(m0, sr[c]); else if ((c & 3) == 1) m1 = fmaxf(m1, sr[c]);
+          else if ((c & 3) == 2) m2 = fmaxf(m2, sr[c]); else m3 = fmaxf(m3, sr[c]);
+        }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if (pr == 1) tr(251);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         uint32_t pl[LP8 / 2], prf[32], zeros[LP8 / 2];
 #pragma unroll
         for (int j = 0; j < LP8 / 2; ++j) {
           const float a = (2 * j < L) ? ex2(sl[(2 * j < L) ? 2 * j : 0] - mx) : 0.f;
           const float c2 = (2 * j + 1 < L) ? ex2(sl[(2 * j + 1 < L) ? 2 * j + 1 : 0] - mx) : 0.f;
-          sum += a + c2;
+          if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
           pl[j] = IoFmt<T>::pack2(a, c2);
           zeros[j] = 0u;
         }
@@ -572,9 +647,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         for (int j = 0; j < 32; ++j) {
           const float a = (2 * j < CN) ? ex2(sr[(2 * j < CN) ? 2 * j : 0] - mx) : 0.f;
           const float c2 = (2 * j + 1 < CN) ? ex2(sr[(2 * j + 1 < CN) ? 2 * j + 1 : 0] - mx) : 0.f;
-          sum += a + c2;
+          if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
           prf[j] = IoFmt<T>::pack2(a, c2);
         }
+        if (pr == 1) tr(252);
         // P (16-bit, two per column) overwrites the S columns this thread has finished reading
         tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)(ws * (LP8 / 2)), pl);
         tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)((1 - ws) * (LP8 / 2)), zeros);
@@ -582,25 +658,55 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kPFull));
-        // ---- epilogue: O / rowsum -> out[b, token, h, :] ---------------------------------------------
-        ptx::mbar_wait(bar(kOFull), np & 1);
+        if (p.bias2 && pr == p.n_pairs - 1) ptx::mbar_arrive(bar(kBiasFree));   // bias table no longer needed for this item
+        tr(31 + 4 * pr);
+        ++np_s;
+        return (s0 + s1) + (s2 + s3);
+      };
+      // epilogue: O / rowsum -> swizzled staging rows -> one TMA store per window
+      auto epilogue_pair = [&](int pr, float sum) {
+        const int wi = 2 * pr + ws;
+        const bool win_ok = wi < p.n_windows;
+        ptx::mbar_wait(bar(kOFull), np_e & 1);
         ptx::tc_fence_after();
+        tr(32 + 4 * pr);
         float o[64];
         tmem_ld_cols<64>(trow + C::cO, reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kOFree));
-        if (valid) {
+        if (pr == 1) tr(253);
+        if (i == 0) ptx::bulk_wait_read0();            // the previous store of this window half has drained the staging rows
+        ptx::named_bar_sync(2 + ws, 64);
+        if (i < L && win_ok) {
           const float inv = 1.0f / sum;
-          const int tok = ((wi / p.nwx) * W + i / W) * p.gw + (wi % p.nwx) * W + i % W;
-          uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * p.N + tok) * p.H + h) * kD);
+          uint8_t* row = ostage + ws * (LP8 * 128) + i * 128;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            dst[ch] = make_uint4(IoFmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), IoFmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
-                                 IoFmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), IoFmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+            *reinterpret_cast<uint4*>(row + ((ch ^ (i & 7)) << 4)) =
+                make_uint4(IoFmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), IoFmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                           IoFmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), IoFmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(2 + ws, 64);
+        if (i == 0 && win_ok) {
+          ptx::tma_store_5d(&t_o, ptx::smem_u32(ostage + ws * (LP8 * 128)), 0, h, (wi % p.nwx) * W, (wi / p.nwx) * W, b);
+          ptx::bulk_commit_group();
+        }
+        tr(33 + 4 * pr);
+        ++np_e;
+      };
+      float sum_cur = softmax_pair(0);
+      for (int pr = 0; pr < p.n_pairs; ++pr) {
+        float sum_next = 0.f;
+        if (pr + 1 < p.n_pairs) sum_next = softmax_pair(pr + 1);
+        epilogue_pair(pr, sum_cur);
+        sum_cur = sum_next;
       }
+      if (i == 0) ptx::bulk_wait_read0();   // staging rows alias phase-A tiles of the next item
     }
+    if (i == 0) ptx::bulk_wait_all();
+    if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
   }
   // ---- teardown ------------------------------------------------------------------------------------
   ptx::tc_fence_before();
@@ -609,13 +715,23 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   if (warp == 5) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
-// [W_q ; W_k] (fp32 [64][64] each, row-major [out][in]) -> fp16 [128][64] in the workspace
-__global__ void pack_adaptive_weights(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ dst) {
+// workspace packing: [W_q ; W_k] (fp32 [64][64] each, row-major [out][in]) -> fp16 [128][64];
+// bias [H or 1][L][L] -> per-head slabs [L][LS] fp32 pre-multiplied by log2(e)
+__global__ void pack_params(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ w16,
+                            const float* __restrict__ bias, long long bias_sh, float* __restrict__ bias2, int H, int L,
+                            int LS, int slab_floats) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 128 * 64) return;
-  const int row = idx >> 6, col = idx & 63;
-  const float* src = row < 64 ? wq : wk;
-  dst[idx] = __float2half_rn(src ? src[(row & 63) * 64 + col] : 0.f);
+  if (idx < 128 * 64) {
+    const int row = idx >> 6, col = idx & 63;
+    const float* src = row < 64 ? wq : wk;
+    w16[idx] = __float2half_rn(src ? src[(row & 63) * 64 + col] : 0.f);
+  }
+  if (bias) {
+    for (int j = idx; j < H * slab_floats; j += gridDim.x * blockDim.x) {
+      const int h = j / slab_floats, o = j % slab_floats, r = o / LS, c = o % LS;
+      bias2[j] = (r < L && c < L) ? bias[(long long)h * bias_sh + r * L + c] * kLog2e : 0.f;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,6 +776,15 @@ static bool make_weight_map(CUtensorMap* tm, const void* w16) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int trace_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EVA_SM100_TRACE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -677,13 +802,16 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   using C = Cfg<W, GW, CH, NR>;
   constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
   __half* w16 = reinterpret_cast<__half*>(workspace);
-  pack_adaptive_weights<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16);
+  float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 128 * 64 * sizeof(__half));
+  pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / 4);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { *msg = "pack_adaptive_weights launch"; return e; }
-  CUtensorMap twq, twk, twv, trq, trk, trv, tw;
+  if (e != cudaSuccess) { *msg = "pack_params launch"; return e; }
+  CUtensorMap twq, twk, twv, trq, trk, trv, tw, to;
+  View ov;
+  ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
   if (!make_box_map(&twq, q, g, io, W, W) || !make_box_map(&twk, k, g, io, W, W) || !make_box_map(&twv, v, g, io, W, W) ||
       !make_box_map(&trq, q, g, io, GW, CH) || !make_box_map(&trk, k, g, io, GW, CH) || !make_box_map(&trv, v, g, io, GW, CH) ||
-      !make_weight_map(&tw, w16)) {
+      !make_weight_map(&tw, w16) || !make_box_map(&to, ov, g, io, W, W)) {
     *msg = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
@@ -695,12 +823,13 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
   p.has_q = ada.w_q != nullptr;
   p.mu_coeff = ada.mu_coeff; p.ln_eps = ada.ln_eps;
-  p.noise = noise; p.bias = bias; p.bias_sh = bias_sh; p.out = out;
+  p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out;
+  p.trace = trace_enabled();
   auto kern = eva_fused_kernel<T, W, GW, CH, NR>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
   const int grid = p.items < 2 * sm_count() ? p.items : 2 * sm_count();
-  kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, p);
+  kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, to, p);
   *msg = "kernel launch";
   return cudaGetLastError();
 }
@@ -739,7 +868,16 @@ bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, c
   return fused::get_encode() != nullptr;
 }
 
-size_t fused_workspace_bytes(const Geo&) { return 128 * 64 * sizeof(__half); }
+size_t fused_workspace_bytes(const Geo& g) {
+  const int L = g.window * g.window, LS = L | 1;
+  return 128 * 64 * sizeof(__half) + (size_t)g.H * ((L * LS * 4 + 15) & ~15);
+}
+
+// diagnostic (not part of the public ABI): copy the phase trace of CTA 0 to the host
+extern "C" int eva_debug_read_trace(unsigned long long* dst, int which, int n) {
+  if (which < 0 || which > 1 || n > fused::kTraceLen) return -22;
+  return cudaMemcpyFromSymbol(dst, fused::g_trace, (size_t)n * 8, (size_t)which * fused::kTraceLen * 8) == cudaSuccess ? 0 : -5;
+}
 
 cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                          const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box session: fused-kernel diagnostics, parity tests, smoke, bench. Everything lands in gpurun_out/.
+# One GPU-box session: fused-kernel diagnostics, parity tests, smoke, bench, phase trace. Everything lands in gpurun_out/.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/smi.txt 2>&1
@@ -15,4 +15,5 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $?" >> gpurun_out/bench.err
-cat gpurun_out/fused_diag.log; tail -5 gpurun_out/fused_diag14.log; tail -5 gpurun_out/pytest.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+if [ $rc -eq 0 ]; then timeout 200 python tools/trace_dump.py 1024 > gpurun_out/trace.log 2>&1; echo "trace exit $?" >> gpurun_out/trace.log; fi
+grep -v "^per \|^sample" gpurun_out/fused_diag.log | tail -12; tail -3 gpurun_out/fused_diag14.log; tail -5 gpurun_out/pytest.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
