@@ -40,7 +40,7 @@ constexpr int kSlotBytes = 16384;
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
   kD2Full0, kD2Full1, kP2Full0, kP2Full1, kP2Free0, kP2Free1, kBetaFull, kStatsFull,
-  kSFull, kPFull, kOFull, kOFree, kBiasFull, kBiasFree, kNumBars
+  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNumBars
 };
 
 struct Params {
@@ -89,11 +89,12 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static_assert(kDynamic <= 115712, "two CTAs per SM need <= 113 KB each");
   static_assert(CN * 65 * 4 <= kSlotBytes, "k_bar staging must fit in the borrowed slot");
   // TMEM columns
-  static constexpr uint32_t cPoolQ = 0, cPoolK = 64;   // pass 1: [feat x (8r+cx)]
+  static constexpr uint32_t cPoolQ = 0, cPoolK = 56;   // pass 1: [feat x (8r+cx)]; stays clear of the X buffers
   static constexpr uint32_t cLin = 0;                  // Linear: [chunk-row x 128]
   static constexpr uint32_t cBetaT = 0;                // pass 2: [feat x (8r+cx)]
   static constexpr uint32_t cD2 = 224;                 // pass 2: 2 x [token x 16]
-  static constexpr uint32_t cSloc = 0, cSrfa = 2 * LP8, cO = 2 * LP8 + 64, cPloc = 0, cPrfa = LP8;
+  // phase B: local logits / P in [0, 2*LP8); chunk logits of pair p and later its O share buffer X[p&1]
+  static constexpr uint32_t cSloc = 0, cX0 = 2 * LP8, cPloc = 0, cPrfa = LP8;
   static_assert(2 * LP8 + 128 <= 256 && (2 * LP8) % 16 == 0, "TMEM budget");
   // loads per item, in ring order
   static constexpr int nAt = 2 * NR, nW = 2 * NR + 1, nPass2 = 2 * NR + 2, nPairs = 4 * NR + 2;
@@ -220,8 +221,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kStatsFull), kComputeThreads);
     ptx::mbar_init(bar(kSFull), 1);
     ptx::mbar_init(bar(kPFull), kComputeThreads);
-    ptx::mbar_init(bar(kOFull), 1);
-    ptx::mbar_init(bar(kOFree), kComputeThreads);
+    ptx::mbar_init(bar(kOFull0), 1);
+    ptx::mbar_init(bar(kOFull1), 1);
+    ptx::mbar_init(bar(kOFree0), kComputeThreads);
+    ptx::mbar_init(bar(kOFree1), kComputeThreads);
     ptx::mbar_init(bar(kBiasFull), 1);
     ptx::mbar_init(bar(kBiasFree), kComputeThreads);
     ptx::fence_mbar_init();
@@ -239,13 +242,13 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 
   if (warp == 4) {
     // =================================== TMA producer ==========================================
-    if (lane == 0) {
+    {
       uint32_t n = 0, ni = 0;
       const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
       auto acquire = [&](uint32_t bytes) -> uint32_t {   // returns the slot; arms its full barrier
         const uint32_t s = slot_of(n);
         ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
         ++n;
         return s;
       };
@@ -253,49 +256,57 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         const int b = item / p.H, h = item % p.H;
         for (int r = 0; r < NR; ++r) {                   // pass 1: q, k chunk-rows (first touch: HBM)
           uint32_t s = acquire(TOK * 128);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           s = acquire(TOK * 128);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
         }
         if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
           ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(bar(kBiasFull), C::kBiasSlab);
-          ptx::bulk_load(ptx::smem_u32(sm + C::kBias), reinterpret_cast<const uint8_t*>(p.bias2) + (size_t)h * C::kBiasSlab,
+          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kBiasFull), C::kBiasSlab);
+          if (ptx::elect_one()) ptx::bulk_load(ptx::smem_u32(sm + C::kBias), reinterpret_cast<const uint8_t*>(p.bias2) + (size_t)h * C::kBiasSlab,
                          C::kBiasSlab, bar(kBiasFull));
         }
         ++n;                                             // slot borrowed by the compute warps for the means tile
         {
           const uint32_t s = acquire(128 * 128);
-          ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
+          if (ptx::elect_one()) ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
         }
         for (int r = 0; r < NR; ++r) {                   // pass 2: k (L2), v (L2 after the prefetch)
           uint32_t s = acquire(TOK * 128);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           s = acquire(TOK * 128);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
         }
+        const int item_next = item + gridDim.x;
         for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: window pairs (L2)
+          if (item_next < p.items) {                     // warm L2 with the next item's q/k chunk-rows, a few per pair
+            const int bn = item_next / p.H, hn = item_next % p.H;
+            for (int r = pr * NR / p.n_pairs; r < (pr + 1) * NR / p.n_pairs; ++r) {
+              if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_q, 0, hn, 0, r * CH, bn, keep);
+              if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_k, 0, hn, 0, r * CH, bn, keep);
+            }
+          }
           const int w0 = 2 * pr, w1 = w0 + 1;
           const bool two = w1 < p.n_windows;
           const int x0 = (w0 % p.nwx) * W, y0 = (w0 / p.nwx) * W;
           const int x1 = (w1 % p.nwx) * W, y1 = (w1 / p.nwx) * W;
           const uint32_t bytes = (two ? 2u : 1u) * L * 128u;
           uint32_t s = acquire(bytes);                   // last use of these lines: let L2 drop them first
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b, stream);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b, stream);
           s = acquire(bytes);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b, stream);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b, stream);
           s = acquire(bytes);
-          ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b, stream);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b, stream);
         }
       }
     }
   } else if (warp == 5) {
     // =================================== MMA issuer ============================================
-    if (lane == 0) {
+    {
       constexpr uint32_t fmt = IoFmt<T>::kUmma;
       constexpr uint32_t id_pool = ptx::umma_idesc(fmt, fmt, 1, 0, 64, 8);      // A MN-major (feat), B K-major
       constexpr uint32_t id_lin = ptx::umma_idesc(ptx::kFmtF16, ptx::kFmtF16, 0, 0, 128, 128);
@@ -311,9 +322,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
       auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
       uint32_t nb = 0, ni = 0, np = 0, par_p2 = 0;   // par_p2: bit b = parity of the next P2Full[b] wait
-      Tracer tr{(p.trace && blockIdx.x == 0) ? g_trace[1] : nullptr, 0};
+      Tracer tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[1] : nullptr, 0};
+      auto mma_ss = [](uint32_t d, uint64_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ss(d, a, b_, idesc, acc); };
+      auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ts(d, a, b_, idesc, acc); };
       auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); };
-      auto free_slot = [&](uint32_t n) { ptx::umma_commit(bar(kFree0 + slot_of(n))); };
+      auto free_slot = [&](uint32_t n) { if (ptx::elect_one()) ptx::umma_commit(bar(kFree0 + slot_of(n))); };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         // ---- pass 1: chunk means ------------------------------------------------------------
         tr(101);
@@ -324,26 +337,26 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
-            ptx::umma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+            mma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
-            ptx::umma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+            mma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
           free_slot(nq);
           free_slot(nk);
         }
-        ptx::umma_commit(bar(kPoolFull));
+        if (ptx::elect_one()) ptx::umma_commit(bar(kPoolFull));
         tr(102);
         // ---- adaptive Linear: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used) ----------
         ptx::mbar_wait(bar(kAFull), ni & 1);
         // the borrowed slot was filled by the compute warps, not by TMA: complete its `full` phase by hand
         // so that the slot's phase count keeps matching the ring counter
-        ptx::mbar_arrive(bar(kFull0 + slot_of(nb + C::nAt)));
+        if (ptx::elect_one()) ptx::mbar_arrive(bar(kFull0 + slot_of(nb + C::nAt)));
         wait_full(nb + C::nW);
         ptx::tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          ptx::umma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
-        ptx::umma_commit(bar(kLinFull));
+          mma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
+        if (ptx::elect_one()) ptx::umma_commit(bar(kLinFull));
         tr(103);
         free_slot(nb + C::nW);
         ptx::mbar_wait(bar(kOmFull), ni & 1);
@@ -357,8 +370,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_ss(tmem + C::cD2 + 16 * (r & 1), dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
-          ptx::umma_commit(bar(kD2Full0 + (r & 1)));
+            mma_ss(tmem + C::cD2 + 16 * (r & 1), dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
+          if (ptx::elect_one()) ptx::umma_commit(bar(kD2Full0 + (r & 1)));
         };
         issue_d2(0);
         for (int r = 0; r < NR; ++r) {
@@ -371,13 +384,13 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
-            ptx::umma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
+            mma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
                          dP2 + (uint64_t)((r & 1) * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
-          ptx::umma_commit(bar(kP2Free0 + (r & 1)));
+          if (ptx::elect_one()) ptx::umma_commit(bar(kP2Free0 + (r & 1)));
           free_slot(nv);
           tr(110 + r);
         }
-        ptx::umma_commit(bar(kBetaFull));
+        if (ptx::elect_one()) ptx::umma_commit(bar(kBetaFull));
         ptx::mbar_wait(bar(kStatsFull), ni & 1);
         tr(120);
         ptx::tc_fence_after();
@@ -386,27 +399,31 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const uint32_t nq = nb + C::nPairs + 3 * pr, nk = nq + 1, nv = nq + 2;
           wait_full(nq);
           wait_full(nk);
+          const uint32_t cX = C::cX0 + 64 * (np & 1);
           ptx::tc_fence_after();
           const uint64_t dQ = dSlot(slot_of(nq)), dK = dSlot(slot_of(nk)), dV = dSlot(slot_of(nv));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + C::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) mma_ss(tmem + C::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+          // X[np&1] last held O of pair np-2: its epilogue must have read it (per-buffer barrier: no lapping).
+          // Only the chunk logits live there, so the local logits above are already in flight.
+          if (np >= 2) ptx::mbar_wait(bar(kOFree0 + (np & 1)), ((np >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + C::cSrfa, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
-          ptx::umma_commit(bar(kSFull));
+          for (int ks = 0; ks < 4; ++ks) mma_ss(tmem + cX, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
+          if (ptx::elect_one()) ptx::umma_commit(bar(kSFull));
           free_slot(nq);
           free_slot(nk);
           tr(130 + 2 * pr);
           ptx::mbar_wait(bar(kPFull), np & 1);
           wait_full(nv);
-          ptx::mbar_wait(bar(kOFree), (np & 1) ^ 1);
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2 * LP8 / 16; ++ks)
-            ptx::umma_ts(tmem + C::cO, tmem + C::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+            mma_ts(tmem + cX, tmem + C::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            ptx::umma_ts(tmem + C::cO, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
-          ptx::umma_commit(bar(kOFull));
+            mma_ts(tmem + cX, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
+          if (ptx::elect_one()) ptx::umma_commit(bar(kOFull0 + (np & 1)));   // per-buffer barrier: the MMA warp may run two pairs ahead of the epilogue
           free_slot(nv);
           tr(131 + 2 * pr);
         }
@@ -614,7 +631,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         tr(30 + 4 * pr);
         float sl[L], sr[CN];
         tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
-        tmem_ld_cols<CN>(trow + C::cSrfa, reinterpret_cast<uint32_t*>(sr));
+        tmem_ld_cols<CN>(trow + C::cX0 + 64 * (np_s & 1), reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
         if (pr == 1) tr(250);
         const float* brow = bias2 + ic * LS;
@@ -667,14 +684,14 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       auto epilogue_pair = [&](int pr, float sum) {
         const int wi = 2 * pr + ws;
         const bool win_ok = wi < p.n_windows;
-        ptx::mbar_wait(bar(kOFull), np_e & 1);
+        ptx::mbar_wait(bar(kOFull0 + (np_e & 1)), (np_e >> 1) & 1);
         ptx::tc_fence_after();
         tr(32 + 4 * pr);
         float o[64];
-        tmem_ld_cols<64>(trow + C::cO, reinterpret_cast<uint32_t*>(o));
+        tmem_ld_cols<64>(trow + C::cX0 + 64 * (np_e & 1), reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(bar(kOFree));
+        ptx::mbar_arrive(bar(kOFree0 + (np_e & 1)));
         if (pr == 1) tr(253);
         if (i == 0) ptx::bulk_wait_read0();            // the previous store of this window half has drained the staging rows
         ptx::named_bar_sync(2 + ws, 64);
