@@ -229,3 +229,20 @@ def test_cabi_error_paths_on_device():
     misaligned = torch.randn(1, 196, 3, 2, 66, device=dev)[..., 1:65]
     with pytest.raises(AssertionError):
         _abi.heads_view(misaligned[:, :, 0].transpose(2, 3))
+
+
+def test_host_pipeline_matches_direct_forward():
+    """efficient_attention.streaming.HostPipeline (chunked H2D / forward / D2H on three streams) must give the
+    same bits as one forward over the whole batch."""
+    from efficient_attention.streaming import HostPipeline
+    m = _bench_layer(torch.float16)
+    torch.manual_seed(7)
+    x_host = torch.randn(50, 28, 28, 192).half().pin_memory()
+    y_host = torch.empty_like(x_host).pin_memory()
+    pipe = HostPipeline(m, chunk=16)
+    for _ in range(2):            # second pass re-uses the staging buffers
+        pipe(x_host, y_host)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = m(x_host.to(_dev())).cpu()
+    assert torch.equal(y_host, want)
