@@ -40,7 +40,7 @@ constexpr int kSlotBytes = 16384;
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
   kD2Full0, kD2Full1, kP2Full0, kP2Full1, kP2Free0, kP2Free1, kBetaFull, kStatsFull,
-  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNumBars
+  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNormDone0, kNormDone1, kNumBars
 };
 
 struct Params {
@@ -227,6 +227,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kOFree1), kComputeThreads);
     ptx::mbar_init(bar(kBiasFull), 1);
     ptx::mbar_init(bar(kBiasFree), kComputeThreads);
+    ptx::mbar_init(bar(kNormDone0), kComputeThreads);
+    ptx::mbar_init(bar(kNormDone1), kComputeThreads);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
     ptx::prefetch_tmap(&tr_q); ptx::prefetch_tmap(&tr_k); ptx::prefetch_tmap(&tr_v);
@@ -375,11 +377,14 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         };
         issue_d2(0);
         for (int r = 0; r < NR; ++r) {
-          if (r + 1 < NR) issue_d2(r + 1);
           const uint32_t nk = nb + C::nPass2 + 2 * r, nv = nk + 1;
+          // K_r: its logits MMA is complete by the time the commit fires, and the compute warps have taken |k|^2
+          // from it -> hand the slot back now so that K_{r+2} is requested ~1 k cycles earlier
+          ptx::mbar_wait(bar(kNormDone0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
+          free_slot(nk);
+          if (r + 1 < NR) issue_d2(r + 1);      // after the hand-back: waiting for K_{r+1} must not delay the request of K_{r+2}
           ptx::mbar_wait(bar(kP2Full0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
           par_p2 ^= 1u << (r & 1);
-          free_slot(nk);   // K_r: its logits MMA is done and the compute warps have read it (they arrived on P2Full)
           wait_full(nv);
           ptx::tc_fence_after();
 #pragma unroll
@@ -558,6 +563,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         const uint32_t nk = nb + C::nPass2 + 2 * r;
         const uint8_t* Kr = slot_ptr(slot_of(nk));
         ptx::mbar_wait(bar(kFull0 + slot_of(nk)), par_of(nk));
+        if (r == 3) tr(260);
         float n2 = 0.f;
         if (tok_ok) {
 #pragma unroll
@@ -568,8 +574,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             n2 = fmaf(c2.x, c2.x, n2); n2 = fmaf(c2.y, c2.y, n2); n2 = fmaf(d2.x, d2.x, n2); n2 = fmaf(d2.y, d2.y, n2);
           }
         }
+        ptx::mbar_arrive(bar(kNormDone0 + (r & 1)));
+        if (r == 3) tr(261);
         ptx::mbar_wait(bar(kD2Full0 + (r & 1)), (par_d2 >> (r & 1)) & 1);
         par_d2 ^= 1u << (r & 1);
+        if (r == 3) tr(262);
         ptx::tc_fence_after();
         float dd[8];
         ptx::tmem_ld8(trow + C::cD2 + 16 * (r & 1), reinterpret_cast<uint32_t*>(dd));
@@ -580,21 +589,35 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         const float lg = tok_ok ? scale_log2 * (dsel - 0.5f * n2) : kNegInf;   // log2 units
         float* lb_ = lbuf + (r & 1) * 128;
         lb_[tid] = lg;
+        if (r == 3) tr(263);
         ptx::named_bar_sync(1, kComputeThreads);
+        if (r == 3) tr(264);
+        float lv[CH * CH];
+        const int t0 = tok_ok ? tcx * CH : 0;
+#pragma unroll
+        for (int yy = 0; yy < CH; ++yy) {
+          if constexpr (CH == 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(lb_ + yy * GW + t0);
+            lv[4 * yy] = v4.x; lv[4 * yy + 1] = v4.y; lv[4 * yy + 2] = v4.z; lv[4 * yy + 3] = v4.w;
+          } else if constexpr (CH == 2) {
+            const float2 v2 = *reinterpret_cast<const float2*>(lb_ + yy * GW + t0);
+            lv[2 * yy] = v2.x; lv[2 * yy + 1] = v2.y;
+          } else {
+#pragma unroll
+            for (int xx = 0; xx < CH; ++xx) lv[CH * yy + xx] = lb_[yy * GW + t0 + xx];
+          }
+        }
         float mx = kNegInf;
-        const int t0 = tcx * CH;
 #pragma unroll
-        for (int yy = 0; yy < CH; ++yy)
-#pragma unroll
-          for (int xx = 0; xx < CH; ++xx) mx = fmaxf(mx, lb_[tok_ok ? yy * GW + t0 + xx : 0]);
+        for (int j = 0; j < CH * CH; ++j) mx = fmaxf(mx, lv[j]);
         float sum = 0.f;
 #pragma unroll
-        for (int yy = 0; yy < CH; ++yy)
-#pragma unroll
-          for (int xx = 0; xx < CH; ++xx) sum += ex2(lb_[tok_ok ? yy * GW + t0 + xx : 0] - mx);
+        for (int j = 0; j < CH * CH; ++j) sum += ex2(lv[j] - mx);
         const float pt = ex2(lg - mx) / sum;
+        if (r == 3) tr(265);
         ptx::mbar_wait(bar(kP2Free0 + (r & 1)), (par_p2f >> (r & 1)) & 1);
         par_p2f ^= 1u << (r & 1);
+        if (r == 3) tr(266);
         if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + (r & 1) * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
@@ -693,8 +716,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kOFree0 + (np_e & 1)));
         if (pr == 1) tr(253);
-        if (i == 0) ptx::bulk_wait_read0();            // the previous store of this window half has drained the staging rows
+        const bool store_warp = (warp & 1) == 0;       // warps 0 and 2: one per window half
+        if (store_warp && ptx::elect_one()) ptx::bulk_wait_read0();   // the previous store of this half has drained the staging rows
+        if (pr == 1) tr(270);
         ptx::named_bar_sync(2 + ws, 64);
+        if (pr == 1) tr(271);
         if (i < L && win_ok) {
           const float inv = 1.0f / sum;
           uint8_t* row = ostage + ws * (LP8 * 128) + i * 128;
@@ -704,9 +730,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
                 make_uint4(IoFmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), IoFmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
                            IoFmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), IoFmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
+        if (pr == 1) tr(272);
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(2 + ws, 64);
-        if (i == 0 && win_ok) {
+        if (pr == 1) tr(273);
+        if (store_warp && win_ok && ptx::elect_one()) {
           ptx::tma_store_5d(&t_o, ptx::smem_u32(ostage + ws * (LP8 * 128)), 0, h, (wi % p.nwx) * W, (wi / p.nwx) * W, b);
           ptx::bulk_commit_group();
         }
@@ -720,9 +748,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         epilogue_pair(pr, sum_cur);
         sum_cur = sum_next;
       }
-      if (i == 0) ptx::bulk_wait_read0();   // staging rows alias phase-A tiles of the next item
+      if ((warp & 1) == 0 && ptx::elect_one()) ptx::bulk_wait_read0();   // staging rows alias phase-A tiles of the next item
     }
-    if (i == 0) ptx::bulk_wait_all();
+    if ((warp & 1) == 0 && ptx::elect_one()) ptx::bulk_wait_all();
     if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
   }
   // ---- teardown ------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@ assert path == 1
 lib = _abi.load()
 names = {1: 'item start', 2: 'pool ready', 3: 'means written', 4: 'linear ready', 5: 'omega/kbar written', 20: 'beta ready',
          21: 'beta tile written', 101: 'mma item start', 102: 'pool issued', 103: 'linear issued', 104: 'omega waited', 120: 'stats waited'}
+names.update({260: 'r3: K landed', 261: 'r3: norm done', 262: 'r3: logits ready', 263: 'r3: logit written', 264: 'r3: exchange barrier', 265: 'r3: p computed', 266: 'r3: P tile free'})
+names.update({270: 'e1: prev store drained', 271: 'e1: barrier 1', 272: 'e1: rows staged', 273: 'e1: barrier 2'})
 names.update({240: 'LN: tmem loaded', 241: 'LN: math done', 242: 'LN: k side written', 243: 'LN: barrier passed', 250: 'p1: S loaded', 251: 'p1: max done', 252: 'p1: exp/pack done', 253: 'p1: O loaded'})
 for r in range(7):
     names[10 + r] = f'pass2 row {r} P written'
