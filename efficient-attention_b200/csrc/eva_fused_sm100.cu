@@ -54,12 +54,14 @@ struct Params {
   const float* bias2;            // [H][kBiasSlab/4] fp32 bias x log2(e), row stride LS (packed by pack_params), or NULL
   void* out;
   int trace;
+  int prefetch_rows;             // chunk-rows of the NEXT item to warm in L2 during phase B (tuning knob)
+  int prefetch_v;                // warm L2 with v during pass 1
 };
 
 template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int L = W * W;
   static constexpr int LP8 = (L + 7) & ~7;
-  static constexpr int LS = L | 1;              // bias row stride (odd: conflict-free across rows)
+  static constexpr int LS = (L + 1) | 1;        // bias row stride (odd: conflict-free across rows); column L = row max
   static constexpr int NCX = GW / CH;           // chunks per chunk-row
   static constexpr int CN = NR * NCX;           // chunks per item
   static constexpr int TOK = GW * CH;           // tokens per chunk-row
@@ -261,7 +263,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           s = acquire(TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
+          if (p.prefetch_v && ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
         }
         if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
           ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
@@ -284,7 +286,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: window pairs (L2)
           if (item_next < p.items) {                     // warm L2 with the next item's q/k chunk-rows, a few per pair
             const int bn = item_next / p.H, hn = item_next % p.H;
-            for (int r = pr * NR / p.n_pairs; r < (pr + 1) * NR / p.n_pairs; ++r) {
+            for (int r = pr * p.prefetch_rows / p.n_pairs; r < (pr + 1) * p.prefetch_rows / p.n_pairs; ++r) {
               if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_q, 0, hn, 0, r * CH, bn, keep);
               if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_k, 0, hn, 0, r * CH, bn, keep);
             }
@@ -657,36 +659,41 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         tmem_ld_cols<CN>(trow + C::cX0 + 64 * (np_s & 1), reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
         if (pr == 1) tr(250);
+        // Shift by M = scale*max_j(raw) + max_j(bias) >= true row max (softmax is shift invariant; M only has to
+        // prevent overflow and sits within max|bias| of the true max, far inside fp16's range for P).
         const float* brow = bias2 + ic * LS;
         float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
         for (int j = 0; j < L; ++j) {
-          sl[j] = fmaf(sl[j], scale_log2, brow[j]);
           if ((j & 3) == 0) m0 = fmaxf(m0, sl[j]); else if ((j & 3) == 1) m1 = fmaxf(m1, sl[j]);
           else if ((j & 3) == 2) m2 = fmaxf(m2, sl[j]); else m3 = fmaxf(m3, sl[j]);
         }
+        float r0 = kNegInf, r1 = kNegInf, r2 = kNegInf, r3 = kNegInf;
 #pragma unroll
         for (int c = 0; c < CN; ++c) {
-          sr[c] *= scale_log2;
-          if ((c & 3) == 0) m0 = fmaxf(m0, sr[c]); else if ((c & 3) == 1) m1 = fmaxf(m1, sr[c]);
-          else if ((c & 3) == 2) m2 = fmaxf(m2, sr[c]); else m3 = fmaxf(m3, sr[c]);
+          if ((c & 3) == 0) r0 = fmaxf(r0, sr[c]); else if ((c & 3) == 1) r1 = fmaxf(r1, sr[c]);
+          else if ((c & 3) == 2) r2 = fmaxf(r2, sr[c]); else r3 = fmaxf(r3, sr[c]);
         }
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float bmax = p.bias2 ? brow[L] : 0.f;
+        const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2 + bmax;
+        const float mrfa = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * scale_log2;
+        const float mx = fmaxf(mloc, mrfa);
         if (pr == 1) tr(251);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         uint32_t pl[LP8 / 2], prf[32], zeros[LP8 / 2];
 #pragma unroll
         for (int j = 0; j < LP8 / 2; ++j) {
-          const float a = (2 * j < L) ? ex2(sl[(2 * j < L) ? 2 * j : 0] - mx) : 0.f;
-          const float c2 = (2 * j + 1 < L) ? ex2(sl[(2 * j + 1 < L) ? 2 * j + 1 : 0] - mx) : 0.f;
+          const float a = (2 * j < L) ? ex2(fmaf(sl[(2 * j < L) ? 2 * j : 0], scale_log2, brow[(2 * j < L) ? 2 * j : 0] - mx)) : 0.f;
+          const float c2 = (2 * j + 1 < L) ? ex2(fmaf(sl[(2 * j + 1 < L) ? 2 * j + 1 : 0], scale_log2, brow[(2 * j + 1 < L) ? 2 * j + 1 : 0] - mx)) : 0.f;
           if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
           pl[j] = IoFmt<T>::pack2(a, c2);
           zeros[j] = 0u;
         }
+        const float nmx = -mx;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float a = (2 * j < CN) ? ex2(sr[(2 * j < CN) ? 2 * j : 0] - mx) : 0.f;
-          const float c2 = (2 * j + 1 < CN) ? ex2(sr[(2 * j + 1 < CN) ? 2 * j + 1 : 0] - mx) : 0.f;
+          const float a = (2 * j < CN) ? ex2(fmaf(sr[(2 * j < CN) ? 2 * j : 0], scale_log2, nmx)) : 0.f;
+          const float c2 = (2 * j + 1 < CN) ? ex2(fmaf(sr[(2 * j + 1 < CN) ? 2 * j + 1 : 0], scale_log2, nmx)) : 0.f;
           if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
           prf[j] = IoFmt<T>::pack2(a, c2);
         }
@@ -774,7 +781,14 @@ __global__ void pack_params(const float* __restrict__ wq, const float* __restric
   if (bias) {
     for (int j = idx; j < H * slab_floats; j += gridDim.x * blockDim.x) {
       const int h = j / slab_floats, o = j % slab_floats, r = o / LS, c = o % LS;
-      bias2[j] = (r < L && c < L) ? bias[(long long)h * bias_sh + r * L + c] * kLog2e : 0.f;
+      float val = 0.f;
+      if (r < L && c < L) {
+        val = bias[(long long)h * bias_sh + r * L + c] * kLog2e;
+      } else if (r < L && c == L) {      // row maximum: lets the softmax bound its max without touching the bias
+        val = -INFINITY;
+        for (int cc = 0; cc < L; ++cc) val = fmaxf(val, bias[(long long)h * bias_sh + r * L + cc] * kLog2e);
+      }
+      bias2[j] = val;
     }
   }
 }
@@ -819,6 +833,11 @@ static bool make_weight_map(CUtensorMap* tm, const void* w16) {
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w16), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 static int trace_enabled() {
@@ -870,6 +889,8 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.mu_coeff = ada.mu_coeff; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out;
   p.trace = trace_enabled();
+  p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", NR);
+  p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
   auto kern = eva_fused_kernel<T, W, GW, CH, NR>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
@@ -914,7 +935,7 @@ bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, c
 }
 
 size_t fused_workspace_bytes(const Geo& g) {
-  const int L = g.window * g.window, LS = L | 1;
+  const int L = g.window * g.window, LS = (L + 1) | 1;
   return 128 * 64 * sizeof(__half) + (size_t)g.H * ((L * LS * 4 + 15) & ~15);
 }
 

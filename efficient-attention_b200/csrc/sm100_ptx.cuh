@@ -51,11 +51,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same, but lets the hardware park the thread for up to `ns` nanoseconds (woken early when the phase
+// completes): waiting warps stop burning issue slots of the co-resident CTA
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 // The slow path is kept out of line so that the ~dozen wait sites stay small.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_suspend(bar, parity, 2000)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("eva fused kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              bar, parity);
