@@ -246,3 +246,58 @@ def test_host_pipeline_matches_direct_forward():
     with torch.no_grad():
         want = m(x_host.to(_dev())).cpu()
     assert torch.equal(y_host, want)
+
+
+@pytest.mark.parametrize('grid,chunk', [(14, 2), (28, 4)])
+@pytest.mark.parametrize('adaptive', ['default', 'no-ln', 'none'])
+@pytest.mark.parametrize('with_noise,with_bias', [(False, True), (True, False), (True, True)])
+def test_fused_kernel_variants_fp16(grid, chunk, adaptive, with_noise, with_bias):
+    """Every option the fused tcgen05/TMA kernel implements (adaptive_proj variants, training noise, optional
+    bias) on both instantiated geometries, against the oracle on identical fp16 inputs.  The call must take
+    the fused path (path == 1): a silent fall-back to the generic kernels would hide a regression."""
+    from efficient_attention import _abi
+    B, H, d, w = 3, 3, 64, 7
+    N = grid * grid
+    g = torch.Generator().manual_seed(grid * 100 + len(adaptive) * 10 + int(with_noise) * 2 + int(with_bias))
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.1).half()
+    bias = 0.5 * torch.randn(H, 49, 49, generator=g) if with_bias else None
+    ada = _rand_ada(d, g, ln=(adaptive != 'no-ln'))
+    if adaptive == 'none':
+        ada.update(wq=None, bq=None, gq=None, betq=None)
+    noise = torch.randn(B, H, 49, d, generator=g) if with_noise else None
+    q64, k64, v64 = (qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3))
+    want = O.eva_core(q64, k64, v64, seq_shape=(grid, grid), window=w, ext=0, chunk=chunk, chunk_ext=0,
+                      **{k_: (v_.double() if v_ is not None else None) for k_, v_ in ada.items()}, mu_coeff=0.5,
+                      use_q=(adaptive != 'none'), noise=noise.double() if with_noise else None,
+                      bias=bias.double() if with_bias else None)
+    want = want.permute(0, 2, 1, 3).reshape(B, N, H * d)
+    dev = _dev()
+    qd = qkv.to(dev)
+    geom = _abi.eva_geometry(qd[:, :, 0], seq_shape=(grid, grid), window=w, ext=0, chunk=chunk, chunk_ext=0)
+    out, path = _abi.eva_forward(qd[:, :, 0], qd[:, :, 1], qd[:, :, 2], geom, _abi_ada(ada, dev, 0.5),
+                                 noise=noise.to(dev) if with_noise else None, bias=bias.to(dev) if with_bias else None,
+                                 return_path=True)
+    assert path == 1
+    err = rel_l2(out.cpu(), want)
+    assert err < TOL_F16, (grid, adaptive, with_noise, with_bias, err)
+
+
+def test_fused_kernel_many_items_per_cta_fp16():
+    """More (batch, head) items than resident CTAs (2 x 148): every CTA loops over several items, which
+    exercises the ring / barrier phase bookkeeping across items; checked against the generic kernels."""
+    from efficient_attention import _abi
+    B, H, d = 400, 3, 64
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    qkv = (torch.randn(B, 196, 3, H, d, generator=g) * 1.1).half().to(dev)
+    bias = (0.5 * torch.randn(H, 49, 49, generator=g)).to(dev)
+    ada = _abi_ada(_rand_ada(d, g), dev, 0.5)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+    out, path = _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
+    assert path == 1
+    kb, bt = _abi.eva_chunk_stats(q, k, v, geom, ada)
+    ref = _abi.eva_window_attention(q, k, v, geom, k_bar=kb, beta=bt, bias=bias)
+    per_item = ((out.float() - ref.float()).view(B, 196, H, d).pow(2).sum((1, 3)).sqrt() /
+                ref.float().view(B, 196, H, d).pow(2).sum((1, 3)).sqrt())
+    assert float(per_item.max()) < TOL_F16, float(per_item.max())
