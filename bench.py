@@ -34,6 +34,16 @@ METRIC = 'EVA attn fwd tokens/sec at N=784,d=192'
 WORKLOAD = 'c3: EVA layer fwd, N=784 (28x28), C=192, h=3, d=64, window 7, 49 landmarks, 2-D RPE, eval'
 
 
+def ncu_traffic(batch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this bench
+    configuration (profiles/r01/ncu_traffic.json); None when the capture was taken at another batch size."""
+    path = os.path.join(ROOT, 'profiles', 'r01', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    return d['dram_bytes_read'] + d['dram_bytes_write'] if d.get('batch_per_gpu') == batch else None
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -221,13 +231,18 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            torch.cuda.synchronize()
-            ev0.record()
-            for _ in range(K):
-                core()
-            ev1.record()
-            torch.cuda.synchronize()
+        clk = ClockSampler(local)
+        clk.__enter__()                      # sampled over both timed regions (core and e2e)
+        torch.cuda.synchronize()
+        per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        ev0.record()
+        for a_, b_ in per_launch:
+            a_.record()
+            core()
+            b_.record()
+        ev1.record()
+        torch.cuda.synchronize()
+        launch_ms = sum(a_.elapsed_time(b_) for a_, b_ in per_launch) / K     # device time of one eva_forward launch
         core_ms = reduce_max_ms(ev0.elapsed_time(ev1), dev, world)
         if world > 1:
             dist.barrier()
@@ -253,13 +268,14 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         e2e_ms = reduce_max_ms(e0.elapsed_time(e1), dev, world)
+        clk.__exit__(None, None, None)
 
     if rank == 0:
         tokens_per_step = aggregate_tokens(B, world)
         value = tokens_per_step * K / (core_ms * 1e-3)
         peak, peak_src = peaks()
         algo_bytes = 4 * DIM * elem * B * TOKENS           # read q,k,v once + write o once, per launch/rank
-        achieved = algo_bytes / (core_ms / K * 1e-3) / 1e9
+        achieved = algo_bytes / (launch_ms * 1e-3) / 1e9     # algorithmic bytes / average launch duration (CUDA events)
         out = {
             'metric': METRIC, 'value': value, 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': max(Wm, 3),
             'ms_per_step': core_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -268,7 +284,9 @@ def run_ours(args):
                        'l2_policy': f'inputs larger than L2 (qkv {3 * DIM * elem * B * TOKENS / 2**20:.0f} MiB per GPU)',
                        'kernel_path': 'fused tcgen05/TMA' if path == 1 else 'generic two-stage CUDA-core'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': ncu_traffic(B), 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': algo_bytes, 'launch_ms': launch_ms,
+                         'launches_timed': K,
                          'algorithmic_bytes_per_token': 4 * DIM * elem},
             'e2e': {'value': tokens_per_step * Ke / (e2e_ms * 1e-3), 'unit': 'tokens/s',
                     'h2d_bytes_per_step': x_host.numel() * elem, 'd2h_bytes_per_step': y_host.numel() * elem,

@@ -453,6 +453,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     const bool tok_ok = tid < TOK;
     uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0, par_d2 = 0, par_p2f = 3;   // bit b = parity of the next wait on buffer b
     uint8_t* const ostage = sm + C::kOStage;
+    const uint64_t out_policy = ptx::policy_evict_first();
     Tracer tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
       const int b = item / p.H, h = item % p.H;
@@ -742,7 +743,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::named_bar_sync(2 + ws, 64);
         if (pr == 1) tr(273);
         if (store_warp && win_ok && ptx::elect_one()) {
-          ptx::tma_store_5d(&t_o, ptx::smem_u32(ostage + ws * (LP8 * 128)), 0, h, (wi % p.nwx) * W, (wi / p.nwx) * W, b);
+          // the output is never re-read here: evict-first keeps L2 for the q/k/v lines that are
+          ptx::tma_store_5d_hint(&t_o, ptx::smem_u32(ostage + ws * (LP8 * 128)), 0, h, (wi % p.nwx) * W, (wi / p.nwx) * W, b, out_policy);
           ptx::bulk_commit_group();
         }
         tr(33 + 4 * pr);

@@ -131,6 +131,11 @@ __device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d_hint(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the N most recent bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
