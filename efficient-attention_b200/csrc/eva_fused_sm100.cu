@@ -4,15 +4,18 @@
 //   pass 1   chunk means:      [feat x chunk]   = Q_r^T . Pool^T, K_r^T . Pool^T       (M=64 MMAs, A MN-major)
 //            adaptive Linear:  [chunk x feat]   = [mq ; mk] . [W_q ; W_k]^T            (M=128 MMA) -> LayerNorm
 //            -> k_bar tile, omega tile                                                  (eva.py:155-190)
-//   pass 2   phi-logits:       [token x chunk]  = K_r . Omega_r^T                      (M=128 MMA)
-//            16-token softmax per chunk (SIMT) -> P tile;  beta^T = V_r^T . P^T         (M=64 MMA)
+//   pass 2   phi-logits:       [token x chunk]  = K_r . (Qbar_r + Kbar_r)^T            (M=128 MMAs, all rows first)
+//            16-token softmax per chunk (SIMT, one batch for the item) -> P tiles;
+//            beta^T = V_r^T . P_r^T                                                     (M=64 MMAs)
 //            -> beta tile                                                               (eva.py:192-196)
 //   phase B  per pair of windows: S = Q [K_w ; k_bar]^T, joint row softmax (TMEM -> RF), P -> TMEM,
 //            O = P [V_w ; beta] (A operand from TMEM), normalise, store                 (eva.py:200-227)
 //
-// q/k/v reach the SM only through TMA: chunk-row boxes (pass 1: q,k from HBM; pass 2: k from L2, v prefetched
-// into L2 during pass 1) and window boxes (phase B, L2 hits).  All tiles travel through one ring of four
-// 16-KB shared-memory slots with full/free mbarriers; the means tile of the Linear step borrows a ring slot.
+// q/k/v reach the SM only through TMA: chunk-row boxes (pass 1: q,k from HBM; pass 2: all k rows from L2, then
+// all v rows) and window boxes (phase B, L2 hits).  All tiles travel through one ring of four 16-KB
+// shared-memory slots with full/free mbarriers; the means tile of the Linear step borrows a ring slot.
+// Chunks are indexed c' = 8 r + cx everywhere (chunk-row r, column cx < 7; every 8th row / column is padding),
+// so that the k_bar tile serves both as the second B operand of the phi-logits and as the chunk keys of phase B.
 //
 // CTA = 6 warps: warps 0-3 compute (thread t <-> TMEM lane t), warp 4 = TMA producer, warp 5 = MMA issuer.
 // Two CTAs per SM (256 TMEM columns, ~105 KB shared memory each).
@@ -39,8 +42,8 @@ constexpr int kSlotBytes = 16384;
 
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
-  kD2Full0, kD2Full1, kP2Full0, kP2Full1, kP2Free0, kP2Free1, kBetaFull, kStatsFull,
-  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNormDone0, kNormDone1, kNumBars
+  kD2Full, kP2Full, kBetaFull, kStatsFull,
+  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNormDone0, kNumBars = kNormDone0 + 7
 };
 
 struct Params {
@@ -49,7 +52,7 @@ struct Params {
   int items;
   const float *b_q, *g_q, *beta_q, *b_k, *g_k, *beta_k;
   int has_q;                     // 0: adaptive_proj == 'none' (mu = 0)
-  float mu_coeff, ln_eps;
+  float mu_coeff, inv_mu_coeff, ln_eps;
   const float* noise;
   const float* bias2;            // [H][kBiasSlab/4] fp32 bias x log2(e), row stride LS (packed by pack_params), or NULL
   void* out;
@@ -64,22 +67,28 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int LS = (L + 1) | 1;        // bias row stride (odd: conflict-free across rows); column L = row max
   static constexpr int NCX = GW / CH;           // chunks per chunk-row
   static constexpr int CN = NR * NCX;           // chunks per item
+  static constexpr int CNP = 8 * NR;            // padded chunk index space: c' = 8 r + cx
   static constexpr int TOK = GW * CH;           // tokens per chunk-row
   static constexpr int KS = (TOK + 15) / 16;    // k-steps over the tokens of a chunk-row
   static constexpr int KBLK = (TOK + 63) / 64;  // 64-token K blocks of the Pool / P2 tiles
   static constexpr int JC = CH * CH;
-  static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOK <= 128 && L <= 64 && CN <= 64, "geometry");
+  static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOK <= 128 && L <= 64 && CNP <= 64, "geometry");
+  __host__ __device__ static constexpr bool chunk_ok(int c) { return c < CNP && (c & 7) < NCX; }
   // shared memory map (bytes from the 1024-aligned base)
   static constexpr int kSlot = 0;
-  static constexpr int kKbar = kSlots * kSlotBytes;    // [64][128 B]  k_bar, row = chunk c
-  static constexpr int kBeta = kKbar + 8192;           // [64][128 B]  beta,  row = chunk c
-  static constexpr int kOm = kBeta + 8192;             // [64][128 B]  omega, row = 8r + cx
-  static constexpr int kLbuf = kOm + 8192;             // 2 x [128] fp32 logit exchange
-  // phase B re-uses [kOm, kP2) as the output staging: window a at +0, window b at +LP8*128 (swizzled rows)
+  static constexpr int kKbar = kSlots * kSlotBytes;    // [64][128 B]  k_bar, row = c'
+  static constexpr int kBeta = kKbar + 8192;           // [64][128 B]  beta,  row = c'
+  static constexpr int kOm = kBeta + 8192;             // [64][128 B]  q_bar (+ noise), row = c'
+  // Three things share [kOm, kLbuf), one after the other: the q_bar tile (until the phi-logit MMAs are done), the
+  // NR softmax tiles P2 of pass 2 (until the beta MMAs are done), the output staging of phase B
+  // (window a at +0, window b at +LP8*128, swizzled rows).
+  static constexpr int kP2 = kOm;                      // NR x KBLK x [8][128 B]
+  static constexpr int kP2Bytes = NR * KBLK * 1024;
   static constexpr int kOStage = kOm;
-  static constexpr int kOStageEnd = kOStage + LP8 * 128 + L * 128;
-  static constexpr int kP2 = ((kLbuf + 1024 > kOStageEnd ? kLbuf + 1024 : kOStageEnd) + 1023) & ~1023;   // 2 x KBLK x [8][128 B]
-  static constexpr int kPool = kP2 + 2 * KBLK * 1024;  // KBLK x [8][128 B] pooling weights (constant)
+  static constexpr int kOStageBytes = LP8 * 128 + L * 128;
+  static constexpr int kShared = kP2Bytes > kOStageBytes ? (kP2Bytes > 8192 ? kP2Bytes : 8192) : (kOStageBytes > 8192 ? kOStageBytes : 8192);
+  static constexpr int kLbuf = (kOm + kShared + 1023) & ~1023;   // NR x [128] fp32 logit exchange
+  static constexpr int kPool = kLbuf + ((NR * 128 * 4 + 1023) & ~1023);   // KBLK x [8][128 B] pooling weights (constant)
   static constexpr int kBias = kPool + KBLK * 1024;    // [L][LS] fp32, x log2(e)
   static constexpr int kBiasSlab = (L * LS * 4 + 15) & ~15;
   static constexpr int kZeroEnd = kBias + kBiasSlab;
@@ -89,16 +98,16 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int kBytes = kTmemPtr + 16;
   static constexpr int kDynamic = kBytes + 1024;
   static_assert(kDynamic <= 115712, "two CTAs per SM need <= 113 KB each");
-  static_assert(CN * 65 * 4 <= kSlotBytes, "k_bar staging must fit in the borrowed slot");
   // TMEM columns
-  static constexpr uint32_t cPoolQ = 0, cPoolK = 56;   // pass 1: [feat x (8r+cx)]; stays clear of the X buffers
-  static constexpr uint32_t cLin = 0;                  // Linear: [chunk-row x 128]
-  static constexpr uint32_t cBetaT = 0;                // pass 2: [feat x (8r+cx)]
-  static constexpr uint32_t cD2 = 224;                 // pass 2: 2 x [token x 16]
+  static constexpr uint32_t cPoolQ = 0, cPoolK = 56;   // pass 1: [feat x c']; stays clear of the X buffers
+  static constexpr uint32_t cLin = 0;                  // Linear: [c' x 128]
+  static constexpr uint32_t cBetaT = 0;                // pass 2: [feat x c']
+  static constexpr uint32_t cD2 = 128;                 // pass 2: NR x [token x 16]
+  static_assert(cD2 + 16 * NR <= 256, "TMEM budget (pass 2)");
   // phase B: local logits / P in [0, 2*LP8); chunk logits of pair p and later its O share buffer X[p&1]
   static constexpr uint32_t cSloc = 0, cX0 = 2 * LP8, cPloc = 0, cPrfa = LP8;
   static_assert(2 * LP8 + 128 <= 256 && (2 * LP8) % 16 == 0, "TMEM budget");
-  // loads per item, in ring order
+  // loads per item, in ring order: NR x (q_r, k_r) | means (borrowed) | W | NR x k_r | NR x v_r | pairs x (q, k, v)
   static constexpr int nAt = 2 * NR, nW = 2 * NR + 1, nPass2 = 2 * NR + 2, nPairs = 4 * NR + 2;
 };
 
@@ -162,7 +171,7 @@ __device__ __forceinline__ uint32_t par_of(uint32_t n) { return (n >> 2) & 1u; }
 
 // optional phase trace of CTA 0 (EVA_SM100_TRACE=1): [0] compute thread 0, [1] MMA thread; pairs (event, clock64)
 constexpr int kTraceLen = 8192;
-__device__ unsigned long long g_trace[2][kTraceLen];
+__device__ unsigned long long g_trace[3][kTraceLen];   // [2] = TMA thread: (1000 + ring position in item, clock) at issue
 struct Tracer {
   unsigned long long* buf;
   int n;
@@ -178,7 +187,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
                  const __grid_constant__ CUtensorMap tr_k, const __grid_constant__ CUtensorMap tr_v,
                  const __grid_constant__ CUtensorMap t_w, const __grid_constant__ CUtensorMap t_o, const Params p) {
   using C = Cfg<W, GW, CH, NR>;
-  constexpr int L = C::L, LP8 = C::LP8, LS = C::LS, CN = C::CN, NCX = C::NCX, TOK = C::TOK, KS = C::KS;
+  constexpr int L = C::L, LP8 = C::LP8, LS = C::LS, CN = C::CN, CNP = C::CNP, NCX = C::NCX, TOK = C::TOK, KS = C::KS;
   extern __shared__ uint8_t smem_raw[];
   // align by offset arithmetic (not by integer round trip) so the compiler keeps the shared address space
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -189,6 +198,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   uint8_t* P2t = sm + C::kP2;
   float* bias2 = reinterpret_cast<float*>(sm + C::kBias);
   float* lbuf = reinterpret_cast<float*>(sm + C::kLbuf);
+  static_assert(NR <= 7, "one kNormDone barrier per chunk-row");
   const uint32_t bars = ptx::smem_u32(sm + C::kBars);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + C::kTmemPtr);
   auto bar = [&](int i) { return bars + 8u * i; };
@@ -213,12 +223,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kAFull), kComputeThreads);
     ptx::mbar_init(bar(kLinFull), 1);
     ptx::mbar_init(bar(kOmFull), kComputeThreads);
-    ptx::mbar_init(bar(kD2Full0), 1);
-    ptx::mbar_init(bar(kD2Full1), 1);
-    ptx::mbar_init(bar(kP2Full0), kComputeThreads);
-    ptx::mbar_init(bar(kP2Full1), kComputeThreads);
-    ptx::mbar_init(bar(kP2Free0), 1);
-    ptx::mbar_init(bar(kP2Free1), 1);
+    ptx::mbar_init(bar(kD2Full), 1);
+    ptx::mbar_init(bar(kP2Full), kComputeThreads);
     ptx::mbar_init(bar(kBetaFull), 1);
     ptx::mbar_init(bar(kStatsFull), kComputeThreads);
     ptx::mbar_init(bar(kSFull), 1);
@@ -229,8 +235,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kOFree1), kComputeThreads);
     ptx::mbar_init(bar(kBiasFull), 1);
     ptx::mbar_init(bar(kBiasFree), kComputeThreads);
-    ptx::mbar_init(bar(kNormDone0), kComputeThreads);
-    ptx::mbar_init(bar(kNormDone1), kComputeThreads);
+    for (int r = 0; r < NR; ++r) ptx::mbar_init(bar(kNormDone0 + r), kComputeThreads);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
     ptx::prefetch_tmap(&tr_q); ptx::prefetch_tmap(&tr_k); ptx::prefetch_tmap(&tr_v);
@@ -247,16 +252,19 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   if (warp == 4) {
     // =================================== TMA producer ==========================================
     {
-      uint32_t n = 0, ni = 0;
+      uint32_t n = 0, ni = 0, n_item0 = 0;
       const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
+      Tracer tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[2] : nullptr, 0};
       auto acquire = [&](uint32_t bytes) -> uint32_t {   // returns the slot; arms its full barrier
         const uint32_t s = slot_of(n);
         ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
+        tr(1000 + (int)(n - n_item0));
         if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
         ++n;
         return s;
       };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni) {
+        n_item0 = n;
         const int b = item / p.H, h = item % p.H;
         for (int r = 0; r < NR; ++r) {                   // pass 1: q, k chunk-rows (first touch: HBM)
           uint32_t s = acquire(TOK * 128);
@@ -276,10 +284,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const uint32_t s = acquire(128 * 128);
           if (ptx::elect_one()) ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
         }
-        for (int r = 0; r < NR; ++r) {                   // pass 2: k (L2), v (L2 after the prefetch)
-          uint32_t s = acquire(TOK * 128);
+        for (int r = 0; r < NR; ++r) {                   // pass 2: all k rows (L2 hits) ...
+          const uint32_t s = acquire(TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          s = acquire(TOK * 128);
+        }
+        for (int r = 0; r < NR; ++r) {                   // ... then all v rows (first touch); the first ones land under the softmax
+          const uint32_t s = acquire(TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
         }
         const int item_next = item + gridDim.x;
@@ -307,6 +317,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b, stream);
         }
       }
+      if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
     }
   } else if (warp == 5) {
     // =================================== MMA issuer ============================================
@@ -325,11 +336,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       const uint64_t dP2 = ptx::umma_desc_sw128(ptx::smem_u32(P2t));
       // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
       auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
-      uint32_t nb = 0, ni = 0, np = 0, par_p2 = 0;   // par_p2: bit b = parity of the next P2Full[b] wait
+      uint32_t nb = 0, ni = 0, np = 0;
       Tracer tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[1] : nullptr, 0};
       auto mma_ss = [](uint32_t d, uint64_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ss(d, a, b_, idesc, acc); };
       auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ts(d, a, b_, idesc, acc); };
-      auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); };
+      auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); tr(2000 + (int)(n - nb)); };
       auto free_slot = [&](uint32_t n) { if (ptx::elect_one()) ptx::umma_commit(bar(kFree0 + slot_of(n))); };
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         // ---- pass 1: chunk means ------------------------------------------------------------
@@ -362,42 +373,47 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           mma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
         if (ptx::elect_one()) ptx::umma_commit(bar(kLinFull));
         tr(103);
+        // both tiles are dead once the Linear MMA has completed: hand the slots back now so that the first k rows of
+        // pass 2 are requested while the compute warps are still in the LayerNorm
         free_slot(nb + C::nW);
-        ptx::mbar_wait(bar(kOmFull), ni & 1);
-        tr(104);      // omega / k_bar tiles written, staging in the borrowed slot dead
         free_slot(nb + C::nAt);
+        ptx::mbar_wait(bar(kOmFull), ni & 1);
+        tr(104);      // q_bar / k_bar tiles written
         ptx::tc_fence_after();
-        // ---- pass 2: logits one row ahead of beta ------------------------------------------------
-        auto issue_d2 = [&](int r) {
-          const uint32_t nk = nb + C::nPass2 + 2 * r;
+        // ---- pass 2: phi-logits of every chunk-row, D2_r = K_r (Qbar_r + Kbar_r)^T ------------------------
+        for (int r = 0; r < NR; ++r) {
+          const uint32_t nk = nb + C::nPass2 + r;
           wait_full(nk);
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            mma_ss(tmem + C::cD2 + 16 * (r & 1), dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
-          if (ptx::elect_one()) ptx::umma_commit(bar(kD2Full0 + (r & 1)));
-        };
-        issue_d2(0);
-        for (int r = 0; r < NR; ++r) {
-          const uint32_t nk = nb + C::nPass2 + 2 * r, nv = nk + 1;
-          // K_r: its logits MMA is complete by the time the commit fires, and the compute warps have taken |k|^2
-          // from it -> hand the slot back now so that K_{r+2} is requested ~1 k cycles earlier
-          ptx::mbar_wait(bar(kNormDone0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
+            mma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
+          if (p.has_q) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dKB + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, 1);
+          }
+          // the compute warps take |k|^2 from the same tile: hand it back when both are done
+          ptx::mbar_wait(bar(kNormDone0 + r), ni & 1);
           free_slot(nk);
-          if (r + 1 < NR) issue_d2(r + 1);      // after the hand-back: waiting for K_{r+1} must not delay the request of K_{r+2}
-          ptx::mbar_wait(bar(kP2Full0 + (r & 1)), (par_p2 >> (r & 1)) & 1);
-          par_p2 ^= 1u << (r & 1);
+        }
+        if (ptx::elect_one()) ptx::umma_commit(bar(kD2Full));
+        tr(110);
+        // ---- beta^T += V_r^T P_r^T once the softmax batch is in shared memory ----------------------------
+        ptx::mbar_wait(bar(kP2Full), ni & 1);
+        ptx::tc_fence_after();
+        for (int r = 0; r < NR; ++r) {
+          const uint32_t nv = nb + C::nPass2 + NR + r;
           wait_full(nv);
           ptx::tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
             mma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
-                         dP2 + (uint64_t)((r & 1) * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
-          if (ptx::elect_one()) ptx::umma_commit(bar(kP2Free0 + (r & 1)));
+                         dP2 + (uint64_t)(r * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
           free_slot(nv);
-          tr(110 + r);
         }
         if (ptx::elect_one()) ptx::umma_commit(bar(kBetaFull));
+        tr(111);
         ptx::mbar_wait(bar(kStatsFull), ni & 1);
         tr(120);
         ptx::tc_fence_after();
@@ -451,17 +467,16 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     // pass 2: token of the chunk-row owned by this thread
     const int tcx = (tid % GW) / CH;
     const bool tok_ok = tid < TOK;
-    uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0, par_d2 = 0, par_p2f = 3;   // bit b = parity of the next wait on buffer b
+    uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0;
     uint8_t* const ostage = sm + C::kOStage;
     const uint64_t out_policy = ptx::policy_evict_first();
     Tracer tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
       const int b = item / p.H, h = item % p.H;
       tr(1);
-      // ---- pass 1 readback: means^T (TMEM) -> fp16 means tile [chunk][feat] in the borrowed slot -----
+      // ---- pass 1 readback: means^T (TMEM) -> fp16 means tile [c'][feat] in the borrowed slot ----------
       const uint32_t nat = nb + C::nAt;
       uint8_t* At = slot_ptr(slot_of(nat));
-      float* stage = reinterpret_cast<float*>(At);    // [CN][65] fp32 k_bar, valid after the Linear MMA
       ptx::mbar_wait(bar(kFree0 + slot_of(nat)), par_of(nat) ^ 1);
       ptx::mbar_wait(bar(kPoolFull), ni & 1);
       ptx::tc_fence_after();
@@ -471,14 +486,14 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         tmem_ld_cols<8 * NR>(trow + C::cPoolQ, reinterpret_cast<uint32_t*>(mq));
         tmem_ld_cols<8 * NR>(trow + C::cPoolK, reinterpret_cast<uint32_t*>(mk));
         ptx::tmem_ld_wait();
-        if (feat_lane) {
+        if (feat_lane) {   // padding rows (cx >= NCX) keep whatever the slot held: their Linear rows are never used
 #pragma unroll
           for (int r = 0; r < NR; ++r)
 #pragma unroll
             for (int cx = 0; cx < NCX; ++cx) {
-              const int c = r * NCX + cx;
-              *reinterpret_cast<uint16_t*>(At + tile_off(c, feat)) = f16_bits(mq[8 * r + cx]);
-              *reinterpret_cast<uint16_t*>(At + tile_off(64 + c, feat)) = f16_bits(mk[8 * r + cx]);
+              const int c = 8 * r + cx;
+              *reinterpret_cast<uint16_t*>(At + tile_off(c, feat)) = f16_bits(mq[c]);
+              *reinterpret_cast<uint16_t*>(At + tile_off(64 + c, feat)) = f16_bits(mk[c]);
             }
         }
       }
@@ -486,7 +501,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kAFull));
       tr(3);
-      // ---- Linear result -> bias, LayerNorm; rows 0-63 = q side, rows 64-127 = k side ------------
+      // ---- Linear result -> bias, LayerNorm; lanes 0-63 = q side, lanes 64-127 = k side, lane & 63 = c' ----
       ptx::mbar_wait(bar(kLinFull), ni & 1);
       ptx::tc_fence_after();
       tr(4);
@@ -529,105 +544,114 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           }
         }
         tr(241);
-        const bool valid = i < CN;
-        if (ws == 1 && valid) {   // k side: k_bar tile (B operand of the chunk logits) + fp32 copy for mu
+        if (C::chunk_ok(i)) {
+          uint8_t* const dst = (ws ? KBt : OMt) + i * 128;
+          if (ws == 0) {
+            // q side: omega = mu_coeff (q_bar + k_bar) + noise is applied as  mu_coeff ((q_bar + noise / mu_coeff) + k_bar):
+            // the phi-logit MMAs accumulate K_r q'^T and K_r k_bar^T, so the two halves never have to meet in a thread
+            const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * CN + (i >> 3) * NCX + (i & 7)) * 64 : nullptr;
+#pragma unroll
+            for (int e4 = 0; e4 < 16; ++e4) {
+              float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (nz) z = __ldg(reinterpret_cast<const float4*>(nz) + e4);
+              if (p.has_q) {
+                y[4 * e4] = fmaf(z.x, p.inv_mu_coeff, y[4 * e4]); y[4 * e4 + 1] = fmaf(z.y, p.inv_mu_coeff, y[4 * e4 + 1]);
+                y[4 * e4 + 2] = fmaf(z.z, p.inv_mu_coeff, y[4 * e4 + 2]); y[4 * e4 + 3] = fmaf(z.w, p.inv_mu_coeff, y[4 * e4 + 3]);
+              } else {
+                y[4 * e4] = z.x; y[4 * e4 + 1] = z.y; y[4 * e4 + 2] = z.z; y[4 * e4 + 3] = z.w;
+              }
+            }
+          }
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            *reinterpret_cast<uint4*>(KBt + i * 128 + ((ch ^ (i & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(dst + ((ch ^ (i & 7)) << 4)) =
                 make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
                            IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7]));
-#pragma unroll
-          for (int e = 0; e < 64; ++e) stage[i * 65 + e] = y[e];
-        }
-        tr(242);
-        ptx::named_bar_sync(1, kComputeThreads);
-        tr(243);
-        if (ws == 0 && valid) {   // q side: omega = mu_coeff (q_bar + k_bar) [+ noise] -> omega tile row 8r+cx
-          const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * CN + i) * 64 : nullptr;
-          const int orow = 8 * (i / NCX) + i % NCX;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              o[e] = p.has_q ? p.mu_coeff * (y[8 * ch + e] + stage[i * 65 + 8 * ch + e]) : 0.f;
-              if (nz) o[e] += __ldg(nz + 8 * ch + e);
-            }
-            *reinterpret_cast<uint4*>(OMt + orow * 128 + ((ch ^ (orow & 7)) << 4)) =
-                make_uint4(IoFmt<T>::pack2(o[0], o[1]), IoFmt<T>::pack2(o[2], o[3]), IoFmt<T>::pack2(o[4], o[5]), IoFmt<T>::pack2(o[6], o[7]));
-          }
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar(kOmFull));
       tr(5);
-      // ---- pass 2: per chunk-row, p_t = softmax over the 16 tokens of my chunk -> P2 tile ------------
+      // ---- pass 2: |k|^2 of my token in every chunk-row while the rows stream through the ring ---------
+      float n2[NR];
+#pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const uint32_t nk = nb + C::nPass2 + 2 * r;
+        const uint32_t nk = nb + C::nPass2 + r;
         const uint8_t* Kr = slot_ptr(slot_of(nk));
         ptx::mbar_wait(bar(kFull0 + slot_of(nk)), par_of(nk));
-        if (r == 3) tr(260);
-        float n2 = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (tok_ok) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             const uint4 raw = *reinterpret_cast<const uint4*>(Kr + tid * 128 + ((ch ^ (tid & 7)) << 4));
             const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
-            n2 = fmaf(a.x, a.x, n2); n2 = fmaf(a.y, a.y, n2); n2 = fmaf(b2.x, b2.x, n2); n2 = fmaf(b2.y, b2.y, n2);
-            n2 = fmaf(c2.x, c2.x, n2); n2 = fmaf(c2.y, c2.y, n2); n2 = fmaf(d2.x, d2.x, n2); n2 = fmaf(d2.y, d2.y, n2);
+            a0 = fmaf(a.x, a.x, a0); a1 = fmaf(a.y, a.y, a1); a2 = fmaf(b2.x, b2.x, a2); a3 = fmaf(b2.y, b2.y, a3);
+            a0 = fmaf(c2.x, c2.x, a0); a1 = fmaf(c2.y, c2.y, a1); a2 = fmaf(d2.x, d2.x, a2); a3 = fmaf(d2.y, d2.y, a3);
           }
         }
-        ptx::mbar_arrive(bar(kNormDone0 + (r & 1)));
-        if (r == 3) tr(261);
-        ptx::mbar_wait(bar(kD2Full0 + (r & 1)), (par_d2 >> (r & 1)) & 1);
-        par_d2 ^= 1u << (r & 1);
-        if (r == 3) tr(262);
-        ptx::tc_fence_after();
-        float dd[8];
-        ptx::tmem_ld8(trow + C::cD2 + 16 * (r & 1), reinterpret_cast<uint32_t*>(dd));
-        ptx::tmem_ld_wait();
-        float dsel = dd[0];
+        n2[r] = (a0 + a1) + (a2 + a3);
+        ptx::mbar_arrive(bar(kNormDone0 + r));
+      }
+      tr(10);
+      // ---- all phi-logits are in TMEM: one exchange, one batch of 16-token softmaxes, NR P2 tiles -------
+      ptx::mbar_wait(bar(kD2Full), ni & 1);
+      ptx::tc_fence_after();
+      tr(11);
+      {
+        const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
+        float lg[NR];
+        {
+          uint32_t dd[NR][8];
 #pragma unroll
-        for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? dd[c] : dsel;
-        const float lg = tok_ok ? scale_log2 * (dsel - 0.5f * n2) : kNegInf;   // log2 units
-        float* lb_ = lbuf + (r & 1) * 128;
-        lb_[tid] = lg;
-        if (r == 3) tr(263);
+          for (int r = 0; r < NR; ++r) ptx::tmem_ld8(trow + C::cD2 + 16 * r, dd[r]);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            float dsel = __uint_as_float(dd[r][0]);
+#pragma unroll
+            for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? __uint_as_float(dd[r][c]) : dsel;
+            lg[r] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * n2[r]) : kNegInf;   // log2 units
+            lbuf[r * 128 + tid] = lg[r];
+          }
+        }
+        // the q_bar tile is dead (every phi-logit MMA has completed): clear the P2 tiles that overlay it
+        for (int z = tid; z < C::kP2Bytes / 16; z += kComputeThreads) reinterpret_cast<uint4*>(P2t)[z] = make_uint4(0, 0, 0, 0);
+        tr(12);
         ptx::named_bar_sync(1, kComputeThreads);
-        if (r == 3) tr(264);
-        float lv[CH * CH];
+        tr(13);
         const int t0 = tok_ok ? tcx * CH : 0;
 #pragma unroll
-        for (int yy = 0; yy < CH; ++yy) {
-          if constexpr (CH == 4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(lb_ + yy * GW + t0);
-            lv[4 * yy] = v4.x; lv[4 * yy + 1] = v4.y; lv[4 * yy + 2] = v4.z; lv[4 * yy + 3] = v4.w;
-          } else if constexpr (CH == 2) {
-            const float2 v2 = *reinterpret_cast<const float2*>(lb_ + yy * GW + t0);
-            lv[2 * yy] = v2.x; lv[2 * yy + 1] = v2.y;
-          } else {
+        for (int r = 0; r < NR; ++r) {
+          const float* lb_ = lbuf + r * 128;
+          float lv[CH * CH];
 #pragma unroll
-            for (int xx = 0; xx < CH; ++xx) lv[CH * yy + xx] = lb_[yy * GW + t0 + xx];
+          for (int yy = 0; yy < CH; ++yy) {
+            if constexpr (CH == 4) {
+              const float4 v4 = *reinterpret_cast<const float4*>(lb_ + yy * GW + t0);
+              lv[4 * yy] = v4.x; lv[4 * yy + 1] = v4.y; lv[4 * yy + 2] = v4.z; lv[4 * yy + 3] = v4.w;
+            } else if constexpr (CH == 2) {
+              const float2 v2 = *reinterpret_cast<const float2*>(lb_ + yy * GW + t0);
+              lv[2 * yy] = v2.x; lv[2 * yy + 1] = v2.y;
+            } else {
+#pragma unroll
+              for (int xx = 0; xx < CH; ++xx) lv[CH * yy + xx] = lb_[yy * GW + t0 + xx];
+            }
           }
+          float mx = kNegInf;
+#pragma unroll
+          for (int j = 0; j < CH * CH; ++j) mx = fmaxf(mx, lv[j]);
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < CH * CH; j += 2) { sum0 += ex2(lv[j] - mx); sum1 += ex2(lv[j + 1] - mx); }
+          const float pt = __fdividef(ex2(lg[r] - mx), sum0 + sum1);
+          if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + r * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
         }
-        float mx = kNegInf;
-#pragma unroll
-        for (int j = 0; j < CH * CH; ++j) mx = fmaxf(mx, lv[j]);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < CH * CH; ++j) sum += ex2(lv[j] - mx);
-        const float pt = ex2(lg - mx) / sum;
-        if (r == 3) tr(265);
-        ptx::mbar_wait(bar(kP2Free0 + (r & 1)), (par_p2f >> (r & 1)) & 1);
-        par_p2f ^= 1u << (r & 1);
-        if (r == 3) tr(266);
-        if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + (r & 1) * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
-        ptx::fence_proxy_async_smem();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(bar(kP2Full0 + (r & 1)));
-        tr(10 + r);
       }
-      // ---- beta^T (TMEM) -> beta tile [chunk][feat] -------------------------------------------------
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kP2Full));
+      tr(14);
+      // ---- beta^T (TMEM) -> beta tile [c'][feat] -------------------------------------------------------
       ptx::mbar_wait(bar(kBetaFull), ni & 1);
       ptx::tc_fence_after();
       tr(20);
@@ -640,7 +664,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           for (int r = 0; r < NR; ++r)
 #pragma unroll
             for (int cx = 0; cx < NCX; ++cx)
-              *reinterpret_cast<uint16_t*>(BTt + tile_off(r * NCX + cx, feat)) = IoFmt<T>::one(bt[8 * r + cx]);
+              *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * r + cx, feat)) = IoFmt<T>::one(bt[8 * r + cx]);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -655,9 +679,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::mbar_wait(bar(kSFull), np_s & 1);
         ptx::tc_fence_after();
         tr(30 + 4 * pr);
-        float sl[L], sr[CN];
+        float sl[L], sr[CNP];    // chunk logits by c' = 8 r + cx; every 8th column is padding (statically skipped)
         tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
-        tmem_ld_cols<CN>(trow + C::cX0 + 64 * (np_s & 1), reinterpret_cast<uint32_t*>(sr));
+        tmem_ld_cols<CNP>(trow + C::cX0 + 64 * (np_s & 1), reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
         if (pr == 1) tr(250);
         // Shift by M = scale*max_j(raw) + max_j(bias) >= true row max (softmax is shift invariant; M only has to
@@ -671,7 +695,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         }
         float r0 = kNegInf, r1 = kNegInf, r2 = kNegInf, r3 = kNegInf;
 #pragma unroll
-        for (int c = 0; c < CN; ++c) {
+        for (int c = 0; c < CNP; ++c) {
+          if (!C::chunk_ok(c)) continue;
           if ((c & 3) == 0) r0 = fmaxf(r0, sr[c]); else if ((c & 3) == 1) r1 = fmaxf(r1, sr[c]);
           else if ((c & 3) == 2) r2 = fmaxf(r2, sr[c]); else r3 = fmaxf(r3, sr[c]);
         }
@@ -693,8 +718,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         const float nmx = -mx;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float a = (2 * j < CN) ? ex2(fmaf(sr[(2 * j < CN) ? 2 * j : 0], scale_log2, nmx)) : 0.f;
-          const float c2 = (2 * j + 1 < CN) ? ex2(fmaf(sr[(2 * j + 1 < CN) ? 2 * j + 1 : 0], scale_log2, nmx)) : 0.f;
+          const float a = C::chunk_ok(2 * j) ? ex2(fmaf(sr[C::chunk_ok(2 * j) ? 2 * j : 0], scale_log2, nmx)) : 0.f;
+          const float c2 = C::chunk_ok(2 * j + 1) ? ex2(fmaf(sr[C::chunk_ok(2 * j + 1) ? 2 * j + 1 : 0], scale_log2, nmx)) : 0.f;
           if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
           prf[j] = IoFmt<T>::pack2(a, c2);
         }
@@ -888,7 +913,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.b_q = ada.b_q; p.g_q = ada.ln_gain_q; p.beta_q = ada.ln_bias_q;
   p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
   p.has_q = ada.w_q != nullptr;
-  p.mu_coeff = ada.mu_coeff; p.ln_eps = ada.ln_eps;
+  p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out;
   p.trace = trace_enabled();
   p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", NR);
@@ -896,7 +921,8 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   auto kern = eva_fused_kernel<T, W, GW, CH, NR>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
-  const int grid = p.items < 2 * sm_count() ? p.items : 2 * sm_count();
+  const int max_ctas = env_int("EVA_SM100_CTAS_PER_SM", 2) * sm_count();   // tuning knob; 2 = as many as fit
+  const int grid = p.items < max_ctas ? p.items : max_ctas;
   kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, to, p);
   *msg = "kernel launch";
   return cudaGetLastError();
@@ -943,7 +969,7 @@ size_t fused_workspace_bytes(const Geo& g) {
 
 // diagnostic (not part of the public ABI): copy the phase trace of CTA 0 to the host
 extern "C" int eva_debug_read_trace(unsigned long long* dst, int which, int n) {
-  if (which < 0 || which > 1 || n > fused::kTraceLen) return -22;
+  if (which < 0 || which > 2 || n > fused::kTraceLen) return -22;
   return cudaMemcpyFromSymbol(dst, fused::g_trace, (size_t)n * 8, (size_t)which * fused::kTraceLen * 8) == cudaSuccess ? 0 : -5;
 }
 

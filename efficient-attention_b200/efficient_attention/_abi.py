@@ -11,6 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libeva_sm100.so')
+# development only: A/B a second build of the same ABI (tools/core_bench.py); never a different code path
+LIB_PATH = os.environ.get('EVA_SM100_LIB', LIB_PATH)
 
 EVA_F32, EVA_F16, EVA_BF16 = 0, 1, 2
 _DTYPES = {torch.float32: EVA_F32, torch.float16: EVA_F16, torch.bfloat16: EVA_BF16}

@@ -28,12 +28,10 @@ assert path == 1
 lib = _abi.load()
 names = {1: 'item start', 2: 'pool ready', 3: 'means written', 4: 'linear ready', 5: 'omega/kbar written', 20: 'beta ready',
          21: 'beta tile written', 101: 'mma item start', 102: 'pool issued', 103: 'linear issued', 104: 'omega waited', 120: 'stats waited'}
-names.update({260: 'r3: K landed', 261: 'r3: norm done', 262: 'r3: logits ready', 263: 'r3: logit written', 264: 'r3: exchange barrier', 265: 'r3: p computed', 266: 'r3: P tile free'})
+names.update({10: 'pass2: |k|^2 of all rows done', 11: 'pass2: phi-logits ready', 12: 'pass2: logits written, P2 cleared',
+              13: 'pass2: exchange barrier', 14: 'pass2: P2 tiles written', 110: 'phi-logit MMAs issued', 111: 'beta MMAs issued'})
 names.update({270: 'e1: prev store drained', 271: 'e1: barrier 1', 272: 'e1: rows staged', 273: 'e1: barrier 2'})
 names.update({240: 'LN: tmem loaded', 241: 'LN: math done', 242: 'LN: k side written', 243: 'LN: barrier passed', 250: 'p1: S loaded', 251: 'p1: max done', 252: 'p1: exp/pack done', 253: 'p1: O loaded'})
-for r in range(7):
-    names[10 + r] = f'pass2 row {r} P written'
-    names[110 + r] = f'beta mma {r} issued'
 for pr in range(8):
     names[30 + 4 * pr] = f'pair {pr} S ready'
     names[31 + 4 * pr] = f'pair {pr} P written'
@@ -70,7 +68,34 @@ for which, label in ((0, 'compute thread 0'), (1, 'MMA thread')):
         order = [(a[0], b[0]) for a, b in zip(it[:-1], it[1:])]
     for key in order:
         d = dur[key]
-        print(f'   {names.get(key[0], key[0]):>24s} -> {names.get(key[1], key[1]):<24s} {sum(d) / len(d):9.0f} cyc  (n={len(d)})')
+        print(f'   {str(names.get(key[0], key[0])):>24s} -> {str(names.get(key[1], key[1])):<24s} {sum(d) / len(d):9.0f} cyc  (n={len(d)})')
     if len(items) > 2:
         gaps = [b[0][1] - a[-1][1] for a, b in zip(items[1:-1], items[2:])]
         print(f'   gap last event -> next item start: mean {sum(gaps) / len(gaps):.0f} cyc')
+
+# ---- load latency per ring position: TMA issue (slot acquired) -> MMA thread saw the tile --------------------
+def read(which):
+    buf = (ctypes.c_ulonglong * 8192)()
+    lib.eva_debug_read_trace(buf, which, 8192)
+    n = int(buf[8191])
+    return [(int(buf[i]), int(buf[i + 1])) for i in range(0, n, 2)]
+tma, mma = read(2), read(1)
+def per_item(ev, base, first):
+    items, cur = [], {}
+    for e, t in ev:
+        if e == base + first and cur:
+            items.append(cur)
+            cur = {}
+        if base <= e < base + 1000:
+            cur[e - base] = t
+    items.append(cur)
+    return items
+ti, mi = per_item(tma, 1000, 0), per_item(mma, 2000, 0)
+print(f'== loads: {len(ti)} items (TMA), {len(mi)} items (MMA); per ring position: issue time relative to the item\'s first issue, issue -> seen by MMA thread')
+k = min(len(ti), len(mi)) - 1
+for pos in sorted(ti[1].keys()) if k > 1 else []:
+    d_issue = [ti[j][pos] - ti[j][0] for j in range(1, k) if pos in ti[j]]
+    d_lat = [mi[j][pos] - ti[j][pos] for j in range(1, k) if pos in ti[j] and pos in mi[j]]
+    if d_issue:
+        lat = f'{sum(d_lat) / len(d_lat):8.0f}' if d_lat else '       -'
+        print(f'   pos {pos:3d}: issued at +{sum(d_issue) / len(d_issue):8.0f}   issue->seen {lat}')
