@@ -72,6 +72,9 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int KS = (TOK + 15) / 16;    // k-steps over the tokens of a chunk-row
   static constexpr int KBLK = (TOK + 63) / 64;  // 64-token K blocks of the Pool / P2 tiles
   static constexpr int JC = CH * CH;
+  static constexpr int kQOff = 64 - L, kKOff = LP8 - L;   // tile row of window a's first token in the q slot / the k, v slots
+  static constexpr int kPairBytes = 2 * L * 128;
+  static_assert(kQOff >= 0 && kQOff + 2 * L <= 128 && kKOff + 2 * L <= 2 * LP8, "stacked pair layout");
   static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOK <= 128 && L <= 64 && CNP <= 64, "geometry");
   __host__ __device__ static constexpr bool chunk_ok(int c) { return c < CNP && (c & 7) < NCX; }
   // shared memory map (bytes from the 1024-aligned base)
@@ -172,15 +175,20 @@ __device__ __forceinline__ uint32_t par_of(uint32_t n) { return (n >> 2) & 1u; }
 // optional phase trace of CTA 0 (EVA_SM100_TRACE=1): [0] compute thread 0, [1] MMA thread; pairs (event, clock64)
 constexpr int kTraceLen = 8192;
 __device__ unsigned long long g_trace[3][kTraceLen];   // [2] = TMA thread: (1000 + ring position in item, clock) at issue
-struct Tracer {
+template <bool kOn> struct Tracer {       // kOn = false (production instantiation): no code at all -- the kernel is instruction-cache bound
   unsigned long long* buf;
   int n;
   __device__ __forceinline__ void operator()(int ev) {
-    if (buf && n + 2 <= kTraceLen) { buf[n] = (unsigned long long)ev; buf[n + 1] = (unsigned long long)clock64(); n += 2; }
+    if constexpr (kOn) {
+      if (buf && n + 2 <= kTraceLen) { buf[n] = (unsigned long long)ev; buf[n + 1] = (unsigned long long)clock64(); n += 2; }
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if constexpr (kOn) { if (buf) buf[kTraceLen - 1] = n; }
   }
 };
 
-template <typename T, int W, int GW, int CH, int NR>
+template <typename T, int W, int GW, int CH, int NR, bool TR>
 __global__ void __launch_bounds__(kThreads, 2)
 eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant__ CUtensorMap tw_k,
                  const __grid_constant__ CUtensorMap tw_v, const __grid_constant__ CUtensorMap tr_q,
@@ -252,26 +260,29 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   if (warp == 4) {
     // =================================== TMA producer ==========================================
     {
-      uint32_t n = 0, ni = 0, n_item0 = 0;
+      // A warp gets one TMA box through the engine every ~0.55 us however deep its ring is (tools/tma_stream.cu), so the
+      // loads of an item are split between this warp (q rows, W, bias, K rows, Q/K windows) and the MMA warp
+      // (k rows, V rows, V windows).  Ring positions stay globally ordered; each issuer acquires its own positions.
+      uint32_t nb = 0, ni = 0;
       const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
-      Tracer tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[2] : nullptr, 0};
-      auto acquire = [&](uint32_t bytes) -> uint32_t {   // returns the slot; arms its full barrier
+      Tracer<TR> tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[2] : nullptr, 0};
+      // With two issuers the previous use of a slot may belong to the other warp.  A parity wait can only tell the last two
+      // phases apart, so at every acquire the use BEFORE the previous one must already be known to be consumed.  That holds
+      // by causality everywhere (commits complete in order, and each warp's own earlier acquires imply it) except for the
+      // first q window of phase B, which therefore waits for the phi-logit MMAs first (see below).
+      auto acquire = [&](uint32_t n, uint32_t bytes) -> uint32_t {   // returns the slot of ring position n; arms its full barrier
         const uint32_t s = slot_of(n);
         ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
-        tr(1000 + (int)(n - n_item0));
+        tr(1000 + (int)(n - nb));
         if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
-        ++n;
         return s;
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni) {
-        n_item0 = n;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         const int b = item / p.H, h = item % p.H;
-        for (int r = 0; r < NR; ++r) {                   // pass 1: q, k chunk-rows (first touch: HBM)
-          uint32_t s = acquire(TOK * 128);
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM)
+          const uint32_t s = acquire(nb + 2 * r, TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          s = acquire(TOK * 128);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          if (p.prefetch_v && ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_v, 0, h, 0, r * CH, b, keep);   // v is first needed in pass 2: warm L2 now
         }
         if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
           ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
@@ -279,21 +290,21 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if (ptx::elect_one()) ptx::bulk_load(ptx::smem_u32(sm + C::kBias), reinterpret_cast<const uint8_t*>(p.bias2) + (size_t)h * C::kBiasSlab,
                          C::kBiasSlab, bar(kBiasFull));
         }
-        ++n;                                             // slot borrowed by the compute warps for the means tile
         {
-          const uint32_t s = acquire(128 * 128);
+          const uint32_t s = acquire(nb + C::nW, 128 * 128);
           if (ptx::elect_one()) ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
         }
-        for (int r = 0; r < NR; ++r) {                   // pass 2: all k rows (L2 hits) ...
-          const uint32_t s = acquire(TOK * 128);
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {                   // pass 2: all k rows (L2 hits)
+          const uint32_t s = acquire(nb + C::nPass2 + r, TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
         }
-        for (int r = 0; r < NR; ++r) {                   // ... then all v rows (first touch); the first ones land under the softmax
-          const uint32_t s = acquire(TOK * 128);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_v, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-        }
+        // Q(0) takes over the slot of V_{NR-4} (MMA warp), whose previous tile K_{NR-1} is this warp's own: make sure that one
+        // has been consumed before the parity wait inside acquire (every K-row hand-back precedes this commit)
+        ptx::mbar_wait(bar(kD2Full), ni & 1);
         const int item_next = item + gridDim.x;
-        for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: window pairs (L2)
+#pragma unroll 1
+        for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: q and k of the window pairs (L2)
           if (item_next < p.items) {                     // warm L2 with the next item's q/k chunk-rows, a few per pair
             const int bn = item_next / p.H, hn = item_next % p.H;
             for (int r = pr * p.prefetch_rows / p.n_pairs; r < (pr + 1) * p.prefetch_rows / p.n_pairs; ++r) {
@@ -301,23 +312,19 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
               if (ptx::elect_one()) ptx::tma_prefetch_5d_hint(&tr_k, 0, hn, 0, r * CH, bn, keep);
             }
           }
-          const int w0 = 2 * pr, w1 = w0 + 1;
-          const bool two = w1 < p.n_windows;
-          const int x0 = (w0 % p.nwx) * W, y0 = (w0 / p.nwx) * W;
-          const int x1 = (w1 % p.nwx) * W, y1 = (w1 / p.nwx) * W;
-          const uint32_t bytes = (two ? 2u : 1u) * L * 128u;
-          uint32_t s = acquire(bytes);                   // last use of these lines: let L2 drop them first
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_q, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + 64 * 128), &tw_q, bar(kFull0 + s), 0, h, x1, y1, b, stream);
-          s = acquire(bytes);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_k, bar(kFull0 + s), 0, h, x1, y1, b, stream);
-          s = acquire(bytes);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tw_v, bar(kFull0 + s), 0, h, x0, y0, b, stream);
-          if (two && ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s) + LP8 * 128), &tw_v, bar(kFull0 + s), 0, h, x1, y1, b, stream);
+          // pair pr = windows (wx, 2 wyp) and (wx, 2 wyp + 1), stacked vertically: ONE box of 7 x 14 tokens per operand
+          // (the TMA engine charges ~300 cycles per box).  The q box lands 15 rows into its slot so that window a sits in
+          // tile rows 15-63 and window b in rows 64-112 (TMEM lane = tile row: b starts on a warp boundary); the k and v
+          // boxes land 7 rows in (a: rows 7-55, b: rows 56-104 of the 112 key columns).  128-byte swizzling is a function
+          // of the shared-memory address, so an offset destination stays consistent with descriptors based at the slot.
+          const int x0 = (pr % p.nwx) * W, y0 = (pr / p.nwx) * 2 * W;
+          uint32_t s = acquire(nb + C::nPairs + 3 * pr, C::kPairBytes);      // last use of these lines: let L2 drop them first
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)) + C::kQOff * 128, &tw_q, bar(kFull0 + s), 0, h, x0, y0, b, stream);
+          s = acquire(nb + C::nPairs + 3 * pr + 1, C::kPairBytes);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)) + C::kKOff * 128, &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
         }
       }
-      if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
+      tr.finish();
     }
   } else if (warp == 5) {
     // =================================== MMA issuer ============================================
@@ -337,29 +344,53 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
       auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
       uint32_t nb = 0, ni = 0, np = 0;
-      Tracer tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[1] : nullptr, 0};
-      auto mma_ss = [](uint32_t d, uint64_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ss(d, a, b_, idesc, acc); };
-      auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b_, uint32_t idesc, uint32_t acc) { if (ptx::elect_one()) ptx::umma_ts(d, a, b_, idesc, acc); };
+      Tracer<TR> tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[1] : nullptr, 0};
       auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); tr(2000 + (int)(n - nb)); };
-      auto free_slot = [&](uint32_t n) { if (ptx::elect_one()) ptx::umma_commit(bar(kFree0 + slot_of(n))); };
+      // one elected region per group of MMAs and their commits: every separate elect costs ~10 instructions of code
+      auto free_raw = [&](uint32_t n) { ptx::umma_commit(bar(kFree0 + slot_of(n))); };
+      // this warp's share of the loads (see the TMA warp): always issued after the MMAs that read the slot's previous tile
+      const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
+      auto acquire = [&](uint32_t n, uint32_t bytes) -> uint32_t {      // see the TMA warp
+        const uint32_t s = slot_of(n);
+        ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
+        tr(1000 + (int)(n - nb));
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
+        return s;
+      };
+      static_assert(NR >= 4, "V rows of pass 2 reuse the slots of the last four K rows");
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
+        const int b = item / p.H, h = item % p.H;
+        auto load_row = [&](uint32_t n, const CUtensorMap* tm, int r) {
+          const uint32_t s = acquire(n, TOK * 128);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), tm, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+        };
+        auto load_v_pair = [&](int pr) {
+          const uint32_t s = acquire(nb + C::nPairs + 3 * pr + 2, C::kPairBytes);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)) + C::kKOff * 128, &tw_v, bar(kFull0 + s), 0, h, (pr % p.nwx) * W, (pr / p.nwx) * 2 * W, b, stream);
+        };
         // ---- pass 1: chunk means ------------------------------------------------------------
         tr(101);
+        load_row(nb + 1, &tr_k, 0);
+        load_row(nb + 3, &tr_k, 1);
+#pragma unroll 1
         for (int r = 0; r < NR; ++r) {
           const uint32_t nq = nb + 2 * r, nk = nq + 1;
           wait_full(nq);
           wait_full(nk);
           ptx::tc_fence_after();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-            mma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+            for (int ks = 0; ks < KS; ++ks)
+              ptx::umma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-            mma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
-          free_slot(nq);
-          free_slot(nk);
+            for (int ks = 0; ks < KS; ++ks)
+              ptx::umma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+            free_raw(nq);
+            free_raw(nk);
+            if (r == NR - 1) ptx::umma_commit(bar(kPoolFull));
+          }
+          if (r + 2 < NR) load_row(nk + 4, &tr_k, r + 2);      // same slot as k_r: waits for the MMAs just issued
         }
-        if (ptx::elect_one()) ptx::umma_commit(bar(kPoolFull));
         tr(102);
         // ---- adaptive Linear: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used) ----------
         ptx::mbar_wait(bar(kAFull), ni & 1);
@@ -368,56 +399,70 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (ptx::elect_one()) ptx::mbar_arrive(bar(kFull0 + slot_of(nb + C::nAt)));
         wait_full(nb + C::nW);
         ptx::tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          mma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
-        if (ptx::elect_one()) ptx::umma_commit(bar(kLinFull));
-        tr(103);
-        // both tiles are dead once the Linear MMA has completed: hand the slots back now so that the first k rows of
+        // both tiles are dead once the Linear MMA has completed: hand the slots back right away so that the first k rows of
         // pass 2 are requested while the compute warps are still in the LayerNorm
-        free_slot(nb + C::nW);
-        free_slot(nb + C::nAt);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_ss(tmem + C::cLin, dSlot(slot_of(nb + C::nAt)) + 2 * ks, dSlot(slot_of(nb + C::nW)) + 2 * ks, id_lin, ks > 0);
+          ptx::umma_commit(bar(kLinFull));
+          free_raw(nb + C::nW);
+          free_raw(nb + C::nAt);
+        }
+        tr(103);
         ptx::mbar_wait(bar(kOmFull), ni & 1);
         tr(104);      // q_bar / k_bar tiles written
         ptx::tc_fence_after();
         // ---- pass 2: phi-logits of every chunk-row, D2_r = K_r (Qbar_r + Kbar_r)^T ------------------------
+#pragma unroll 1
         for (int r = 0; r < NR; ++r) {
           const uint32_t nk = nb + C::nPass2 + r;
           wait_full(nk);
           ptx::tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
-          if (p.has_q) {
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              mma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dKB + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, 1);
+              ptx::umma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
+            if (p.has_q) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                ptx::umma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dKB + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, 1);
+            }
           }
           // the compute warps take |k|^2 from the same tile: hand it back when both are done
           ptx::mbar_wait(bar(kNormDone0 + r), ni & 1);
-          free_slot(nk);
+          if (ptx::elect_one()) {
+            free_raw(nk);
+            if (r == NR - 1) ptx::umma_commit(bar(kD2Full));
+          }
+          if (r >= NR - 4) load_row(nk + 4, &tr_v, r - (NR - 4));   // V_j takes over the slot of K_{NR-4+j}
         }
-        if (ptx::elect_one()) ptx::umma_commit(bar(kD2Full));
         tr(110);
         // ---- beta^T += V_r^T P_r^T once the softmax batch is in shared memory ----------------------------
         ptx::mbar_wait(bar(kP2Full), ni & 1);
         ptx::tc_fence_after();
+#pragma unroll 1
         for (int r = 0; r < NR; ++r) {
           const uint32_t nv = nb + C::nPass2 + NR + r;
           wait_full(nv);
           ptx::tc_fence_after();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-            mma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
-                         dP2 + (uint64_t)(r * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
-          free_slot(nv);
+            for (int ks = 0; ks < KS; ++ks)
+              ptx::umma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
+                           dP2 + (uint64_t)(r * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
+            free_raw(nv);
+            if (r == NR - 1) ptx::umma_commit(bar(kBetaFull));
+          }
+          if (r + 4 < NR) load_row(nv + 4, &tr_v, r + 4);
         }
-        if (ptx::elect_one()) ptx::umma_commit(bar(kBetaFull));
+        load_v_pair(0);                                      // slot of V_{NR-2}
         tr(111);
         ptx::mbar_wait(bar(kStatsFull), ni & 1);
         tr(120);
         ptx::tc_fence_after();
         // ---- phase B --------------------------------------------------------------------------------
+#pragma unroll 1
         for (int pr = 0; pr < p.n_pairs; ++pr, ++np) {
           const uint32_t nq = nb + C::nPairs + 3 * pr, nk = nq + 1, nv = nq + 2;
           wait_full(nq);
@@ -425,39 +470,47 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const uint32_t cX = C::cX0 + 64 * (np & 1);
           ptx::tc_fence_after();
           const uint64_t dQ = dSlot(slot_of(nq)), dK = dSlot(slot_of(nk)), dV = dSlot(slot_of(nv));
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_ss(tmem + C::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + C::cSloc, dQ + 2 * ks, dK + 2 * ks, id_sl, ks > 0);
+          }
           // X[np&1] last held O of pair np-2: its epilogue must have read it (per-buffer barrier: no lapping).
           // Only the chunk logits live there, so the local logits above are already in flight.
           if (np >= 2) ptx::mbar_wait(bar(kOFree0 + (np & 1)), ((np >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) mma_ss(tmem + cX, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
-          if (ptx::elect_one()) ptx::umma_commit(bar(kSFull));
-          free_slot(nq);
-          free_slot(nk);
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cX, dQ + 2 * ks, dKB + 2 * ks, id_sr, ks > 0);
+            ptx::umma_commit(bar(kSFull));
+            free_raw(nq);
+            free_raw(nk);
+          }
+          if (pr + 1 < p.n_pairs) load_v_pair(pr + 1);     // slot of K(pr): waits for the S MMAs just issued, under the softmax
           tr(130 + 2 * pr);
           ptx::mbar_wait(bar(kPFull), np & 1);
           wait_full(nv);
           ptx::tc_fence_after();
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2 * LP8 / 16; ++ks)
-            mma_ts(tmem + cX, tmem + C::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+            for (int ks = 0; ks < 2 * LP8 / 16; ++ks)
+              ptx::umma_ts(tmem + cX, tmem + C::cPloc + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_ts(tmem + cX, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
-          if (ptx::elect_one()) ptx::umma_commit(bar(kOFull0 + (np & 1)));   // per-buffer barrier: the MMA warp may run two pairs ahead of the epilogue
-          free_slot(nv);
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::umma_ts(tmem + cX, tmem + C::cPrfa + 8 * ks, dBT + 128 * ks, id_pv, 1);
+            ptx::umma_commit(bar(kOFull0 + (np & 1)));   // per-buffer barrier: the MMA warp may run two pairs ahead of the epilogue
+            free_raw(nv);
+          }
           tr(131 + 2 * pr);
         }
       }
-      if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
+      tr.finish();
     }
   } else {
     // =================================== compute warps ==========================================
     const int ws = tid >> 6;           // phase B: which window of the pair this row belongs to (warp-uniform)
     const int i = tid & 63;            // phase B: query slot inside the window (valid if < L)
-    const int ic = i < L ? i : L - 1;
+    const int iq = ws ? (tid - 64) : (tid - C::kQOff);   // phase B: query slot inside my window (valid if 0 <= iq < L)
+    const int ic = iq < 0 ? 0 : (iq < L ? iq : L - 1);
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
     const float scale = 0.125f;        // head_dim 64
     const float scale_log2 = scale * kLog2e;
@@ -470,7 +523,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0;
     uint8_t* const ostage = sm + C::kOStage;
     const uint64_t out_policy = ptx::policy_evict_first();
-    Tracer tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
+    Tracer<TR> tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
       const int b = item / p.H, h = item % p.H;
       tr(1);
@@ -680,7 +733,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::tc_fence_after();
         tr(30 + 4 * pr);
         float sl[L], sr[CNP];    // chunk logits by c' = 8 r + cx; every 8th column is padding (statically skipped)
-        tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws * LP8), reinterpret_cast<uint32_t*>(sl));
+        tmem_ld_cols<L>(trow + C::cSloc + (uint32_t)(ws ? LP8 : C::kKOff), reinterpret_cast<uint32_t*>(sl));   // my window's key columns
         tmem_ld_cols<CNP>(trow + C::cX0 + 64 * (np_s & 1), reinterpret_cast<uint32_t*>(sr));
         ptx::tmem_ld_wait();
         if (pr == 1) tr(250);
@@ -707,13 +760,17 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (pr == 1) tr(251);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         uint32_t pl[LP8 / 2], prf[32], zeros[LP8 / 2];
+        // 16-bit P, two keys per TMEM column: word m = (e[2m], e[2m+1]).  Window b's keys start at the even position LP8
+        // (words go left-aligned into the second LP8/2 columns as they are); window a's start at the odd position
+        // LP8 - L, so its words are funnel-shifted by 16 bits and right-aligned in the first LP8/2 columns (below).
+        static_assert((L & 1) == 1 && LP8 - L == 7, "P packing assumes window 7");
 #pragma unroll
-        for (int j = 0; j < LP8 / 2; ++j) {
-          const float a = (2 * j < L) ? ex2(fmaf(sl[(2 * j < L) ? 2 * j : 0], scale_log2, brow[(2 * j < L) ? 2 * j : 0] - mx)) : 0.f;
-          const float c2 = (2 * j + 1 < L) ? ex2(fmaf(sl[(2 * j + 1 < L) ? 2 * j + 1 : 0], scale_log2, brow[(2 * j + 1 < L) ? 2 * j + 1 : 0] - mx)) : 0.f;
-          if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
-          pl[j] = IoFmt<T>::pack2(a, c2);
-          zeros[j] = 0u;
+        for (int m = 0; m < LP8 / 2; ++m) {
+          const float a = (2 * m < L) ? ex2(fmaf(sl[(2 * m < L) ? 2 * m : 0], scale_log2, brow[(2 * m < L) ? 2 * m : 0] - mx)) : 0.f;
+          const float c2 = (2 * m + 1 < L) ? ex2(fmaf(sl[(2 * m + 1 < L) ? 2 * m + 1 : 0], scale_log2, brow[(2 * m + 1 < L) ? 2 * m + 1 : 0] - mx)) : 0.f;
+          if (m & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
+          pl[m] = IoFmt<T>::pack2(a, c2);
+          zeros[m] = 0u;
         }
         const float nmx = -mx;
 #pragma unroll
@@ -725,8 +782,17 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         }
         if (pr == 1) tr(252);
         // P (16-bit, two per column) overwrites the S columns this thread has finished reading
-        tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)(ws * (LP8 / 2)), pl);
-        tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)((1 - ws) * (LP8 / 2)), zeros);
+        if (ws) {
+          tmem_st_cols<LP8 / 2>(trow + C::cPloc + LP8 / 2, pl);
+        } else {
+          constexpr int kLead = LP8 / 2 - (L + 1) / 2;      // 3 leading zero words, then (e[2m-1], e[2m]) for m = 0 .. (L-1)/2
+          uint32_t ps[LP8 / 2];
+#pragma unroll
+          for (int m = 0; m < LP8 / 2; ++m)
+            ps[m] = m < kLead ? 0u : __funnelshift_l(m - kLead > 0 ? pl[m - kLead - 1] : 0u, pl[m - kLead], 16);
+          tmem_st_cols<LP8 / 2>(trow + C::cPloc, ps);
+        }
+        tmem_st_cols<LP8 / 2>(trow + C::cPloc + (uint32_t)(ws ? 0 : LP8 / 2), zeros);
         tmem_st_cols<32>(trow + C::cPrfa, prf);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -736,10 +802,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ++np_s;
         return (s0 + s1) + (s2 + s3);
       };
-      // epilogue: O / rowsum -> swizzled staging rows -> one TMA store per window
+      // epilogue: O / rowsum -> swizzled staging rows (window a: rows 0..L-1, window b: rows L..2L-1) -> one TMA store per pair
       auto epilogue_pair = [&](int pr, float sum) {
-        const int wi = 2 * pr + ws;
-        const bool win_ok = wi < p.n_windows;
         ptx::mbar_wait(bar(kOFull0 + (np_e & 1)), (np_e >> 1) & 1);
         ptx::tc_fence_after();
         tr(32 + 4 * pr);
@@ -749,43 +813,45 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::tc_fence_before();
         ptx::mbar_arrive(bar(kOFree0 + (np_e & 1)));
         if (pr == 1) tr(253);
-        const bool store_warp = (warp & 1) == 0;       // warps 0 and 2: one per window half
-        if (store_warp && ptx::elect_one()) ptx::bulk_wait_read0();   // the previous store of this half has drained the staging rows
+        if (warp == 0 && ptx::elect_one()) ptx::bulk_wait_read0();   // the previous store has drained the staging rows
         if (pr == 1) tr(270);
-        ptx::named_bar_sync(2 + ws, 64);
+        ptx::named_bar_sync(2, kComputeThreads);
         if (pr == 1) tr(271);
-        if (i < L && win_ok) {
+        if (iq >= 0 && iq < L) {
           const float inv = 1.0f / sum;
-          uint8_t* row = ostage + ws * (LP8 * 128) + i * 128;
+          const int orow = ws * L + iq;
+          uint8_t* row = ostage + orow * 128;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
-            *reinterpret_cast<uint4*>(row + ((ch ^ (i & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(row + ((ch ^ (orow & 7)) << 4)) =
                 make_uint4(IoFmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), IoFmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
                            IoFmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), IoFmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
         if (pr == 1) tr(272);
         ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(2 + ws, 64);
+        ptx::named_bar_sync(2, kComputeThreads);
         if (pr == 1) tr(273);
-        if (store_warp && win_ok && ptx::elect_one()) {
+        if (warp == 0 && ptx::elect_one()) {
           // the output is never re-read here: evict-first keeps L2 for the q/k/v lines that are
-          ptx::tma_store_5d_hint(&t_o, ptx::smem_u32(ostage + ws * (LP8 * 128)), 0, h, (wi % p.nwx) * W, (wi / p.nwx) * W, b, out_policy);
+          // (a direct st.global of each thread's 128-byte row was measured 14 % slower: 16-byte pieces of 32 different lines per instruction)
+          ptx::tma_store_5d_hint(&t_o, ptx::smem_u32(ostage), 0, h, (pr % p.nwx) * W, (pr / p.nwx) * 2 * W, b, out_policy);
           ptx::bulk_commit_group();
         }
         tr(33 + 4 * pr);
         ++np_e;
       };
-      float sum_cur = softmax_pair(0);
-      for (int pr = 0; pr < p.n_pairs; ++pr) {
-        float sum_next = 0.f;
-        if (pr + 1 < p.n_pairs) sum_next = softmax_pair(pr + 1);
-        epilogue_pair(pr, sum_cur);
-        sum_cur = sum_next;
+      float sum_prev = 0.f;
+#pragma unroll 1
+      for (int pr = 0; pr <= p.n_pairs; ++pr) {            // one call site each: the kernel is instruction-cache sensitive
+        float sum_new = 0.f;
+        if (pr < p.n_pairs) sum_new = softmax_pair(pr);
+        if (pr > 0) epilogue_pair(pr - 1, sum_prev);
+        sum_prev = sum_new;
       }
-      if ((warp & 1) == 0 && ptx::elect_one()) ptx::bulk_wait_read0();   // staging rows alias phase-A tiles of the next item
+      if (warp == 0 && ptx::elect_one()) ptx::bulk_wait_read0();   // staging rows alias phase-A tiles of the next item
     }
-    if ((warp & 1) == 0 && ptx::elect_one()) ptx::bulk_wait_all();
-    if (tr.buf) tr.buf[kTraceLen - 1] = tr.n;
+    if (warp == 0 && ptx::elect_one()) ptx::bulk_wait_all();
+    tr.finish();
   }
   // ---- teardown ------------------------------------------------------------------------------------
   ptx::tc_fence_before();
@@ -900,9 +966,9 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   CUtensorMap twq, twk, twv, trq, trk, trv, tw, to;
   View ov;
   ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
-  if (!make_box_map(&twq, q, g, io, W, W) || !make_box_map(&twk, k, g, io, W, W) || !make_box_map(&twv, v, g, io, W, W) ||
+  if (!make_box_map(&twq, q, g, io, W, 2 * W) || !make_box_map(&twk, k, g, io, W, 2 * W) || !make_box_map(&twv, v, g, io, W, 2 * W) ||
       !make_box_map(&trq, q, g, io, GW, CH) || !make_box_map(&trk, k, g, io, GW, CH) || !make_box_map(&trv, v, g, io, GW, CH) ||
-      !make_weight_map(&tw, w16) || !make_box_map(&to, ov, g, io, W, W)) {
+      !make_weight_map(&tw, w16) || !make_box_map(&to, ov, g, io, W, 2 * W)) {
     *msg = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
@@ -918,7 +984,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.trace = trace_enabled();
   p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", NR);
   p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
-  auto kern = eva_fused_kernel<T, W, GW, CH, NR>;
+  auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, true> : eva_fused_kernel<T, W, GW, CH, NR, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
   const int max_ctas = env_int("EVA_SM100_CTAS_PER_SM", 2) * sm_count();   // tuning knob; 2 = as many as fit

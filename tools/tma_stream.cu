@@ -101,6 +101,38 @@ __global__ void __launch_bounds__(256, 1) stream_kernel(const __grid_constant__ 
           if (ptx::elect_one()) ptx::tma_load_5d(slot(n_issue), &t_win, bar0 + 8 * (n_issue % p.D), 0, t * p.H + h, 7 * (w & 3), 7 * (w >> 2), b);
           ++n_issue;
         }
+    } else if (p.mode == 6 && p.sub == 3) {
+      const int lane = threadIdx.x & 31;
+      for (int t = 0; t < 3; ++t)
+        for (int r = 0; r < 7; ++r) {
+          if ((t * 7 + r) % p.warps != wid) continue;
+          if (n_issue - n_wait == (uint32_t)p.D) {
+            wait(bar0 + 8 * (n_wait % p.D), (n_wait / p.D) & 1);
+            ++n_wait;
+          }
+          // tile = 112 tokens x 128 B; token stride 3*H*128 B; lane -> (row = 4 j + lane / 8, 16-byte chunk = lane % 8)
+          const uint8_t* src = p.flat + ((long long)(b * 784 + 112 * r) * 3 * p.H + (t * p.H + h)) * 128 + (long long)(lane >> 3) * 3 * p.H * 128 + (lane & 7) * 16;
+          const uint32_t dst0 = slot(n_issue) + (lane >> 3) * 128;
+          const uint32_t sw0 = (uint32_t)(((lane & 7) ^ (lane >> 3)) << 4), sw1 = (uint32_t)(((lane & 7) ^ (4 + (lane >> 3))) << 4);
+#pragma unroll 4
+          for (int j = 0; j < 28; ++j) {
+            const uint32_t dst = dst0 + j * 512 + ((j & 1) ? sw1 : sw0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            src += (long long)4 * 3 * p.H * 128;
+          }
+          asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(bar0 + 8 * (n_issue % p.D)) : "memory");
+          __syncwarp();
+          if (ptx::elect_one()) ptx::mbar_arrive(bar0 + 8 * (n_issue % p.D));
+          ++n_issue;
+        }
+    } else if (p.mode == 6 && (p.sub == 4 || p.sub == 5)) {      // stacked window pairs (7 x 14 tokens), aligned / 15 rows into the slot
+      for (int t = 0; t < 3; ++t)
+        for (int w = 0; w < 8; ++w) {
+          if ((t * 8 + w) % p.warps != wid) continue;
+          acquire();
+          if (ptx::elect_one()) ptx::tma_load_5d(slot(n_issue) + (p.sub == 5 ? 15 * 128 : 0), &t_win2, bar0 + 8 * (n_issue % p.D), 0, t * p.H + h, 7 * (w & 3), 14 * (w >> 2), b);
+          ++n_issue;
+        }
     } else if (p.mode == 6 && p.sub == 2) {
       if (h == 0)
         for (int t = 0; t < 3; ++t)
@@ -204,16 +236,16 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const int tile_bytes[8] = {14336, 6272, 14336, 43008, 14336, 7168, 14336, 12544};
-  for (int Bsub : {49})            // 49 images = 147 items (one per CTA), 43 MB: L2-resident after the first pass
-    for (int sub = 0; sub < 1; ++sub)
-      for (int warps : {1, 4})
+  for (int Bsub : {49, B})            // 49 images = 147 items (one per CTA), 43 MB: L2-resident after the first pass
+    for (int sub : {1, 4, 5})
+      for (int warps : {1, 2})
         for (int per_sm = 1; per_sm <= (Bsub == B ? 2 : 1); ++per_sm)
-          for (int D : {1, 2, 3}) {
+          for (int D : {2, 4}) {
             const size_t smem = (size_t)D * (sub == 2 ? kSlot : 16384) * warps + 1024;
             if (smem * per_sm > 225 * 1024 || smem > 220 * 1024) continue;
-            if (Bsub == B && !(warps * per_sm >= 4 && D == 2)) continue;
+            
             const int reps = Bsub == B ? 1 : 40;
-            P p{Bsub * H, H, 6, D, sub == 2 ? 43008 : sub ? 6272 : 14336, 0, warps, reps, sub, qkv, (long long)bytes};
+            P p{Bsub * H, H, 6, D, sub == 2 ? 43008 : sub == 1 ? 6272 : sub >= 4 ? 12544 : 14336, 0, warps, reps, sub, qkv, (long long)bytes};
             const size_t smem_req = per_sm == 1 ? (smem > 116 * 1024 ? smem : 116 * 1024) : smem;
             float best = 1e9f;
             for (int it = 0; it < 3; ++it) {
@@ -227,13 +259,13 @@ int main(int argc, char** argv) {
             }
             unsigned long long hc[4096];
             cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
-            if (sub == 0) printf("   CTA 0 warp 0: %llu ops, total %llu cyc, in acquire (wait) %llu cyc/op, in the TMA instruction %llu cyc/op\n", hc[1024], hc[0],
+            if (false) printf("   CTA 0 warp 0: %llu ops, total %llu cyc, in acquire (wait) %llu cyc/op, in the TMA instruction %llu cyc/op\n", hc[1024], hc[0],
                                  hc[2048] / (hc[1024] ? hc[1024] : 1), hc[3072] / (hc[1024] ? hc[1024] : 1));
             const double moved = (double)Bsub * N * 3 * H * 128 * reps;
             const double active = Bsub == B ? sms * per_sm : (Bsub * (sub == 2 ? 1 : H) < sms ? Bsub * (sub == 2 ? 1 : H) : sms);
-            const double ops = (double)Bsub * (sub == 2 ? 21 : sub ? 48 * H : 21 * H) * reps;
+            const double ops = (double)Bsub * (sub == 2 ? 21 : sub == 1 ? 48 * H : sub >= 4 ? 24 * H : 21 * H) * reps;
             printf("%s %s  warps/CTA %d  CTAs/SM %d  depth %d: %7.1f us  %6.0f GB/s  %.2f ops/us per active SM (%.0f active)\n", Bsub == B ? "HBM" : "L2 ",
-                   sub == 2 ? "384B-row box" : sub ? "window boxes" : "row boxes   ", warps, per_sm, D, best * 1e3, moved / (best * 1e-3) / 1e9,
+                   sub == 5 ? "stacked +15 rows" : sub == 4 ? "stacked aligned " : sub == 3 ? "cp.async rows" : sub == 2 ? "384B-row box" : sub ? "window boxes" : "row boxes   ", warps, per_sm, D, best * 1e3, moved / (best * 1e-3) / 1e9,
                    ops / (best * 1e3) / (Bsub == B ? sms : active), active);
             fflush(stdout);
           }

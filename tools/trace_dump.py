@@ -80,22 +80,28 @@ def read(which):
     n = int(buf[8191])
     return [(int(buf[i]), int(buf[i + 1])) for i in range(0, n, 2)]
 tma, mma = read(2), read(1)
-def per_item(ev, base, first):
-    items, cur = [], {}
-    for e, t in ev:
-        if e == base + first and cur:
+def split(ev, start_ev):
+    items, cur = [], []
+    for e in ev:
+        if e[0] == start_ev and cur:
             items.append(cur)
-            cur = {}
-        if base <= e < base + 1000:
-            cur[e - base] = t
-    items.append(cur)
+            cur = []
+        cur.append(e)
+    if cur:
+        items.append(cur)
     return items
-ti, mi = per_item(tma, 1000, 0), per_item(mma, 2000, 0)
-print(f'== loads: {len(ti)} items (TMA), {len(mi)} items (MMA); per ring position: issue time relative to the item\'s first issue, issue -> seen by MMA thread')
+ti, mi = split(tma, 1000), split(mma, 101)
 k = min(len(ti), len(mi)) - 1
-for pos in sorted(ti[1].keys()) if k > 1 else []:
-    d_issue = [ti[j][pos] - ti[j][0] for j in range(1, k) if pos in ti[j]]
-    d_lat = [mi[j][pos] - ti[j][pos] for j in range(1, k) if pos in ti[j] and pos in mi[j]]
-    if d_issue:
-        lat = f'{sum(d_lat) / len(d_lat):8.0f}' if d_lat else '       -'
-        print(f'   pos {pos:3d}: issued at +{sum(d_issue) / len(d_issue):8.0f}   issue->seen {lat}')
+print(f'== loads: per ring position, issue time relative to the first issue of the item (T = TMA warp, M = MMA warp), issue -> seen by the MMA thread')
+rows = {}
+for j in range(1, k):
+    t0 = ti[j][0][1]
+    issued = {e - 1000: (t, 'T') for e, t in ti[j] if 1000 <= e < 2000}
+    issued.update({e - 1000: (t, 'M') for e, t in mi[j] if 1000 <= e < 2000})
+    seen = {e - 2000: t for e, t in mi[j] if 2000 <= e < 3000}
+    for pos, (t, who) in issued.items():
+        rows.setdefault(pos, []).append((t - t0, (seen[pos] - t) if pos in seen else None, who))
+for pos in sorted(rows):
+    r = rows[pos]
+    lat = [x[1] for x in r if x[1] is not None]
+    print(f'   pos {pos:3d} {r[0][2]}: issued at +{sum(x[0] for x in r) / len(r):8.0f}   issue->seen ' + (f'{sum(lat) / len(lat):8.0f}' if lat else '       -'))
