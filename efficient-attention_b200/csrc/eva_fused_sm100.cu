@@ -206,7 +206,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   uint8_t* P2t = sm + C::kP2;
   float* bias2 = reinterpret_cast<float*>(sm + C::kBias);
   float* lbuf = reinterpret_cast<float*>(sm + C::kLbuf);
-  static_assert(NR <= 7, "one kNormDone barrier per chunk-row");
+  static_assert(NR <= 7 && (NR & 1) == 1, "one kNormDone barrier per chunk-row; pass-2 issuer parity assumes odd NR");
   const uint32_t bars = ptx::smem_u32(sm + C::kBars);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + C::kTmemPtr);
   auto bar = [&](int i) { return bars + 8u * i; };
@@ -267,9 +267,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       const uint64_t keep = ptx::policy_evict_last(), stream = ptx::policy_evict_first();
       Tracer<TR> tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[2] : nullptr, 0};
       // With two issuers the previous use of a slot may belong to the other warp.  A parity wait can only tell the last two
-      // phases apart, so at every acquire the use BEFORE the previous one must already be known to be consumed.  That holds
-      // by causality everywhere (commits complete in order, and each warp's own earlier acquires imply it) except for the
-      // first q window of phase B, which therefore waits for the phi-logit MMAs first (see below).
+      // phases apart, so at every acquire the use BEFORE the previous one must already be known to be consumed.  The
+      // assignment (passes 1 and 2: even ring positions here, odd ones in the MMA warp, except k_0 and k_1; phase B: q and k
+      // here, v there) makes that hold by causality: commits complete in order, and each warp's own earlier acquires or
+      // waits imply it.
       auto acquire = [&](uint32_t n, uint32_t bytes) -> uint32_t {   // returns the slot of ring position n; arms its full barrier
         const uint32_t s = slot_of(n);
         ptx::mbar_wait(bar(kFree0 + s), par_of(n) ^ 1);
@@ -280,9 +281,13 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         const int b = item / p.H, h = item % p.H;
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM)
-          const uint32_t s = acquire(nb + 2 * r, TOK * 128);
+        for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM) ...
+          uint32_t s = acquire(nb + 2 * r, TOK * 128);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          if (r < 2) {                                   // ... and the first two k rows: the MMA warp is still finishing the previous item
+            s = acquire(nb + 2 * r + 1, TOK * 128);
+            if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          }
         }
         if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
           ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
@@ -295,13 +300,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if (ptx::elect_one()) ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
         }
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {                   // pass 2: all k rows (L2 hits)
-          const uint32_t s = acquire(nb + C::nPass2 + r, TOK * 128);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+        for (int q = 0; q < 2 * NR; q += 2) {            // pass 2: K_0 .. K_{NR-1}, V_0 .. V_{NR-1}; this warp issues the even positions
+          const uint32_t s = acquire(nb + C::nPass2 + q, TOK * 128);
+          const bool is_k = q < NR;
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), is_k ? &tr_k : &tr_v, bar(kFull0 + s), 0, h, 0, (is_k ? q : q - NR) * CH, b, keep);
         }
-        // Q(0) takes over the slot of V_{NR-4} (MMA warp), whose previous tile K_{NR-1} is this warp's own: make sure that one
-        // has been consumed before the parity wait inside acquire (every K-row hand-back precedes this commit)
-        ptx::mbar_wait(bar(kD2Full), ni & 1);
         const int item_next = item + gridDim.x;
 #pragma unroll 1
         for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: q and k of the window pairs (L2)
@@ -357,7 +360,6 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
         return s;
       };
-      static_assert(NR >= 4, "V rows of pass 2 reuse the slots of the last four K rows");
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
         const int b = item / p.H, h = item % p.H;
         auto load_row = [&](uint32_t n, const CUtensorMap* tm, int r) {
@@ -370,8 +372,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         };
         // ---- pass 1: chunk means ------------------------------------------------------------
         tr(101);
-        load_row(nb + 1, &tr_k, 0);
-        load_row(nb + 3, &tr_k, 1);
+        auto load_pass2 = [&](int q) {                        // relative position in pass 2: K_q (q < NR) or V_{q-NR}
+          load_row(nb + C::nPass2 + q, q < NR ? &tr_k : &tr_v, q < NR ? q : q - NR);
+        };
 #pragma unroll 1
         for (int r = 0; r < NR; ++r) {
           const uint32_t nq = nb + 2 * r, nk = nq + 1;
@@ -410,6 +413,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           free_raw(nb + C::nAt);
         }
         tr(103);
+        load_pass2(1);                                        // slot of k_{NR-1}
+        load_pass2(3);                                        // slot of W: waits for the Linear MMA just issued
         ptx::mbar_wait(bar(kOmFull), ni & 1);
         tr(104);      // q_bar / k_bar tiles written
         ptx::tc_fence_after();
@@ -435,7 +440,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             free_raw(nk);
             if (r == NR - 1) ptx::umma_commit(bar(kD2Full));
           }
-          if (r >= NR - 4) load_row(nk + 4, &tr_v, r - (NR - 4));   // V_j takes over the slot of K_{NR-4+j}
+          if (r & 1) load_pass2(r + 4);                     // odd positions are this warp's: K_5, V_0, V_2 for NR = 7
         }
         tr(110);
         // ---- beta^T += V_r^T P_r^T once the softmax batch is in shared memory ----------------------------
@@ -454,7 +459,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             free_raw(nv);
             if (r == NR - 1) ptx::umma_commit(bar(kBetaFull));
           }
-          if (r + 4 < NR) load_row(nv + 4, &tr_v, r + 4);
+          if ((r & 1) == 0 && r + 4 < NR) load_pass2(NR + r + 4);   // V_4, V_6
         }
         load_v_pair(0);                                      // slot of V_{NR-2}
         tr(111);
@@ -652,7 +657,6 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       tr(11);
       {
         const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
-        float lg[NR];
         {
           uint32_t dd[NR][8];
 #pragma unroll
@@ -663,8 +667,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             float dsel = __uint_as_float(dd[r][0]);
 #pragma unroll
             for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? __uint_as_float(dd[r][c]) : dsel;
-            lg[r] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * n2[r]) : kNegInf;   // log2 units
-            lbuf[r * 128 + tid] = lg[r];
+            lbuf[r * 128 + tid] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * n2[r]) : kNegInf;   // log2 units
           }
         }
         // the q_bar tile is dead (every phi-logit MMA has completed): clear the P2 tiles that overlay it
@@ -673,8 +676,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::named_bar_sync(1, kComputeThreads);
         tr(13);
         const int t0 = tok_ok ? tcx * CH : 0;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {                       // not unrolled: instruction-cache footprint
           const float* lb_ = lbuf + r * 128;
           float lv[CH * CH];
 #pragma unroll
@@ -696,7 +699,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
           for (int j = 0; j < CH * CH; j += 2) { sum0 += ex2(lv[j] - mx); sum1 += ex2(lv[j + 1] - mx); }
-          const float pt = __fdividef(ex2(lg[r] - mx), sum0 + sum1);
+          const float pt = __fdividef(ex2(lb_[tid] - mx), sum0 + sum1);
           if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + r * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
         }
       }
