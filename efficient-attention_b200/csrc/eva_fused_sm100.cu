@@ -43,7 +43,7 @@ constexpr int kSlotBytes = 16384;
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
   kD2Full, kP2Full, kBetaFull, kStatsFull,
-  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kNormDone0, kNumBars = kNormDone0 + 7
+  kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kItem0, kItem1, kNormDone0, kNumBars = kNormDone0 + 7
 };
 
 struct Params {
@@ -54,6 +54,7 @@ struct Params {
   int has_q;                     // 0: adaptive_proj == 'none' (mu = 0)
   float mu_coeff, inv_mu_coeff, ln_eps;
   const float* noise;
+  unsigned int* next_item;       // global work counter (starts at gridDim.x): items are handed out dynamically, SMs differ by > 10 %
   const float* bias2;            // [H][kBiasSlab/4] fp32 bias x log2(e), row stride LS (packed by pack_params), or NULL
   void* out;
   int trace;
@@ -98,7 +99,8 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int kLn = kZeroEnd;                 // [6][64] fp32: b_q, gain_q, beta_q, b_k, gain_k, beta_k
   static constexpr int kBars = (kLn + 6 * 64 * 4 + 7) & ~7;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
-  static constexpr int kBytes = kTmemPtr + 16;
+  static constexpr int kItemIds = kTmemPtr + 16;       // 2 x int: work item of the current / next round (dynamic scheduling)
+  static constexpr int kBytes = kItemIds + 16;
   static constexpr int kDynamic = kBytes + 1024;
   static_assert(kDynamic <= 115712, "two CTAs per SM need <= 113 KB each");
   // TMEM columns
@@ -214,6 +216,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_per_item = C::nPairs + 3 * p.n_pairs;
+  volatile int* const item_ids = reinterpret_cast<volatile int*>(sm + C::kItemIds);
+  // consumers (MMA warp, compute warps): the TMA warp publishes the item of round ni in item_ids[ni & 1]
+  auto item_of_round = [&](uint32_t ni) -> int {
+    ptx::mbar_wait(bar(kItem0 + (ni & 1)), (ni >> 1) & 1);
+    return item_ids[ni & 1];
+  };
 
   // ---- one-time setup --------------------------------------------------------------------------
   for (int i = tid; i < C::kZeroEnd / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
@@ -243,6 +251,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kOFree1), kComputeThreads);
     ptx::mbar_init(bar(kBiasFull), 1);
     ptx::mbar_init(bar(kBiasFree), kComputeThreads);
+    ptx::mbar_init(bar(kItem0), 1);
+    ptx::mbar_init(bar(kItem1), 1);
     for (int r = 0; r < NR; ++r) ptx::mbar_init(bar(kNormDone0 + r), kComputeThreads);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
@@ -278,8 +288,15 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
         return s;
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
+      auto publish = [&](uint32_t round, int it) {       // safe to overwrite: round - 2 was read before any load of round - 1 was consumed
+        if (ptx::elect_one()) { item_ids[round & 1] = it; ptx::mbar_arrive(bar(kItem0 + (round & 1))); }
+      };
+      int item = blockIdx.x;
+      publish(0, item);
+      for (; item < p.items; ++ni, nb += n_per_item) {
         const int b = item / p.H, h = item % p.H;
+        int item_next = 0;                               // fetched now, needed in phase B: the atomic's latency hides under pass 1
+        if (lane == 0) item_next = (int)atomicAdd(p.next_item, 1u);
 #pragma unroll 1
         for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM) ...
           uint32_t s = acquire(nb + 2 * r, TOK * 128);
@@ -305,7 +322,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           const bool is_k = q < NR;
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), is_k ? &tr_k : &tr_v, bar(kFull0 + s), 0, h, 0, (is_k ? q : q - NR) * CH, b, keep);
         }
-        const int item_next = item + gridDim.x;
+        item_next = __shfl_sync(0xffffffffu, item_next, 0);
+        publish(ni + 1, item_next);
 #pragma unroll 1
         for (int pr = 0; pr < p.n_pairs; ++pr) {         // phase B: q and k of the window pairs (L2)
           if (item_next < p.items) {                     // warm L2 with the next item's q/k chunk-rows, a few per pair
@@ -326,6 +344,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           s = acquire(nb + C::nPairs + 3 * pr + 1, C::kPairBytes);
           if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)) + C::kKOff * 128, &tw_k, bar(kFull0 + s), 0, h, x0, y0, b, stream);
         }
+        item = item_next;
       }
       tr.finish();
     }
@@ -360,7 +379,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(bar(kFull0 + s), bytes);
         return s;
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
+      for (;; ++ni, nb += n_per_item) {
+        const int item = item_of_round(ni);
+        if (item >= p.items) break;
         const int b = item / p.H, h = item % p.H;
         auto load_row = [&](uint32_t n, const CUtensorMap* tm, int r) {
           const uint32_t s = acquire(n, TOK * 128);
@@ -529,7 +550,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     uint8_t* const ostage = sm + C::kOStage;
     const uint64_t out_policy = ptx::policy_evict_first();
     Tracer<TR> tr{(p.trace && blockIdx.x == 0 && tid == 0) ? g_trace[0] : nullptr, 0};
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++ni, nb += n_per_item) {
+    for (;; ++ni, nb += n_per_item) {
+      const int item = item_of_round(ni);
+      if (item >= p.items) break;
       const int b = item / p.H, h = item % p.H;
       tr(1);
       // ---- pass 1 readback: means^T (TMEM) -> fp16 means tile [c'][feat] in the borrowed slot ----------
@@ -867,8 +890,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 // bias [H or 1][L][L] -> per-head slabs [L][LS] fp32 pre-multiplied by log2(e)
 __global__ void pack_params(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ w16,
                             const float* __restrict__ bias, long long bias_sh, float* __restrict__ bias2, int H, int L,
-                            int LS, int slab_floats) {
+                            int LS, int slab_floats, unsigned int* next_item, unsigned int first_free_item) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *next_item = first_free_item;          // items 0 .. grid-1 are taken by blockIdx, the rest are handed out dynamically
   if (idx < 128 * 64) {
     const int row = idx >> 6, col = idx & 63;
     const float* src = row < 64 ? wq : wk;
@@ -963,7 +987,11 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
   __half* w16 = reinterpret_cast<__half*>(workspace);
   float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 128 * 64 * sizeof(__half));
-  pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / 4);
+  unsigned int* next_item = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(bias2) + (size_t)g.H * C::kBiasSlab);
+  const int items = g.B * g.H;
+  const int max_ctas = env_int("EVA_SM100_CTAS_PER_SM", 2) * sm_count();   // tuning knob; 2 = as many as fit
+  const int grid = items < max_ctas ? items : max_ctas;
+  pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / 4, next_item, (unsigned)grid);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *msg = "pack_params launch"; return e; }
   CUtensorMap twq, twk, twv, trq, trk, trv, tw, to;
@@ -983,15 +1011,13 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
   p.has_q = ada.w_q != nullptr;
   p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
-  p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out;
+  p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out; p.next_item = next_item;
   p.trace = trace_enabled();
   p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", NR);
   p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
   auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, true> : eva_fused_kernel<T, W, GW, CH, NR, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
-  const int max_ctas = env_int("EVA_SM100_CTAS_PER_SM", 2) * sm_count();   // tuning knob; 2 = as many as fit
-  const int grid = p.items < max_ctas ? p.items : max_ctas;
   kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, to, p);
   *msg = "kernel launch";
   return cudaGetLastError();
@@ -1033,7 +1059,7 @@ bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, c
 
 size_t fused_workspace_bytes(const Geo& g) {
   const int L = g.window * g.window, LS = (L + 1) | 1;
-  return 128 * 64 * sizeof(__half) + (size_t)g.H * ((L * LS * 4 + 15) & ~15);
+  return 128 * 64 * sizeof(__half) + (size_t)g.H * ((L * LS * 4 + 15) & ~15) + 16;   // W tile | bias slabs | work counter
 }
 
 // diagnostic (not part of the public ABI): copy the phase trace of CTA 0 to the host
