@@ -52,42 +52,58 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled through NVML every 2 ms WHILE the timed regions run (the recipe's clocks line).
+    In-process NVML instead of an `nvidia-smi -lms` child: the child's start-up stalls kernel submission for tens of
+    milliseconds, which is longer than a whole timed region."""
+
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.t, self.stop = index, [], None, threading.Event()
+        self.max_mhz = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.t = None
         return self
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), int(mask)))
+            except Exception:
+                pass
+            self.stop.wait(0.002)
+
+    def mark(self):
+        """Samples taken before this call are warm-up and do not count."""
+        self.t0 = time.perf_counter()
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop.set()
+        if self.t is not None:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in self.rows if len(r) >= 6)]
-        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
-                'samples': len(sm)}
+        rows = [r for r in self.rows if r[0] >= getattr(self, 't0', 0.0)]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        reasons = [n for n, bit in self.REASONS if any(r[2] & bit for r in rows)]
+        return {'sm_mhz': statistics.median(r[1] for r in rows), 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                'samples': len(rows)}
 
 
 def build_layer(device, dtype):
@@ -225,14 +241,19 @@ def run_ours(args):
         def core():
             return _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
 
-        for _ in range(max(Wm, 3)):
+        clk = ClockSampler(local)
+        clk.__enter__()                      # sampled over both timed regions (core and e2e)
+        t_w, n_w = time.perf_counter(), 0
+        while n_w < max(Wm, 3) or time.perf_counter() - t_w < 0.2:     # >= W launches and >= 0.2 s: clocks and caches settled
             _, path = core()
+            n_w += 1
+            if n_w % 16 == 0:
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        clk = ClockSampler(local)
-        clk.__enter__()                      # sampled over both timed regions (core and e2e)
+        clk.mark()
         torch.cuda.synchronize()
         per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         ev0.record()
@@ -282,7 +303,8 @@ def run_ours(args):
             'dtype': args.dtype + ' I/O, f32 softmax/accumulate', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'tokens_per_step': tokens_per_step,
                        'l2_policy': f'inputs larger than L2 (qkv {3 * DIM * elem * B * TOKENS / 2**20:.0f} MiB per GPU)',
-                       'kernel_path': 'fused tcgen05/TMA' if path == 1 else 'generic two-stage CUDA-core'},
+                       'kernel_path': 'fused tcgen05/TMA' if path == 1 else 'generic two-stage CUDA-core',
+                       'warmup_launches': n_w},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(B), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'launch_ms': launch_ms,
@@ -305,7 +327,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')

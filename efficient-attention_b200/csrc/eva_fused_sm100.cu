@@ -65,7 +65,7 @@ struct Params {
 template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int L = W * W;
   static constexpr int LP8 = (L + 7) & ~7;
-  static constexpr int LS = (L + 1) | 1;        // bias row stride (odd: conflict-free across rows); column L = row max
+  static constexpr int LS = (L + 4) & ~3;       // bias row stride: 16-byte rows (LDS.128, conflict-free for stride 52); column L = row max
   static constexpr int NCX = GW / CH;           // chunks per chunk-row
   static constexpr int CN = NR * NCX;           // chunks per item
   static constexpr int CNP = 8 * NR;            // padded chunk index space: c' = 8 r + cx
@@ -140,6 +140,24 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): halves the FP32 instruction count of the softmax
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // N consecutive TMEM columns -> registers (x16 / x8 / x1 pieces, compile time)
@@ -784,28 +802,51 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         const float mrfa = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * scale_log2;
         const float mx = fmaxf(mloc, mrfa);
         if (pr == 1) tr(251);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         uint32_t pl[LP8 / 2], prf[32], zeros[LP8 / 2];
         // 16-bit P, two keys per TMEM column: word m = (e[2m], e[2m+1]).  Window b's keys start at the even position LP8
         // (words go left-aligned into the second LP8/2 columns as they are); window a's start at the odd position
         // LP8 - L, so its words are funnel-shifted by 16 bits and right-aligned in the first LP8/2 columns (below).
-        static_assert((L & 1) == 1 && LP8 - L == 7, "P packing assumes window 7");
+        // The exponent arguments and the row sum are computed two at a time (FADD2 / FFMA2).
+        static_assert((L & 1) == 1 && LP8 - L == 7 && LS % 4 == 0, "P packing assumes window 7");
+        const uint64_t sc2 = pk2(scale_log2, scale_log2), nmx2 = pk2(-mx, -mx);
+        uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-        for (int m = 0; m < LP8 / 2; ++m) {
-          const float a = (2 * m < L) ? ex2(fmaf(sl[(2 * m < L) ? 2 * m : 0], scale_log2, brow[(2 * m < L) ? 2 * m : 0] - mx)) : 0.f;
-          const float c2 = (2 * m + 1 < L) ? ex2(fmaf(sl[(2 * m + 1 < L) ? 2 * m + 1 : 0], scale_log2, brow[(2 * m + 1 < L) ? 2 * m + 1 : 0] - mx)) : 0.f;
-          if (m & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
-          pl[m] = IoFmt<T>::pack2(a, c2);
-          zeros[m] = 0u;
+        for (int m4 = 0; m4 < (L + 3) / 4; ++m4) {          // four keys per 16-byte bias load
+          const float4 bq = *reinterpret_cast<const float4*>(brow + 4 * m4);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int m = 2 * m4 + hh;                      // P word: keys 2m, 2m+1
+            if (2 * m < L) {
+              const uint64_t t = fma2(pk2(sl[2 * m], sl[(2 * m + 1 < L) ? 2 * m + 1 : 2 * m]), sc2,
+                                      add2(hh ? pk2(bq.z, bq.w) : pk2(bq.x, bq.y), nmx2));
+              float x0, x1;
+              upk2(t, x0, x1);
+              const float e0 = ex2(x0), e1 = (2 * m + 1 < L) ? ex2(x1) : 0.f;
+              if (m & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1));
+              pl[m] = IoFmt<T>::pack2(e0, e1);
+            }
+          }
         }
-        const float nmx = -mx;
+#pragma unroll
+        for (int m = (L + 1) / 2; m < LP8 / 2; ++m) pl[m] = 0u;
+#pragma unroll
+        for (int m = 0; m < LP8 / 2; ++m) zeros[m] = 0u;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float a = C::chunk_ok(2 * j) ? ex2(fmaf(sr[C::chunk_ok(2 * j) ? 2 * j : 0], scale_log2, nmx)) : 0.f;
-          const float c2 = C::chunk_ok(2 * j + 1) ? ex2(fmaf(sr[C::chunk_ok(2 * j + 1) ? 2 * j + 1 : 0], scale_log2, nmx)) : 0.f;
-          if (j & 1) { s1 += a; s3 += c2; } else { s0 += a; s2 += c2; }
-          prf[j] = IoFmt<T>::pack2(a, c2);
+          if (C::chunk_ok(2 * j)) {                          // 2j is never a padding column when 2j+1 is a chunk
+            const uint64_t t = fma2(pk2(sr[2 * j], sr[C::chunk_ok(2 * j + 1) ? 2 * j + 1 : 2 * j]), sc2, nmx2);
+            float x0, x1;
+            upk2(t, x0, x1);
+            const float e0 = ex2(x0), e1 = C::chunk_ok(2 * j + 1) ? ex2(x1) : 0.f;
+            if (j & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1));
+            prf[j] = IoFmt<T>::pack2(e0, e1);
+          } else {
+            prf[j] = 0u;
+          }
         }
+        float s0, s1, s2, s3;
+        upk2(acc0, s0, s1);
+        upk2(acc1, s2, s3);
         if (pr == 1) tr(252);
         // P (16-bit, two per column) overwrites the S columns this thread has finished reading
         if (ws) {
@@ -1058,7 +1099,7 @@ bool fused_supported(const Geo& g, int io_dtype, const View& q, const View& k, c
 }
 
 size_t fused_workspace_bytes(const Geo& g) {
-  const int L = g.window * g.window, LS = (L + 1) | 1;
+  const int L = g.window * g.window, LS = (L + 4) & ~3;
   return 128 * 64 * sizeof(__half) + (size_t)g.H * ((L * LS * 4 + 15) & ~15) + 16;   // W tile | bias slabs | work counter
 }
 
