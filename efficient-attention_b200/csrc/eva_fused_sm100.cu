@@ -39,10 +39,11 @@ constexpr int kComputeThreads = 128;
 constexpr uint32_t kTmemCols = 256;
 constexpr int kSlots = 4;
 constexpr int kSlotBytes = 16384;
+constexpr int kP2Split = 4;     // pass 2: chunk-rows [0, kP2Split) and [kP2Split, NR) are handed to the beta MMAs separately
 
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
-  kD2Full, kP2Full, kBetaFull, kStatsFull,
+  kD2Full, kP2Full, kP2FullB, kBetaFull, kStatsFull,
   kSFull, kPFull, kOFull0, kOFull1, kOFree0, kOFree1, kBiasFull, kBiasFree, kItem0, kItem1, kNormDone0, kNumBars = kNormDone0 + 7
 };
 
@@ -259,6 +260,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kOmFull), kComputeThreads);
     ptx::mbar_init(bar(kD2Full), 1);
     ptx::mbar_init(bar(kP2Full), kComputeThreads);
+    ptx::mbar_init(bar(kP2FullB), kComputeThreads);
     ptx::mbar_init(bar(kBetaFull), 1);
     ptx::mbar_init(bar(kStatsFull), kComputeThreads);
     ptx::mbar_init(bar(kSFull), 1);
@@ -487,6 +489,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int r = 0; r < NR; ++r) {
+          if (r == kP2Split) { ptx::mbar_wait(bar(kP2FullB), ni & 1); ptx::tc_fence_after(); }
           const uint32_t nv = nb + C::nPass2 + NR + r;
           wait_full(nv);
           ptx::tc_fence_after();
@@ -717,8 +720,15 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         ptx::named_bar_sync(1, kComputeThreads);
         tr(13);
         const int t0 = tok_ok ? tcx * CH : 0;
+        // two sub-batches: the beta MMAs of the first rows (and with them the hand-back of their V slots, i.e. the
+        // request of the last V rows) start while the softmax of the remaining rows is still being computed
 #pragma unroll 1
         for (int r = 0; r < NR; ++r) {                       // not unrolled: instruction-cache footprint
+          if (r == kP2Split) {
+            ptx::fence_proxy_async_smem();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar(kP2Full));
+          }
           const float* lb_ = lbuf + r * 128;
           float lv[CH * CH];
 #pragma unroll
@@ -746,7 +756,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(kP2Full));
+      ptx::mbar_arrive(bar(kP2FullB));
       tr(14);
       // ---- beta^T (TMEM) -> beta tile [c'][feat] -------------------------------------------------------
       ptx::mbar_wait(bar(kBetaFull), ni & 1);
@@ -1054,7 +1064,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out; p.next_item = next_item;
   p.trace = trace_enabled();
-  p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", NR);
+  p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", 0);   // measured: warming L2 with the next item's rows no longer pays (0.5 % slower)
   p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
   auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, true> : eva_fused_kernel<T, W, GW, CH, NR, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
