@@ -134,6 +134,12 @@ int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const Ev
   if (!out) return fail(EVA_ERR_INVALID, "out is NULL");
   if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
     return fail(EVA_ERR_INVALID, "bias_stride_h must be 0 or L*J = %d", g.L * g.J);
+  if (g.n_chunks > 0 && eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias)) {
+    const char* msg = "";
+    const cudaError_t ec = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, out,
+                                                     reinterpret_cast<cudaStream_t>(stream), &msg);
+    return ec == cudaSuccess ? EVA_OK : fail(EVA_ERR_CUDA, "eva_window_attention(causal window): %s: %s", msg, cudaGetErrorString(ec));
+  }
   const cudaError_t e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias,
                                                 bias_stride_h, out, reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_window_attention");
@@ -183,6 +189,13 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   if (path_taken) *path_taken = 0;
   cudaError_t e = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, k_bar, beta, st);
   if (e != cudaSuccess) return cuda_fail(e, "eva_forward(chunk_stats)");
+  if (eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias)) {
+    const char* msg = "";
+    e = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, out, st, &msg);
+    if (path_taken) *path_taken = 2;
+    if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal window): %s: %s", msg, cudaGetErrorString(e));
+    return EVA_OK;
+  }
   e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out, st);
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_forward(window_attention)");
 }

@@ -1,0 +1,357 @@
+// Causal EVA window attention for sm_100a (causal_eva.py:722-783) on tcgen05 / TMEM / TMA: stage B of the causal layer
+// for window = 256, no halo, head_dim 64, 16-bit I/O, no padding mask, no position bias (BASELINE config c5).  Stage A
+// (chunk statistics k_bar, beta) stays in chunk_stats_kernel.
+//
+// Work item = one window of one (batch, head): 256 queries x (256 causal local keys + up to 64 chunk keys).
+//   S   = Q [K_w ; k_bar]^T     M = 128 per row-block; row-block 0 only needs keys 0-127 (causality), row-block 1 all 256
+//   P   = softmax(S) with the causal mask j <= i inside the diagonal block and the chunk mask c < (query chunk)
+//         (masked logits are -5e4 in the reference, i.e. exactly 0 after the softmax: every row sees its own key)
+//   O   = P [V_w ; beta]        A operand from TMEM
+// One persistent CTA per SM, 10 warps: warps 0-3 own row-block 0 (TMEM lane = query row), warps 4-7 row-block 1,
+// warp 8 = TMA producer (+ k_bar / beta fp32 -> 16-bit tiles), warp 9 = MMA issuer.  Two stages of {Q, K, V} (3 x 32 KB) so
+// the loads of the next window run under the current one.  The logits stay in TMEM and are read twice (max, then exp) in
+// 32-column pieces; P overwrites the first half of the columns it came from; O lands in columns of the same region that
+// are dead by then, so each row-block needs exactly n_keys TMEM columns (192 + 320 = 512).  The output rows are staged in
+// the (dead) Q tile of the stage and leave through one TMA store per row-block.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <type_traits>
+
+#include "common.cuh"
+#include "launch.h"
+#include "sm100_ptx.cuh"
+
+namespace eva {
+namespace causal {
+
+constexpr int kWin = 256, kThreads = 320, kStageBytes = 3 * 32768, kKbBytes = 16384;
+constexpr int kSmemBars = 2 * kStageBytes + 2 * kKbBytes;
+constexpr int kDynamic = kSmemBars + 256 + 1024;
+
+enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFree1,
+           kSFull0, kSFull1, kPFull0, kPFull1, kOFull0, kOFull1, kOFree0, kOFree1, kNumBars };
+
+struct Params {
+  int B, H, N, n_win, items, n_chunks, cnp, chunk;
+  const float *kbar, *beta;      // [B, H, n_chunks, 64] fp32 from chunk_stats_kernel
+};
+
+template <typename T> struct Fmt;
+template <> struct Fmt<__half> {
+  static constexpr uint32_t kUmma = ptx::kFmtF16;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+template <> struct Fmt<__nv_bfloat16> {
+  static constexpr uint32_t kUmma = ptx::kFmtBF16;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
+                         const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_o, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t bars = ptx::smem_u32(sm + kSmemBars);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kSmemBars + kNumBars * 8);
+  auto bar = [&](int i) { return bars + 8u * i; };
+  auto stage_ptr = [&](int s) { return sm + s * kStageBytes; };                       // Q | K | V, 32 KB each
+  auto kb_ptr = [&](int s) { return sm + 2 * kStageBytes + s * kKbBytes; };           // k_bar | beta, 8 KB each
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < (2 * kKbBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(sm + 2 * kStageBytes)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 8 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(bar(kFullQK0 + s), 1);
+      ptx::mbar_init(bar(kFullV0 + s), 1);
+      ptx::mbar_init(bar(kFullKB0 + s), 1);
+      ptx::mbar_init(bar(kFree0 + s), 3);          // MMA commit (K, V, k_bar, beta read) + one output-store drain per row-block (Q tile)
+      ptx::mbar_init(bar(kSFull0 + s), 1);
+      ptx::mbar_init(bar(kPFull0 + s), 128);
+      ptx::mbar_init(bar(kOFull0 + s), 1);
+      ptx::mbar_init(bar(kOFree0 + s), 128);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
+  }
+  if (warp == 9) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  // TMEM columns of row-block rb: logits [base, base + n_loc + cnp), P (16-bit pairs) from base, O in the last 64 columns
+  // of [base, base + n_loc + 64): rb 0 -> [0, 192), rb 1 -> [192, 512)
+  auto base_col = [](int rb) -> uint32_t { return rb ? 192u : 0u; };
+  auto o_col = [](int rb) -> uint32_t { return rb ? 448u : 128u; };
+
+  if (warp == 8) {
+    // =================================== TMA producer ==========================================
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int wi = item % p.n_win, bh = item / p.n_win, h = bh % p.H, b = bh / p.H;
+      if (it >= 2) ptx::mbar_wait(bar(kFree0 + s), ((it >> 1) - 1) & 1);
+      const uint32_t st = ptx::smem_u32(stage_ptr(s));
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bar(kFullQK0 + s), 65536);
+        ptx::tma_load_4d(st, &t_q, bar(kFullQK0 + s), 0, h, wi * kWin, b);
+        ptx::tma_load_4d(st + 32768, &t_k, bar(kFullQK0 + s), 0, h, wi * kWin, b);
+        ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), 32768);
+        ptx::tma_load_4d(st + 65536, &t_v, bar(kFullV0 + s), 0, h, wi * kWin, b);
+      }
+      // chunk keys / values of this (batch, head): fp32 rows -> 16-bit swizzled tiles (rows >= n_chunks stay zero)
+      uint8_t* kb = kb_ptr(s);
+      const float* src_k = p.kbar + (long long)bh * p.n_chunks * 64;
+      const float* src_b = p.beta + (long long)bh * p.n_chunks * 64;
+      for (int idx = lane; idx < p.n_chunks * 8; idx += 32) {
+        const int row = idx >> 3, ch = idx & 7;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8) + 1);
+        const int off = row * 128 + ((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(kb + off) = make_uint4(Fmt<T>::pack2(a0.x, a0.y), Fmt<T>::pack2(a0.z, a0.w), Fmt<T>::pack2(a1.x, a1.y), Fmt<T>::pack2(a1.z, a1.w));
+        *reinterpret_cast<uint4*>(kb + 8192 + off) = make_uint4(Fmt<T>::pack2(b0.x, b0.y), Fmt<T>::pack2(b0.z, b0.w), Fmt<T>::pack2(b1.x, b1.y), Fmt<T>::pack2(b1.z, b1.w));
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(bar(kFullKB0 + s));
+    }
+  } else if (warp == 9) {
+    // =================================== MMA issuer ============================================
+    constexpr uint32_t fmt = Fmt<T>::kUmma;
+    constexpr uint32_t id_s128 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 128), id_s256 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 256);
+    constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+    const uint32_t id_rfa = ptx::umma_idesc(fmt, fmt, 0, 0, 128, (uint32_t)p.cnp);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(stage_ptr(s))), dK = dQ + (32768 >> 4), dV = dQ + (65536 >> 4);
+      const uint64_t dKB = ptx::umma_desc_sw128(ptx::smem_u32(kb_ptr(s))), dBT = dKB + (8192 >> 4);
+      ptx::mbar_wait(bar(kFullQK0 + s), ph);
+      ptx::mbar_wait(bar(kFullKB0 + s), ph);
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        if (it > 0) ptx::mbar_wait(bar(kOFree0 + rb), (it - 1) & 1);     // the epilogue has read O of the previous window
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t dQr = dQ + (uint64_t)(rb * (16384 >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + base_col(rb), dQr + 2 * ks, dK + 2 * ks, rb ? id_s256 : id_s128, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + base_col(rb) + 128u * (rb + 1), dQr + 2 * ks, dKB + 2 * ks, id_rfa, ks > 0);
+          ptx::umma_commit(bar(kSFull0 + rb));
+        }
+      }
+      ptx::mbar_wait(bar(kFullV0 + s), ph);
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        ptx::mbar_wait(bar(kPFull0 + rb), it & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const int n_ks = 8 * (rb + 1);
+#pragma unroll 1
+          for (int ks = 0; ks < n_ks; ++ks) ptx::umma_ts(tmem + o_col(rb), tmem + base_col(rb) + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+#pragma unroll 1
+          for (int ks = 0; ks < p.cnp / 16; ++ks) ptx::umma_ts(tmem + o_col(rb), tmem + base_col(rb) + 64u * (rb + 1) + 8 * ks, dBT + 128 * ks, id_pv, 1);
+          ptx::umma_commit(bar(kOFull0 + rb));
+          if (rb == 1) ptx::umma_commit(bar(kFree0 + s));
+        }
+      }
+    }
+  } else {
+    // =================================== softmax / epilogue warps ===============================
+    const int rb = warp >> 2, wl = warp & 3;
+    const int i = 32 * wl + lane;                        // query row inside the row-block
+    const uint32_t trow = tmem + ((uint32_t)(32 * wl) << 16);
+    const uint32_t cS = base_col(rb), cO = o_col(rb);
+    const int n_blk = rb + 1;                            // 128-key blocks this row-block attends to
+    const float scale_log2 = 0.125f * kLog2e;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int wi = item % p.n_win, bh = item / p.n_win, h = bh % p.H, b = bh / p.H;
+      const int qc = (wi * kWin + 128 * rb + i) / p.chunk;     // chunk keys c < qc are visible (causal_eva.py:725-739)
+      ptx::mbar_wait(bar(kSFull0 + rb), it & 1);
+      ptx::tc_fence_after();
+      // ---- pass 1: row maximum over the visible keys ----
+      float m0 = kNegInf, m1 = kNegInf;
+#pragma unroll 1
+      for (int g = 0; g < 4 * n_blk; ++g) {
+        float v[32];
+        ptx::tmem_ld16(trow + cS + 32 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld16(trow + cS + 32 * g + 16, reinterpret_cast<uint32_t*>(v) + 16);
+        ptx::tmem_ld_wait();
+        const int lim = (g >> 2) < rb ? 1 << 30 : i - 32 * (g & 3);       // key e of this piece is visible iff e <= lim
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          m0 = fmaxf(m0, e <= lim ? v[e] : kNegInf);
+          m1 = fmaxf(m1, e + 1 <= lim ? v[e + 1] : kNegInf);
+        }
+      }
+#pragma unroll 1
+      for (int g = 0; g < p.cnp / 16; ++g) {
+        float v[16];
+        ptx::tmem_ld16(trow + cS + 128 * n_blk + 16 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) m0 = fmaxf(m0, 16 * g + e < qc ? v[e] : kNegInf);
+      }
+      const float nmx = -fmaxf(m0, m1) * scale_log2;
+      // ---- pass 2: P = exp2(scale * s - max), 16-bit pairs written over the first half of the columns just read ----
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < 4 * n_blk; ++g) {
+        float v[32];
+        uint32_t pk[16];
+        ptx::tmem_ld16(trow + cS + 32 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld16(trow + cS + 32 * g + 16, reinterpret_cast<uint32_t*>(v) + 16);
+        ptx::tmem_ld_wait();
+        const int lim = (g >> 2) < rb ? 1 << 30 : i - 32 * (g & 3);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float a = e <= lim ? ex2(fmaf(v[e], scale_log2, nmx)) : 0.f;
+          const float c = e + 1 <= lim ? ex2(fmaf(v[e + 1], scale_log2, nmx)) : 0.f;
+          s0 += a; s1 += c;
+          pk[e >> 1] = Fmt<T>::pack2(a, c);
+        }
+        ptx::tmem_st16(trow + cS + 16 * g, pk);
+      }
+#pragma unroll 1
+      for (int g = 0; g < p.cnp / 16; ++g) {
+        float v[16];
+        uint32_t pk[8];
+        ptx::tmem_ld16(trow + cS + 128 * n_blk + 16 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float a = 16 * g + e < qc ? ex2(fmaf(v[e], scale_log2, nmx)) : 0.f;
+          const float c = 16 * g + e + 1 < qc ? ex2(fmaf(v[e + 1], scale_log2, nmx)) : 0.f;
+          s0 += a; s1 += c;
+          pk[e >> 1] = Fmt<T>::pack2(a, c);
+        }
+        ptx::tmem_st8(trow + cS + 64 * n_blk + 8 * g, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kPFull0 + rb));
+      // ---- epilogue: O / rowsum -> the (dead) Q rows of this row-block -> TMA store ----
+      ptx::mbar_wait(bar(kOFull0 + rb), it & 1);
+      ptx::tc_fence_after();
+      float o[64];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cO + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kOFree0 + rb));
+      const float inv = 1.0f / (s0 + s1);
+      const int orow = 128 * rb + i;
+      uint8_t* row = stage_ptr(s) + orow * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(row + ((ch ^ (orow & 7)) << 4)) =
+            make_uint4(Fmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), Fmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                       Fmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Fmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1 + rb, 128);
+      if (wl == 0 && ptx::elect_one()) {
+        ptx::tma_store_4d(&t_o, ptx::smem_u32(stage_ptr(s)) + rb * 16384, 0, h, wi * kWin + 128 * rb, b);
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_read0();                          // the Q tile of this stage may be overwritten by the next load
+        ptx::mbar_arrive(bar(kFree0 + s));
+      }
+    }
+    if (wl == 0 && ptx::elect_one()) ptx::bulk_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 9) ptx::tmem_dealloc(tmem, 512);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// [B, N, H, 64] view -> (64, H, N, B) tensor map with a (64, 1, rows, 1) box, 128-byte swizzle
+static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long long sn, long long sh, const Geo& g, int io_dtype, int rows) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)g.H, (cuuint64_t)g.N, (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, io_dtype == EVA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T>
+static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar, const float* beta,
+                            void* out, cudaStream_t st, const char** msg) {
+  CUtensorMap tq, tk, tv, to;
+  if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin) ||
+      !make_seq_map(&tv, v.ptr, v.sb, v.sn, v.sh, g, io_dtype, kWin) ||
+      !make_seq_map(&to, out, (long long)g.N * g.H * 64, (long long)g.H * 64, 64, g, io_dtype, 128)) {
+    *msg = "cuTensorMapEncodeTiled failed";
+    return cudaErrorInvalidValue;
+  }
+  Params p{};
+  p.B = g.B; p.H = g.H; p.N = g.N; p.n_win = g.N / kWin; p.items = g.B * g.H * p.n_win;
+  p.n_chunks = g.n_chunks; p.cnp = (g.n_chunks + 15) & ~15; p.chunk = g.chunk;
+  p.kbar = kbar; p.beta = beta;
+  auto kern = eva_causal_window_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamic);
+  if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.items < sms ? p.items : sms;
+  kern<<<grid, kThreads, kDynamic, st>>>(tq, tk, tv, to, p);
+  *msg = "kernel launch";
+  return cudaGetLastError();
+}
+
+}  // namespace causal
+
+bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                             const float* bias) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (disabled) return false;
+  if (g.dims != 1 || !g.causal || g.D != 64 || g.window != causal::kWin || g.ext != 0 || g.chunk_ext != 0 || mask || bias) return false;
+  if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
+  if (g.N % causal::kWin != 0 || g.n_chunks < 1 || g.n_chunks > 64 || g.chunk < 1) return false;
+  for (const View* x : {&q, &k, &v}) {
+    if (x->sh * 2 % 16 || x->sn * 2 % 16 || x->sb * 2 % 16) return false;
+    if (x->sh <= 0 || x->sn <= 0 || x->sb <= 0) return false;
+    if (reinterpret_cast<uintptr_t>(x->ptr) % 16) return false;
+  }
+  return causal::get_encode() != nullptr;
+}
+
+cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
+                                 const float* beta, void* out, cudaStream_t st, const char** msg) {
+  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, out, st, msg);
+  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, out, st, msg);
+}
+
+}  // namespace eva

@@ -6,6 +6,8 @@
 //   chunk_stats_kernel    eva.py:155-196, causal_eva.py:676-719
 //   window_attn_kernel    eva.py:200-227, causal_eva.py:722-783, local_attention.py:134-182,
 //                         abstract_attention.py:115-133
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -106,6 +108,153 @@ chunk_stats_kernel(const Geo g, const View q, const View k, const View v, const 
 #pragma unroll
     for (int i = 0; i < DPL; ++i)
       if (Feat<D>::has(lane, i)) beta_out[obase + lane + 32 * i] = acc[i] * inv_l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage A for long 1-D chunks (causal LM: 256 tokens per chunk): one CTA of 8 warps per (batch, head, chunk) instead
+// of one warp -- the warp kernel above walks the chunk token by token with a shuffle reduction per logit.
+//   phase 1  means: warp w sums tokens w, w+8, ...; lane = feature pair (coalesced 128-byte rows)
+//   phase 2  Linear + LayerNorm: thread t < 64 -> k side feature t, 64 <= t < 128 -> q side; omega -> shared memory
+//   phase 3  logits: thread = token (its 128-byte k row from global / L2), block softmax
+//   phase 4  beta: warp w accumulates p_s v_s over its tokens, lane = feature pair; cross-warp sum
+// head_dim 64, no halo, no padding mask (the warp kernel keeps those cases).  Semantics as chunk_stats_kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, const EvaAdaptive ada,
+                       const float* __restrict__ noise, float* __restrict__ kbar_out, float* __restrict__ beta_out) {
+  constexpr int D = 64;
+  extern __shared__ float sm[];
+  float* part = sm;                 // [8][128]  per-warp partial sums (q | k), later beta partials [8][64]
+  float* mean = part + 8 * 128;     // [128]     q means | k means
+  float* yv = mean + 128;           // [128]     Linear outputs, q side | k side
+  float* om = yv + 128;             // [64]      omega
+  float* red = om + 64;             // [16]      block reductions
+  float* pj = red + 16;             // [Jc]      softmax weights
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long wg = blockIdx.x;
+  const int c = (int)(wg % g.n_chunks);
+  const int h = (int)((wg / g.n_chunks) % g.H);
+  const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+  const int t0 = c * g.chunk;
+  const float scale = 0.125f;
+  // ---- phase 1 ----
+  float sq0 = 0.f, sq1 = 0.f, sk0 = 0.f, sk1 = 0.f;
+  for (int s = warp; s < g.Jc; s += 8) {
+    const T* qr = q.row<T>(b, t0 + s, h);
+    const T* kr = k.row<T>(b, t0 + s, h);
+    sq0 += to_f32(qr[2 * lane]); sq1 += to_f32(qr[2 * lane + 1]);
+    sk0 += to_f32(kr[2 * lane]); sk1 += to_f32(kr[2 * lane + 1]);
+  }
+  part[warp * 128 + 2 * lane] = sq0; part[warp * 128 + 2 * lane + 1] = sq1;
+  part[warp * 128 + 64 + 2 * lane] = sk0; part[warp * 128 + 64 + 2 * lane + 1] = sk1;
+  __syncthreads();
+  if (tid < 128) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += part[w * 128 + tid];
+    mean[tid] = a / (float)g.Jc;
+  }
+  __syncthreads();
+  // ---- phase 2 ----
+  if (tid < 128) {
+    const bool kside = tid < 64;
+    const int f = tid & 63;
+    const float* W = kside ? ada.w_k : ada.w_q;
+    const float* bias = kside ? ada.b_k : ada.b_q;
+    const float* mv = mean + (kside ? 64 : 0);
+    float y = 0.f;
+    if (W) {
+      y = bias ? __ldg(bias + f) : 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(W + f * D);
+#pragma unroll 4
+      for (int i4 = 0; i4 < D / 4; ++i4) {
+        const float4 w4 = __ldg(wr + i4);
+        y = fmaf(w4.x, mv[4 * i4], y); y = fmaf(w4.y, mv[4 * i4 + 1], y);
+        y = fmaf(w4.z, mv[4 * i4 + 2], y); y = fmaf(w4.w, mv[4 * i4 + 3], y);
+      }
+    }
+    yv[kside ? 64 + f : f] = y;
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const bool kside = tid < 64;
+    const int f = tid & 63;
+    const float* yy = yv + (kside ? 64 : 0);
+    const float* gain = kside ? ada.ln_gain_k : ada.ln_gain_q;
+    const float* lb = kside ? ada.ln_bias_k : ada.ln_bias_q;
+    float y = yy[f];
+    if (gain) {
+      float s1 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < D; ++i) s1 += yy[i];
+      const float mu = s1 * (1.0f / D);
+      float s2 = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < D; ++i) { const float d = yy[i] - mu; s2 = fmaf(d, d, s2); }
+      y = (y - mu) * (1.0f / sqrtf(s2 * (1.0f / D) + ada.ln_eps)) * __ldg(gain + f) + __ldg(lb + f);
+    }
+    if (kside) kbar_out[wg * D + f] = y;
+    mean[kside ? 64 + f : f] = y;          // normalised q_bar | k_bar (the means are dead)
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float o = ada.w_q ? ada.mu_coeff * (mean[tid] + mean[64 + tid]) : 0.f;
+    if (noise) o += __ldg(noise + wg * D + tid);
+    om[tid] = o;
+  }
+  __syncthreads();
+  // ---- phase 3 ----
+  float mloc = kNegInf;
+  for (int s = tid; s < g.Jc; s += 256) {
+    const T* kr = k.row<T>(b, t0 + s, h);
+    float acc = 0.f;
+#pragma unroll
+    for (int p8 = 0; p8 < 8; ++p8) {
+      float f[8];
+      load8<T>(kr + 8 * p8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(f[i], om[8 * p8 + i] - 0.5f * f[i], acc);
+    }
+    const float lg = scale * acc;
+    pj[s] = lg;
+    mloc = fmaxf(mloc, lg);
+  }
+  mloc = warp_max(mloc);
+  if (lane == 0) red[warp] = mloc;
+  __syncthreads();
+  float mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  float lsum = 0.f;
+  for (int s = tid; s < g.Jc; s += 256) {
+    const float pe = exp_nonpos(pj[s] - mx);
+    pj[s] = pe;
+    lsum += pe;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[8 + warp] = lsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[8 + w];
+  // ---- phase 4 ----
+  float b0 = 0.f, b1 = 0.f;
+  for (int s = warp; s < g.Jc; s += 8) {
+    const T* vr = v.row<T>(b, t0 + s, h);
+    const float pe = pj[s];
+    b0 = fmaf(pe, to_f32(vr[2 * lane]), b0);
+    b1 = fmaf(pe, to_f32(vr[2 * lane + 1]), b1);
+  }
+  part[warp * 64 + 2 * lane] = b0;
+  part[warp * 64 + 2 * lane + 1] = b1;
+  __syncthreads();
+  if (tid < 64) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += part[w * 64 + tid];
+    beta_out[wg * D + tid] = a / tot;
   }
 }
 
@@ -277,6 +426,16 @@ static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View&
                                         const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
                                         float* kbar, float* beta, cudaStream_t st) {
   constexpr int DPL = Feat<D>::kPerLane;
+  if constexpr (D == 64) {
+    // long 1-D chunks (causal LM): one CTA per chunk
+    static const bool generic_only = [] { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); return e && e[0] == '1'; }();
+    if (!generic_only && g.dims == 1 && g.chunk_ext == 0 && !mask && g.Jc >= 64 && g.Jc <= 8192) {
+      const size_t smem_cta = (size_t)(8 * 128 + 128 + 128 + 64 + 16 + g.Jc) * sizeof(float);
+      const long long total_cta = (long long)g.B * g.H * g.n_chunks;
+      chunk_stats_cta_kernel<T><<<(unsigned)total_cta, 256, smem_cta, st>>>(g, q, k, v, ada, noise, kbar, beta);
+      return cudaGetLastError();
+    }
+  }
   const size_t smem = 2 * (size_t)D * D * sizeof(float);
   auto kern = chunk_stats_kernel<T, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

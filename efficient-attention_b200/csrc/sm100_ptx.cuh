@@ -66,7 +66,7 @@ __device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t par
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 // The slow path is kept out of line so that the ~dozen wait sites stay small.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait_suspend(bar, parity, 2000)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
@@ -123,6 +123,17 @@ __device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const void* tmap,
 __device__ __forceinline__ void tma_prefetch_5d_hint(const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
   asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.L2::cache_hint [%0, {%1, %2, %3, %4, %5}], %6;"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 // TMA store shared -> global (bulk async group)

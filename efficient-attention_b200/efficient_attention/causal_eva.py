@@ -132,6 +132,8 @@ class CausalEVAttention(nn.Module):
     def _process_input(self, x, key_padding_mask):
         if self.window_size > 0:
             if key_padding_mask is None:
+                if x.shape[-2] % self.window_size == 0:
+                    return x, None        # nothing padded: an all-False mask would only keep the kernels off their mask-free paths
                 x, key_padding_mask = pad_to_multiple(x, self.window_size, dim=-2, create_mask=True)
             else:
                 x = pad_to_multiple(x, self.window_size, dim=-2)

@@ -107,7 +107,7 @@ int eva_window_attention(const EvaGeometry* g, const EvaHeadsView* q, const EvaH
 int eva_forward_workspace_bytes(const EvaGeometry* g, size_t* bytes);
 
 /* Both stages in one call.  *path_taken (optional) receives 1 when the fused sm_100a kernel ran,
- * 0 when the generic two-stage path ran. */
+ * 2 when the generic statistics kernel + the tcgen05 causal window kernel ran, 0 when the generic two-stage path ran. */
 int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
                 const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,

@@ -301,3 +301,66 @@ def test_fused_kernel_many_items_per_cta_fp16():
     per_item = ((out.float() - ref.float()).view(B, 196, H, d).pow(2).sum((1, 3)).sqrt() /
                 ref.float().view(B, 196, H, d).pow(2).sum((1, 3)).sqrt())
     assert float(per_item.max()) < TOL_F16, float(per_item.max())
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float16, TOL_F16), (torch.bfloat16, TOL_BF16)])
+@pytest.mark.parametrize('chunk,with_noise', [(256, False), (64, True), (128, False)])
+def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, dtype, tol):
+    """Causal EVA core (window 256, no halo, head_dim 64, 16-bit I/O: the c5 geometry) through the tcgen05 window kernel
+    and the CTA-per-chunk statistics kernel, against the oracle on identical inputs.  path == 2 proves the tcgen05
+    kernel ran (a silent fall-back to the CUDA-core kernel would hide a regression)."""
+    from efficient_attention import _abi
+    B, H, d, N, w = 2, 2, 64, 1024, 256
+    g = torch.Generator().manual_seed(chunk + int(with_noise))
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.1).to(dtype)
+    ada = _rand_ada(d, g)
+    C = N // chunk
+    noise = torch.randn(B, H, C, d, generator=g) if with_noise else None
+    q64, k64, v64 = (qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3))
+    want, kbar_w, beta_w = O.eva_core(q64, k64, v64, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0,
+                                      **{k_: v_.double() for k_, v_ in ada.items()}, mu_coeff=1.0,
+                                      noise=noise.double() if with_noise else None, causal=True, halo_right=False,
+                                      mask_queries=True, return_stats=True)
+    want = want.permute(0, 2, 1, 3).reshape(B, N, H * d)
+    dev = _dev()
+    qd = qkv.to(dev)
+    q, k, v = qd[:, :, 0], qd[:, :, 1], qd[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0, causal=True, halo_left_only=True,
+                             mask_queries=True)
+    ada_s = _abi_ada(ada, dev, 1.0)
+    nz = noise.to(dev) if with_noise else None
+    kbar, beta = _abi.eva_chunk_stats(q, k, v, geom, ada_s, noise=nz)          # CTA-per-chunk kernel (chunk >= 64)
+    assert rel_l2(kbar.cpu(), kbar_w) < 2e-5 and rel_l2(beta.cpu(), beta_w) < 2e-5
+    out, path = _abi.eva_forward(q, k, v, geom, ada_s, noise=nz, return_path=True)
+    assert path == 2
+    assert not torch.isnan(out).any()
+    err = rel_l2(out.cpu(), want)
+    assert err < tol, (chunk, with_noise, dtype, err)
+
+
+def test_causal_tcgen05_many_windows_per_cta_fp16():
+    """More windows than SMs (every CTA loops over several windows, both stages of the ring are reused) against the
+    CUDA-core kernels fed with the same statistics."""
+    import os
+    import subprocess
+    import sys
+    from efficient_attention import _abi
+    B, H, d, N = 6, 8, 64, 2048           # 6 * 8 * 8 = 384 windows
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.1).half().to(dev)
+    ada = _abi_ada(_rand_ada(d, g), dev, 1.0)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    geom = _abi.eva_geometry(q, seq_shape=(N,), window=256, ext=0, chunk=256, chunk_ext=0, causal=True, halo_left_only=True,
+                             mask_queries=True)
+    out, path = _abi.eva_forward(q, k, v, geom, ada, return_path=True)
+    assert path == 2
+    # reference: fp32 copies of the same 16-bit values take the CUDA-core kernels (the tcgen05 path is 16-bit only)
+    q32, k32, v32 = (t.float() for t in (q, k, v))
+    geom32 = _abi.eva_geometry(q32, seq_shape=(N,), window=256, ext=0, chunk=256, chunk_ext=0, causal=True,
+                               halo_left_only=True, mask_queries=True)
+    ref, path32 = _abi.eva_forward(q32, k32, v32, geom32, ada, return_path=True)
+    assert path32 == 0
+    per_item = ((out.float() - ref).view(B, N // 256, 256, H, d).pow(2).sum((2, 4)).sqrt() /
+                ref.view(B, N // 256, 256, H, d).pow(2).sum((2, 4)).sqrt())
+    assert float(per_item.max()) < TOL_F16, float(per_item.max())

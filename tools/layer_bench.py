@@ -82,5 +82,5 @@ with torch.no_grad(), warnings.catch_warnings():
                             overlap_window=False)
     m = reinit(ea.CausalEVAttention(embed_dim=512, num_heads=8, dropout=0.0, self_attention=True, attn_args=ns)).to(dev).half().eval()
     x = torch.randn(4096, 16, 512, device=dev, dtype=torch.float16)
-    report('c5 causal EVA T=4096 C=512 B=16 (generic CUDA-core kernels)', 16 * 4096, 512,
+    report('c5 causal EVA T=4096 C=512 B=16 (CTA-per-chunk statistics + tcgen05 window kernel)', 16 * 4096, 512,
            timed(lambda: m(x, x, x, need_weights=False)[0], max(3, args.iters // 4)))
