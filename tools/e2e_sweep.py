@@ -1,0 +1,32 @@
+"""e2e (host -> device -> host) throughput of EVA.forward through HostPipeline for several chunk counts / depths, plus the
+raw pinned-copy bandwidth of the box in both directions at once (the bound)."""
+import os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'efficient-attention_b200')); sys.path.insert(0, ROOT)
+import bench
+from efficient_attention.streaming import HostPipeline
+dev = torch.device('cuda', 0)
+B = 1024
+layer = bench.build_layer(dev, torch.float16)
+x_host = torch.randn(B, 28, 28, 192).half().pin_memory()
+y_host = torch.empty_like(x_host).pin_memory()
+# raw duplex copy bound
+xd = torch.empty_like(x_host, device=dev); yd = torch.randn(B, 28, 28, 192, device=dev, dtype=torch.float16)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def duplex():
+    with torch.cuda.stream(s1): xd.copy_(x_host, non_blocking=True)
+    with torch.cuda.stream(s2): y_host.copy_(yd, non_blocking=True)
+for _ in range(2): duplex()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5): duplex()
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+print(f'raw duplex copy of one step: {dt * 1e3:.2f} ms  ({x_host.numel() * 2 / dt / 1e9:.1f} GB/s each way)  -> bound {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
+for n_chunks in (4, 8, 16, 32):
+    for depth in (2, 3):
+        pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth)
+        for _ in range(3): pipe(x_host, y_host)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(8): pipe(x_host, y_host)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 8
+        print(f'chunks {n_chunks:2d} depth {depth}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
