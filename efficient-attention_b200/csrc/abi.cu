@@ -39,6 +39,7 @@ int make_geo(const EvaGeometry* in, eva::Geo* g) {
   g->chunk = in->chunk; g->chunk_ext = in->chunk_ext;
   g->causal = in->causal ? 1 : 0; g->mask_queries = in->mask_queries ? 1 : 0;
   g->mask_fill = in->mask_is_neg_inf ? -INFINITY : eva::kMaskVal;
+  g->bias_toeplitz = in->bias_toeplitz ? 1 : 0;
   if (in->dims == 2) {
     if (in->grid_h <= 0 || in->grid_w <= 0 || in->grid_h * in->grid_w != in->tokens)
       return fail(EVA_ERR_INVALID, "grid %dx%d does not cover %d tokens", in->grid_h, in->grid_w, in->tokens);
@@ -134,9 +135,9 @@ int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const Ev
   if (!out) return fail(EVA_ERR_INVALID, "out is NULL");
   if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
     return fail(EVA_ERR_INVALID, "bias_stride_h must be 0 or L*J = %d", g.L * g.J);
-  if (g.n_chunks > 0 && eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias)) {
+  if (g.n_chunks > 0 && eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias, bias_stride_h)) {
     const char* msg = "";
-    const cudaError_t ec = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, out,
+    const cudaError_t ec = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out,
                                                      reinterpret_cast<cudaStream_t>(stream), &msg);
     return ec == cudaSuccess ? EVA_OK : fail(EVA_ERR_CUDA, "eva_window_attention(causal window): %s: %s", msg, cudaGetErrorString(ec));
   }
@@ -189,9 +190,9 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   if (path_taken) *path_taken = 0;
   cudaError_t e = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, k_bar, beta, st);
   if (e != cudaSuccess) return cuda_fail(e, "eva_forward(chunk_stats)");
-  if (eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias)) {
+  if (eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias, bias_stride_h)) {
     const char* msg = "";
-    e = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, out, st, &msg);
+    e = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out, st, &msg);
     if (path_taken) *path_taken = 2;
     if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal window): %s: %s", msg, cudaGetErrorString(e));
     return EVA_OK;

@@ -119,6 +119,7 @@ struct Geo {
   int n_windows, L, J;    // queries per window, local keys per window
   int n_chunks, Jc;       // chunk keys, tokens per chunk (incl. halo)
   float mask_fill;        // -5e4, or -inf for the dense softmax baseline
+  int bias_toeplitz;      // caller's hint: bias[i][j] = f(i - j)
 };
 
 // token id of slot `slot` of group `grp` (edge `size`, halo `ext`), -1 when off the sequence.

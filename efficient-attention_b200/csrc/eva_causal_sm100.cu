@@ -1,5 +1,5 @@
 // Causal EVA window attention for sm_100a (causal_eva.py:722-783) on tcgen05 / TMEM / TMA: stage B of the causal layer
-// for window = 256, no halo, head_dim 64, 16-bit I/O, no padding mask, no position bias (BASELINE config c5).  Stage A
+// for window = 256, no halo, head_dim 64, 16-bit I/O, no padding mask, optional Toeplitz (T5) position bias (BASELINE c5).  Stage A
 // (chunk statistics k_bar, beta) stays in chunk_stats_kernel.
 //
 // Work item = one window of one (batch, head): 256 queries x (256 causal local keys + up to 64 chunk keys).
@@ -29,7 +29,8 @@ namespace causal {
 
 constexpr int kWin = 256, kThreads = 320, kStageBytes = 3 * 32768, kKbBytes = 16384;
 constexpr int kSmemBars = 2 * kStageBytes + 2 * kKbBytes;
-constexpr int kDynamic = kSmemBars + 256 + 1024;
+constexpr int kSmemBias = kSmemBars + 256;          // [256] fp32: Toeplitz position bias by distance i - j, x log2(e)
+constexpr int kDynamic = kSmemBias + 1024 + 1024;
 
 enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFree1,
            kSFull0, kSFull1, kPFull0, kPFull1, kOFull0, kOFull1, kOFree0, kOFree1, kNumBars };
@@ -37,6 +38,7 @@ enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFr
 struct Params {
   int B, H, N, n_win, items, n_chunks, cnp, chunk;
   const float *kbar, *beta;      // [B, H, n_chunks, 64] fp32 from chunk_stats_kernel
+  const float* bias;             // [256, 256] fp32 with bias[i][j] = f(i - j) (T5 bias shared by the heads), or NULL
 };
 
 template <typename T> struct Fmt;
@@ -82,6 +84,8 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
   }
+  float* const dbias = reinterpret_cast<float*>(sm + kSmemBias);
+  for (int n = tid; n < kWin; n += kThreads) dbias[n] = p.bias ? __ldg(p.bias + (long long)n * kWin) * kLog2e : 0.f;   // column 0: distance n
   if (warp == 9) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
@@ -193,10 +197,19 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
         ptx::tmem_ld16(trow + cS + 32 * g + 16, reinterpret_cast<uint32_t*>(v) + 16);
         ptx::tmem_ld_wait();
         const int lim = (g >> 2) < rb ? 1 << 30 : i - 32 * (g & 3);       // key e of this piece is visible iff e <= lim
+        if (p.bias) {
+          const float* db = dbias + (128 * rb + i - 32 * g);              // distance of key e: 128 rb + i - (32 g + e) >= 0 when visible
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          m0 = fmaxf(m0, e <= lim ? v[e] : kNegInf);
-          m1 = fmaxf(m1, e + 1 <= lim ? v[e + 1] : kNegInf);
+          for (int e = 0; e < 32; e += 2) {
+            m0 = fmaxf(m0, e <= lim ? fmaf(v[e], scale_log2, db[-e]) : kNegInf);
+            m1 = fmaxf(m1, e + 1 <= lim ? fmaf(v[e + 1], scale_log2, db[-e - 1]) : kNegInf);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            m0 = fmaxf(m0, e <= lim ? v[e] * scale_log2 : kNegInf);
+            m1 = fmaxf(m1, e + 1 <= lim ? v[e + 1] * scale_log2 : kNegInf);
+          }
         }
       }
 #pragma unroll 1
@@ -205,9 +218,9 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
         ptx::tmem_ld16(trow + cS + 128 * n_blk + 16 * g, reinterpret_cast<uint32_t*>(v));
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) m0 = fmaxf(m0, 16 * g + e < qc ? v[e] : kNegInf);
+        for (int e = 0; e < 16; ++e) m0 = fmaxf(m0, 16 * g + e < qc ? v[e] * scale_log2 : kNegInf);
       }
-      const float nmx = -fmaxf(m0, m1) * scale_log2;
+      const float nmx = -fmaxf(m0, m1);
       // ---- pass 2: P = exp2(scale * s - max), 16-bit pairs written over the first half of the columns just read ----
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
@@ -218,12 +231,23 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
         ptx::tmem_ld16(trow + cS + 32 * g + 16, reinterpret_cast<uint32_t*>(v) + 16);
         ptx::tmem_ld_wait();
         const int lim = (g >> 2) < rb ? 1 << 30 : i - 32 * (g & 3);
+        if (p.bias) {
+          const float* db = dbias + (128 * rb + i - 32 * g);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a = e <= lim ? ex2(fmaf(v[e], scale_log2, nmx)) : 0.f;
-          const float c = e + 1 <= lim ? ex2(fmaf(v[e + 1], scale_log2, nmx)) : 0.f;
-          s0 += a; s1 += c;
-          pk[e >> 1] = Fmt<T>::pack2(a, c);
+          for (int e = 0; e < 32; e += 2) {
+            const float a = e <= lim ? ex2(fmaf(v[e], scale_log2, db[-e] + nmx)) : 0.f;
+            const float c = e + 1 <= lim ? ex2(fmaf(v[e + 1], scale_log2, db[-e - 1] + nmx)) : 0.f;
+            s0 += a; s1 += c;
+            pk[e >> 1] = Fmt<T>::pack2(a, c);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float a = e <= lim ? ex2(fmaf(v[e], scale_log2, nmx)) : 0.f;
+            const float c = e + 1 <= lim ? ex2(fmaf(v[e + 1], scale_log2, nmx)) : 0.f;
+            s0 += a; s1 += c;
+            pk[e >> 1] = Fmt<T>::pack2(a, c);
+          }
         }
         ptx::tmem_st16(trow + cS + 16 * g, pk);
       }
@@ -306,7 +330,7 @@ static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long lo
 
 template <typename T>
 static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar, const float* beta,
-                            void* out, cudaStream_t st, const char** msg) {
+                            const float* bias, void* out, cudaStream_t st, const char** msg) {
   CUtensorMap tq, tk, tv, to;
   if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin) ||
       !make_seq_map(&tv, v.ptr, v.sb, v.sn, v.sh, g, io_dtype, kWin) ||
@@ -317,7 +341,7 @@ static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const Vie
   Params p{};
   p.B = g.B; p.H = g.H; p.N = g.N; p.n_win = g.N / kWin; p.items = g.B * g.H * p.n_win;
   p.n_chunks = g.n_chunks; p.cnp = (g.n_chunks + 15) & ~15; p.chunk = g.chunk;
-  p.kbar = kbar; p.beta = beta;
+  p.kbar = kbar; p.beta = beta; p.bias = bias;
   auto kern = eva_causal_window_kernel<T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
@@ -333,11 +357,12 @@ static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const Vie
 }  // namespace causal
 
 bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                             const float* bias) {
+                             const float* bias, long long bias_sh) {
   static int disabled = -1;
   if (disabled < 0) { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); disabled = (e && e[0] == '1') ? 1 : 0; }
   if (disabled) return false;
-  if (g.dims != 1 || !g.causal || g.D != 64 || g.window != causal::kWin || g.ext != 0 || g.chunk_ext != 0 || mask || bias) return false;
+  if (g.dims != 1 || !g.causal || g.D != 64 || g.window != causal::kWin || g.ext != 0 || g.chunk_ext != 0 || mask) return false;
+  if (bias && !(g.bias_toeplitz && bias_sh == 0)) return false;      // a dense per-head table would be 256 KB of uncoalesced reads per window
   if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
   if (g.N % causal::kWin != 0 || g.n_chunks < 1 || g.n_chunks > 64 || g.chunk < 1) return false;
   for (const View* x : {&q, &k, &v}) {
@@ -349,9 +374,9 @@ bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const Vi
 }
 
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
-                                 const float* beta, void* out, cudaStream_t st, const char** msg) {
-  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, out, st, msg);
-  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, out, st, msg);
+                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg) {
+  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg);
+  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg);
 }
 
 }  // namespace eva

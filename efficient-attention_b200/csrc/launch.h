@@ -27,9 +27,9 @@ cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& 
 
 // Causal window attention on tcgen05 (eva_causal_sm100.cu): stage B of the causal layer for window 256 / head_dim 64 / 16-bit I/O
 bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                             const float* bias);
+                             const float* bias, long long bias_sh);
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
-                                 const float* beta, void* out, cudaStream_t st, const char** msg);
+                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg);
 
 // LARA (lara_generic.cu)
 struct LaraGeo {

@@ -28,7 +28,7 @@ class EvaHeadsView(ctypes.Structure):
 class EvaGeometry(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         'batch', 'heads', 'tokens', 'head_dim', 'dims', 'grid_h', 'grid_w', 'window', 'ext', 'halo_left_only',
-        'chunk', 'chunk_ext', 'causal', 'mask_queries', 'mask_is_neg_inf', 'io_dtype')]
+        'chunk', 'chunk_ext', 'causal', 'mask_queries', 'mask_is_neg_inf', 'io_dtype', 'bias_toeplitz')]
 
 
 class EvaAdaptive(ctypes.Structure):
@@ -77,7 +77,7 @@ def load():
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
                    'eva_forward', 'lara_forward_workspace_bytes', 'lara_forward'):
             getattr(lib, fn).restype = ctypes.c_int
-        if lib.eva_sm100_abi_version() != 1:
+        if lib.eva_sm100_abi_version() != 2:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
         _lib = lib
     return _lib
@@ -134,12 +134,12 @@ def _stream(dev):
 
 
 def eva_geometry(q, *, seq_shape, window, ext, chunk, chunk_ext, causal=False, halo_left_only=False,
-                 mask_queries=False, mask_is_neg_inf=False):
+                 mask_queries=False, mask_is_neg_inf=False, bias_toeplitz=False):
     B, N, H, D = q.shape
     two_d = len(seq_shape) == 2
     return EvaGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N,
                        window, ext, int(halo_left_only), chunk, chunk_ext, int(causal), int(mask_queries),
-                       int(mask_is_neg_inf), io_dtype(q))
+                       int(mask_is_neg_inf), io_dtype(q), int(bias_toeplitz))
 
 
 def num_chunks(geom):

@@ -179,7 +179,8 @@ class CausalEVAttention(nn.Module):
         if chunk >= N:
             raise ValueError('chunk size %d must be smaller than the padded sequence %d (causal_eva.py:680-683)' % (chunk, N))
         geom = _abi.eva_geometry(q, seq_shape=(N,), window=self.window_size, ext=self.ext_size, chunk=chunk,
-                                 chunk_ext=0, causal=bool(self.causal), halo_left_only=True, mask_queries=True)
+                                 chunk_ext=0, causal=bool(self.causal), halo_left_only=True, mask_queries=True,
+                                 bias_toeplitz=bool(self.use_t5_rpe))
         if self.training and noise is None:
             noise = torch.randn(B, H, _abi.num_chunks(geom), D, dtype=torch.float32, device=x.device)
         bias = None

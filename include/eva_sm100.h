@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define EVA_SM100_ABI_VERSION 1
+#define EVA_SM100_ABI_VERSION 2
 
 enum EvaDtype { EVA_F32 = 0, EVA_F16 = 1, EVA_BF16 = 2 };
 
@@ -71,6 +71,9 @@ typedef struct EvaGeometry {
   int32_t mask_is_neg_inf;                /* 1: padded keys get -inf (softmax baseline),
                                              0: -5e4 (eva.py:139)                             */
   int32_t io_dtype;                       /* EvaDtype of q, k, v and out                      */
+  int32_t bias_toeplitz;                  /* (ABI v2) 1: the caller guarantees bias[i][j] depends on i - j only
+                                             (T5 bucketed bias, eva.py:31-65, causal_eva.py:62-97); a hint that lets a
+                                             kernel read one column of the table instead of all of it; 0 is always valid */
 } EvaGeometry;
 
 /* adaptive_mu_q / adaptive_mu_k = Linear(d,d) [+ LayerNorm(d)] shared by all heads

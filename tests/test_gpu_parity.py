@@ -304,8 +304,8 @@ def test_fused_kernel_many_items_per_cta_fp16():
 
 
 @pytest.mark.parametrize('dtype,tol', [(torch.float16, TOL_F16), (torch.bfloat16, TOL_BF16)])
-@pytest.mark.parametrize('chunk,with_noise', [(256, False), (64, True), (128, False)])
-def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, dtype, tol):
+@pytest.mark.parametrize('chunk,with_noise,with_bias', [(256, False, False), (64, True, False), (128, False, True), (256, True, True)])
+def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, with_bias, dtype, tol):
     """Causal EVA core (window 256, no halo, head_dim 64, 16-bit I/O: the c5 geometry) through the tcgen05 window kernel
     and the CTA-per-chunk statistics kernel, against the oracle on identical inputs.  path == 2 proves the tcgen05
     kernel ran (a silent fall-back to the CUDA-core kernel would hide a regression)."""
@@ -316,23 +316,33 @@ def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, dtype, tol):
     ada = _rand_ada(d, g)
     C = N // chunk
     noise = torch.randn(B, H, C, d, generator=g) if with_noise else None
+    bias = None
+    if with_bias:          # Toeplitz like the T5 bucketed bias: bias[i][j] = f(i - j) (entries with j > i are masked anyway)
+        dist = torch.randn(w, generator=g)
+        ii = torch.arange(w)
+        bias = dist[(ii[:, None] - ii[None, :]).clamp(min=0)].unsqueeze(0)
     q64, k64, v64 = (qkv[:, :, i].permute(0, 2, 1, 3).double() for i in range(3))
     want, kbar_w, beta_w = O.eva_core(q64, k64, v64, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0,
                                       **{k_: v_.double() for k_, v_ in ada.items()}, mu_coeff=1.0,
                                       noise=noise.double() if with_noise else None, causal=True, halo_right=False,
-                                      mask_queries=True, return_stats=True)
+                                      mask_queries=True, bias=bias.double() if with_bias else None, return_stats=True)
     want = want.permute(0, 2, 1, 3).reshape(B, N, H * d)
     dev = _dev()
     qd = qkv.to(dev)
     q, k, v = qd[:, :, 0], qd[:, :, 1], qd[:, :, 2]
     geom = _abi.eva_geometry(q, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0, causal=True, halo_left_only=True,
-                             mask_queries=True)
+                             mask_queries=True, bias_toeplitz=with_bias)
     ada_s = _abi_ada(ada, dev, 1.0)
     nz = noise.to(dev) if with_noise else None
     kbar, beta = _abi.eva_chunk_stats(q, k, v, geom, ada_s, noise=nz)          # CTA-per-chunk kernel (chunk >= 64)
     assert rel_l2(kbar.cpu(), kbar_w) < 2e-5 and rel_l2(beta.cpu(), beta_w) < 2e-5
-    out, path = _abi.eva_forward(q, k, v, geom, ada_s, noise=nz, return_path=True)
+    out, path = _abi.eva_forward(q, k, v, geom, ada_s, noise=nz, bias=bias.to(dev) if with_bias else None, return_path=True)
     assert path == 2
+    if with_bias:          # without the caller's Toeplitz guarantee a biased call must stay on the CUDA-core kernel
+        geom0 = _abi.eva_geometry(q, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0, causal=True,
+                                  halo_left_only=True, mask_queries=True)
+        out0, path0 = _abi.eva_forward(q, k, v, geom0, ada_s, noise=nz, bias=bias.to(dev), return_path=True)
+        assert path0 == 0 and rel_l2(out0.cpu(), want) < tol
     assert not torch.isnan(out).any()
     err = rel_l2(out.cpu(), want)
     assert err < tol, (chunk, with_noise, dtype, err)
