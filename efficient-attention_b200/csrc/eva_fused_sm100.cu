@@ -583,20 +583,19 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::mbar_wait(bar(kPoolFull), ni & 1);
       ptx::tc_fence_after();
       tr(2);
-      {
-        float mq[8 * NR], mk[8 * NR];
-        tmem_ld_cols<8 * NR>(trow + C::cPoolQ, reinterpret_cast<uint32_t*>(mq));
-        tmem_ld_cols<8 * NR>(trow + C::cPoolK, reinterpret_cast<uint32_t*>(mk));
+#pragma unroll 1
+      for (int r = 0; r < NR; ++r) {          // rolled (instruction-cache footprint): one chunk-row of means per iteration
+        float mq[8], mk[8];
+        ptx::tmem_ld8(trow + C::cPoolQ + 8 * r, reinterpret_cast<uint32_t*>(mq));
+        ptx::tmem_ld8(trow + C::cPoolK + 8 * r, reinterpret_cast<uint32_t*>(mk));
         ptx::tmem_ld_wait();
         if (feat_lane) {   // padding rows (cx >= NCX) keep whatever the slot held: their Linear rows are never used
 #pragma unroll
-          for (int r = 0; r < NR; ++r)
-#pragma unroll
-            for (int cx = 0; cx < NCX; ++cx) {
-              const int c = 8 * r + cx;
-              *reinterpret_cast<uint16_t*>(At + tile_off(c, feat)) = f16_bits(mq[c]);
-              *reinterpret_cast<uint16_t*>(At + tile_off(64 + c, feat)) = f16_bits(mk[c]);
-            }
+          for (int cx = 0; cx < NCX; ++cx) {
+            const int c = 8 * r + cx;
+            *reinterpret_cast<uint16_t*>(At + tile_off(c, feat)) = f16_bits(mq[cx]);
+            *reinterpret_cast<uint16_t*>(At + tile_off(64 + c, feat)) = f16_bits(mk[cx]);
+          }
         }
       }
       ptx::fence_proxy_async_smem();
@@ -675,9 +674,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::mbar_arrive(bar(kOmFull));
       tr(5);
       // ---- pass 2: |k|^2 of my token in every chunk-row while the rows stream through the ring ---------
-      float n2[NR];
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
+#pragma unroll 1
+      for (int r = 0; r < NR; ++r) {          // rolled (instruction-cache footprint); |k|^2 waits in the logit exchange buffer
         const uint32_t nk = nb + C::nPass2 + r;
         const uint8_t* Kr = slot_ptr(slot_of(nk));
         ptx::mbar_wait(bar(kFull0 + slot_of(nk)), par_of(nk));
@@ -691,7 +689,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             a0 = fmaf(c2.x, c2.x, a0); a1 = fmaf(c2.y, c2.y, a1); a2 = fmaf(d2.x, d2.x, a2); a3 = fmaf(d2.y, d2.y, a3);
           }
         }
-        n2[r] = (a0 + a1) + (a2 + a3);
+        lbuf[r * 128 + tid] = (a0 + a1) + (a2 + a3);
         ptx::mbar_arrive(bar(kNormDone0 + r));
       }
       tr(10);
@@ -711,7 +709,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             float dsel = __uint_as_float(dd[r][0]);
 #pragma unroll
             for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? __uint_as_float(dd[r][c]) : dsel;
-            lbuf[r * 128 + tid] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * n2[r]) : kNegInf;   // log2 units
+            lbuf[r * 128 + tid] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * lbuf[r * 128 + tid]) : kNegInf;   // log2 units
           }
         }
         // the q_bar tile is dead (every phi-logit MMA has completed): clear the P2 tiles that overlay it
@@ -762,16 +760,15 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       ptx::mbar_wait(bar(kBetaFull), ni & 1);
       ptx::tc_fence_after();
       tr(20);
-      {
-        float bt[8 * NR];
-        tmem_ld_cols<8 * NR>(trow + C::cBetaT, reinterpret_cast<uint32_t*>(bt));
+#pragma unroll 1
+      for (int r = 0; r < NR; ++r) {
+        float bt[8];
+        ptx::tmem_ld8(trow + C::cBetaT + 8 * r, reinterpret_cast<uint32_t*>(bt));
         ptx::tmem_ld_wait();
         if (feat_lane) {
 #pragma unroll
-          for (int r = 0; r < NR; ++r)
-#pragma unroll
-            for (int cx = 0; cx < NCX; ++cx)
-              *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * r + cx, feat)) = IoFmt<T>::one(bt[8 * r + cx]);
+          for (int cx = 0; cx < NCX; ++cx)
+            *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * r + cx, feat)) = IoFmt<T>::one(bt[cx]);
         }
       }
       ptx::fence_proxy_async_smem();
