@@ -1,0 +1,447 @@
+// LARA forward core on tcgen05 / TMEM / TMA for sm_100a: replaces lara_stats_kernel + lara_out_kernel (lara.py:201-246) for
+// the DeiT geometry (BASELINE config c4): mis-opt weights, one proposal sample per landmark (S == C <= 64), N <= 224 tokens,
+// head_dim 64, 16-bit I/O, no padding mask.  lara_landmark_kernel still produces q_bar, omega, lp, bh per (batch, head).
+//
+// Per (batch, head) item, everything from one TMA load of q, k, v (N x 128 B each):
+//   phase S (TMEM lane = landmark): with the 128-row tile AW = [omega (rows 0-63) ; q_bar (rows 64-127)]
+//       D1 = AW K^T   rows 0-63:   phi-logits of the keys  -> softmax over the tokens (thread-local) -> P, lse_k
+//       D2 = AW Q^T   rows 64-127: q_bar q^T               -> lse_t (the normaliser of t_nc, lara.py:222-223)
+//       kv = P V      (A operand from TMEM)                -> 16-bit kv tile in shared memory
+//   phase O (TMEM lane = token, two blocks of 128 tokens):
+//       D3 = Q AW^T   columns 0-63: q . omega_c (phi(q)), columns 64-127: q . q_bar_c (t_nc)
+//       per token: t, alpha = bh + coeff (t - mean_c t), log w = log alpha + phi(q) + lse_k - lp, softmax over c (thread-local)
+//       O = W kv      (A operand from TMEM) -> normalise -> staged in the (dead) q tile -> TMA store
+// One persistent CTA per SM: warps 0-3 compute, warp 4 producer (TMA + the fp32 -> 16-bit AW tile), warp 5 MMA issuer;
+// two stages of {q, k, v, AW} so the next item loads under the current one.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "lara_ws.cuh"
+#include "launch.h"
+#include "sm100_ptx.cuh"
+
+namespace eva {
+namespace laracore {
+
+constexpr int kThreads = 192;
+enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullAW0, kFullAW1, kFree0, kFree1,
+           kSFull, kPFull, kKvFull, kKvTile, kD3Full, kP2Full0, kP2Full1, kOFull0, kOFull1, kEpiDone, kNumBars };
+
+struct Params {
+  int B, H, N, NP, C, items;
+  float alpha_coeff;
+  const float* ws;               // lara workspace (float32) written by lara_landmark_kernel
+  int sl;                        // bytes of one q / k / v tile = NP * 128
+};
+
+template <typename T> struct Fmt;
+template <> struct Fmt<__half> {
+  static constexpr uint32_t kUmma = ptx::kFmtF16;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  static __device__ __forceinline__ float2 unpack2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+};
+template <> struct Fmt<__nv_bfloat16> {
+  static constexpr uint32_t kUmma = ptx::kFmtBF16;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  static __device__ __forceinline__ float2 unpack2(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+};
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// TMEM columns
+constexpr uint32_t cD1 = 0, cD2 = 224, cKv = 448;          // phase S: logits [128 x NP] twice, kv [128 x 64]
+constexpr uint32_t cD3 = 0, cO = 256;                      // phase O: per token block rb: D3 at 128 rb, O at 256 + 64 rb
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
+                 const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_o, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int SL = p.sl;
+  uint8_t* const aw0 = sm + 6 * SL;                  // 2 x [128][128 B]: omega rows 0-63, q_bar rows 64-127
+  uint8_t* const kvt = aw0 + 2 * 16384;              // [64][128 B] kv, row = landmark
+  float* const n2k = reinterpret_cast<float*>(kvt + 8192);     // [256] |k_n|^2
+  float* const n2q = n2k + 256;                                 // [256] |q_n|^2
+  float* const lpS = n2q + 256;                                 // [2][64] lp  (per stage, from the workspace)
+  float* const bhS = lpS + 128;                                 // [2][64] bh
+  float* const cst2 = bhS + 128;                                // [64] (lse_k - lp) log2(e)
+  float* const lse2t = cst2 + 64;                               // [64] lse of the t logits, log2 units
+  const uint32_t bars = ptx::smem_u32(reinterpret_cast<uint8_t*>(lse2t + 64));
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(lse2t + 64) + kNumBars * 8);
+  auto bar = [&](int i) { return bars + 8u * i; };
+  auto tile = [&](int s, int which) { return sm + (3 * s + which) * SL; };    // which: 0 q, 1 k, 2 v
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, NP = p.NP, C = p.C;
+
+  for (int i = tid; i < (2 * 16384 + 8192) / 16; i += kThreads) reinterpret_cast<uint4*>(aw0)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(bar(kFullQK0 + s), 1);
+      ptx::mbar_init(bar(kFullV0 + s), 1);
+      ptx::mbar_init(bar(kFullAW0 + s), 1);
+      ptx::mbar_init(bar(kFree0 + s), 3);            // MMA commit + one output-store drain per token block
+      ptx::mbar_init(bar(kP2Full0 + s), 128);
+      ptx::mbar_init(bar(kOFull0 + s), 1);
+    }
+    ptx::mbar_init(bar(kSFull), 1);
+    ptx::mbar_init(bar(kPFull), 128);
+    ptx::mbar_init(bar(kKvFull), 1);
+    ptx::mbar_init(bar(kKvTile), 128);
+    ptx::mbar_init(bar(kD3Full), 1);
+    ptx::mbar_init(bar(kEpiDone), 128);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
+  }
+  if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const float scale_log2 = 0.125f * kLog2e;
+
+  if (warp == 4) {
+    // =================================== producer ==============================================
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int h = item % p.H, b = item / p.H;
+      if (it >= 2) ptx::mbar_wait(bar(kFree0 + s), ((it >> 1) - 1) & 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bar(kFullQK0 + s), 2 * SL);
+        ptx::tma_load_4d(ptx::smem_u32(tile(s, 0)), &t_q, bar(kFullQK0 + s), 0, h, 0, b);
+        ptx::tma_load_4d(ptx::smem_u32(tile(s, 1)), &t_k, bar(kFullQK0 + s), 0, h, 0, b);
+        ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
+        ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
+      }
+      const LaraWs w = lara_ws_at(const_cast<float*>(p.ws), item, C, C, 64);
+      uint8_t* aw = aw0 + s * 16384;
+      for (int idx = lane; idx < C * 8; idx += 32) {
+        const int row = idx >> 3, ch = idx & 7;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(w.omega + row * 64 + ch * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(w.omega + row * 64 + ch * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.qbar + row * 64 + ch * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(w.qbar + row * 64 + ch * 8) + 1);
+        const int off = row * 128 + ((ch ^ (row & 7)) << 4);       // row and row + 64 share (row & 7)
+        *reinterpret_cast<uint4*>(aw + off) = make_uint4(Fmt<T>::pack2(a0.x, a0.y), Fmt<T>::pack2(a0.z, a0.w), Fmt<T>::pack2(a1.x, a1.y), Fmt<T>::pack2(a1.z, a1.w));
+        *reinterpret_cast<uint4*>(aw + 8192 + off) = make_uint4(Fmt<T>::pack2(b0.x, b0.y), Fmt<T>::pack2(b0.z, b0.w), Fmt<T>::pack2(b1.x, b1.y), Fmt<T>::pack2(b1.z, b1.w));
+      }
+      for (int c = lane; c < C; c += 32) { lpS[s * 64 + c] = __ldg(w.lp + c); bhS[s * 64 + c] = __ldg(w.bh + c); }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(bar(kFullAW0 + s));
+    }
+  } else if (warp == 5) {
+    // =================================== MMA issuer ============================================
+    constexpr uint32_t fmt = Fmt<T>::kUmma;
+    const uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 128, (uint32_t)NP);
+    constexpr uint32_t id_d3 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 128);
+    constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+    const uint64_t dKV = ptx::umma_desc_sw128(ptx::smem_u32(kvt));
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1, pi = it & 1;
+      const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 0))), dK = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 1)));
+      const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 2))), dAW = ptx::umma_desc_sw128(ptx::smem_u32(aw0 + s * 16384));
+      ptx::mbar_wait(bar(kFullQK0 + s), ph);
+      ptx::mbar_wait(bar(kFullAW0 + s), ph);
+      if (it > 0) ptx::mbar_wait(bar(kEpiDone), (it - 1) & 1);      // the previous item's TMEM has been read
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD1, dAW + 2 * ks, dK + 2 * ks, id_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2, dAW + 2 * ks, dQ + 2 * ks, id_s, ks > 0);
+        ptx::umma_commit(bar(kSFull));
+      }
+      ptx::mbar_wait(bar(kPFull), pi);
+      ptx::mbar_wait(bar(kFullV0 + s), ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll 1
+        for (int ks = 0; ks < NP / 16; ++ks) ptx::umma_ts(tmem + cKv, tmem + cD1 + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+        ptx::umma_commit(bar(kKvFull));
+      }
+      ptx::mbar_wait(bar(kKvTile), pi);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll 1
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_ss(tmem + cD3 + 128 * rb, dQ + (uint64_t)(rb * (16384 >> 4)) + 2 * ks, dAW + 2 * ks, id_d3, ks > 0);
+        ptx::umma_commit(bar(kD3Full));
+      }
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        ptx::mbar_wait(bar(kP2Full0 + rb), pi);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cO + 64 * rb, tmem + cD3 + 128 * rb + 8 * ks, dKV + 128 * ks, id_pv, ks > 0);
+          ptx::umma_commit(bar(kOFull0 + rb));
+          if (rb == 1) ptx::umma_commit(bar(kFree0 + s));
+        }
+      }
+    }
+  } else {
+    // =================================== compute warps =========================================
+    const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+    const bool d1_side = tid < 64;                     // warps 0-1: omega rows (D1); warps 2-3: q_bar rows (D2)
+    const int c_row = tid & 63;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1, pi = it & 1;
+      const int h = item % p.H, b = item / p.H;
+      // |k_n|^2 and |q_n|^2 from the tiles
+      ptx::mbar_wait(bar(kFullQK0 + s), ph);
+      for (int n = tid; n < NP; n += 128) {
+        float aq = 0.f, ak = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const int off = n * 128 + ((ch ^ (n & 7)) << 4);
+          const uint4 rq = *reinterpret_cast<const uint4*>(tile(s, 0) + off), rk = *reinterpret_cast<const uint4*>(tile(s, 1) + off);
+          const uint32_t wq[4] = {rq.x, rq.y, rq.z, rq.w}, wk[4] = {rk.x, rk.y, rk.z, rk.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fq = Fmt<T>::unpack2(wq[j]), fk = Fmt<T>::unpack2(wk[j]);
+            aq = fmaf(fq.x, fq.x, aq); aq = fmaf(fq.y, fq.y, aq);
+            ak = fmaf(fk.x, fk.x, ak); ak = fmaf(fk.y, fk.y, ak);
+          }
+        }
+        n2q[n] = aq; n2k[n] = ak;
+      }
+      ptx::named_bar_sync(1, 128);
+      // ---- phase S: softmax over the tokens, thread = landmark row ----
+      ptx::mbar_wait(bar(kSFull), pi);
+      ptx::mbar_wait(bar(kFullAW0 + s), ph);          // lp / bh of this stage (written by the producer warp) are visible
+      ptx::tc_fence_after();
+      const uint32_t cS = d1_side ? cD1 : cD2;
+      float m0 = kNegInf;
+#pragma unroll 1
+      for (int g = 0; g < NP / 16; ++g) {
+        float v[16];
+        ptx::tmem_ld16(trow + cS + 16 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int n = 16 * g + e;
+          const float x = d1_side ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
+          m0 = fmaxf(m0, n < N ? x : kNegInf);
+        }
+      }
+      float sum = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < NP / 16; ++g) {
+        float v[16];
+        uint32_t pk[8];
+        ptx::tmem_ld16(trow + cS + 16 * g, reinterpret_cast<uint32_t*>(v));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const int n = 16 * g + e;
+          const float x0 = d1_side ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
+          const float x1 = d1_side ? scale_log2 * (v[e + 1] - 0.5f * n2k[n + 1]) : scale_log2 * v[e + 1];
+          const float a = n < N ? ex2(x0 - m0) : 0.f, c2 = n + 1 < N ? ex2(x1 - m0) : 0.f;
+          sum += a + c2;
+          pk[e >> 1] = Fmt<T>::pack2(a, c2);
+        }
+        if (d1_side) ptx::tmem_st8(trow + cD1 + 8 * g, pk);          // P over the first half of the D1 columns already read
+      }
+      const float lse2 = m0 + lg2(sum);                              // log2 units
+      if (d1_side) cst2[c_row] = lse2 - lpS[s * 64 + c_row] * kLog2e; else lse2t[c_row] = lse2;
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kPFull));
+      // ---- kv rows -> 16-bit tile ----
+      ptx::mbar_wait(bar(kKvFull), pi);
+      ptx::tc_fence_after();
+      if (d1_side) {
+        float o[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cKv + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
+        ptx::tmem_ld_wait();
+        if (c_row < C) {
+          const float inv = 1.0f / sum;
+          uint8_t* row = kvt + c_row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(row + ((ch ^ (c_row & 7)) << 4)) =
+                make_uint4(Fmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), Fmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                           Fmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Fmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kKvTile));                                 // also publishes cst2 / lse2t to the other warps (acq / rel)
+      // ---- phase O: thread = token ----
+      ptx::mbar_wait(bar(kD3Full), pi);
+      ptx::tc_fence_after();
+      ptx::named_bar_sync(1, 128);                                    // cst2 / lse2t written by all rows
+#pragma unroll 1
+      for (int rb = 0; rb < 2; ++rb) {
+        const int n = 128 * rb + tid;
+        const uint32_t cB = cD3 + 128 * rb;
+        float a[64], t[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cB + 16 * g, reinterpret_cast<uint32_t*>(a) + 16 * g);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cB + 64 + 16 * g, reinterpret_cast<uint32_t*>(t) + 16 * g);
+        ptx::tmem_ld_wait();
+        const float hq = 0.5f * n2q[n < NP ? n : 0];
+        float tsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          t[c] = ex2(fmaf(t[c], scale_log2, -lse2t[c]));               // t_nc = softmax_n(scale q_bar_c . q_n)
+          tsum += c < C ? t[c] : 0.f;
+        }
+        const float mean_t = tsum / (float)C;
+        float mw = kNegInf;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const float alpha = bhS[s * 64 + c] + p.alpha_coeff * (t[c] - mean_t);
+          a[c] = lg2(fmaxf(alpha, 1e-8f)) + scale_log2 * (a[c] - hq) + cst2[c];     // log2 of the importance weight
+          mw = fmaxf(mw, c < C ? a[c] : kNegInf);
+        }
+        float wsum = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float w0 = c < C ? ex2(a[c] - mw) : 0.f, w1 = c + 1 < C ? ex2(a[c + 1] - mw) : 0.f;
+          wsum += w0 + w1;
+          pk[c >> 1] = Fmt<T>::pack2(w0, w1);
+        }
+        ptx::tmem_st16(trow + cB, pk);
+        ptx::tmem_st16(trow + cB + 16, pk + 16);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(kP2Full0 + rb));
+        ptx::mbar_wait(bar(kOFull0 + rb), pi);
+        ptx::tc_fence_after();
+        float o[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cO + 64 * rb + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
+        ptx::tmem_ld_wait();
+        const float inv = 1.0f / wsum;
+        uint8_t* row = tile(s, 0) + n * 128;                           // the q tile is dead: every D3 MMA has completed
+        if (n < NP) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(row + ((ch ^ (n & 7)) << 4)) =
+                make_uint4(Fmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), Fmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                           Fmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Fmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1, 128);
+        if (warp == 0 && ptx::elect_one()) {
+          if (128 * rb < N) {                                          // rows >= N are clipped by the tensor map
+            ptx::tma_store_4d(&t_o, ptx::smem_u32(tile(s, 0)) + rb * 16384, 0, h, 128 * rb, b);
+            ptx::bulk_commit_group();
+            ptx::bulk_wait_read0();
+          }
+          ptx::mbar_arrive(bar(kFree0 + s));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kEpiDone));
+    }
+    if (warp == 0 && ptx::elect_one()) ptx::bulk_wait_all();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 5) ptx::tmem_dealloc(tmem, 512);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long long sn, long long sh, const LaraGeo& g, int io_dtype, int rows) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)g.H, (cuuint64_t)g.N, (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, io_dtype == EVA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T>
+static cudaError_t launch_t(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const float* ws, void* out,
+                            cudaStream_t st) {
+  const int NP = (g.N + 15) & ~15;
+  CUtensorMap tq, tk, tv, to;
+  if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, NP) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, NP) ||
+      !make_seq_map(&tv, v.ptr, v.sb, v.sn, v.sh, g, io_dtype, NP) ||
+      !make_seq_map(&to, out, (long long)g.N * g.H * 64, (long long)g.H * 64, 64, g, io_dtype, 128))
+    return cudaErrorInvalidValue;
+  Params p{};
+  p.B = g.B; p.H = g.H; p.N = g.N; p.NP = NP; p.C = g.C; p.items = g.B * g.H;
+  p.alpha_coeff = g.alpha_coeff; p.ws = ws; p.sl = NP * 128;
+  const int dyn = 6 * p.sl + 2 * 16384 + 8192 + (2 * 256 + 2 * 128 + 2 * 64) * 4 + kNumBars * 8 + 16 + 1024;
+  auto kern = lara_core_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.items < sms ? p.items : sms;
+  kern<<<grid, kThreads, dyn, st>>>(tq, tk, tv, to, p);
+  return cudaGetLastError();
+}
+
+}  // namespace laracore
+
+bool lara_core_supported(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (disabled) return false;
+  if (g.D != 64 || g.mis_type != LARA_MIS_OPT || g.sample_mode != LARA_SAMPLE_SINGLE || g.S != g.C || g.C > 64 || mask) return false;
+  if (g.N > 224 || g.N < 16) return false;
+  if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
+  for (const View* x : {&q, &k, &v}) {
+    if (x->sh * 2 % 16 || x->sn * 2 % 16 || x->sb * 2 % 16) return false;
+    if (x->sh <= 0 || x->sn <= 0 || x->sb <= 0) return false;
+    if (reinterpret_cast<uintptr_t>(x->ptr) % 16) return false;
+  }
+  return laracore::get_encode() != nullptr;
+}
+
+static int g_core_launches = 0;
+// diagnostic (not part of the public ABI): how many times the tcgen05 core has been launched by this process
+extern "C" int eva_debug_lara_core_launches(void) { return g_core_launches; }
+
+cudaError_t launch_lara_core(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const float* ws, void* out,
+                             cudaStream_t st) {
+  ++g_core_launches;
+  if (io_dtype == EVA_F16) return laracore::launch_t<__half>(g, io_dtype, q, k, v, ws, out, st);
+  return laracore::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, ws, out, st);
+}
+
+}  // namespace eva

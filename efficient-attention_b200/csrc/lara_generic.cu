@@ -8,31 +8,14 @@
 //   qbar[C,D] mu[C,D] omega[S,D] kv[S,D] lp[S] bh[S] lse_k[S] lse_t[C]
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.h"
 
+#include "lara_ws.cuh"
+
 namespace eva {
-
-struct LaraWs {
-  float *qbar, *mu, *omega, *kv, *lp, *bh, *lse_k, *lse_t;
-};
-
-__host__ __device__ inline size_t lara_ws_floats_per_bh(int C, int S, int D) {
-  return (size_t)(2 * C + 2 * S) * D + 3 * (size_t)S + C;
-}
-__host__ __device__ inline LaraWs lara_ws_at(float* base, long long bh, int C, int S, int D) {
-  float* p = base + bh * (long long)lara_ws_floats_per_bh(C, S, D);
-  LaraWs w;
-  w.qbar = p; p += (size_t)C * D;
-  w.mu = p; p += (size_t)C * D;
-  w.omega = p; p += (size_t)S * D;
-  w.kv = p; p += (size_t)S * D;
-  w.lp = p; p += S;
-  w.bh = p; p += S;
-  w.lse_k = p; p += S;
-  w.lse_t = p;
-  return w;
-}
 
 __device__ __forceinline__ void bin_of(int i, int n_in, int n_out, int& lo, int& hi) {
   // AdaptiveAvgPool bins: [floor(i*n_in/n_out), ceil((i+1)*n_in/n_out))
@@ -71,6 +54,89 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
   const LaraWs ws = lara_ws_at(ws_base, blockIdx.x, C, S, D);
   const bool has_proj = proj.w_q != nullptr;
 
+  bool coop = false;
+  if constexpr (D == 64) coop = g.dims == 2 && !g.per_token_proj;
+  if constexpr (D == 64) if (coop) {
+    // Cooperative path for the pooled 2-D proposals (DeiT): the warp-per-landmark loop below serialises global-load latency
+    // (4 dependent-looking token loads per landmark) and a 64-shuffle Linear per landmark.
+    //   1. pooling: one work item per (side, landmark, 8 features), all threads, 16-byte loads
+    //   2. Linear:  thread = (output feature, row group); its weight row lives in registers, the means are broadcast reads
+    //   3. LayerNorm: one warp per row, in place
+    // [3][C][D] means (16-byte aligned for float4 reads); kb2 | om | Wt | rowbuf are dead until the mixing step
+    float* xm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(kb2) + 15) & ~(uintptr_t)15);
+    const int n_sides = g.mixed == 2 ? 3 : 2;
+    for (int idx = tid; idx < n_sides * C * (D / 8); idx += blockDim.x) {
+      const int part = idx % (D / 8), c = (idx / (D / 8)) % C, side = idx / (C * (D / 8));
+      const View& src = side == 0 ? q : (side == 1 ? k : v);
+      int y0, y1, x0, x1;
+      bin_of(c / g.side, g.gh, g.side, y0, y1);
+      bin_of(c % g.side, g.gw, g.side, x0, x1);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+          const int tok = y * g.gw + x;
+          if (g.zero_padded && mask && mask[(long long)b * g.N + tok]) continue;
+          float f[8];
+          load8<T>(src.row<T>(b, tok, h) + part * 8, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+      const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xm[(side * C + c) * D + part * 8 + i] = acc[i] * inv;
+    }
+    __syncthreads();
+    if (g.mixed == 2)
+      for (int idx = tid; idx < C * D; idx += blockDim.x) vb[(idx / D) * DP + idx % D] = xm[2 * C * D + idx];
+    for (int side = 0; side < 2; ++side) {
+      float* dst = side == 0 ? qb : kb;
+      const float* xs = xm + side * C * D;
+      if (has_proj) {
+        const int o = tid & (D - 1), grp = tid / D, n_grp = blockDim.x / D;
+        const float* W = (side == 0 ? proj.w_q : proj.w_k) + o * D;
+        const float* bias = side == 0 ? proj.b_q : proj.b_k;
+        float wrow[D];
+#pragma unroll
+        for (int i4 = 0; i4 < D / 4; ++i4) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(W) + i4);
+          wrow[4 * i4] = w4.x; wrow[4 * i4 + 1] = w4.y; wrow[4 * i4 + 2] = w4.z; wrow[4 * i4 + 3] = w4.w;
+        }
+        const float b0 = bias ? __ldg(bias + o) : 0.f;
+        for (int c = grp; c < C; c += n_grp) {
+          const float4* xr = reinterpret_cast<const float4*>(xs + c * D);
+          float a0 = b0, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int i4 = 0; i4 < D / 4; ++i4) {
+            const float4 x4 = xr[i4];
+            a0 = fmaf(wrow[4 * i4], x4.x, a0); a1 = fmaf(wrow[4 * i4 + 1], x4.y, a1);
+            a2 = fmaf(wrow[4 * i4 + 2], x4.z, a2); a3 = fmaf(wrow[4 * i4 + 3], x4.w, a3);
+          }
+          dst[c * DP + o] = (a0 + a1) + (a2 + a3);
+        }
+      } else {
+        for (int idx = tid; idx < C * D; idx += blockDim.x) dst[(idx / D) * DP + idx % D] = xs[idx];
+      }
+    }
+    __syncthreads();
+    if (has_proj) {
+      for (int r = warp; r < 2 * C; r += 8) {
+        const int side = r / C, c = r % C;
+        const float* gain = side == 0 ? proj.ln_gain_q : proj.ln_gain_k;
+        if (!gain) continue;
+        const float* lb = side == 0 ? proj.ln_bias_q : proj.ln_bias_k;
+        float* row = (side == 0 ? qb : kb) + c * DP;
+        const float y0v = row[lane], y1v = row[lane + 32];
+        const float mean = warp_sum(y0v + y1v) * (1.0f / D);
+        const float d0 = y0v - mean, d1 = y1v - mean;
+        const float inv = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + proj.ln_eps);
+        row[lane] = d0 * inv * __ldg(gain + lane) + __ldg(lb + lane);
+        row[lane + 32] = d1 * inv * __ldg(gain + lane + 32) + __ldg(lb + lane + 32);
+      }
+    }
+  }
+  if (!coop)
   for (int side = 0; side < 3; ++side) {  // 0: q, 1: k, 2: v (only for '-vmixed')
     if (side == 2 && g.mixed != 2) break;
     const bool per_tok = g.per_token_proj && side < 2;
@@ -487,6 +553,10 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
     kern<<<g.B * g.H, 256, sm1, st>>>(g, q, k, v, mask, proj, noise, ws);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if constexpr (D == 64 && !std::is_same<T, float>::value) {
+    constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
+    if (lara_core_supported(g, io, q, k, v, mask)) return launch_lara_core(g, io, q, k, v, ws, out, st);
   }
   {
     auto kern = lara_stats_kernel<T, D>;

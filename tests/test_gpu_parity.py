@@ -374,3 +374,53 @@ def test_causal_tcgen05_many_windows_per_cta_fp16():
     per_item = ((out.float() - ref).view(B, N // 256, 256, H, d).pow(2).sum((2, 4)).sqrt() /
                 ref.view(B, N // 256, 256, H, d).pow(2).sum((2, 4)).sqrt())
     assert float(per_item.max()) < TOL_F16, float(per_item.max())
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float16, 2e-3), (torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize('proposal', ['pool-mixed', 'pool'])
+def test_c4_lara_tcgen05_core_16bit(proposal, dtype, tol):
+    """BASELINE config c4 through the tcgen05 LARA core (mis-opt, one sample per landmark, 16-bit I/O) against the oracle
+    evaluated in float64 on the same 16-bit weights and inputs (module level: the qkv / proj GEMMs round too, hence the
+    looser tolerance).  The library's launch counter proves the tcgen05 core ran, not the CUDA-core kernels."""
+    import ctypes
+    import efficient_attention as ea
+    from efficient_attention import _abi
+    torch.manual_seed(14)
+    m = ea.AttentionFactory.build_attention('lara', dict(dim=384, num_heads=6, num_landmarks=49,
+                                                         proposal_gen=proposal, mis_type='mis-opt')).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 1.0 / math.sqrt(p.shape[1]))
+    m = m.to(dtype)
+    x = torch.randn(6, 14, 14, 384).to(dtype)
+    cfg = dict(num_heads=6, num_landmarks=49, proposal_gen=proposal, mis_type='mis-opt', alpha_coeff=1.0)
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    want = O.lara_forward(sd, cfg, x.double())
+    lib = _abi.load()
+    lib.eva_debug_lara_core_launches.restype = ctypes.c_int
+    before = lib.eva_debug_lara_core_launches()
+    with torch.no_grad():
+        got = m.to(_dev())(x.to(_dev()))
+    assert lib.eva_debug_lara_core_launches() == before + 1
+    assert not torch.isnan(got).any()
+    err = rel_l2(got.cpu(), want)
+    assert err < tol, (proposal, dtype, err)
+
+
+def test_lara_tcgen05_core_many_items_fp16():
+    """More (batch, head) items than SMs: every CTA loops over several items (both stages reused); checked against the
+    CUDA-core kernels on fp32 copies of the same 16-bit values."""
+    from efficient_attention import _abi
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+    B, H, d, N = 64, 6, 64, 196
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.1).half().to(dev)
+    proj = _abi_ada(_rand_ada(d, g), dev, 1.0)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    kw = dict(seq_shape=(14, 14), landmarks=49, per_token_proj=False, mixed=1, mis_type='mis-opt', sample_mode=0,
+              zero_padded=False, alpha_coeff=1.0, proj=proj)
+    out = _abi.lara_forward(q, k, v, **kw)
+    ref = _abi.lara_forward(q.float(), k.float(), v.float(), **kw)
+    per_item = ((out.float() - ref).view(B, N, H, d).pow(2).sum((1, 3)).sqrt() / ref.view(B, N, H, d).pow(2).sum((1, 3)).sqrt())
+    assert float(per_item.max()) < TOL_F16, float(per_item.max())
