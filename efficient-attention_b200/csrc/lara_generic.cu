@@ -31,6 +31,34 @@ __device__ __forceinline__ void warp_linear_ln(const float* Wt, const EvaAdaptiv
   if (gain) warp_layer_norm<D>(y, gain, q_side ? p.ln_bias_q : p.ln_bias_k, p.ln_eps, lane);
 }
 
+// Ms[r][c] = <X_r, Y_c> for r < R, c < C.  X: rows with stride D+1 in shared memory; Yal: 16-byte aligned [C][D] copy of Y.
+// One work item = (row, block of 10 columns): the row lives in registers, every Y row is a broadcast read -- ~13x fewer
+// shared-memory instructions than one 64-step dot product per lane.
+template <int D>
+__device__ __forceinline__ void dots_rows_cols(const float* __restrict__ X, int R, const float* __restrict__ Yal, int C,
+                                               float* __restrict__ Ms, int tid, int nthreads) {
+  constexpr int DP = D + 1, CB = 10;
+  const int n_cb = (C + CB - 1) / CB;
+  for (int w = tid; w < R * n_cb; w += nthreads) {
+    const int r = w % R, c0 = (w / R) * CB;
+    float x[D];
+#pragma unroll
+    for (int e = 0; e < D; ++e) x[e] = X[r * DP + e];
+    const int c1 = c0 + CB < C ? c0 + CB : C;
+    for (int c = c0; c < c1; ++c) {
+      const float4* y = reinterpret_cast<const float4*>(Yal + c * D);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int i4 = 0; i4 < D / 4; ++i4) {
+        const float4 y4 = y[i4];
+        a0 = fmaf(x[4 * i4], y4.x, a0); a1 = fmaf(x[4 * i4 + 1], y4.y, a1);
+        a2 = fmaf(x[4 * i4 + 2], y4.z, a2); a3 = fmaf(x[4 * i4 + 3], y4.w, a3);
+      }
+      Ms[r * C + c] = (a0 + a1) + (a2 + a3);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // L1: landmarks + proposal statistics.  One CTA per (batch, head).
 // ------------------------------------------------------------------------------------------------
@@ -203,7 +231,48 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
 
   // landmark mixing: k_bar <- softmax(scale k_bar k_bar^T [+ log|v_bar|]) k_bar  (lara.py:157-174)
   float* kfin = kb;
-  if (g.mixed) {
+  bool tiled = false;                                  // register-tiled mixing / proposal statistics (cooperative path only)
+  if constexpr (D == 64) tiled = coop && g.mixed != 2 && S == C;
+  float* const Yal = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Wt) + 15) & ~(uintptr_t)15);   // [C][D], Wt is unused on this path
+  float* const Ms = vb;                                // [C][C] (vb only holds data for '-vmixed')
+  if (g.mixed && tiled) {
+    if constexpr (D == 64) {
+      for (int idx = tid; idx < C * D; idx += blockDim.x) Yal[idx] = kb[(idx / D) * DP + idx % D];
+      __syncthreads();
+      dots_rows_cols<D>(kb, C, Yal, C, Ms, tid, blockDim.x);
+      __syncthreads();
+      for (int pr_ = warp; pr_ < C; pr_ += 8) {          // row softmax, in place
+        float mx = kNegInf;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, Ms[pr_ * C + c] * scale);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) { const float e_ = exp_nonpos(Ms[pr_ * C + c] * scale - mx); Ms[pr_ * C + c] = e_; sum += e_; }
+        const float inv = 1.0f / warp_sum(sum);
+        for (int c = lane; c < C; c += 32) Ms[pr_ * C + c] *= inv;
+      }
+      __syncthreads();
+      for (int w = tid; w < C * (D / 16); w += blockDim.x) {   // k_bar2[p][16 f .. 16 f + 15] = sum_c P[p][c] k_bar[c][..]
+        const int pp = w % C, fb = w / C;
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float pw = Ms[pp * C + c];
+          const float4* y = reinterpret_cast<const float4*>(Yal + c * D + 16 * fb);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 y4 = y[i4];
+            acc[4 * i4] = fmaf(pw, y4.x, acc[4 * i4]); acc[4 * i4 + 1] = fmaf(pw, y4.y, acc[4 * i4 + 1]);
+            acc[4 * i4 + 2] = fmaf(pw, y4.z, acc[4 * i4 + 2]); acc[4 * i4 + 3] = fmaf(pw, y4.w, acc[4 * i4 + 3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) kb2[pp * DP + 16 * fb + i] = acc[i];
+      }
+      kfin = kb2;
+      __syncthreads();
+    }
+  } else if (g.mixed) {
     float* pr = rowbuf + warp * C;
     for (int p = warp; p < C; p += 8) {
       float mx = kNegInf;
@@ -263,6 +332,43 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
 
   // proposal statistics over Lm[s][c] = prm(mu_c, omega_s)   (lara.py:215,228-236)
   const float log_rep = logf((float)(S / C));
+  if (tiled) {
+    if constexpr (D == 64) {
+      for (int idx = tid; idx < C * D; idx += blockDim.x) Yal[idx] = qb[(idx / D) * DP + idx % D];      // mu
+      __syncthreads();
+      for (int c = tid; c < C; c += blockDim.x) {
+        float n2 = 0.f;
+        for (int e = 0; e < D; ++e) n2 = fmaf(Yal[c * D + e], Yal[c * D + e], n2);
+        rowbuf[c] = n2;
+      }
+      dots_rows_cols<D>(om, S, Yal, C, Ms, tid, blockDim.x);
+      __syncthreads();
+      for (int s_ = warp; s_ < S; s_ += 8) {
+        float mx = kNegInf;
+        for (int c = lane; c < C; c += 32) {
+          const float lv = scale * (Ms[s_ * C + c] - 0.5f * rowbuf[c]);
+          Ms[s_ * C + c] = lv;
+          mx = fmaxf(mx, lv);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c < C; c += 32) sum += exp_nonpos(Ms[s_ * C + c] - mx);
+        const float lse = mx + logf(warp_sum(sum));
+        __syncwarp();
+        if (lane == 0) {
+          if (g.mis_type == LARA_MIS_OPT) {
+            const float lp = Ms[s_ * C + s_ % C];
+            ws.lp[s_] = lp;
+            ws.bh[s_] = expf(lp - (lse + log_rep));
+          } else {
+            ws.lp[s_] = lse;
+            ws.bh[s_] = 0.f;
+          }
+        }
+      }
+    }
+    return;
+  }
   float* pr = rowbuf + warp * C;
   for (int s = warp; s < S; s += 8) {
     float mx = kNegInf;
