@@ -29,13 +29,19 @@ namespace laracore {
 
 constexpr int kThreads = 192;
 enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullAW0, kFullAW1, kFree0, kFree1,
-           kSFull, kPFull, kKvFull, kKvTile, kD3Full, kP2Full0, kP2Full1, kOFull0, kOFull1, kEpiDone, kNumBars };
+           kSFull, kPFull, kKvFull, kKvTile, kD3Full, kP2Full0, kP2Full1, kOFull0, kOFull1, kEpiDone,
+           kFullW0, kFullW1, kWFree, kToMma, kToCompute, kNumBars };
 
 struct Params {
   int B, H, N, NP, C, items;
   float alpha_coeff;
   const float* ws;               // lara workspace (float32) written by lara_landmark_kernel
   int sl;                        // bytes of one q / k / v tile = NP * 128
+  // fused landmark phase (phase L): pooled 2-D proposals, Linear + LayerNorm, optional landmark mixing, proposal statistics
+  int fuse, side, gh, gw, mixed, has_proj;
+  const float *b_q, *g_q, *beta_q, *b_k, *g_k, *beta_k;
+  float ln_eps;
+  const float* noise;            // [B, H, C, 64] or NULL
 };
 
 template <typename T> struct Fmt;
@@ -67,26 +73,29 @@ constexpr uint32_t cD3 = 0, cO = 256;                      // phase O: per token
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
-                 const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_o, const Params p) {
+                 const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_o,
+                 const __grid_constant__ CUtensorMap t_w, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int SL = p.sl;
   uint8_t* const aw0 = sm + 6 * SL;                  // 2 x [128][128 B]: omega rows 0-63, q_bar rows 64-127
-  uint8_t* const kvt = aw0 + 2 * 16384;              // [64][128 B] kv, row = landmark
-  float* const n2k = reinterpret_cast<float*>(kvt + 8192);     // [256] |k_n|^2
+  uint8_t* const kvt = aw0 + 2 * 16384;              // [128][128 B]: kv (rows = landmarks; phase L: k_bar, then mu); rows 64-127 stay zero (M = 128 A operand of the mixing MMA)
+  float* const n2k = reinterpret_cast<float*>(kvt + 16384);    // [256] |k_n|^2
   float* const n2q = n2k + 256;                                 // [256] |q_n|^2
   float* const lpS = n2q + 256;                                 // [2][64] lp  (per stage, from the workspace)
   float* const bhS = lpS + 128;                                 // [2][64] bh
   float* const cst2 = bhS + 128;                                // [64] (lse_k - lp) log2(e)
   float* const lse2t = cst2 + 64;                               // [64] lse of the t logits, log2 units
-  const uint32_t bars = ptx::smem_u32(reinterpret_cast<uint8_t*>(lse2t + 64));
-  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(lse2t + 64) + kNumBars * 8);
+  float* const mu2 = lse2t + 64;                                // [64] |mu_c|^2 (phase L)
+  float* const lnp = mu2 + 64;                                  // [6][64] Linear bias, LayerNorm gain / bias: q side | k side
+  const uint32_t bars = ptx::smem_u32(reinterpret_cast<uint8_t*>(lnp + 384));
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(lnp + 384) + kNumBars * 8);
   auto bar = [&](int i) { return bars + 8u * i; };
   auto tile = [&](int s, int which) { return sm + (3 * s + which) * SL; };    // which: 0 q, 1 k, 2 v
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, NP = p.NP, C = p.C;
 
-  for (int i = tid; i < (2 * 16384 + 8192) / 16; i += kThreads) reinterpret_cast<uint4*>(aw0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (3 * 16384) / 16; i += kThreads) reinterpret_cast<uint4*>(aw0)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(bar(kFullQK0 + s), 1);
@@ -102,8 +111,17 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     ptx::mbar_init(bar(kKvTile), 128);
     ptx::mbar_init(bar(kD3Full), 1);
     ptx::mbar_init(bar(kEpiDone), 128);
+    ptx::mbar_init(bar(kFullW0), 1);
+    ptx::mbar_init(bar(kFullW1), 1);
+    ptx::mbar_init(bar(kWFree), 1);
+    ptx::mbar_init(bar(kToMma), 128);
+    ptx::mbar_init(bar(kToCompute), 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
+  }
+  if (p.fuse) {
+    const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
+    for (int idx = tid; idx < 384; idx += kThreads) lnp[idx] = src[idx >> 6] ? __ldg(src[idx >> 6] + (idx & 63)) : 0.f;
   }
   if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
   ptx::fence_proxy_async_smem();
@@ -124,8 +142,21 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         ptx::mbar_arrive_expect_tx(bar(kFullQK0 + s), 2 * SL);
         ptx::tma_load_4d(ptx::smem_u32(tile(s, 0)), &t_q, bar(kFullQK0 + s), 0, h, 0, b);
         ptx::tma_load_4d(ptx::smem_u32(tile(s, 1)), &t_k, bar(kFullQK0 + s), 0, h, 0, b);
-        ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
-        ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
+        if (!p.fuse) {
+          ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
+          ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
+        } else if (p.has_proj) {                     // [W_q ; W_k] borrows the v tile until the Linear MMA has read it
+          ptx::mbar_arrive_expect_tx(bar(kFullW0 + s), 16384);
+          ptx::tma_load_2d(ptx::smem_u32(tile(s, 2)), &t_w, bar(kFullW0 + s), 0, 0);
+        }
+      }
+      if (p.fuse) {
+        if (p.has_proj) ptx::mbar_wait(bar(kWFree), it & 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
+          ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
+        }
+        continue;                                    // the AW tile, lp and bh are produced on chip (phase L)
       }
       const LaraWs w = lara_ws_at(const_cast<float*>(p.ws), item, C, C, 64);
       uint8_t* aw = aw0 + s * 16384;
@@ -150,16 +181,54 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     const uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 128, (uint32_t)NP);
     constexpr uint32_t id_d3 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 128);
     constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+    constexpr uint32_t id_m64 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
     const uint64_t dKV = ptx::umma_desc_sw128(ptx::smem_u32(kvt));
-    uint32_t it = 0;
+    uint32_t it = 0, hand = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1, pi = it & 1;
       const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 0))), dK = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 1)));
       const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 2))), dAW = ptx::umma_desc_sw128(ptx::smem_u32(aw0 + s * 16384));
       ptx::mbar_wait(bar(kFullQK0 + s), ph);
-      ptx::mbar_wait(bar(kFullAW0 + s), ph);
-      if (it > 0) ptx::mbar_wait(bar(kEpiDone), (it - 1) & 1);      // the previous item's TMEM has been read
+      if (!p.fuse) {
+        ptx::mbar_wait(bar(kFullAW0 + s), ph);
+        if (it > 0) ptx::mbar_wait(bar(kEpiDone), (it - 1) & 1);    // the previous item's TMEM has been read
+      } else {
+        // phase L: a strict ping-pong with the compute warps (kToMma: 128 arrivals, kToCompute: one commit per hand-off)
+        const uint64_t dKBm = dKV;                                   // k_bar / mu tile lives in the kv tile until the kv read-back
+        auto wait_compute = [&]() { ptx::mbar_wait(bar(kToMma), hand & 1); ++hand; ptx::tc_fence_after(); };
+        if (p.has_proj) {
+          wait_compute();                                            // means tile written (in the AW tile of this stage)
+          ptx::mbar_wait(bar(kFullW0 + s), ph);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 0, dAW + 2 * ks, dV + 2 * ks, id_d3, ks > 0);
+            ptx::umma_commit(bar(kToCompute));
+            ptx::umma_commit(bar(kWFree));
+          }
+        }
+        if (p.mixed) {
+          wait_compute();                                            // k_bar tile written
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 128, dKBm + 2 * ks, dKBm + 2 * ks, id_m64, ks > 0);
+            ptx::umma_commit(bar(kToCompute));
+          }
+          wait_compute();                                            // mixing weights P written over the logits
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + 192, tmem + 128 + 8 * ks, dKBm + 128 * ks, id_pv, ks > 0);
+            ptx::umma_commit(bar(kToCompute));
+          }
+        }
+        wait_compute();                                              // AW (omega | q_bar) and mu tiles written
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 256, dAW + 2 * ks, dKBm + 2 * ks, id_m64, ks > 0);
+          ptx::umma_commit(bar(kToCompute));
+        }
+        wait_compute();                                              // lp / bh done, phase-L TMEM reads finished
+      }
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll
@@ -203,7 +272,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
     const bool d1_side = tid < 64;                     // warps 0-1: omega rows (D1); warps 2-3: q_bar rows (D2)
     const int c_row = tid & 63;
-    uint32_t it = 0;
+    uint32_t it = 0, hc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1, pi = it & 1;
@@ -227,9 +296,168 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         n2q[n] = aq; n2k[n] = ak;
       }
       ptx::named_bar_sync(1, 128);
+      if (p.fuse) {
+        // ---- phase L: landmarks on chip (lara.py:129-175, 182-198, 221-232) ----
+        uint8_t* const awt = aw0 + s * 16384;           // first the means tile, finally [omega ; q_bar]
+        const int ws_ = tid >> 6, c = tid & 63;         // lanes 0-63: q side, 64-127: k side; c = landmark
+        auto wait_mma = [&]() { ptx::mbar_wait(bar(kToCompute), hc & 1); ++hc; ptx::tc_fence_after(); };
+        auto to_mma = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); ptx::mbar_arrive(bar(kToMma)); };
+        // L1: adaptive average pooling of q and k (AdaptiveAvgPool2d bins), 16-byte pieces -> means tile
+        for (int idx = tid; idx < 2 * C * 8; idx += 128) {
+          const int part = idx & 7, cc = (idx >> 3) % C, sd = idx / (8 * C);
+          const int by = cc / p.side, bx = cc % p.side;
+          const int y0 = (by * p.gh) / p.side, y1 = ((by + 1) * p.gh + p.side - 1) / p.side;
+          const int x0 = (bx * p.gw) / p.side, x1 = ((bx + 1) * p.gw + p.side - 1) / p.side;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) {
+              const int n = y * p.gw + x;
+              const uint4 raw = *reinterpret_cast<const uint4*>(tile(s, sd) + n * 128 + ((part ^ (n & 7)) << 4));
+              const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = Fmt<T>::unpack2(w4[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+            }
+          const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+          const int r = 64 * sd + cc;
+          *reinterpret_cast<uint4*>(awt + r * 128 + ((part ^ (r & 7)) << 4)) =
+              make_uint4(Fmt<T>::pack2(acc[0] * inv, acc[1] * inv), Fmt<T>::pack2(acc[2] * inv, acc[3] * inv),
+                         Fmt<T>::pack2(acc[4] * inv, acc[5] * inv), Fmt<T>::pack2(acc[6] * inv, acc[7] * inv));
+        }
+        to_mma();
+        // L2: Linear (MMA) -> bias, LayerNorm
+        wait_mma();
+        float y[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + (ws_ ? 64u : 0u) + 16 * g, reinterpret_cast<uint32_t*>(y) + 16 * g);
+        ptx::tmem_ld_wait();
+        {
+          const float* lp_ = lnp + (ws_ ? 192 : 0);
+#pragma unroll
+          for (int e = 0; e < 64; ++e) y[e] += lp_[e];
+          if (ws_ ? (p.g_k != nullptr) : (p.g_q != nullptr)) {
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 2) { s0 += y[e]; s1 += y[e + 1]; }
+            const float mean = (s0 + s1) * (1.0f / 64);
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 2) { const float d0 = y[e] - mean, d1 = y[e + 1] - mean; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
+            const float rs = 1.0f / sqrtf((v0 + v1) * (1.0f / 64) + p.ln_eps);
+#pragma unroll
+            for (int e = 0; e < 64; ++e) y[e] = (y[e] - mean) * rs * lp_[64 + e] + lp_[128 + e];
+          }
+        }
+        if (ws_ == 1) {                                  // k_bar rows -> tile (rows >= C zero)
+          uint8_t* row = kvt + c * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(row + ((ch ^ (c & 7)) << 4)) = c < C ?
+                make_uint4(Fmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), Fmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
+                           Fmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), Fmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7])) : make_uint4(0, 0, 0, 0);
+        }
+        float k2[64], lp_exact = 0.f;
+        if (p.mixed) {
+          // L3: k_bar <- softmax(scale k_bar k_bar^T) k_bar (lara.py:157-174); row p on lane p
+          to_mma();
+          wait_mma();
+          if (ws_ == 0) {
+            float v[64];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + 128 + 16 * g, reinterpret_cast<uint32_t*>(v) + 16 * g);
+            ptx::tmem_ld_wait();
+            float mx = kNegInf;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) mx = fmaxf(mx, e < C ? v[e] : kNegInf);
+            float sum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) { v[e] = e < C ? ex2((v[e] - mx) * scale_log2) : 0.f; sum += v[e]; }
+            const float inv = 1.0f / sum;
+            uint32_t pk[32];
+#pragma unroll
+            for (int e = 0; e < 64; e += 2) pk[e >> 1] = Fmt<T>::pack2(v[e] * inv, v[e + 1] * inv);
+            ptx::tmem_st16(trow + 128, pk);
+            ptx::tmem_st16(trow + 144, pk + 16);
+            ptx::tmem_st_wait();
+          }
+          to_mma();
+          wait_mma();
+          if (ws_ == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + 192 + 16 * g, reinterpret_cast<uint32_t*>(k2) + 16 * g);
+            ptx::tmem_ld_wait();
+          }
+        } else {
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, 128);                   // k_bar rows visible to the q-side lanes
+          if (ws_ == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(kvt + c * 128 + ((ch ^ (c & 7)) << 4));
+              const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = Fmt<T>::unpack2(w4[j]); k2[8 * ch + 2 * j] = f.x; k2[8 * ch + 2 * j + 1] = f.y; }
+            }
+          }
+        }
+        // L4: mu = q_bar + k_bar (lara.py:182), omega = mu (+ noise); tiles for the proposal statistics and the later phases
+        if (ws_ == 0) {
+          const bool live = c < C;
+          const float* nz = (p.noise && live) ? p.noise + ((long long)item * C + c) * 64 : nullptr;
+          float m2 = 0.f, dot = 0.f;
+          uint8_t* const r_om = awt + c * 128;
+          uint8_t* const r_qb = awt + (64 + c) * 128;
+          uint8_t* const r_mu = kvt + c * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float mu[8], om[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              mu[j] = live ? y[8 * ch + j] + k2[8 * ch + j] : 0.f;
+              om[j] = mu[j] + (nz ? __ldg(nz + 8 * ch + j) : 0.f);
+              m2 = fmaf(mu[j], mu[j], m2);
+              dot = fmaf(om[j], mu[j], dot);
+            }
+            const int sw = (ch ^ (c & 7)) << 4;
+            *reinterpret_cast<uint4*>(r_om + sw) = make_uint4(Fmt<T>::pack2(om[0], om[1]), Fmt<T>::pack2(om[2], om[3]), Fmt<T>::pack2(om[4], om[5]), Fmt<T>::pack2(om[6], om[7]));
+            *reinterpret_cast<uint4*>(r_mu + sw) = make_uint4(Fmt<T>::pack2(mu[0], mu[1]), Fmt<T>::pack2(mu[2], mu[3]), Fmt<T>::pack2(mu[4], mu[5]), Fmt<T>::pack2(mu[6], mu[7]));
+            *reinterpret_cast<uint4*>(r_qb + sw) = live ?
+                make_uint4(Fmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), Fmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
+                           Fmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), Fmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7])) : make_uint4(0, 0, 0, 0);
+          }
+          mu2[c] = m2;
+          lp_exact = scale_log2 * (dot - 0.5f * m2);   // L[s][s] from the fp32 rows (the MMA below sees 16-bit copies), log2 units
+        }
+        to_mma();
+        // L5: proposal statistics L[s][c] = prm(mu_c, omega_s): lp = L[s][s], bh = exp(lp - lse_c L[s][c]) (mis-opt)
+        wait_mma();
+        ptx::named_bar_sync(1, 128);                     // mu2 of every landmark
+        if (ws_ == 0) {
+          float v[64];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + 256 + 16 * g, reinterpret_cast<uint32_t*>(v) + 16 * g);
+          ptx::tmem_ld_wait();
+          float mx = kNegInf;
+          const float lp = lp_exact;
+#pragma unroll
+          for (int e = 0; e < 64; ++e) {
+            v[e] = scale_log2 * (v[e] - 0.5f * mu2[e]);  // log2 units
+            v[e] = e == c ? lp : v[e];                   // keep the diagonal consistent with lp
+            mx = fmaxf(mx, e < C ? v[e] : kNegInf);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int e = 0; e < 64; ++e) sum += e < C ? ex2(v[e] - mx) : 0.f;
+          const float lse2 = mx + lg2(sum);
+          lpS[s * 64 + c] = lp * (1.0f / kLog2e);        // natural-log units, as the workspace of the landmark kernel
+          bhS[s * 64 + c] = ex2(lp - lse2);
+        }
+        to_mma();
+      }
       // ---- phase S: softmax over the tokens, thread = landmark row ----
       ptx::mbar_wait(bar(kSFull), pi);
-      ptx::mbar_wait(bar(kFullAW0 + s), ph);          // lp / bh of this stage (written by the producer warp) are visible
+      if (!p.fuse) ptx::mbar_wait(bar(kFullAW0 + s), ph);          // lp / bh of this stage (written by the producer warp) are visible
       ptx::tc_fence_after();
       const uint32_t cS = d1_side ? cD1 : cD2;
       float m0 = kNegInf;
@@ -392,9 +620,16 @@ static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long lo
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [W_q ; W_k] (fp32 [64][64] each, row-major [out][in]) -> 16-bit [128][64] for the Linear MMA of phase L
+template <typename T>
+__global__ void pack_proj_weights(const float* __restrict__ wq, const float* __restrict__ wk, T* __restrict__ w16) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 128 * 64) w16[idx] = from_f32<T>((idx < 64 * 64 ? wq : wk)[idx & 4095]);
+}
+
 template <typename T>
 static cudaError_t launch_t(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const float* ws, void* out,
-                            cudaStream_t st) {
+                            const EvaAdaptive* proj, const float* noise, cudaStream_t st) {
   const int NP = (g.N + 15) & ~15;
   CUtensorMap tq, tk, tv, to;
   if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, NP) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, NP) ||
@@ -404,7 +639,25 @@ static cudaError_t launch_t(const LaraGeo& g, int io_dtype, const View& q, const
   Params p{};
   p.B = g.B; p.H = g.H; p.N = g.N; p.NP = NP; p.C = g.C; p.items = g.B * g.H;
   p.alpha_coeff = g.alpha_coeff; p.ws = ws; p.sl = NP * 128;
-  const int dyn = 6 * p.sl + 2 * 16384 + 8192 + (2 * 256 + 2 * 128 + 2 * 64) * 4 + kNumBars * 8 + 16 + 1024;
+  CUtensorMap tw = tq;                       // placeholder when phase L is not fused
+  if (proj) {                                // fused landmark phase: the workspace only holds the packed projection weights
+    p.fuse = 1; p.side = g.side; p.gh = g.gh; p.gw = g.gw; p.mixed = g.mixed; p.has_proj = 1;
+    p.b_q = proj->b_q; p.g_q = proj->ln_gain_q; p.beta_q = proj->ln_bias_q;
+    p.b_k = proj->b_k; p.g_k = proj->ln_gain_k; p.beta_k = proj->ln_bias_k;
+    p.ln_eps = proj->ln_eps; p.noise = noise;
+    T* w16 = reinterpret_cast<T*>(const_cast<float*>(ws));
+    pack_proj_weights<T><<<32, 256, 0, st>>>(proj->w_q, proj->w_k, w16);
+    auto enc = get_encode();
+    const cuuint64_t dims[2] = {64, 128};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (!enc || enc(&tw, io_dtype == EVA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w16, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  const int dyn = 6 * p.sl + 3 * 16384 + (2 * 256 + 2 * 128 + 3 * 64 + 384) * 4 + kNumBars * 8 + 16 + 1024;
   auto kern = lara_core_kernel<T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e != cudaSuccess) return e;
@@ -412,7 +665,7 @@ static cudaError_t launch_t(const LaraGeo& g, int io_dtype, const View& q, const
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.items < sms ? p.items : sms;
-  kern<<<grid, kThreads, dyn, st>>>(tq, tk, tv, to, p);
+  kern<<<grid, kThreads, dyn, st>>>(tq, tk, tv, to, tw, p);
   return cudaGetLastError();
 }
 
@@ -437,11 +690,19 @@ static int g_core_launches = 0;
 // diagnostic (not part of the public ABI): how many times the tcgen05 core has been launched by this process
 extern "C" int eva_debug_lara_core_launches(void) { return g_core_launches; }
 
+// proj != NULL: the landmark phase is fused too (lara_landmark_kernel is not needed); see lara_core_fuses_landmarks
+// pooled 2-D proposals with Linear + LayerNorm ('pool', 'pool-mixed'), at most 208 tokens: phase L runs inside the core kernel
+bool lara_core_fuses_landmarks(const LaraGeo& g, const EvaAdaptive& proj) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("EVA_SM100_LARA_NO_FUSED_LANDMARKS"); off = (e && e[0] == '1') ? 1 : 0; }
+  return !off && g.dims == 2 && !g.per_token_proj && g.mixed <= 1 && proj.w_q && proj.w_k && ((g.N + 15) & ~15) <= 208;
+}
+
 cudaError_t launch_lara_core(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const float* ws, void* out,
-                             cudaStream_t st) {
+                             const EvaAdaptive* proj, const float* noise, cudaStream_t st) {
   ++g_core_launches;
-  if (io_dtype == EVA_F16) return laracore::launch_t<__half>(g, io_dtype, q, k, v, ws, out, st);
-  return laracore::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, ws, out, st);
+  if (io_dtype == EVA_F16) return laracore::launch_t<__half>(g, io_dtype, q, k, v, ws, out, proj, noise, st);
+  return laracore::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, ws, out, proj, noise, st);
 }
 
 }  // namespace eva

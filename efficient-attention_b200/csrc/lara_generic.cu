@@ -654,6 +654,11 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
   const size_t sm1 = landmark_smem(g), sm3 = out_smem(g);
   if (sm1 > 227 * 1024 || sm3 > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e;
+  if constexpr (D == 64 && !std::is_same<T, float>::value) {
+    constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
+    if (lara_core_supported(g, io, q, k, v, mask) && lara_core_fuses_landmarks(g, proj))
+      return launch_lara_core(g, io, q, k, v, ws, out, &proj, noise, st);      // landmarks, statistics and output in one kernel
+  }
   {
     auto kern = lara_landmark_kernel<T, D>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
@@ -662,7 +667,7 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
   }
   if constexpr (D == 64 && !std::is_same<T, float>::value) {
     constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
-    if (lara_core_supported(g, io, q, k, v, mask)) return launch_lara_core(g, io, q, k, v, ws, out, st);
+    if (lara_core_supported(g, io, q, k, v, mask)) return launch_lara_core(g, io, q, k, v, ws, out, nullptr, nullptr, st);
   }
   {
     auto kern = lara_stats_kernel<T, D>;

@@ -42,8 +42,9 @@ struct LaraGeo {
 size_t lara_workspace_bytes(const LaraGeo& g);
 // tcgen05 core (lara_core_sm100.cu): replaces the stats + out kernels for the DeiT geometry (mis-opt, S == C <= 64, N <= 224)
 bool lara_core_supported(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask);
+bool lara_core_fuses_landmarks(const LaraGeo& g, const EvaAdaptive& proj);
 cudaError_t launch_lara_core(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v, const float* ws, void* out,
-                             cudaStream_t st);
+                             const EvaAdaptive* proj, const float* noise, cudaStream_t st);
 cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
                         const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
                         void* workspace, cudaStream_t st);

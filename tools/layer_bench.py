@@ -75,7 +75,7 @@ with torch.no_grad(), warnings.catch_warnings():
         dim=384, num_heads=6, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, num_landmarks=49, proposal_gen='pool-mixed',
         use_antithetics=False, use_multisample=False, pool_module_type='light', mis_type='mis-opt', alpha_coeff=1.0))).to(dev).half().eval()
     x = torch.randn(512, 14, 14, 384, device=dev, dtype=torch.float16)
-    report('c4 LARA N=196 C=384 B=512 (generic CUDA-core kernels)', 512 * 196, 384, timed(lambda: m(x), max(3, args.iters // 4)))
+    report('c4 LARA N=196 C=384 B=512 (fused tcgen05 LARA kernel)', 512 * 196, 384, timed(lambda: m(x), max(3, args.iters // 4)))
     del m, x
     # c5: causal EVA LM layer, T = 4096, C = 512, 8 heads, chunk 256, window 256
     ns = argparse.Namespace(adaptive_proj='qk', num_chunks=None, chunk_size=256, causal=True, use_t5_rpe=False, window_size=256,
