@@ -377,8 +377,8 @@ def test_causal_tcgen05_many_windows_per_cta_fp16():
 
 
 @pytest.mark.parametrize('dtype,tol', [(torch.float16, 2e-3), (torch.bfloat16, 1.5e-2)])
-@pytest.mark.parametrize('proposal', ['pool-mixed', 'pool'])
-def test_c4_lara_tcgen05_core_16bit(proposal, dtype, tol):
+@pytest.mark.parametrize('proposal,with_noise', [('pool-mixed', False), ('pool', False), ('pool-mixed', True)])
+def test_c4_lara_tcgen05_core_16bit(proposal, with_noise, dtype, tol):
     """BASELINE config c4 through the tcgen05 LARA core (mis-opt, one sample per landmark, 16-bit I/O) against the oracle
     evaluated in float64 on the same 16-bit weights and inputs (module level: the qkv / proj GEMMs round too, hence the
     looser tolerance).  The library's launch counter proves the tcgen05 core ran, not the CUDA-core kernels."""
@@ -396,12 +396,13 @@ def test_c4_lara_tcgen05_core_16bit(proposal, dtype, tol):
     x = torch.randn(6, 14, 14, 384).to(dtype)
     cfg = dict(num_heads=6, num_landmarks=49, proposal_gen=proposal, mis_type='mis-opt', alpha_coeff=1.0)
     sd = {k: v.detach().double() for k, v in m.state_dict().items()}
-    want = O.lara_forward(sd, cfg, x.double())
+    noise = torch.randn(6, 6, 49, 64) if with_noise else None      # training-mode draw of lara.py:197-198 (one sample per landmark)
+    want = O.lara_forward(sd, cfg, x.double(), noise=noise.double() if with_noise else None)
     lib = _abi.load()
     lib.eva_debug_lara_core_launches.restype = ctypes.c_int
     before = lib.eva_debug_lara_core_launches()
     with torch.no_grad():
-        got = m.to(_dev())(x.to(_dev()))
+        got = m.to(_dev())(x.to(_dev()), noise=noise.to(_dev()) if with_noise else None)
     assert lib.eva_debug_lara_core_launches() == before + 1
     assert not torch.isnan(got).any()
     err = rel_l2(got.cpu(), want)
