@@ -14,10 +14,17 @@ class HostPipeline:
     chunk:  images per stage; depth: device-side buffers per stage (2 = double buffering).
     """
 
-    def __init__(self, module, chunk, depth=2):
+    def __init__(self, module, chunk, depth=2, use_graphs=False):
         self.module = module
         self.chunk = int(chunk)
         self.depth = int(depth)
+        # optional: one CUDA graph per buffer slot replays the module forward (a dozen launches + their host-side set-up) in one
+        # call.  Measured on B200 (tools/e2e_sweep.py): no gain -- at 8-16 stages the copies, not the host thread, bound the
+        # pipeline (7.4 ms per step against a 6.4 ms duplex-copy bound) -- so it is off by default.
+        self.use_graphs = bool(use_graphs)
+        self._graphs = [None] * self.depth
+        self._y = [None] * self.depth
+        self._ev_y_free = [None] * self.depth
         p = next(module.parameters())
         self.device = p.device
         self.s_in = torch.cuda.Stream(self.device)
@@ -47,12 +54,32 @@ class HostPipeline:
                 xd.copy_(x_host[lo:hi], non_blocking=True)
                 self._ev_in[s].record(self.s_in)
             main.wait_event(self._ev_in[s])
-            y = self.module(xd)
+            if self.use_graphs and hi - lo == self.chunk:
+                if self._ev_y_free[s] is not None:
+                    main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
+                y = self._replay(s, xd)
+            else:
+                y = self.module(xd)
             self._ev_comp[s].record(main)
             self._ev_x_free[s] = self._ev_comp[s]
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self._ev_comp[s])
                 y.record_stream(self.s_out)
                 y_host[lo:hi].copy_(y, non_blocking=True)
+                if self.use_graphs and hi - lo == self.chunk:
+                    self._ev_y_free[s] = torch.cuda.Event()
+                    self._ev_y_free[s].record(self.s_out)
         main.wait_stream(self.s_out)
         return y_host
+
+    def _replay(self, s, xd):
+        """Forward of slot s through its CUDA graph (captured on first use; x / y buffers of a slot are static)."""
+        if self._graphs[s] is None or self._graphs[s][1] != xd.data_ptr():
+            self.module(xd)                                          # warm-up outside capture (lazy initialisation, allocator)
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._y[s] = self.module(xd)
+            self._graphs[s] = (g, xd.data_ptr())
+        self._graphs[s][0].replay()
+        return self._y[s]

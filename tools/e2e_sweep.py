@@ -22,11 +22,15 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5): duplex()
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print(f'raw duplex copy of one step: {dt * 1e3:.2f} ms  ({x_host.numel() * 2 / dt / 1e9:.1f} GB/s each way)  -> bound {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
-for n_chunks in (4, 8, 16, 32):
-    for depth in (2, 3):
-        pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth)
+for n_chunks, depth, graphs in ((8, 2, False), (8, 2, True), (16, 2, True), (16, 3, True), (32, 2, True), (32, 3, True), (64, 3, True)):
+    if True:
+        pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth, use_graphs=graphs)
         for _ in range(3): pipe(x_host, y_host)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for _ in range(8): pipe(x_host, y_host)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 8
-        print(f'chunks {n_chunks:2d} depth {depth}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
+        y1 = y_host.clone()
+        HostPipeline(layer, chunk=B // 8, use_graphs=False)(x_host, y_host)
+        torch.cuda.synchronize()
+        same = bool((y1 == y_host).all())
+        print(f'chunks {n_chunks:2d} depth {depth} graphs {graphs}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s  identical to eager: {same}', flush=True)
