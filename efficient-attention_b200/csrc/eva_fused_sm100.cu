@@ -316,7 +316,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       for (; item < p.items; ++ni, nb += n_per_item) {
         const int b = item / p.H, h = item % p.H;
         int item_next = 0;                               // fetched now, needed in phase B: the atomic's latency hides under pass 1
-        if (lane == 0) item_next = (int)atomicAdd(p.next_item, 1u);
+        if (ni > 0 && lane == 0) item_next = (int)atomicAdd(p.next_item, 1u);
 #pragma unroll 1
         for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM) ...
           uint32_t s = acquire(nb + 2 * r, TOK * 128);
@@ -325,6 +325,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
             s = acquire(nb + 2 * r + 1, TOK * 128);
             if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
           }
+        }
+        if (ni == 0) {
+          // programmatic dependent launch: this grid may start while pack_params (weight tile, bias slabs, work counter)
+          // is still running; everything it produced is first touched below, by this warp only
+          asm volatile("griddepcontrol.wait;" ::: "memory");
+          if (lane == 0) item_next = (int)atomicAdd(p.next_item, 1u);
         }
         if (p.bias2) {                                   // this head's bias table, once the previous item's softmax is done
           ptx::mbar_wait(bar(kBiasFree), (ni & 1) ^ 1);
@@ -939,6 +945,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 __global__ void pack_params(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ w16,
                             const float* __restrict__ bias, long long bias_sh, float* __restrict__ bias2, int H, int L,
                             int LS, int slab_floats, unsigned int* next_item, unsigned int first_free_item) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fused kernel may begin its prologue and first loads now
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) *next_item = first_free_item;          // items 0 .. grid-1 are taken by blockIdx, the rest are handed out dynamically
   if (idx < 128 * 64) {
@@ -1066,7 +1073,14 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, true> : eva_fused_kernel<T, W, GW, CH, NR, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
-  kern<<<grid, kThreads, C::kDynamic, st>>>(twq, twk, twv, trq, trk, trv, tw, to, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kDynamic; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;           // overlap with pack_params (see griddepcontrol.wait in the TMA warp)
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, twq, twk, twv, trq, trk, trv, tw, to, p);
+  if (e != cudaSuccess) { *msg = "kernel launch"; return e; }
   *msg = "kernel launch";
   return cudaGetLastError();
 }
