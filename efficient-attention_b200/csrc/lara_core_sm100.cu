@@ -11,8 +11,9 @@
 //       D3 = Q AW^T   columns 0-63: q . omega_c (phi(q)), columns 64-127: q . q_bar_c (t_nc)
 //       per token: t, alpha = bh + coeff (t - mean_c t), log w = log alpha + phi(q) + lse_k - lp, softmax over c (thread-local)
 //       O = W kv      (A operand from TMEM) -> normalise -> staged in the (dead) q tile -> TMA store
-// One persistent CTA per SM: warps 0-3 compute, warp 4 producer (TMA + the fp32 -> 16-bit AW tile), warp 5 MMA issuer;
-// two stages of {q, k, v, AW} so the next item loads under the current one.
+// Two persistent CTAs per SM (<= 113 KB shared memory, 256 TMEM columns, 168 registers each) hide each other's serial per-item
+// chain: warps 0-3 compute, warp 4 producer (TMA + the fp32 -> 16-bit AW tile), warp 5 MMA issuer.  One q tile and one k/v
+// tile per CTA: v is loaded into the k tile once D1 has read it; D2 reuses the TMEM columns of D1 after the kv read-back.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -30,7 +31,7 @@ namespace laracore {
 constexpr int kThreads = 192;
 enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullAW0, kFullAW1, kFree0, kFree1,
            kSFull, kPFull, kKvFull, kKvTile, kD3Full, kP2Full0, kP2Full1, kOFull0, kOFull1, kEpiDone,
-           kFullW0, kFullW1, kWFree, kToMma, kToCompute, kNumBars };
+           kFullW0, kFullW1, kWFree, kToMma, kToCompute, kKFree, kS2Full, kLtDone, kNumBars };
 
 struct Params {
   int B, H, N, NP, C, items;
@@ -67,18 +68,19 @@ __device__ __forceinline__ float lg2(float x) {
 }
 
 // TMEM columns
-constexpr uint32_t cD1 = 0, cD2 = 224, cKv = 448;          // phase S: logits [128 x NP] twice, kv [128 x 64]
-constexpr uint32_t cD3 = 0, cO = 256;                      // phase O: per token block rb: D3 at 128 rb, O at 256 + 64 rb
+constexpr uint32_t cD1 = 0, cD2 = 0, cKv = 128;            // phase S: D1 [128 x NP], then (after the kv read-back) D2 in the same columns; kv [128 x 64] in the
+                                                           // columns of D1 that are dead once P (NP / 2 <= 112 columns) has been written
+constexpr uint32_t cD3 = 0, cO = 64;                       // phase O, token block rb at 128 rb: D3 [128 x 128]; O over the dead t half (+64)
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
                  const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_o,
                  const __grid_constant__ CUtensorMap t_w, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int SL = p.sl;
-  uint8_t* const aw0 = sm + 6 * SL;                  // 2 x [128][128 B]: omega rows 0-63, q_bar rows 64-127
+  uint8_t* const aw0 = sm + 2 * SL;                  // [128][128 B]: omega rows 0-63, q_bar rows 64-127 (second 16 KB unused)
   uint8_t* const kvt = aw0 + 2 * 16384;              // [128][128 B]: kv (rows = landmarks; phase L: k_bar, then mu); rows 64-127 stay zero (M = 128 A operand of the mixing MMA)
   float* const n2k = reinterpret_cast<float*>(kvt + 16384);    // [256] |k_n|^2
   float* const n2q = n2k + 256;                                 // [256] |q_n|^2
@@ -91,7 +93,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
   const uint32_t bars = ptx::smem_u32(reinterpret_cast<uint8_t*>(lnp + 384));
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(lnp + 384) + kNumBars * 8);
   auto bar = [&](int i) { return bars + 8u * i; };
-  auto tile = [&](int s, int which) { return sm + (3 * s + which) * SL; };    // which: 0 q, 1 k, 2 v
+  auto tile = [&](int, int which) { return sm + (which == 0 ? 0 : SL); };      // which: 0 q, 1 k, 2 v (v takes over the k tile)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, NP = p.NP, C = p.C;
 
@@ -116,6 +118,9 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     ptx::mbar_init(bar(kWFree), 1);
     ptx::mbar_init(bar(kToMma), 128);
     ptx::mbar_init(bar(kToCompute), 1);
+    ptx::mbar_init(bar(kKFree), 1);
+    ptx::mbar_init(bar(kS2Full), 1);
+    ptx::mbar_init(bar(kLtDone), 128);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
   }
@@ -123,7 +128,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
     for (int idx = tid; idx < 384; idx += kThreads) lnp[idx] = src[idx >> 6] ? __ldg(src[idx >> 6] + (idx & 63)) : 0.f;
   }
-  if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 512);
+  if (warp == 5) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
@@ -135,27 +140,27 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     // =================================== producer ==============================================
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int s = it & 1;
+      const int s = 0;
       const int h = item % p.H, b = item / p.H;
-      if (it >= 2) ptx::mbar_wait(bar(kFree0 + s), ((it >> 1) - 1) & 1);
+      if (it >= 1) ptx::mbar_wait(bar(kFree0 + s), (it - 1) & 1);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(bar(kFullQK0 + s), 2 * SL);
         ptx::tma_load_4d(ptx::smem_u32(tile(s, 0)), &t_q, bar(kFullQK0 + s), 0, h, 0, b);
         ptx::tma_load_4d(ptx::smem_u32(tile(s, 1)), &t_k, bar(kFullQK0 + s), 0, h, 0, b);
-        if (!p.fuse) {
-          ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
-          ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
-        } else if (p.has_proj) {                     // [W_q ; W_k] borrows the v tile until the Linear MMA has read it
+        if (p.fuse && p.has_proj) {                  // [W_q ; W_k] borrows the kv tile until the Linear MMA has read it
           ptx::mbar_arrive_expect_tx(bar(kFullW0 + s), 16384);
-          ptx::tma_load_2d(ptx::smem_u32(tile(s, 2)), &t_w, bar(kFullW0 + s), 0, 0);
+          ptx::tma_load_2d(ptx::smem_u32(kvt), &t_w, bar(kFullW0 + s), 0, 0);
         }
       }
-      if (p.fuse) {
-        if (p.has_proj) ptx::mbar_wait(bar(kWFree), it & 1);
+      auto load_v = [&]() {                          // v takes over the k tile once D1 has read it
+        ptx::mbar_wait(bar(kKFree), it & 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
           ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
         }
+      };
+      if (p.fuse) {
+        load_v();
         continue;                                    // the AW tile, lp and bh are produced on chip (phase L)
       }
       const LaraWs w = lara_ws_at(const_cast<float*>(p.ws), item, C, C, 64);
@@ -174,6 +179,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (ptx::elect_one()) ptx::mbar_arrive(bar(kFullAW0 + s));
+      load_v();
     }
   } else if (warp == 5) {
     // =================================== MMA issuer ============================================
@@ -185,14 +191,16 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     const uint64_t dKV = ptx::umma_desc_sw128(ptx::smem_u32(kvt));
     uint32_t it = 0, hand = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1, pi = it & 1;
+      const int s = 0;
+      const uint32_t ph = it & 1, pi = it & 1;
       const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 0))), dK = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 1)));
       const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 2))), dAW = ptx::umma_desc_sw128(ptx::smem_u32(aw0 + s * 16384));
       ptx::mbar_wait(bar(kFullQK0 + s), ph);
       if (!p.fuse) {
         ptx::mbar_wait(bar(kFullAW0 + s), ph);
         if (it > 0) ptx::mbar_wait(bar(kEpiDone), (it - 1) & 1);    // the previous item's TMEM has been read
+        ptx::mbar_wait(bar(kToMma), hand & 1);                       // |k|^2 taken: D1 may release the k tile to the v load
+        ++hand;
       } else {
         // phase L: a strict ping-pong with the compute warps (kToMma: 128 arrivals, kToCompute: one commit per hand-off)
         const uint64_t dKBm = dKV;                                   // k_bar / mu tile lives in the kv tile until the kv read-back
@@ -202,9 +210,8 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           ptx::mbar_wait(bar(kFullW0 + s), ph);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 0, dAW + 2 * ks, dV + 2 * ks, id_d3, ks > 0);
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 0, dAW + 2 * ks, dKV + 2 * ks, id_d3, ks > 0);
             ptx::umma_commit(bar(kToCompute));
-            ptx::umma_commit(bar(kWFree));
           }
         }
         if (p.mixed) {
@@ -224,7 +231,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         wait_compute();                                              // AW (omega | q_bar) and mu tiles written
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 256, dAW + 2 * ks, dKBm + 2 * ks, id_m64, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 0, dAW + 2 * ks, dKBm + 2 * ks, id_m64, ks > 0);   // the Linear result is dead
           ptx::umma_commit(bar(kToCompute));
         }
         wait_compute();                                              // lp / bh done, phase-L TMEM reads finished
@@ -233,9 +240,8 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD1, dAW + 2 * ks, dK + 2 * ks, id_s, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2, dAW + 2 * ks, dQ + 2 * ks, id_s, ks > 0);
         ptx::umma_commit(bar(kSFull));
+        ptx::umma_commit(bar(kKFree));
       }
       ptx::mbar_wait(bar(kPFull), pi);
       ptx::mbar_wait(bar(kFullV0 + s), ph);
@@ -246,6 +252,13 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         ptx::umma_commit(bar(kKvFull));
       }
       ptx::mbar_wait(bar(kKvTile), pi);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2, dAW + 2 * ks, dQ + 2 * ks, id_s, ks > 0);
+        ptx::umma_commit(bar(kS2Full));
+      }
+      ptx::mbar_wait(bar(kLtDone), pi);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll 1
@@ -261,7 +274,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cO + 64 * rb, tmem + cD3 + 128 * rb + 8 * ks, dKV + 128 * ks, id_pv, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cO + 128 * rb, tmem + cD3 + 128 * rb + 8 * ks, dKV + 128 * ks, id_pv, ks > 0);
           ptx::umma_commit(bar(kOFull0 + rb));
           if (rb == 1) ptx::umma_commit(bar(kFree0 + s));
         }
@@ -274,8 +287,8 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     const int c_row = tid & 63;
     uint32_t it = 0, hc = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1, pi = it & 1;
+      const int s = 0;
+      const uint32_t ph = it & 1, pi = it & 1;
       const int h = item % p.H, b = item / p.H;
       // |k_n|^2 and |q_n|^2 from the tiles
       ptx::mbar_wait(bar(kFullQK0 + s), ph);
@@ -296,6 +309,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         n2q[n] = aq; n2k[n] = ak;
       }
       ptx::named_bar_sync(1, 128);
+      if (!p.fuse) ptx::mbar_arrive(bar(kToMma));
       if (p.fuse) {
         // ---- phase L: landmarks on chip (lara.py:129-175, 182-198, 221-232) ----
         uint8_t* const awt = aw0 + s * 16384;           // first the means tile, finally [omega ; q_bar]
@@ -436,7 +450,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         if (ws_ == 0) {
           float v[64];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + 256 + 16 * g, reinterpret_cast<uint32_t*>(v) + 16 * g);
+          for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + 0 + 16 * g, reinterpret_cast<uint32_t*>(v) + 16 * g);
           ptx::tmem_ld_wait();
           float mx = kNegInf;
           const float lp = lp_exact;
@@ -456,44 +470,50 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         to_mma();
       }
       // ---- phase S: softmax over the tokens, thread = landmark row ----
+      // one two-pass softmax routine, used on D1 by the omega rows (lanes 0-63) and later on D2 by the q_bar rows (64-127)
+      float sum = 0.f, lse2 = 0.f;
+      auto row_softmax = [&](const bool with_k2, const bool write_p) {
+        float m0 = kNegInf;
+#pragma unroll 1
+        for (int g = 0; g < NP / 16; ++g) {
+          float v[16];
+          ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = 16 * g + e;
+            const float x = with_k2 ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
+            m0 = fmaxf(m0, n < N ? x : kNegInf);
+          }
+        }
+        sum = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < NP / 16; ++g) {
+          float v[16];
+          uint32_t pk[8];
+          ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const int n = 16 * g + e;
+            const float x0 = with_k2 ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
+            const float x1 = with_k2 ? scale_log2 * (v[e + 1] - 0.5f * n2k[n + 1]) : scale_log2 * v[e + 1];
+            const float a = n < N ? ex2(x0 - m0) : 0.f, c2 = n + 1 < N ? ex2(x1 - m0) : 0.f;
+            sum += a + c2;
+            pk[e >> 1] = Fmt<T>::pack2(a, c2);
+          }
+          if (write_p) ptx::tmem_st8(trow + 8 * g, pk);               // P over the first half of the columns already read
+        }
+        lse2 = m0 + lg2(sum);                                          // log2 units
+      };
       ptx::mbar_wait(bar(kSFull), pi);
       if (!p.fuse) ptx::mbar_wait(bar(kFullAW0 + s), ph);          // lp / bh of this stage (written by the producer warp) are visible
       ptx::tc_fence_after();
-      const uint32_t cS = d1_side ? cD1 : cD2;
-      float m0 = kNegInf;
-#pragma unroll 1
-      for (int g = 0; g < NP / 16; ++g) {
-        float v[16];
-        ptx::tmem_ld16(trow + cS + 16 * g, reinterpret_cast<uint32_t*>(v));
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int n = 16 * g + e;
-          const float x = d1_side ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
-          m0 = fmaxf(m0, n < N ? x : kNegInf);
-        }
+      if (d1_side) {
+        row_softmax(true, true);
+        cst2[c_row] = lse2 - lpS[s * 64 + c_row] * kLog2e;
+        ptx::tmem_st_wait();
       }
-      float sum = 0.f;
-#pragma unroll 1
-      for (int g = 0; g < NP / 16; ++g) {
-        float v[16];
-        uint32_t pk[8];
-        ptx::tmem_ld16(trow + cS + 16 * g, reinterpret_cast<uint32_t*>(v));
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const int n = 16 * g + e;
-          const float x0 = d1_side ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
-          const float x1 = d1_side ? scale_log2 * (v[e + 1] - 0.5f * n2k[n + 1]) : scale_log2 * v[e + 1];
-          const float a = n < N ? ex2(x0 - m0) : 0.f, c2 = n + 1 < N ? ex2(x1 - m0) : 0.f;
-          sum += a + c2;
-          pk[e >> 1] = Fmt<T>::pack2(a, c2);
-        }
-        if (d1_side) ptx::tmem_st8(trow + cD1 + 8 * g, pk);          // P over the first half of the D1 columns already read
-      }
-      const float lse2 = m0 + lg2(sum);                              // log2 units
-      if (d1_side) cst2[c_row] = lse2 - lpS[s * 64 + c_row] * kLog2e; else lse2t[c_row] = lse2;
-      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kPFull));
       // ---- kv rows -> 16-bit tile ----
@@ -512,11 +532,24 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
             *reinterpret_cast<uint4*>(row + ((ch ^ (c_row & 7)) << 4)) =
                 make_uint4(Fmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), Fmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
                            Fmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Fmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        } else {
+          uint8_t* row = kvt + c_row * 128;              // rows >= C must be zero (K dimension of the output MMA)
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(row + (ch << 4)) = make_uint4(0, 0, 0, 0);
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(kKvTile));                                 // also publishes cst2 / lse2t to the other warps (acq / rel)
+      ptx::mbar_arrive(bar(kKvTile));
+      // ---- D2 = q_bar q^T in the same columns: lse_t, by the q_bar rows ----
+      ptx::mbar_wait(bar(kS2Full), pi);
+      ptx::tc_fence_after();
+      if (!d1_side) {
+        row_softmax(false, false);
+        lse2t[c_row] = lse2;
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(kLtDone));
       // ---- phase O: thread = token ----
       ptx::mbar_wait(bar(kD3Full), pi);
       ptx::tc_fence_after();
@@ -563,7 +596,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         ptx::tc_fence_after();
         float o[64];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cO + 64 * rb + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
+        for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cO + 128 * rb + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
         ptx::tmem_ld_wait();
         const float inv = 1.0f / wsum;
         uint8_t* row = tile(s, 0) + n * 128;                           // the q tile is dead: every D3 MMA has completed
@@ -593,7 +626,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == 5) ptx::tmem_dealloc(tmem, 512);
+  if (warp == 5) ptx::tmem_dealloc(tmem, 256);
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -657,14 +690,14 @@ static cudaError_t launch_t(const LaraGeo& g, int io_dtype, const View& q, const
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  const int dyn = 6 * p.sl + 3 * 16384 + (2 * 256 + 2 * 128 + 3 * 64 + 384) * 4 + kNumBars * 8 + 16 + 1024;
+  const int dyn = 2 * p.sl + 3 * 16384 + (2 * 256 + 2 * 128 + 3 * 64 + 384) * 4 + kNumBars * 8 + 16 + 1024;
   auto kern = lara_core_kernel<T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.items < sms ? p.items : sms;
+  const int grid = p.items < 2 * sms ? p.items : 2 * sms;
   kern<<<grid, kThreads, dyn, st>>>(tq, tk, tv, to, tw, p);
   return cudaGetLastError();
 }
