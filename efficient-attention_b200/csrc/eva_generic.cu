@@ -132,6 +132,10 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
   float* om = yv + 128;             // [64]      omega
   float* red = om + 64;             // [16]      block reductions
   float* pj = red + 16;             // [Jc]      softmax weights
+  // the chunk's k rows staged by phase 1 for the per-token logits of phase 3 (row stride 144 B: conflict-free 16-byte reads)
+  constexpr int kKs = 144;
+  uint8_t* kst = reinterpret_cast<uint8_t*>(pj + ((g.Jc + 3) & ~3));
+  const bool stage_k = sizeof(T) == 2 && g.Jc <= 512;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long wg = blockIdx.x;
   const int c = (int)(wg % g.n_chunks);
@@ -141,11 +145,14 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
   const float scale = 0.125f;
   // ---- phase 1 ----
   float sq0 = 0.f, sq1 = 0.f, sk0 = 0.f, sk1 = 0.f;
+#pragma unroll 4
   for (int s = warp; s < g.Jc; s += 8) {
     const T* qr = q.row<T>(b, t0 + s, h);
     const T* kr = k.row<T>(b, t0 + s, h);
+    const T k0 = kr[2 * lane], k1 = kr[2 * lane + 1];
     sq0 += to_f32(qr[2 * lane]); sq1 += to_f32(qr[2 * lane + 1]);
-    sk0 += to_f32(kr[2 * lane]); sk1 += to_f32(kr[2 * lane + 1]);
+    sk0 += to_f32(k0); sk1 += to_f32(k1);
+    if (stage_k) { T* dst = reinterpret_cast<T*>(kst + s * kKs); dst[2 * lane] = k0; dst[2 * lane + 1] = k1; }
   }
   part[warp * 128 + 2 * lane] = sq0; part[warp * 128 + 2 * lane + 1] = sq1;
   part[warp * 128 + 64 + 2 * lane] = sk0; part[warp * 128 + 64 + 2 * lane + 1] = sk1;
@@ -208,12 +215,19 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
   // ---- phase 3 ----
   float mloc = kNegInf;
   for (int s = tid; s < g.Jc; s += 256) {
-    const T* kr = k.row<T>(b, t0 + s, h);
+    const T* kr = stage_k ? reinterpret_cast<const T*>(kst + s * kKs) : k.row<T>(b, t0 + s, h);
     float acc = 0.f;
 #pragma unroll
     for (int p8 = 0; p8 < 8; ++p8) {
       float f[8];
-      load8<T>(kr + 8 * p8, f);
+      if (stage_k) {                 // staged rows live in shared memory: plain 16-byte read (load8 is ld.global.nc)
+        const uint4 raw = *reinterpret_cast<const uint4*>(kr + 8 * p8);
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = to_f32(e[i]);
+      } else {
+        load8<T>(kr + 8 * p8, f);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc = fmaf(f[i], om[8 * p8 + i] - 0.5f * f[i], acc);
     }
@@ -430,7 +444,8 @@ static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View&
     // long 1-D chunks (causal LM): one CTA per chunk
     static const bool generic_only = [] { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); return e && e[0] == '1'; }();
     if (!generic_only && g.dims == 1 && g.chunk_ext == 0 && !mask && g.Jc >= 64 && g.Jc <= 8192) {
-      const size_t smem_cta = (size_t)(8 * 128 + 128 + 128 + 64 + 16 + g.Jc) * sizeof(float);
+      const size_t smem_cta = (size_t)(8 * 128 + 128 + 128 + 64 + 16 + ((g.Jc + 3) & ~3)) * sizeof(float) + (sizeof(T) == 2 && g.Jc <= 512 ? (size_t)g.Jc * 144 : 0);
+      if (smem_cta > 48 * 1024) cudaFuncSetAttribute(chunk_stats_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta);
       const long long total_cta = (long long)g.B * g.H * g.n_chunks;
       chunk_stats_cta_kernel<T><<<(unsigned)total_cta, 256, smem_cta, st>>>(g, q, k, v, ada, noise, kbar, beta);
       return cudaGetLastError();

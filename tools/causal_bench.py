@@ -60,5 +60,5 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     ms_w = e0.elapsed_time(e1) / 20
     tok = B * N
-    print(f'eva_forward {ms:.3f} ms ({tok / ms / 1e6:.1f} M tokens/s, {tok * 4096 / (ms * 1e-3) / 6469.3e9 * 100:.1f} % of the core HBM roofline); window kernel alone {ms_w:.3f} ms', flush=True)
+    print(f'eva_forward {ms:.3f} ms ({tok / ms / 1e3:.1f} M tokens/s, {tok * 4096 / (ms * 1e-3) / 6469.3e9 * 100:.1f} % of the core HBM roofline); window kernel alone {ms_w:.3f} ms', flush=True)
     assert err < 3e-3, err
