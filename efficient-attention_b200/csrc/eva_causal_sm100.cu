@@ -37,6 +37,7 @@ enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFr
 
 struct Params {
   int B, H, N, n_win, items, n_chunks, cnp, chunk;
+  int swap;                      // bit i: tensor map i (q, k, v) has its batch and token dimensions exchanged (time-major activations)
   const float *kbar, *beta;      // [B, H, n_chunks, 64] fp32 from chunk_stats_kernel
   const float* bias;             // [256, 256] fp32 with bias[i][j] = f(i - j) (T5 bias shared by the heads), or NULL
 };
@@ -107,10 +108,11 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
       const uint32_t st = ptx::smem_u32(stage_ptr(s));
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(bar(kFullQK0 + s), 65536);
-        ptx::tma_load_4d(st, &t_q, bar(kFullQK0 + s), 0, h, wi * kWin, b);
-        ptx::tma_load_4d(st + 32768, &t_k, bar(kFullQK0 + s), 0, h, wi * kWin, b);
+        const int n0 = wi * kWin;
+        ptx::tma_load_4d(st, &t_q, bar(kFullQK0 + s), 0, h, (p.swap & 1) ? b : n0, (p.swap & 1) ? n0 : b);
+        ptx::tma_load_4d(st + 32768, &t_k, bar(kFullQK0 + s), 0, h, (p.swap & 2) ? b : n0, (p.swap & 2) ? n0 : b);
         ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), 32768);
-        ptx::tma_load_4d(st + 65536, &t_v, bar(kFullV0 + s), 0, h, wi * kWin, b);
+        ptx::tma_load_4d(st + 65536, &t_v, bar(kFullV0 + s), 0, h, (p.swap & 4) ? b : n0, (p.swap & 4) ? n0 : b);
       }
       // chunk keys / values of this (batch, head): fp32 rows -> 16-bit swizzled tiles (rows >= n_chunks stay zero)
       uint8_t* kb = kb_ptr(s);
@@ -315,13 +317,18 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// [B, N, H, 64] view -> (64, H, N, B) tensor map with a (64, 1, rows, 1) box, 128-byte swizzle
-static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long long sn, long long sh, const Geo& g, int io_dtype, int rows) {
+// [B, N, H, 64] view -> (64, H, N, B) tensor map with a (64, 1, rows, 1) box, 128-byte swizzle.  Tensor-map strides have to grow
+// with the dimension, so a time-major activation (token stride > batch stride: fairseq's [T, B, C]) gets (64, H, B, N) and a
+// (64, 1, 1, rows) box instead -- same tile in shared memory -- and *swapped tells the kernel to exchange the two coordinates.
+static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long long sn, long long sh, const Geo& g, int io_dtype, int rows,
+                         bool* swapped = nullptr) {
   auto enc = get_encode();
   if (!enc) return false;
-  const cuuint64_t dims[4] = {64, (cuuint64_t)g.H, (cuuint64_t)g.N, (cuuint64_t)g.B};
-  const cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
-  const cuuint32_t box[4] = {64, 1, (cuuint32_t)rows, 1};
+  const bool sw = swapped && sb < sn;
+  if (swapped) *swapped = sw;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)g.H, (cuuint64_t)(sw ? g.B : g.N), (cuuint64_t)(sw ? g.N : g.B)};
+  const cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)(sw ? sb : sn) * 2, (cuuint64_t)(sw ? sn : sb) * 2};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)(sw ? 1 : rows), (cuuint32_t)(sw ? rows : 1)};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(tm, io_dtype == EVA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -332,8 +339,9 @@ template <typename T>
 static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar, const float* beta,
                             const float* bias, void* out, cudaStream_t st, const char** msg) {
   CUtensorMap tq, tk, tv, to;
-  if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin) ||
-      !make_seq_map(&tv, v.ptr, v.sb, v.sn, v.sh, g, io_dtype, kWin) ||
+  bool swq = false, swk = false, swv = false;
+  if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin, &swq) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin, &swk) ||
+      !make_seq_map(&tv, v.ptr, v.sb, v.sn, v.sh, g, io_dtype, kWin, &swv) ||
       !make_seq_map(&to, out, (long long)g.N * g.H * 64, (long long)g.H * 64, 64, g, io_dtype, 128)) {
     *msg = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
@@ -342,6 +350,7 @@ static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const Vie
   p.B = g.B; p.H = g.H; p.N = g.N; p.n_win = g.N / kWin; p.items = g.B * g.H * p.n_win;
   p.n_chunks = g.n_chunks; p.cnp = (g.n_chunks + 15) & ~15; p.chunk = g.chunk;
   p.kbar = kbar; p.beta = beta; p.bias = bias;
+  p.swap = (swq ? 1 : 0) | (swk ? 2 : 0) | (swv ? 4 : 0);
   auto kern = eva_causal_window_kernel<T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }

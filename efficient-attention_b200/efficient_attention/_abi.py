@@ -115,6 +115,23 @@ def _f32(t):
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
 
+def memo(owner, tag, sources, build):
+    """Per-module cache of tensors derived from parameters (fp32 copies, gathered bias tables, fused weights).
+
+    Rebuilt whenever a source tensor was modified in place (optimizer step, load_state_dict: `_version` changes) or replaced
+    (`.to()`, `.half()`: storage / dtype / device change); the cache lives in the module and dies with it.  Saves a dozen tiny
+    conversion kernels and their host-side launches on every forward.
+    """
+    key = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device, tuple(t.shape)) for t in sources)
+    cache = owner.__dict__.setdefault('_sm100_memo', {})
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = build()
+    cache[tag] = (key, val)
+    return val
+
+
 def adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff, ln_eps=1e-5):
     """Returns (struct, keepalive list of float32 tensors)."""
     keep = [_f32(t) for t in (wq, bq, gq, betq, wk, bk, gk, betk)]

@@ -9,6 +9,7 @@ import uuid
 from typing import Dict, Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import _abi
@@ -144,7 +145,24 @@ class CausalEVAttention(nn.Module):
         def parts(seq):
             ln = seq[1] if len(seq) > 1 else None
             return (seq[0].weight, seq[0].bias, ln.weight if ln is not None else None, ln.bias if ln is not None else None)
-        return _abi.adaptive(*parts(self.adaptive_mu_q), *parts(self.adaptive_mu_k), mu_coeff=1.0)
+        params = parts(self.adaptive_mu_q) + parts(self.adaptive_mu_k)
+        return _abi.memo(self, 'adaptive', params, lambda: _abi.adaptive(*params, mu_coeff=1.0))
+
+    def _project_qkv_time_major(self, query):
+        """Self-attention without padding and without autograd: q, k, v of all heads from ONE GEMM on the [T, B, C] input as it
+        arrives (no [T,B,C] -> [B,T,C] copy, no three separate projections), returned as [B, T, H, D] strided views -- the
+        kernels take any (batch, token, head) strides."""
+        lins = (self.q_proj, self.k_proj, self.v_proj)
+        srcs = tuple(l.weight for l in lins) + tuple(l.bias for l in lins)
+
+        def fuse():
+            w = torch.cat([l.weight.detach() for l in lins], 0).contiguous()
+            b = None if lins[0].bias is None else torch.cat([l.bias.detach() for l in lins], 0).contiguous()
+            return w, b
+        w, b = _abi.memo(self, 'qkv_fused', srcs, fuse)
+        T, B, C = query.shape
+        qkv = F.linear(query, w, b).view(T, B, 3, self.num_heads, self.head_dim)
+        return tuple(qkv[:, :, i].transpose(0, 1) for i in range(3))
 
     def forward(self, query, key: Optional[Tensor], value: Optional[Tensor],
                 key_padding_mask: Optional[Tensor] = None,
@@ -157,11 +175,15 @@ class CausalEVAttention(nn.Module):
             raise NotImplementedError('incremental decoding is not built yet (SURVEY.md 8f-3)')
         if self.dropout_module.active():
             raise NotImplementedError('attention-probability dropout is not built into the sm_100a kernels')
+        time_major = query
         query = query.transpose(0, 1)
         bsz, tgt_len, embed_dim = query.size()
         assert embed_dim == self.embed_dim, f"query dim {embed_dim} != {self.embed_dim}"
         x, key_padding_mask = self._process_input(query, key_padding_mask)
         B, N, C = x.shape
+        fused_qkv = ((self.self_attention or key is None) and N == tgt_len and not torch.is_grad_enabled()
+                     and time_major.is_contiguous() and all((l.bias is None) == (self.q_proj.bias is None) for l in (self.k_proj, self.v_proj))
+                     and self.kdim == self.embed_dim and self.vdim == self.embed_dim)
         if self.self_attention or key is None:
             k_in = v_in = x
         else:
@@ -172,9 +194,12 @@ class CausalEVAttention(nn.Module):
             k_in = pad_to_multiple(key, self.window_size, dim=-2) if self.window_size > 0 else key
             v_in = pad_to_multiple(value, self.window_size, dim=-2) if self.window_size > 0 else value
         H, D = self.num_heads, self.head_dim
-        q = self.q_proj(x).view(B, N, H, D)
-        k = self.k_proj(k_in).view(B, N, H, D)
-        v = self.v_proj(v_in).view(B, N, H, D)
+        if fused_qkv:
+            q, k, v = self._project_qkv_time_major(time_major)
+        else:
+            q = self.q_proj(x).view(B, N, H, D)
+            k = self.k_proj(k_in).view(B, N, H, D)
+            v = self.v_proj(v_in).view(B, N, H, D)
         chunk = self.chunk_size if self.chunk_size is not None else int(N // self.num_chunks)
         if chunk >= N:
             raise ValueError('chunk size %d must be smaller than the padded sequence %d (causal_eva.py:680-683)' % (chunk, N))
@@ -185,7 +210,9 @@ class CausalEVAttention(nn.Module):
             noise = torch.randn(B, H, _abi.num_chunks(geom), D, dtype=torch.float32, device=x.device)
         bias = None
         if self.use_t5_rpe:
-            bias = self.rel_pos_bias.dense(self.window_size, self.window_size + self.ext_size).unsqueeze(0)
+            table = self.rel_pos_bias.relative_attention_bias.weight
+            bias = _abi.memo(self, 'bias', (table,), lambda: self.rel_pos_bias.dense(
+                self.window_size, self.window_size + self.ext_size).unsqueeze(0).detach().float().contiguous())
         out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise, bias=bias)
         out = attach_forward_only(out, q, k, v)
         y = self.out_proj(out)

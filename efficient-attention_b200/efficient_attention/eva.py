@@ -91,13 +91,15 @@ class EVA(LocalAttention):
             ln = seq[1] if len(seq) > 1 else None
             return (lin.weight, lin.bias, ln.weight if ln is not None else None, ln.bias if ln is not None else None)
         q = parts(self.adaptive_mu_q) if self.adaptive_proj != 'none' else (None, None, None, None)
-        return _abi.adaptive(*q, *parts(self.adaptive_mu_k), mu_coeff=0.5)
+        k = parts(self.adaptive_mu_k)
+        return _abi.memo(self, 'adaptive', q + k, lambda: _abi.adaptive(*q, *k, mu_coeff=0.5))
 
     def _local_bias(self):
         if self.use_t5_rpe:
             w, e = self.window_size, self.ext_size
             L, J = (w * w, (w + 2 * e) ** 2) if self.attn_2d else (w, w + 2 * e)
-            return self.rel_pos_bias.dense(L, J)
+            table = self.rel_pos_bias.relative_attention_bias.weight
+            return _abi.memo(self, 'bias', (table,), lambda: self.rel_pos_bias.dense(L, J).detach().float().contiguous())
         return self._window_bias()
 
     def forward(self, x, key_padding_mask=None, noise=None):

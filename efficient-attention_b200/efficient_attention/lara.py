@@ -60,8 +60,8 @@ class LinearRA(MultiheadAttention):
             lin_q, ln_q, lin_k, ln_k = self.q_bar_gen[2], self.q_bar_gen[3], self.k_bar_gen[2], self.k_bar_gen[3]
         else:  # 'no-param-pool', or pooled proposals on a 1-D input (plain segment means, lara.py:98-103)
             return _abi.adaptive(*([None] * 8), mu_coeff=1.0)
-        return _abi.adaptive(lin_q.weight, lin_q.bias, ln_q.weight, ln_q.bias,
-                             lin_k.weight, lin_k.bias, ln_k.weight, ln_k.bias, mu_coeff=1.0, ln_eps=ln_q.eps)
+        params = (lin_q.weight, lin_q.bias, ln_q.weight, ln_q.bias, lin_k.weight, lin_k.bias, ln_k.weight, ln_k.bias)
+        return _abi.memo(self, 'proj_params', params, lambda: _abi.adaptive(*params, mu_coeff=1.0, ln_eps=ln_q.eps))
 
     def forward(self, x, key_padding_mask=None, noise=None):
         """x: [B, H', W', C] or [B, N, C].  `noise` optionally overrides the training-mode draw

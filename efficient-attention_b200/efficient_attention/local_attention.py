@@ -42,8 +42,12 @@ class LocalAttention(MultiheadAttention):
         table = self.local_relative_position_bias_table
         if not self.attn_2d:
             return table
-        L, J = self.relative_position_index.shape
-        return table[self.relative_position_index.reshape(-1)].view(L, J, self.num_heads).permute(2, 0, 1)
+
+        def gather():
+            L, J = self.relative_position_index.shape
+            dense = table[self.relative_position_index.reshape(-1)].view(L, J, self.num_heads).permute(2, 0, 1)
+            return dense.detach().float().contiguous()
+        return _abi.memo(self, 'window_bias', (table, self.relative_position_index), gather)
 
     def _core(self, q, k, v, packed, key_padding_mask, seq_shape):
         B, N, H, D = q.shape

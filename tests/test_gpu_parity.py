@@ -376,6 +376,57 @@ def test_causal_tcgen05_many_windows_per_cta_fp16():
     assert float(per_item.max()) < TOL_F16, float(per_item.max())
 
 
+def test_causal_time_major_views_fp16():
+    """Batch / token strides exchanged ([T, B, ...] activations, as the causal module's fused q/k/v projection produces them):
+    the tcgen05 window kernel builds its tensor maps with the two dimensions swapped; results must equal the batch-major call
+    bit for bit (same kernels, same values, only the addressing differs)."""
+    from efficient_attention import _abi
+    B, H, d, N = 3, 4, 64, 1024
+    dev = _dev()
+    g = torch.Generator().manual_seed(11)
+    tm = (torch.randn(N, B, 3, H, d, generator=g) * 1.1).half().to(dev)          # time-major storage
+    bm = tm.transpose(0, 1).contiguous()                                         # batch-major copy of the same values
+    ada = _abi_ada(_rand_ada(d, g), dev, 1.0)
+    outs = []
+    for src in (tm.transpose(0, 1), bm):
+        q, k, v = src[:, :, 0], src[:, :, 1], src[:, :, 2]
+        geom = _abi.eva_geometry(q, seq_shape=(N,), window=256, ext=0, chunk=128, chunk_ext=0, causal=True, halo_left_only=True,
+                                 mask_queries=True)
+        out, path = _abi.eva_forward(q, k, v, geom, ada, return_path=True)
+        assert path == 2
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_causal_module_fused_projection_matches_separate_fp16():
+    """CausalEVAttention under no_grad projects q, k, v with one GEMM on the [T, B, C] input (no transposed copies); with
+    autograd enabled it takes the three separate projections.  Same module, same input: same output up to GEMM rounding."""
+    import argparse
+    import warnings
+    import efficient_attention as ea
+    dev = _dev()
+    ns = argparse.Namespace(adaptive_proj='qk', num_chunks=None, chunk_size=128, causal=True, use_t5_rpe=True, window_size=256,
+                            overlap_window=False)
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = ea.CausalEVAttention(embed_dim=256, num_heads=4, dropout=0.0, self_attention=True, attn_args=ns).to(dev).half().eval()
+    x = torch.randn(512, 3, 256, device=dev, dtype=torch.float16)
+    with torch.no_grad():
+        y_fused = m(x, x, x, need_weights=False)[0]
+        assert 'qkv_fused' in m.__dict__['_sm100_memo']
+    y_sep = m(x, x, x, need_weights=False)[0].detach()
+    err = float((y_fused.float() - y_sep.float()).norm() / y_sep.float().norm())
+    assert err < 1e-3, err
+    # the cache follows in-place parameter updates
+    with torch.no_grad():
+        m.q_proj.weight.mul_(0.5)
+        y2 = m(x, x, x, need_weights=False)[0]
+    y2_sep = m(x, x, x, need_weights=False)[0].detach()
+    assert float((y2.float() - y2_sep.float()).norm() / y2_sep.float().norm()) < 1e-3
+    assert float((y2.float() - y_fused.float()).norm()) > 0
+
+
 @pytest.mark.parametrize('dtype,tol', [(torch.float16, 2e-3), (torch.bfloat16, 1.5e-2)])
 @pytest.mark.parametrize('proposal,with_noise', [('pool-mixed', False), ('pool', False), ('pool-mixed', True)])
 def test_c4_lara_tcgen05_core_16bit(proposal, with_noise, dtype, tol):

@@ -66,6 +66,14 @@ with torch.no_grad(), warnings.catch_warnings():
         overlap_window=False, adaptive_proj='default', num_landmarks=49, use_t5_rpe=False))).to(dev).half().eval()
     x = torch.randn(2048, 14, 14, 192, device=dev, dtype=torch.float16)
     report('c2 EVA N=196 C=192 B=2048 (fused core)', 2048 * 196, 192, timed(lambda: m(x), args.iters))
+    from efficient_attention import _abi
+    q, k, v, _ = m._qkv_heads(x.reshape(2048, 196, 192))
+    geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+    ada, bias = m._adaptive(), m._local_bias().float().contiguous()
+    sec = timed(lambda: _abi.eva_forward(q, k, v, geom, ada, bias=bias), args.iters)
+    print(json.dumps({'config': 'c2 core only (eva_forward, q/k/v resident)', 'tokens_per_s': 2048 * 196 / sec, 'ms': sec * 1e3,
+                      'frac_of_core_hbm_roofline': 2048 * 196 / sec * 1536 / peak}), flush=True)
+    del q, k, v
     # c3 at module level, for comparison with the core number of bench.py
     x = torch.randn(1024, 28, 28, 192, device=dev, dtype=torch.float16)
     report('c3 EVA N=784 C=192 B=1024 (fused core)', 1024 * 784, 192, timed(lambda: m(x), args.iters))
