@@ -143,23 +143,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// packed fp32 pairs (sm_100 FFMA2 / FADD2): halves the FP32 instruction count of the softmax
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+using ptx::pk2; using ptx::upk2; using ptx::fma2; using ptx::add2;
 
 // N consecutive TMEM columns -> registers (x16 / x8 / x1 pieces, compile time)
 template <int N>

@@ -82,9 +82,9 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
   const int SL = p.sl;
   uint8_t* const aw0 = sm + 2 * SL;                  // [128][128 B]: omega rows 0-63, q_bar rows 64-127 (second 16 KB unused)
   uint8_t* const kvt = aw0 + 2 * 16384;              // [128][128 B]: kv (rows = landmarks; phase L: k_bar, then mu); rows 64-127 stay zero (M = 128 A operand of the mixing MMA)
-  float* const n2k = reinterpret_cast<float*>(kvt + 16384);    // [256] |k_n|^2
-  float* const n2q = n2k + 256;                                 // [256] |q_n|^2
-  float* const lpS = n2q + 256;                                 // [2][64] lp  (per stage, from the workspace)
+  float* const n2k = reinterpret_cast<float*>(kvt + 16384);    // [256] |k_n|^2 scale log2(e) / 2 (+inf for n >= N)
+  uint32_t* const bins = reinterpret_cast<uint32_t*>(n2k + 256);   // [64] pooling bin of landmark c: y0 | y1 << 8 | x0 << 16 | x1 << 24 (|q_n|^2 is not needed: it cancels in the softmax over c)
+  float* const lpS = n2k + 512;                                 // [2][64] lp  (per stage, from the workspace)
   float* const bhS = lpS + 128;                                 // [2][64] bh
   float* const cst2 = bhS + 128;                                // [64] (lse_k - lp) log2(e)
   float* const lse2t = cst2 + 64;                               // [64] lse of the t logits, log2 units
@@ -125,6 +125,12 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
     ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
   }
   if (p.fuse) {
+    if (tid < 64) {                                   // AdaptiveAvgPool2d bins, once per CTA (no integer divisions in the item loop)
+      const int cc = tid < C ? tid : 0, by = cc / p.side, bx = cc % p.side;
+      const int y0 = (by * p.gh) / p.side, y1 = ((by + 1) * p.gh + p.side - 1) / p.side;
+      const int x0 = (bx * p.gw) / p.side, x1 = ((bx + 1) * p.gw + p.side - 1) / p.side;
+      bins[tid] = (uint32_t)y0 | ((uint32_t)y1 << 8) | ((uint32_t)x0 << 16) | ((uint32_t)x1 << 24);
+    }
     const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
     for (int idx = tid; idx < 384; idx += kThreads) lnp[idx] = src[idx >> 6] ? __ldg(src[idx >> 6] + (idx & 63)) : 0.f;
   }
@@ -157,6 +163,15 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(bar(kFullV0 + s), SL);
           ptx::tma_load_4d(ptx::smem_u32(tile(s, 2)), &t_v, bar(kFullV0 + s), 0, h, 0, b);
+          // one q tile and one k/v tile per CTA: the next item's loads cannot start before this item is finished, so at least
+          // make them L2 hits
+          const int nxt = item + (int)gridDim.x;
+          if (nxt < p.items) {
+            const int hn = nxt % p.H, bn = nxt / p.H;
+            ptx::tma_prefetch_4d(&t_q, 0, hn, 0, bn);
+            ptx::tma_prefetch_4d(&t_k, 0, hn, 0, bn);
+            ptx::tma_prefetch_4d(&t_v, 0, hn, 0, bn);
+          }
         }
       };
       if (p.fuse) {
@@ -290,23 +305,28 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       const int s = 0;
       const uint32_t ph = it & 1, pi = it & 1;
       const int h = item % p.H, b = item / p.H;
-      // |k_n|^2 and |q_n|^2 from the tiles
+      // |k_n|^2 from the tile: two threads per token row (64 B each), packed fp32x2 FMAs
       ptx::mbar_wait(bar(kFullQK0 + s), ph);
-      for (int n = tid; n < NP; n += 128) {
-        float aq = 0.f, ak = 0.f;
+      for (int idx = tid; idx < 2 * NP; idx += 128) {
+        const int n = idx >> 1, half = idx & 1;
+        uint64_t acc2 = 0ull;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int off = n * 128 + ((ch ^ (n & 7)) << 4);
-          const uint4 rq = *reinterpret_cast<const uint4*>(tile(s, 0) + off), rk = *reinterpret_cast<const uint4*>(tile(s, 1) + off);
-          const uint32_t wq[4] = {rq.x, rq.y, rq.z, rq.w}, wk[4] = {rk.x, rk.y, rk.z, rk.w};
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int ch = 4 * half + c4;
+          const uint4 rk = *reinterpret_cast<const uint4*>(tile(s, 1) + n * 128 + ((ch ^ (n & 7)) << 4));
+          const uint32_t wk[4] = {rk.x, rk.y, rk.z, rk.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 fq = Fmt<T>::unpack2(wq[j]), fk = Fmt<T>::unpack2(wk[j]);
-            aq = fmaf(fq.x, fq.x, aq); aq = fmaf(fq.y, fq.y, aq);
-            ak = fmaf(fk.x, fk.x, ak); ak = fmaf(fk.y, fk.y, ak);
+            const float2 fk = Fmt<T>::unpack2(wk[j]);
+            const uint64_t f2 = ptx::pk2(fk.x, fk.y);
+            acc2 = ptx::fma2(f2, f2, acc2);
           }
         }
-        n2q[n] = aq; n2k[n] = ak;
+        float a0, a1;
+        ptx::upk2(acc2, a0, a1);
+        float ak = a0 + a1;
+        ak += __shfl_xor_sync(0xffffffffu, ak, 1);
+        if (!half) n2k[n] = n < N ? 0.5f * scale_log2 * ak : __int_as_float(0x7f800000);   // pre-scaled; +inf masks the padding columns of D1
       }
       ptx::named_bar_sync(1, 128);
       if (!p.fuse) ptx::mbar_arrive(bar(kToMma));
@@ -318,10 +338,9 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         auto to_mma = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); ptx::mbar_arrive(bar(kToMma)); };
         // L1: adaptive average pooling of q and k (AdaptiveAvgPool2d bins), 16-byte pieces -> means tile
         for (int idx = tid; idx < 2 * C * 8; idx += 128) {
-          const int part = idx & 7, cc = (idx >> 3) % C, sd = idx / (8 * C);
-          const int by = cc / p.side, bx = cc % p.side;
-          const int y0 = (by * p.gh) / p.side, y1 = ((by + 1) * p.gh + p.side - 1) / p.side;
-          const int x0 = (bx * p.gw) / p.side, x1 = ((bx + 1) * p.gw + p.side - 1) / p.side;
+          const int part = idx & 7, u = idx >> 3, sd = u >= C ? 1 : 0, cc = u - (sd ? C : 0);
+          const uint32_t bin = bins[cc];
+          const int y0 = bin & 255, y1 = (bin >> 8) & 255, x0 = (bin >> 16) & 255, x1 = bin >> 24;
           float acc[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -480,10 +499,19 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
           ptx::tmem_ld_wait();
 #pragma unroll
+          float hk[16];
+          if (with_k2) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 x = *reinterpret_cast<const float4*>(n2k + 16 * g + 4 * e4);
+              hk[4 * e4] = x.x; hk[4 * e4 + 1] = x.y; hk[4 * e4 + 2] = x.z; hk[4 * e4 + 3] = x.w;
+            }
+          }
+#pragma unroll
           for (int e = 0; e < 16; ++e) {
             const int n = 16 * g + e;
-            const float x = with_k2 ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
-            m0 = fmaxf(m0, n < N ? x : kNegInf);
+            if (with_k2) m0 = fmaxf(m0, fmaf(scale_log2, v[e], -hk[e]));
+            else m0 = fmaxf(m0, n < N ? scale_log2 * v[e] : kNegInf);
           }
         }
         sum = 0.f;
@@ -494,11 +522,25 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
           ptx::tmem_ld_wait();
 #pragma unroll
+          float hk[16];
+          if (with_k2) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 x = *reinterpret_cast<const float4*>(n2k + 16 * g + 4 * e4);
+              hk[4 * e4] = x.x + m0; hk[4 * e4 + 1] = x.y + m0; hk[4 * e4 + 2] = x.z + m0; hk[4 * e4 + 3] = x.w + m0;
+            }
+          }
+#pragma unroll
           for (int e = 0; e < 16; e += 2) {
             const int n = 16 * g + e;
-            const float x0 = with_k2 ? scale_log2 * (v[e] - 0.5f * n2k[n]) : scale_log2 * v[e];
-            const float x1 = with_k2 ? scale_log2 * (v[e + 1] - 0.5f * n2k[n + 1]) : scale_log2 * v[e + 1];
-            const float a = n < N ? ex2(x0 - m0) : 0.f, c2 = n + 1 < N ? ex2(x1 - m0) : 0.f;
+            float a, c2;
+            if (with_k2) {                                             // padding columns: hk = +inf -> ex2(-inf) = 0
+              a = ex2(fmaf(scale_log2, v[e], -hk[e]));
+              c2 = ex2(fmaf(scale_log2, v[e + 1], -hk[e + 1]));
+            } else {
+              a = n < N ? ex2(fmaf(scale_log2, v[e], -m0)) : 0.f;
+              c2 = n + 1 < N ? ex2(fmaf(scale_log2, v[e + 1], -m0)) : 0.f;
+            }
             sum += a + c2;
             pk[e >> 1] = Fmt<T>::pack2(a, c2);
           }
@@ -564,28 +606,59 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cB + 64 + 16 * g, reinterpret_cast<uint32_t*>(t) + 16 * g);
         ptx::tmem_ld_wait();
-        const float hq = 0.5f * n2q[n < NP ? n : 0];
+        // landmark columns in groups of 8; groups past C are skipped (uniform), per-landmark constants come as 16-byte broadcasts
+        const int G8 = (C + 7) >> 3;
+        auto ld8 = [](const float* src, float* dst) {
+          const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
+          dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; dst[4] = y.x; dst[5] = y.y; dst[6] = y.z; dst[7] = y.w;
+        };
         float tsum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          t[c] = ex2(fmaf(t[c], scale_log2, -lse2t[c]));               // t_nc = softmax_n(scale q_bar_c . q_n)
-          tsum += c < C ? t[c] : 0.f;
+        for (int g8 = 0; g8 < 8; ++g8) {
+          if (g8 < G8) {
+            float ls[8];
+            ld8(lse2t + 8 * g8, ls);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * g8 + j;
+              t[c] = ex2(fmaf(t[c], scale_log2, -ls[j]));             // t_nc = softmax_n(scale q_bar_c . q_n)
+              tsum += c < C ? t[c] : 0.f;
+            }
+          }
         }
         const float mean_t = tsum / (float)C;
         float mw = kNegInf;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const float alpha = bhS[s * 64 + c] + p.alpha_coeff * (t[c] - mean_t);
-          a[c] = lg2(fmaxf(alpha, 1e-8f)) + scale_log2 * (a[c] - hq) + cst2[c];     // log2 of the importance weight
-          mw = fmaxf(mw, c < C ? a[c] : kNegInf);
+        for (int g8 = 0; g8 < 8; ++g8) {
+          if (g8 < G8) {
+            float bh8[8], cs8[8];
+            ld8(bhS + s * 64 + 8 * g8, bh8);
+            ld8(cst2 + 8 * g8, cs8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * g8 + j;
+              const float alpha = bh8[j] + p.alpha_coeff * (t[c] - mean_t);
+              // log2 of the importance weight, up to the per-token constant -|q_n|^2/2 that the softmax over c removes
+              a[c] = lg2(fmaxf(alpha, 1e-8f)) + fmaf(scale_log2, a[c], cs8[j]);
+              mw = fmaxf(mw, c < C ? a[c] : kNegInf);
+            }
+          }
         }
         float wsum = 0.f;
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float w0 = c < C ? ex2(a[c] - mw) : 0.f, w1 = c + 1 < C ? ex2(a[c + 1] - mw) : 0.f;
-          wsum += w0 + w1;
-          pk[c >> 1] = Fmt<T>::pack2(w0, w1);
+        for (int g8 = 0; g8 < 8; ++g8) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const int c = 8 * g8 + j;
+            float w0 = 0.f, w1 = 0.f;
+            if (g8 < G8) {
+              w0 = c < C ? ex2(a[c] - mw) : 0.f;
+              w1 = c + 1 < C ? ex2(a[c + 1] - mw) : 0.f;
+            }
+            wsum += w0 + w1;
+            pk[c >> 1] = Fmt<T>::pack2(w0, w1);
+          }
         }
         ptx::tmem_st16(trow + cB, pk);
         ptx::tmem_st16(trow + cB + 16, pk + 16);

@@ -43,4 +43,17 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f'module forward B={B}: {ms:.3f} ms  ({B * 196 / ms / 1e3:.1f} M tokens/s)', flush=True)
+    from efficient_attention import _abi
+    q, k, v, _ = m._qkv_heads(x.reshape(B, 196, 384))
+    core = lambda: _abi.lara_forward(q, k, v, seq_shape=(14, 14), landmarks=49, per_token_proj=False, mixed=1, mis_type='mis-opt',
+                                     sample_mode=_abi.LARA_SAMPLE_SINGLE, zero_padded=False, alpha_coeff=1.0, proj=m._proj_params(True),
+                                     pad_mask=None, noise=None)
+    for _ in range(3): core()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20): core()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f'core only (lara_forward, q/k/v resident) B={B}: {ms:.3f} ms  ({B * 196 / ms / 1e3:.1f} M tokens/s, '
+          f'{B * 196 * 3072 / (ms * 1e-3) / 6469.3e9 * 100:.1f} % of the core HBM roofline)', flush=True)
     assert err < 3e-3, err
