@@ -39,7 +39,6 @@ constexpr int kComputeThreads = 128;
 constexpr uint32_t kTmemCols = 256;
 constexpr int kSlots = 4;
 constexpr int kSlotBytes = 16384;
-constexpr int kP2Split = 4;     // pass 2: chunk-rows [0, kP2Split) and [kP2Split, NR) are handed to the beta MMAs separately
 
 enum Bar {
   kFull0 = 0, kFree0 = kFull0 + kSlots, kPoolFull = kFree0 + kSlots, kAFull, kLinFull, kOmFull,
@@ -63,7 +62,9 @@ struct Params {
   int prefetch_v;                // warm L2 with v during pass 1
 };
 
-template <int W, int GW, int CH, int NR> struct Cfg {
+// G = chunk-rows per pass-1 / pass-2 tile: 1 on the 28-wide grid (112-token rows); 4 on the 14-wide grid, where a 28-token row
+// per TMA box would leave the kernel bound by the per-warp box issue rate (34 boxes per 196-token item)
+template <int W, int GW, int CH, int NR, int G> struct Cfg {
   static constexpr int L = W * W;
   static constexpr int LP8 = (L + 7) & ~7;
   static constexpr int LS = (L + 4) & ~3;       // bias row stride: 16-byte rows (LDS.128, conflict-free for stride 52); column L = row max
@@ -71,13 +72,22 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr int CN = NR * NCX;           // chunks per item
   static constexpr int CNP = 8 * NR;            // padded chunk index space: c' = 8 r + cx
   static constexpr int TOK = GW * CH;           // tokens per chunk-row
-  static constexpr int KS = (TOK + 15) / 16;    // k-steps over the tokens of a chunk-row
-  static constexpr int KBLK = (TOK + 63) / 64;  // 64-token K blocks of the Pool / P2 tiles
+  static constexpr int NT = (NR + G - 1) / G;   // tiles per operand and pass
+  static constexpr int TOKT = G * TOK;          // tokens per tile
+  static constexpr int CW = 8 * G;              // chunk columns (c' slots) per tile
+  static constexpr int D2N = CW < 16 ? 16 : CW; // N of the phi-logit MMA (M = 128 needs a multiple of 16)
+  static constexpr int KS = (TOKT + 15) / 16;   // k-steps over the tokens of a tile
+  static constexpr int KBLK = (TOKT + 63) / 64; // 64-token K blocks of the Pool / P2 tiles
+  static constexpr int kBlk = CW * 128;         // bytes of one 64-token block of a K-major [CW][TOKT] tile
+  static constexpr bool kSplitIssue = G == 1;   // pass-1 / pass-2 loads shared between the TMA and MMA warps (schedule written for NT = 7)
+  static constexpr int kP2Split = NT > 4 ? 4 : (NT + 1) / 2;   // pass 2: tiles [0, kP2Split) and the rest are handed to the beta MMAs separately
+  __host__ __device__ static constexpr int rows_in(int R) { return (R + 1) * G <= NR ? G : NR - R * G; }   // chunk-rows of tile R
   static constexpr int JC = CH * CH;
   static constexpr int kQOff = 64 - L, kKOff = LP8 - L;   // tile row of window a's first token in the q slot / the k, v slots
   static constexpr int kPairBytes = 2 * L * 128;
   static_assert(kQOff >= 0 && kQOff + 2 * L <= 128 && kKOff + 2 * L <= 2 * LP8, "stacked pair layout");
-  static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOK <= 128 && L <= 64 && CNP <= 64, "geometry");
+  static_assert(GW % CH == 0 && NCX <= 7 && NR <= 7 && TOKT <= 128 && L <= 64 && CNP <= 64 && CW <= 32, "geometry");
+  static_assert(G == 1 || NT * G * 8 <= 64, "tile columns");
   __host__ __device__ static constexpr bool chunk_ok(int c) { return c < CNP && (c & 7) < NCX; }
   // shared memory map (bytes from the 1024-aligned base)
   static constexpr int kSlot = 0;
@@ -87,14 +97,14 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   // Three things share [kOm, kLbuf), one after the other: the q_bar tile (until the phi-logit MMAs are done), the
   // NR softmax tiles P2 of pass 2 (until the beta MMAs are done), the output staging of phase B
   // (window a at +0, window b at +LP8*128, swizzled rows).
-  static constexpr int kP2 = kOm;                      // NR x KBLK x [8][128 B]
-  static constexpr int kP2Bytes = NR * KBLK * 1024;
+  static constexpr int kP2 = kOm;                      // NT x KBLK x [CW][128 B]
+  static constexpr int kP2Bytes = NT * KBLK * kBlk;
   static constexpr int kOStage = kOm;
   static constexpr int kOStageBytes = LP8 * 128 + L * 128;
   static constexpr int kShared = kP2Bytes > kOStageBytes ? (kP2Bytes > 8192 ? kP2Bytes : 8192) : (kOStageBytes > 8192 ? kOStageBytes : 8192);
-  static constexpr int kLbuf = (kOm + kShared + 1023) & ~1023;   // NR x [128] fp32 logit exchange
-  static constexpr int kPool = kLbuf + ((NR * 128 * 4 + 1023) & ~1023);   // KBLK x [8][128 B] pooling weights (constant)
-  static constexpr int kBias = kPool + KBLK * 1024;    // [L][LS] fp32, x log2(e)
+  static constexpr int kLbuf = (kOm + kShared + 1023) & ~1023;   // NT x [128] fp32 logit exchange
+  static constexpr int kPool = kLbuf + ((NT * 128 * 4 + 1023) & ~1023);   // KBLK x [CW][128 B] pooling weights (constant)
+  static constexpr int kBias = kPool + KBLK * kBlk;    // [L][LS] fp32, x log2(e)
   static constexpr int kBiasSlab = (L * LS * 4 + 15) & ~15;
   static constexpr int kZeroEnd = kBias + kBiasSlab;
   static constexpr int kLn = kZeroEnd;                 // [6][64] fp32: b_q, gain_q, beta_q, b_k, gain_k, beta_k
@@ -108,13 +118,13 @@ template <int W, int GW, int CH, int NR> struct Cfg {
   static constexpr uint32_t cPoolQ = 0, cPoolK = 56;   // pass 1: [feat x c']; stays clear of the X buffers
   static constexpr uint32_t cLin = 0;                  // Linear: [c' x 128]
   static constexpr uint32_t cBetaT = 0;                // pass 2: [feat x c']
-  static constexpr uint32_t cD2 = 128;                 // pass 2: NR x [token x 16]
-  static_assert(cD2 + 16 * NR <= 256, "TMEM budget (pass 2)");
+  static constexpr uint32_t cD2 = 128;                 // pass 2: NT x [token x D2N]
+  static_assert(cD2 + D2N * NT <= 256, "TMEM budget (pass 2)");
   // phase B: local logits / P in [0, 2*LP8); chunk logits of pair p and later its O share buffer X[p&1]
   static constexpr uint32_t cSloc = 0, cX0 = 2 * LP8, cPloc = 0, cPrfa = LP8;
   static_assert(2 * LP8 + 128 <= 256 && (2 * LP8) % 16 == 0, "TMEM budget");
-  // loads per item, in ring order: NR x (q_r, k_r) | means (borrowed) | W | NR x k_r | NR x v_r | pairs x (q, k, v)
-  static constexpr int nAt = 2 * NR, nW = 2 * NR + 1, nPass2 = 2 * NR + 2, nPairs = 4 * NR + 2;
+  // loads per item, in ring order: NT x (q_r, k_r) | means (borrowed) | W | NT x k_r | NT x v_r | pairs x (q, k, v)
+  static constexpr int nAt = 2 * NT, nW = 2 * NT + 1, nPass2 = 2 * NT + 2, nPairs = 4 * NT + 2;
 };
 
 template <typename T> struct IoFmt;
@@ -171,8 +181,8 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r) 
 __device__ __forceinline__ int tile_off(int row, int col) {
   return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
-// byte offset of 16-bit element (row n < 8, token t) in a K-major [8][TOK] tile made of 64-token blocks
-__device__ __forceinline__ int ktile_off(int n, int t) { return (t >> 6) * 1024 + tile_off(n, t & 63); }
+// byte offset of 16-bit element (row n, token t) in a K-major [rows][tokens] tile made of 64-token blocks of `blk` bytes (rows x 128)
+__device__ __forceinline__ int ktile_off(int n, int t, int blk) { return (t >> 6) * blk + tile_off(n, t & 63); }
 
 __device__ __forceinline__ uint32_t slot_of(uint32_t n) { return n & (kSlots - 1); }
 __device__ __forceinline__ uint32_t par_of(uint32_t n) { return (n >> 2) & 1u; }
@@ -193,14 +203,15 @@ template <bool kOn> struct Tracer {       // kOn = false (production instantiati
   }
 };
 
-template <typename T, int W, int GW, int CH, int NR, bool TR>
+template <typename T, int W, int GW, int CH, int NR, int G, bool TR>
 __global__ void __launch_bounds__(kThreads, 2)
 eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant__ CUtensorMap tw_k,
                  const __grid_constant__ CUtensorMap tw_v, const __grid_constant__ CUtensorMap tr_q,
                  const __grid_constant__ CUtensorMap tr_k, const __grid_constant__ CUtensorMap tr_v,
                  const __grid_constant__ CUtensorMap t_w, const __grid_constant__ CUtensorMap t_o, const Params p) {
-  using C = Cfg<W, GW, CH, NR>;
+  using C = Cfg<W, GW, CH, NR, G>;
   constexpr int L = C::L, LP8 = C::LP8, LS = C::LS, CN = C::CN, CNP = C::CNP, NCX = C::NCX, TOK = C::TOK, KS = C::KS;
+  constexpr int NT = C::NT, TOKT = C::TOKT, CW = C::CW;
   extern __shared__ uint8_t smem_raw[];
   // align by offset arithmetic (not by integer round trip) so the compiler keeps the shared address space
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -211,7 +222,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   uint8_t* P2t = sm + C::kP2;
   float* bias2 = reinterpret_cast<float*>(sm + C::kBias);
   float* lbuf = reinterpret_cast<float*>(sm + C::kLbuf);
-  static_assert(NR <= 7 && (NR & 1) == 1, "one kNormDone barrier per chunk-row; pass-2 issuer parity assumes odd NR");
+  static_assert(NT <= 7 && (!C::kSplitIssue || (NR & 1) == 1), "one kNormDone barrier per tile; the split pass-2 issue schedule assumes odd NR");
   const uint32_t bars = ptx::smem_u32(sm + C::kBars);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + C::kTmemPtr);
   auto bar = [&](int i) { return bars + 8u * i; };
@@ -229,8 +240,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
   // ---- one-time setup --------------------------------------------------------------------------
   for (int i = tid; i < C::kZeroEnd / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int t = tid; t < TOK; t += kThreads)   // Pool^T[n][t] = 1/Jc for the chunk column n that owns token t
-    *reinterpret_cast<uint16_t*>(PoolT + ktile_off((t % GW) / CH, t)) = IoFmt<T>::one(1.0f / C::JC);
+  for (int t = tid; t < TOKT; t += kThreads)   // Pool^T[n][t] = 1/Jc for the chunk column n = 8 (row in tile) + cx that owns token t
+    *reinterpret_cast<uint16_t*>(PoolT + ktile_off(8 * (t / TOK) + (t % GW) / CH, t, C::kBlk)) = IoFmt<T>::one(1.0f / C::JC);
   {
     float* ln = reinterpret_cast<float*>(sm + C::kLn);
     const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
@@ -257,7 +268,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     ptx::mbar_init(bar(kBiasFree), kComputeThreads);
     ptx::mbar_init(bar(kItem0), 1);
     ptx::mbar_init(bar(kItem1), 1);
-    for (int r = 0; r < NR; ++r) ptx::mbar_init(bar(kNormDone0 + r), kComputeThreads);
+    for (int r = 0; r < NT; ++r) ptx::mbar_init(bar(kNormDone0 + r), kComputeThreads);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tw_q); ptx::prefetch_tmap(&tw_k); ptx::prefetch_tmap(&tw_v);
     ptx::prefetch_tmap(&tr_q); ptx::prefetch_tmap(&tr_k); ptx::prefetch_tmap(&tr_v);
@@ -302,12 +313,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         int item_next = 0;                               // fetched now, needed in phase B: the atomic's latency hides under pass 1
         if (ni > 0 && lane == 0) item_next = (int)atomicAdd(p.next_item, 1u);
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {                   // pass 1: q chunk-rows (first touch: HBM) ...
-          uint32_t s = acquire(nb + 2 * r, TOK * 128);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
-          if (r < 2) {                                   // ... and the first two k rows: the MMA warp is still finishing the previous item
-            s = acquire(nb + 2 * r + 1, TOK * 128);
-            if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+        for (int r = 0; r < NT; ++r) {                   // pass 1: q tiles (first touch: HBM) ...
+          uint32_t s = acquire(nb + 2 * r, TOKT * 128);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_q, bar(kFull0 + s), 0, h, 0, r * CH * G, b, keep);
+          if (!C::kSplitIssue || r < 2) {                // ... and the first two k rows: the MMA warp is still finishing the previous item
+            s = acquire(nb + 2 * r + 1, TOKT * 128);
+            if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), &tr_k, bar(kFull0 + s), 0, h, 0, r * CH * G, b, keep);
           }
         }
         if (ni == 0) {
@@ -327,10 +338,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if (ptx::elect_one()) ptx::tma_load_2d(ptx::smem_u32(slot_ptr(s)), &t_w, bar(kFull0 + s), 0, 0);
         }
 #pragma unroll 1
-        for (int q = 0; q < 2 * NR; q += 2) {            // pass 2: K_0 .. K_{NR-1}, V_0 .. V_{NR-1}; this warp issues the even positions
-          const uint32_t s = acquire(nb + C::nPass2 + q, TOK * 128);
-          const bool is_k = q < NR;
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), is_k ? &tr_k : &tr_v, bar(kFull0 + s), 0, h, 0, (is_k ? q : q - NR) * CH, b, keep);
+        for (int q = 0; q < 2 * NT; q += C::kSplitIssue ? 2 : 1) {   // pass 2: K_0 .. K_{NT-1}, V_0 .. V_{NT-1}; split issue: the even positions
+          const uint32_t s = acquire(nb + C::nPass2 + q, TOKT * 128);
+          const bool is_k = q < NT;
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), is_k ? &tr_k : &tr_v, bar(kFull0 + s), 0, h, 0, (is_k ? q : q - NT) * CH * G, b, keep);
         }
         item_next = __shfl_sync(0xffffffffu, item_next, 0);
         publish(ni + 1, item_next);
@@ -362,9 +373,10 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     // =================================== MMA issuer ============================================
     {
       constexpr uint32_t fmt = IoFmt<T>::kUmma;
-      constexpr uint32_t id_pool = ptx::umma_idesc(fmt, fmt, 1, 0, 64, 8);      // A MN-major (feat), B K-major
+      constexpr uint32_t id_pool = ptx::umma_idesc(fmt, fmt, 1, 0, 64, CW);     // A MN-major (feat), B K-major; N = chunk columns of a full tile ...
+      constexpr uint32_t id_pool_last = ptx::umma_idesc(fmt, fmt, 1, 0, 64, 8 * C::rows_in(NT - 1));   // ... and of the last one
       constexpr uint32_t id_lin = ptx::umma_idesc(ptx::kFmtF16, ptx::kFmtF16, 0, 0, 128, 128);
-      constexpr uint32_t id_d2 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 16);
+      constexpr uint32_t id_d2 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, C::D2N);
       constexpr uint32_t id_sl = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 2 * LP8);
       constexpr uint32_t id_sr = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
       constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
@@ -373,8 +385,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       const uint64_t dKB = ptx::umma_desc_sw128(ptx::smem_u32(KBt)), dBT = ptx::umma_desc_sw128(ptx::smem_u32(BTt));
       const uint64_t dOM = ptx::umma_desc_sw128(ptx::smem_u32(OMt)), dPool = ptx::umma_desc_sw128(ptx::smem_u32(PoolT));
       const uint64_t dP2 = ptx::umma_desc_sw128(ptx::smem_u32(P2t));
-      // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [8][TOK]) 32 B inside a 64-token block
-      auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (1024 >> 4) + (ks & 3) * 2); };
+      // k-step ks over tokens: A (MN-major, rows = tokens) advances 16 rows; B (K-major [CW][TOKT]) 32 B inside a 64-token block
+      auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (C::kBlk >> 4) + (ks & 3) * 2); };
       uint32_t nb = 0, ni = 0, np = 0;
       Tracer<TR> tr{(p.trace && blockIdx.x == 0 && lane == 0) ? g_trace[1] : nullptr, 0};
       auto wait_full = [&](uint32_t n) { ptx::mbar_wait(bar(kFull0 + slot_of(n)), par_of(n)); tr(2000 + (int)(n - nb)); };
@@ -394,8 +406,8 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         if (item >= p.items) break;
         const int b = item / p.H, h = item % p.H;
         auto load_row = [&](uint32_t n, const CUtensorMap* tm, int r) {
-          const uint32_t s = acquire(n, TOK * 128);
-          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), tm, bar(kFull0 + s), 0, h, 0, r * CH, b, keep);
+          const uint32_t s = acquire(n, TOKT * 128);
+          if (ptx::elect_one()) ptx::tma_load_5d_hint(ptx::smem_u32(slot_ptr(s)), tm, bar(kFull0 + s), 0, h, 0, r * CH * G, b, keep);
         };
         auto load_v_pair = [&](int pr) {
           const uint32_t s = acquire(nb + C::nPairs + 3 * pr + 2, C::kPairBytes);
@@ -404,26 +416,29 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         // ---- pass 1: chunk means ------------------------------------------------------------
         tr(101);
         auto load_pass2 = [&](int q) {                        // relative position in pass 2: K_q (q < NR) or V_{q-NR}
-          load_row(nb + C::nPass2 + q, q < NR ? &tr_k : &tr_v, q < NR ? q : q - NR);
+          load_row(nb + C::nPass2 + q, q < NT ? &tr_k : &tr_v, q < NT ? q : q - NT);
         };
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {
+        for (int r = 0; r < NT; ++r) {
           const uint32_t nq = nb + 2 * r, nk = nq + 1;
           wait_full(nq);
           wait_full(nk);
           ptx::tc_fence_after();
+          const uint32_t idp = (G > 1 && r == NT - 1) ? id_pool_last : id_pool;
           if (ptx::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
-              ptx::umma_ss(tmem + C::cPoolQ + 8 * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+              ptx::umma_ss(tmem + C::cPoolQ + CW * r, dSlot(slot_of(nq)) + 128 * ks, dPool + tokB(ks), idp, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
-              ptx::umma_ss(tmem + C::cPoolK + 8 * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+              ptx::umma_ss(tmem + C::cPoolK + CW * r, dSlot(slot_of(nk)) + 128 * ks, dPool + tokB(ks), idp, ks > 0);
             free_raw(nq);
             free_raw(nk);
-            if (r == NR - 1) ptx::umma_commit(bar(kPoolFull));
+            if (r == NT - 1) ptx::umma_commit(bar(kPoolFull));
           }
-          if (r + 2 < NR) load_row(nk + 4, &tr_k, r + 2);      // same slot as k_r: waits for the MMAs just issued
+          if constexpr (C::kSplitIssue) {
+            if (r + 2 < NT) load_row(nk + 4, &tr_k, r + 2);    // same slot as k_r: waits for the MMAs just issued
+          }
         }
         tr(102);
         // ---- adaptive Linear: [q means ; k means] x [W_q ; W_k]^T (diagonal blocks used) ----------
@@ -444,56 +459,63 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           free_raw(nb + C::nAt);
         }
         tr(103);
-        load_pass2(1);                                        // slot of k_{NR-1}
-        load_pass2(3);                                        // slot of W: waits for the Linear MMA just issued
+        if constexpr (C::kSplitIssue) {
+          load_pass2(1);                                      // slot of k_{NR-1}
+          load_pass2(3);                                      // slot of W: waits for the Linear MMA just issued
+        }
         ptx::mbar_wait(bar(kOmFull), ni & 1);
         tr(104);      // q_bar / k_bar tiles written
         ptx::tc_fence_after();
         // ---- pass 2: phi-logits of every chunk-row, D2_r = K_r (Qbar_r + Kbar_r)^T ------------------------
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {
+        for (int r = 0; r < NT; ++r) {
           const uint32_t nk = nb + C::nPass2 + r;
           wait_full(nk);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              ptx::umma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, ks > 0);
+              ptx::umma_ss(tmem + C::cD2 + C::D2N * r, dSlot(slot_of(nk)) + 2 * ks, dOM + (uint64_t)(r * (C::kBlk >> 4)) + 2 * ks, id_d2, ks > 0);
             if (p.has_q) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                ptx::umma_ss(tmem + C::cD2 + 16 * r, dSlot(slot_of(nk)) + 2 * ks, dKB + (uint64_t)(r * (1024 >> 4)) + 2 * ks, id_d2, 1);
+                ptx::umma_ss(tmem + C::cD2 + C::D2N * r, dSlot(slot_of(nk)) + 2 * ks, dKB + (uint64_t)(r * (C::kBlk >> 4)) + 2 * ks, id_d2, 1);
             }
           }
           // the compute warps take |k|^2 from the same tile: hand it back when both are done
           ptx::mbar_wait(bar(kNormDone0 + r), ni & 1);
           if (ptx::elect_one()) {
             free_raw(nk);
-            if (r == NR - 1) ptx::umma_commit(bar(kD2Full));
+            if (r == NT - 1) ptx::umma_commit(bar(kD2Full));
           }
-          if (r & 1) load_pass2(r + 4);                     // odd positions are this warp's: K_5, V_0, V_2 for NR = 7
+          if constexpr (C::kSplitIssue) {
+            if (r & 1) load_pass2(r + 4);                   // odd positions are this warp's: K_5, V_0, V_2 for NR = 7
+          }
         }
         tr(110);
         // ---- beta^T += V_r^T P_r^T once the softmax batch is in shared memory ----------------------------
         ptx::mbar_wait(bar(kP2Full), ni & 1);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {
-          if (r == kP2Split) { ptx::mbar_wait(bar(kP2FullB), ni & 1); ptx::tc_fence_after(); }
-          const uint32_t nv = nb + C::nPass2 + NR + r;
+        for (int r = 0; r < NT; ++r) {
+          if (r == C::kP2Split) { ptx::mbar_wait(bar(kP2FullB), ni & 1); ptx::tc_fence_after(); }
+          const uint32_t nv = nb + C::nPass2 + NT + r;
           wait_full(nv);
           ptx::tc_fence_after();
+          const uint32_t idp = (G > 1 && r == NT - 1) ? id_pool_last : id_pool;
           if (ptx::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
-              ptx::umma_ss(tmem + C::cBetaT + 8 * r, dSlot(slot_of(nv)) + 128 * ks,
-                           dP2 + (uint64_t)(r * C::KBLK * (1024 >> 4)) + tokB(ks), id_pool, ks > 0);
+              ptx::umma_ss(tmem + C::cBetaT + CW * r, dSlot(slot_of(nv)) + 128 * ks,
+                           dP2 + (uint64_t)(r * C::KBLK * (C::kBlk >> 4)) + tokB(ks), idp, ks > 0);
             free_raw(nv);
-            if (r == NR - 1) ptx::umma_commit(bar(kBetaFull));
+            if (r == NT - 1) ptx::umma_commit(bar(kBetaFull));
           }
-          if ((r & 1) == 0 && r + 4 < NR) load_pass2(NR + r + 4);   // V_4, V_6
+          if constexpr (C::kSplitIssue) {
+            if ((r & 1) == 0 && r + 4 < NT) load_pass2(NT + r + 4);   // V_4, V_6
+          }
         }
-        load_v_pair(0);                                      // slot of V_{NR-2}
+        load_v_pair(0);                                      // slot of V_{NT-2}
         tr(111);
         ptx::mbar_wait(bar(kStatsFull), ni & 1);
         tr(120);
@@ -554,9 +576,9 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
     // pass 1 / beta readback: lanes 0-15 of each warp hold feature 16*warp + lane of an M=64 accumulator
     const int feat = 16 * warp + (lane & 15);
     const bool feat_lane = lane < 16;
-    // pass 2: token of the chunk-row owned by this thread
+    // pass 2: token of the tile owned by this thread: chunk-row trr inside the tile, chunk column tcx
     const int tcx = (tid % GW) / CH;
-    const bool tok_ok = tid < TOK;
+    const int trr = G > 1 ? tid / TOK : 0;
     uint32_t nb = 0, ni = 0, np_s = 0, np_e = 0;
     uint8_t* const ostage = sm + C::kOStage;
     const uint64_t out_policy = ptx::policy_evict_first();
@@ -665,12 +687,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       tr(5);
       // ---- pass 2: |k|^2 of my token in every chunk-row while the rows stream through the ring ---------
 #pragma unroll 1
-      for (int r = 0; r < NR; ++r) {          // rolled (instruction-cache footprint); |k|^2 waits in the logit exchange buffer
+      for (int r = 0; r < NT; ++r) {          // rolled (instruction-cache footprint); |k|^2 waits in the logit exchange buffer
         const uint32_t nk = nb + C::nPass2 + r;
         const uint8_t* Kr = slot_ptr(slot_of(nk));
         ptx::mbar_wait(bar(kFull0 + slot_of(nk)), par_of(nk));
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (tok_ok) {
+        if (tid < C::rows_in(r) * TOK) {
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             const uint4 raw = *reinterpret_cast<const uint4*>(Kr + tid * 128 + ((ch ^ (tid & 7)) << 4));
@@ -690,16 +712,24 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
       {
         const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
         {
-          uint32_t dd[NR][8];
+          uint32_t dd[NT][CW];
 #pragma unroll
-          for (int r = 0; r < NR; ++r) ptx::tmem_ld8(trow + C::cD2 + 16 * r, dd[r]);
+          for (int r = 0; r < NT; ++r) tmem_ld_cols<CW>(trow + C::cD2 + C::D2N * r, dd[r]);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            float dsel = __uint_as_float(dd[r][0]);
+          for (int r = 0; r < NT; ++r) {
+            uint32_t d8[8];                    // the 8 chunk columns of my chunk-row inside the tile
 #pragma unroll
-            for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? __uint_as_float(dd[r][c]) : dsel;
-            lbuf[r * 128 + tid] = tok_ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * lbuf[r * 128 + tid]) : kNegInf;   // log2 units
+            for (int c = 0; c < 8; ++c) {
+              d8[c] = dd[r][c];
+#pragma unroll
+              for (int g = 1; g < G; ++g) d8[c] = (trr == g) ? dd[r][8 * g + c] : d8[c];
+            }
+            float dsel = __uint_as_float(d8[0]);
+#pragma unroll
+            for (int c = 1; c < NCX; ++c) dsel = (tcx == c) ? __uint_as_float(d8[c]) : dsel;
+            const bool ok = tid < C::rows_in(r) * TOK;
+            lbuf[r * 128 + tid] = ok ? scale_log2 * fmaf(dcoef, dsel, -0.5f * lbuf[r * 128 + tid]) : kNegInf;   // log2 units
           }
         }
         // the q_bar tile is dead (every phi-logit MMA has completed): clear the P2 tiles that overlay it
@@ -707,12 +737,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         tr(12);
         ptx::named_bar_sync(1, kComputeThreads);
         tr(13);
-        const int t0 = tok_ok ? tcx * CH : 0;
+        const int t0 = tid < TOKT ? trr * CH * GW + tcx * CH : 0;   // first token of my chunk inside the tile
         // two sub-batches: the beta MMAs of the first rows (and with them the hand-back of their V slots, i.e. the
         // request of the last V rows) start while the softmax of the remaining rows is still being computed
 #pragma unroll 1
-        for (int r = 0; r < NR; ++r) {                       // not unrolled: instruction-cache footprint
-          if (r == kP2Split) {
+        for (int r = 0; r < NT; ++r) {                       // not unrolled: instruction-cache footprint
+          if (r == C::kP2Split) {
             ptx::fence_proxy_async_smem();
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar(kP2Full));
@@ -739,7 +769,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 #pragma unroll
           for (int j = 0; j < CH * CH; j += 2) { sum0 += ex2(lv[j] - mx); sum1 += ex2(lv[j + 1] - mx); }
           const float pt = __fdividef(ex2(lb_[tid] - mx), sum0 + sum1);
-          if (tok_ok) *reinterpret_cast<uint16_t*>(P2t + r * C::KBLK * 1024 + ktile_off(tcx, tid)) = IoFmt<T>::one(pt);
+          if (tid < C::rows_in(r) * TOK) *reinterpret_cast<uint16_t*>(P2t + r * C::KBLK * C::kBlk + ktile_off(8 * trr + tcx, tid, C::kBlk)) = IoFmt<T>::one(pt);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -1018,11 +1048,11 @@ static int sm_count() {
   return n > 0 ? n : 148;
 }
 
-template <typename T, int W, int GW, int CH, int NR>
+template <typename T, int W, int GW, int CH, int NR, int G>
 static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
                             const float* noise, const float* bias, long long bias_sh, void* out, void* workspace,
                             cudaStream_t st, const char** msg) {
-  using C = Cfg<W, GW, CH, NR>;
+  using C = Cfg<W, GW, CH, NR, G>;
   constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
   __half* w16 = reinterpret_cast<__half*>(workspace);
   float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 128 * 64 * sizeof(__half));
@@ -1037,7 +1067,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   View ov;
   ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
   if (!make_box_map(&twq, q, g, io, W, 2 * W) || !make_box_map(&twk, k, g, io, W, 2 * W) || !make_box_map(&twv, v, g, io, W, 2 * W) ||
-      !make_box_map(&trq, q, g, io, GW, CH) || !make_box_map(&trk, k, g, io, GW, CH) || !make_box_map(&trv, v, g, io, GW, CH) ||
+      !make_box_map(&trq, q, g, io, GW, CH * G) || !make_box_map(&trk, k, g, io, GW, CH * G) || !make_box_map(&trv, v, g, io, GW, CH * G) ||
       !make_weight_map(&tw, w16) || !make_box_map(&to, ov, g, io, W, 2 * W)) {
     *msg = "cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
@@ -1054,7 +1084,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.trace = trace_enabled();
   p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", 0);   // measured: warming L2 with the next item's rows no longer pays (0.5 % slower)
   p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
-  auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, true> : eva_fused_kernel<T, W, GW, CH, NR, false>;
+  auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, G, true> : eva_fused_kernel<T, W, GW, CH, NR, G, false>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
   cudaLaunchConfig_t cfg{};
@@ -1082,6 +1112,8 @@ static bool fused_disabled() {
 
 // geometry families the fused kernel is instantiated for: window 7, 49 chunks on a 28-wide (chunk 4) or
 // 14-wide (chunk 2) grid -- DeiT-tiny/small p8 and p16 (BASELINE configs c2, c3)
+// chunk-rows per pass-1 / pass-2 tile on the 14-wide grid (see Cfg): 2 keeps the P2 / pooling tiles inside the 113 KB a CTA may use
+constexpr int kG14 = 2;
 static int fused_variant(const Geo& g) {
   if (g.window != 7 || g.n_chunks != 49) return 0;
   if (g.gw == 28 && g.gh == 28 && g.chunk == 4) return 1;
@@ -1119,11 +1151,11 @@ cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& 
                          void* out, void* workspace, cudaStream_t st, const char** msg) {
   const int var = fused_variant(g);
   if (io_dtype == EVA_F16) {
-    if (var == 1) return fused::launch_t<__half, 7, 28, 4, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
-    return fused::launch_t<__half, 7, 14, 2, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+    if (var == 1) return fused::launch_t<__half, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+    return fused::launch_t<__half, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
   }
-  if (var == 1) return fused::launch_t<__nv_bfloat16, 7, 28, 4, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
-  return fused::launch_t<__nv_bfloat16, 7, 14, 2, 7>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  if (var == 1) return fused::launch_t<__nv_bfloat16, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  return fused::launch_t<__nv_bfloat16, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
 }
 
 }  // namespace eva
