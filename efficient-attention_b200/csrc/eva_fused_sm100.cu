@@ -1112,7 +1112,9 @@ static bool fused_disabled() {
 
 // geometry families the fused kernel is instantiated for: window 7, 49 chunks on a 28-wide (chunk 4) or
 // 14-wide (chunk 2) grid -- DeiT-tiny/small p8 and p16 (BASELINE configs c2, c3)
-// chunk-rows per pass-1 / pass-2 tile on the 14-wide grid (see Cfg): 2 keeps the P2 / pooling tiles inside the 113 KB a CTA may use
+// chunk-rows per pass-1 / pass-2 tile on the 14-wide grid (see Cfg): 2 keeps the P2 / pooling tiles inside the 113 KB a CTA may use.
+// G = 4 (one 112-token box per 4 rows) measured 0.24 ms against 0.28 ms for c2, but its [32][112] P2 / pooling tiles need 4.8 KB
+// more than there is: 15 KB ring slots cannot hold the 16 KB [W_q ; W_k] tile (tried: the overflow corrupts the next slot)
 constexpr int kG14 = 2;
 static int fused_variant(const Geo& g) {
   if (g.window != 7 || g.n_chunks != 49) return 0;
