@@ -12,10 +12,20 @@ class HostPipeline:
 
     module: any nn.Module on a CUDA device whose forward maps [B, ...] -> [B, ...] batch-wise.
     chunk:  images per stage; depth: device-side buffers per stage (2 = double buffering).
+    defer_join: by default the caller's stream waits for the last D2H copy before `pipe(...)` returns control of the stream,
+        so consecutive calls are serialised (the next batch's first H2D copy cannot overlap this batch's last D2H copies:
+        one stage of fill / drain per call).  With `defer_join=True` the call only records `pipe.done` on the copy-out
+        stream; a serving loop that alternates two (x_host, y_host) buffer pairs can then overlap batches at their
+        boundaries and calls `pipe.join()` (stream-side wait) or `pipe.done.synchronize()` (host-side wait) before it
+        reads a result.  Measured on B200 (tools/e2e_sweep.py): 6.7 ms per 1024-image step against 7.4 ms in the best runs
+        (92 % of the duplex PCIe bound), but 8.7-10.6 ms in others (allocator / stream-ordering effects not understood yet),
+        so bench.py keeps the default.
     """
 
-    def __init__(self, module, chunk, depth=2, use_graphs=False):
+    def __init__(self, module, chunk, depth=2, use_graphs=False, defer_join=False):
         self.module = module
+        self.defer_join = bool(defer_join)
+        self.done = None
         self.chunk = int(chunk)
         self.depth = int(depth)
         # optional: one CUDA graph per buffer slot replays the module forward (a dozen launches + their host-side set-up) in one
@@ -47,6 +57,7 @@ class HostPipeline:
             s = c % self.depth
             if self._x[s] is None or self._x[s].shape[0] < hi - lo or self._x[s].dtype != x_host.dtype:
                 self._x[s] = torch.empty((self.chunk,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=self.device)
+                self._x[s].record_stream(self.s_in)       # written on the copy-in stream: the allocator must not recycle it early if the pipeline is dropped
             xd = self._x[s][:hi - lo]
             with torch.cuda.stream(self.s_in):
                 if self._ev_x_free[s] is not None:
@@ -69,8 +80,16 @@ class HostPipeline:
                 if self.use_graphs and hi - lo == self.chunk:
                     self._ev_y_free[s] = torch.cuda.Event()
                     self._ev_y_free[s].record(self.s_out)
-        main.wait_stream(self.s_out)
+        self.done = torch.cuda.Event()
+        self.done.record(self.s_out)
+        if not self.defer_join:
+            main.wait_event(self.done)
         return y_host
+
+    def join(self):
+        """Make the current stream wait for the copies of the most recent call (needed with `defer_join=True`)."""
+        if self.done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done)
 
     def _replay(self, s, xd):
         """Forward of slot s through its CUDA graph (captured on first use; x / y buffers of a slot are static)."""

@@ -246,6 +246,19 @@ def test_host_pipeline_matches_direct_forward():
     with torch.no_grad():
         want = m(x_host.to(_dev())).cpu()
     assert torch.equal(y_host, want)
+    # deferred join: two batches in flight over two host buffer pairs, host-side wait on pipe.done
+    pipe2 = HostPipeline(m, chunk=16, defer_join=True)
+    xs = [x_host, (x_host * 0.5).pin_memory()]
+    ys = [torch.empty_like(x_host).pin_memory() for _ in range(2)]
+    events = []
+    for i in range(4):
+        pipe2(xs[i & 1], ys[i & 1])
+        events.append(pipe2.done)
+    for e in events:
+        e.synchronize()
+    with torch.no_grad():
+        want2 = m(xs[1].to(_dev())).cpu()
+    assert torch.equal(ys[0], want) and torch.equal(ys[1], want2)
 
 
 @pytest.mark.parametrize('grid,chunk', [(14, 2), (28, 4)])

@@ -22,7 +22,16 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5): duplex()
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
 print(f'raw duplex copy of one step: {dt * 1e3:.2f} ms  ({x_host.numel() * 2 / dt / 1e9:.1f} GB/s each way)  -> bound {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
-for n_chunks, depth, graphs in ((8, 2, False), (8, 2, True), (16, 2, True), (16, 3, True), (32, 2, True), (32, 3, True), (64, 3, True)):
+x2 = x_host.clone().pin_memory(); y2 = torch.empty_like(x_host).pin_memory()
+for n_chunks, depth, defer, two in ((8, 2, False, False), (8, 2, True, False), (8, 2, True, True), (8, 3, True, True), (16, 2, False, False), (16, 3, True, True), (4, 2, False, False), (4, 2, True, True)):
+    pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth, defer_join=defer)
+    xs, ys = ([x_host, x2], [y_host, y2]) if two else ([x_host, x_host], [y_host, y_host])
+    for i in range(3): pipe(xs[i & 1], ys[i & 1])
+    pipe.join(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for i in range(8): pipe(xs[i & 1], ys[i & 1])
+    pipe.join(); torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 8
+    print(f'chunks {n_chunks:2d} depth {depth} defer_join {defer} two buffer pairs {two}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
+for n_chunks, depth, graphs in ((8, 2, False),):
     if True:
         pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth, use_graphs=graphs)
         for _ in range(3): pipe(x_host, y_host)
