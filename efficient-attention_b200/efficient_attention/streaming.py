@@ -17,9 +17,8 @@ class HostPipeline:
         one stage of fill / drain per call).  With `defer_join=True` the call only records `pipe.done` on the copy-out
         stream; a serving loop that alternates two (x_host, y_host) buffer pairs can then overlap batches at their
         boundaries and calls `pipe.join()` (stream-side wait) or `pipe.done.synchronize()` (host-side wait) before it
-        reads a result.  Measured on B200 (tools/e2e_sweep.py): 6.7 ms per 1024-image step against 7.4 ms in the best runs
-        (92 % of the duplex PCIe bound), but 8.7-10.6 ms in others (allocator / stream-ordering effects not understood yet),
-        so bench.py keeps the default.
+        reads a result.  Measured on B200 (tools/e2e_sweep.py): 6.7 ms per 1024-image step against 7.3 ms (92 % of the
+        duplex PCIe bound).
     """
 
     def __init__(self, module, chunk, depth=2, use_graphs=False, defer_join=False):
@@ -34,6 +33,7 @@ class HostPipeline:
         self.use_graphs = bool(use_graphs)
         self._graphs = [None] * self.depth
         self._y = [None] * self.depth
+        self._ys = [None] * self.depth
         self._ev_y_free = [None] * self.depth
         p = next(module.parameters())
         self.device = p.device
@@ -50,14 +50,19 @@ class HostPipeline:
         assert x_host.is_pinned() and y_host.is_pinned(), 'HostPipeline needs pinned host tensors'
         B = x_host.shape[0]
         main = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(main)
         n_chunks = (B + self.chunk - 1) // self.chunk
+        # All input staging buffers exist BEFORE the copy-in stream synchronises with the compute stream: a block the allocator
+        # hands out may still be in use by kernels queued on the compute stream (it recycles in stream order), and the copy-in
+        # stream only knows about work queued before the wait below.  (Allocating inside the loop let the H2D copy of chunk 1
+        # overwrite a block that the forward of chunk 0 had just released: wrong results on a pipeline's first call.)
+        for s in range(min(self.depth, n_chunks)):
+            if (self._x[s] is None or self._x[s].shape[1:] != x_host.shape[1:] or self._x[s].dtype != x_host.dtype):
+                self._x[s] = torch.empty((self.chunk,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=self.device)
+                self._x[s].record_stream(self.s_in)       # written on the copy-in stream: not to be recycled early if the pipeline is dropped
+        self.s_in.wait_stream(main)
         for c in range(n_chunks):
             lo, hi = c * self.chunk, min(B, (c + 1) * self.chunk)
             s = c % self.depth
-            if self._x[s] is None or self._x[s].shape[0] < hi - lo or self._x[s].dtype != x_host.dtype:
-                self._x[s] = torch.empty((self.chunk,) + tuple(x_host.shape[1:]), dtype=x_host.dtype, device=self.device)
-                self._x[s].record_stream(self.s_in)       # written on the copy-in stream: the allocator must not recycle it early if the pipeline is dropped
             xd = self._x[s][:hi - lo]
             with torch.cuda.stream(self.s_in):
                 if self._ev_x_free[s] is not None:
@@ -70,16 +75,26 @@ class HostPipeline:
                     main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
                 y = self._replay(s, xd)
             else:
-                y = self.module(xd)
+                # The module's output is a fresh tensor of the caching allocator.  Handing it to the copy-out stream directly
+                # (record_stream) makes the allocator hold the block until that stream has passed it, and with several
+                # chunks in flight it keeps growing the pool (cudaMalloc inside the timed loop).  One device-to-device copy
+                # into a persistent per-slot buffer (0.1 ms per 1024-image step) keeps all allocation on the compute stream.
+                y_mod = self.module(xd)
+                if self._ys[s] is None or self._ys[s].shape[1:] != y_mod.shape[1:] or self._ys[s].dtype != y_mod.dtype:
+                    self._ys[s] = torch.empty((self.chunk,) + tuple(y_mod.shape[1:]), dtype=y_mod.dtype, device=self.device)
+                    self._ys[s].record_stream(self.s_out)
+                if self._ev_y_free[s] is not None:
+                    main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
+                y = self._ys[s][:hi - lo]
+                y.copy_(y_mod)
+                del y_mod
             self._ev_comp[s].record(main)
             self._ev_x_free[s] = self._ev_comp[s]
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self._ev_comp[s])
-                y.record_stream(self.s_out)
                 y_host[lo:hi].copy_(y, non_blocking=True)
-                if self.use_graphs and hi - lo == self.chunk:
-                    self._ev_y_free[s] = torch.cuda.Event()
-                    self._ev_y_free[s].record(self.s_out)
+                self._ev_y_free[s] = torch.cuda.Event()
+                self._ev_y_free[s].record(self.s_out)
         self.done = torch.cuda.Event()
         self.done.record(self.s_out)
         if not self.defer_join:

@@ -261,6 +261,27 @@ def test_host_pipeline_matches_direct_forward():
     assert torch.equal(ys[0], want) and torch.equal(ys[1], want2)
 
 
+def test_host_pipeline_first_call_after_other_work():
+    """A pipeline's FIRST call allocates its staging buffers while the compute stream is busy: blocks recycled by the caching
+    allocator must not be overwritten by the copy-in stream before the kernels that still use them have run (regression: the
+    H2D copy of chunk 1 used to land in a block the forward of chunk 0 had just released)."""
+    from efficient_attention.streaming import HostPipeline
+    m = _bench_layer(torch.float16)
+    torch.manual_seed(9)
+    B = 384
+    x_host = torch.randn(B, 28, 28, 192).half().pin_memory()
+    y_host = torch.empty_like(x_host).pin_memory()
+    with torch.no_grad():
+        want = m(x_host.to(_dev())).cpu()
+    for trial in range(4):
+        with torch.no_grad():
+            for _ in range(2):
+                m(x_host[:96 * (trial + 1)].to(_dev()))      # leaves freed blocks of various sizes behind, kernels still queued
+        HostPipeline(m, chunk=48)(x_host, y_host)              # dropped right after the call
+        torch.cuda.synchronize()
+        assert torch.equal(y_host, want), trial
+
+
 @pytest.mark.parametrize('grid,chunk', [(14, 2), (28, 4)])
 @pytest.mark.parametrize('adaptive', ['default', 'no-ln', 'none'])
 @pytest.mark.parametrize('with_noise,with_bias', [(False, True), (True, False), (True, True)])

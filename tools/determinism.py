@@ -38,3 +38,15 @@ with torch.no_grad():
         pipe(x_host, y_host); torch.cuda.synchronize()
         bad += 0 if torch.equal(y_host, y1) else 1
     print(f'pipeline: {bad} of 5 repeats differ; equals direct module forward: {torch.equal(y1, yref.cpu())}', flush=True)
+    # a short-lived pipeline object (dropped while its copies are still in flight) must give the same bits
+    for trial in range(3):
+        HostPipeline(layer, chunk=B // 8)(x_host, y_host)
+        torch.cuda.synchronize()
+        neq = (y_host != y1)
+        print(f'temporary pipeline {trial}: {int(neq.sum())} elements differ in images {neq.view(B, -1).any(1).nonzero().flatten().tolist()[:12]}, '
+              f'max abs diff {float((y_host.float() - y1.float()).abs().max()):.3e}, nan {int(torch.isnan(y_host).sum())}', flush=True)
+    for seed in range(6):
+        torch.manual_seed(100 + seed)
+        xs = torch.randn(B, 28, 28, 192).half().to(dev)
+        ys = layer(xs)
+        print(f'seed {100 + seed}: nan {int(torch.isnan(ys).sum())} inf {int(torch.isinf(ys).sum())} max |y| {float(ys.float().abs().max()):.3f}', flush=True)

@@ -42,4 +42,10 @@ for n_chunks, depth, graphs in ((8, 2, False),):
         HostPipeline(layer, chunk=B // 8, use_graphs=False)(x_host, y_host)
         torch.cuda.synchronize()
         same = bool((y1 == y_host).all())
+        with torch.no_grad():
+            want = layer(x_host.to(dev)).cpu()
+        neq = (y1 != y_host)
+        print(f'   differing elements {int(neq.sum())} in images {neq.view(B, -1).any(1).nonzero().flatten().tolist()[:10]}; '
+              f'loop result == direct forward: {torch.equal(y1, want)}; fresh pipeline == direct forward: {torch.equal(y_host, want)}; '
+              f'max |diff| {float((y1.float() - y_host.float()).abs().max()):.3e}', flush=True)
         print(f'chunks {n_chunks:2d} depth {depth} graphs {graphs}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s  identical to eager: {same}', flush=True)
