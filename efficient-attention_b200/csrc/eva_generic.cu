@@ -144,18 +144,44 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
   const int t0 = c * g.chunk;
   const float scale = 0.125f;
   // ---- phase 1 ----
-  float sq0 = 0.f, sq1 = 0.f, sk0 = 0.f, sk1 = 0.f;
+  if constexpr (sizeof(T) == 2) {
+    // 16-byte loads: 8 lanes cover one 128-byte row, a warp covers 4 tokens per instruction (4x the bytes in flight of the
+    // 4-byte-per-lane version); lane = (token sub-index ts, 16-byte piece p8)
+    const int ts = lane >> 3, p8 = lane & 7;
+    float sq[8], sk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sq[i] = 0.f; sk[i] = 0.f; }
+#pragma unroll 2
+    for (int s = 4 * warp + ts; s < g.Jc; s += 32) {
+      const uint4 rq = __ldg(reinterpret_cast<const uint4*>(q.row<T>(b, t0 + s, h)) + p8);
+      const uint4 rk = __ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t0 + s, h)) + p8);
+      const T* eq = reinterpret_cast<const T*>(&rq);
+      const T* ek = reinterpret_cast<const T*>(&rk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sq[i] += to_f32(eq[i]); sk[i] += to_f32(ek[i]); }
+      if (stage_k) *reinterpret_cast<uint4*>(kst + s * kKs + p8 * 16) = rk;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], 8);  sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], 16);
+      sk[i] += __shfl_xor_sync(0xffffffffu, sk[i], 8);  sk[i] += __shfl_xor_sync(0xffffffffu, sk[i], 16);
+    }
+    if (ts == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { part[warp * 128 + 8 * p8 + i] = sq[i]; part[warp * 128 + 64 + 8 * p8 + i] = sk[i]; }
+    }
+  } else {
+    float sq0 = 0.f, sq1 = 0.f, sk0 = 0.f, sk1 = 0.f;
 #pragma unroll 4
-  for (int s = warp; s < g.Jc; s += 8) {
-    const T* qr = q.row<T>(b, t0 + s, h);
-    const T* kr = k.row<T>(b, t0 + s, h);
-    const T k0 = kr[2 * lane], k1 = kr[2 * lane + 1];
-    sq0 += to_f32(qr[2 * lane]); sq1 += to_f32(qr[2 * lane + 1]);
-    sk0 += to_f32(k0); sk1 += to_f32(k1);
-    if (stage_k) { T* dst = reinterpret_cast<T*>(kst + s * kKs); dst[2 * lane] = k0; dst[2 * lane + 1] = k1; }
+    for (int s = warp; s < g.Jc; s += 8) {
+      const T* qr = q.row<T>(b, t0 + s, h);
+      const T* kr = k.row<T>(b, t0 + s, h);
+      sq0 += to_f32(qr[2 * lane]); sq1 += to_f32(qr[2 * lane + 1]);
+      sk0 += to_f32(kr[2 * lane]); sk1 += to_f32(kr[2 * lane + 1]);
+    }
+    part[warp * 128 + 2 * lane] = sq0; part[warp * 128 + 2 * lane + 1] = sq1;
+    part[warp * 128 + 64 + 2 * lane] = sk0; part[warp * 128 + 64 + 2 * lane + 1] = sk1;
   }
-  part[warp * 128 + 2 * lane] = sq0; part[warp * 128 + 2 * lane + 1] = sq1;
-  part[warp * 128 + 64 + 2 * lane] = sk0; part[warp * 128 + 64 + 2 * lane + 1] = sk1;
   __syncthreads();
   if (tid < 128) {
     float a = 0.f;
@@ -254,15 +280,39 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += red[8 + w];
   // ---- phase 4 ----
-  float b0 = 0.f, b1 = 0.f;
-  for (int s = warp; s < g.Jc; s += 8) {
-    const T* vr = v.row<T>(b, t0 + s, h);
-    const float pe = pj[s];
-    b0 = fmaf(pe, to_f32(vr[2 * lane]), b0);
-    b1 = fmaf(pe, to_f32(vr[2 * lane + 1]), b1);
+  if constexpr (sizeof(T) == 2) {
+    const int ts = lane >> 3, p8 = lane & 7;
+    float bacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bacc[i] = 0.f;
+#pragma unroll 2
+    for (int s = 4 * warp + ts; s < g.Jc; s += 32) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(v.row<T>(b, t0 + s, h)) + p8);
+      const T* ev = reinterpret_cast<const T*>(&rv);
+      const float pe = pj[s];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bacc[i] = fmaf(pe, to_f32(ev[i]), bacc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bacc[i] += __shfl_xor_sync(0xffffffffu, bacc[i], 8);
+      bacc[i] += __shfl_xor_sync(0xffffffffu, bacc[i], 16);
+    }
+    if (ts == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[warp * 64 + 8 * p8 + i] = bacc[i];
+    }
+  } else {
+    float b0 = 0.f, b1 = 0.f;
+    for (int s = warp; s < g.Jc; s += 8) {
+      const T* vr = v.row<T>(b, t0 + s, h);
+      const float pe = pj[s];
+      b0 = fmaf(pe, to_f32(vr[2 * lane]), b0);
+      b1 = fmaf(pe, to_f32(vr[2 * lane + 1]), b1);
+    }
+    part[warp * 64 + 2 * lane] = b0;
+    part[warp * 64 + 2 * lane + 1] = b1;
   }
-  part[warp * 64 + 2 * lane] = b0;
-  part[warp * 64 + 2 * lane + 1] = b1;
   __syncthreads();
   if (tid < 64) {
     float a = 0.f;
