@@ -143,3 +143,33 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in src.replace('SURVEY', ''), os.path.join(dirpath, f)
+
+
+def test_memo_follows_parameter_updates():
+    """_abi.memo caches tensors derived from parameters per module; the entry must be rebuilt after an in-place update
+    (optimizer step, load_state_dict), after the parameter's storage was replaced (.data = ..., .to()), and must not be
+    shared between modules."""
+    lin = torch.nn.Linear(4, 4)
+    calls = []
+
+    def build():
+        calls.append(1)
+        return lin.weight.detach().double().clone()
+
+    a = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    b = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert a is b and len(calls) == 1
+    with torch.no_grad():
+        lin.weight.mul_(2.0)                                     # in place: version counter changes
+    c = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert len(calls) == 2 and torch.equal(c, lin.weight.detach().double())
+    lin.weight.data = torch.ones(4, 4)                           # storage replaced
+    d = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert len(calls) == 3 and torch.equal(d, torch.ones(4, 4, dtype=torch.float64))
+    lin.load_state_dict({'weight': torch.zeros(4, 4), 'bias': torch.zeros(4)})
+    e = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert len(calls) == 4 and float(e.abs().sum()) == 0.0
+    other = torch.nn.Linear(4, 4)
+    _abi.memo(other, 'w64', (other.weight,), lambda: calls.append(1) or other.weight.detach().clone())
+    assert len(calls) == 5 and '_sm100_memo' in other.__dict__ and '_sm100_memo' not in dict(other.named_buffers())
+    assert 'w64' not in lin.state_dict() and all(not k.startswith('_sm100') for k in lin.state_dict())
