@@ -6,6 +6,7 @@ or eager fallback: if the library is missing or a tensor is not on a CUDA device
 import ctypes
 import os
 import threading
+import weakref
 
 import torch
 
@@ -115,15 +116,22 @@ def _f32(t):
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
 
+# module -> {tag: (key, value)}; weak keys: the cache dies with the module and stays out of its __dict__ (the values hold ctypes
+# structures with raw pointers, which copy.deepcopy / pickle of a module -- timm's ModelEma, torch.save(model) -- must never see)
+_MEMO = weakref.WeakKeyDictionary()
+
+
 def memo(owner, tag, sources, build):
     """Per-module cache of tensors derived from parameters (fp32 copies, gathered bias tables, fused weights).
 
     Rebuilt whenever a source tensor was modified in place (optimizer step, load_state_dict: `_version` changes) or replaced
-    (`.to()`, `.half()`: storage / dtype / device change); the cache lives in the module and dies with it.  Saves a dozen tiny
+    (`.to()`, `.half()`: storage / dtype / device change); the cache is keyed weakly by the module and dies with it.  Saves a dozen tiny
     conversion kernels and their host-side launches on every forward.
     """
     key = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device, tuple(t.shape)) for t in sources)
-    cache = owner.__dict__.setdefault('_sm100_memo', {})
+    cache = _MEMO.get(owner)
+    if cache is None:
+        cache = _MEMO[owner] = {}
     hit = cache.get(tag)
     if hit is not None and hit[0] == key:
         return hit[1]
