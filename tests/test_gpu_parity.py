@@ -316,24 +316,26 @@ def test_fused_kernel_variants_fp16(grid, chunk, adaptive, with_noise, with_bias
     assert err < TOL_F16, (grid, adaptive, with_noise, with_bias, err)
 
 
-def test_fused_kernel_many_items_per_cta_fp16():
-    """More (batch, head) items than resident CTAs (2 x 148): every CTA loops over several items, which
-    exercises the ring / barrier phase bookkeeping across items; checked against the generic kernels."""
+@pytest.mark.parametrize('grid,chunk,B', [(14, 2, 400), (28, 4, 120)])
+def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B):
+    """More (batch, head) items than resident CTAs (2 x 148): every CTA loops over several items handed out by the
+    dynamic work counter, which exercises the ring / barrier phase bookkeeping across items; both instantiations
+    (14-wide grid: two chunk-rows per tile; 28-wide: one), checked against the generic kernels."""
     from efficient_attention import _abi
-    B, H, d = 400, 3, 64
+    H, d, N = 3, 64, grid * grid
     dev = _dev()
     g = torch.Generator().manual_seed(11)
-    qkv = (torch.randn(B, 196, 3, H, d, generator=g) * 1.1).half().to(dev)
+    qkv = (torch.randn(B, N, 3, H, d, generator=g) * 1.1).half().to(dev)
     bias = (0.5 * torch.randn(H, 49, 49, generator=g)).to(dev)
     ada = _abi_ada(_rand_ada(d, g), dev, 0.5)
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
-    geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+    geom = _abi.eva_geometry(q, seq_shape=(grid, grid), window=7, ext=0, chunk=chunk, chunk_ext=0)
     out, path = _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
     assert path == 1
     kb, bt = _abi.eva_chunk_stats(q, k, v, geom, ada)
     ref = _abi.eva_window_attention(q, k, v, geom, k_bar=kb, beta=bt, bias=bias)
-    per_item = ((out.float() - ref.float()).view(B, 196, H, d).pow(2).sum((1, 3)).sqrt() /
-                ref.float().view(B, 196, H, d).pow(2).sum((1, 3)).sqrt())
+    per_item = ((out.float() - ref.float()).view(B, N, H, d).pow(2).sum((1, 3)).sqrt() /
+                ref.float().view(B, N, H, d).pow(2).sum((1, 3)).sqrt())
     assert float(per_item.max()) < TOL_F16, float(per_item.max())
 
 
