@@ -224,6 +224,20 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        # several ranks stream from pinned host memory at once (e2e leg): keep this rank's threads -- and with them the pages
+        # of its pinned buffers (first touch) -- on the NUMA node its GPU hangs off, instead of wherever torchrun started it
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(dev).uuid
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID('GPU-' + str(uuid))
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(uuid)).encode())
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+        except Exception as e:                               # affinity is an optimisation, never a requirement
+            if rank == 0:
+                sys.stderr.write(f'bench: NUMA affinity not set ({type(e).__name__}: {e})\n')
     dtype = {'fp16': torch.float16, 'bf16': torch.bfloat16, 'fp32': torch.float32}[args.dtype]
     B, K, Wm = args.batch, args.steps, args.warmup
     layer = build_layer(dev, dtype)
