@@ -3,23 +3,26 @@
 // head_dim 64, 16-bit I/O, no padding mask.  lara_landmark_kernel still produces q_bar, omega, lp, bh per (batch, head).
 //
 // Per (batch, head) item, everything from one TMA load of q, k, v (N x 128 B each):
-//   phase S (TMEM lane = landmark): with the 128-row tile AW = [omega (rows 0-63) ; q_bar (rows 64-127)]
-//       D1 = AW K^T   rows 0-63:   phi-logits of the keys  -> softmax over the tokens (thread-local) -> P, lse_k
-//       D2 = AW Q^T   rows 64-127: q_bar q^T               -> lse_t (the normaliser of t_nc, lara.py:222-223)
+//   phase S (TMEM lane = landmark): two 128-row A tiles, T1 = [omega ; 0] and T2 = [0 ; q_bar], ONE accumulator
+//       D = T1 K^T + T2 Q^T   lanes 0-63:   phi-logits of the keys  -> softmax over the tokens (thread-local) -> P, lse_k
+//                             lanes 64-127: q_bar q^T               -> lse_t (the normaliser of t_nc, lara.py:222-223)
+//                             (both row softmaxes run side by side on the four compute warps)
 //       kv = P V      (A operand from TMEM)                -> 16-bit kv tile in shared memory
 //   phase O (TMEM lane = token, two blocks of 128 tokens):
-//       D3 = Q AW^T   columns 0-63: q . omega_c (phi(q)), columns 64-127: q . q_bar_c (t_nc)
+//       D3 = Q T1^T + Q T2^T   columns 0-63: q . omega_c (phi(q)), columns 64-127: q . q_bar_c (t_nc)
 //       per token: t, alpha = bh + coeff (t - mean_c t), log w = log alpha + phi(q) + lse_k - lp, softmax over c (thread-local)
 //       O = W kv      (A operand from TMEM) -> normalise -> staged in the (dead) q tile -> TMA store
-// Two persistent CTAs per SM (<= 113 KB shared memory, 256 TMEM columns, 168 registers each) hide each other's serial per-item
-// chain: warps 0-3 compute, warp 4 producer (TMA + the fp32 -> 16-bit AW tile), warp 5 MMA issuer.  One q tile and one k/v
-// tile per CTA: v is loaded into the k tile once D1 has read it; D2 reuses the TMEM columns of D1 after the kv read-back.
+// Two persistent CTAs per SM (<= 113 KB shared memory, 256 TMEM columns) hide each other's serial per-item chain: warps 0-3
+// compute, warp 4 producer (TMA + the fp32 -> 16-bit tiles), warp 5 MMA issuer, warps 6-7 only complete the second warpgroup:
+// the kernel launches with 128 registers per thread and re-balances with setmaxnreg (compute 208, the others 48).  One q tile
+// and one k/v tile per CTA: v is loaded into the k tile once the D MMAs have read it.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdio.h>
 
 #include <mutex>
 
+#define EVA_MBAR_WAIT_NO_CALL   // setmaxnreg below: no out-of-line calls in this translation unit's kernels
 #include "common.cuh"
 #include "lara_ws.cuh"
 #include "launch.h"
@@ -28,7 +31,9 @@
 namespace eva {
 namespace laracore {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;         // two warpgroups: compute (warps 0-3) | producer, MMA issuer and two idle warps (setmaxnreg works on whole warpgroups)
+constexpr int kRegsCompute = 208, kRegsOther = 48;   // after re-balancing; launch allocation: 128 x 256 with two CTAs per SM
+static_assert(128 * (kRegsCompute + kRegsOther) <= 128 * kThreads, "setmaxnreg budget");
 enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullAW0, kFullAW1, kFree0, kFree1,
            kSFull, kPFull, kKvFull, kKvTile, kD3Full, kP2Full0, kP2Full1, kOFull0, kOFull1, kEpiDone,
            kFullW0, kFullW1, kWFree, kToMma, kToCompute, kKFree, kS2Full, kLtDone, kNumBars };
@@ -80,7 +85,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int SL = p.sl;
-  uint8_t* const aw0 = sm + 2 * SL;                  // [128][128 B]: omega rows 0-63, q_bar rows 64-127 (second 16 KB unused)
+  uint8_t* const aw0 = sm + 2 * SL;                  // two [128][128 B] tiles: T1 = [omega ; 0], T2 = [0 ; q_bar] (T1 first holds the means tile)
   uint8_t* const kvt = aw0 + 2 * 16384;              // [128][128 B]: kv (rows = landmarks; phase L: k_bar, then mu); rows 64-127 stay zero (M = 128 A operand of the mixing MMA)
   float* const n2k = reinterpret_cast<float*>(kvt + 16384);    // [256] |k_n|^2 scale log2(e) / 2 (+inf for n >= N)
   uint32_t* const bins = reinterpret_cast<uint32_t*>(n2k + 256);   // [64] pooling bin of landmark c: y0 | y1 << 8 | x0 << 16 | x1 << 24 (|q_n|^2 is not needed: it cancels in the softmax over c)
@@ -142,7 +147,12 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
   const uint32_t tmem = *tmem_ptr;
   const float scale_log2 = 0.125f * kLog2e;
 
-  if (warp == 4) {
+  // register re-balancing: each role changes its budget INSIDE its own branch (ptxas gives code after a join of branches with
+  // different budgets the smallest one)
+  if (warp >= 6) {
+    ptx::setmaxnreg_dec<kRegsOther>();              // only there to complete the second warpgroup
+  } else if (warp == 4) {
+    ptx::setmaxnreg_dec<kRegsOther>();
     // =================================== producer ==============================================
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -188,7 +198,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(w.qbar + row * 64 + ch * 8) + 1);
         const int off = row * 128 + ((ch ^ (row & 7)) << 4);       // row and row + 64 share (row & 7)
         *reinterpret_cast<uint4*>(aw + off) = make_uint4(Fmt<T>::pack2(a0.x, a0.y), Fmt<T>::pack2(a0.z, a0.w), Fmt<T>::pack2(a1.x, a1.y), Fmt<T>::pack2(a1.z, a1.w));
-        *reinterpret_cast<uint4*>(aw + 8192 + off) = make_uint4(Fmt<T>::pack2(b0.x, b0.y), Fmt<T>::pack2(b0.z, b0.w), Fmt<T>::pack2(b1.x, b1.y), Fmt<T>::pack2(b1.z, b1.w));
+        *reinterpret_cast<uint4*>(aw + 16384 + 8192 + off) = make_uint4(Fmt<T>::pack2(b0.x, b0.y), Fmt<T>::pack2(b0.z, b0.w), Fmt<T>::pack2(b1.x, b1.y), Fmt<T>::pack2(b1.z, b1.w));
       }
       for (int c = lane; c < C; c += 32) { lpS[s * 64 + c] = __ldg(w.lp + c); bhS[s * 64 + c] = __ldg(w.bh + c); }
       ptx::fence_proxy_async_smem();
@@ -197,6 +207,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       load_v();
     }
   } else if (warp == 5) {
+    ptx::setmaxnreg_dec<kRegsOther>();
     // =================================== MMA issuer ============================================
     constexpr uint32_t fmt = Fmt<T>::kUmma;
     const uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 128, (uint32_t)NP);
@@ -210,6 +221,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       const uint32_t ph = it & 1, pi = it & 1;
       const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 0))), dK = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 1)));
       const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(tile(s, 2))), dAW = ptx::umma_desc_sw128(ptx::smem_u32(aw0 + s * 16384));
+      const uint64_t dT2 = dAW + (uint64_t)(16384 >> 4);            // [0 ; q_bar]
       ptx::mbar_wait(bar(kFullQK0 + s), ph);
       if (!p.fuse) {
         ptx::mbar_wait(bar(kFullAW0 + s), ph);
@@ -255,6 +267,10 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD1, dAW + 2 * ks, dK + 2 * ks, id_s, ks > 0);
+        // [omega ; 0] K^T + [0 ; q_bar] Q^T in ONE accumulator: lanes 0-63 hold the phi-logits of the keys, lanes 64-127 the
+        // t-logits, so that the two row softmaxes run side by side on all four compute warps
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD1, dT2 + 2 * ks, dQ + 2 * ks, id_s, 1);
         ptx::umma_commit(bar(kSFull));
         ptx::umma_commit(bar(kKFree));
       }
@@ -269,18 +285,15 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       ptx::mbar_wait(bar(kKvTile), pi);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2, dAW + 2 * ks, dQ + 2 * ks, id_s, ks > 0);
-        ptx::umma_commit(bar(kS2Full));
-      }
-      ptx::mbar_wait(bar(kLtDone), pi);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
 #pragma unroll 1
-        for (int rb = 0; rb < 2; ++rb)
+        for (int rb = 0; rb < 2; ++rb) {                             // D3 = Q [omega ; 0]^T + Q [0 ; q_bar]^T
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             ptx::umma_ss(tmem + cD3 + 128 * rb, dQ + (uint64_t)(rb * (16384 >> 4)) + 2 * ks, dAW + 2 * ks, id_d3, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            ptx::umma_ss(tmem + cD3 + 128 * rb, dQ + (uint64_t)(rb * (16384 >> 4)) + 2 * ks, dT2 + 2 * ks, id_d3, 1);
+        }
         ptx::umma_commit(bar(kD3Full));
       }
 #pragma unroll 1
@@ -296,6 +309,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       }
     }
   } else {
+    ptx::setmaxnreg_inc<kRegsCompute>();
     // =================================== compute warps =========================================
     const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
     const bool d1_side = tid < 64;                     // warps 0-1: omega rows (D1); warps 2-3: q_bar rows (D2)
@@ -352,7 +366,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 4; ++j) { const float2 f = Fmt<T>::unpack2(w4[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
             }
-          const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+          const float inv = __fdividef(1.0f, (float)((y1 - y0) * (x1 - x0)));
           const int r = 64 * sd + cc;
           *reinterpret_cast<uint4*>(awt + r * 128 + ((part ^ (r & 7)) << 4)) =
               make_uint4(Fmt<T>::pack2(acc[0] * inv, acc[1] * inv), Fmt<T>::pack2(acc[2] * inv, acc[3] * inv),
@@ -377,7 +391,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
             float v0 = 0.f, v1 = 0.f;
 #pragma unroll
             for (int e = 0; e < 64; e += 2) { const float d0 = y[e] - mean, d1 = y[e + 1] - mean; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
-            const float rs = 1.0f / sqrtf((v0 + v1) * (1.0f / 64) + p.ln_eps);
+            const float rs = rsqrtf((v0 + v1) * (1.0f / 64) + p.ln_eps);
 #pragma unroll
             for (int e = 0; e < 64; ++e) y[e] = (y[e] - mean) * rs * lp_[64 + e] + lp_[128 + e];
           }
@@ -406,7 +420,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
             float sum = 0.f;
 #pragma unroll
             for (int e = 0; e < 64; ++e) { v[e] = e < C ? ex2((v[e] - mx) * scale_log2) : 0.f; sum += v[e]; }
-            const float inv = 1.0f / sum;
+            const float inv = __fdividef(1.0f, sum);
             uint32_t pk[32];
 #pragma unroll
             for (int e = 0; e < 64; e += 2) pk[e >> 1] = Fmt<T>::pack2(v[e] * inv, v[e + 1] * inv);
@@ -435,12 +449,16 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           }
         }
         // L4: mu = q_bar + k_bar (lara.py:182), omega = mu (+ noise); tiles for the proposal statistics and the later phases
+        if (ws_ == 1) {                                  // the k-side means of T1 are dead: T1 becomes [omega ; 0]
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(awt + (64 + c) * 128 + (ch << 4)) = make_uint4(0, 0, 0, 0);
+        }
         if (ws_ == 0) {
           const bool live = c < C;
           const float* nz = (p.noise && live) ? p.noise + ((long long)item * C + c) * 64 : nullptr;
           float m2 = 0.f, dot = 0.f;
           uint8_t* const r_om = awt + c * 128;
-          uint8_t* const r_qb = awt + (64 + c) * 128;
+          uint8_t* const r_qb = awt + 16384 + (64 + c) * 128;   // T2
           uint8_t* const r_mu = kvt + c * 128;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
@@ -498,7 +516,6 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           float v[16];
           ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
           ptx::tmem_ld_wait();
-#pragma unroll
           float hk[16];
           if (with_k2) {
 #pragma unroll
@@ -521,7 +538,6 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
           uint32_t pk[8];
           ptx::tmem_ld16(trow + 16 * g, reinterpret_cast<uint32_t*>(v));
           ptx::tmem_ld_wait();
-#pragma unroll
           float hk[16];
           if (with_k2) {
 #pragma unroll
@@ -555,6 +571,9 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         row_softmax(true, true);
         cst2[c_row] = lse2 - lpS[s * 64 + c_row] * kLog2e;
         ptx::tmem_st_wait();
+      } else {                                                        // the q_bar rows: lse_t, side by side with the omega rows
+        row_softmax(false, false);
+        lse2t[c_row] = lse2;
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kPFull));
@@ -567,7 +586,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
         for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cKv + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
         ptx::tmem_ld_wait();
         if (c_row < C) {
-          const float inv = 1.0f / sum;
+          const float inv = __fdividef(1.0f, sum);
           uint8_t* row = kvt + c_row * 128;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
@@ -583,15 +602,6 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(kKvTile));
-      // ---- D2 = q_bar q^T in the same columns: lse_t, by the q_bar rows ----
-      ptx::mbar_wait(bar(kS2Full), pi);
-      ptx::tc_fence_after();
-      if (!d1_side) {
-        row_softmax(false, false);
-        lse2t[c_row] = lse2;
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(kLtDone));
       // ---- phase O: thread = token ----
       ptx::mbar_wait(bar(kD3Full), pi);
       ptx::tc_fence_after();
@@ -626,7 +636,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
             }
           }
         }
-        const float mean_t = tsum / (float)C;
+        const float mean_t = __fdividef(tsum, (float)C);
         float mw = kNegInf;
 #pragma unroll
         for (int g8 = 0; g8 < 8; ++g8) {
@@ -671,7 +681,7 @@ lara_core_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) ptx::tmem_ld16(trow + cO + 128 * rb + 16 * g, reinterpret_cast<uint32_t*>(o) + 16 * g);
         ptx::tmem_ld_wait();
-        const float inv = 1.0f / wsum;
+        const float inv = __fdividef(1.0f, wsum);
         uint8_t* row = tile(s, 0) + n * 128;                           // the q tile is dead: every D3 MMA has completed
         if (n < NP) {
 #pragma unroll

@@ -76,11 +76,23 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
     }
   }
 }
+#ifdef EVA_MBAR_WAIT_NO_CALL
+// Kernels that re-balance registers between warp roles (setmaxnreg) must not contain out-of-line calls: ptxas then gives every
+// role the smallest budget.  Same bounded wait, inline, without the diagnostic printf.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_suspend(bar, parity, 2000)) {
+    if (++spins > 4000000u) __trap();
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity);
 }
+#endif
 
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -174,6 +186,9 @@ __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// register re-balancing between warp roles (whole warpgroups; the immediate is the new per-thread budget)
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 // ---- tcgen05: TMEM allocation --------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {  // whole warp
