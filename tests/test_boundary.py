@@ -178,3 +178,25 @@ def test_memo_follows_parameter_updates():
     assert set(lin.state_dict()) == {'weight', 'bias'} and not any('memo' in k for k in lin.__dict__)
     clone = pickle.loads(pickle.dumps(copy.deepcopy(lin)))
     assert torch.equal(clone.weight, lin.weight)
+
+
+def test_bench_reference_arm_line_on_cpu():
+    """`bench.py --impl reference` needs no GPU: it must print ONE JSON line with the contract's keys, `impl: reference`,
+    a `cpu_baseline` describing the run and an `e2e` object that repeats the line's own value with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['unit'] == 'tokens/s' and d['value'] > 0 and 'workload' in d['config']
+    assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] and d['e2e']['value'] == d['value']
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
