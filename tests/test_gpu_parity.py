@@ -517,3 +517,29 @@ def test_lara_tcgen05_core_many_items_fp16():
     # landmarks, mixing and proposal statistics go through 16-bit MMA operands on this path: worst item of 384 within 1.5e-3
     assert float(per_item.max()) < 1.5e-3, float(per_item.max())
     assert float(per_item.mean()) < TOL_F16, float(per_item.mean())
+
+
+def test_bench_line_has_the_contract_keys():
+    """bench.py on a small batch: ONE JSON line carrying every key of the measurement contract (roofline, e2e with
+    per-step copy bytes, launch count, clocks sampled during the timed region)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '3', '--warmup', '3', '--batch', '64', '--no-cpu'],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
+        assert key in d, key
+    assert d['steps'] == 3 and d['warmup'] == 3 and d['n_gpus'] == 1 and d['gpu_launches'] > 0
+    r = d['roofline']
+    assert r['bound'] == 'hbm' and r['unit'] == 'GB/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    e = d['e2e']
+    assert e['value'] > 0 and e['h2d_bytes_per_step'] == 64 * 784 * 192 * 2 == e['d2h_bytes_per_step']
+    assert e['value'] < d['value']                       # host copies are inside the e2e region
+    assert d['config']['kernel_path'] == 'fused tcgen05/TMA' and 'sm_mhz' in d['clocks']
