@@ -23,6 +23,8 @@
 #include <cudaTypedefs.h>
 #include <stdio.h>
 
+#include <string.h>
+
 #include <mutex>
 #include <type_traits>
 
@@ -1038,15 +1040,49 @@ static int trace_enabled() {
   return v;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n > 0 ? n : 148;
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
 }
+// per device: a process may drive several different GPUs
+static int sm_count(int dev) {
+  static int n[kMaxDevices] = {};
+  if (dev < 0 || dev >= kMaxDevices) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
+
+// Tensor maps depend only on the pointers / strides / sizes of a call: a model that runs the same layer on the same
+// activation buffers (every layer of a network under the caching allocator, every replay of a CUDA graph) re-encodes the same
+// eight maps on each forward.  Small per-thread cache, keyed by everything the encode reads (cached tensor-map state).
+struct MapKey {
+  const void *q, *k, *v, *out, *w16;
+  long long qs[3], ks[3], vs[3];
+  int B, H, gh, gw, io, variant;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapSet { CUtensorMap twq, twk, twv, trq, trk, trv, tw, to; };
+struct MapCache {
+  static constexpr int kEntries = 16;
+  MapKey key[kEntries];
+  MapSet val[kEntries];
+  int used = 0, next = 0;
+  MapSet* find(const MapKey& k) {
+    for (int i = 0; i < used; ++i) if (key[i] == k) return &val[i];
+    return nullptr;
+  }
+  MapSet* insert(const MapKey& k) {
+    const int i = used < kEntries ? used++ : (next++ % kEntries);
+    key[i] = k;
+    return &val[i];
+  }
+};
 
 template <typename T, int W, int GW, int CH, int NR, int G>
 static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
@@ -1058,19 +1094,33 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 128 * 64 * sizeof(__half));
   unsigned int* next_item = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(bias2) + (size_t)g.H * C::kBiasSlab);
   const int items = g.B * g.H;
-  const int max_ctas = env_int("EVA_SM100_CTAS_PER_SM", 2) * sm_count();   // tuning knob; 2 = as many as fit
+  const int dev = current_device();
+  static const int ctas_per_sm = env_int("EVA_SM100_CTAS_PER_SM", 2);   // tuning knob, read once; 2 = as many as fit
+  const int max_ctas = ctas_per_sm * sm_count(dev);
   const int grid = items < max_ctas ? items : max_ctas;
   pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / 4, next_item, (unsigned)grid);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *msg = "pack_params launch"; return e; }
-  CUtensorMap twq, twk, twv, trq, trk, trv, tw, to;
-  View ov;
-  ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
-  if (!make_box_map(&twq, q, g, io, W, 2 * W) || !make_box_map(&twk, k, g, io, W, 2 * W) || !make_box_map(&twv, v, g, io, W, 2 * W) ||
-      !make_box_map(&trq, q, g, io, GW, CH * G) || !make_box_map(&trk, k, g, io, GW, CH * G) || !make_box_map(&trv, v, g, io, GW, CH * G) ||
-      !make_weight_map(&tw, w16) || !make_box_map(&to, ov, g, io, W, 2 * W)) {
-    *msg = "cuTensorMapEncodeTiled failed";
-    return cudaErrorInvalidValue;
+  static thread_local MapCache cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.q = q.ptr; key.k = k.ptr; key.v = v.ptr; key.out = out; key.w16 = w16;
+  key.qs[0] = q.sb; key.qs[1] = q.sn; key.qs[2] = q.sh; key.ks[0] = k.sb; key.ks[1] = k.sn; key.ks[2] = k.sh;
+  key.vs[0] = v.sb; key.vs[1] = v.sn; key.vs[2] = v.sh;
+  key.B = g.B; key.H = g.H; key.gh = g.gh; key.gw = g.gw; key.io = io; key.variant = GW * 16 + G;
+  MapSet* ms = cache.find(key);
+  if (!ms) {
+    MapSet fresh;
+    View ov;
+    ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
+    if (!make_box_map(&fresh.twq, q, g, io, W, 2 * W) || !make_box_map(&fresh.twk, k, g, io, W, 2 * W) || !make_box_map(&fresh.twv, v, g, io, W, 2 * W) ||
+        !make_box_map(&fresh.trq, q, g, io, GW, CH * G) || !make_box_map(&fresh.trk, k, g, io, GW, CH * G) || !make_box_map(&fresh.trv, v, g, io, GW, CH * G) ||
+        !make_weight_map(&fresh.tw, w16) || !make_box_map(&fresh.to, ov, g, io, W, 2 * W)) {
+      *msg = "cuTensorMapEncodeTiled failed";
+      return cudaErrorInvalidValue;
+    }
+    ms = cache.insert(key);
+    *ms = fresh;
   }
   Params p{};
   p.B = g.B; p.H = g.H; p.N = g.N; p.gh = g.gh; p.gw = g.gw;
@@ -1082,18 +1132,24 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias2 = bias ? bias2 : nullptr; p.out = out; p.next_item = next_item;
   p.trace = trace_enabled();
-  p.prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", 0);   // measured: warming L2 with the next item's rows no longer pays (0.5 % slower)
-  p.prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);   // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
+  static const int prefetch_rows = env_int("EVA_SM100_PREFETCH_ROWS", 0);   // measured: warming L2 with the next item's rows no longer pays (0.5 % slower)
+  static const int prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);         // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
+  p.prefetch_rows = prefetch_rows;
+  p.prefetch_v = prefetch_v;
   auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, G, true> : eva_fused_kernel<T, W, GW, CH, NR, G, false>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
-  if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
+  static bool attr_set[2][kMaxDevices] = {};         // per (instantiation, traced or not, device): the attribute is sticky
+  if (dev < 0 || dev >= kMaxDevices || !attr_set[p.trace ? 1 : 0][dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kDynamic);
+    if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
+    if (dev >= 0 && dev < kMaxDevices) attr_set[p.trace ? 1 : 0][dev] = true;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kDynamic; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;           // overlap with pack_params (see griddepcontrol.wait in the TMA warp)
   cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, twq, twk, twv, trq, trk, trv, tw, to, p);
+  e = cudaLaunchKernelEx(&cfg, kern, ms->twq, ms->twk, ms->twv, ms->trq, ms->trk, ms->trv, ms->tw, ms->to, p);
   if (e != cudaSuccess) { *msg = "kernel launch"; return e; }
   *msg = "kernel launch";
   return cudaGetLastError();

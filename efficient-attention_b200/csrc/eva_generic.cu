@@ -347,8 +347,12 @@ window_attn_kernel(const Geo g, const View q, const View k, const View v, const 
   int* qpad = qtok + kRows;             // [kRows]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rb = blockIdx.x, win = blockIdx.y;
-  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
+  // (row block, window, batch * head) folded into gridDim.x: gridDim.y / .z stop at 65535, the reference has no such limit
+  const int n_rb = (g.L + kRows - 1) / kRows;
+  const long long cta = blockIdx.x;
+  const int rb = (int)(cta % n_rb), win = (int)((cta / n_rb) % g.n_windows);
+  const int bh = (int)(cta / ((long long)n_rb * g.n_windows));
+  const int b = bh / g.H, h = bh % g.H;
   const float scale = rsqrtf((float)D);
   const int n_keys = g.J + g.n_chunks;
 
@@ -495,7 +499,10 @@ static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View&
     static const bool generic_only = [] { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); return e && e[0] == '1'; }();
     if (!generic_only && g.dims == 1 && g.chunk_ext == 0 && !mask && g.Jc >= 64 && g.Jc <= 8192) {
       const size_t smem_cta = (size_t)(8 * 128 + 128 + 128 + 64 + 16 + ((g.Jc + 3) & ~3)) * sizeof(float) + (sizeof(T) == 2 && g.Jc <= 512 ? (size_t)g.Jc * 144 : 0);
-      if (smem_cta > 48 * 1024) cudaFuncSetAttribute(chunk_stats_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta);
+      if (smem_cta > 48 * 1024) {
+        const cudaError_t ea = cudaFuncSetAttribute(chunk_stats_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta);
+        if (ea != cudaSuccess) return ea;
+      }
       const long long total_cta = (long long)g.B * g.H * g.n_chunks;
       chunk_stats_cta_kernel<T><<<(unsigned)total_cta, 256, smem_cta, st>>>(g, q, k, v, ada, noise, kbar, beta);
       return cudaGetLastError();
@@ -523,8 +530,9 @@ static cudaError_t launch_window_attn_t(const Geo& g, const View& q, const View&
   auto kern = window_attn_kernel<T, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((g.L + kRows - 1) / kRows, g.n_windows, g.B * g.H);
-  kern<<<grid, 128, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<T*>(out));
+  const long long ctas = (long long)((g.L + kRows - 1) / kRows) * g.n_windows * g.B * g.H;
+  if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)ctas, 128, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<T*>(out));
   return cudaGetLastError();
 }
 

@@ -419,10 +419,11 @@ lara_stats_kernel(const LaraGeo g, const View q, const View k, const View v, con
   float* Ps = Vs + KT * DP;       // [4][RPW][KT]
   int* kflag = reinterpret_cast<int*>(Ps + 4 * RPW * KT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
-  const LaraWs ws = lara_ws_at(ws_base, blockIdx.z, g.C, g.S, D);
-  const bool kv_mode = (int)blockIdx.x < kv_blocks;
-  const int rb = kv_mode ? blockIdx.x : blockIdx.x - kv_blocks;
+  // grid = (batch * head, row blocks): gridDim.x has no 65535 cap
+  const int b = blockIdx.x / g.H, h = blockIdx.x % g.H;
+  const LaraWs ws = lara_ws_at(ws_base, blockIdx.x, g.C, g.S, D);
+  const bool kv_mode = (int)blockIdx.y < kv_blocks;
+  const int rb = kv_mode ? blockIdx.y : blockIdx.y - kv_blocks;
   const int n_rows = kv_mode ? g.S : g.C;
   const float* rows = kv_mode ? ws.omega : ws.qbar;
   const View& keys = kv_mode ? k : q;
@@ -548,8 +549,8 @@ lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask,
   float* wv = qv + 8 * D;       // [8][S]
   float* tb = wv + 8 * S;       // [8][C]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.z / g.H, h = blockIdx.z % g.H;
-  const LaraWs ws = lara_ws_at(const_cast<float*>(ws_base), blockIdx.z, C, S, D);
+  const int b = blockIdx.x / g.H, h = blockIdx.x % g.H;      // grid = (batch * head, token blocks)
+  const LaraWs ws = lara_ws_at(const_cast<float*>(ws_base), blockIdx.x, C, S, D);
   const float scale = rsqrtf((float)D);
   const float* auxsrc = g.mis_type == LARA_MIS_OPT ? ws.qbar : ws.mu;
   for (int idx = tid; idx < S * D; idx += blockDim.x) {
@@ -564,8 +565,8 @@ lara_out_kernel(const LaraGeo g, const View q, const uint8_t* __restrict__ mask,
   float* myq = qv + warp * D;
   float* myw = wv + warp * S;
   float* myt = tb + warp * C;
-  const int t_end = min(g.N, (int)(blockIdx.x + 1) * kLaraTokPerCta);
-  for (int tok = blockIdx.x * kLaraTokPerCta + warp; tok < t_end; tok += 8) {
+  const int t_end = min(g.N, (int)(blockIdx.y + 1) * kLaraTokPerCta);
+  for (int tok = blockIdx.y * kLaraTokPerCta + warp; tok < t_end; tok += 8) {
     const bool zero = g.zero_padded && mask && mask[(long long)b * g.N + tok];
     const T* qr = q.row<T>(b, tok, h);
     float n2 = 0.f;
@@ -675,14 +676,14 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)) != cudaSuccess) return e;
     const int kv_blocks = (g.S + 15) / 16;
     const int t_blocks = g.mis_type == LARA_MIS_OPT ? (g.C + 15) / 16 : 0;
-    dim3 grid(kv_blocks + t_blocks, 1, g.B * g.H);
+    dim3 grid(g.B * g.H, kv_blocks + t_blocks);
     kern<<<grid, 128, sm2, st>>>(g, q, k, v, mask, ws, kv_blocks);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
     auto kern = lara_out_kernel<T, D>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
-    dim3 grid((g.N + kLaraTokPerCta - 1) / kLaraTokPerCta, 1, g.B * g.H);
+    dim3 grid(g.B * g.H, (g.N + kLaraTokPerCta - 1) / kLaraTokPerCta);
     kern<<<grid, 256, sm3, st>>>(g, q, mask, ws, reinterpret_cast<T*>(out));
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }

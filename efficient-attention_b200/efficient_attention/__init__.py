@@ -57,6 +57,7 @@ from .local_attention import LocalAttention  # noqa: E402
 from .lara import LinearRA  # noqa: E402
 from .eva import EVA  # noqa: E402
 from .causal_eva import CausalEVAttention  # noqa: E402
+from ._abi import invalidate_caches  # noqa: E402,F401
 
 
 class AttentionFactory(object):

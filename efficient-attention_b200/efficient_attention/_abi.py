@@ -124,12 +124,24 @@ _MEMO = weakref.WeakKeyDictionary()
 def memo(owner, tag, sources, build):
     """Per-module cache of tensors derived from parameters (fp32 copies, gathered bias tables, fused weights).
 
-    Rebuilt whenever a source tensor was modified in place (optimizer step, load_state_dict: `_version` changes) or replaced
-    (`.to()`, `.half()`: storage / dtype / device change); the cache is keyed weakly by the module and dies with it.  Saves a dozen tiny
-    conversion kernels and their host-side launches on every forward.
+    An entry is rebuilt whenever a source tensor was modified in place through the parameter itself (optimizer step, `p.copy_`,
+    load_state_dict: `_version` changes) or replaced (`.to()`, `.half()`: storage / dtype / device change).  Writes through
+    `p.data` (`p.data.copy_(...)`: fairseq's FP16 optimizer sync, some EMA / weight-conversion scripts) do NOT move `_version`,
+    so the key cannot see them; two rules close that hole:
+      * a module in training mode never uses the cache and drops its entry (weights change every step anyway), so whatever
+        a training loop does to `.data` is picked up by the next forward and by the first eval forward after it;
+      * `invalidate_caches(module)` (re-exported by the package) is the explicit hook for scripts that write `.data` on a
+        module that stays in eval mode.
+    float32 contiguous sources are never copied at all (`_f32` returns a view of the parameter's own storage), so for float32
+    modules only gathered tables (relative-position bias) are real copies.  The cache is keyed weakly by the module and dies
+    with it.  Saves a dozen tiny conversion kernels and their host-side launches on every eval forward.
     """
-    key = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device, tuple(t.shape)) for t in sources)
     cache = _MEMO.get(owner)
+    if getattr(owner, 'training', False):
+        if cache is not None:
+            cache.pop(tag, None)
+        return build()
+    key = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device, tuple(t.shape)) for t in sources)
     if cache is None:
         cache = _MEMO[owner] = {}
     hit = cache.get(tag)
@@ -138,6 +150,17 @@ def memo(owner, tag, sources, build):
     val = build()
     cache[tag] = (key, val)
     return val
+
+
+def invalidate_caches(module=None):
+    """Drop the parameter-derived caches of `module` and its sub-modules (all modules when None).  Needed only after writing
+    parameters through `.data` on a module that stays in eval mode (see `memo`)."""
+    if module is None:
+        _MEMO.clear()
+        return
+    mods = module.modules() if hasattr(module, 'modules') else (module,)
+    for m in mods:
+        _MEMO.pop(m, None)
 
 
 def adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff, ln_eps=1e-5):

@@ -64,8 +64,10 @@ class LinearRA(MultiheadAttention):
         return _abi.memo(self, 'proj_params', params, lambda: _abi.adaptive(*params, mu_coeff=1.0, ln_eps=ln_q.eps))
 
     def forward(self, x, key_padding_mask=None, noise=None):
-        """x: [B, H', W', C] or [B, N, C].  `noise` optionally overrides the training-mode draw
-        ([B, heads, C or 2C, head_dim], see lara.py:188-196)."""
+        """x: [B, H', W', C] or [B, N, C].  `noise` (test hook, not part of the reference signature) overrides the
+        training-mode draw ([B, heads, C or 2C, head_dim], see lara.py:188-196).  As in the reference, the antithetic /
+        multi-sample estimators exist in training mode only (lara.py:189-196 key on `self.training`): a `noise` passed to a
+        module in eval mode is added as one sample per landmark and never switches the estimator."""
         B, *seq_shape, C = x.shape
         two_d = len(seq_shape) == 2
         if len(seq_shape) not in (1, 2):
@@ -80,9 +82,9 @@ class LinearRA(MultiheadAttention):
             mixed = 1
         mode = _abi.LARA_SAMPLE_SINGLE
         if self.training or noise is not None:
-            if self.use_multisample:
+            if self.training and self.use_multisample:
                 mode, rows = _abi.LARA_SAMPLE_MULTI, 2 * landmarks
-            elif self.use_antithetics:
+            elif self.training and self.use_antithetics:
                 mode, rows = _abi.LARA_SAMPLE_ANTITHETIC, landmarks
             else:
                 rows = landmarks

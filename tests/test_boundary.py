@@ -149,7 +149,7 @@ def test_memo_follows_parameter_updates():
     """_abi.memo caches tensors derived from parameters per module; the entry must be rebuilt after an in-place update
     (optimizer step, load_state_dict), after the parameter's storage was replaced (.data = ..., .to()), and must not be
     shared between modules."""
-    lin = torch.nn.Linear(4, 4)
+    lin = torch.nn.Linear(4, 4).eval()                          # the cache serves eval-mode modules only (see below)
     calls = []
 
     def build():
@@ -169,9 +169,27 @@ def test_memo_follows_parameter_updates():
     lin.load_state_dict({'weight': torch.zeros(4, 4), 'bias': torch.zeros(4)})
     e = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
     assert len(calls) == 4 and float(e.abs().sum()) == 0.0
-    other = torch.nn.Linear(4, 4)
+    other = torch.nn.Linear(4, 4).eval()
     _abi.memo(other, 'w64', (other.weight,), lambda: calls.append(1) or other.weight.detach().clone())
     assert len(calls) == 5
+    # writes through `.data` do not move `_version` (fairseq FP16 optimizer sync, EMA scripts): a training-mode module never
+    # caches and drops its entry, so the first eval forward after training sees them; in pure eval mode the explicit hook does
+    n = len(calls)
+    lin.train()
+    lin.weight.data.copy_(torch.full((4, 4), 3.0))
+    f = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert len(calls) == n + 1 and float(f[0, 0]) == 3.0 and 'w64' not in _abi._MEMO.get(lin, {})
+    lin.weight.data.copy_(torch.full((4, 4), 4.0))
+    lin.eval()
+    g = _abi.memo(lin, 'w64', (lin.weight, lin.bias), build)
+    assert len(calls) == n + 2 and float(g[0, 0]) == 4.0
+    lin.weight.data.copy_(torch.full((4, 4), 5.0))               # eval mode + .data write: invisible to the key ...
+    assert float(_abi.memo(lin, 'w64', (lin.weight, lin.bias), build)[0, 0]) == 4.0
+    import efficient_attention
+    efficient_attention.invalidate_caches(lin)                   # ... until the caller says so
+    assert float(_abi.memo(lin, 'w64', (lin.weight, lin.bias), build)[0, 0]) == 5.0
+    # float32 contiguous parameters are handed to the kernels as views of their own storage: nothing to go stale
+    assert _abi._f32(lin.weight).data_ptr() == lin.weight.data_ptr()
     # the cache holds ctypes structures with raw pointers: it must stay out of the module (deepcopy / pickle / state_dict)
     import copy
     import pickle
