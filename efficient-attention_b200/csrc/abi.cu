@@ -156,6 +156,11 @@ int eva_forward_workspace_bytes(const EvaGeometry* gin, size_t* bytes) {
   return EVA_OK;
 }
 
+// diagnostic (not part of the public ABI): eva_forward calls by the path they took (0 generic, 1 fused, 2 causal tcgen05,
+// 3 cluster-resident fused) -- lets module- and model-level tests prove which kernels ran
+static int g_path_count[4] = {0, 0, 0, 0};
+int eva_debug_path_count(int path) { return path >= 0 && path < 4 ? g_path_count[path] : -1; }
+
 int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
                 const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,
@@ -184,6 +189,7 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
     const cudaError_t e = eva::launch_fused(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out,
                                             ws + 2 * stats, st, &msg);
     if (path_taken) *path_taken = 1;
+    ++g_path_count[1];
     if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(fused): %s: %s", msg, cudaGetErrorString(e));
     return EVA_OK;
   }
@@ -194,9 +200,11 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
     const char* msg = "";
     e = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out, st, &msg);
     if (path_taken) *path_taken = 2;
+    ++g_path_count[2];
     if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal window): %s: %s", msg, cudaGetErrorString(e));
     return EVA_OK;
   }
+  ++g_path_count[0];
   e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out, st);
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_forward(window_attention)");
 }
