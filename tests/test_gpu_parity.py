@@ -527,7 +527,7 @@ def test_bench_line_has_the_contract_keys():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '3', '--warmup', '3', '--batch', '64', '--no-cpu'],
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '3', '--warmup', '3', '--batch', '64', '--no-cpu', '--no-deit'],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -542,7 +542,8 @@ def test_bench_line_has_the_contract_keys():
     e = d['e2e']
     assert e['value'] > 0 and e['h2d_bytes_per_step'] == 64 * 784 * 192 * 2 == e['d2h_bytes_per_step']
     assert e['value'] < d['value']                       # host copies are inside the e2e region
-    assert d['config']['kernel_path'] == 'fused tcgen05/TMA' and 'sm_mhz' in d['clocks']
+    assert d['config']['kernel_path'].startswith('fused tcgen05/TMA') and 'sm_mhz' in d['clocks']
+    assert d['e2e']['copy_ceiling']['value'] > 0 and 0 < d['e2e']['frac_of_copy_ceiling'] < 1.2
 
 
 # ---- round 2: parity gaps named by the round-1 review -------------------------------------------------
