@@ -184,6 +184,14 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   char* ws = reinterpret_cast<char*>(workspace);
   float* k_bar = reinterpret_cast<float*>(ws);
   float* beta = reinterpret_cast<float*>(ws + stats);
+  if (eva::cluster_supported(g, gin->io_dtype, vq, vk, vv, pad_mask)) {
+    const char* msg = "";
+    const cudaError_t e = eva::launch_cluster(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out, ws + 2 * stats, st, &msg);
+    if (path_taken) *path_taken = 3;
+    ++g_path_count[3];
+    if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(cluster): %s: %s", msg, cudaGetErrorString(e));
+    return EVA_OK;
+  }
   if (eva::fused_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, bias, bias_stride_h)) {
     const char* msg = "";
     const cudaError_t e = eva::launch_fused(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out,

@@ -1,0 +1,847 @@
+// Fused EVA forward for sm_100a, cluster-resident version (BASELINE config c3: 28x28 tokens, window 7, 4x4 chunks, d = 64).
+//
+// One (batch, head) work item per CLUSTER of two CTAs (one CTA per SM).  CTA `rank` owns window rows 2*rank, 2*rank+1 (raster
+// rows 14*rank .. 14*rank+13): four vertically stacked window PAIRS, one per window column.  Each pair's q, k, v arrive ONCE,
+// as one TMA box of 7 x 16 tokens (the pair's 14 raster rows plus the two rows below it), and stay in shared memory (k, v) or
+// tensor memory (q) for the whole item: k/v/q are read from L2 1.14x per item (r1 kernel: 7 x 98 KB through a ring = 2.4x).
+//
+//   stage A (chunk statistics, eva.py:155-196).  Chunk rows 0-3 belong to rank 0 (raster rows 0-15: the two extra rows of its
+//            boxes complete chunk row 3, which straddles the window boundary), chunk rows 4-6 to rank 1 (rows 16-27).
+//            pooling over y as MMAs ([feat x (chunk-row, x)] = Tile^T . Pool^T, the x-sums are taken at read-back), adaptive
+//            Linear as one M=64 MMA + LayerNorm, phi-logits as MMAs against [q_bar' ; k_bar], 16-token softmaxes through a
+//            shared-memory exchange, beta^T = V^T . P2^T as MMAs.  Each CTA then pushes its rows of the k_bar / beta tiles
+//            into the peer's shared memory (cp.async.bulk shared::cta -> shared::cluster, completion counted on the PEER's
+//            mbarrier) -- the only data the two CTAs exchange.
+//   phase B  (eva.py:200-227) per window pair: S = Q [K_w ; k_bar]^T with Q from TENSOR MEMORY, joint row softmax (TMEM -> RF),
+//            P -> TMEM, O = P [V_w ; beta], normalise, stage, TMA store.  Two compute warpgroups work on different pairs,
+//            each with its own MMA-issuer warp.
+//
+// Shared-memory slots are recycled pair by pair: as soon as pair p of item i has retired, the producer warp requests k, v, q
+// of pair p of item i+1 into the same slots, so the next item's loads run under the current item's phase B.
+// CTA = 12 warps: 0-3 warpgroup 0, 4-7 warpgroup 1 (thread t <-> TMEM lane t & 127), 8 TMA producer (loads AND output stores),
+// 9 MMA issuer (stage A + warpgroup 0's pairs), 10 MMA issuer (warpgroup 1's pairs), 11 idle.
+#include <string.h>
+
+#include <type_traits>
+
+#include "fused_common.cuh"
+
+namespace eva {
+namespace cluster2 {
+
+using fused::IoFmt;
+using fused::ex2;
+using fused::f16_bits;
+using fused::ktile_off;
+using fused::tile_off;
+using fused::tmem_ld_cols;
+using fused::tmem_st_cols;
+using ptx::add2; using ptx::fma2; using ptx::pk2; using ptx::upk2;
+
+constexpr int W = 7, L = 49, LP8 = 56, LS = 52, CNP = 56, NCX = 7;
+constexpr int kTiles = 4;                       // window pairs per CTA (one per window column)
+constexpr int kOff = 7;                         // a pair's box lands 7 rows into its slot: window a = rows 7-55, b = rows 56-104
+constexpr int kSlotBytes = 112 * 128;           // slot pitch = box size (7 x 16 tokens); rows 105-118 (raster rows +14, +15) spill
+constexpr int kThreads = 384, kCompute = 256, kWg = 128;   // into rows 0-6 of the NEXT slot, which every slot keeps free for that
+constexpr uint32_t kTmemCols = 512;
+constexpr int kBiasSlab = (L * LS * 4 + 15) & ~15;
+constexpr int kPoolBlk = 32 * 128;              // one 64-token block of a K-major [32 x 128-token] tile
+
+// ---- shared memory map (bytes from the 1024-aligned base) ------------------------------------------------------------
+constexpr int kK = 0;
+constexpr int kV = kK + kTiles * kSlotBytes;
+constexpr int kQS = kV + kTiles * kSlotBytes;   // q landing slots; once a q tile is in TMEM its slot is scratch: stage A keeps
+constexpr int kPad = kQS + kTiles * kSlotBytes; //   P2 / means / q_bar' there, phase B stages the pair's output rows there
+constexpr int kLbuf = kPad + 2048;              // (kPad: 16 rows behind the last q slot: its spill, and what M / K = 128 MMAs read past it --
+constexpr int kWt = kLbuf + 2048;               //  must stay 16-bit data, never the fp32 exchange buffer)  [W_q ; W_k] fp16 [128][64], loaded once
+constexpr int kPool = kWt + 16384;              // Pool_y^T [32][128] (constant per rank)
+constexpr int kKbar = kPool + 2 * kPoolBlk;     // k_bar tile, row c' = 8 r + cx (both CTAs hold all 56 rows)
+constexpr int kBeta = kKbar + 8192;             // beta tile, same rows
+constexpr int kBias = kBeta + 8192;             // [L][LS] fp32 x log2(e), this item's head
+constexpr int kLn = kBias + ((kBiasSlab + 1023) & ~1023);
+constexpr int kZeroEnd = kLn;
+constexpr int kBars = kLn + 6 * 64 * 4;
+constexpr int kScratch = 1024;                  // scratch / staging start 8 rows into a q slot (rows 0-6 hold the previous tile's spill)
+constexpr int kQBOff = kScratch + 8192;         // q_bar' tile [32][64] in slot 0 behind means / P2_0
+
+enum Bar {
+  bFullQ = 0, bFullK = 4, bFullV = 8, bKFree = 12, bVFree = 16, bStaged = 20,
+  bWFull = 24, bBiasFull, bBiasFree, bPoolFull, bAFull, bLinFull, bOmFull, bD2Full, bP2Full, bBetaFull, bQReady, bTmemFree,
+  bStatsFull, bStatsFree, bSFull0, bSFull1, bPFull0, bPFull1, bOFull0, bOFull1, bXFree0, bXFree1, kNumBars
+};
+constexpr int kTmemPtr = kBars + kNumBars * 8;
+constexpr int kBytes = kTmemPtr + 16;
+constexpr int kDynamic = kBytes + 1024;
+static_assert(kDynamic <= 232448, "shared memory budget (227 KB per CTA)");
+static_assert(kQBOff + 4096 <= kSlotBytes && kScratch + 2 * L * 128 <= kSlotBytes, "scratch fits a q slot");
+
+// ---- tensor memory map (512 columns) ---------------------------------------------------------------------------------
+constexpr uint32_t cQ = 0;                      // 4 x 32: q of the four pairs (16-bit, two features per column), lane = slot row + 8
+constexpr uint32_t cWg0 = 128, cWgPitch = 192;  // per warpgroup: S_loc / P in [0, 112), chunk logits then O in [112, 176)
+constexpr uint32_t cXOff = 2 * LP8, cPrfaOff = LP8;
+constexpr uint32_t cPoolQ = 128, cPoolK = 256;  // stage A (overlays the warpgroup regions; the phases never overlap in time)
+constexpr uint32_t cLin = 128, cD2 = 256, cBetaT = 384;
+
+struct Params {
+  int B, H, items;
+  const float *b_q, *g_q, *beta_q, *b_k, *g_k, *beta_k;
+  int has_q;
+  float mu_coeff, inv_mu_coeff, ln_eps;
+  const float* noise;
+  const float* bias2;
+  unsigned long long* prof;       // optional per-phase cycle counters of cluster 0 (EVA_SM100_TRACE=1)
+};
+
+__host__ __device__ constexpr bool chunk_ok(int c) { return c < CNP && (c & 7) < NCX; }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
+                   const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_w,
+                   const __grid_constant__ CUtensorMap t_o, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sm_u32 = ptx::smem_u32(sm);
+  const uint32_t bars = sm_u32 + kBars;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank(), peer = rank ^ 1u;
+  const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int y0 = 14 * (int)rank;                 // first raster row of this CTA's boxes
+  const int r0 = 4 * (int)rank;                  // first chunk row this CTA owns
+  const int nrl = rank ? 3 : 4;                  // chunk rows it owns
+  const int yy_lo = rank ? 2 : 0, yy_hi = rank ? 14 : 16;   // box rows whose tokens belong to owned chunks
+
+  // ---- one-time setup --------------------------------------------------------------------------------------------
+  for (int i = tid; i < kZeroEnd / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int s = tid; s < 128; s += kThreads) {    // Pool_y^T[8 r_l + xx][slot row s] = 1/16 for the owned tokens
+    const int t = s - kOff;
+    if (t >= 0 && t < 112) {
+      const int yy = t / W, xx = t % W;
+      if (yy >= yy_lo && yy < yy_hi) {
+        const int rl = ((y0 + yy) >> 2) - r0;
+        *reinterpret_cast<uint16_t*>(sm + kPool + ktile_off(8 * rl + xx, s, kPoolBlk)) = IoFmt<T>::one(1.0f / 16);
+      }
+    }
+  }
+  {
+    float* ln = reinterpret_cast<float*>(sm + kLn);
+    const float* src[6] = {p.b_q, p.g_q, p.beta_q, p.b_k, p.g_k, p.beta_k};
+    for (int idx = tid; idx < 6 * 64; idx += kThreads) ln[idx] = src[idx >> 6] ? __ldg(src[idx >> 6] + (idx & 63)) : 0.f;
+  }
+  if (warp == 8 && lane == 0) {
+    for (int i = 0; i < 12; ++i) ptx::mbar_init(bar(bFullQ + i), 1);          // full q / k / v
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bar(bKFree + i), 1);           // k / v slots handed back by tcgen05.commit
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(bStaged + i), kWg);
+    ptx::mbar_init(bar(bWFull), 1);
+    ptx::mbar_init(bar(bBiasFull), 1);
+    ptx::mbar_init(bar(bBiasFree), kCompute);
+    ptx::mbar_init(bar(bPoolFull), 1);
+    ptx::mbar_init(bar(bAFull), kCompute);
+    ptx::mbar_init(bar(bLinFull), 1);
+    ptx::mbar_init(bar(bOmFull), kCompute);
+    ptx::mbar_init(bar(bD2Full), 1);
+    ptx::mbar_init(bar(bP2Full), kCompute);
+    ptx::mbar_init(bar(bBetaFull), 1);
+    ptx::mbar_init(bar(bQReady), kCompute);
+    ptx::mbar_init(bar(bTmemFree), kCompute);
+    ptx::mbar_init(bar(bStatsFull), 1);
+    ptx::mbar_init(bar(bStatsFree), 2);
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(bar(bSFull0 + g), 1);
+      ptx::mbar_init(bar(bPFull0 + g), kWg);
+      ptx::mbar_init(bar(bOFull0 + g), 1);
+      ptx::mbar_init(bar(bXFree0 + g), kWg);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_w); ptx::prefetch_tmap(&t_o);
+  }
+  if (warp == 9) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), kTmemCols);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  ptx::cluster_arrive();                         // the peer's barriers exist before anything is sent to them
+  ptx::cluster_wait();
+
+  const bool has_bias = p.bias2 != nullptr;
+  unsigned long long* const prof = (p.prof && cid == 0 && rank == 0) ? p.prof : nullptr;
+
+  if (warp == 8) {
+    // =========================================== TMA producer ====================================================
+    const uint64_t pol_in = ptx::policy_evict_first(), pol_out = ptx::policy_evict_first();
+    auto load = [&](const CUtensorMap* tm, int base, int fullbar, int pr, int b, int h) {
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bar(fullbar + pr), kSlotBytes);
+        ptx::tma_load_5d_hint(sm_u32 + base + pr * kSlotBytes + kOff * 128, tm, bar(fullbar + pr), 0, h, W * pr, y0, b, pol_in);
+      }
+    };
+    auto load_bias = [&](int h) {
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(bar(bBiasFull), kBiasSlab);
+        ptx::bulk_load(sm_u32 + kBias, reinterpret_cast<const uint8_t*>(p.bias2) + (size_t)h * kBiasSlab, kBiasSlab, bar(bBiasFull));
+      }
+    };
+    uint32_t round = 0;
+    for (int item = cid; item < p.items; item += n_clusters, ++round) {
+      const int b = item / p.H, h = item % p.H;
+      const uint32_t par = round & 1u;
+      if (round == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");     // pack_params (weight tile, bias slabs) has finished
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar(bWFull), 16384);
+          ptx::tma_load_2d(sm_u32 + kWt, &t_w, bar(bWFull), 0, 0);
+        }
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) { load(&t_q, kQS, bFullQ, pr, b, h); load(&t_k, kK, bFullK, pr, b, h); load(&t_v, kV, bFullV, pr, b, h); }
+        if (has_bias) load_bias(h);
+      }
+      const int nxt = item + n_clusters;
+      const bool has_next = nxt < p.items;
+      const int bn = has_next ? nxt / p.H : 0, hn = has_next ? nxt % p.H : 0;
+#pragma unroll 1
+      for (int pr = 0; pr < kTiles; ++pr) {      // pairs retire in this order (warpgroup 0: pairs 0, 2; warpgroup 1: pairs 1, 3)
+        ptx::mbar_wait(bar(bKFree + pr), par);
+        if (has_next) load(&t_k, kK, bFullK, pr, bn, hn);
+        ptx::mbar_wait(bar(bVFree + pr), par);
+        if (has_next) load(&t_v, kV, bFullV, pr, bn, hn);
+        ptx::mbar_wait(bar(bStaged + pr), par);
+        if (ptx::elect_one()) {                  // the pair's output rows: one box; the slot is re-used once the store has read it
+          ptx::tma_store_5d_hint(&t_o, sm_u32 + kQS + pr * kSlotBytes + kScratch, 0, h, W * pr, y0, b, pol_out);
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_read0();
+        }
+        __syncwarp();
+        if (has_next) load(&t_q, kQS, bFullQ, pr, bn, hn);
+      }
+      if (has_bias) {
+        ptx::mbar_wait(bar(bBiasFree), par);
+        if (has_next) load_bias(hn);
+      }
+    }
+    if (ptx::elect_one()) ptx::bulk_wait_all();
+  } else if (warp == 9 || warp == 10) {
+    // =========================================== MMA issuers =====================================================
+    constexpr uint32_t fmt = IoFmt<T>::kUmma;
+    constexpr uint32_t id_pool = ptx::umma_idesc(fmt, fmt, 1, 0, 64, 32);       // [feat x 32] = Tile^T (A MN-major) . Pool^T / P2^T
+    constexpr uint32_t id_lin = ptx::umma_idesc(ptx::kFmtF16, ptx::kFmtF16, 0, 0, 64, 128);
+    constexpr uint32_t id_d2 = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 32);
+    constexpr uint32_t id_sl = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 2 * LP8);
+    constexpr uint32_t id_sr = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
+    constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+    const int g = warp - 9;                      // the warpgroup this issuer serves in phase B
+    const uint64_t dK0 = ptx::umma_desc_sw128(sm_u32 + kK), dV0 = ptx::umma_desc_sw128(sm_u32 + kV), dQ0 = ptx::umma_desc_sw128(sm_u32 + kQS);
+    auto tile = [&](uint64_t d0, int pr) { return d0 + (uint64_t)(pr * (kSlotBytes >> 4)); };
+    const uint64_t dKB = ptx::umma_desc_sw128(sm_u32 + kKbar), dBT = ptx::umma_desc_sw128(sm_u32 + kBeta);
+    const uint64_t dPool = ptx::umma_desc_sw128(sm_u32 + kPool), dW = ptx::umma_desc_sw128(sm_u32 + kWt);
+    const uint64_t dMeans = ptx::umma_desc_sw128(sm_u32 + kQS + kScratch), dQB = ptx::umma_desc_sw128(sm_u32 + kQS + kQBOff);
+    const uint64_t dKBown = dKB + (uint64_t)(r0 * (1024 >> 4));                 // this CTA's rows of the k_bar tile: [8 r0, 8 r0 + 32)
+    auto tokB = [](int ks) { return (uint64_t)((ks >> 2) * (kPoolBlk >> 4) + (ks & 3) * 2); };   // k-step over the tokens of a K-major tile
+    const uint32_t cS = cWg0 + cWgPitch * g, cX = cS + cXOff;
+    uint32_t round = 0;
+    for (int item = cid; item < p.items; item += n_clusters, ++round) {
+      const uint32_t par = round & 1u;
+      if (g == 0) {
+        // ---- stage A ----------------------------------------------------------------------------------------------
+        if (round > 0) { ptx::mbar_wait(bar(bTmemFree), par ^ 1u); ptx::tc_fence_after(); }   // phase B of the previous item has left TMEM
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) {    // pooling over y: [feat x (r_l, xx)] per tile, q and k
+          ptx::mbar_wait(bar(bFullQ + pr), par);
+          ptx::mbar_wait(bar(bFullK + pr), par);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cPoolQ + 32 * pr, tile(dQ0, pr) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cPoolK + 32 * pr, tile(dK0, pr) + 128 * ks, dPool + tokB(ks), id_pool, ks > 0);
+            if (pr == kTiles - 1) ptx::umma_commit(bar(bPoolFull));
+          }
+        }
+        if (round == 0) ptx::mbar_wait(bar(bWFull), 0);
+        ptx::mbar_wait(bar(bAFull), par);        // means tile written
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cLin, dMeans + 2 * ks, dW + 2 * ks, id_lin, ks > 0);
+          ptx::umma_commit(bar(bLinFull));
+        }
+        ptx::mbar_wait(bar(bOmFull), par);       // q_bar' / k_bar rows written
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll 1
+          for (int pr = 0; pr < kTiles; ++pr) {  // phi-logits of every token against the owned chunks: K (q_bar' + k_bar)^T
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2 + 32 * pr, tile(dK0, pr) + 2 * ks, dQB + 2 * ks, id_d2, ks > 0);
+            if (p.has_q) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cD2 + 32 * pr, tile(dK0, pr) + 2 * ks, dKBown + 2 * ks, id_d2, 1);
+            }
+          }
+          ptx::umma_commit(bar(bD2Full));
+        }
+        ptx::mbar_wait(bar(bP2Full), par);       // P2 tiles written
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) {    // beta^T += V^T P2^T
+          ptx::mbar_wait(bar(bFullV + pr), par);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::umma_ss(tmem + cBetaT, tile(dV0, pr) + 128 * ks, dQ0 + (uint64_t)((pr * kSlotBytes + kScratch) >> 4) + tokB(ks), id_pool,
+                           (pr | ks) != 0);
+            if (pr == kTiles - 1) ptx::umma_commit(bar(bBetaFull));
+          }
+        }
+      }
+      // ---- phase B: this warpgroup's two pairs ------------------------------------------------------------------------
+      ptx::mbar_wait(bar(bQReady), par);         // q of all pairs is in tensor memory
+      ptx::mbar_wait_cluster(bar(bStatsFull), par);   // k_bar / beta complete: own rows written, the peer's rows received
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int kk = 0; kk < 2; ++kk) {
+        const int pr = g + 2 * kk;
+        const uint64_t dK = tile(dK0, pr), dV = tile(dV0, pr);
+        const uint32_t tQ = tmem + cQ + 32 * pr;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cS, tQ + 8 * ks, dK + 2 * ks, id_sl, ks > 0);
+        }
+        if (kk == 1) { ptx::mbar_wait(bar(bXFree0 + g), par); ptx::tc_fence_after(); }   // the first pair's O has been read
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cX, tQ + 8 * ks, dKB + 2 * ks, id_sr, ks > 0);
+          ptx::umma_commit(bar(bSFull0 + g));
+          ptx::umma_commit(bar(bKFree + pr));
+        }
+        ptx::mbar_wait(bar(bPFull0 + g), kk);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 2 * LP8 / 16; ++ks) ptx::umma_ts(tmem + cX, tmem + cS + 8 * ks, dV + 128 * ks, id_pv, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ts(tmem + cX, tmem + cS + cPrfaOff + 8 * ks, dBT + 128 * ks, id_pv, 1);
+          ptx::umma_commit(bar(bOFull0 + g));
+          ptx::umma_commit(bar(bVFree + pr));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // =========================================== compute warpgroups ===============================================
+    const int g = warp >> 2;                     // warpgroup
+    const int tw = tid & 127;                    // TMEM lane / slot row this thread owns
+    const int wq = warp & 3;                     // TMEM lane quarter
+    const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint32_t cS = cWg0 + cWgPitch * g, cX = cS + cXOff;
+    const float scale_log2 = 0.125f * kLog2e;    // head_dim 64
+    // phase B roles (as in the streamed kernel): window a on lanes 15-63, window b on lanes 64-112
+    const int ws = tw >> 6;
+    const int iq = ws ? (tw - 64) : (tw - (64 - L));
+    const int ic = iq < 0 ? 0 : (iq < L ? iq : L - 1);
+    // stage A roles
+    const int feat = 16 * wq + (lane & 15);      // M = 64 accumulators: lanes 0-15 of each quarter hold row 16 * quarter + lane
+    const bool feat_lane = lane < 16;
+    const int tk = tw - kOff;                    // token inside the box owned as slot row tw (valid: 0 .. 111)
+    const int yy = tk >= 0 ? tk / W : 0, xx = tk >= 0 ? tk % W : 0;
+    const bool tok_ok = tk >= 0 && tk < 112 && yy >= yy_lo && yy < yy_hi;
+    const int rl_tok = tok_ok ? ((y0 + yy) >> 2) - r0 : 0;
+    const int yl = y0 + yy - 4 * r0;             // raster row inside the owned region (0 .. 4 nrl - 1)
+    uint8_t* const KBt = sm + kKbar;
+    uint8_t* const BTt = sm + kBeta;
+    float* const lbuf = reinterpret_cast<float*>(sm + kLbuf);
+    const float* const bias2 = reinterpret_cast<const float*>(sm + kBias);
+    uint32_t round = 0;
+    for (int item = cid; item < p.items; item += n_clusters, ++round) {
+      const int b = item / p.H, h = item % p.H;
+      const uint32_t par = round & 1u;
+      long long t_a0 = 0;
+      if (prof && tid == 0) t_a0 = clock64();
+      // ---- A1: q of my pairs -> tensor memory; |k|^2 of my slot row ---------------------------------------------------
+      float kn[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int pr = g + 2 * j;
+        ptx::mbar_wait(bar(bFullQ + pr), par);
+        uint32_t qv[32];
+        if (tw >= 8) {                           // TMEM lane = slot row + 8: window a -> lanes 15-63, window b -> lanes 64-112
+          const int row = tw - 8;
+          const uint8_t* src = sm + kQS + pr * kSlotBytes + row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + ((ch ^ (row & 7)) << 4));
+            qv[4 * ch] = raw.x; qv[4 * ch + 1] = raw.y; qv[4 * ch + 2] = raw.z; qv[4 * ch + 3] = raw.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) qv[e] = 0u;
+        }
+        tmem_st_cols<32>(trow + cQ + 32 * pr, qv);
+        ptx::mbar_wait(bar(bFullK + pr), par);
+        const uint8_t* Kr = sm + kK + pr * kSlotBytes + tw * 128;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(Kr + ((ch ^ (tw & 7)) << 4));
+          const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
+          a0 = fmaf(a.x, a.x, a0); a1 = fmaf(a.y, a.y, a1); a2 = fmaf(b2.x, b2.x, a2); a3 = fmaf(b2.y, b2.y, a3);
+          a0 = fmaf(c2.x, c2.x, a0); a1 = fmaf(c2.y, c2.y, a1); a2 = fmaf(d2.x, d2.x, a2); a3 = fmaf(d2.y, d2.y, a3);
+        }
+        kn[j] = (a0 + a1) + (a2 + a3);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(bQReady));
+      // ---- A2: pooled sums (TMEM) -> chunk means tile [8 r_l + cx (+32 on the k side)][feat] (fp16) -------------------------
+      ptx::mbar_wait(bar(bPoolFull), par);
+      ptx::tc_fence_after();
+      {
+        float acc[4][NCX];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < NCX; ++c) acc[r][c] = 0.f;
+#pragma unroll
+        for (int pr = 0; pr < kTiles; ++pr) {    // warpgroup 0: q side, warpgroup 1: k side
+          float v[32];
+          tmem_ld_cols<32>(trow + (g ? cPoolK : cPoolQ) + 32 * pr, reinterpret_cast<uint32_t*>(v));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int x = 0; x < W; ++x) acc[r][(W * pr + x) >> 2] += v[8 * r + x];
+        }
+        if (feat_lane) {
+          uint8_t* At = sm + kQS + kScratch;
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < NCX; ++c)
+              *reinterpret_cast<uint16_t*>(At + tile_off(32 * g + 8 * r + c, feat)) = f16_bits(acc[r][c]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(bAFull));
+      // ---- A3: Linear result -> bias, LayerNorm -> q_bar' rows (q side) / k_bar rows (k side) ----------------------------
+      ptx::mbar_wait(bar(bLinFull), par);
+      ptx::tc_fence_after();
+      {
+        // the means tile is dead: clear the four P2 tiles (P2_0 overlays it)
+        for (int z = tw + kWg * g; z < 4 * 8192 / 16; z += kCompute) {
+          const int pr = z >> 9, o = z & 511;
+          reinterpret_cast<uint4*>(sm + kQS + pr * kSlotBytes + kScratch)[o] = make_uint4(0, 0, 0, 0);
+        }
+        // rows of the M = 64 accumulator: quarter 0, 1 = q side (rows 0-31), quarter 2, 3 = k side; warpgroup 0 takes the q
+        // side, warpgroup 1 the k side
+        const bool kside = wq >= 2;
+        if (kside == (g == 1)) {                 // warp-uniform: tcgen05.ld is warp-collective; lanes 16-31 carry no row
+          const int c = (16 * wq + (lane & 15)) & 31;   // 8 r_l + cx
+          float y[64];
+          tmem_ld_cols<64>(trow + cLin + (kside ? 64u : 0u), reinterpret_cast<uint32_t*>(y));
+          ptx::tmem_ld_wait();
+          const float* lnp = reinterpret_cast<const float*>(sm + kLn) + (kside ? 192 : 0);   // bias | gain | beta
+          const bool has_lin_bias = kside ? (p.b_k != nullptr) : (p.b_q != nullptr);
+          const bool has_ln = kside ? (p.g_k != nullptr) : (p.g_q != nullptr);
+          if (has_lin_bias) {
+#pragma unroll
+            for (int e4 = 0; e4 < 16; ++e4) {
+              const float4 bb = *reinterpret_cast<const float4*>(lnp + 4 * e4);
+              y[4 * e4] += bb.x; y[4 * e4 + 1] += bb.y; y[4 * e4 + 2] += bb.z; y[4 * e4 + 3] += bb.w;
+            }
+          }
+          if (has_ln) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) { s0 += y[e]; s1 += y[e + 1]; s2 += y[e + 2]; s3 += y[e + 3]; }
+            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4) {
+              const float d0 = y[e] - mean, d1 = y[e + 1] - mean, d2_ = y[e + 2] - mean, d3 = y[e + 3] - mean;
+              v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2_, d2_, v2); v3 = fmaf(d3, d3, v3);
+            }
+            const float inv = 1.0f / sqrtf(((v0 + v1) + (v2 + v3)) * (1.0f / 64) + p.ln_eps);
+#pragma unroll
+            for (int e4 = 0; e4 < 16; ++e4) {
+              const float4 gg = *reinterpret_cast<const float4*>(lnp + 64 + 4 * e4);
+              const float4 bb = *reinterpret_cast<const float4*>(lnp + 128 + 4 * e4);
+              y[4 * e4] = (y[4 * e4] - mean) * inv * gg.x + bb.x;
+              y[4 * e4 + 1] = (y[4 * e4 + 1] - mean) * inv * gg.y + bb.y;
+              y[4 * e4 + 2] = (y[4 * e4 + 2] - mean) * inv * gg.z + bb.z;
+              y[4 * e4 + 3] = (y[4 * e4 + 3] - mean) * inv * gg.w + bb.w;
+            }
+          }
+          const int rl = c >> 3, cx = c & 7;
+          if (feat_lane && cx < NCX && rl < nrl) {
+            uint8_t* dst;
+            if (kside) {
+              dst = KBt + (8 * r0 + c) * 128;
+            } else {
+              // omega = mu_coeff (q_bar + k_bar) + noise is applied as mu_coeff ((q_bar + noise / mu_coeff) + k_bar): the phi-logit
+              // MMAs accumulate K q'^T and K k_bar^T, so the two halves never have to meet in a thread
+              dst = sm + kQS + kQBOff + c * 128;
+              const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * (NCX * 7) + (r0 + rl) * NCX + cx) * 64 : nullptr;
+#pragma unroll
+              for (int e4 = 0; e4 < 16; ++e4) {
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nz) z = __ldg(reinterpret_cast<const float4*>(nz) + e4);
+                if (p.has_q) {
+                  y[4 * e4] = fmaf(z.x, p.inv_mu_coeff, y[4 * e4]); y[4 * e4 + 1] = fmaf(z.y, p.inv_mu_coeff, y[4 * e4 + 1]);
+                  y[4 * e4 + 2] = fmaf(z.z, p.inv_mu_coeff, y[4 * e4 + 2]); y[4 * e4 + 3] = fmaf(z.w, p.inv_mu_coeff, y[4 * e4 + 3]);
+                } else {
+                  y[4 * e4] = z.x; y[4 * e4 + 1] = z.y; y[4 * e4 + 2] = z.z; y[4 * e4 + 3] = z.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<uint4*>(dst + ((ch ^ (c & 7)) << 4)) =
+                  make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
+                             IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7]));
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(bOmFull));
+      // ---- A4: phi-logit of my token in my two tiles -> exchange -> 16-token softmax -> P2 tiles -------------------------------
+      ptx::mbar_wait(bar(bD2Full), par);
+      ptx::tc_fence_after();
+      const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
+      float mylog[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int pr = g + 2 * j;
+        uint32_t dd[32];
+        tmem_ld_cols<32>(trow + cD2 + 32 * pr, dd);
+        ptx::tmem_ld_wait();
+        const int sel = 8 * rl_tok + ((W * pr + xx) >> 2);
+        float dsel = __uint_as_float(dd[0]);
+#pragma unroll
+        for (int c = 1; c < 32; ++c)
+          if (chunk_ok(c)) dsel = (sel == c) ? __uint_as_float(dd[c]) : dsel;
+        mylog[j] = scale_log2 * fmaf(dcoef, dsel, -0.5f * kn[j]);            // log2 units
+        if (tok_ok) lbuf[yl * 28 + W * pr + xx] = mylog[j];
+      }
+      ptx::named_bar_sync(1, kCompute);
+      if (tok_ok) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int pr = g + 2 * j;
+          const int cx = (W * pr + xx) >> 2;
+          const float* lb_ = lbuf + (4 * rl_tok) * 28 + 4 * cx;
+          float lv[16];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const float4 v4 = *reinterpret_cast<const float4*>(lb_ + 28 * r);
+            lv[4 * r] = v4.x; lv[4 * r + 1] = v4.y; lv[4 * r + 2] = v4.z; lv[4 * r + 3] = v4.w;
+          }
+          float mx = lv[0];
+#pragma unroll
+          for (int e = 1; e < 16; ++e) mx = fmaxf(mx, lv[e]);
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) { sum0 += ex2(lv[e] - mx); sum1 += ex2(lv[e + 1] - mx); }
+          const float pt = __fdividef(ex2(mylog[j] - mx), sum0 + sum1);
+          *reinterpret_cast<uint16_t*>(sm + kQS + pr * kSlotBytes + kScratch + ktile_off(8 * rl_tok + cx, tw, kPoolBlk)) = IoFmt<T>::one(pt);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar(bP2Full));
+      // ---- A5: beta^T (TMEM) -> beta rows; own k_bar / beta rows -> the peer ----------------------------------------------------
+      ptx::mbar_wait(bar(bBetaFull), par);
+      ptx::tc_fence_after();
+      {
+        float bt[16];                            // warpgroup 0: chunk rows r_l = 0, 1; warpgroup 1: r_l = 2, 3
+        tmem_ld_cols<16>(trow + cBetaT + 16 * g, reinterpret_cast<uint32_t*>(bt));
+        ptx::tmem_ld_wait();
+        if (feat_lane) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int rl = 2 * g + (c >> 3);
+            if ((c & 7) < NCX && rl < nrl) *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * (r0 + rl) + (c & 7), feat)) = IoFmt<T>::one(bt[c]);
+          }
+        }
+      }
+      ptx::fence_proxy_async_all();
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(2, kCompute);
+      if (warp == 0) {
+        // the peer must have finished phase B of the previous item before its k_bar / beta tiles are overwritten
+        if (round > 0) ptx::mbar_wait_cluster(bar(bStatsFree), par ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t own_off = (uint32_t)r0 * 1024u, own_bytes = (uint32_t)nrl * 1024u, peer_bytes = (uint32_t)(7 - nrl) * 1024u;
+          const uint32_t peer_bar = ptx::mapa(bar(bStatsFull), peer);
+          ptx::bulk_copy_to_peer(ptx::mapa(sm_u32 + kKbar + own_off, peer), sm_u32 + kKbar + own_off, own_bytes, peer_bar);
+          ptx::bulk_copy_to_peer(ptx::mapa(sm_u32 + kBeta + own_off, peer), sm_u32 + kBeta + own_off, own_bytes, peer_bar);
+          ptx::mbar_arrive_expect_tx(bar(bStatsFull), 2u * peer_bytes);       // own rows are in place; the peer's arrive as transaction bytes
+        }
+        __syncwarp();
+      }
+      long long t_b0 = 0;
+      if (prof && tid == 0) t_b0 = clock64();
+      if (has_bias) ptx::mbar_wait(bar(bBiasFull), par);
+
+      // ---- phase B: my warpgroup's two pairs --------------------------------------------------------------------------------
+#pragma unroll 1
+      for (int kk = 0; kk < 2; ++kk) {
+        const int pr = g + 2 * kk;
+        // joint softmax over the 49 keys of my window and the 49 chunks (same arithmetic as the streamed kernel)
+        ptx::mbar_wait(bar(bSFull0 + g), kk);
+        ptx::tc_fence_after();
+        float sl[L], sr[CNP];
+        tmem_ld_cols<L>(trow + cS + (uint32_t)(ws ? LP8 : kOff), reinterpret_cast<uint32_t*>(sl));   // my window's key columns
+        tmem_ld_cols<CNP>(trow + cX, reinterpret_cast<uint32_t*>(sr));
+        ptx::tmem_ld_wait();
+        const float* brow = bias2 + ic * LS;
+        float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          if ((j & 3) == 0) m0 = fmaxf(m0, sl[j]); else if ((j & 3) == 1) m1 = fmaxf(m1, sl[j]);
+          else if ((j & 3) == 2) m2 = fmaxf(m2, sl[j]); else m3 = fmaxf(m3, sl[j]);
+        }
+        float r0m = kNegInf, r1m = kNegInf, r2m = kNegInf, r3m = kNegInf;
+#pragma unroll
+        for (int c = 0; c < CNP; ++c) {
+          if (!chunk_ok(c)) continue;
+          if ((c & 3) == 0) r0m = fmaxf(r0m, sr[c]); else if ((c & 3) == 1) r1m = fmaxf(r1m, sr[c]);
+          else if ((c & 3) == 2) r2m = fmaxf(r2m, sr[c]); else r3m = fmaxf(r3m, sr[c]);
+        }
+        // shift by M = scale * max(raw) + max(bias row) >= true row max (softmax is shift invariant)
+        const float bmax = has_bias ? brow[L] : 0.f;
+        const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2 + bmax;
+        const float mrfa = fmaxf(fmaxf(r0m, r1m), fmaxf(r2m, r3m)) * scale_log2;
+        const float mx = fmaxf(mloc, mrfa);
+        uint32_t pl[LP8 / 2], prf[32], zeros[LP8 / 2];
+        const uint64_t sc2 = pk2(scale_log2, scale_log2), nmx2 = pk2(-mx, -mx);
+        uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+        for (int m4 = 0; m4 < (L + 3) / 4; ++m4) {          // four keys per 16-byte bias load
+          const float4 bq = *reinterpret_cast<const float4*>(brow + 4 * m4);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int m = 2 * m4 + hh;                      // P word: keys 2m, 2m+1
+            if (2 * m < L) {
+              const uint64_t t = fma2(pk2(sl[2 * m], sl[(2 * m + 1 < L) ? 2 * m + 1 : 2 * m]), sc2,
+                                      add2(hh ? pk2(bq.z, bq.w) : pk2(bq.x, bq.y), nmx2));
+              float x0, x1;
+              upk2(t, x0, x1);
+              const float e0 = ex2(x0), e1 = (2 * m + 1 < L) ? ex2(x1) : 0.f;
+              if (m & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1));
+              pl[m] = IoFmt<T>::pack2(e0, e1);
+            }
+          }
+        }
+#pragma unroll
+        for (int m = (L + 1) / 2; m < LP8 / 2; ++m) pl[m] = 0u;
+#pragma unroll
+        for (int m = 0; m < LP8 / 2; ++m) zeros[m] = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (chunk_ok(2 * j)) {
+            const uint64_t t = fma2(pk2(sr[2 * j], sr[chunk_ok(2 * j + 1) ? 2 * j + 1 : 2 * j]), sc2, nmx2);
+            float x0, x1;
+            upk2(t, x0, x1);
+            const float e0 = ex2(x0), e1 = chunk_ok(2 * j + 1) ? ex2(x1) : 0.f;
+            if (j & 1) acc1 = add2(acc1, pk2(e0, e1)); else acc0 = add2(acc0, pk2(e0, e1));
+            prf[j] = IoFmt<T>::pack2(e0, e1);
+          } else {
+            prf[j] = 0u;
+          }
+        }
+        float s0, s1, s2, s3;
+        upk2(acc0, s0, s1);
+        upk2(acc1, s2, s3);
+        // P (16-bit, two per column) overwrites the S columns this thread has finished reading: window b's keys start at the even
+        // position LP8 (words as they are), window a's at the odd position 7 (funnel-shifted, right-aligned in the first 28 columns)
+        if (ws) {
+          tmem_st_cols<LP8 / 2>(trow + cS + LP8 / 2, pl);
+        } else {
+          constexpr int kLead = LP8 / 2 - (L + 1) / 2;
+          uint32_t ps[LP8 / 2];
+#pragma unroll
+          for (int m = 0; m < LP8 / 2; ++m)
+            ps[m] = m < kLead ? 0u : __funnelshift_l(m - kLead > 0 ? pl[m - kLead - 1] : 0u, pl[m - kLead], 16);
+          tmem_st_cols<LP8 / 2>(trow + cS, ps);
+        }
+        tmem_st_cols<LP8 / 2>(trow + cS + (uint32_t)(ws ? 0 : LP8 / 2), zeros);
+        tmem_st_cols<32>(trow + cS + cPrfaOff, prf);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar(bPFull0 + g));
+        if (has_bias && kk == 1) ptx::mbar_arrive(bar(bBiasFree));           // bias table no longer needed for this item
+        const float sum = (s0 + s1) + (s2 + s3);
+        // epilogue: O / rowsum -> staging rows in the pair's (dead) q slot -> the producer warp stores them with one TMA box
+        ptx::mbar_wait(bar(bOFull0 + g), kk);
+        ptx::tc_fence_after();
+        float o[64];
+        tmem_ld_cols<64>(trow + cX, reinterpret_cast<uint32_t*>(o));
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        if (kk == 0) ptx::mbar_arrive(bar(bXFree0 + g)); else ptx::mbar_arrive(bar(bTmemFree));
+        if (iq >= 0 && iq < L) {
+          const float inv = 1.0f / sum;
+          const int orow = ws * L + iq;
+          uint8_t* row = sm + kQS + pr * kSlotBytes + kScratch + orow * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(row + ((ch ^ (orow & 7)) << 4)) =
+                make_uint4(IoFmt<T>::pack2(o[8 * ch] * inv, o[8 * ch + 1] * inv), IoFmt<T>::pack2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                           IoFmt<T>::pack2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), IoFmt<T>::pack2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(bar(bStaged + pr));
+      }
+      // both MMA groups that read this CTA's k_bar / beta tiles have completed (O of my last pair is in): tell the peer
+      if ((warp & 3) == 0 && ptx::elect_one()) ptx::mbar_arrive_remote(ptx::mapa(bar(bStatsFree), peer));
+      if (prof && tid == 0) {
+        const long long t_e = clock64();
+        atomicAdd(prof + 0, (unsigned long long)(t_b0 - t_a0));
+        atomicAdd(prof + 1, (unsigned long long)(t_e - t_b0));
+        atomicAdd(prof + 2, 1ull);
+      }
+    }
+  }
+  // ---- teardown: nobody leaves while the peer may still write into this CTA or signal its barriers ----------------------------
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  ptx::tc_fence_after();
+  if (warp == 9) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct MapKey {
+  const void *q, *k, *v, *out, *w16;
+  long long qs[3], ks[3], vs[3];
+  int B, H, io;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapSet { CUtensorMap tq, tk, tv, tw, to; };
+struct MapCache {
+  static constexpr int kEntries = 16;
+  MapKey key[kEntries];
+  MapSet val[kEntries];
+  int used = 0, next = 0;
+  MapSet* find(const MapKey& k) {
+    for (int i = 0; i < used; ++i) if (key[i] == k) return &val[i];
+    return nullptr;
+  }
+  MapSet* insert(const MapKey& k) {
+    const int i = used < kEntries ? used++ : (next++ % kEntries);
+    key[i] = k;
+    return &val[i];
+  }
+};
+
+__device__ unsigned long long g_prof[4];
+
+template <typename T>
+static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada, const float* noise,
+                            const float* bias, long long bias_sh, void* out, void* workspace, cudaStream_t st, const char** msg) {
+  constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
+  __half* w16 = reinterpret_cast<__half*>(workspace);
+  float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 128 * 64 * sizeof(__half));
+  unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(bias2) + (size_t)g.H * kBiasSlab);
+  const int items = g.B * g.H;
+  const int dev = fused::current_device();
+  const int max_clusters = fused::sm_count(dev) / 2;
+  const int n_clusters = items < max_clusters ? items : max_clusters;
+  fused::pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, L, LS, kBiasSlab / 4, counter, 0u);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *msg = "pack_params launch"; return e; }
+  static thread_local MapCache cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.q = q.ptr; key.k = k.ptr; key.v = v.ptr; key.out = out; key.w16 = w16;
+  key.qs[0] = q.sb; key.qs[1] = q.sn; key.qs[2] = q.sh; key.ks[0] = k.sb; key.ks[1] = k.sn; key.ks[2] = k.sh;
+  key.vs[0] = v.sb; key.vs[1] = v.sn; key.vs[2] = v.sh;
+  key.B = g.B; key.H = g.H; key.io = io;
+  MapSet* ms = cache.find(key);
+  if (!ms) {
+    MapSet fresh;
+    View ov;
+    ov.ptr = out; ov.sh = 64; ov.sn = (long long)g.H * 64; ov.sb = (long long)g.N * g.H * 64;
+    if (!fused::make_box_map(&fresh.tq, q, g, io, W, 16) || !fused::make_box_map(&fresh.tk, k, g, io, W, 16) ||
+        !fused::make_box_map(&fresh.tv, v, g, io, W, 16) || !fused::make_weight_map(&fresh.tw, w16) ||
+        !fused::make_box_map(&fresh.to, ov, g, io, W, 2 * W)) {
+      *msg = "cuTensorMapEncodeTiled failed";
+      return cudaErrorInvalidValue;
+    }
+    ms = cache.insert(key);
+    *ms = fresh;
+  }
+  Params p{};
+  p.B = g.B; p.H = g.H; p.items = items;
+  p.b_q = ada.b_q; p.g_q = ada.ln_gain_q; p.beta_q = ada.ln_bias_q;
+  p.b_k = ada.b_k; p.g_k = ada.ln_gain_k; p.beta_k = ada.ln_bias_k;
+  p.has_q = ada.w_q != nullptr;
+  p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
+  p.noise = noise; p.bias2 = bias ? bias2 : nullptr;
+  static const bool trace = [] { const char* t = getenv("EVA_SM100_TRACE"); return t && t[0] == '1'; }();
+  p.prof = nullptr;
+  if (trace) cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_prof);
+  auto kern = eva_cluster_kernel<T>;
+  static bool attr_set[fused::kMaxDevices] = {};
+  if (dev < 0 || dev >= fused::kMaxDevices || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamic);
+    if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
+    if (dev >= 0 && dev < fused::kMaxDevices) attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_clusters); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kDynamic; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;            // overlap the prologue with pack_params (griddepcontrol.wait in the producer)
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  e = cudaLaunchKernelEx(&cfg, kern, ms->tq, ms->tk, ms->tv, ms->tw, ms->to, p);
+  *msg = "kernel launch";
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+}  // namespace cluster2
+
+static bool cluster_disabled() {
+  static const bool v = [] { const char* e = getenv("EVA_SM100_DISABLE_CLUSTER"); return e && e[0] == '1'; }();
+  return v;
+}
+
+// c3 geometry only: 28 x 28 tokens, window 7, 4 x 4 chunks, head_dim 64, 16-bit, no halo, no padding mask
+bool cluster_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask) {
+  if (cluster_disabled()) return false;
+  if (g.dims != 2 || g.ext != 0 || g.chunk_ext != 0 || g.causal || g.D != 64 || mask != nullptr) return false;
+  if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
+  if (g.window != 7 || g.n_chunks != 49 || g.gw != 28 || g.gh != 28 || g.chunk != 4) return false;
+  for (const View* x : {&q, &k, &v}) {
+    if (x->sh * 2 % 16 || x->sn * 2 % 16 || x->sb * 2 % 16) return false;
+    if (x->sh <= 0 || x->sn <= 0 || x->sb <= 0) return false;
+  }
+  return fused::get_encode() != nullptr;
+}
+
+extern "C" int eva_debug_read_cluster_prof(unsigned long long* dst) {
+  return cudaMemcpyFromSymbol(dst, cluster2::g_prof, sizeof(cluster2::g_prof)) == cudaSuccess ? 0 : -5;
+}
+extern "C" int eva_debug_reset_cluster_prof(void) {
+  unsigned long long z[4] = {0, 0, 0, 0};
+  return cudaMemcpyToSymbol(cluster2::g_prof, z, sizeof(z)) == cudaSuccess ? 0 : -5;
+}
+
+cudaError_t launch_cluster(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
+                           const float* noise, const float* bias, long long bias_sh, void* out, void* workspace, cudaStream_t st,
+                           const char** msg) {
+  if (io_dtype == EVA_F16) return cluster2::launch_t<__half>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  return cluster2::launch_t<__nv_bfloat16>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+}
+
+}  // namespace eva

@@ -25,6 +25,13 @@ cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& 
                          const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,
                          void* out, void* workspace, cudaStream_t st, const char** msg);
 
+// Cluster-resident fused path (eva_cluster_sm100.cu): the c3 geometry (28 x 28 tokens, window 7, 4 x 4 chunks), one item per
+// two-CTA cluster with k / v resident in shared memory; same workspace layout as the streamed fused kernel
+bool cluster_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask);
+cudaError_t launch_cluster(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
+                           const float* noise, const float* bias, long long bias_sh, void* out, void* workspace, cudaStream_t st,
+                           const char** msg);
+
 // Causal window attention on tcgen05 (eva_causal_sm100.cu): stage B of the causal layer for window 256 / head_dim 64 / 16-bit I/O
 bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                              const float* bias, long long bias_sh);

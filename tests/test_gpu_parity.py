@@ -311,7 +311,7 @@ def test_fused_kernel_variants_fp16(grid, chunk, adaptive, with_noise, with_bias
     out, path = _abi.eva_forward(qd[:, :, 0], qd[:, :, 1], qd[:, :, 2], geom, _abi_ada(ada, dev, 0.5),
                                  noise=noise.to(dev) if with_noise else None, bias=bias.to(dev) if with_bias else None,
                                  return_path=True)
-    assert path == 1
+    assert path == (3 if grid == 28 else 1)          # 28-wide grid: cluster-resident kernel; 14-wide: streamed kernel
     err = rel_l2(out.cpu(), want)
     assert err < TOL_F16, (grid, adaptive, with_noise, with_bias, err)
 
@@ -331,7 +331,7 @@ def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B):
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     geom = _abi.eva_geometry(q, seq_shape=(grid, grid), window=7, ext=0, chunk=chunk, chunk_ext=0)
     out, path = _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
-    assert path == 1
+    assert path == (3 if grid == 28 else 1)
     kb, bt = _abi.eva_chunk_stats(q, k, v, geom, ada)
     ref = _abi.eva_window_attention(q, k, v, geom, k_bar=kb, beta=bt, bias=bias)
     per_item = ((out.float() - ref.float()).view(B, N, H, d).pow(2).sum((1, 3)).sqrt() /
