@@ -66,7 +66,7 @@ constexpr int kQBOff = kScratch + 8192;         // q_bar' tile [32][64] in slot 
 
 enum Bar {
   bFullQ = 0, bFullK = 4, bFullV = 8, bKFree = 12, bVFree = 16, bStaged = 20,
-  bWFull = 24, bBiasFull, bBiasFree, bPoolFull, bAFull, bLinFull, bOmFull, bD2Full, bP2Full, bBetaFull, bQReady, bTmemFree,
+  bWFull = 24, bBiasFull, bBiasFree, bPoolFull, bAFull, bLinFull, bOmFull, bD2Full, bQReady, bTmemFree,
   bStatsFull, bStatsFree, bSFull0, bSFull1, bPFull0, bPFull1, bOFull0, bOFull1, bXFree0, bXFree1, kNumBars
 };
 constexpr int kTmemPtr = kBars + kNumBars * 8;
@@ -80,16 +80,17 @@ constexpr uint32_t cQ = 0;                      // 4 x 32: q of the four pairs (
 constexpr uint32_t cWg0 = 128, cWgPitch = 192;  // per warpgroup: S_loc / P in [0, 112), chunk logits then O in [112, 176)
 constexpr uint32_t cXOff = 2 * LP8, cPrfaOff = LP8;
 constexpr uint32_t cPoolQ = 128, cPoolK = 256;  // stage A (overlays the warpgroup regions; the phases never overlap in time)
-constexpr uint32_t cLin = 128, cD2 = 256, cBetaT = 384;
+constexpr uint32_t cLin = 128, cD2 = 256;
 
 struct Params {
   int B, H, items;
   const float *b_q, *g_q, *beta_q, *b_k, *g_k, *beta_k;
-  int has_q;
+  int has_q, prefetch_next;
   float mu_coeff, inv_mu_coeff, ln_eps;
   const float* noise;
   const float* bias2;
   unsigned long long* prof;       // optional per-phase cycle counters of cluster 0 (EVA_SM100_TRACE=1)
+  long long* prof_last;
 };
 
 __host__ __device__ constexpr bool chunk_ok(int c) { return c < CNP && (c & 7) < NCX; }
@@ -143,8 +144,6 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
     ptx::mbar_init(bar(bLinFull), 1);
     ptx::mbar_init(bar(bOmFull), kCompute);
     ptx::mbar_init(bar(bD2Full), 1);
-    ptx::mbar_init(bar(bP2Full), kCompute);
-    ptx::mbar_init(bar(bBetaFull), 1);
     ptx::mbar_init(bar(bQReady), kCompute);
     ptx::mbar_init(bar(bTmemFree), kCompute);
     ptx::mbar_init(bar(bStatsFull), 1);
@@ -202,6 +201,15 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
       const int nxt = item + n_clusters;
       const bool has_next = nxt < p.items;
       const int bn = has_next ? nxt / p.H : 0, hn = has_next ? nxt % p.H : 0;
+      if (has_next && p.prefetch_next && ptx::elect_one()) {   // warm L2 with the next item's tiles: their loads are issued late (as pairs retire)
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) {
+          ptx::tma_prefetch_5d(&t_q, 0, hn, W * pr, y0, bn);
+          ptx::tma_prefetch_5d(&t_k, 0, hn, W * pr, y0, bn);
+          ptx::tma_prefetch_5d(&t_v, 0, hn, W * pr, y0, bn);
+        }
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int pr = 0; pr < kTiles; ++pr) {      // pairs retire in this order (warpgroup 0: pairs 0, 2; warpgroup 1: pairs 1, 3)
         ptx::mbar_wait(bar(bKFree + pr), par);
@@ -282,22 +290,15 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
           }
           ptx::umma_commit(bar(bD2Full));
         }
-        ptx::mbar_wait(bar(bP2Full), par);       // P2 tiles written
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int pr = 0; pr < kTiles; ++pr) {    // beta^T += V^T P2^T
-          ptx::mbar_wait(bar(bFullV + pr), par);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              ptx::umma_ss(tmem + cBetaT, tile(dV0, pr) + 128 * ks, dQ0 + (uint64_t)((pr * kSlotBytes + kScratch) >> 4) + tokB(ks), id_pool,
-                           (pr | ks) != 0);
-            if (pr == kTiles - 1) ptx::umma_commit(bar(bBetaFull));
-          }
-        }
       }
       // ---- phase B: this warpgroup's two pairs ------------------------------------------------------------------------
+      if (g == 1) {                              // (long complete: stage A used the tiles; keeps this issuer's own view ordered)
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) { ptx::mbar_wait(bar(bFullK + pr), par); ptx::mbar_wait(bar(bFullV + pr), par); }
+      } else {
+#pragma unroll 1
+        for (int pr = 0; pr < kTiles; ++pr) ptx::mbar_wait(bar(bFullV + pr), par);
+      }
       ptx::mbar_wait(bar(bQReady), par);         // q of all pairs is in tensor memory
       ptx::mbar_wait_cluster(bar(bStatsFull), par);   // k_bar / beta complete: own rows written, the peer's rows received
       ptx::tc_fence_after();
@@ -357,8 +358,10 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
     for (int item = cid; item < p.items; item += n_clusters, ++round) {
       const int b = item / p.H, h = item % p.H;
       const uint32_t par = round & 1u;
-      long long t_a0 = 0;
-      if (prof && tid == 0) t_a0 = clock64();
+      long long tp[16];
+      int np_ = 0;
+      auto mark = [&]() { if (prof && tid == 0 && np_ < 16) tp[np_++] = clock64(); };
+      mark();                                  // 0: item start
       // ---- A1: q of my pairs -> tensor memory; |k|^2 of my slot row ---------------------------------------------------
       float kn[2];
 #pragma unroll
@@ -379,24 +382,15 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
           for (int e = 0; e < 32; ++e) qv[e] = 0u;
         }
         tmem_st_cols<32>(trow + cQ + 32 * pr, qv);
-        ptx::mbar_wait(bar(bFullK + pr), par);
-        const uint8_t* Kr = sm + kK + pr * kSlotBytes + tw * 128;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(Kr + ((ch ^ (tw & 7)) << 4));
-          const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
-          a0 = fmaf(a.x, a.x, a0); a1 = fmaf(a.y, a.y, a1); a2 = fmaf(b2.x, b2.x, a2); a3 = fmaf(b2.y, b2.y, a3);
-          a0 = fmaf(c2.x, c2.x, a0); a1 = fmaf(c2.y, c2.y, a1); a2 = fmaf(d2.x, d2.x, a2); a3 = fmaf(d2.y, d2.y, a3);
-        }
-        kn[j] = (a0 + a1) + (a2 + a3);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(bQReady));
+      mark();                                  // 1: q copied, |k|^2 done
       // ---- A2: pooled sums (TMEM) -> chunk means tile [8 r_l + cx (+32 on the k side)][feat] (fp16) -------------------------
       ptx::mbar_wait(bar(bPoolFull), par);
       ptx::tc_fence_after();
+      mark();                                  // 2: pooling MMAs done
       {
         float acc[4][NCX];
 #pragma unroll
@@ -413,6 +407,7 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
 #pragma unroll
             for (int x = 0; x < W; ++x) acc[r][(W * pr + x) >> 2] += v[8 * r + x];
         }
+        ptx::mbar_wait(bar(bQReady), par);       // every thread has copied its q tiles: slot 0 may be overwritten
         if (feat_lane) {
           uint8_t* At = sm + kQS + kScratch;
 #pragma unroll
@@ -425,114 +420,132 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(bAFull));
+      mark();                                  // 3: means written
       // ---- A3: Linear result -> bias, LayerNorm -> q_bar' rows (q side) / k_bar rows (k side) ----------------------------
+      // Rows of the M = 64 accumulator sit on lanes 0-15 of each TMEM quarter (quarters 0, 1: q side, 2, 3: k side).  Two warps
+      // (one per warpgroup) can read the same quarter, so every row is normalised by TWO threads: warpgroup g takes features
+      // [32 g, 32 g + 32) and the halves meet through one (sum, sum of squares) exchange.
       ptx::mbar_wait(bar(bLinFull), par);
       ptx::tc_fence_after();
+      mark();                                  // 4: Linear done
       {
-        // the means tile is dead: clear the four P2 tiles (P2_0 overlays it)
-        for (int z = tw + kWg * g; z < 4 * 8192 / 16; z += kCompute) {
-          const int pr = z >> 9, o = z & 511;
-          reinterpret_cast<uint4*>(sm + kQS + pr * kSlotBytes + kScratch)[o] = make_uint4(0, 0, 0, 0);
-        }
-        // rows of the M = 64 accumulator: quarter 0, 1 = q side (rows 0-31), quarter 2, 3 = k side; warpgroup 0 takes the q
-        // side, warpgroup 1 the k side
         const bool kside = wq >= 2;
-        if (kside == (g == 1)) {                 // warp-uniform: tcgen05.ld is warp-collective; lanes 16-31 carry no row
-          const int c = (16 * wq + (lane & 15)) & 31;   // 8 r_l + cx
-          float y[64];
-          tmem_ld_cols<64>(trow + cLin + (kside ? 64u : 0u), reinterpret_cast<uint32_t*>(y));
-          ptx::tmem_ld_wait();
-          const float* lnp = reinterpret_cast<const float*>(sm + kLn) + (kside ? 192 : 0);   // bias | gain | beta
-          const bool has_lin_bias = kside ? (p.b_k != nullptr) : (p.b_q != nullptr);
-          const bool has_ln = kside ? (p.g_k != nullptr) : (p.g_q != nullptr);
-          if (has_lin_bias) {
+        const int m = 16 * wq + (lane & 15);     // accumulator row
+        const int c = m & 31;                    // 8 r_l + cx
+        float y[32];
+        tmem_ld_cols<32>(trow + cLin + (kside ? 64u : 0u) + 32u * g, reinterpret_cast<uint32_t*>(y));
+        ptx::tmem_ld_wait();
+        const float* lnp = reinterpret_cast<const float*>(sm + kLn) + (kside ? 192 : 0) + 32 * g;   // bias | gain | beta
+        const bool has_lin_bias = kside ? (p.b_k != nullptr) : (p.b_q != nullptr);
+        const bool has_ln = kside ? (p.g_k != nullptr) : (p.g_q != nullptr);
+        if (has_lin_bias) {
 #pragma unroll
-            for (int e4 = 0; e4 < 16; ++e4) {
-              const float4 bb = *reinterpret_cast<const float4*>(lnp + 4 * e4);
-              y[4 * e4] += bb.x; y[4 * e4 + 1] += bb.y; y[4 * e4 + 2] += bb.z; y[4 * e4 + 3] += bb.w;
-            }
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 bb = *reinterpret_cast<const float4*>(lnp + 4 * e4);
+            y[4 * e4] += bb.x; y[4 * e4 + 1] += bb.y; y[4 * e4 + 2] += bb.z; y[4 * e4 + 3] += bb.w;
           }
-          if (has_ln) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        }
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) { s0 += y[e]; s1 += y[e + 1]; s2 += y[e + 2]; s3 += y[e + 3]; }
-            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64);
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        for (int e = 0; e < 32; e += 2) { s0 += y[e]; s1 += y[e + 1]; q0 = fmaf(y[e], y[e], q0); q1 = fmaf(y[e + 1], y[e + 1], q1); }
+        float2* xch = reinterpret_cast<float2*>(lbuf);             // [64 rows][2 halves]; the logit exchange buffer is idle until A4
+        if (feat_lane) xch[2 * m + g] = make_float2(s0 + s1, q0 + q1);
+        ptx::named_bar_sync(3, kCompute);
+        if (has_ln) {
+          const float2 other = xch[2 * m + (g ^ 1)];
+          const float mean = (s0 + s1 + other.x) * (1.0f / 64);
+          const float var = fmaxf((q0 + q1 + other.y) * (1.0f / 64) - mean * mean, 0.f);
+          const float inv = rsqrtf(var + p.ln_eps);
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) {
-              const float d0 = y[e] - mean, d1 = y[e + 1] - mean, d2_ = y[e + 2] - mean, d3 = y[e + 3] - mean;
-              v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2_, d2_, v2); v3 = fmaf(d3, d3, v3);
-            }
-            const float inv = 1.0f / sqrtf(((v0 + v1) + (v2 + v3)) * (1.0f / 64) + p.ln_eps);
-#pragma unroll
-            for (int e4 = 0; e4 < 16; ++e4) {
-              const float4 gg = *reinterpret_cast<const float4*>(lnp + 64 + 4 * e4);
-              const float4 bb = *reinterpret_cast<const float4*>(lnp + 128 + 4 * e4);
-              y[4 * e4] = (y[4 * e4] - mean) * inv * gg.x + bb.x;
-              y[4 * e4 + 1] = (y[4 * e4 + 1] - mean) * inv * gg.y + bb.y;
-              y[4 * e4 + 2] = (y[4 * e4 + 2] - mean) * inv * gg.z + bb.z;
-              y[4 * e4 + 3] = (y[4 * e4 + 3] - mean) * inv * gg.w + bb.w;
-            }
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 gg = *reinterpret_cast<const float4*>(lnp + 64 + 4 * e4);
+            const float4 bb = *reinterpret_cast<const float4*>(lnp + 128 + 4 * e4);
+            y[4 * e4] = (y[4 * e4] - mean) * inv * gg.x + bb.x;
+            y[4 * e4 + 1] = (y[4 * e4 + 1] - mean) * inv * gg.y + bb.y;
+            y[4 * e4 + 2] = (y[4 * e4 + 2] - mean) * inv * gg.z + bb.z;
+            y[4 * e4 + 3] = (y[4 * e4 + 3] - mean) * inv * gg.w + bb.w;
           }
-          const int rl = c >> 3, cx = c & 7;
-          if (feat_lane && cx < NCX && rl < nrl) {
-            uint8_t* dst;
-            if (kside) {
-              dst = KBt + (8 * r0 + c) * 128;
-            } else {
-              // omega = mu_coeff (q_bar + k_bar) + noise is applied as mu_coeff ((q_bar + noise / mu_coeff) + k_bar): the phi-logit
-              // MMAs accumulate K q'^T and K k_bar^T, so the two halves never have to meet in a thread
-              dst = sm + kQS + kQBOff + c * 128;
-              const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * (NCX * 7) + (r0 + rl) * NCX + cx) * 64 : nullptr;
+        }
+        const int rl = c >> 3, cx = c & 7;
+        if (feat_lane && cx < NCX && rl < nrl) {
+          uint8_t* dst;
+          if (kside) {
+            dst = KBt + (8 * r0 + c) * 128;
+          } else {
+            // omega = mu_coeff (q_bar + k_bar) + noise is applied as mu_coeff ((q_bar + noise / mu_coeff) + k_bar): the phi-logit
+            // MMAs accumulate K q'^T and K k_bar^T, so the two sides never have to meet in a thread
+            dst = sm + kQS + kQBOff + c * 128;
+            const float* nz = p.noise ? p.noise + (((long long)b * p.H + h) * (NCX * 7) + (r0 + rl) * NCX + cx) * 64 + 32 * g : nullptr;
 #pragma unroll
-              for (int e4 = 0; e4 < 16; ++e4) {
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nz) z = __ldg(reinterpret_cast<const float4*>(nz) + e4);
-                if (p.has_q) {
-                  y[4 * e4] = fmaf(z.x, p.inv_mu_coeff, y[4 * e4]); y[4 * e4 + 1] = fmaf(z.y, p.inv_mu_coeff, y[4 * e4 + 1]);
-                  y[4 * e4 + 2] = fmaf(z.z, p.inv_mu_coeff, y[4 * e4 + 2]); y[4 * e4 + 3] = fmaf(z.w, p.inv_mu_coeff, y[4 * e4 + 3]);
-                } else {
-                  y[4 * e4] = z.x; y[4 * e4 + 1] = z.y; y[4 * e4 + 2] = z.z; y[4 * e4 + 3] = z.w;
-                }
+            for (int e4 = 0; e4 < 8; ++e4) {
+              float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (nz) z = __ldg(reinterpret_cast<const float4*>(nz) + e4);
+              if (p.has_q) {
+                y[4 * e4] = fmaf(z.x, p.inv_mu_coeff, y[4 * e4]); y[4 * e4 + 1] = fmaf(z.y, p.inv_mu_coeff, y[4 * e4 + 1]);
+                y[4 * e4 + 2] = fmaf(z.z, p.inv_mu_coeff, y[4 * e4 + 2]); y[4 * e4 + 3] = fmaf(z.w, p.inv_mu_coeff, y[4 * e4 + 3]);
+              } else {
+                y[4 * e4] = z.x; y[4 * e4 + 1] = z.y; y[4 * e4 + 2] = z.z; y[4 * e4 + 3] = z.w;
               }
             }
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<uint4*>(dst + ((ch ^ (c & 7)) << 4)) =
-                  make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
-                             IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7]));
           }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(dst + (((4 * g + ch) ^ (c & 7)) << 4)) =
+                make_uint4(IoFmt<T>::pack2(y[8 * ch], y[8 * ch + 1]), IoFmt<T>::pack2(y[8 * ch + 2], y[8 * ch + 3]),
+                           IoFmt<T>::pack2(y[8 * ch + 4], y[8 * ch + 5]), IoFmt<T>::pack2(y[8 * ch + 6], y[8 * ch + 7]));
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar(bOmFull));
-      // ---- A4: phi-logit of my token in my two tiles -> exchange -> 16-token softmax -> P2 tiles -------------------------------
-      ptx::mbar_wait(bar(bD2Full), par);
-      ptx::tc_fence_after();
-      const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
-      float mylog[2];
+      mark();                                  // 5: LayerNorm rows written
+      // |k|^2 of my slot row in my two tiles, under the phi-logit MMAs
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int pr = g + 2 * j;
-        uint32_t dd[32];
-        tmem_ld_cols<32>(trow + cD2 + 32 * pr, dd);
-        ptx::tmem_ld_wait();
-        const int sel = 8 * rl_tok + ((W * pr + xx) >> 2);
-        float dsel = __uint_as_float(dd[0]);
+        ptx::mbar_wait(bar(bFullK + pr), par);
+        const uint8_t* Kr = sm + kK + pr * kSlotBytes + tw * 128;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int c = 1; c < 32; ++c)
-          if (chunk_ok(c)) dsel = (sel == c) ? __uint_as_float(dd[c]) : dsel;
-        mylog[j] = scale_log2 * fmaf(dcoef, dsel, -0.5f * kn[j]);            // log2 units
-        if (tok_ok) lbuf[yl * 28 + W * pr + xx] = mylog[j];
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(Kr + ((ch ^ (tw & 7)) << 4));
+          const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
+          a0 = fmaf(a.x, a.x, a0); a1 = fmaf(a.y, a.y, a1); a2 = fmaf(b2.x, b2.x, a2); a3 = fmaf(b2.y, b2.y, a3);
+          a0 = fmaf(c2.x, c2.x, a0); a1 = fmaf(c2.y, c2.y, a1); a2 = fmaf(d2.x, d2.x, a2); a3 = fmaf(d2.y, d2.y, a3);
+        }
+        kn[j] = (a0 + a1) + (a2 + a3);
       }
-      ptx::named_bar_sync(1, kCompute);
-      if (tok_ok) {
+      // ---- A4: phi-logit of my token in my two tiles -> exchange buffer ----------------------------------------------------
+      ptx::mbar_wait(bar(bD2Full), par);
+      ptx::tc_fence_after();
+      mark();                                  // 6: phi-logits ready
+      {
+        const float dcoef = p.has_q ? p.mu_coeff : 1.0f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int pr = g + 2 * j;
-          const int cx = (W * pr + xx) >> 2;
-          const float* lb_ = lbuf + (4 * rl_tok) * 28 + 4 * cx;
+          uint32_t dd[32];
+          tmem_ld_cols<32>(trow + cD2 + 32 * pr, dd);
+          ptx::tmem_ld_wait();
+          const int sel = 8 * rl_tok + ((W * pr + xx) >> 2);
+          float dsel = __uint_as_float(dd[0]);
+#pragma unroll
+          for (int c = 1; c < 32; ++c)
+            if (chunk_ok(c)) dsel = (sel == c) ? __uint_as_float(dd[c]) : dsel;
+          if (tok_ok) lbuf[yl * 28 + W * pr + xx] = scale_log2 * fmaf(dcoef, dsel, -0.5f * kn[j]);            // log2 units
+        }
+      }
+      ptx::mbar_wait(bar(bFullV + wq), par);     // each v tile's arrival is observed by two warps; the barrier below publishes it to all
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(1, kCompute);
+      mark();                                  // 7: logits exchanged
+      // ---- A5: per (chunk, 8-feature slice) thread: 16-token softmax and beta = sum_j p_j v_j straight from the resident v tiles
+      //      (no P2 tiles, no MMA round trip); rows go to the local beta tile, then own k_bar / beta rows to the peer -----------
+      {
+        const int ci = tid >> 3, sl8 = tid & 7;  // chunk r_l * 7 + cx, feature slice
+        if (ci < NCX * nrl) {
+          const int rl = ci / NCX, cx = ci - rl * NCX;
+          const float* lb_ = lbuf + (4 * rl) * 28 + 4 * cx;
           float lv[16];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
@@ -544,32 +557,40 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
           for (int e = 1; e < 16; ++e) mx = fmaxf(mx, lv[e]);
           float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) { sum0 += ex2(lv[e] - mx); sum1 += ex2(lv[e + 1] - mx); }
-          const float pt = __fdividef(ex2(mylog[j] - mx), sum0 + sum1);
-          *reinterpret_cast<uint16_t*>(sm + kQS + pr * kSlotBytes + kScratch + ktile_off(8 * rl_tok + cx, tw, kPoolBlk)) = IoFmt<T>::one(pt);
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(bar(bP2Full));
-      // ---- A5: beta^T (TMEM) -> beta rows; own k_bar / beta rows -> the peer ----------------------------------------------------
-      ptx::mbar_wait(bar(bBetaFull), par);
-      ptx::tc_fence_after();
-      {
-        float bt[16];                            // warpgroup 0: chunk rows r_l = 0, 1; warpgroup 1: r_l = 2, 3
-        tmem_ld_cols<16>(trow + cBetaT + 16 * g, reinterpret_cast<uint32_t*>(bt));
-        ptx::tmem_ld_wait();
-        if (feat_lane) {
+          for (int e = 0; e < 16; e += 2) { lv[e] = ex2(lv[e] - mx); lv[e + 1] = ex2(lv[e + 1] - mx); sum0 += lv[e]; sum1 += lv[e + 1]; }
+          uint64_t acc[4];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int rl = 2 * g + (c >> 3);
-            if ((c & 7) < NCX && rl < nrl) *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * (r0 + rl) + (c & 7), feat)) = IoFmt<T>::one(bt[c]);
+          for (int e = 0; e < 4; ++e) acc[e] = pk2(0.f, 0.f);
+          const int yy0 = 4 * (r0 + rl) - y0;    // box row of the chunk's first raster row
+#pragma unroll
+          for (int dx = 0; dx < 4; ++dx) {
+            const int x = 4 * cx + dx;
+            const int wx = (x * 37) >> 8;        // x / 7 for x < 28
+            const uint8_t* vcol = sm + kV + wx * kSlotBytes + (kOff + (x - W * wx)) * 128;
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy) {
+              const int row = kOff + (x - W * wx) + W * (yy0 + dy);
+              const uint4 raw = *reinterpret_cast<const uint4*>(vcol + W * (yy0 + dy) * 128 + ((sl8 ^ (row & 7)) << 4));
+              const float pj = lv[4 * dy + dx];
+              const uint64_t pp = pk2(pj, pj);
+              const float2 a = IoFmt<T>::unpack2(raw.x), b2 = IoFmt<T>::unpack2(raw.y), c2 = IoFmt<T>::unpack2(raw.z), d2 = IoFmt<T>::unpack2(raw.w);
+              acc[0] = fma2(pk2(a.x, a.y), pp, acc[0]); acc[1] = fma2(pk2(b2.x, b2.y), pp, acc[1]);
+              acc[2] = fma2(pk2(c2.x, c2.y), pp, acc[2]); acc[3] = fma2(pk2(d2.x, d2.y), pp, acc[3]);
+            }
           }
+          const float inv = __fdividef(1.0f, sum0 + sum1);
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { upk2(acc[e], o8[2 * e], o8[2 * e + 1]); }
+          const int crow = 8 * (r0 + rl) + cx;
+          *reinterpret_cast<uint4*>(BTt + crow * 128 + ((sl8 ^ (crow & 7)) << 4)) =
+              make_uint4(IoFmt<T>::pack2(o8[0] * inv, o8[1] * inv), IoFmt<T>::pack2(o8[2] * inv, o8[3] * inv),
+                         IoFmt<T>::pack2(o8[4] * inv, o8[5] * inv), IoFmt<T>::pack2(o8[6] * inv, o8[7] * inv));
         }
       }
       ptx::fence_proxy_async_all();
-      ptx::tc_fence_before();
       ptx::named_bar_sync(2, kCompute);
+      mark();                                  // 8: beta rows written
       if (warp == 0) {
         // the peer must have finished phase B of the previous item before its k_bar / beta tiles are overwritten
         if (round > 0) ptx::mbar_wait_cluster(bar(bStatsFree), par ^ 1u);
@@ -582,8 +603,7 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
         }
         __syncwarp();
       }
-      long long t_b0 = 0;
-      if (prof && tid == 0) t_b0 = clock64();
+      mark();                                  // 9: own rows sent
       if (has_bias) ptx::mbar_wait(bar(bBiasFull), par);
 
       // ---- phase B: my warpgroup's two pairs --------------------------------------------------------------------------------
@@ -593,6 +613,7 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
         // joint softmax over the 49 keys of my window and the 49 chunks (same arithmetic as the streamed kernel)
         ptx::mbar_wait(bar(bSFull0 + g), kk);
         ptx::tc_fence_after();
+        mark();                                // 10 / 13: S ready
         float sl[L], sr[CNP];
         tmem_ld_cols<L>(trow + cS + (uint32_t)(ws ? LP8 : kOff), reinterpret_cast<uint32_t*>(sl));   // my window's key columns
         tmem_ld_cols<CNP>(trow + cX, reinterpret_cast<uint32_t*>(sr));
@@ -676,8 +697,10 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
         if (has_bias && kk == 1) ptx::mbar_arrive(bar(bBiasFree));           // bias table no longer needed for this item
         const float sum = (s0 + s1) + (s2 + s3);
         // epilogue: O / rowsum -> staging rows in the pair's (dead) q slot -> the producer warp stores them with one TMA box
+        mark();                                // 11 / 14: P written
         ptx::mbar_wait(bar(bOFull0 + g), kk);
         ptx::tc_fence_after();
+        mark();                                // 12 / 15: O ready
         float o[64];
         tmem_ld_cols<64>(trow + cX, reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
@@ -700,9 +723,11 @@ eva_cluster_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constan
       if ((warp & 3) == 0 && ptx::elect_one()) ptx::mbar_arrive_remote(ptx::mapa(bar(bStatsFree), peer));
       if (prof && tid == 0) {
         const long long t_e = clock64();
-        atomicAdd(prof + 0, (unsigned long long)(t_b0 - t_a0));
-        atomicAdd(prof + 1, (unsigned long long)(t_e - t_b0));
-        atomicAdd(prof + 2, 1ull);
+        for (int i = 0; i + 1 < np_; ++i) atomicAdd(prof + i, (unsigned long long)(tp[i + 1] - tp[i]));
+        atomicAdd(prof + 15, (unsigned long long)(t_e - tp[np_ - 1]));
+        atomicAdd(prof + 16, 1ull);
+        if (round > 0) atomicAdd(prof + 17, (unsigned long long)(tp[0] - p.prof_last[0]));
+        p.prof_last[0] = t_e;
       }
     }
   }
@@ -741,7 +766,7 @@ struct MapCache {
   }
 };
 
-__device__ unsigned long long g_prof[4];
+__device__ unsigned long long g_prof[20];
 
 template <typename T>
 static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada, const float* noise,
@@ -785,9 +810,14 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   p.has_q = ada.w_q != nullptr;
   p.mu_coeff = ada.mu_coeff; p.inv_mu_coeff = ada.mu_coeff != 0.f ? 1.0f / ada.mu_coeff : 0.f; p.ln_eps = ada.ln_eps;
   p.noise = noise; p.bias2 = bias ? bias2 : nullptr;
+  static const int prefetch_next = fused::env_int("EVA_SM100_CLUSTER_PREFETCH", 1);
+  p.prefetch_next = prefetch_next;
   static const bool trace = [] { const char* t = getenv("EVA_SM100_TRACE"); return t && t[0] == '1'; }();
   p.prof = nullptr;
-  if (trace) cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_prof);
+  if (trace) {
+    cudaGetSymbolAddress(reinterpret_cast<void**>(&p.prof), g_prof);
+    p.prof_last = reinterpret_cast<long long*>(p.prof + 19);
+  }
   auto kern = eva_cluster_kernel<T>;
   static bool attr_set[fused::kMaxDevices] = {};
   if (dev < 0 || dev >= fused::kMaxDevices || !attr_set[dev]) {
@@ -811,9 +841,19 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
 
 }  // namespace cluster2
 
+// Measured (profiles/r02): correct (3.1e-4 vs the float64 oracle) and reads k/v/q from L2 1.26x per item (streamed kernel: 2.4x),
+// but one item at a time per SM pair is a serial chain of ~16 MMA <-> SIMT hand-offs that nothing overlaps (shared memory holds
+// exactly one half item), so it runs at 38 % of the HBM roofline against 48-53 % for the streamed kernel with its two
+// independent CTAs per SM.  It is therefore OPT-IN: EVA_SM100_CLUSTER=1, or eva_debug_set_cluster_mode(1) at run time (tests).
+static int g_cluster_mode = -1;            // -1: environment, 0: off, 1: on
+extern "C" int eva_debug_set_cluster_mode(int mode) {
+  const int prev = g_cluster_mode;
+  g_cluster_mode = mode;
+  return prev;
+}
 static bool cluster_disabled() {
-  static const bool v = [] { const char* e = getenv("EVA_SM100_DISABLE_CLUSTER"); return e && e[0] == '1'; }();
-  return v;
+  static const bool env_on = [] { const char* e = getenv("EVA_SM100_CLUSTER"); return e && e[0] == '1'; }();
+  return g_cluster_mode < 0 ? !env_on : g_cluster_mode == 0;
 }
 
 // c3 geometry only: 28 x 28 tokens, window 7, 4 x 4 chunks, head_dim 64, 16-bit, no halo, no padding mask
@@ -833,7 +873,7 @@ extern "C" int eva_debug_read_cluster_prof(unsigned long long* dst) {
   return cudaMemcpyFromSymbol(dst, cluster2::g_prof, sizeof(cluster2::g_prof)) == cudaSuccess ? 0 : -5;
 }
 extern "C" int eva_debug_reset_cluster_prof(void) {
-  unsigned long long z[4] = {0, 0, 0, 0};
+  unsigned long long z[20] = {};
   return cudaMemcpyToSymbol(cluster2::g_prof, z, sizeof(z)) == cudaSuccess ? 0 : -5;
 }
 

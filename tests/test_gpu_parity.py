@@ -282,10 +282,28 @@ def test_host_pipeline_first_call_after_other_work():
         assert torch.equal(y_host, want), trial
 
 
-@pytest.mark.parametrize('grid,chunk', [(14, 2), (28, 4)])
+class _cluster_mode:
+    """Run a block with the opt-in cluster-resident kernel (eva_cluster_sm100.cu) switched on / off."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        import ctypes
+        from efficient_attention import _abi
+        self.lib = _abi.load()
+        self.lib.eva_debug_set_cluster_mode.restype = ctypes.c_int
+        self.prev = self.lib.eva_debug_set_cluster_mode(ctypes.c_int(1 if self.on else 0))
+
+    def __exit__(self, *exc):
+        import ctypes
+        self.lib.eva_debug_set_cluster_mode(ctypes.c_int(self.prev))
+
+
+@pytest.mark.parametrize('grid,chunk,cluster', [(14, 2, False), (28, 4, False), (28, 4, True)])
 @pytest.mark.parametrize('adaptive', ['default', 'no-ln', 'none'])
 @pytest.mark.parametrize('with_noise,with_bias', [(False, True), (True, False), (True, True)])
-def test_fused_kernel_variants_fp16(grid, chunk, adaptive, with_noise, with_bias):
+def test_fused_kernel_variants_fp16(grid, chunk, cluster, adaptive, with_noise, with_bias):
     """Every option the fused tcgen05/TMA kernel implements (adaptive_proj variants, training noise, optional
     bias) on both instantiated geometries, against the oracle on identical fp16 inputs.  The call must take
     the fused path (path == 1): a silent fall-back to the generic kernels would hide a regression."""
@@ -308,16 +326,17 @@ def test_fused_kernel_variants_fp16(grid, chunk, adaptive, with_noise, with_bias
     dev = _dev()
     qd = qkv.to(dev)
     geom = _abi.eva_geometry(qd[:, :, 0], seq_shape=(grid, grid), window=w, ext=0, chunk=chunk, chunk_ext=0)
-    out, path = _abi.eva_forward(qd[:, :, 0], qd[:, :, 1], qd[:, :, 2], geom, _abi_ada(ada, dev, 0.5),
-                                 noise=noise.to(dev) if with_noise else None, bias=bias.to(dev) if with_bias else None,
-                                 return_path=True)
-    assert path == (3 if grid == 28 else 1)          # 28-wide grid: cluster-resident kernel; 14-wide: streamed kernel
+    with _cluster_mode(cluster):
+        out, path = _abi.eva_forward(qd[:, :, 0], qd[:, :, 1], qd[:, :, 2], geom, _abi_ada(ada, dev, 0.5),
+                                     noise=noise.to(dev) if with_noise else None, bias=bias.to(dev) if with_bias else None,
+                                     return_path=True)
+    assert path == (3 if cluster else 1)          # 3: cluster-resident kernel (opt-in), 1: streamed kernel
     err = rel_l2(out.cpu(), want)
     assert err < TOL_F16, (grid, adaptive, with_noise, with_bias, err)
 
 
-@pytest.mark.parametrize('grid,chunk,B', [(14, 2, 400), (28, 4, 120)])
-def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B):
+@pytest.mark.parametrize('grid,chunk,B,cluster', [(14, 2, 400, False), (28, 4, 120, False), (28, 4, 200, True)])
+def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B, cluster):
     """More (batch, head) items than resident CTAs (2 x 148): every CTA loops over several items handed out by the
     dynamic work counter, which exercises the ring / barrier phase bookkeeping across items; both instantiations
     (14-wide grid: two chunk-rows per tile; 28-wide: one), checked against the generic kernels."""
@@ -330,8 +349,9 @@ def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B):
     ada = _abi_ada(_rand_ada(d, g), dev, 0.5)
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     geom = _abi.eva_geometry(q, seq_shape=(grid, grid), window=7, ext=0, chunk=chunk, chunk_ext=0)
-    out, path = _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
-    assert path == (3 if grid == 28 else 1)
+    with _cluster_mode(cluster):
+        out, path = _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
+    assert path == (3 if cluster else 1)
     kb, bt = _abi.eva_chunk_stats(q, k, v, geom, ada)
     ref = _abi.eva_window_attention(q, k, v, geom, k_bar=kb, beta=bt, bias=bias)
     per_item = ((out.float() - ref.float()).view(B, N, H, d).pow(2).sum((1, 3)).sqrt() /
@@ -630,8 +650,8 @@ def test_fast_path_goldens_fp16(name):
     assert err_ref < 4e-3, (name, err_ref)
 
 
-@pytest.mark.parametrize('grid,chunk,B', [(14, 2, 400), (28, 4, 120)])
-def test_fused_kernel_many_items_vs_oracle_fp16(grid, chunk, B):
+@pytest.mark.parametrize('grid,chunk,B,cluster', [(14, 2, 400, False), (28, 4, 120, False), (28, 4, 200, True)])
+def test_fused_kernel_many_items_vs_oracle_fp16(grid, chunk, B, cluster):
     """Same situation as test_fused_kernel_many_items_per_cta_fp16 (every CTA / cluster loops over several items: ring, barrier
     phase and buffer reuse across items) but judged by the float64 ORACLE, item by item, not by the repo's own generic kernels."""
     from efficient_attention import _abi
@@ -644,8 +664,9 @@ def test_fused_kernel_many_items_vs_oracle_fp16(grid, chunk, B):
     qd = qkv.to(dev)
     q, k, v = qd[:, :, 0], qd[:, :, 1], qd[:, :, 2]
     geom = _abi.eva_geometry(q, seq_shape=(grid, grid), window=7, ext=0, chunk=chunk, chunk_ext=0)
-    out, path = _abi.eva_forward(q, k, v, geom, _abi_ada(ada, dev, 0.5), bias=bias.to(dev), return_path=True)
-    assert path in (1, 3)
+    with _cluster_mode(cluster):
+        out, path = _abi.eva_forward(q, k, v, geom, _abi_ada(ada, dev, 0.5), bias=bias.to(dev), return_path=True)
+    assert path == (3 if cluster else 1)
     out = out.cpu().double().view(B, N, H, d)
     worst = 0.0
     for lo in range(0, B, 40):                                   # the oracle in batches of 40 images

@@ -20,6 +20,8 @@ def main():
     from oracle import eva_oracle as O
     from test_gpu_parity import _abi_ada, _rand_ada
     dev = torch.device('cuda', 0)
+    if os.environ.get('EVA_SM100_DISABLE_CLUSTER') != '1':
+        _abi.load().eva_debug_set_cluster_mode(ctypes.c_int(1))
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
     H, d, grid, chunk = 3, 64, 28, 4
@@ -71,10 +73,17 @@ def main():
     print(f'B={B} path {path}: {ms * 1e3:.1f} us per launch, {B * N / (ms * 1e-3) / 1e9:.3f} G tokens/s, {gbs:.0f} GB/s = {gbs / 6545.9 * 100:.1f} % of 6545.9')
     if os.environ.get('EVA_SM100_TRACE') == '1':
         lib = _abi.load()
-        buf = (ctypes.c_ulonglong * 4)()
+        buf = (ctypes.c_ulonglong * 20)()
         lib.eva_debug_read_cluster_prof(buf)
-        n = max(1, buf[2])
-        print(f'cluster 0 rank 0: stage A {buf[0] / n:.0f} cycles, phase B {buf[1] / n:.0f} cycles per item ({n} items)')
+        n = max(1, buf[16])
+        names = ['start->q copied,|k|^2', '->pool MMAs done', '->means written', '->Linear done', '->LN rows written', '->phi-logits ready',
+                 '->logits exchanged', '->beta rows written', '->rows sent', '->pair0 S ready', '->pair0 P written', '->pair0 O ready',
+                 '->pair1 S ready (incl. pair0 epilogue)', '->pair1 P written', '->pair1 O ready', '->item end (pair1 epilogue)']
+        tot = 0
+        for i, nm in enumerate(names):
+            print(f'   {nm:45s} {buf[i] / n:8.0f} cyc')
+            tot += buf[i] / n
+        print(f'   item total {tot:.0f} cyc; gap between items {buf[17] / max(1, n - 1):.0f} cyc ({n} items of cluster 0 rank 0, warpgroup 0 thread 0)')
 
 
 if __name__ == '__main__':
