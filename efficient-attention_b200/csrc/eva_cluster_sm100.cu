@@ -841,7 +841,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
 
 }  // namespace cluster2
 
-// Measured (profiles/r02): correct (3.1e-4 vs the float64 oracle) and reads k/v/q from L2 1.26x per item (streamed kernel: 2.4x),
+// Measured (profiles/r02): correct (3.1e-4 relative L2 in fp16 against a float64 evaluation) and reads k/v/q from L2 1.26x per item (streamed kernel: 2.4x),
 // but one item at a time per SM pair is a serial chain of ~16 MMA <-> SIMT hand-offs that nothing overlaps (shared memory holds
 // exactly one half item), so it runs at 38 % of the HBM roofline against 48-53 % for the streamed kernel with its two
 // independent CTAs per SM.  It is therefore OPT-IN: EVA_SM100_CLUSTER=1, or eva_debug_set_cluster_mode(1) at run time (tests).
