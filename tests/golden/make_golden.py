@@ -200,6 +200,9 @@ def main():
     gen_eva(ref, 'eva_c3_geom', B=1, shape=(28, 28), dim=128, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, seed=3)
     gen_eva(ref, 'eva_2d_overlap', B=2, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, overlap=True, use_rpe=True, seed=5)
     gen_eva(ref, 'eva_2d_train', B=2, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, train_seed=11, seed=7)
+    # training-mode draws on the geometries the tcgen05 kernels take (head_dim 64): c3 and c1 grids
+    gen_eva(ref, 'eva_c3_train', B=1, shape=(28, 28), dim=128, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, train_seed=63, seed=61)
+    gen_eva(ref, 'eva_c1_train', B=2, shape=(14, 14), dim=128, heads=2, window=7, landmarks=49, attn_2d=True, use_rpe=True, train_seed=67, seed=65)
     gen_eva(ref, 'eva_2d_noln', B=1, shape=(8, 8), dim=64, heads=2, window=4, landmarks=16, attn_2d=True, adaptive='no-ln', seed=9)
     gen_eva(ref, 'eva_2d_none', B=1, shape=(8, 8), dim=64, heads=2, window=4, landmarks=16, attn_2d=True, adaptive='none', seed=13)
     gen_eva(ref, 'eva_2d_t5', B=1, shape=(14, 14), dim=64, heads=2, window=7, landmarks=49, attn_2d=True, use_t5=True, seed=14)
@@ -212,6 +215,7 @@ def main():
     gen_local(ref, 'local_1d_mask', kind='local', B=2, shape=(30,), dim=64, heads=2, window=8, overlap=True, use_rpe=True, mask_tail=[4, 0], seed=27)
     # --- LARA (lara.py) ---
     gen_lara(ref, 'lara_c4_geom', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', seed=29)
+    gen_lara(ref, 'lara_c4_train', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', train_seed=71, seed=69)
     gen_lara(ref, 'lara_2d_pool_bh', B=1, shape=(10, 12), dim=64, heads=2, landmarks=16, proposal_gen='pool', mis_type='mis-bh', seed=31)
     gen_lara(ref, 'lara_2d_vmixed_biased', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='pool-vmixed', mis_type='mis-biased', seed=33)
     gen_lara(ref, 'lara_2d_noparam', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='no-param-pool', alpha=0.5, seed=35)
@@ -223,6 +227,8 @@ def main():
     # the reference's own self-check configuration (causal_eva.py:916-950), shortened sequence
     gen_causal(ref, 'causal_selfcheck', T=128, B=2, dim=128, heads=8, window=64, chunk_size=16, seed=51)
     gen_causal(ref, 'causal_c5_geom', T=96, B=2, dim=128, heads=2, window=32, chunk_size=32, seed=53)
+    # window = chunk = 256, head_dim 64: the geometry of the tcgen05 causal kernels (c5) at two windows
+    gen_causal(ref, 'causal_c5_fast', T=512, B=1, dim=128, heads=2, window=256, chunk_size=256, seed=73)
     gen_causal(ref, 'causal_overlap_mask', T=75, B=3, dim=64, heads=2, window=16, chunk_size=8, overlap=True, mask_tail=[0, 7, 30], seed=55)
     gen_causal(ref, 'causal_numchunks_train', T=64, B=2, dim=64, heads=2, window=16, num_chunks=8, use_t5=False, adaptive='no-ln', train_seed=61, seed=57)
     gen_causal(ref, 'noncausal_flag', T=64, B=1, dim=64, heads=2, window=16, chunk_size=8, causal=False, overlap=True, seed=59)

@@ -614,8 +614,10 @@ def test_lara_core_only_prequantised_fp16_vs_oracle(mixed, with_noise):
     assert float(per_item.max()) < 1.5 * TOL_F16, float(per_item.max())
 
 
-FAST_GOLDENS = {   # fixture -> eva_forward path(s) / LARA core the 16-bit module must take
-    'eva_c1': 'eva', 'eva_c3_geom': 'eva', 'eva_2d_train': 'eva', 'lara_c4_geom': 'lara',
+FAST_GOLDENS = {   # fixture -> the tcgen05 kernel family the 16-bit module must take (head_dim 64 geometries; `eva_2d_train` has
+    # head_dim 32 and stays on the generic kernels, so the training-mode draws have fixtures of their own here)
+    'eva_c1': 'eva', 'eva_c3_geom': 'eva', 'eva_c1_train': 'eva', 'eva_c3_train': 'eva',
+    'lara_c4_geom': 'lara', 'lara_c4_train': 'lara', 'causal_c5_fast': 'causal',
 }
 
 
@@ -635,6 +637,8 @@ def test_fast_path_goldens_fp16(name):
     noise = a['noise'].double() if a['noise'] is not None else None
     if cfg['kind'] == 'eva':
         want16 = O.eva_forward(sd16, cfg, x16.double(), noise=noise)
+    elif cfg['kind'] == 'causal_eva':
+        want16 = O.causal_eva_forward(sd16, cfg, x16.double(), noise=noise)
     else:
         want16 = O.lara_forward(sd16, cfg, x16.double(), noise=noise)
     before, lara_before = _path_counts(), _lara_core_launches()
@@ -642,6 +646,8 @@ def test_fast_path_goldens_fp16(name):
     after, lara_after = _path_counts(), _lara_core_launches()
     if FAST_GOLDENS[name] == 'eva':
         assert after[0] == before[0] and (after[1] - before[1]) + (after[3] - before[3]) == 1, (before, after)
+    elif FAST_GOLDENS[name] == 'causal':
+        assert after[0] == before[0] and after[2] == before[2] + 1, (before, after)
     else:
         assert lara_after == lara_before + 1
     err16 = rel_l2(y.cpu(), want16)

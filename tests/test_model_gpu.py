@@ -90,6 +90,8 @@ def test_reference_vit_with_dropin_attention_matches_oracle(name, attn, fast_pat
     model = _build(name, attn)
     torch.manual_seed(2)
     x = torch.randn(2, 3, 224, 224)
+    torch.backends.cudnn.allow_tf32 = False            # the patch-embedding convolution would otherwise run in TF32 (1e-4 on its own)
+    torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         want32 = _oracle_model(model, attn)(x.double())
         got32 = model.to(_dev())(x.to(_dev())).cpu()
