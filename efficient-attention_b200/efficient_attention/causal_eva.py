@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-from . import _abi
+from . import _abi, _recompute
 from .attn_utils import attach_forward_only, pad_to_multiple, t5_bucket_table
 
 
@@ -141,11 +141,14 @@ class CausalEVAttention(nn.Module):
                 key_padding_mask = pad_to_multiple(key_padding_mask, self.window_size, dim=-1, value=True)
         return x, key_padding_mask
 
-    def _adaptive(self):
+    def _adaptive_params(self):
         def parts(seq):
             ln = seq[1] if len(seq) > 1 else None
             return (seq[0].weight, seq[0].bias, ln.weight if ln is not None else None, ln.bias if ln is not None else None)
-        params = parts(self.adaptive_mu_q) + parts(self.adaptive_mu_k)
+        return parts(self.adaptive_mu_q) + parts(self.adaptive_mu_k)
+
+    def _adaptive(self):
+        params = self._adaptive_params()
         return _abi.memo(self, 'adaptive', params, lambda: _abi.adaptive(*params, mu_coeff=1.0))
 
     def _project_qkv_time_major(self, query):
@@ -168,13 +171,11 @@ class CausalEVAttention(nn.Module):
                 key_padding_mask: Optional[Tensor] = None,
                 incremental_state: Optional[Dict[str, Dict[str, Optional[Tensor]]]] = None,
                 need_weights: bool = True, attn_mask: Optional[Tensor] = None,
-                noise: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+                noise: Optional[Tensor] = None, drop_mask: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
         """Time x Batch x Channel in and out; `attn_mask` is accepted and ignored like the reference
         (causality comes from the window / chunk masks).  Returns (output, None)."""
         if incremental_state is not None:
             raise NotImplementedError('incremental decoding is not built yet (SURVEY.md 8f-3)')
-        if self.dropout_module.active():
-            raise NotImplementedError('attention-probability dropout is not built into the sm_100a kernels')
         time_major = query
         query = query.transpose(0, 1)
         bsz, tgt_len, embed_dim = query.size()
@@ -203,18 +204,36 @@ class CausalEVAttention(nn.Module):
         chunk = self.chunk_size if self.chunk_size is not None else int(N // self.num_chunks)
         if chunk >= N:
             raise ValueError('chunk size %d must be smaller than the padded sequence %d (causal_eva.py:680-683)' % (chunk, N))
-        geom = _abi.eva_geometry(q, seq_shape=(N,), window=self.window_size, ext=self.ext_size, chunk=chunk,
-                                 chunk_ext=0, causal=bool(self.causal), halo_left_only=True, mask_queries=True,
-                                 bias_toeplitz=bool(self.use_t5_rpe))
+        geometry = dict(seq_shape=(N,), window=self.window_size, ext=self.ext_size, chunk=chunk, chunk_ext=0,
+                        causal=bool(self.causal), halo_left_only=True, mask_queries=True, bias_toeplitz=bool(self.use_t5_rpe))
+        geom = _abi.eva_geometry(q, **geometry)
         if self.training and noise is None:
             noise = torch.randn(B, H, _abi.num_chunks(geom), D, dtype=torch.float32, device=x.device)
+        table = self.rel_pos_bias.relative_attention_bias.weight if self.use_t5_rpe else None
+        params = self._adaptive_params()
+        dropping = self.dropout_module.active()
+        grad = _recompute.needs_grad(q, k, v, table, *params)
         bias = None
         if self.use_t5_rpe:
-            table = self.rel_pos_bias.relative_attention_bias.weight
-            bias = _abi.memo(self, 'bias', (table,), lambda: self.rel_pos_bias.dense(
-                self.window_size, self.window_size + self.ext_size).unsqueeze(0).detach().float().contiguous())
-        out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise, bias=bias)
-        out = attach_forward_only(out, q, k, v)
+            if grad or dropping:
+                bias = self.rel_pos_bias.dense(self.window_size, self.window_size + self.ext_size).unsqueeze(0).float().contiguous()
+            else:
+                bias = _abi.memo(self, 'bias', (table,), lambda: self.rel_pos_bias.dense(
+                    self.window_size, self.window_size + self.ext_size).unsqueeze(0).detach().float().contiguous())
+        if dropping:
+            # attention-probability dropout (causal_eva.py:778): the kernels have none, so this one configuration evaluates the core
+            # with the float32 PyTorch recomputation in the forward as well (library ops on the device; autograd does the rest)
+            wq_, bq_, gq_, betq_, wk_, bk_, gk_, betk_ = params
+            out = _recompute.eva_core_torch(q, k, v, seq_shape=(N,), window=self.window_size, ext=self.ext_size, chunk=chunk,
+                                            chunk_ext=0, wq=wq_, bq=bq_, gq=gq_, betq=betq_, wk=wk_, bk=bk_, gk=gk_, betk=betk_,
+                                            mu_coeff=1.0, pad_mask=key_padding_mask, noise=noise, bias=bias, causal=bool(self.causal),
+                                            left_only=True, mask_queries=True, p_drop=float(self.dropout_module.p),
+                                            drop_mask=drop_mask).to(q.dtype)
+        elif grad:
+            out = _recompute.eva_core(q, k, v, geometry=geometry, mu_coeff=1.0, params=params, pad_mask=key_padding_mask,
+                                      noise=noise, bias=bias)
+        else:
+            out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise, bias=bias)
         y = self.out_proj(out)
         if tgt_len != N:
             y = y[:, :tgt_len]

@@ -8,8 +8,8 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _abi
-from .attn_utils import attach_forward_only, pad_to_multiple, t5_bucket_table
+from . import _abi, _recompute
+from .attn_utils import pad_to_multiple, t5_bucket_table
 from .local_attention import LocalAttention
 
 
@@ -85,22 +85,28 @@ class EVA(LocalAttention):
             seq_shape = [x.shape[-2]]
         return x, key_padding_mask, seq_shape
 
-    def _adaptive(self):
+    def _adaptive_params(self):
+        """(w_q, b_q, ln_gain_q, ln_bias_q, w_k, b_k, ln_gain_k, ln_bias_k); absent parts are None."""
         def parts(seq):
             lin = seq[0]
             ln = seq[1] if len(seq) > 1 else None
             return (lin.weight, lin.bias, ln.weight if ln is not None else None, ln.bias if ln is not None else None)
         q = parts(self.adaptive_mu_q) if self.adaptive_proj != 'none' else (None, None, None, None)
-        k = parts(self.adaptive_mu_k)
-        return _abi.memo(self, 'adaptive', q + k, lambda: _abi.adaptive(*q, *k, mu_coeff=0.5))
+        return q + parts(self.adaptive_mu_k)
 
-    def _local_bias(self):
+    def _adaptive(self):
+        params = self._adaptive_params()
+        return _abi.memo(self, 'adaptive', params, lambda: _abi.adaptive(*params, mu_coeff=0.5))
+
+    def _local_bias(self, differentiable=False):
         if self.use_t5_rpe:
             w, e = self.window_size, self.ext_size
             L, J = (w * w, (w + 2 * e) ** 2) if self.attn_2d else (w, w + 2 * e)
+            if differentiable:
+                return self.rel_pos_bias.dense(L, J).float().contiguous()
             table = self.rel_pos_bias.relative_attention_bias.weight
             return _abi.memo(self, 'bias', (table,), lambda: self.rel_pos_bias.dense(L, J).detach().float().contiguous())
-        return self._window_bias()
+        return self._window_bias(differentiable)
 
     def forward(self, x, key_padding_mask=None, noise=None):
         """x: [B, H', W', C] (attn_2d) or [B, N, C]; key_padding_mask [B, N], True = padding.
@@ -114,17 +120,27 @@ class EVA(LocalAttention):
         chunk = int(math.sqrt(N // self.num_landmarks)) if self.attn_2d else int(N // self.num_landmarks)
         if chunk <= 0:
             raise ValueError('num_landmarks=%d is larger than the sequence (%d tokens)' % (self.num_landmarks, N))
-        geom = _abi.eva_geometry(q, seq_shape=tuple(seq_shape), window=self.window_size, ext=self.ext_size,
-                                 chunk=chunk, chunk_ext=self.ext_size)
+        geometry = dict(seq_shape=tuple(seq_shape), window=self.window_size, ext=self.ext_size, chunk=chunk, chunk_ext=self.ext_size)
+        geom = _abi.eva_geometry(q, **geometry)
         if self.training and noise is None:
             noise = torch.randn(B, self.num_heads, _abi.num_chunks(geom), self.head_dim, dtype=torch.float32,
                                 device=x.device)
-        out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise,
-                               bias=self._local_bias())
-        out = attach_forward_only(out, packed)
+        params = self._adaptive_params()
+        if _recompute.needs_grad(packed, *params, *self._bias_sources()):
+            # training (vit/engine.py:47-62): kernel forward, backward by recomputation (see _recompute.py)
+            out = _recompute.eva_core(q, k, v, geometry=geometry, mu_coeff=0.5, params=params, pad_mask=key_padding_mask,
+                                      noise=noise, bias=self._local_bias(differentiable=True))
+        else:
+            out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise,
+                                   bias=self._local_bias())
         x = self.proj(out.view((B,) + tuple(seq_shape) + (C,)))
         x = x[..., :orig_n, :]          # eva.py:230-231 (slices W' in 2-D: a no-op)
         return self.proj_drop(x)
+
+    def _bias_sources(self):
+        if self.use_t5_rpe:
+            return (self.rel_pos_bias.relative_attention_bias.weight,)
+        return (self.local_relative_position_bias_table,) if self.use_rpe else ()
 
     @staticmethod
     def add_attn_specific_args(parent_parser, struct_name="attn_args", prefix=""):

@@ -35,18 +35,21 @@ class LocalAttention(MultiheadAttention):
             nn.init.trunc_normal_(self.local_relative_position_bias_table, std=.02)
         self.apply(self._init_weights)
 
-    def _window_bias(self):
-        """Dense float32 [H, L, J] bias for the local logits (reference add_rel_pos_bias, :70-79)."""
+    def _window_bias(self, differentiable=False):
+        """Dense float32 [H, L, J] bias for the local logits (reference add_rel_pos_bias, :70-79).  `differentiable`: keep the
+        autograd link to the table (training); otherwise a cached, detached copy."""
         if not self.use_rpe:
             return None
         table = self.local_relative_position_bias_table
         if not self.attn_2d:
             return table
 
-        def gather():
+        def gather(detach=True):
             L, J = self.relative_position_index.shape
             dense = table[self.relative_position_index.reshape(-1)].view(L, J, self.num_heads).permute(2, 0, 1)
-            return dense.detach().float().contiguous()
+            return dense.detach().float().contiguous() if detach else dense.float().contiguous()
+        if differentiable:
+            return gather(detach=False)
         return _abi.memo(self, 'window_bias', (table, self.relative_position_index), gather)
 
     def _core(self, q, k, v, packed, key_padding_mask, seq_shape):

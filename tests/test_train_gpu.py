@@ -1,0 +1,165 @@
+"""Training path (`-m gpu`): kernel forward + backward by recomputation (`efficient_attention/_recompute.py`).
+
+* the float32 PyTorch recomputation equals the kernels' forward (it is what autograd differentiates);
+* gradients of the drop-in modules (w.r.t. the input and every parameter) equal autograd through the float64 CPU oracle on the
+  reference-generated training fixtures (identical noise draw);
+* an fp16-autocast training step through the fused tcgen05 path produces finite gradients;
+* attention-probability dropout of the causal layer (causal_eva.py:778);
+* two-rank DDP step with the NCCL gradient all-reduce (vit/main.py:286-288) -- needs two GPUs, skipped otherwise.
+"""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from helpers import build_module
+from oracle import eva_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dev():
+    return torch.device('cuda', 0)
+
+
+@pytest.mark.parametrize('seq_shape,window,ext,chunk,causal,with_mask', [
+    ((14, 14), 7, 0, 2, False, False), ((28, 28), 7, 0, 4, False, False), ((14, 14), 7, 3, 2, False, False),
+    ((96,), 16, 8, 12, False, True), ((128,), 32, 0, 16, True, True), ((96,), 16, 16, 8, True, False)])
+def test_recomputation_equals_the_kernels_fp32(seq_shape, window, ext, chunk, causal, with_mask):
+    """`eva_core_torch` (what the backward differentiates) against `eva_forward` of the library on identical float32 inputs."""
+    from efficient_attention import _abi, _recompute
+    from test_gpu_parity import _rand_ada
+    dev = _dev()
+    B, H, d = 2, 2, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + window + ext)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dev)
+    two_d = len(seq_shape) == 2
+    L = window * window if two_d else window
+    J = (window + 2 * ext) ** 2 if two_d else window + (ext if causal else 2 * ext)
+    bias = (0.5 * torch.randn(H, L, J, generator=g)).to(dev)
+    ada = {k_: (v_.to(dev) if v_ is not None else None) for k_, v_ in _rand_ada(d, g).items()}
+    mask = None
+    if with_mask:
+        mask = torch.zeros(B, N, dtype=torch.bool, device=dev)
+        mask[1, N - 9:] = True
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    chunk_ext = 0 if causal else ext
+    n_chunks = _recompute.num_chunks_of(seq_shape, chunk)
+    noise = torch.randn(B, H, n_chunks, d, generator=g).to(dev)
+    coeff = 1.0 if causal else 0.5
+    geometry = dict(seq_shape=seq_shape, window=window, ext=ext, chunk=chunk, chunk_ext=chunk_ext, causal=causal,
+                    halo_left_only=causal, mask_queries=causal)
+    geom = _abi.eva_geometry(q, **geometry)
+    out = _abi.eva_forward(q, k, v, geom, _abi.adaptive(ada['wq'], ada['bq'], ada['gq'], ada['betq'], ada['wk'], ada['bk'], ada['gk'],
+                                                        ada['betk'], mu_coeff=coeff), pad_mask=mask, noise=noise, bias=bias)
+    ref = _recompute.eva_core_torch(q, k, v, seq_shape=seq_shape, window=window, ext=ext, chunk=chunk, chunk_ext=chunk_ext, **ada,
+                                    mu_coeff=coeff, pad_mask=mask, noise=noise, bias=bias, causal=causal, left_only=causal,
+                                    mask_queries=causal)
+    assert rel_l2(out.cpu(), ref.cpu()) < 2e-5
+
+
+def _grads_of(module, cfg, a, dev, dtype):
+    """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
+    x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
+    mask = a['mask'].to(dev) if a['mask'] is not None else None
+    noise = a['noise'].to(device=dev, dtype=torch.float32) if a['noise'] is not None else None
+    if cfg['kind'] == 'causal_eva':
+        y = module(x, x, x, key_padding_mask=mask, noise=noise)[0]
+    else:
+        y = module(x, mask, noise=noise)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(device=dev, dtype=y.dtype)
+    (y * w).sum().backward()
+    return y.detach(), x.grad.detach(), {n: p.grad.detach() for n, p in module.named_parameters() if p.grad is not None}
+
+
+def _oracle_grads(cfg, sd, a):
+    sd64 = {k_: (v_.double().requires_grad_(True) if v_.is_floating_point() else v_) for k_, v_ in sd.items()}
+    x = a['x'].double().requires_grad_(True)
+    noise = a['noise'].double() if a['noise'] is not None else None
+    if cfg['kind'] == 'causal_eva':
+        y = O.causal_eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
+    else:
+        y = O.eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
+    w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).double()
+    (y * w).sum().backward()
+    return y.detach(), x.grad, {k_: v_.grad for k_, v_ in sd64.items() if v_.is_floating_point() and v_.grad is not None}
+
+
+@pytest.mark.parametrize('name', ['eva_2d_train', 'eva_1d_train', 'eva_c1_train', 'eva_c3_train', 'causal_numchunks_train'])
+def test_module_gradients_match_oracle_autograd_fp32(name):
+    cfg, sd, a = load_golden(name, dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    m = m.to(_dev()).train()
+    y, gx, gp = _grads_of(m, cfg, a, _dev(), torch.float32)
+    y64, gx64, gp64 = _oracle_grads(cfg, sd, a)
+    assert rel_l2(y.cpu(), y64) < 2e-5
+    assert rel_l2(gx.cpu(), gx64) < 1e-4, ('x', rel_l2(gx.cpu(), gx64))
+    assert set(gp) == set(gp64), (sorted(set(gp) ^ set(gp64)))
+    for n_ in gp64:
+        if float(gp64[n_].norm()) > 1e-9:
+            assert rel_l2(gp[n_].cpu(), gp64[n_]) < 2e-4, (n_, rel_l2(gp[n_].cpu(), gp64[n_]))
+
+
+def test_autocast_training_step_through_the_fused_path():
+    """DeiT-style step (vit/engine.py:47-62): fp16 autocast forward through the fused tcgen05 kernel, backward by recomputation,
+    every parameter receives a finite gradient; the forward took path 1 or 3."""
+    import bench
+    from test_gpu_parity import _path_counts
+    m = bench.build_layer(_dev(), torch.float32).train()
+    x = torch.randn(8, 28, 28, 192, device=_dev(), requires_grad=True)
+    before = _path_counts()
+    with torch.autocast('cuda', dtype=torch.float16):
+        y = m(x)
+    after = _path_counts()
+    assert after[0] == before[0] and (after[1] - before[1]) + (after[3] - before[3]) == 1
+    y.float().pow(2).mean().backward()
+    assert torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+    for n_, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+
+
+def test_causal_attention_dropout():
+    """causal_eva.py:778: dropout on the joint probabilities.  With an all-keep mask the output before the projection bias is the
+    no-dropout output / (1 - p); with random draws it is unbiased; gradients flow."""
+    from argparse import Namespace
+    import efficient_attention as ea
+    torch.manual_seed(0)
+    ns = Namespace(adaptive_proj='qk', num_chunks=None, chunk_size=16, causal=True, use_t5_rpe=True, window_size=32, overlap_window=False)
+    m = ea.CausalEVAttention(128, 2, dropout=0.25, self_attention=True, attn_args=ns).to(_dev())
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 1.0 / math.sqrt(p.shape[1]))
+    x = torch.randn(64, 2, 128, device=_dev())
+    noise = torch.randn(2, 2, 4, 64, device=_dev())
+    m.eval()
+    with torch.no_grad():
+        y0 = m(x, x, x, noise=noise)[0]
+    m.train()
+    keep = torch.ones(2, 2, 2, 32, 32 + 4, dtype=torch.bool, device=_dev())
+    with torch.no_grad():
+        y1 = m(x, x, x, noise=noise, drop_mask=keep)[0]
+    b = m.out_proj.bias
+    assert rel_l2(((y1 - b) * 0.75).cpu(), (y0 - b).cpu()) < 2e-5
+    with torch.no_grad():
+        ys = torch.stack([m(x, x, x, noise=noise)[0] for _ in range(300)]).mean(0)
+    assert rel_l2(ys.cpu(), y0.cpu()) < 0.08                   # unbiased: the mean over draws approaches the no-dropout output
+    xg = x.clone().requires_grad_(True)
+    m(xg, xg, xg, noise=noise)[0].pow(2).mean().backward()
+    assert torch.isfinite(xg.grad).all() and float(xg.grad.abs().sum()) > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_ddp_two_rank_training_step():
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29641', os.path.join(ROOT, 'tools', 'ddp_smoke.py')], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert 'DDP_SMOKE_OK' in out.stdout, out.stdout[-2000:]
