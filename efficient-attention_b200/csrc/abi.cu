@@ -261,9 +261,30 @@ int lara_forward_workspace_bytes(const LaraGeometry* gin, size_t* bytes) {
   return EVA_OK;
 }
 
+static int lara_forward_impl(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                             const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
+                             void* out, void* workspace, size_t workspace_bytes, void* stream, const float* given);
+
 int lara_forward(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
                  void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return lara_forward_impl(gin, q, k, v, pad_mask, proj, noise, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int lara_forward_given_landmarks(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                                 const uint8_t* pad_mask, const float* landmarks, const float* noise,
+                                 void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!landmarks) return fail(EVA_ERR_INVALID, "landmarks is NULL");
+  if (gin && gin->per_token_proj) return fail(EVA_ERR_INVALID, "'adaptive-1d' proposals are computed per token, not given");
+  EvaAdaptive none;
+  memset(&none, 0, sizeof(none));
+  none.ln_eps = 1e-5f;
+  return lara_forward_impl(gin, q, k, v, pad_mask, &none, noise, out, workspace, workspace_bytes, stream, landmarks);
+}
+
+static int lara_forward_impl(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                             const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
+                             void* out, void* workspace, size_t workspace_bytes, void* stream, const float* given) {
   eva::LaraGeo g{};
   eva::View vq, vk, vv;
   int rc;
@@ -279,7 +300,7 @@ int lara_forward(const LaraGeometry* gin, const EvaHeadsView* q, const EvaHeadsV
   if (workspace_bytes < eva::lara_workspace_bytes(g)) return fail(EVA_ERR_INVALID, "workspace too small");
   if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return fail(EVA_ERR_INVALID, "workspace must be 256-byte aligned");
   const cudaError_t e = eva::launch_lara(g, gin->io_dtype, vq, vk, vv, pad_mask, *proj, noise, out, workspace,
-                                         reinterpret_cast<cudaStream_t>(stream));
+                                         reinterpret_cast<cudaStream_t>(stream), given);
   if (e == cudaErrorInvalidConfiguration)
     return fail(EVA_ERR_UNSUPPORTED, "landmarks x head_dim too large for one CTA's shared memory");
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "lara_forward");

@@ -65,7 +65,8 @@ __device__ __forceinline__ void dots_rows_cols(const float* __restrict__ X, int 
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
-                     const EvaAdaptive proj, const float* __restrict__ noise, float* __restrict__ ws_base) {
+                     const EvaAdaptive proj, const float* __restrict__ noise, float* __restrict__ ws_base,
+                     const float* __restrict__ given) {
   constexpr int DPL = Feat<D>::kPerLane, DP = D + 1;
   extern __shared__ float sm[];
   const int C = g.C, S = g.S;
@@ -84,7 +85,18 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
 
   bool coop = false;
   if constexpr (D == 64) coop = g.dims == 2 && !g.per_token_proj;
-  if constexpr (D == 64) if (coop) {
+  // `given`: landmarks computed by the caller (pool_module_type == 'dense', lara.py:36-39,131-139: Linear / LayerNorm over ALL
+  // channels, i.e. across heads), float32 [batch * heads][3][C][D] = q_bar | k_bar (before mixing) | v_bar ('-vmixed' only)
+  const bool gen = given == nullptr;
+  if (!gen) {
+    const float* src = given + (long long)blockIdx.x * 3 * C * D;
+    for (int idx = tid; idx < (g.mixed == 2 ? 3 : 2) * C * D; idx += blockDim.x) {
+      const int part = idx / (C * D), r = idx % (C * D);
+      float* dst = part == 0 ? qb : (part == 1 ? kb : vb);
+      dst[(r / D) * DP + r % D] = __ldg(src + idx);
+    }
+  }
+  if constexpr (D == 64) if (coop && gen) {
     // Cooperative path for the pooled 2-D proposals (DeiT): the warp-per-landmark loop below serialises global-load latency
     // (4 dependent-looking token loads per landmark) and a 64-shuffle Linear per landmark.
     //   1. pooling: one work item per (side, landmark, 8 features), all threads, 16-byte loads
@@ -164,7 +176,7 @@ lara_landmark_kernel(const LaraGeo g, const View q, const View k, const View v, 
       }
     }
   }
-  if (!coop)
+  if (!coop && gen)
   for (int side = 0; side < 3; ++side) {  // 0: q, 1: k, 2: v (only for '-vmixed')
     if (side == 2 && g.mixed != 2) break;
     const bool per_tok = g.per_token_proj && side < 2;
@@ -650,20 +662,20 @@ size_t lara_workspace_bytes(const LaraGeo& g) {
 template <typename T, int D>
 static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k, const View& v, const uint8_t* mask,
                                  const EvaAdaptive& proj, const float* noise, void* out, void* workspace,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const float* given) {
   float* ws = reinterpret_cast<float*>(workspace);
   const size_t sm1 = landmark_smem(g), sm3 = out_smem(g);
   if (sm1 > 227 * 1024 || sm3 > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   if constexpr (D == 64 && !std::is_same<T, float>::value) {
     constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
-    if (lara_core_supported(g, io, q, k, v, mask) && lara_core_fuses_landmarks(g, proj))
+    if (!given && lara_core_supported(g, io, q, k, v, mask) && lara_core_fuses_landmarks(g, proj))
       return launch_lara_core(g, io, q, k, v, ws, out, &proj, noise, st);      // landmarks, statistics and output in one kernel
   }
   {
     auto kern = lara_landmark_kernel<T, D>;
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
-    kern<<<g.B * g.H, 256, sm1, st>>>(g, q, k, v, mask, proj, noise, ws);
+    kern<<<g.B * g.H, 256, sm1, st>>>(g, q, k, v, mask, proj, noise, ws, given);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if constexpr (D == 64 && !std::is_same<T, float>::value) {
@@ -692,20 +704,20 @@ static cudaError_t launch_lara_t(const LaraGeo& g, const View& q, const View& k,
 
 cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
                         const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
-                        void* workspace, cudaStream_t st) {
+                        void* workspace, cudaStream_t st, const float* given) {
   switch (io_dtype * 256 + g.D) {
-    case EVA_F32 * 256 + 16: return launch_lara_t<float, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F32 * 256 + 32: return launch_lara_t<float, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F32 * 256 + 64: return launch_lara_t<float, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F32 * 256 + 128: return launch_lara_t<float, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 256 + 16: return launch_lara_t<__half, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 256 + 32: return launch_lara_t<__half, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 256 + 64: return launch_lara_t<__half, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_F16 * 256 + 128: return launch_lara_t<__half, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 256 + 16: return launch_lara_t<__nv_bfloat16, 16>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 256 + 32: return launch_lara_t<__nv_bfloat16, 32>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 256 + 64: return launch_lara_t<__nv_bfloat16, 64>(g, q, k, v, mask, proj, noise, out, workspace, st);
-    case EVA_BF16 * 256 + 128: return launch_lara_t<__nv_bfloat16, 128>(g, q, k, v, mask, proj, noise, out, workspace, st);
+    case EVA_F32 * 256 + 16: return launch_lara_t<float, 16>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F32 * 256 + 32: return launch_lara_t<float, 32>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F32 * 256 + 64: return launch_lara_t<float, 64>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F32 * 256 + 128: return launch_lara_t<float, 128>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F16 * 256 + 16: return launch_lara_t<__half, 16>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F16 * 256 + 32: return launch_lara_t<__half, 32>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F16 * 256 + 64: return launch_lara_t<__half, 64>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_F16 * 256 + 128: return launch_lara_t<__half, 128>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_BF16 * 256 + 16: return launch_lara_t<__nv_bfloat16, 16>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_BF16 * 256 + 32: return launch_lara_t<__nv_bfloat16, 32>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_BF16 * 256 + 64: return launch_lara_t<__nv_bfloat16, 64>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
+    case EVA_BF16 * 256 + 128: return launch_lara_t<__nv_bfloat16, 128>(g, q, k, v, mask, proj, noise, out, workspace, st, given);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -54,6 +54,6 @@ cudaError_t launch_lara_core(const LaraGeo& g, int io_dtype, const View& q, cons
                              const EvaAdaptive* proj, const float* noise, cudaStream_t st);
 cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const View& k, const View& v,
                         const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
-                        void* workspace, cudaStream_t st);
+                        void* workspace, cudaStream_t st, const float* given_landmarks = nullptr);
 
 }  // namespace eva

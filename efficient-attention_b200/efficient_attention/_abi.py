@@ -75,8 +75,9 @@ def load():
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
+        lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
-                   'eva_forward', 'lara_forward_workspace_bytes', 'lara_forward'):
+                   'eva_forward', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
             getattr(lib, fn).restype = ctypes.c_int
         if lib.eva_sm100_abi_version() != 2:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
@@ -258,9 +259,11 @@ def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None,
 
 
 def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded,
-                 alpha_coeff, proj, pad_mask=None, noise=None):
+                 alpha_coeff, proj, pad_mask=None, noise=None, given_landmarks=None):
+    """`given_landmarks`: float32 [B, H, 3, C, D] (q_bar | k_bar before mixing | v_bar) computed by the caller
+    (pool_module_type == 'dense'); `proj` is ignored then."""
     lib = load()
-    _require_cuda(q, k, v, pad_mask, noise)
+    _require_cuda(q, k, v, pad_mask, noise, given_landmarks)
     B, N, H, D = q.shape
     two_d = len(seq_shape) == 2
     geom = LaraGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N,
@@ -274,9 +277,16 @@ def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_ty
     _check(lib.lara_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'lara_forward_workspace_bytes')
     ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
-        rc = lib.lara_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
-                              ctypes.byref(heads_view(v)), _ptr(mask), ctypes.byref(proj_s), _ptr(noise), _ptr(out),
-                              _ptr(ws), ws.numel(), _stream(q.device))
+        if given_landmarks is not None:
+            given = _f32(given_landmarks)
+            assert tuple(given.shape) == (B, H, 3, landmarks, D), 'given_landmarks must be [B, H, 3, C, D]'
+            rc = lib.lara_forward_given_landmarks(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                                  ctypes.byref(heads_view(v)), _ptr(mask), _ptr(given), _ptr(noise), _ptr(out),
+                                                  _ptr(ws), ws.numel(), _stream(q.device))
+        else:
+            rc = lib.lara_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                  ctypes.byref(heads_view(v)), _ptr(mask), ctypes.byref(proj_s), _ptr(noise), _ptr(out),
+                                  _ptr(ws), ws.numel(), _stream(q.device))
     _check(rc, 'lara_forward')
     del keep
     return out

@@ -26,7 +26,7 @@ class LinearRA(MultiheadAttention):
         if pool_module_type == 'light':
             ch = self.head_dim
         elif pool_module_type == 'dense':
-            raise NotImplementedError("pool_module_type='dense' is not built into the sm_100a LARA kernels")
+            ch = self.dim      # Linear / LayerNorm over all channels, i.e. across heads (lara.py:36-39)
         else:
             raise NotImplementedError(pool_module_type)
         if mis_type not in _abi.LARA_MIS:
@@ -55,13 +55,35 @@ class LinearRA(MultiheadAttention):
         if gen.startswith('adaptive-1d'):
             if two_d:
                 raise ValueError("proposal_gen='adaptive-1d' expects [B, N, C] inputs")
+            if self.pool_module_type == 'dense':     # the reference applies Linear(dim, dim) to [.., head_dim] rows here and fails
+                raise ValueError("proposal_gen='adaptive-1d' needs pool_module_type='light'")
             lin_q, ln_q, lin_k, ln_k = self.q_bar_gen[0], self.q_bar_gen[1], self.k_bar_gen[0], self.k_bar_gen[1]
-        elif gen.startswith('pool') and two_d:
+        elif gen.startswith('pool') and two_d and self.pool_module_type == 'light':
             lin_q, ln_q, lin_k, ln_k = self.q_bar_gen[2], self.q_bar_gen[3], self.k_bar_gen[2], self.k_bar_gen[3]
         else:  # 'no-param-pool', or pooled proposals on a 1-D input (plain segment means, lara.py:98-103)
             return _abi.adaptive(*([None] * 8), mu_coeff=1.0)
         params = (lin_q.weight, lin_q.bias, ln_q.weight, ln_q.bias, lin_k.weight, lin_k.bias, ln_k.weight, ln_k.bias)
         return _abi.memo(self, 'proj_params', params, lambda: _abi.adaptive(*params, mu_coeff=1.0, ln_eps=ln_q.eps))
+
+    def _dense_landmarks(self, q, k, v, seq_shape, with_v):
+        """pool_module_type == 'dense' (lara.py:131-139): AdaptiveAvgPool2d over the token grid of ALL channels, then Linear(dim, dim)
+        + LayerNorm(dim) -- a library GEMM on [B, C, dim] -- and back to heads.  -> float32 [B, H, 3, C, d] for the kernels."""
+        B, N, H, d = q.shape
+        gh, gw = seq_shape
+        side = int(math.sqrt(self.num_landmarks))
+
+        def pooled(t):                         # [B, N, H, d] view -> [B, side^2, H * d]
+            grid = t.reshape(B, gh, gw, H * d).permute(0, 3, 1, 2)
+            return nn.functional.adaptive_avg_pool2d(grid.float(), side).flatten(2).transpose(1, 2)
+
+        def proj(seq, m):
+            lin, ln = seq[2], seq[3]
+            y = nn.functional.linear(m, lin.weight.float(), None if lin.bias is None else lin.bias.float())
+            return nn.functional.layer_norm(y, (y.shape[-1],), ln.weight.float(), ln.bias.float(), ln.eps)
+        q_bar = proj(self.q_bar_gen, pooled(q)).view(B, -1, H, d)
+        k_bar = proj(self.k_bar_gen, pooled(k)).view(B, -1, H, d)
+        v_bar = pooled(v).view(B, -1, H, d) if with_v else torch.zeros_like(k_bar)
+        return torch.stack([q_bar, k_bar, v_bar], 1).permute(0, 3, 1, 2, 4).contiguous()      # [B, H, 3, C, d]
 
     def forward(self, x, key_padding_mask=None, noise=None):
         """x: [B, H', W', C] or [B, N, C].  `noise` (test hook, not part of the reference signature) overrides the
@@ -90,8 +112,11 @@ class LinearRA(MultiheadAttention):
                 rows = landmarks
             if noise is None:
                 noise = torch.randn(B, self.num_heads, rows, self.head_dim, dtype=torch.float32, device=x.device)
+        given = None
+        if two_d and self.pool_module_type == 'dense' and self.proposal_gen.startswith('pool'):
+            given = self._dense_landmarks(q, k, v, seq_shape, mixed == 2)
         out = _abi.lara_forward(
-            q, k, v, seq_shape=tuple(seq_shape), landmarks=landmarks,
+            q, k, v, seq_shape=tuple(seq_shape), landmarks=landmarks, given_landmarks=given,
             per_token_proj=self.proposal_gen.startswith('adaptive-1d'), mixed=mixed, mis_type=self.mis_type,
             sample_mode=mode, zero_padded=(not two_d and key_padding_mask is not None),
             alpha_coeff=self.alpha_coeff, proj=self._proj_params(two_d), pad_mask=key_padding_mask, noise=noise)

@@ -11,17 +11,17 @@
  *                          local_attention.py:134-182   abstract_attention.py:115-133   joint softmax, PV)
  *   eva_forward            eva.py:151-227 as one call (selects the fused sm_100a tcgen05/TMA kernel
  *                          when the geometry allows, else the two generic stages)
- *   lara_landmarks         lara.py:84-175          (landmark pooling, Linear+LN, mixing, proposal stats)
- *   lara_forward           lara.py:201-246         (phi-projections, kv statistics, MIS weights, SNIS)
+ *   lara_forward           lara.py:84-175          (landmark pooling, Linear+LN, mixing, proposal stats) and
+ *                          lara.py:201-246         (phi-projections, kv statistics, MIS weights, SNIS) in one call
  *
  * Conventions
  *   - every function returns 0 on success or a negative errno-style code; it never throws, never
  *     calls exit(), never allocates or frees device memory and never synchronises the device;
  *   - all buffers are caller-owned device memory (the Python host side hands out PyTorch tensors);
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns;
- *   - the library is re-entrant across streams and devices; the only process-global state is a
- *     per-device cache of function attributes / tensor maps guarded by a mutex, and a thread-local
- *     last-error string;
+ *   - the library is re-entrant across streams and devices; the only state it keeps is per-device
+ *     "attribute already set" flags (idempotent), a thread-local cache of encoded tensor maps keyed by
+ *     the pointers / strides / sizes of a call, and a thread-local last-error string;
  *   - q, k, v are described as strided views [batch, tokens, heads, head_dim] with head_dim
  *     contiguous, so both the packed `qkv` Linear output ([B,N,3,h,d], abstract_attention.py:72-78)
  *     and separate q/k/v projections (causal_eva.py:511-536) are consumed without a permute copy;
@@ -145,6 +145,13 @@ int lara_forward_workspace_bytes(const LaraGeometry* g, size_t* bytes);
 int lara_forward(const LaraGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* proj, const float* noise,
                  void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same as lara_forward with the landmarks computed by the caller: pool_module_type == 'dense' (lara.py:36-39, 131-139) runs its
+ * Linear / LayerNorm over ALL channels, i.e. across heads, which is a plain library GEMM on a [batch, C, dim] tensor.
+ * landmarks: float32 [batch, heads, 3, C, head_dim] = q_bar | k_bar (before the '-mixed' step) | v_bar (read for '-vmixed' only). */
+int lara_forward_given_landmarks(const LaraGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                                 const uint8_t* pad_mask, const float* landmarks, const float* noise,
+                                 void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -251,9 +251,11 @@ def softmax_core(q, k, v, pad_mask=None):
 # --------------------------------------------------------------------------------------------
 # LARA core (lara.py:129-246)
 # --------------------------------------------------------------------------------------------
-def lara_landmarks_2d(q, k, v, gh, gw, n_lm, *, wq, bq, gq, betq, wk, bk, gk, betk, mixed: bool, vmixed: bool):
-    """'light' pooling: AdaptiveAvgPool2d(sqrt n_lm) over the token grid, Linear+LN (absent for
-    'no-param-pool'), optional landmark mixing (lara.py:141-174)."""
+def lara_landmarks_2d(q, k, v, gh, gw, n_lm, *, wq, bq, gq, betq, wk, bk, gk, betk, mixed: bool, vmixed: bool,
+                      dense: bool = False):
+    """AdaptiveAvgPool2d(sqrt n_lm) over the token grid, Linear+LN (absent for 'no-param-pool') per head ('light',
+    lara.py:141-151) or over all channels at once ('dense', lara.py:131-139: channel = head * d + feature), optional
+    landmark mixing (lara.py:157-174)."""
     B, h, N, d = q.shape
     side = int(math.sqrt(n_lm))
     by, bx = adaptive_pool_bins(gh, side), adaptive_pool_bins(gw, side)
@@ -264,7 +266,12 @@ def lara_landmarks_2d(q, k, v, gh, gw, n_lm, *, wq, bq, gq, betq, wk, bk, gk, be
         return torch.stack(rows, 2).reshape(B, h, side * side, d)
 
     q_bar, k_bar = pool(q), pool(k)
-    if wq is not None:
+    if wq is not None and dense:
+        merge = lambda t: t.permute(0, 2, 1, 3).reshape(B, side * side, h * d)
+        split = lambda t: t.reshape(B, side * side, h, d).permute(0, 2, 1, 3)
+        q_bar = split(layer_norm(linear(merge(q_bar), wq, bq), gq, betq))
+        k_bar = split(layer_norm(linear(merge(k_bar), wk, bk), gk, betk))
+    elif wq is not None:
         q_bar = layer_norm(linear(q_bar, wq, bq), gq, betq)
         k_bar = layer_norm(linear(k_bar, wk, bk), gk, betk)
     if mixed:
@@ -462,7 +469,7 @@ def softmax_forward(sd, cfg, x, pad_mask=None):
 
 
 def lara_forward(sd, cfg, x, pad_mask=None, noise=None):
-    """LinearRA.forward (lara.py:177-251), pool_module_type == 'light'.  cfg keys: num_heads,
+    """LinearRA.forward (lara.py:177-251).  cfg keys: pool_module_type ('light' default | 'dense'), num_heads,
     num_landmarks, proposal_gen, mis_type, alpha_coeff, use_antithetics, use_multisample."""
     heads = cfg['num_heads']
     B, *shape, C = x.shape
@@ -481,7 +488,8 @@ def lara_forward(sd, cfg, x, pad_mask=None, noise=None):
         pk = dict(wk=None, bk=None, gk=None, betk=None)
     if len(shape) == 2:
         q_bar, k_bar = lara_landmarks_2d(q, k, v, shape[0], shape[1], cfg['num_landmarks'], **pq, **pk,
-                                         mixed=gen.endswith('mixed'), vmixed=gen.endswith('-vmixed'))
+                                         mixed=gen.endswith('mixed'), vmixed=gen.endswith('-vmixed'),
+                                         dense=cfg.get('pool_module_type', 'light') == 'dense')
     else:
         if pad_mask is not None:
             keep = (~pad_mask.bool()).to(q.dtype).unsqueeze(1).unsqueeze(-1)

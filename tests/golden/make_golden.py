@@ -137,14 +137,14 @@ def gen_local(ref, name, *, kind, B, shape, dim, heads, window=4, attn_2d=False,
 
 
 def gen_lara(ref, name, *, B, shape, dim, heads, landmarks, proposal_gen, mis_type='mis-opt', alpha=1.0,
-             antithetic=False, multisample=False, mask_tail=None, train_seed=None, seed=0):
+             antithetic=False, multisample=False, mask_tail=None, train_seed=None, seed=0, pool='light'):
     cfg = dict(kind='lara', dim=dim, num_heads=heads, num_landmarks=landmarks, proposal_gen=proposal_gen,
                mis_type=mis_type, alpha_coeff=alpha, use_antithetics=antithetic, use_multisample=multisample,
-               pool_module_type='light', qkv_bias=True)
+               pool_module_type=pool, qkv_bias=True)
     m = ref.AttentionFactory.build_attention('lara', dict(
         dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, num_landmarks=landmarks,
         kernel_size=None, proposal_gen=proposal_gen, use_antithetics=antithetic, use_multisample=multisample,
-        pool_module_type='light', mis_type=mis_type, alpha_coeff=alpha))
+        pool_module_type=pool, mis_type=mis_type, alpha_coeff=alpha))
     _lively_init(m, seed)
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
@@ -216,6 +216,9 @@ def main():
     # --- LARA (lara.py) ---
     gen_lara(ref, 'lara_c4_geom', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', seed=29)
     gen_lara(ref, 'lara_c4_train', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', train_seed=71, seed=69)
+    # pool_module_type == 'dense' (Linear / LayerNorm across heads, lara.py:36-39, 131-139; the PVT configuration of the README)
+    gen_lara(ref, 'lara_2d_dense', B=2, shape=(14, 14), dim=128, heads=2, landmarks=49, proposal_gen='pool-mixed', pool='dense', alpha=2.0, seed=75)
+    gen_lara(ref, 'lara_2d_dense_vmixed', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='pool-vmixed', pool='dense', mis_type='mis-bh', seed=77)
     gen_lara(ref, 'lara_2d_pool_bh', B=1, shape=(10, 12), dim=64, heads=2, landmarks=16, proposal_gen='pool', mis_type='mis-bh', seed=31)
     gen_lara(ref, 'lara_2d_vmixed_biased', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='pool-vmixed', mis_type='mis-biased', seed=33)
     gen_lara(ref, 'lara_2d_noparam', B=1, shape=(8, 8), dim=64, heads=2, landmarks=16, proposal_gen='no-param-pool', alpha=0.5, seed=35)

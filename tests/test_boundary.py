@@ -218,3 +218,18 @@ def test_bench_reference_arm_line_on_cpu():
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1
     assert d['cpu_baseline']['value'] == d['value'] and d['e2e']['value'] == d['value']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_integration_md_ctypes_stub_matches_the_abi():
+    """The ctypes stub printed in INTEGRATION.md must declare the same EvaGeometry / EvaAdaptive fields as the binding the
+    package uses (a maintainer copying a stale stub makes the library read past the struct)."""
+    import re
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text[text.index('class EvaGeometry(ctypes.Structure)'):text.index('class EvaAdaptive(ctypes.Structure)')]
+    names = re.findall(r'"([a-z_]+)"', block)
+    assert names == [n for n, _ in _abi.EvaGeometry._fields_], names
+    call = re.search(r'g = EvaGeometry\(([^)]*)\)', text).group(1)
+    assert len(call.split(',')) == len(_abi.EvaGeometry._fields_)
+    header = open(os.path.join(ROOT, 'include', 'eva_sm100.h')).read()
+    for n, _ in _abi.EvaGeometry._fields_:
+        assert re.search(r'\b%s\b' % n, header), n
