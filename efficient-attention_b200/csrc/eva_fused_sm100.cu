@@ -313,6 +313,12 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         }
         item = item_next;
       }
+      // drain: the last hand-back of every ring slot is observed before the CTA exits (nothing depends on it, but a completed
+      // mbarrier phase that nobody waited for is what compute-sanitizer's synccheck reports as "missing wait")
+      if (nb >= (uint32_t)kSlots) {
+#pragma unroll 1
+        for (uint32_t n = nb - kSlots; n < nb; ++n) ptx::mbar_wait(bar(kFree0 + slot_of(n)), par_of(n));
+      }
       tr.finish();
     }
   } else if (warp == 5) {
