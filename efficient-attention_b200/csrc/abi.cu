@@ -202,10 +202,11 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
     if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(fused): %s: %s", msg, cudaGetErrorString(e));
     return EVA_OK;
   }
-  // Two kernels read q, k, v once each.  Run them back to back on SLICES of the batch small enough for the statistics pass
-  // to leave its slice in L2 (126 MB) for the window pass: the second read then hits L2 instead of HBM (c5 at batch 16:
-  // 1.67x algorithmic DRAM traffic with one pass over the whole batch).  EVA_SM100_L2_SLICE_MB=0 turns slicing off.
-  static const long long slice_mb = [] { const char* e_ = getenv("EVA_SM100_L2_SLICE_MB"); return e_ ? atoll(e_) : 40LL; }();
+  // Two kernels read q, k, v once each (c5 at batch 16: 1.67x algorithmic DRAM traffic).  Optionally they run back to back on
+  // SLICES of the batch small enough for the statistics pass to leave its slice in L2 for the window pass
+  // (EVA_SM100_L2_SLICE_MB=<MB>).  Measured on c5 (profiles/r02/README.md): 0.160 ms unsliced, 0.224 / 0.239 / 0.264 ms with
+  // 64 / 40 / 24 MB slices -- four to eight small launches cost more than the HBM re-read saves -- so the default is OFF.
+  static const long long slice_mb = [] { const char* e_ = getenv("EVA_SM100_L2_SLICE_MB"); return e_ ? atoll(e_) : 0LL; }();
   const long long elem = gin->io_dtype == EVA_F32 ? 4 : 2;
   const long long per_b = 3LL * g.N * g.H * g.D * elem;
   int nb = g.B;
