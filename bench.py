@@ -463,29 +463,50 @@ def run_ours(args):
             return _abi.eva_forward(q, k, v, geom, ada, bias=bias, return_path=True)
 
         clk = ClockSampler(local)
-        clk.__enter__()                      # sampled over both timed regions (core and e2e)
-        t_w, n_w = time.perf_counter(), 0
-        while n_w < max(Wm, 3) or time.perf_counter() - t_w < 0.2:     # >= W launches and >= 0.2 s: clocks and caches settled
+        clk.__enter__()                      # sampled over the timed regions (core, sustained core, e2e)
+        # EXACTLY max(W, 3) warm-up launches, then K timed launches (the contract's protocol).  The kernel draws ~1 kW: after
+        # ~0.1 s of back-to-back launches the board reaches its power cap and the SM clock settles near 1.77 GHz (sw_power_cap),
+        # so a long warm-up would time the power-capped state -- that state is measured separately below (`sustained`), like the
+        # two bf16 figures of MEASURED_PEAKS.json; its HBM figure, this line's denominator, is a burst measurement too.
+        n_w = max(Wm, 3)
+        for _ in range(n_w):
             _, path = core()
-            n_w += 1
-            if n_w % 16 == 0:
-                torch.cuda.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed_launches(n):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            ev0.record()
+            for a_, b_ in per_launch:
+                a_.record()
+                core()
+                b_.record()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1), sum(a_.elapsed_time(b_) for a_, b_ in per_launch) / n
+
         clk.mark()
         torch.cuda.synchronize()
-        per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        ev0.record()
-        for a_, b_ in per_launch:
-            a_.record()
-            core()
-            b_.record()
-        ev1.record()
-        torch.cuda.synchronize()
-        launch_ms = sum(a_.elapsed_time(b_) for a_, b_ in per_launch) / K     # device time of one eva_forward launch
-        core_ms = reduce_max_ms(ev0.elapsed_time(ev1), dev, world)
+        total_ms, launch_ms = timed_launches(K)          # launch_ms: device time of one eva_forward launch
+        core_ms = reduce_max_ms(total_ms, dev, world)
+        core_clk = clk.summary()
+        # the same K launches after `--sustain-seconds` of continuous load (power-capped steady state)
+        sustained = None
+        if args.sustain_seconds > 0:
+            t_s = time.perf_counter()
+            while time.perf_counter() - t_s < args.sustain_seconds:
+                for _ in range(16):
+                    core()
+                torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            clk.mark()
+            s_total, s_launch = timed_launches(K)
+            s_ms = reduce_max_ms(s_total, dev, world)
+            sustained = {'ms_per_step': s_ms / K, 'launch_ms': s_launch, 'after_seconds_of_load': args.sustain_seconds,
+                         'clocks': clk.summary()}
         if world > 1:
             dist.barrier()
 
@@ -512,6 +533,7 @@ def run_ours(args):
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         Ke = max(3, min(K, 10))
+        clk.mark()
         e0.record()
         for _ in range(Ke):
             e2e_step()
@@ -520,6 +542,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_ms = reduce_max_ms(e0.elapsed_time(e1), dev, world)
         clk.__exit__(None, None, None)
+        e2e_clk = clk.summary()
         # the copy-only ceiling of the same buffers at this rank count (explains the e2e number)
         ceil_ms = copy_ceiling_ms(x_hosts, y_hosts, x_dev, torch.empty_like(x_dev), n_chunks, Ke, dev, world)
         del pipe
@@ -547,8 +570,10 @@ def run_ours(args):
             'dtype': args.dtype + ' I/O, f32 softmax/accumulate', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'tokens_per_step': tokens_per_step,
                        'l2_policy': f'inputs larger than L2 (qkv {3 * DIM * elem * B * TOKENS / 2**20:.0f} MiB per GPU)',
-                       'kernel_path': kernel_paths.get(path, str(path)), 'warmup_launches': n_w},
+                       'kernel_path': kernel_paths.get(path, str(path)), 'warmup_launches': n_w,
+                       'timing': 'K launches timed right after W warm-up launches (contract protocol); see `sustained` for the power-capped steady state'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'kernel': 'eva_fused_kernel' if path == 1 else ('eva_cluster_kernel' if path == 3 else 'chunk_stats + window_attn'),
                          'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': algo_bytes, 'launch_ms': launch_ms,
                          'launches_timed': K,
@@ -562,8 +587,15 @@ def run_ours(args):
                                      'what': 'same pinned buffers, chunks and streams, H2D + D2H in full duplex, no compute, all ranks at once'},
                     'frac_of_copy_ceiling': e2e_val / ceil_val},
             'gpu_launches': K * 2,  # fused: weight-pack + fused kernel; generic: chunk_stats + window_attn
-            'clocks': clk.summary(),
+            'clocks': core_clk,
         }
+        out['e2e']['clocks'] = e2e_clk
+        if sustained is not None:
+            sustained.update(value=tokens_per_step / (sustained['ms_per_step'] * 1e-3), unit='tokens/s',
+                             roofline_frac=algo_bytes / (sustained['launch_ms'] * 1e-3) / 1e9 / peak,
+                             what='the same K launches timed after continuous load: the kernel draws ~1 kW, the board sits at its power '
+                                  'cap (sw_power_cap) and the SM clock settles ~10 % below boost')
+            out['sustained'] = sustained
         if deit is not None:
             out['deit_p8'] = deit
         if world == 1 and not args.no_cpu:
@@ -594,6 +626,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-deit', action='store_true', help='skip the DeiT-tiny-p8 images/s leg')
     ap.add_argument('--deit-steps', type=int, default=100)
+    ap.add_argument('--sustain-seconds', type=float, default=1.0, help='continuous load before the `sustained` measurement (0 = skip)')
     ap.add_argument('--baseline-json', action='store_true', help='(internal) print the cpu_baseline object only')
     ap.add_argument('--baseline-seconds', type=float, default=12.0)
     args = ap.parse_args()
