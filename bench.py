@@ -480,15 +480,22 @@ def run_ours(args):
         def timed_launches(n):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for ev in [ev0, ev1] + [e_ for pair in per_launch for e_ in pair]:
+                ev.record()                    # CUDA events are created lazily at their first record: do that outside the timed region
+            torch.cuda.synchronize()
+            host = []
             ev0.record()
             for a_, b_ in per_launch:
+                t_h = time.perf_counter()
                 a_.record()
                 core()
                 b_.record()
+                host.append(time.perf_counter() - t_h)
             ev1.record()
             torch.cuda.synchronize()
             if os.environ.get('BENCH_DEBUG') == '1' and rank == 0:
                 sys.stderr.write('per-launch ms: ' + ' '.join(f'{a_.elapsed_time(b_):.3f}' for a_, b_ in per_launch) + '\n')
+                sys.stderr.write('host ms per iteration: ' + ' '.join(f'{h_ * 1e3:.3f}' for h_ in host) + '\n')
             return ev0.elapsed_time(ev1), sum(a_.elapsed_time(b_) for a_, b_ in per_launch) / n
 
         clk.mark()
