@@ -17,7 +17,7 @@ cuobjdump -sass "$LIB" | c++filt | awk '
   if ($0 ~ /STTM/) sttm[name]++
   if ($0 ~ /SYNCS/) syncs[name]++
   if ($0 ~ /UCGABAR/) cga[name]++
-  if ($0 ~ /HMMA/) hmma[name]++
+  if ($0 ~ /[^A-Z]HMMA/) hmma[name]++
   if ($0 ~ /FFMA2|FADD2/) f2[name]++
   if ($0 ~ /MUFU.EX2/) ex2[name]++
 }
