@@ -168,3 +168,143 @@ def num_chunks_of(seq_shape, chunk, chunk_ext=0):
     if len(seq_shape) == 2:
         return (seq_shape[0] // chunk) * (seq_shape[1] // chunk)
     return seq_shape[0] // chunk
+
+
+# ------------------------------------------------------------------------------------------------
+# LARA (lara.py:84-251)
+# ------------------------------------------------------------------------------------------------
+def _prm(data, omega):
+    """d^-1/2 <omega_c, x_n> - d^-1/2 |x_n|^2 / 2 -> [..., c, n]   (attn_utils.py:324-336, 347)."""
+    s = data.shape[-1] ** -0.5
+    return s * (omega @ data.transpose(-1, -2)) - 0.5 * s * (data * data).sum(-1).unsqueeze(-2)
+
+
+def _segment_means(t, n_lm):
+    """1-D landmarks: means over n_lm consecutive segments, the first ones one token shorter when N % n_lm != 0 (lara.py:104-124)."""
+    B, H, N, d = t.shape
+    if N <= n_lm:
+        return t
+    seg = N // n_lm
+    if N % n_lm == 0:
+        return t.reshape(B, H, n_lm, seg, d).mean(-2)
+    n_short = (seg + 1) * n_lm - N
+    a = t[:, :, :n_short * seg].reshape(B, H, n_short, seg, d).mean(-2)
+    b = t[:, :, n_short * seg:].reshape(B, H, n_lm - n_short, seg + 1, d).mean(-2)
+    return torch.cat([a, b], -2)
+
+
+def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded, alpha_coeff,
+                    wq, bq, gq, betq, wk, bk, gk, betk, dense=False, ln_eps=1e-5, pad_mask=None, noise=None):
+    """q, k, v [B, N, H, d] -> [B, N, H * d] float32: landmarks (pooled 2-D 'light' / 'dense', or 1-D segment means with optional
+    per-token Linear + LayerNorm), optional landmark mixing, then the self-normalised importance-sampling estimator with the three
+    MIS variants.  sample_mode: 0 one sample per landmark, 1 antithetic (noise [.., C, d] -> [mu + e ; mu - e]), 2 multi (noise [.., 2C, d])."""
+    B, N, H, d = q.shape
+    scale = d ** -0.5
+    qh, kh, vh = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))           # [B, H, N, d]
+    if zero_padded and pad_mask is not None:
+        keep = (~pad_mask.to(torch.bool)).to(torch.float32).view(B, 1, N, 1)
+        qh, kh, vh = qh * keep, kh * keep, vh * keep
+    two_d = len(seq_shape) == 2
+    if two_d:
+        gh, gw = seq_shape
+        side = int(math.isqrt(landmarks))
+
+        def pool(t):                                                            # [B, H, N, d] -> [B, H, side^2, d]
+            grid = t.reshape(B * H, gh, gw, d).permute(0, 3, 1, 2)
+            return F.adaptive_avg_pool2d(grid, side).flatten(2).transpose(1, 2).reshape(B, H, side * side, d)
+        q_bar, k_bar = pool(qh), pool(kh)
+        if wq is not None and dense:                                            # Linear / LayerNorm over all channels (head-major)
+            merge = lambda t: t.permute(0, 2, 1, 3).reshape(B, -1, H * d)
+            split = lambda t: t.reshape(B, -1, H, d).permute(0, 2, 1, 3)
+            q_bar = split(_linear_ln(merge(q_bar), wq, bq, gq, betq, ln_eps))
+            k_bar = split(_linear_ln(merge(k_bar), wk, bk, gk, betk, ln_eps))
+        elif wq is not None:
+            q_bar, k_bar = _linear_ln(q_bar, wq, bq, gq, betq, ln_eps), _linear_ln(k_bar, wk, bk, gk, betk, ln_eps)
+        if mixed:
+            lg = scale * (k_bar @ k_bar.transpose(-1, -2))
+            if mixed == 2:
+                lg = lg + torch.log(torch.linalg.vector_norm(pool(vh), ord=2, dim=-1) + 1e-4).unsqueeze(-2)
+            k_bar = torch.softmax(lg, -1) @ k_bar
+    else:
+        q2, k2 = qh, kh
+        if per_token_proj:
+            q2, k2 = _linear_ln(qh, wq, bq, gq, betq, ln_eps), _linear_ln(kh, wk, bk, gk, betk, ln_eps)
+        q_bar, k_bar = _segment_means(q2, landmarks), _segment_means(k2, landmarks)
+    mu = q_bar + k_bar
+    rep = 1
+    if noise is None:
+        omega = mu
+    elif sample_mode == _abi.LARA_SAMPLE_ANTITHETIC:
+        omega, rep = torch.cat([mu + noise.float(), mu - noise.float()], -2), 2
+    elif sample_mode == _abi.LARA_SAMPLE_MULTI:
+        omega, rep = mu.repeat(1, 1, 2, 1) + noise.float(), 2
+    else:
+        omega = mu + noise.float()
+    A = _prm(qh, omega)                                                         # [B, H, S, N]
+    Bk = _prm(kh, omega)
+    if pad_mask is not None:
+        Bk = Bk.masked_fill(pad_mask.to(torch.bool).view(B, 1, 1, N), float('-inf'))
+    kv = torch.softmax(Bk, -1) @ vh
+    if mis_type == 'mis-opt':
+        t = torch.softmax(scale * (q_bar @ qh.transpose(-1, -2)), -1).repeat(1, 1, rep, 1)
+        Lm = _prm(mu.repeat(1, 1, rep, 1), omega)                               # [B, H, S(omega), S(mu)]
+        lp = torch.diagonal(Lm, dim1=-1, dim2=-2).unsqueeze(-1)
+        bh = torch.exp(lp - torch.logsumexp(Lm, -1, keepdim=True))
+        log_alpha = torch.log((bh + alpha_coeff * (t - t.mean(-2, keepdim=True))).clamp(min=1e-8))
+    elif mis_type == 'mis-bh':
+        log_alpha = 0.0
+        lp = torch.logsumexp(_prm(mu, omega), -1, keepdim=True)
+    else:                                                                       # 'mis-biased'
+        log_alpha = (scale * (mu @ qh.transpose(-1, -2))).repeat(1, 1, rep, 1)
+        lp = torch.logsumexp(_prm(mu, omega), -1, keepdim=True)
+    logw = log_alpha + A + torch.logsumexp(Bk, -1, keepdim=True) - lp
+    out = torch.softmax(logw, -2).transpose(-1, -2) @ kv                        # [B, H, N, d]
+    return out.permute(0, 2, 1, 3).reshape(B, N, H * d)
+
+
+class LaraCoreFn(torch.autograd.Function):
+    """forward: `lara_forward` of libeva_sm100 (landmarks given by the caller when `dense`); backward: autograd through
+    `lara_core_torch` on the saved inputs."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, noise, given, wq, bq, gq, betq, wk, bk, gk, betk, meta):
+        proj = _abi.adaptive(*([None] * 8), mu_coeff=1.0) if (meta['dense'] or wq is None) else \
+            _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=1.0, ln_eps=meta['ln_eps'])
+        out = _abi.lara_forward(q, k, v, proj=proj, pad_mask=meta['pad_mask'], noise=noise,
+                                given_landmarks=None if given is None else given.detach(), **meta['kernel'])
+        ctx.meta = meta
+        ctx.save_for_backward(q, k, v, noise, wq, bq, gq, betq, wk, bk, gk, betk)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        meta = ctx.meta
+        need = list(ctx.needs_input_grad[:4]) + list(ctx.needs_input_grad[5:13])
+        with torch.enable_grad():
+            ins = [None if t is None else t.detach().requires_grad_(n and t.is_floating_point()) for t, n in zip(saved, need)]
+            q, k, v, noise, wq, bq, gq, betq, wk, bk, gk, betk = ins
+            kk = meta['kernel']
+            out = lara_core_torch(q, k, v, seq_shape=kk['seq_shape'], landmarks=kk['landmarks'], per_token_proj=kk['per_token_proj'],
+                                  mixed=kk['mixed'], mis_type=kk['mis_type'], sample_mode=kk['sample_mode'],
+                                  zero_padded=kk['zero_padded'], alpha_coeff=kk['alpha_coeff'], wq=wq, bq=bq, gq=gq, betq=betq,
+                                  wk=wk, bk=bk, gk=gk, betk=betk, dense=meta['dense'], ln_eps=meta['ln_eps'],
+                                  pad_mask=meta['pad_mask'], noise=noise)
+            wanted = [t for t in ins if t is not None and t.requires_grad]
+            grads = torch.autograd.grad(out, wanted, grad_out.float().reshape(out.shape), allow_unused=True)
+        it = iter(grads)
+        res = []
+        for t, src in zip(ins, saved):
+            if t is not None and t.requires_grad:
+                gr = next(it)
+                res.append(None if gr is None else gr.to(src.dtype))
+            else:
+                res.append(None)
+        # inputs were (q, k, v, noise, given, 8 params, meta): `given` is a function of q, k and the parameters -- its gradient is
+        # already accounted for by recomputing the landmarks from q, k inside lara_core_torch
+        return tuple(res[:4]) + (None,) + tuple(res[4:]) + (None,)
+
+
+def lara_core(q, k, v, *, kernel_args, params, dense, ln_eps, pad_mask=None, noise=None, given=None):
+    meta = dict(kernel=kernel_args, dense=dense, ln_eps=ln_eps, pad_mask=pad_mask)
+    return LaraCoreFn.apply(q, k, v, noise, given, *params, meta)

@@ -6,9 +6,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _abi
+from . import _abi, _recompute
 from .abstract_attention import MultiheadAttention
-from .attn_utils import FlattenTranspose, attach_forward_only
+from .attn_utils import FlattenTranspose
 
 
 class LinearRA(MultiheadAttention):
@@ -65,6 +65,18 @@ class LinearRA(MultiheadAttention):
         params = (lin_q.weight, lin_q.bias, ln_q.weight, ln_q.bias, lin_k.weight, lin_k.bias, ln_k.weight, ln_k.bias)
         return _abi.memo(self, 'proj_params', params, lambda: _abi.adaptive(*params, mu_coeff=1.0, ln_eps=ln_q.eps))
 
+    def _raw_proj_params(self, two_d):
+        """The eight q_bar_gen / k_bar_gen parameters that take part in this call (None where absent) and the LayerNorm eps."""
+        gen = self.proposal_gen
+        if gen.startswith('adaptive-1d'):
+            mods = (self.q_bar_gen[0], self.q_bar_gen[1], self.k_bar_gen[0], self.k_bar_gen[1])
+        elif gen.startswith('pool') and two_d:
+            mods = (self.q_bar_gen[2], self.q_bar_gen[3], self.k_bar_gen[2], self.k_bar_gen[3])
+        else:
+            return (None,) * 8, 1e-5
+        lin_q, ln_q, lin_k, ln_k = mods
+        return (lin_q.weight, lin_q.bias, ln_q.weight, ln_q.bias, lin_k.weight, lin_k.bias, ln_k.weight, ln_k.bias), ln_q.eps
+
     def _dense_landmarks(self, q, k, v, seq_shape, with_v):
         """pool_module_type == 'dense' (lara.py:131-139): AdaptiveAvgPool2d over the token grid of ALL channels, then Linear(dim, dim)
         + LayerNorm(dim) -- a library GEMM on [B, C, dim] -- and back to heads.  -> float32 [B, H, 3, C, d] for the kernels."""
@@ -115,12 +127,17 @@ class LinearRA(MultiheadAttention):
         given = None
         if two_d and self.pool_module_type == 'dense' and self.proposal_gen.startswith('pool'):
             given = self._dense_landmarks(q, k, v, seq_shape, mixed == 2)
-        out = _abi.lara_forward(
-            q, k, v, seq_shape=tuple(seq_shape), landmarks=landmarks, given_landmarks=given,
-            per_token_proj=self.proposal_gen.startswith('adaptive-1d'), mixed=mixed, mis_type=self.mis_type,
-            sample_mode=mode, zero_padded=(not two_d and key_padding_mask is not None),
-            alpha_coeff=self.alpha_coeff, proj=self._proj_params(two_d), pad_mask=key_padding_mask, noise=noise)
-        out = attach_forward_only(out, packed)
+        kernel_args = dict(seq_shape=tuple(seq_shape), landmarks=landmarks, per_token_proj=self.proposal_gen.startswith('adaptive-1d'),
+                           mixed=mixed, mis_type=self.mis_type, sample_mode=mode,
+                           zero_padded=(not two_d and key_padding_mask is not None), alpha_coeff=self.alpha_coeff)
+        raw, ln_eps = self._raw_proj_params(two_d)
+        if _recompute.needs_grad(packed, *raw):
+            # training: kernel forward, backward by recomputation (see _recompute.py)
+            out = _recompute.lara_core(q, k, v, kernel_args=kernel_args, params=raw, dense=given is not None, ln_eps=ln_eps,
+                                       pad_mask=key_padding_mask, noise=noise, given=given)
+        else:
+            out = _abi.lara_forward(q, k, v, given_landmarks=given, proj=self._proj_params(two_d), pad_mask=key_padding_mask,
+                                    noise=noise, **kernel_args)
         x = self.proj(out.view((B,) + tuple(seq_shape) + (C,)))
         return self.proj_drop(x)
 

@@ -84,6 +84,8 @@ def _oracle_grads(cfg, sd, a):
     noise = a['noise'].double() if a['noise'] is not None else None
     if cfg['kind'] == 'causal_eva':
         y = O.causal_eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
+    elif cfg['kind'] == 'lara':
+        y = O.lara_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
     else:
         y = O.eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
     w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).double()
@@ -91,12 +93,15 @@ def _oracle_grads(cfg, sd, a):
     return y.detach(), x.grad, {k_: v_.grad for k_, v_ in sd64.items() if v_.is_floating_point() and v_.grad is not None}
 
 
-@pytest.mark.parametrize('name', ['eva_2d_train', 'eva_1d_train', 'eva_c1_train', 'eva_c3_train', 'causal_numchunks_train'])
+@pytest.mark.parametrize('name', ['eva_2d_train', 'eva_1d_train', 'eva_c1_train', 'eva_c3_train', 'causal_numchunks_train',
+                                  'lara_c4_train', 'lara_2d_train_anti', 'lara_2d_train_multi', 'lara_1d_even', 'lara_1d_uneven_mask',
+                                  'lara_2d_dense', 'lara_2d_dense_vmixed', 'lara_2d_vmixed_biased'])
 def test_module_gradients_match_oracle_autograd_fp32(name):
     cfg, sd, a = load_golden(name, dtype=torch.float32)
     m = build_module(cfg)
     m.load_state_dict(sd)
-    m = m.to(_dev()).train()
+    m = m.to(_dev())
+    m.train(a['noise'] is not None)              # fixtures without a noise draw were generated in eval mode
     y, gx, gp = _grads_of(m, cfg, a, _dev(), torch.float32)
     y64, gx64, gp64 = _oracle_grads(cfg, sd, a)
     assert rel_l2(y.cpu(), y64) < 2e-5
