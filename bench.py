@@ -412,6 +412,26 @@ def deit_leg(dev, world, batch=128, warm=20, steps=100):
                    host_overhead_ms_per_layer=(eager_ms - graph_ms) / len(model.blocks))
     except Exception as e:                                   # a capture problem must not lose the eager number
         out['graph_error'] = f'{type(e).__name__}: {e}'[:300]
+    if world == 1:
+        # where the model's time goes: the same forward with every attention layer replaced by the identity (eager, same protocol)
+        import copy
+        try:
+            bare = copy.deepcopy(model)
+            for blk in bare.blocks:
+                blk.attn = torch.nn.Identity()
+
+            def fwd_bare():
+                with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+                    return bare(x)
+            for _ in range(5):
+                fwd_bare()
+            torch.cuda.synchronize()
+            bare_ms = statistics.median(timed(fwd_bare, max(10, steps // 4)))
+            out.update(eager_ms_without_attention=bare_ms, attention_share_of_eager=(eager_ms - bare_ms) / eager_ms,
+                       attention_ms_per_layer=(eager_ms - bare_ms) / len(model.blocks))
+            del bare
+        except Exception as e:
+            out['attention_share_error'] = f'{type(e).__name__}: {e}'[:200]
     best = min(eager_ms, graph_ms) if graph_ms is not None else eager_ms
     out.update(images_per_s=batch * world / (best * 1e-3), ms_per_step=best, unit='images/s',
                timing='median of per-forward CUDA-event times, max over ranks')
