@@ -153,7 +153,8 @@ int eva_forward_workspace_bytes(const EvaGeometry* gin, size_t* bytes) {
   if (rc) return rc;
   if (!bytes) return fail(EVA_ERR_INVALID, "bytes is NULL");
   const size_t stats = align256((size_t)g.B * g.H * g.n_chunks * g.D * sizeof(float));
-  *bytes = 2 * stats + align256(eva::fused_workspace_bytes(g));
+  // k_bar | beta | fused-kernel scratch | per-window flags of the one-pass causal kernel
+  *bytes = 2 * stats + align256(eva::fused_workspace_bytes(g)) + align256((size_t)g.B * g.H * (g.n_windows > 0 ? g.n_windows : 1) * sizeof(unsigned int));
   return EVA_OK;
 }
 
@@ -217,6 +218,14 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   const bool causal_fast = eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias, bias_stride_h);
   if (path_taken) *path_taken = causal_fast ? 2 : 0;
   ++g_path_count[causal_fast ? 2 : 0];
+  if (causal_fast && eva::causal_one_pass_supported(g, *ada)) {
+    // one pass over q, k, v: the window kernel computes the chunk statistics itself
+    unsigned int* flags = reinterpret_cast<unsigned int*>(ws + 2 * stats + align256(eva::fused_workspace_bytes(g)));
+    const char* msg = "";
+    const cudaError_t e1 = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out, st, &msg, ada, noise, flags);
+    if (e1 != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal one-pass): %s: %s", msg, cudaGetErrorString(e1));
+    return EVA_OK;
+  }
   for (int b0 = 0; b0 < g.B; b0 += nb) {
     eva::Geo gs = g;
     gs.B = (g.B - b0) < nb ? (g.B - b0) : nb;

@@ -1,6 +1,11 @@
 // Causal EVA window attention for sm_100a (causal_eva.py:722-783) on tcgen05 / TMEM / TMA: stage B of the causal layer
-// for window = 256, no halo, head_dim 64, 16-bit I/O, no padding mask, optional Toeplitz (T5) position bias (BASELINE c5).  Stage A
-// (chunk statistics k_bar, beta) stays in chunk_stats_kernel.
+// for window = 256, no halo, head_dim 64, 16-bit I/O, no padding mask, optional Toeplitz (T5) position bias (BASELINE c5).
+// ONE PASS (round 2): when a window holds whole chunks (chunk in {64, 128, 256}) and there are <= 32 of them, the chunk statistics
+// (causal_eva.py:676-719: means, adaptive Linear + LayerNorm, phi-logits, softmax, beta) of the window's own chunks are computed by
+// the compute warps from the q / k / v tiles the window already has in shared memory and published to global memory with a
+// per-window flag; windows are handed out in window-major order, so the chunks a window needs (c < its queries' chunk) come from
+// CTAs that started earlier, and the producer warp waits for their flags before it converts the rows.  q, k, v are read from HBM
+// once instead of twice (chunk_stats kernel + this one).  Other geometries keep the separate statistics kernel.
 //
 // Work item = one window of one (batch, head): 256 queries x (256 causal local keys + up to 64 chunk keys).
 //   S   = Q [K_w ; k_bar]^T     M = 128 per row-block; row-block 0 only needs keys 0-127 (causality), row-block 1 all 256
@@ -38,8 +43,15 @@ enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFr
 struct Params {
   int B, H, N, n_win, items, n_chunks, cnp, chunk;
   int swap;                      // bit i: tensor map i (q, k, v) has its batch and token dimensions exchanged (time-major activations)
-  const float *kbar, *beta;      // [B, H, n_chunks, 64] fp32 from chunk_stats_kernel
+  const float *kbar, *beta;      // [B, H, n_chunks, 64] fp32 from chunk_stats_kernel (fuse == 0) or written by this kernel (fuse == 1)
   const float* bias;             // [256, 256] fp32 with bias[i][j] = f(i - j) (T5 bias shared by the heads), or NULL
+  // one-pass mode
+  int fuse, cpw;                 // chunks per window
+  float *kbar_w, *beta_w;        // same arrays, writable
+  unsigned int* flags;           // [B * H * n_win], zeroed by the launcher: 1 = the window's chunk statistics are in global memory
+  const float *w_q, *b_q, *g_q, *beta_q, *w_k, *b_k, *g_k, *beta_k;
+  float mu_coeff, ln_eps;
+  const float* noise;            // [B, H, n_chunks, 64] or NULL
 };
 
 template <typename T> struct Fmt;
@@ -95,6 +107,12 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
   const uint32_t tmem = *tmem_ptr;
   // TMEM columns of row-block rb: logits [base, base + n_loc + cnp), P (16-bit pairs) from base, O in the last 64 columns
   // of [base, base + n_loc + 64): rb 0 -> [0, 192), rb 1 -> [192, 512)
+  // work items: (batch * head)-major for the two-kernel path; WINDOW-major for the one-pass path (all windows 0 first), so that
+  // the windows a window depends on were handed out earlier
+  const int n_bh = p.B * p.H;
+  auto decode = [&](int item, int& wi, int& bh) {
+    if (p.fuse) { wi = item / n_bh; bh = item % n_bh; } else { wi = item % p.n_win; bh = item / p.n_win; }
+  };
   auto base_col = [](int rb) -> uint32_t { return rb ? 192u : 0u; };
   auto o_col = [](int rb) -> uint32_t { return rb ? 448u : 128u; };
 
@@ -103,7 +121,9 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int s = it & 1;
-      const int wi = item % p.n_win, bh = item / p.n_win, h = bh % p.H, b = bh / p.H;
+      int wi, bh;
+      decode(item, wi, bh);
+      const int h = bh % p.H, b = bh / p.H;
       if (it >= 2) ptx::mbar_wait(bar(kFree0 + s), ((it >> 1) - 1) & 1);
       const uint32_t st = ptx::smem_u32(stage_ptr(s));
       if (ptx::elect_one()) {
@@ -118,13 +138,37 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
       uint8_t* kb = kb_ptr(s);
       const float* src_k = p.kbar + (long long)bh * p.n_chunks * 64;
       const float* src_b = p.beta + (long long)bh * p.n_chunks * 64;
-      for (int idx = lane; idx < p.n_chunks * 8; idx += 32) {
+      int n_rows = p.n_chunks;
+      if (p.fuse) {
+        // rows of the chunks this window can see: those of earlier windows, and (several chunks per window) its own; wait until the
+        // CTAs that own them have published them
+        const int n_need = p.cpw > 1 ? wi + 1 : wi;
+        n_rows = n_need * p.cpw;
+        if (lane < n_need) {
+          const unsigned int* f = p.flags + (long long)bh * p.n_win + lane;
+          unsigned int v_ = 0, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v_) : "l"(f) : "memory");
+            if (!v_ && ++spins > 20000000u) __trap();          // bounded: a scheduling bug must not hang the GPU
+          } while (!v_);
+        }
+        __syncwarp();
+      }
+      for (int idx = lane; idx < p.cnp * 8; idx += 32) {
         const int row = idx >> 3, ch = idx & 7;
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8) + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8) + 1);
         const int off = row * 128 + ((ch ^ (row & 7)) << 4);
+        if (row >= n_rows) {                       // not visible to this window (or not computed yet): exact zeros, never stale data
+          if (p.fuse) {
+            *reinterpret_cast<uint4*>(kb + off) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(kb + 8192 + off) = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
+        // plain (coherent) loads: in the one-pass mode these rows were written by other CTAs of this launch
+        const float4 a0 = *reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8);
+        const float4 a1 = *(reinterpret_cast<const float4*>(src_k + row * 64 + ch * 8) + 1);
+        const float4 b0 = *reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8);
+        const float4 b1 = *(reinterpret_cast<const float4*>(src_b + row * 64 + ch * 8) + 1);
         *reinterpret_cast<uint4*>(kb + off) = make_uint4(Fmt<T>::pack2(a0.x, a0.y), Fmt<T>::pack2(a0.z, a0.w), Fmt<T>::pack2(a1.x, a1.y), Fmt<T>::pack2(a1.z, a1.w));
         *reinterpret_cast<uint4*>(kb + 8192 + off) = make_uint4(Fmt<T>::pack2(b0.x, b0.y), Fmt<T>::pack2(b0.z, b0.w), Fmt<T>::pack2(b1.x, b1.y), Fmt<T>::pack2(b1.z, b1.w));
       }
@@ -186,8 +230,170 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int s = it & 1;
-      const int wi = item % p.n_win, bh = item / p.n_win, h = bh % p.H, b = bh / p.H;
+      int wi, bh;
+      decode(item, wi, bh);
+      const int h = bh % p.H, b = bh / p.H;
       const int qc = (wi * kWin + 128 * rb + i) / p.chunk;     // chunk keys c < qc are visible (causal_eva.py:725-739)
+      if (p.fuse) {
+        // ---- one-pass mode: statistics of this window's own chunks from the tiles in shared memory (causal_eva.py:676-719) ----
+        // All 256 compute threads; scratch = rows 32-63 of the four k_bar / beta tile buffers (never read when cnp <= 32).
+        const uint32_t phq = (it >> 1) & 1;
+        ptx::mbar_wait(bar(kFullQK0 + s), phq);
+        const uint8_t* Qs = stage_ptr(s);
+        const uint8_t* Ks = Qs + 32768;
+        const uint8_t* Vs = Qs + 65536;
+        float* const partQ = reinterpret_cast<float*>(kb_ptr(0) + 4096);           // [16][64] partial sums (q) / beta partials 0-15
+        float* const partK = reinterpret_cast<float*>(kb_ptr(0) + 8192 + 4096);    // [16][64] partial sums (k) / beta partials 16-31
+        float* const meanv = reinterpret_cast<float*>(kb_ptr(1) + 4096);           // [2][4][64] chunk means, then [2][4][64] Linear + LN
+        float* const yv = meanv + 512;
+        float* const om = reinterpret_cast<float*>(kb_ptr(1) + 8192 + 4096);       // [4][64] omega
+        float* const lgv = om + 256;                                               // [256] logits, then softmax weights
+        float* const red = lgv + 256;                                              // [16] per-warp max | sum
+        const int t = tid;
+        const int gpc = p.chunk >> 4;                                              // 16-token groups per chunk
+        const long long c0 = (long long)bh * p.n_chunks + (long long)wi * p.cpw;   // first chunk of this window
+        {
+          const uint8_t* src = (t >> 7) ? Ks : Qs;
+          const int c8 = t & 7, g = (t >> 3) & 15;
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+          for (int j = 0; j < 16; ++j) {
+            const int row = 16 * g + j;
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + row * 128 + ((c8 ^ (row & 7)) << 4));
+            const T* e8 = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += to_f32(e8[e]);
+          }
+          float* dst = ((t >> 7) ? partK : partQ) + g * 64 + 8 * c8;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        ptx::named_bar_sync(3, 256);
+        for (int idx = t; idx < 2 * p.cpw * 64; idx += 256) {
+          const int f = idx & 63, cc = (idx >> 6) % p.cpw, side = idx / (64 * p.cpw);
+          const float* part = side ? partK : partQ;
+          float a = 0.f;
+          for (int g = cc * gpc; g < (cc + 1) * gpc; ++g) a += part[g * 64 + f];
+          meanv[(side * 4 + cc) * 64 + f] = a / (float)p.chunk;
+        }
+        ptx::named_bar_sync(3, 256);
+        {
+          // one warp per (side, chunk): lane owns outputs lane and lane + 32; LayerNorm by shuffles
+          const int side = warp >> 2, cc = warp & 3;
+          if (cc < p.cpw) {
+            const float* Wm = side ? p.w_k : p.w_q;
+            const float* bv = side ? p.b_k : p.b_q;
+            const float* gain = side ? p.g_k : p.g_q;
+            const float* lb = side ? p.beta_k : p.beta_q;
+            const float* mv = meanv + (side * 4 + cc) * 64;
+            float y0 = 0.f, y1 = 0.f;
+            if (Wm) {
+              y0 = bv ? __ldg(bv + lane) : 0.f;
+              y1 = bv ? __ldg(bv + lane + 32) : 0.f;
+              const float4* w0 = reinterpret_cast<const float4*>(Wm + lane * 64);
+              const float4* w1 = reinterpret_cast<const float4*>(Wm + (lane + 32) * 64);
+#pragma unroll 4
+              for (int i4 = 0; i4 < 16; ++i4) {
+                const float4 a = __ldg(w0 + i4), c = __ldg(w1 + i4);
+                const float4 m = *reinterpret_cast<const float4*>(mv + 4 * i4);
+                y0 = fmaf(a.x, m.x, y0); y0 = fmaf(a.y, m.y, y0); y0 = fmaf(a.z, m.z, y0); y0 = fmaf(a.w, m.w, y0);
+                y1 = fmaf(c.x, m.x, y1); y1 = fmaf(c.y, m.y, y1); y1 = fmaf(c.z, m.z, y1); y1 = fmaf(c.w, m.w, y1);
+              }
+              if (gain) {
+                const float mu = warp_sum(y0 + y1) * (1.0f / 64);
+                const float d0 = y0 - mu, d1 = y1 - mu;
+                const float inv = 1.0f / sqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / 64) + p.ln_eps);
+                y0 = d0 * inv * __ldg(gain + lane) + __ldg(lb + lane);
+                y1 = d1 * inv * __ldg(gain + lane + 32) + __ldg(lb + lane + 32);
+              }
+            }
+            yv[(side * 4 + cc) * 64 + lane] = y0;
+            yv[(side * 4 + cc) * 64 + lane + 32] = y1;
+            if (side) {
+              p.kbar_w[(c0 + cc) * 64 + lane] = y0;
+              p.kbar_w[(c0 + cc) * 64 + lane + 32] = y1;
+            }
+          }
+        }
+        ptx::named_bar_sync(3, 256);
+        for (int idx = t; idx < p.cpw * 64; idx += 256) {
+          const int f = idx & 63, cc = idx >> 6;
+          float o = p.w_q ? p.mu_coeff * (yv[cc * 64 + f] + yv[(4 + cc) * 64 + f]) : 0.f;
+          if (p.noise) o += __ldg(p.noise + (c0 + cc) * 64 + f);
+          om[cc * 64 + f] = o;
+        }
+        ptx::named_bar_sync(3, 256);
+        const int wpc = p.chunk >> 5;                       // warps per chunk
+        const int mycc = t / p.chunk;
+        float lg;
+        {
+          const float* omr = om + mycc * 64;
+          float acc = 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(Ks + t * 128 + ((c8 ^ (t & 7)) << 4));
+            const T* e8 = reinterpret_cast<const T*>(&raw);
+            const float4 o0 = *reinterpret_cast<const float4*>(omr + 8 * c8), o1 = *reinterpret_cast<const float4*>(omr + 8 * c8 + 4);
+            const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float f = to_f32(e8[e]); acc = fmaf(f, ov[e] - 0.5f * f, acc); }
+          }
+          lg = 0.125f * acc;
+          const float wm = warp_max(lg);
+          if (lane == 0) red[warp] = wm;
+        }
+        ptx::named_bar_sync(3, 256);
+        float pe;
+        {
+          float mx = kNegInf;
+          for (int w = (warp / wpc) * wpc; w < (warp / wpc + 1) * wpc; ++w) mx = fmaxf(mx, red[w]);
+          pe = exp_nonpos(lg - mx);
+          const float ws_ = warp_sum(pe);
+          if (lane == 0) red[8 + warp] = ws_;
+        }
+        ptx::named_bar_sync(3, 256);
+        {
+          float tot = 0.f;
+          for (int w = (warp / wpc) * wpc; w < (warp / wpc + 1) * wpc; ++w) tot += red[8 + w];
+          lgv[t] = pe / tot;
+        }
+        ptx::mbar_wait(bar(kFullV0 + s), phq);
+        ptx::named_bar_sync(3, 256);
+        {
+          const int c8 = t & 7, g = t >> 3;                 // 32 groups of 8 tokens
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = 8 * g + j;
+            const uint4 raw = *reinterpret_cast<const uint4*>(Vs + row * 128 + ((c8 ^ (row & 7)) << 4));
+            const T* e8 = reinterpret_cast<const T*>(&raw);
+            const float w_ = lgv[row];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(w_, to_f32(e8[e]), acc[e]);
+          }
+          float* dst = (g < 16 ? partQ + g * 64 : partK + (g - 16) * 64) + 8 * c8;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        ptx::named_bar_sync(3, 256);
+        for (int idx = t; idx < p.cpw * 64; idx += 256) {
+          const int f = idx & 63, cc = idx >> 6;
+          const int g8 = p.chunk >> 3;                      // 8-token groups per chunk
+          float a = 0.f;
+          for (int g = cc * g8; g < (cc + 1) * g8; ++g) a += (g < 16 ? partQ[g * 64 + f] : partK[(g - 16) * 64 + f]);
+          p.beta_w[(c0 + cc) * 64 + f] = a;
+        }
+        __threadfence();
+        ptx::named_bar_sync(3, 256);
+        if (t == 0) {
+          unsigned int* fl = p.flags + (long long)bh * p.n_win + wi;
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(fl), "r"(1u) : "memory");
+        }
+      }
       ptx::mbar_wait(bar(kSFull0 + rb), it & 1);
       ptx::tc_fence_after();
       // ---- pass 1: row maximum over the visible keys ----
@@ -337,7 +543,8 @@ static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long lo
 
 template <typename T>
 static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar, const float* beta,
-                            const float* bias, void* out, cudaStream_t st, const char** msg) {
+                            const float* bias, void* out, cudaStream_t st, const char** msg, const EvaAdaptive* ada, const float* noise,
+                            unsigned int* flags) {
   CUtensorMap tq, tk, tv, to;
   bool swq = false, swk = false, swv = false;
   if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin, &swq) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin, &swk) ||
@@ -351,6 +558,16 @@ static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const Vie
   p.n_chunks = g.n_chunks; p.cnp = (g.n_chunks + 15) & ~15; p.chunk = g.chunk;
   p.kbar = kbar; p.beta = beta; p.bias = bias;
   p.swap = (swq ? 1 : 0) | (swk ? 2 : 0) | (swv ? 4 : 0);
+  p.fuse = 0; p.cpw = kWin / (g.chunk > 0 ? g.chunk : kWin);
+  if (ada && flags) {                                   // one-pass mode (see causal_one_pass_supported)
+    p.fuse = 1;
+    p.kbar_w = const_cast<float*>(kbar); p.beta_w = const_cast<float*>(beta); p.flags = flags;
+    p.w_q = ada->w_q; p.b_q = ada->b_q; p.g_q = ada->ln_gain_q; p.beta_q = ada->ln_bias_q;
+    p.w_k = ada->w_k; p.b_k = ada->b_k; p.g_k = ada->ln_gain_k; p.beta_k = ada->ln_bias_k;
+    p.mu_coeff = ada->mu_coeff; p.ln_eps = ada->ln_eps; p.noise = noise;
+    const cudaError_t em = cudaMemsetAsync(flags, 0, sizeof(unsigned int) * (size_t)g.B * g.H * p.n_win, st);
+    if (em != cudaSuccess) { *msg = "cudaMemsetAsync(flags)"; return em; }
+  }
   auto kern = eva_causal_window_kernel<T>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamic);
   if (e != cudaSuccess) { *msg = "cudaFuncSetAttribute"; return e; }
@@ -382,10 +599,22 @@ bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const Vi
   return causal::get_encode() != nullptr;
 }
 
+// One pass (chunk statistics inside the window kernel): whole chunks per window, at most four of them, at most 32 chunks in all
+// (their tiles then leave rows 32-63 of the k_bar / beta buffers free as scratch), Linear on the k side present
+bool causal_one_pass_supported(const Geo& g, const EvaAdaptive& ada) {
+  static const bool off = [] { const char* e = getenv("EVA_SM100_CAUSAL_TWO_PASS"); return e && e[0] == '1'; }();
+  if (off) return false;
+  if (g.chunk != 64 && g.chunk != 128 && g.chunk != 256) return false;
+  if (((g.n_chunks + 15) & ~15) > 32) return false;
+  if (g.n_chunks * g.chunk != g.N) return false;
+  return ada.w_k != nullptr;
+}
+
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
-                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg) {
-  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg);
-  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg);
+                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg,
+                                 const EvaAdaptive* ada, const float* noise, unsigned int* flags) {
+  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags);
+  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags);
 }
 
 }  // namespace eva

@@ -35,8 +35,12 @@ cudaError_t launch_cluster(const Geo& g, int io_dtype, const View& q, const View
 // Causal window attention on tcgen05 (eva_causal_sm100.cu): stage B of the causal layer for window 256 / head_dim 64 / 16-bit I/O
 bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                              const float* bias, long long bias_sh);
+// ada + flags != NULL: one-pass mode -- the kernel computes the chunk statistics of every window itself (kbar / beta are then
+// OUTPUT scratch, flags = B * H * (N / 256) words of scratch); see causal_one_pass_supported
+bool causal_one_pass_supported(const Geo& g, const EvaAdaptive& ada);
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
-                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg);
+                                 const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg,
+                                 const EvaAdaptive* ada = nullptr, const float* noise = nullptr, unsigned int* flags = nullptr);
 
 // LARA (lara_generic.cu)
 struct LaraGeo {
