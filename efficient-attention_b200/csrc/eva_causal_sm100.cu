@@ -32,13 +32,13 @@
 namespace eva {
 namespace causal {
 
-constexpr int kWin = 256, kThreads = 320, kStageBytes = 3 * 32768, kKbBytes = 16384;
+constexpr int kWin = 256, kThreads = 448, kStatsThreads = 128, kStageBytes = 3 * 32768, kKbBytes = 16384;
 constexpr int kSmemBars = 2 * kStageBytes + 2 * kKbBytes;
 constexpr int kSmemBias = kSmemBars + 256;          // [256] fp32: Toeplitz position bias by distance i - j, x log2(e)
 constexpr int kDynamic = kSmemBias + 1024 + 1024;
 
 enum Bar { kFullQK0, kFullQK1, kFullV0, kFullV1, kFullKB0, kFullKB1, kFree0, kFree1,
-           kSFull0, kSFull1, kPFull0, kPFull1, kOFull0, kOFull1, kOFree0, kOFree1, kNumBars };
+           kSFull0, kSFull1, kPFull0, kPFull1, kOFull0, kOFull1, kOFree0, kOFree1, kStatsDone0, kStatsDone1, kNumBars };
 
 struct Params {
   int B, H, N, n_win, items, n_chunks, cnp, chunk;
@@ -93,6 +93,7 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
       ptx::mbar_init(bar(kPFull0 + s), 128);
       ptx::mbar_init(bar(kOFull0 + s), 1);
       ptx::mbar_init(bar(kOFree0 + s), 128);
+      ptx::mbar_init(bar(kStatsDone0 + s), kStatsThreads);
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_o);
@@ -219,42 +220,36 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
         }
       }
     }
-  } else {
-    // =================================== softmax / epilogue warps ===============================
-    const int rb = warp >> 2, wl = warp & 3;
-    const int i = 32 * wl + lane;                        // query row inside the row-block
-    const uint32_t trow = tmem + ((uint32_t)(32 * wl) << 16);
-    const uint32_t cS = base_col(rb), cO = o_col(rb);
-    const int n_blk = rb + 1;                            // 128-key blocks this row-block attends to
-    const float scale_log2 = 0.125f * kLog2e;
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int s = it & 1;
-      int wi, bh;
-      decode(item, wi, bh);
-      const int h = bh % p.H, b = bh / p.H;
-      const int qc = (wi * kWin + 128 * rb + i) / p.chunk;     // chunk keys c < qc are visible (causal_eva.py:725-739)
-      if (p.fuse) {
-        // ---- one-pass mode: statistics of this window's own chunks from the tiles in shared memory (causal_eva.py:676-719) ----
-        // All 256 compute threads; scratch = rows 32-63 of the four k_bar / beta tile buffers (never read when cnp <= 32).
+  } else if (warp >= 10) {
+    // =================================== chunk-statistics warpgroup (one-pass mode) =============
+    // Runs on its own four warps, up to one window AHEAD of the softmax warps (on the prefetched stage), so the statistics of
+    // window i + 1 are computed under the softmax of window i.  Scratch = rows 32-63 of the four k_bar / beta tile buffers
+    // (never read when cnp <= 32).
+    if (p.fuse) {
+      const int t = tid - 320, w4 = warp - 10;
+      float* const partQ = reinterpret_cast<float*>(kb_ptr(0) + 4096);           // [16][64] partial sums (q) / beta partials 0-15
+      float* const partK = reinterpret_cast<float*>(kb_ptr(0) + 8192 + 4096);    // [16][64] partial sums (k) / beta partials 16-31
+      float* const meanv = reinterpret_cast<float*>(kb_ptr(1) + 4096);           // [2][4][64] chunk means, then [2][4][64] Linear + LN
+      float* const yv = meanv + 512;
+      float* const om = reinterpret_cast<float*>(kb_ptr(1) + 8192 + 4096);       // [4][64] omega
+      float* const lgv = om + 256;                                               // [256] logits, then softmax weights
+      float* const red = lgv + 256;                                              // [4] chunk max | [4] chunk sum
+      const int gpc = p.chunk >> 4;                                              // 16-token groups per chunk
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int s = it & 1;
         const uint32_t phq = (it >> 1) & 1;
+        int wi, bh;
+        decode(item, wi, bh);
+        const long long c0 = (long long)bh * p.n_chunks + (long long)wi * p.cpw;   // first chunk of this window
         ptx::mbar_wait(bar(kFullQK0 + s), phq);
         const uint8_t* Qs = stage_ptr(s);
         const uint8_t* Ks = Qs + 32768;
         const uint8_t* Vs = Qs + 65536;
-        float* const partQ = reinterpret_cast<float*>(kb_ptr(0) + 4096);           // [16][64] partial sums (q) / beta partials 0-15
-        float* const partK = reinterpret_cast<float*>(kb_ptr(0) + 8192 + 4096);    // [16][64] partial sums (k) / beta partials 16-31
-        float* const meanv = reinterpret_cast<float*>(kb_ptr(1) + 4096);           // [2][4][64] chunk means, then [2][4][64] Linear + LN
-        float* const yv = meanv + 512;
-        float* const om = reinterpret_cast<float*>(kb_ptr(1) + 8192 + 4096);       // [4][64] omega
-        float* const lgv = om + 256;                                               // [256] logits, then softmax weights
-        float* const red = lgv + 256;                                              // [16] per-warp max | sum
-        const int t = tid;
-        const int gpc = p.chunk >> 4;                                              // 16-token groups per chunk
-        const long long c0 = (long long)bh * p.n_chunks + (long long)wi * p.cpw;   // first chunk of this window
-        {
-          const uint8_t* src = (t >> 7) ? Ks : Qs;
-          const int c8 = t & 7, g = (t >> 3) & 15;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {             // column sums of q and k over 16-token groups
+          const uint8_t* src = side ? Ks : Qs;
+          const int c8 = t & 7, g = t >> 3;
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -266,23 +261,24 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] += to_f32(e8[e]);
           }
-          float* dst = ((t >> 7) ? partK : partQ) + g * 64 + 8 * c8;
+          float* dst = (side ? partK : partQ) + g * 64 + 8 * c8;
           *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
-        ptx::named_bar_sync(3, 256);
-        for (int idx = t; idx < 2 * p.cpw * 64; idx += 256) {
+        ptx::named_bar_sync(3, kStatsThreads);
+        for (int idx = t; idx < 2 * p.cpw * 64; idx += kStatsThreads) {
           const int f = idx & 63, cc = (idx >> 6) % p.cpw, side = idx / (64 * p.cpw);
           const float* part = side ? partK : partQ;
           float a = 0.f;
           for (int g = cc * gpc; g < (cc + 1) * gpc; ++g) a += part[g * 64 + f];
           meanv[(side * 4 + cc) * 64 + f] = a / (float)p.chunk;
         }
-        ptx::named_bar_sync(3, 256);
-        {
-          // one warp per (side, chunk): lane owns outputs lane and lane + 32; LayerNorm by shuffles
-          const int side = warp >> 2, cc = warp & 3;
-          if (cc < p.cpw) {
+        ptx::named_bar_sync(3, kStatsThreads);
+        if (w4 < p.cpw) {
+          // one warp per chunk, q side then k side: lane owns outputs lane and lane + 32; LayerNorm by shuffles
+#pragma unroll 1
+          for (int side = 0; side < 2; ++side) {
+            const int cc = w4;
             const float* Wm = side ? p.w_k : p.w_q;
             const float* bv = side ? p.b_k : p.b_q;
             const float* gain = side ? p.g_k : p.g_q;
@@ -316,53 +312,55 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
               p.kbar_w[(c0 + cc) * 64 + lane + 32] = y1;
             }
           }
+          __syncwarp();
+          // omega of this chunk (same warp: no block barrier needed)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int f = lane + 32 * hh;
+            float o = p.w_q ? p.mu_coeff * (yv[w4 * 64 + f] + yv[(4 + w4) * 64 + f]) : 0.f;
+            if (p.noise) o += __ldg(p.noise + (c0 + w4) * 64 + f);
+            om[w4 * 64 + f] = o;
+          }
         }
-        ptx::named_bar_sync(3, 256);
-        for (int idx = t; idx < p.cpw * 64; idx += 256) {
-          const int f = idx & 63, cc = idx >> 6;
-          float o = p.w_q ? p.mu_coeff * (yv[cc * 64 + f] + yv[(4 + cc) * 64 + f]) : 0.f;
-          if (p.noise) o += __ldg(p.noise + (c0 + cc) * 64 + f);
-          om[cc * 64 + f] = o;
-        }
-        ptx::named_bar_sync(3, 256);
-        const int wpc = p.chunk >> 5;                       // warps per chunk
-        const int mycc = t / p.chunk;
-        float lg;
-        {
-          const float* omr = om + mycc * 64;
+        ptx::named_bar_sync(3, kStatsThreads);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {                   // phi-logit of token rows t and t + 128
+          const int row = t + 128 * hh;
+          const float* omr = om + (row / p.chunk) * 64;
           float acc = 0.f;
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(Ks + t * 128 + ((c8 ^ (t & 7)) << 4));
+            const uint4 raw = *reinterpret_cast<const uint4*>(Ks + row * 128 + ((c8 ^ (row & 7)) << 4));
             const T* e8 = reinterpret_cast<const T*>(&raw);
             const float4 o0 = *reinterpret_cast<const float4*>(omr + 8 * c8), o1 = *reinterpret_cast<const float4*>(omr + 8 * c8 + 4);
             const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float f = to_f32(e8[e]); acc = fmaf(f, ov[e] - 0.5f * f, acc); }
           }
-          lg = 0.125f * acc;
-          const float wm = warp_max(lg);
-          if (lane == 0) red[warp] = wm;
+          lgv[row] = 0.125f * acc;
         }
-        ptx::named_bar_sync(3, 256);
-        float pe;
-        {
+        ptx::named_bar_sync(3, kStatsThreads);
+        if (w4 < p.cpw) {                                  // one warp per chunk: max and sum over the chunk's tokens
+          const float* lc = lgv + w4 * p.chunk;
           float mx = kNegInf;
-          for (int w = (warp / wpc) * wpc; w < (warp / wpc + 1) * wpc; ++w) mx = fmaxf(mx, red[w]);
-          pe = exp_nonpos(lg - mx);
-          const float ws_ = warp_sum(pe);
-          if (lane == 0) red[8 + warp] = ws_;
+          for (int j = lane; j < p.chunk; j += 32) mx = fmaxf(mx, lc[j]);
+          mx = warp_max(mx);
+          float sm_ = 0.f;
+          for (int j = lane; j < p.chunk; j += 32) sm_ += exp_nonpos(lc[j] - mx);
+          sm_ = warp_sum(sm_);
+          if (lane == 0) { red[w4] = mx; red[4 + w4] = sm_; }
         }
-        ptx::named_bar_sync(3, 256);
-        {
-          float tot = 0.f;
-          for (int w = (warp / wpc) * wpc; w < (warp / wpc + 1) * wpc; ++w) tot += red[8 + w];
-          lgv[t] = pe / tot;
+        ptx::named_bar_sync(3, kStatsThreads);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = t + 128 * hh, cc = row / p.chunk;
+          lgv[row] = exp_nonpos(lgv[row] - red[cc]) / red[4 + cc];
         }
         ptx::mbar_wait(bar(kFullV0 + s), phq);
-        ptx::named_bar_sync(3, 256);
-        {
-          const int c8 = t & 7, g = t >> 3;                 // 32 groups of 8 tokens
+        ptx::named_bar_sync(3, kStatsThreads);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {                   // beta partial sums over 8-token groups
+          const int c8 = t & 7, g = (t >> 3) + 16 * hh;
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -375,12 +373,13 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] = fmaf(w_, to_f32(e8[e]), acc[e]);
           }
-          float* dst = (g < 16 ? partQ + g * 64 : partK + (g - 16) * 64) + 8 * c8;
+          float* dst = (hh ? partK : partQ) + (g & 15) * 64 + 8 * c8;
           *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
           *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
-        ptx::named_bar_sync(3, 256);
-        for (int idx = t; idx < p.cpw * 64; idx += 256) {
+        ptx::mbar_arrive(bar(kStatsDone0 + s));            // this stage's tiles are not read again by this warpgroup
+        ptx::named_bar_sync(3, kStatsThreads);
+        for (int idx = t; idx < p.cpw * 64; idx += kStatsThreads) {
           const int f = idx & 63, cc = idx >> 6;
           const int g8 = p.chunk >> 3;                      // 8-token groups per chunk
           float a = 0.f;
@@ -388,12 +387,28 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
           p.beta_w[(c0 + cc) * 64 + f] = a;
         }
         __threadfence();
-        ptx::named_bar_sync(3, 256);
+        ptx::named_bar_sync(3, kStatsThreads);
         if (t == 0) {
           unsigned int* fl = p.flags + (long long)bh * p.n_win + wi;
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(fl), "r"(1u) : "memory");
         }
       }
+    }
+  } else {
+    // =================================== softmax / epilogue warps ===============================
+    const int rb = warp >> 2, wl = warp & 3;
+    const int i = 32 * wl + lane;                        // query row inside the row-block
+    const uint32_t trow = tmem + ((uint32_t)(32 * wl) << 16);
+    const uint32_t cS = base_col(rb), cO = o_col(rb);
+    const int n_blk = rb + 1;                            // 128-key blocks this row-block attends to
+    const float scale_log2 = 0.125f * kLog2e;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int s = it & 1;
+      int wi, bh;
+      decode(item, wi, bh);
+      const int h = bh % p.H, b = bh / p.H;
+      const int qc = (wi * kWin + 128 * rb + i) / p.chunk;     // chunk keys c < qc are visible (causal_eva.py:725-739)
       ptx::mbar_wait(bar(kSFull0 + rb), it & 1);
       ptx::tc_fence_after();
       // ---- pass 1: row maximum over the visible keys ----
@@ -488,6 +503,7 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
       ptx::mbar_arrive(bar(kOFree0 + rb));
       const float inv = 1.0f / (s0 + s1);
       const int orow = 128 * rb + i;
+      if (p.fuse) ptx::mbar_wait(bar(kStatsDone0 + s), (it >> 1) & 1);   // the statistics warpgroup has read this stage's q tile
       uint8_t* row = stage_ptr(s) + orow * 128;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
