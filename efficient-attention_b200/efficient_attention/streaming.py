@@ -21,18 +21,12 @@ class HostPipeline:
         duplex PCIe bound).
     """
 
-    def __init__(self, module, chunk, depth=2, use_graphs=False, defer_join=False):
+    def __init__(self, module, chunk, depth=2, defer_join=False):
         self.module = module
         self.defer_join = bool(defer_join)
         self.done = None
         self.chunk = int(chunk)
         self.depth = int(depth)
-        # optional: one CUDA graph per buffer slot replays the module forward (a dozen launches + their host-side set-up) in one
-        # call.  Measured on B200 (tools/e2e_sweep.py): no gain -- at 8-16 stages the copies, not the host thread, bound the
-        # pipeline (7.4 ms per step against a 6.4 ms duplex-copy bound) -- so it is off by default.
-        self.use_graphs = bool(use_graphs)
-        self._graphs = [None] * self.depth
-        self._y = [None] * self.depth
         self._ys = [None] * self.depth
         self._ev_y_free = [None] * self.depth
         p = next(module.parameters())
@@ -70,24 +64,19 @@ class HostPipeline:
                 xd.copy_(x_host[lo:hi], non_blocking=True)
                 self._ev_in[s].record(self.s_in)
             main.wait_event(self._ev_in[s])
-            if self.use_graphs and hi - lo == self.chunk:
-                if self._ev_y_free[s] is not None:
-                    main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
-                y = self._replay(s, xd)
-            else:
-                # The module's output is a fresh tensor of the caching allocator.  Handing it to the copy-out stream directly
-                # (record_stream) makes the allocator hold the block until that stream has passed it, and with several
-                # chunks in flight it keeps growing the pool (cudaMalloc inside the timed loop).  One device-to-device copy
-                # into a persistent per-slot buffer (0.1 ms per 1024-image step) keeps all allocation on the compute stream.
-                y_mod = self.module(xd)
-                if self._ys[s] is None or self._ys[s].shape[1:] != y_mod.shape[1:] or self._ys[s].dtype != y_mod.dtype:
-                    self._ys[s] = torch.empty((self.chunk,) + tuple(y_mod.shape[1:]), dtype=y_mod.dtype, device=self.device)
-                    self._ys[s].record_stream(self.s_out)
-                if self._ev_y_free[s] is not None:
-                    main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
-                y = self._ys[s][:hi - lo]
-                y.copy_(y_mod)
-                del y_mod
+            # The module's output is a fresh tensor of the caching allocator.  Handing it to the copy-out stream directly
+            # (record_stream) makes the allocator hold the block until that stream has passed it, and with several
+            # chunks in flight it keeps growing the pool (cudaMalloc inside the timed loop).  One device-to-device copy
+            # into a persistent per-slot buffer (0.1 ms per 1024-image step) keeps all allocation on the compute stream.
+            y_mod = self.module(xd)
+            if self._ys[s] is None or self._ys[s].shape[1:] != y_mod.shape[1:] or self._ys[s].dtype != y_mod.dtype:
+                self._ys[s] = torch.empty((self.chunk,) + tuple(y_mod.shape[1:]), dtype=y_mod.dtype, device=self.device)
+                self._ys[s].record_stream(self.s_out)
+            if self._ev_y_free[s] is not None:
+                main.wait_event(self._ev_y_free[s])            # D2H of the chunk that used this slot's output buffer
+            y = self._ys[s][:hi - lo]
+            y.copy_(y_mod)
+            del y_mod
             self._ev_comp[s].record(main)
             self._ev_x_free[s] = self._ev_comp[s]
             with torch.cuda.stream(self.s_out):
@@ -105,15 +94,3 @@ class HostPipeline:
         """Make the current stream wait for the copies of the most recent call (needed with `defer_join=True`)."""
         if self.done is not None:
             torch.cuda.current_stream(self.device).wait_event(self.done)
-
-    def _replay(self, s, xd):
-        """Forward of slot s through its CUDA graph (captured on first use; x / y buffers of a slot are static)."""
-        if self._graphs[s] is None or self._graphs[s][1] != xd.data_ptr():
-            self.module(xd)                                          # warm-up outside capture (lazy initialisation, allocator)
-            torch.cuda.current_stream(self.device).synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._y[s] = self.module(xd)
-            self._graphs[s] = (g, xd.data_ptr())
-        self._graphs[s][0].replay()
-        return self._y[s]

@@ -33,13 +33,13 @@ for n_chunks, depth, defer, two in ((8, 2, False, False), (8, 2, True, False), (
     print(f'chunks {n_chunks:2d} depth {depth} defer_join {defer} two buffer pairs {two}: {dt * 1e3:.2f} ms/step  {B * 784 / dt / 1e6:.1f} M tokens/s', flush=True)
 for n_chunks, depth, graphs in ((8, 2, False),):
     if True:
-        pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth, use_graphs=graphs)
+        pipe = HostPipeline(layer, chunk=B // n_chunks, depth=depth)
         for _ in range(3): pipe(x_host, y_host)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for _ in range(8): pipe(x_host, y_host)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 8
         y1 = y_host.clone()
-        HostPipeline(layer, chunk=B // 8, use_graphs=False)(x_host, y_host)
+        HostPipeline(layer, chunk=B // 8)(x_host, y_host)
         torch.cuda.synchronize()
         same = bool((y1 == y_host).all())
         with torch.no_grad():
