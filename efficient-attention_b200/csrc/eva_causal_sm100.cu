@@ -617,9 +617,20 @@ bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const Vi
 
 // One pass (chunk statistics inside the window kernel): whole chunks per window, at most four of them, at most 32 chunks in all
 // (their tiles then leave rows 32-63 of the k_bar / beta buffers free as scratch), Linear on the k side present
+// Measured (c5, T = 4096, h = 8, profiles/r02/README.md 8): batch 16: 0.160 ms one pass vs 0.162 ms two passes (statistics kernel 0.071
+// + window kernel 0.086); batch 4: 0.061 vs 0.051 ms.  The statistics are SIMT work either way (TMEM is fully taken by the window's
+// logits, so they cannot use the tensor cores here), and four extra warps per SM do them no faster than a full-chip kernel does;
+// the flag dependencies add latency at small batches.  HBM traffic drops to 1.0x, time does not: OPT-IN
+// (EVA_SM100_CAUSAL_ONE_PASS=1 or eva_debug_set_causal_one_pass(1)).
+static int g_one_pass_mode = -1;           // -1: environment, 0: off, 1: on
+extern "C" int eva_debug_set_causal_one_pass(int mode) {
+  const int prev = g_one_pass_mode;
+  g_one_pass_mode = mode;
+  return prev;
+}
 bool causal_one_pass_supported(const Geo& g, const EvaAdaptive& ada) {
-  static const bool off = [] { const char* e = getenv("EVA_SM100_CAUSAL_TWO_PASS"); return e && e[0] == '1'; }();
-  if (off) return false;
+  static const bool env_on = [] { const char* e = getenv("EVA_SM100_CAUSAL_ONE_PASS"); return e && e[0] == '1'; }();
+  if (g_one_pass_mode < 0 ? !env_on : g_one_pass_mode == 0) return false;
   if (g.chunk != 64 && g.chunk != 128 && g.chunk != 256) return false;
   if (((g.n_chunks + 15) & ~15) > 32) return false;
   if (g.n_chunks * g.chunk != g.N) return false;

@@ -359,9 +359,28 @@ def test_fused_kernel_many_items_per_cta_fp16(grid, chunk, B, cluster):
     assert float(per_item.max()) < TOL_F16, float(per_item.max())
 
 
+class _causal_one_pass:
+    """Run a block with the opt-in one-pass mode of the causal tcgen05 kernel (chunk statistics inside the window kernel)."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        import ctypes
+        from efficient_attention import _abi
+        self.lib = _abi.load()
+        self.lib.eva_debug_set_causal_one_pass.restype = ctypes.c_int
+        self.prev = self.lib.eva_debug_set_causal_one_pass(ctypes.c_int(1 if self.on else 0))
+
+    def __exit__(self, *exc):
+        import ctypes
+        self.lib.eva_debug_set_causal_one_pass(ctypes.c_int(self.prev))
+
+
+@pytest.mark.parametrize('one_pass', [False, True])
 @pytest.mark.parametrize('dtype,tol', [(torch.float16, TOL_F16), (torch.bfloat16, TOL_BF16)])
 @pytest.mark.parametrize('chunk,with_noise,with_bias', [(256, False, False), (64, True, False), (128, False, True), (256, True, True)])
-def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, with_bias, dtype, tol):
+def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, with_bias, dtype, tol, one_pass):
     """Causal EVA core (window 256, no halo, head_dim 64, 16-bit I/O: the c5 geometry) through the tcgen05 window kernel
     and the CTA-per-chunk statistics kernel, against the oracle on identical inputs.  path == 2 proves the tcgen05
     kernel ran (a silent fall-back to the CUDA-core kernel would hide a regression)."""
@@ -392,7 +411,8 @@ def test_causal_tcgen05_window_kernel_vs_oracle(chunk, with_noise, with_bias, dt
     nz = noise.to(dev) if with_noise else None
     kbar, beta = _abi.eva_chunk_stats(q, k, v, geom, ada_s, noise=nz)          # CTA-per-chunk kernel (chunk >= 64)
     assert rel_l2(kbar.cpu(), kbar_w) < 2e-5 and rel_l2(beta.cpu(), beta_w) < 2e-5
-    out, path = _abi.eva_forward(q, k, v, geom, ada_s, noise=nz, bias=bias.to(dev) if with_bias else None, return_path=True)
+    with _causal_one_pass(one_pass):
+        out, path = _abi.eva_forward(q, k, v, geom, ada_s, noise=nz, bias=bias.to(dev) if with_bias else None, return_path=True)
     assert path == 2
     if with_bias:          # without the caller's Toeplitz guarantee a biased call must stay on the CUDA-core kernel
         geom0 = _abi.eva_geometry(q, seq_shape=(N,), window=w, ext=0, chunk=chunk, chunk_ext=0, causal=True,
@@ -686,9 +706,10 @@ def test_fused_kernel_many_items_vs_oracle_fp16(grid, chunk, B, cluster):
     assert worst < TOL_F16, worst
 
 
-def test_c5_causal_core_full_shape_fp16_vs_oracle():
-    """BASELINE config c5 at FULL size through the tcgen05 causal kernels: T=4096, h=8, d=64, window = chunk = 256, T5 bias,
-    fp16, against the float64 oracle on identical pre-quantised q/k/v (path == 2)."""
+@pytest.mark.parametrize('one_pass', [False, True])
+def test_c5_causal_core_full_shape_fp16_vs_oracle(one_pass):
+    """BASELINE config c5 at FULL size through the tcgen05 causal kernels (two passes, and the opt-in one-pass mode): T=4096, h=8,
+    d=64, window = chunk = 256, T5 bias, fp16, against the float64 oracle on identical pre-quantised q/k/v (path == 2)."""
     from efficient_attention import _abi
     B, H, d, N, w = 2, 8, 64, 4096, 256
     g = torch.Generator().manual_seed(41)
@@ -707,7 +728,8 @@ def test_c5_causal_core_full_shape_fp16_vs_oracle():
     q, k, v = qd[:, :, 0], qd[:, :, 1], qd[:, :, 2]
     geom = _abi.eva_geometry(q, seq_shape=(N,), window=w, ext=0, chunk=w, chunk_ext=0, causal=True, halo_left_only=True,
                              mask_queries=True, bias_toeplitz=True)
-    out, path = _abi.eva_forward(q, k, v, geom, _abi_ada(ada, dev, 1.0), bias=bias.to(dev), return_path=True)
+    with _causal_one_pass(one_pass):
+        out, path = _abi.eva_forward(q, k, v, geom, _abi_ada(ada, dev, 1.0), bias=bias.to(dev), return_path=True)
     assert path == 2
     err = rel_l2(out.cpu(), want)
     assert err < TOL_F16, err
