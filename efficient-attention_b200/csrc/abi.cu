@@ -249,6 +249,37 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   return EVA_OK;
 }
 
+int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
+                 const void* out, const void* grad_out, float* grad_qkv, float* grad_bias, float* chunk_rows, void* stream) {
+  eva::Geo g{};
+  eva::View vq, vk, vv;
+  int rc;
+  if ((rc = make_geo(gin, &g)) || (rc = make_view(q, "q", &vq)) || (rc = make_view(k, "k", &vk)) || (rc = make_view(v, "v", &vv)))
+    return rc;
+  if (g.n_chunks > 0 && (rc = check_ada(ada))) return rc;
+  if (g.n_chunks > 0 && !chunk_rows) return fail(EVA_ERR_INVALID, "chunk_rows is NULL");
+  if (!out || !grad_out || !grad_qkv) return fail(EVA_ERR_INVALID, "out / grad_out / grad_qkv is NULL");
+  if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(chunk_rows)) & 15u) != 0)
+    return fail(EVA_ERR_INVALID, "out / grad_out / chunk_rows must be 16-byte aligned");
+  if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
+    return fail(EVA_ERR_INVALID, "bias_stride_h must be 0 or L*J = %d", g.L * g.J);
+  if (grad_bias && !bias) return fail(EVA_ERR_INVALID, "grad_bias without bias");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long slot = (long long)g.B * g.H * g.n_chunks * g.D;
+  const long long tens = (long long)g.B * g.N * g.H * g.D;
+  float* kbar = chunk_rows;
+  float* beta = chunk_rows + slot;
+  if (g.n_chunks > 0) {
+    const cudaError_t e0 = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, kbar, beta, st);
+    if (e0 != cudaSuccess) return cuda_fail(e0, "eva_backward(chunk_stats)");
+  }
+  const cudaError_t e = eva::launch_eva_backward(g, gin->io_dtype, vq, vk, vv, pad_mask, ada, noise, kbar, beta, bias, bias_stride_h, out,
+                                                 grad_out, grad_qkv, grad_qkv + tens, grad_qkv + 2 * tens, chunk_rows + 2 * slot,
+                                                 chunk_rows + 3 * slot, grad_bias, chunk_rows + 4 * slot, st);
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_backward");
+}
+
 // ---------------------------------------------------------------------------------------------
 static int make_lara_geo(const LaraGeometry* in, eva::LaraGeo* g) {
   if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");

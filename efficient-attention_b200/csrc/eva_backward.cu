@@ -1,0 +1,634 @@
+// Backward of the EVA attention core for every geometry the forward kernels accept: 1-D / 2-D, halos, padding
+// masks, causal, chunk-less local / dense attention, head_dim 16 .. 128.  float32 maths on CUDA cores (gradients are accumulated
+// in float32 whatever the I/O format); T is only the HBM format of q, k, v, out and grad_out.
+//
+//   window_attn_bwd_kernel    gradient of eva.py:200-227 / causal_eva.py:722-783 / local_attention.py:134-182: the joint softmax over
+//                             [local keys | chunk keys] is recomputed tile by tile (no probabilities are stored by the forward),
+//                             dS = P o (dP - rowsum(dO o O)); writes dq, accumulates dk / dv / d k_bar / d beta / d bias
+//   chunk_stats_bwd_kernel    gradient of eva.py:155-196 / causal_eva.py:676-719: chunk softmax -> omega -> LayerNorm -> Linear ->
+//                             chunk means, back to dq / dk / dv; leaves per-chunk rows from which the caller forms the PARAMETER
+//                             gradients with library reductions (dW = dy^T mean, ...)
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace eva {
+
+constexpr int kBR = 64;    // query rows per CTA, 8 per warp
+constexpr int kBK = 64;    // keys per tile: 2 per lane in the logit phase, 8 per warp in the dK / dV phase
+constexpr int kBRw = 8;
+constexpr int kStS = kBR + 4;  // row stride of the transposed dS tile (16-byte aligned rows)
+
+template <int D> struct BwdSmem {
+  static constexpr int DP = D + 1;
+  static constexpr int kQ = 0;
+  static constexpr int kG = kQ + kBR * D;                      // grad_out rows
+  static constexpr int kK = kG + kBR * D;
+  static constexpr int kV = kK + kBK * DP;                     // v tile, later the transposed dS tile
+  static constexpr int kVsz = kBK * DP > kBK * kStS ? kBK * DP : kBK * kStS;
+  static constexpr int kP = kV + kVsz;
+  static constexpr int kS = kP + kBR * kBK;
+  static constexpr int kFloats = kS + kBR * kBK;
+  static constexpr size_t kBytes = (size_t)kFloats * sizeof(float) + (size_t)(kBK + 2 * kBR) * sizeof(int);
+};
+
+// logit of (query row li / token tq, key gj) after bias and masks, exactly as window_attn_kernel; returns whether it still depends
+// on q . k (false: the forward overwrote it with a constant, so no gradient flows to q, k or the bias)
+__device__ __forceinline__ bool finish_logit(const Geo& g, float& sv, int flag, int gj, int li, int tq, int qpad,
+                                             const float* __restrict__ bias, long long bias_off) {
+  if (flag == 2) { sv = kNegInf; return false; }
+  if (gj < g.J) {
+    bool live = true;
+    if (bias) sv += __ldg(bias + bias_off + (long long)li * g.J + gj);
+    if (flag == 1 || (g.mask_queries && qpad)) { sv = g.mask_fill; live = false; }
+    if (g.causal && gj > li + g.ext) { sv = kMaskVal; live = false; }
+    return live;
+  }
+  if (g.causal && (gj - g.J) >= tq / g.chunk) { sv = kMaskVal; return false; }
+  return true;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256, (D <= 64 ? 2 : 1))
+window_attn_bwd_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                       const float* __restrict__ kbar, const float* __restrict__ beta, const float* __restrict__ bias,
+                       const long long bias_sh, const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ dq,
+                       float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dkbar, float* __restrict__ dbeta,
+                       float* __restrict__ dbias) {
+  using L = BwdSmem<D>;
+  constexpr int DPL = Feat<D>::kPerLane;
+  constexpr int DP = L::DP;
+  extern __shared__ float sm[];
+  float* Qs = sm + L::kQ;       // [kBR][D] pre-scaled by d^-1/2
+  float* Gs = sm + L::kG;       // [kBR][D] grad_out
+  float* Ks = sm + L::kK;       // [kBK][DP]
+  float* Vs = sm + L::kV;       // [kBK][DP]
+  float* St = sm + L::kV;       // [kBK][kStS] dS, key-major (overwrites the v tile once dP is done)
+  float* Ps = sm + L::kP;       // [kBR][kBK]
+  float* Ss = sm + L::kS;       // [kBR][kBK] dS, row-major
+  int* kflag = reinterpret_cast<int*>(sm + L::kFloats);   // [kBK] 0 live, 1 masked, 2 absent
+  int* qtok = kflag + kBK;                                // [kBR]
+  int* qpad = qtok + kBR;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_rb = (g.L + kBR - 1) / kBR;
+  const long long cta = blockIdx.x;
+  const int rb = (int)(cta % n_rb), win = (int)((cta / n_rb) % g.n_windows);
+  const int bh = (int)(cta / ((long long)n_rb * g.n_windows));
+  const int b = bh / g.H, h = bh % g.H;
+  const float scale = rsqrtf((float)D);
+  const int n_keys = g.J + g.n_chunks;
+  const long long HD = (long long)g.H * D;
+  const long long bias_off = (long long)h * bias_sh;
+
+  if (tid < kBR) {
+    const int li = rb * kBR + tid;
+    const int tok = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+    qtok[tid] = tok;
+    qpad[tid] = (tok >= 0 && mask) ? (int)mask[(long long)b * g.N + tok] : 0;
+  }
+  for (int idx = tid; idx < kBR * (D / 8); idx += blockDim.x) {
+    const int r = idx / (D / 8), part = idx % (D / 8);
+    const int li = rb * kBR + r;
+    const int tok = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+    float f[8], gg[8];
+    if (tok >= 0) {
+      load8<T>(q.row<T>(b, tok, h) + part * 8, f);
+      load8<T>(dout + ((long long)b * g.N + tok) * HD + (long long)h * D + part * 8, gg);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      Qs[r * D + part * 8 + i] = tok >= 0 ? f[i] * scale : 0.f;
+      Gs[r * D + part * 8 + i] = tok >= 0 ? gg[i] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // delta_r = <grad_out_r, out_r>: the softmax Jacobian's rank-one term
+  float delta[kBRw];
+#pragma unroll
+  for (int r = 0; r < kBRw; ++r) {
+    const int row = warp * kBRw + r;
+    const int tq = qtok[row];
+    float part = 0.f;
+    if (tq >= 0) {
+      const T* orow = out + ((long long)b * g.N + tq) * HD + (long long)h * D;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) part = fmaf(to_f32(orow[lane + 32 * i]), Gs[row * D + lane + 32 * i], part);
+    }
+    delta[r] = warp_sum(part);
+  }
+
+  auto load_tile = [&](int kt0, bool with_v) {
+    for (int idx = tid; idx < kBK * (D / 8); idx += blockDim.x) {
+      const int j = idx / (D / 8), part = idx % (D / 8);
+      const int gj = kt0 + j;
+      float fk[8], fv[8];
+      int flag = 0;
+      bool have = false;
+      if (gj < g.J) {
+        const int tok = group_token(g, win, gj, g.window, g.ext);
+        if (tok >= 0) {
+          load8<T>(k.row<T>(b, tok, h) + part * 8, fk);
+          if (with_v) load8<T>(v.row<T>(b, tok, h) + part * 8, fv);
+          have = true;
+          flag = (mask && mask[(long long)b * g.N + tok]) ? 1 : 0;
+        } else {
+          flag = 1;
+        }
+      } else if (gj < n_keys) {
+        const long long base = (((long long)b * g.H + h) * g.n_chunks + (gj - g.J)) * D + part * 8;
+        load8<float>(kbar + base, fk);
+        if (with_v) load8<float>(beta + base, fv);
+        have = true;
+      } else {
+        flag = 2;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        Ks[j * DP + part * 8 + i] = have ? fk[i] : 0.f;
+        if (with_v) Vs[j * DP + part * 8 + i] = have ? fv[i] : 0.f;
+      }
+      if (part == 0) kflag[j] = flag;
+    }
+  };
+
+  // ---- pass 0: row maxima and normalisers of the joint softmax ----
+  float m[kBRw], linv[kBRw];
+#pragma unroll
+  for (int r = 0; r < kBRw; ++r) { m[r] = kNegInf; linv[r] = 0.f; }
+  for (int kt0 = 0; kt0 < n_keys; kt0 += kBK) {
+    __syncthreads();
+    load_tile(kt0, false);
+    __syncthreads();
+    float s[kBRw][2];
+#pragma unroll
+    for (int r = 0; r < kBRw; ++r) s[r][0] = s[r][1] = 0.f;
+    const float* k0 = Ks + lane * DP;
+    const float* k1 = Ks + (lane + 32) * DP;
+#pragma unroll 2
+    for (int e = 0; e < D; e += 4) {
+      const float a0 = k0[e], a1 = k0[e + 1], a2 = k0[e + 2], a3 = k0[e + 3];
+      const float c0 = k1[e], c1 = k1[e + 1], c2 = k1[e + 2], c3 = k1[e + 3];
+#pragma unroll
+      for (int r = 0; r < kBRw; ++r) {
+        const float4 qv = *reinterpret_cast<const float4*>(Qs + (warp * kBRw + r) * D + e);
+        s[r][0] = fmaf(qv.x, a0, fmaf(qv.y, a1, fmaf(qv.z, a2, fmaf(qv.w, a3, s[r][0]))));
+        s[r][1] = fmaf(qv.x, c0, fmaf(qv.y, c1, fmaf(qv.z, c2, fmaf(qv.w, c3, s[r][1]))));
+      }
+    }
+    const int f0 = kflag[lane], f1 = kflag[lane + 32];
+#pragma unroll
+    for (int r = 0; r < kBRw; ++r) {
+      const int row = warp * kBRw + r;
+      const int tq = qtok[row];
+      if (tq < 0) continue;
+      const int li = rb * kBR + row;
+      float s0 = s[r][0], s1 = s[r][1];
+      finish_logit(g, s0, f0, kt0 + lane, li, tq, qpad[row], bias, bias_off);
+      finish_logit(g, s1, f1, kt0 + lane + 32, li, tq, qpad[row], bias, bias_off);
+      const float mn = fmaxf(m[r], warp_max(fmaxf(s0, s1)));
+      float corr = 1.f, p = 0.f;
+      if (mn != kNegInf) { corr = exp_nonpos(m[r] - mn); p = exp_nonpos(s0 - mn) + exp_nonpos(s1 - mn); }
+      linv[r] = fmaf(linv[r], corr, warp_sum(p));
+      m[r] = mn;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kBRw; ++r) linv[r] = linv[r] > 0.f ? 1.0f / linv[r] : 0.f;
+
+  // ---- pass 1: per key tile dS, then dQ (registers), dK / dV (atomics) ----
+  float dqa[kBRw][DPL];
+#pragma unroll
+  for (int r = 0; r < kBRw; ++r)
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) dqa[r][i] = 0.f;
+
+  for (int kt0 = 0; kt0 < n_keys; kt0 += kBK) {
+    __syncthreads();
+    load_tile(kt0, true);
+    __syncthreads();
+    float s[kBRw][2], dp[kBRw][2];
+#pragma unroll
+    for (int r = 0; r < kBRw; ++r) s[r][0] = s[r][1] = dp[r][0] = dp[r][1] = 0.f;
+    {
+      const float* k0 = Ks + lane * DP;
+      const float* k1 = Ks + (lane + 32) * DP;
+      const float* v0 = Vs + lane * DP;
+      const float* v1 = Vs + (lane + 32) * DP;
+#pragma unroll 1
+      for (int e = 0; e < D; e += 4) {
+        const float a0 = k0[e], a1 = k0[e + 1], a2 = k0[e + 2], a3 = k0[e + 3];
+        const float c0 = k1[e], c1 = k1[e + 1], c2 = k1[e + 2], c3 = k1[e + 3];
+        const float x0 = v0[e], x1 = v0[e + 1], x2 = v0[e + 2], x3 = v0[e + 3];
+        const float y0 = v1[e], y1 = v1[e + 1], y2 = v1[e + 2], y3 = v1[e + 3];
+#pragma unroll
+        for (int r = 0; r < kBRw; ++r) {
+          const float4 qv = *reinterpret_cast<const float4*>(Qs + (warp * kBRw + r) * D + e);
+          const float4 gv = *reinterpret_cast<const float4*>(Gs + (warp * kBRw + r) * D + e);
+          s[r][0] = fmaf(qv.x, a0, fmaf(qv.y, a1, fmaf(qv.z, a2, fmaf(qv.w, a3, s[r][0]))));
+          s[r][1] = fmaf(qv.x, c0, fmaf(qv.y, c1, fmaf(qv.z, c2, fmaf(qv.w, c3, s[r][1]))));
+          dp[r][0] = fmaf(gv.x, x0, fmaf(gv.y, x1, fmaf(gv.z, x2, fmaf(gv.w, x3, dp[r][0]))));
+          dp[r][1] = fmaf(gv.x, y0, fmaf(gv.y, y1, fmaf(gv.z, y2, fmaf(gv.w, y3, dp[r][1]))));
+        }
+      }
+    }
+    const int f0 = kflag[lane], f1 = kflag[lane + 32];
+#pragma unroll
+    for (int r = 0; r < kBRw; ++r) {
+      const int row = warp * kBRw + r;
+      const int tq = qtok[row];
+      const int li = rb * kBR + row;
+      float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+      if (tq >= 0 && m[r] != kNegInf) {
+        float s0 = s[r][0], s1 = s[r][1];
+        const bool l0 = finish_logit(g, s0, f0, kt0 + lane, li, tq, qpad[row], bias, bias_off);
+        const bool l1 = finish_logit(g, s1, f1, kt0 + lane + 32, li, tq, qpad[row], bias, bias_off);
+        p0 = exp_nonpos(s0 - m[r]) * linv[r];
+        p1 = exp_nonpos(s1 - m[r]) * linv[r];
+        d0 = l0 ? p0 * (dp[r][0] - delta[r]) : 0.f;
+        d1 = l1 ? p1 * (dp[r][1] - delta[r]) : 0.f;
+        if (dbias) {
+          if (l0 && kt0 + lane < g.J) atomicAdd(dbias + bias_off + (long long)li * g.J + kt0 + lane, d0);
+          if (l1 && kt0 + lane + 32 < g.J) atomicAdd(dbias + bias_off + (long long)li * g.J + kt0 + lane + 32, d1);
+        }
+      }
+      s[r][0] = p0; s[r][1] = p1; dp[r][0] = d0; dp[r][1] = d1;
+    }
+    __syncthreads();   // every warp is done with the v tile: the transposed dS tile may take its place
+#pragma unroll
+    for (int r = 0; r < kBRw; ++r) {
+      const int row = warp * kBRw + r;
+      Ps[row * kBK + lane] = s[r][0];           Ps[row * kBK + lane + 32] = s[r][1];
+      Ss[row * kBK + lane] = dp[r][0];          Ss[row * kBK + lane + 32] = dp[r][1];
+      St[lane * kStS + row] = dp[r][0];         St[(lane + 32) * kStS + row] = dp[r][1];
+    }
+    __syncthreads();
+    // dQ rows of this warp: sum_j dS[r][j] K[j][:]
+#pragma unroll 2
+    for (int j = 0; j < kBK; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(St + j * kStS + warp * kBRw);
+      const float4 c = *reinterpret_cast<const float4*>(St + j * kStS + warp * kBRw + 4);
+      const float ds[kBRw] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      float kk[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) kk[i] = Feat<D>::has(lane, i) ? Ks[j * DP + lane + 32 * i] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kBRw; ++r)
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) dqa[r][i] = fmaf(ds[r], kk[i], dqa[r][i]);
+    }
+    // dK / dV of keys 8 warp .. 8 warp + 7 of the tile: sum over the CTA's rows
+    float dka[8][DPL], dva[8][DPL];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) dka[jj][i] = dva[jj][i] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < kBR; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(Ss + r * kBK + warp * 8);
+      const float4 c = *reinterpret_cast<const float4*>(Ss + r * kBK + warp * 8 + 4);
+      const float4 pa = *reinterpret_cast<const float4*>(Ps + r * kBK + warp * 8);
+      const float4 pc = *reinterpret_cast<const float4*>(Ps + r * kBK + warp * 8 + 4);
+      const float ds[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      const float pp[8] = {pa.x, pa.y, pa.z, pa.w, pc.x, pc.y, pc.z, pc.w};
+      float qf[DPL], gf[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        qf[i] = Feat<D>::has(lane, i) ? Qs[r * D + lane + 32 * i] : 0.f;
+        gf[i] = Feat<D>::has(lane, i) ? Gs[r * D + lane + 32 * i] : 0.f;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+          dka[jj][i] = fmaf(ds[jj], qf[i], dka[jj][i]);
+          dva[jj][i] = fmaf(pp[jj], gf[i], dva[jj][i]);
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = warp * 8 + jj, gj = kt0 + j;
+      float* pk = nullptr;
+      float* pv = nullptr;
+      if (gj < g.J) {
+        const int tok = group_token(g, win, gj, g.window, g.ext);
+        if (tok >= 0) {
+          const long long base = (((long long)b * g.N + tok) * g.H + h) * D;
+          pk = dk + base; pv = dv + base;
+        }
+      } else if (gj < n_keys) {
+        const long long base = (((long long)b * g.H + h) * g.n_chunks + (gj - g.J)) * D;
+        pk = dkbar + base; pv = dbeta + base;
+      }
+      if (!pk) continue;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) {
+          atomicAdd(pk + lane + 32 * i, dka[jj][i]);     // Qs carries d^-1/2 already
+          atomicAdd(pv + lane + 32 * i, dva[jj][i]);
+        }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kBRw; ++r) {
+    const int tq = qtok[warp * kBRw + r];
+    if (tq < 0) continue;
+    float* dst = dq + (((long long)b * g.N + tq) * g.H + h) * D;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i)
+      if (Feat<D>::has(lane, i)) atomicAdd(dst + lane + 32 * i, dqa[r][i] * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one warp per (batch, head, chunk); lane l owns features l, l + 32, ... (as chunk_stats_kernel)
+//   rows[slot][chunk row][D]: 0 dy_k  1 dy_q (at the Linear outputs)   2 mean_k  3 mean_q (Linear inputs)
+//                             4 n_k   5 n_q  (LayerNorm-normalised)    6 dout_k  7 dout_q (at the LayerNorm outputs)
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void warp_ln_stats(const float (&y)[Feat<D>::kPerLane], float eps, int lane, float (&n)[Feat<D>::kPerLane],
+                                              float& inv) {
+  constexpr int DPL = Feat<D>::kPerLane;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) s += Feat<D>::has(lane, i) ? y[i] : 0.f;
+  const float mean = warp_sum(s) * (1.0f / D);
+  float vv = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) { const float c = Feat<D>::has(lane, i) ? y[i] - mean : 0.f; vv = fmaf(c, c, vv); }
+  inv = 1.0f / sqrtf(warp_sum(vv) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) n[i] = Feat<D>::has(lane, i) ? (y[i] - mean) * inv : 0.f;
+}
+
+// gradient at the Linear output from the gradient at the (optional) LayerNorm output
+template <int D>
+__device__ __forceinline__ void warp_ln_bwd(const float (&dout)[Feat<D>::kPerLane], const float (&n)[Feat<D>::kPerLane], float inv,
+                                            const float* __restrict__ gain, int lane, float (&dy)[Feat<D>::kPerLane]) {
+  constexpr int DPL = Feat<D>::kPerLane;
+  if (!gain) {
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) dy[i] = dout[i];
+    return;
+  }
+  float dn[DPL], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) {
+    dn[i] = Feat<D>::has(lane, i) ? dout[i] * __ldg(gain + lane + 32 * i) : 0.f;
+    s1 += dn[i];
+    s2 = fmaf(dn[i], n[i], s2);
+  }
+  s1 = warp_sum(s1) * (1.0f / D);
+  s2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) dy[i] = Feat<D>::has(lane, i) ? inv * (dn[i] - s1 - n[i] * s2) : 0.f;
+}
+
+// dx[i] = sum_e W[e][i] dy[e]   (W row-major [out][in], read through L1)
+template <int D>
+__device__ __forceinline__ void warp_linear_bwd(const float* __restrict__ W, const float (&dy)[Feat<D>::kPerLane],
+                                                float (&dx)[Feat<D>::kPerLane], int lane) {
+  constexpr int DPL = Feat<D>::kPerLane;
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) dx[i] = 0.f;
+#pragma unroll
+  for (int ee = 0; ee < DPL; ++ee) {
+#pragma unroll 8
+    for (int jj = 0; jj < (D < 32 ? D : 32); ++jj) {
+      const float d = __shfl_sync(0xffffffffu, dy[ee], jj);
+      const float* wrow = W + (long long)(jj + 32 * ee) * D + lane;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) dx[i] = fmaf(__ldg(wrow + 32 * i), d, dx[i]);
+    }
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                       const EvaAdaptive ada, const float* __restrict__ noise, const float* __restrict__ dkbar,
+                       const float* __restrict__ dbeta, float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
+                       float* __restrict__ rows) {
+  constexpr int DPL = Feat<D>::kPerLane;
+  extern __shared__ float sm[];
+  float* WtK = sm;
+  float* WtQ = sm + D * D;
+  for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const int e = idx / D, i = idx % D;
+    WtK[i * D + e] = __ldg(ada.w_k + idx);
+    if (ada.w_q) WtQ[i * D + e] = __ldg(ada.w_q + idx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float scale = rsqrtf((float)D);
+  const float inv_cnt = 1.0f / (float)g.Jc;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  const long long slot = total * D;
+  for (long long wg = (long long)blockIdx.x * wpb + warp; wg < total; wg += (long long)gridDim.x * wpb) {
+    const int c = (int)(wg % g.n_chunks);
+    const int h = (int)((wg / g.n_chunks) % g.H);
+    const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+    const long long obase = wg * D;
+    // ---- forward, recomputed (chunk_stats_kernel) ----
+    float sq[DPL], sk[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) sq[i] = sk[i] = 0.f;
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;
+      const T* qr = q.row<T>(b, tok, h);
+      const T* kr = k.row<T>(b, tok, h);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        if (Feat<D>::has(lane, i)) { sq[i] += to_f32(qr[lane + 32 * i]); sk[i] += to_f32(kr[lane + 32 * i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { sq[i] *= inv_cnt; sk[i] *= inv_cnt; }
+    float yk[DPL], nk[DPL], kb[DPL], om[DPL], nq[DPL];
+    float inv_k = 1.f, inv_q = 1.f;
+    warp_linear<D>(WtK, ada.b_k, sk, yk, lane);
+    if (ada.ln_gain_k) {
+      warp_ln_stats<D>(yk, ada.ln_eps, lane, nk, inv_k);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i)
+        kb[i] = Feat<D>::has(lane, i) ? nk[i] * __ldg(ada.ln_gain_k + lane + 32 * i) + __ldg(ada.ln_bias_k + lane + 32 * i) : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) { kb[i] = yk[i]; nk[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { om[i] = 0.f; nq[i] = 0.f; }
+    if (ada.w_q) {
+      float yq[DPL], qb[DPL];
+      warp_linear<D>(WtQ, ada.b_q, sq, yq, lane);
+      if (ada.ln_gain_q) {
+        warp_ln_stats<D>(yq, ada.ln_eps, lane, nq, inv_q);
+#pragma unroll
+        for (int i = 0; i < DPL; ++i)
+          qb[i] = Feat<D>::has(lane, i) ? nq[i] * __ldg(ada.ln_gain_q + lane + 32 * i) + __ldg(ada.ln_bias_q + lane + 32 * i) : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) qb[i] = yq[i];
+      }
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) om[i] = ada.mu_coeff * (qb[i] + kb[i]);
+    }
+    float db[DPL], dkb_in[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+      db[i] = dkb_in[i] = 0.f;
+      if (!Feat<D>::has(lane, i)) continue;
+      if (noise) om[i] += __ldg(noise + obase + lane + 32 * i);
+      db[i] = dbeta[obase + lane + 32 * i];
+      dkb_in[i] = dkbar[obase + lane + 32 * i];
+    }
+    float m = kNegInf, l = 0.f, acc[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      const bool dead = tok < 0 || (mask && mask[(long long)b * g.N + tok]);
+      float lg = kMaskVal, vv[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) vv[i] = 0.f;
+      if (!dead) {
+        const T* kr = k.row<T>(b, tok, h);
+        const T* vr = v.row<T>(b, tok, h);
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+          if (!Feat<D>::has(lane, i)) continue;
+          const float kk = to_f32(kr[lane + 32 * i]);
+          part = fmaf(kk, om[i] - 0.5f * kk, part);
+          vv[i] = to_f32(vr[lane + 32 * i]);
+        }
+        lg = scale * warp_sum(part);
+      }
+      const float mn = fmaxf(m, lg);
+      const float corr = exp_nonpos(m - mn), p = exp_nonpos(lg - mn);
+      l = fmaf(l, corr, p);
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc[i] = fmaf(acc[i], corr, p * vv[i]);
+      m = mn;
+    }
+    const float inv_l = 1.0f / l;
+    float dsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) dsum = fmaf(db[i], acc[i] * inv_l, dsum);
+    dsum = warp_sum(dsum);            // <d beta, beta>
+    // ---- chunk softmax backward: dv, dk (logit path), d omega ----
+    float dom[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) dom[i] = 0.f;
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;     // constant logit, zero value: no gradient
+      const T* kr = k.row<T>(b, tok, h);
+      const T* vr = v.row<T>(b, tok, h);
+      float kk[DPL], p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        kk[i] = 0.f;
+        if (!Feat<D>::has(lane, i)) continue;
+        kk[i] = to_f32(kr[lane + 32 * i]);
+        p1 = fmaf(kk[i], om[i] - 0.5f * kk[i], p1);
+        p2 = fmaf(db[i], to_f32(vr[lane + 32 * i]), p2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
+      const float a = exp_nonpos(scale * p1 - m) * inv_l;
+      const float dlg = scale * a * (p2 - dsum);
+      const long long base = (((long long)b * g.N + tok) * g.H + h) * D;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        if (!Feat<D>::has(lane, i)) continue;
+        atomicAdd(dv + base + lane + 32 * i, a * db[i]);
+        atomicAdd(dk + base + lane + 32 * i, dlg * (om[i] - kk[i]));
+        dom[i] = fmaf(dlg, kk[i], dom[i]);
+      }
+    }
+    // ---- omega -> LayerNorm -> Linear -> means ----
+    float dok[DPL], doq[DPL], dyk[DPL], dyq[DPL], dmk[DPL], dmq[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+      dok[i] = dkb_in[i] + (ada.w_q ? ada.mu_coeff * dom[i] : 0.f);
+      doq[i] = ada.w_q ? ada.mu_coeff * dom[i] : 0.f;
+      dyq[i] = dmq[i] = 0.f;
+    }
+    warp_ln_bwd<D>(dok, nk, inv_k, ada.ln_gain_k, lane, dyk);
+    warp_linear_bwd<D>(ada.w_k, dyk, dmk, lane);
+    if (ada.w_q) {
+      warp_ln_bwd<D>(doq, nq, inv_q, ada.ln_gain_q, lane, dyq);
+      warp_linear_bwd<D>(ada.w_q, dyq, dmq, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+      if (!Feat<D>::has(lane, i)) continue;
+      const long long o = obase + lane + 32 * i;
+      rows[0 * slot + o] = dyk[i];  rows[1 * slot + o] = dyq[i];
+      rows[2 * slot + o] = sk[i];   rows[3 * slot + o] = sq[i];
+      rows[4 * slot + o] = nk[i];   rows[5 * slot + o] = nq[i];
+      rows[6 * slot + o] = dok[i];  rows[7 * slot + o] = doq[i];
+    }
+    for (int s = 0; s < g.Jc; ++s) {
+      const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
+      if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;
+      const long long base = (((long long)b * g.N + tok) * g.H + h) * D;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        if (!Feat<D>::has(lane, i)) continue;
+        atomicAdd(dk + base + lane + 32 * i, dmk[i] * inv_cnt);
+        if (ada.w_q) atomicAdd(dq + base + lane + 32 * i, dmq[i] * inv_cnt);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, int D>
+static cudaError_t launch_bwd_t(const Geo& g, const View& q, const View& k, const View& v, const uint8_t* mask,
+                                const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
+                                long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
+                                float* dbeta, float* dbias, float* rows, cudaStream_t st) {
+  auto kern = window_attn_bwd_kernel<T, D>;
+  const size_t smem = BwdSmem<D>::kBytes;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long ctas = (long long)((g.L + kBR - 1) / kBR) * g.n_windows * g.B * g.H;
+  if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)ctas, 256, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<const T*>(out),
+                                          reinterpret_cast<const T*>(dout), dq, dk, dv, dkbar, dbeta, dbias);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || g.n_chunks == 0) return e;
+  auto kern2 = chunk_stats_bwd_kernel<T, D>;
+  const size_t smem2 = 2 * (size_t)D * D * sizeof(float);
+  e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  if (e != cudaSuccess) return e;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  long long blocks = (total + 7) / 8;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  kern2<<<(unsigned)blocks, 256, smem2, st>>>(g, q, k, v, mask, *ada, noise, dkbar, dbeta, dq, dk, dv, rows);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                                const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
+                                long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
+                                float* dbeta, float* dbias, float* rows, cudaStream_t st) {
+#define EVA_BWD_CASE(DT, TY, DD) \
+  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, st);
+  switch (io_dtype * 256 + g.D) {
+    EVA_BWD_CASE(EVA_F32, float, 16) EVA_BWD_CASE(EVA_F32, float, 32) EVA_BWD_CASE(EVA_F32, float, 64) EVA_BWD_CASE(EVA_F32, float, 128)
+    EVA_BWD_CASE(EVA_F16, __half, 16) EVA_BWD_CASE(EVA_F16, __half, 32) EVA_BWD_CASE(EVA_F16, __half, 64) EVA_BWD_CASE(EVA_F16, __half, 128)
+    EVA_BWD_CASE(EVA_BF16, __nv_bfloat16, 16) EVA_BWD_CASE(EVA_BF16, __nv_bfloat16, 32) EVA_BWD_CASE(EVA_BF16, __nv_bfloat16, 64)
+    EVA_BWD_CASE(EVA_BF16, __nv_bfloat16, 128)
+    default: return cudaErrorInvalidValue;
+  }
+#undef EVA_BWD_CASE
+}
+
+}  // namespace eva

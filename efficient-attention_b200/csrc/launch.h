@@ -42,6 +42,13 @@ cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, cons
                                  const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg,
                                  const EvaAdaptive* ada = nullptr, const float* noise = nullptr, unsigned int* flags = nullptr);
 
+// Backward of the two generic stages (eva_backward.cu); kbar / beta are the forward statistics, dkbar / dbeta zeroed scratch,
+// rows = 8 per-chunk row slots (see chunk_stats_bwd_kernel); ada / noise / dkbar / dbeta / rows unused when g.n_chunks == 0
+cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                                const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
+                                long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
+                                float* dbeta, float* dbias, float* rows, cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

@@ -73,13 +73,14 @@ def load():
         lib.eva_window_attention.argtypes = [G, V, V, V, P, P, P, P, I64, P, P]
         lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
+        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
-                   'eva_forward', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
+                   'eva_forward', 'eva_backward', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
             getattr(lib, fn).restype = ctypes.c_int
-        if lib.eva_sm100_abi_version() != 2:
+        if lib.eva_sm100_abi_version() != 3:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
         _lib = lib
     return _lib
@@ -220,6 +221,34 @@ def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, ret
     _check(rc, 'eva_forward')
     del keep
     return (out, path.value) if return_path else out
+
+
+def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False):
+    """Gradients of eva_forward / eva_window_attention (`ada` None for chunk-less geometries).
+    Returns (grad_qkv float32 [3, B, N, H, D], grad_bias float32 like bias or None, chunk_rows float32 [12, B, H, C, D] or None --
+    the slots are listed at eva_backward in include/eva_sm100.h)."""
+    lib = load()
+    _require_cuda(q, k, v, out, grad_out, pad_mask, noise, bias)
+    B, N, H, D = q.shape
+    C = num_chunks(geom) if geom.chunk > 0 else 0
+    mask = _mask_u8(pad_mask, B, N)
+    noise = _f32(noise)
+    bias = _f32(bias)
+    out = out.detach().contiguous()
+    grad_out = grad_out.detach().to(out.dtype).contiguous()
+    grad_qkv = torch.zeros(3, B, N, H, D, dtype=torch.float32, device=q.device)
+    rows = torch.zeros(12, B, H, C, D, dtype=torch.float32, device=q.device) if C > 0 else None
+    grad_bias = torch.zeros_like(bias) if (want_bias_grad and bias is not None) else None
+    ada_s, keep = ada if ada is not None else (None, None)
+    bias_sh = 0 if bias is None or bias.shape[0] == 1 else bias.shape[1] * bias.shape[2]
+    with torch.cuda.device(q.device):
+        rc = lib.eva_backward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                              ctypes.byref(heads_view(v)), _ptr(mask), None if ada_s is None else ctypes.byref(ada_s), _ptr(noise),
+                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(grad_qkv), _ptr(grad_bias), _ptr(rows),
+                              _stream(q.device))
+    _check(rc, 'eva_backward')
+    del keep
+    return grad_qkv, grad_bias, rows
 
 
 def eva_chunk_stats(q, k, v, geom, ada, *, pad_mask=None, noise=None):

@@ -1,14 +1,18 @@
-"""Backward of the EVA attention cores: `autograd.Function`s whose FORWARD is the libeva_sm100 kernel call and
-whose BACKWARD recomputes the core in float32 with differentiable PyTorch ops on the device and lets autograd differentiate
-that recomputation (the flash-attention recipe -- store inputs, not probabilities -- with library ops standing in for
-hand-written backward kernels, which are the next step).
+"""Backward of the attention cores: `autograd.Function`s whose FORWARD is the libeva_sm100 kernel call.
 
-`eva_core_torch` is that recomputation: the maths of eva.py:151-227 / causal_eva.py:676-783 on [B, N, H, d] views, written with
-gather-index tables.  It is NEVER used for a forward result, with one labelled exception: attention-probability dropout
-(`CausalEVAttention(dropout > 0)` in training mode, causal_eva.py:778) -- the kernels have no dropout, so that configuration
-runs the recomputation for the forward too (`EvaCoreFn` is bypassed; see causal_eva.py here).
+EVA / causal EVA (`EvaCoreFn`): the BACKWARD is `eva_backward` of libeva_sm100 (csrc/eva_backward.cu: the probabilities are
+recomputed tile by tile from q, k, v -- the flash-attention recipe: store inputs and the output, not probabilities); the parameter
+gradients of the adaptive Linear / LayerNorm are library reductions over the per-chunk rows the kernel leaves.  `set_backward_impl(
+'torch')` (or EVA_SM100_BACKWARD=torch) switches to the older route, autograd through `eva_core_torch`, which the tests keep as a
+second opinion.  LARA (`LaraCoreFn`) still differentiates `lara_core_torch`.
+
+`eva_core_torch` / `lara_core_torch` are float32 restatements with differentiable PyTorch ops on [B, N, H, d] views (eva.py:151-227 /
+causal_eva.py:676-783 / lara.py:84-251).  They are NEVER used for a forward result, with one labelled exception:
+attention-probability dropout (`CausalEVAttention(dropout > 0)` in training mode, causal_eva.py:778) -- the kernels have no dropout,
+so that configuration runs `eva_core_torch` for the forward too (`EvaCoreFn` is bypassed; see causal_eva.py here).
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -16,6 +20,15 @@ import torch.nn.functional as F
 from . import _abi
 
 MASK_VAL = -5.0e4          # eva.py:139, causal_eva.py:488
+_BACKWARD_IMPL = os.environ.get('EVA_SM100_BACKWARD', 'cuda')
+
+
+def set_backward_impl(name):
+    """'cuda' (eva_backward kernels) or 'torch' (autograd through eva_core_torch); returns the previous setting."""
+    global _BACKWARD_IMPL
+    assert name in ('cuda', 'torch')
+    prev, _BACKWARD_IMPL = _BACKWARD_IMPL, name
+    return prev
 
 
 def _groups_1d(n, size, left, right, device):
@@ -115,7 +128,7 @@ def eva_core_torch(q, k, v, *, seq_shape, window, ext, chunk, chunk_ext, wq, bq,
 
 
 class EvaCoreFn(torch.autograd.Function):
-    """forward: `eva_forward` of libeva_sm100; backward: autograd through `eva_core_torch` on the saved inputs."""
+    """forward: `eva_forward` of libeva_sm100; backward: `eva_backward` (or autograd through `eva_core_torch`, see the module docstring)."""
 
     @staticmethod
     def forward(ctx, q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, meta):
@@ -124,12 +137,34 @@ class EvaCoreFn(torch.autograd.Function):
         out = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise,
                                bias=None if bias is None else bias.detach())
         ctx.meta = meta
-        ctx.save_for_backward(q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk)
+        ctx.save_for_backward(q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out)
         return out
 
     @staticmethod
+    def _backward_cuda(ctx, grad_out):
+        q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = ctx.saved_tensors
+        meta = ctx.meta
+        need = ctx.needs_input_grad
+        geom = _abi.eva_geometry(q, **meta['geometry'])
+        ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
+        gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
+                                              want_bias_grad=bias is not None and need[4])
+        D = q.shape[-1]
+        dyk, dyq, mk, mq, nk, nq, dok, doq = (rows[i].reshape(-1, D) for i in range(4, 12))
+        like = lambda g_, src: None if src is None else g_.to(src.dtype)
+        res = [gqkv[0].to(q.dtype) if need[0] else None, gqkv[1].to(k.dtype) if need[1] else None,
+               gqkv[2].to(v.dtype) if need[2] else None, None, like(gbias, bias) if gbias is not None else None]
+        for i, (src, make) in enumerate(((wq, lambda: dyq.t() @ mq), (bq, lambda: dyq.sum(0)), (gq, lambda: (doq * nq).sum(0)),
+                                         (betq, lambda: doq.sum(0)), (wk, lambda: dyk.t() @ mk), (bk, lambda: dyk.sum(0)),
+                                         (gk, lambda: (dok * nk).sum(0)), (betk, lambda: dok.sum(0)))):
+            res.append(like(make(), src) if (src is not None and need[5 + i]) else None)
+        return tuple(res) + (None,)
+
+    @staticmethod
     def backward(ctx, grad_out):
-        saved = ctx.saved_tensors
+        if _BACKWARD_IMPL == 'cuda':
+            return EvaCoreFn._backward_cuda(ctx, grad_out)
+        saved = ctx.saved_tensors[:13]
         meta = ctx.meta
         need = ctx.needs_input_grad[:13]
         with torch.enable_grad():

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define EVA_SM100_ABI_VERSION 2
+#define EVA_SM100_ABI_VERSION 3
 
 enum EvaDtype { EVA_F32 = 0, EVA_F16 = 1, EVA_BF16 = 2 };
 
@@ -115,6 +115,22 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
                 const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,
                 int32_t* path_taken, void* stream);
+
+/* Backward of eva_forward / eva_window_attention (the reference differentiates eva.py:151-227 / causal_eva.py:676-783 /
+ * local_attention.py:134-182 with autograd).  float32 CUDA-core kernels for every geometry the forward accepts; the
+ * probabilities are recomputed from q, k, v (nothing but the forward OUTPUT is kept between the two calls).
+ *   out, grad_out  io_dtype [batch, tokens, heads*head_dim] contiguous: the forward result and the gradient arriving at it
+ *   grad_qkv       float32 [3, batch, tokens, heads, head_dim] = dq | dk | dv, ZEROED by the caller (accumulated with atomics)
+ *   grad_bias      float32, the shape of `bias`, zeroed by the caller; NULL: not wanted
+ *   chunk_rows     float32 [12, batch, heads, C_n, head_dim], zeroed by the caller; NULL iff g->chunk == 0.  Slots on return:
+ *                  0 k_bar | 1 beta (recomputed) | 2 d k_bar | 3 d beta | 4 dy_k | 5 dy_q (gradients at the adaptive Linear outputs) |
+ *                  6 mean_k | 7 mean_q (the Linear inputs) | 8 n_k | 9 n_q (LayerNorm-normalised rows) | 10 dout_k | 11 dout_q
+ *                  (gradients at the LayerNorm outputs).  The PARAMETER gradients are plain reductions over the chunk rows, left to
+ *                  the caller's library: dW = dy^T mean, db = sum dy, d gain = sum dout * n, d ln_bias = sum dout.
+ *   ada            may be NULL iff g->chunk == 0. */
+int eva_backward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
+                 const void* out, const void* grad_out, float* grad_qkv, float* grad_bias, float* chunk_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LARA (lara.py).  Landmarks are the pooled q/k summaries; samples S = landmarks C, or 2C with

@@ -114,7 +114,7 @@ def test_cabi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_abi.LIB_PATH)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert _abi.load().eva_sm100_abi_version() == 2
+    assert _abi.load().eva_sm100_abi_version() == 3
 
 
 def test_cabi_rejects_bad_geometry_without_touching_the_gpu():

@@ -64,6 +64,58 @@ def test_recomputation_equals_the_kernels_fp32(seq_shape, window, ext, chunk, ca
     assert rel_l2(out.cpu(), ref.cpu()) < 2e-5
 
 
+@pytest.mark.parametrize('seq_shape,window,ext,chunk,causal,with_mask,d,dtype', [
+    ((14, 14), 7, 0, 2, False, False, 64, torch.float32), ((28, 28), 7, 0, 4, False, False, 64, torch.float32),
+    ((14, 14), 7, 3, 2, False, False, 64, torch.float32), ((96,), 16, 8, 12, False, True, 64, torch.float32),
+    ((128,), 32, 0, 16, True, True, 64, torch.float32), ((96,), 16, 16, 8, True, False, 64, torch.float32),
+    ((14, 14), 7, 0, 2, False, False, 32, torch.float32), ((96,), 16, 8, 12, False, True, 128, torch.float32),
+    ((28, 28), 7, 0, 4, False, False, 16, torch.float32), ((512,), 128, 128, 64, True, True, 64, torch.float32),
+    ((28, 28), 7, 0, 4, False, False, 64, torch.float16), ((512,), 128, 128, 64, True, False, 64, torch.bfloat16)])
+def test_backward_kernels_equal_autograd_through_the_recomputation(seq_shape, window, ext, chunk, causal, with_mask, d, dtype):
+    """`eva_backward` (csrc/eva_backward.cu) against autograd through `eva_core_torch` on identical inputs: gradients with respect
+    to q, k, v, the bias table and all eight adaptive Linear / LayerNorm parameters."""
+    from efficient_attention import _recompute
+    from test_gpu_parity import _rand_ada
+    dev = _dev()
+    B, H = 2, 2
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + window + ext + d)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dev, dtype)
+    two_d = len(seq_shape) == 2
+    L = window * window if two_d else window
+    J = (window + 2 * ext) ** 2 if two_d else window + (ext if causal else 2 * ext)
+    bias = (0.5 * torch.randn(H, L, J, generator=g)).to(dev)
+    ada = {k_: (v_.to(dev) if v_ is not None else None) for k_, v_ in _rand_ada(d, g).items()}
+    mask = None
+    if with_mask:
+        mask = torch.zeros(B, N, dtype=torch.bool, device=dev)
+        mask[1, N - 9:] = True
+    chunk_ext = 0 if causal else ext
+    noise = torch.randn(B, H, _recompute.num_chunks_of(seq_shape, chunk), d, generator=g).to(dev)
+    geometry = dict(seq_shape=seq_shape, window=window, ext=ext, chunk=chunk, chunk_ext=chunk_ext, causal=causal,
+                    halo_left_only=causal, mask_queries=causal)
+    names = ('wq', 'bq', 'gq', 'betq', 'wk', 'bk', 'gk', 'betk')
+    w = torch.randn(B, N, H * d, generator=g).to(dev)
+
+    def run(impl):
+        prev = _recompute.set_backward_impl(impl)
+        try:
+            x = qkv.clone().requires_grad_(True)
+            b_ = bias.clone().requires_grad_(True)
+            prm = [ada[n_].clone().requires_grad_(True) for n_ in names]
+            out = _recompute.eva_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, mu_coeff=1.0 if causal else 0.5,
+                                      params=prm, pad_mask=mask, noise=noise, bias=b_)
+            (out.float() * w).sum().backward()
+            return [x.grad.float(), b_.grad] + [p_.grad for p_ in prm]
+        finally:
+            _recompute.set_backward_impl(prev)
+    got, want = run('cuda'), run('torch')
+    tol = 2e-5 if dtype == torch.float32 else 6e-3     # 16-bit: the saved forward output and grad_out are rounded to the I/O format
+    for n_, a_, b_ in zip(('qkv', 'bias') + names, got, want):
+        assert torch.isfinite(a_).all(), n_
+        assert rel_l2(a_.cpu(), b_.cpu()) < tol, (n_, rel_l2(a_.cpu(), b_.cpu()))
+
+
 def _grads_of(module, cfg, a, dev, dtype):
     """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
     x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
