@@ -590,19 +590,24 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
 
 // ------------------------------------------------------------------------------------------------
 template <typename T, int D>
-static cudaError_t launch_bwd_t(const Geo& g, const View& q, const View& k, const View& v, const uint8_t* mask,
+static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
                                 float* dbeta, float* dbias, float* rows, cudaStream_t st) {
-  auto kern = window_attn_bwd_kernel<T, D>;
-  const size_t smem = BwdSmem<D>::kBytes;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const long long ctas = (long long)((g.L + kBR - 1) / kBR) * g.n_windows * g.B * g.H;
-  if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  kern<<<(unsigned)ctas, 256, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<const T*>(out),
-                                          reinterpret_cast<const T*>(dout), dq, dk, dv, dkbar, dbeta, dbias);
-  e = cudaGetLastError();
+  cudaError_t e;
+  if (window_bwd_tc_supported(g, io_dtype, mask)) {
+    e = launch_window_bwd_tc(g, io_dtype, q, k, v, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
+  } else {
+    auto kern = window_attn_bwd_kernel<T, D>;
+    const size_t smem = BwdSmem<D>::kBytes;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long ctas = (long long)((g.L + kBR - 1) / kBR) * g.n_windows * g.B * g.H;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    kern<<<(unsigned)ctas, 256, smem, st>>>(g, q, k, v, mask, kbar, beta, bias, bias_sh, reinterpret_cast<const T*>(out),
+                                            reinterpret_cast<const T*>(dout), dq, dk, dv, dkbar, dbeta, dbias);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess || g.n_chunks == 0) return e;
   auto kern2 = chunk_stats_bwd_kernel<T, D>;
   const size_t smem2 = 2 * (size_t)D * D * sizeof(float);
@@ -620,7 +625,7 @@ cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
                                 float* dbeta, float* dbias, float* rows, cudaStream_t st) {
 #define EVA_BWD_CASE(DT, TY, DD) \
-  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, st);
+  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, io_dtype, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, st);
   switch (io_dtype * 256 + g.D) {
     EVA_BWD_CASE(EVA_F32, float, 16) EVA_BWD_CASE(EVA_F32, float, 32) EVA_BWD_CASE(EVA_F32, float, 64) EVA_BWD_CASE(EVA_F32, float, 128)
     EVA_BWD_CASE(EVA_F16, __half, 16) EVA_BWD_CASE(EVA_F16, __half, 32) EVA_BWD_CASE(EVA_F16, __half, 64) EVA_BWD_CASE(EVA_F16, __half, 128)

@@ -49,6 +49,12 @@ cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
                                 float* dbeta, float* dbias, float* rows, cudaStream_t st);
 
+// tcgen05 window-attention backward (eva_bwd_sm100.cu): head_dim 64, 16-bit I/O, halo-free windows of <= 64 tokens, <= 64 chunks
+bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask);
+cudaError_t launch_window_bwd_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
+                                 const float* beta, const float* bias, long long bias_sh, const void* out, const void* dout,
+                                 float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias, cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

@@ -116,6 +116,47 @@ def test_backward_kernels_equal_autograd_through_the_recomputation(seq_shape, wi
         assert rel_l2(a_.cpu(), b_.cpu()) < tol, (n_, rel_l2(a_.cpu(), b_.cpu()))
 
 
+@pytest.mark.parametrize('seq_shape,window,chunk,dtype,with_bias,B', [
+    ((28, 28), 7, 4, torch.float16, True, 2), ((14, 14), 7, 2, torch.bfloat16, True, 3), ((28, 28), 7, 4, torch.float16, False, 40),
+    ((96,), 16, 8, torch.float16, True, 2), ((56, 56), 7, 8, torch.bfloat16, False, 2), ((16, 16), 8, 2, torch.float16, True, 2)])
+def test_tcgen05_backward_kernel_matches_the_cuda_core_kernel(seq_shape, window, chunk, dtype, with_bias, B):
+    """eva_bwd_sm100.cu (tensor cores, 16-bit P / dS tiles) against eva_backward.cu (float32) on identical 16-bit inputs, and the
+    dispatch counter proves which one ran."""
+    from efficient_attention import _abi, _recompute
+    from test_gpu_parity import _rand_ada
+    dev = _dev()
+    lib = _abi.load()
+    H, d = 3, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + window + chunk)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dev, dtype)
+    L = window * window if len(seq_shape) == 2 else window
+    bias = (0.5 * torch.randn(H, L, L, generator=g)).to(dev) if with_bias else None
+    ada = {k_: v_.to(dev) for k_, v_ in _rand_ada(d, g).items()}
+    noise = torch.randn(B, H, _recompute.num_chunks_of(seq_shape, chunk), d, generator=g).to(dev)
+    geometry = dict(seq_shape=seq_shape, window=window, ext=0, chunk=chunk, chunk_ext=0)
+    names = ('wq', 'bq', 'gq', 'betq', 'wk', 'bk', 'gk', 'betk')
+    w = torch.randn(B, N, H * d, generator=g).to(dev)
+
+    def run(mode):
+        lib.eva_debug_set_bwd_tc(mode)
+        try:
+            before = lib.eva_debug_bwd_tc_count()
+            x = qkv.clone().requires_grad_(True)
+            b_ = bias.clone().requires_grad_(True) if with_bias else None
+            prm = [ada[n_].clone().requires_grad_(True) for n_ in names]
+            out = _recompute.eva_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, mu_coeff=0.5, params=prm, noise=noise, bias=b_)
+            (out.float() * w).sum().backward()
+            assert lib.eva_debug_bwd_tc_count() - before == mode
+            return [x.grad.float()] + ([b_.grad] if with_bias else []) + [p_.grad for p_ in prm]
+        finally:
+            lib.eva_debug_set_bwd_tc(-1)
+    got, want = run(1), run(0)
+    for n_, a_, b_ in zip(('qkv',) + (('bias',) if with_bias else ()) + names, got, want):
+        assert torch.isfinite(a_).all(), n_
+        assert rel_l2(a_.cpu(), b_.cpu()) < (3e-3 if dtype == torch.float16 else 1.2e-2), (n_, rel_l2(a_.cpu(), b_.cpu()))
+
+
 def _grads_of(module, cfg, a, dev, dtype):
     """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
     x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
