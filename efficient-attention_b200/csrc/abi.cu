@@ -270,6 +270,15 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   const long long tens = (long long)g.B * g.N * g.H * g.D;
   float* kbar = chunk_rows;
   float* beta = chunk_rows + slot;
+  // accumulation targets start from zero: d k_bar | d beta, the bias gradient, and -- unless the tcgen05 window kernel runs, which
+  // writes every dq / dk / dv row exactly once before the chunk-statistics kernel adds to it -- dq | dk | dv
+  cudaError_t ez = cudaSuccess;
+  if (g.n_chunks > 0) ez = cudaMemsetAsync(chunk_rows + 2 * slot, 0, 2 * (size_t)slot * sizeof(float), st);
+  if (ez == cudaSuccess && grad_bias)
+    ez = cudaMemsetAsync(grad_bias, 0, (size_t)(bias_stride_h ? g.H : 1) * g.L * g.J * sizeof(float), st);
+  if (ez == cudaSuccess && !eva::window_bwd_tc_supported(g, gin->io_dtype, pad_mask))
+    ez = cudaMemsetAsync(grad_qkv, 0, 3 * (size_t)tens * sizeof(float), st);
+  if (ez != cudaSuccess) return cuda_fail(ez, "eva_backward(memset)");
   if (g.n_chunks > 0) {
     const cudaError_t e0 = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, kbar, beta, st);
     if (e0 != cudaSuccess) return cuda_fail(e0, "eva_backward(chunk_stats)");

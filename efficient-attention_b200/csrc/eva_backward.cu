@@ -437,6 +437,7 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
     float sq[DPL], sk[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) sq[i] = sk[i] = 0.f;
+#pragma unroll 4
     for (int s = 0; s < g.Jc; ++s) {
       const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
       if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;
@@ -489,6 +490,7 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
     float m = kNegInf, l = 0.f, acc[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+#pragma unroll 4
     for (int s = 0; s < g.Jc; ++s) {
       const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
       const bool dead = tok < 0 || (mask && mask[(long long)b * g.N + tok]);
@@ -524,6 +526,7 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
     float dom[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) dom[i] = 0.f;
+#pragma unroll 4
     for (int s = 0; s < g.Jc; ++s) {
       const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
       if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;     // constant logit, zero value: no gradient
@@ -574,6 +577,7 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
       rows[4 * slot + o] = nk[i];   rows[5 * slot + o] = nq[i];
       rows[6 * slot + o] = dok[i];  rows[7 * slot + o] = doq[i];
     }
+#pragma unroll 4
     for (int s = 0; s < g.Jc; ++s) {
       const int tok = group_token(g, c, s, g.chunk, g.chunk_ext);
       if (tok < 0 || (mask && mask[(long long)b * g.N + tok])) continue;

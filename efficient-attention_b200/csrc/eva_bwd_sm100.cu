@@ -31,6 +31,7 @@ namespace bwdtc {
 using fused::IoFmt;
 using fused::tile_off;
 using fused::tmem_ld_cols;
+using fused::ex2;
 
 constexpr int kThreads = 256;
 constexpr int kQ = 0, kG = 8192, kKx = 16384, kVx = 32768, kdS = 49152, kdSt = 65536, kPt = 81920, kMisc = 98304;
@@ -161,12 +162,12 @@ eva_window_bwd_tc_kernel(const Params p) {
       }
       float lloc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) lloc += exp2f(s[j] - mloc);
+      for (int j = 0; j < 64; ++j) lloc += ex2(s[j] - mloc);
       if (act) { pm[hf * 64 + r] = mloc; pl[hf * 64 + r] = lloc; }
       __syncthreads();
       const float m0 = pm[r], m1 = pm[64 + r];
       const float mm = fmaxf(m0, m1);
-      const float linv = 1.0f / (pl[r] * exp2f(m0 - mm) + pl[64 + r] * exp2f(m1 - mm));
+      const float linv = 1.0f / (pl[r] * ex2(m0 - mm) + pl[64 + r] * ex2(m1 - mm));
       const float dl = delta[r];
       float* dbrow = (p.dbias && !hf && row_live) ? p.dbias + (long long)h * p.bias_sh + (long long)r * g.J : nullptr;
 #pragma unroll
@@ -182,7 +183,7 @@ eva_window_bwd_tc_kernel(const Params p) {
           for (int u = 0; u < 2; ++u) {
             const int j = 16 * blk + jj + u;
             const bool live = row_live && j < ncol;
-            pv[u] = live ? exp2f(s[j] - mm) * linv : 0.f;
+            pv[u] = live ? ex2(s[j] - mm) * linv : 0.f;
             ds[u] = pv[u] * (dp[jj + u] - dl);
             if (dbrow && live) atomicAdd(dbrow + j, ds[u]);
             if (act) {

@@ -236,9 +236,9 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     bias = _f32(bias)
     out = out.detach().contiguous()
     grad_out = grad_out.detach().to(out.dtype).contiguous()
-    grad_qkv = torch.zeros(3, B, N, H, D, dtype=torch.float32, device=q.device)
-    rows = torch.zeros(12, B, H, C, D, dtype=torch.float32, device=q.device) if C > 0 else None
-    grad_bias = torch.zeros_like(bias) if (want_bias_grad and bias is not None) else None
+    grad_qkv = torch.empty(3, B, N, H, D, dtype=torch.float32, device=q.device)
+    rows = torch.empty(12, B, H, C, D, dtype=torch.float32, device=q.device) if C > 0 else None
+    grad_bias = torch.empty_like(bias) if (want_bias_grad and bias is not None) else None
     ada_s, keep = ada if ada is not None else (None, None)
     bias_sh = 0 if bias is None or bias.shape[0] == 1 else bias.shape[1] * bias.shape[2]
     with torch.cuda.device(q.device):

@@ -127,6 +127,27 @@ def eva_core_torch(q, k, v, *, seq_shape, window, ext, chunk, chunk_ext, wq, bq,
     return out.reshape(B, N, H * d)
 
 
+def _cuda_backward(saved, meta, need, grad_out):
+    """`eva_backward` on the saved (q, k, v, noise, bias, 8 parameters, out); need = needs_input_grad of (bias, 8 parameters).
+    Returns (float32 [3, B, N, H, D] = dq | dk | dv, (d bias, 8 parameter gradients))."""
+    q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = saved
+    geom = _abi.eva_geometry(q, **meta['geometry'])
+    ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
+    gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
+                                          want_bias_grad=bias is not None and need[0])
+    B, H, D = q.shape[0], q.shape[2], q.shape[-1]
+    # per-chunk rows, grouped per (batch, head): the reductions over ~B*H*C rows run as B*H small GEMMs and one sum
+    dyk, dyq, mk, mq, nk, nq, dok, doq = (rows[i].reshape(B * H, -1, D) for i in range(4, 12))
+    like = lambda g_, src: g_.to(src.dtype)
+    res = [like(gbias, bias) if gbias is not None else None]
+    makers = ((wq, lambda: torch.bmm(dyq.transpose(1, 2), mq).sum(0)), (bq, lambda: dyq.sum((0, 1))), (gq, lambda: (doq * nq).sum((0, 1))),
+              (betq, lambda: doq.sum((0, 1))), (wk, lambda: torch.bmm(dyk.transpose(1, 2), mk).sum(0)), (bk, lambda: dyk.sum((0, 1))),
+              (gk, lambda: (dok * nk).sum((0, 1))), (betk, lambda: dok.sum((0, 1))))
+    for i, (src, make) in enumerate(makers):
+        res.append(like(make(), src) if (src is not None and need[1 + i]) else None)
+    return gqkv, tuple(res)
+
+
 class EvaCoreFn(torch.autograd.Function):
     """forward: `eva_forward` of libeva_sm100; backward: `eva_backward` (or autograd through `eva_core_torch`, see the module docstring)."""
 
@@ -142,23 +163,11 @@ class EvaCoreFn(torch.autograd.Function):
 
     @staticmethod
     def _backward_cuda(ctx, grad_out):
-        q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = ctx.saved_tensors
-        meta = ctx.meta
+        q, k, v = ctx.saved_tensors[:3]
         need = ctx.needs_input_grad
-        geom = _abi.eva_geometry(q, **meta['geometry'])
-        ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
-        gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
-                                              want_bias_grad=bias is not None and need[4])
-        D = q.shape[-1]
-        dyk, dyq, mk, mq, nk, nq, dok, doq = (rows[i].reshape(-1, D) for i in range(4, 12))
-        like = lambda g_, src: None if src is None else g_.to(src.dtype)
-        res = [gqkv[0].to(q.dtype) if need[0] else None, gqkv[1].to(k.dtype) if need[1] else None,
-               gqkv[2].to(v.dtype) if need[2] else None, None, like(gbias, bias) if gbias is not None else None]
-        for i, (src, make) in enumerate(((wq, lambda: dyq.t() @ mq), (bq, lambda: dyq.sum(0)), (gq, lambda: (doq * nq).sum(0)),
-                                         (betq, lambda: doq.sum(0)), (wk, lambda: dyk.t() @ mk), (bk, lambda: dyk.sum(0)),
-                                         (gk, lambda: (dok * nk).sum(0)), (betk, lambda: dok.sum(0)))):
-            res.append(like(make(), src) if (src is not None and need[5 + i]) else None)
-        return tuple(res) + (None,)
+        gqkv, rest = _cuda_backward(ctx.saved_tensors, ctx.meta, need[4:13], grad_out)
+        return (gqkv[0].to(q.dtype) if need[0] else None, gqkv[1].to(k.dtype) if need[1] else None,
+                gqkv[2].to(v.dtype) if need[2] else None, None) + rest + (None,)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -189,9 +198,40 @@ class EvaCoreFn(torch.autograd.Function):
         return tuple(result) + (None,)
 
 
-def eva_core(q, k, v, *, geometry, mu_coeff, params, pad_mask=None, noise=None, bias=None):
-    """Kernel forward + recomputation backward.  `params` = (wq, bq, gq, betq, wk, bk, gk, betk), entries may be None."""
+class EvaCorePackedFn(torch.autograd.Function):
+    """EvaCoreFn for q, k, v that are the three slices of one packed [B, N, 3, H, d] projection output (abstract_attention.py:72-78):
+    the gradient goes back as ONE tensor in that layout (a single convert-and-interleave pass over dq | dk | dv) instead of three
+    casts followed by autograd's three zero-filled `select` gradients and their sums."""
+
+    @staticmethod
+    def forward(ctx, packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, meta):
+        q, k, v = packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]
+        geom = _abi.eva_geometry(q, **meta['geometry'])
+        ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
+        out = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise, bias=None if bias is None else bias.detach())
+        ctx.meta = meta
+        ctx.save_for_backward(packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        packed = ctx.saved_tensors[0]
+        need = ctx.needs_input_grad
+        saved = (packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]) + tuple(ctx.saved_tensors[1:])
+        gqkv, rest = _cuda_backward(saved, ctx.meta, need[2:11], grad_out)
+        gp = None
+        if need[0]:
+            gp = torch.empty(packed.shape, dtype=packed.dtype, device=packed.device)
+            gp.copy_(gqkv.permute(1, 2, 0, 3, 4))
+        return (gp, None) + rest + (None,)
+
+
+def eva_core(q, k, v, *, geometry, mu_coeff, params, pad_mask=None, noise=None, bias=None, packed=None):
+    """Kernel forward + backward.  `params` = (wq, bq, gq, betq, wk, bk, gk, betk), entries may be None.  `packed`: the contiguous
+    [B, N, 3, H, d] tensor q, k, v are slices of, when there is one."""
     meta = dict(geometry=geometry, mu_coeff=mu_coeff, pad_mask=pad_mask)
+    if packed is not None and _BACKWARD_IMPL == 'cuda' and packed.dim() == 5 and packed.shape[2] == 3 and packed.is_contiguous():
+        return EvaCorePackedFn.apply(packed, noise, bias, *params, meta)
     return EvaCoreFn.apply(q, k, v, noise, bias, *params, meta)
 
 

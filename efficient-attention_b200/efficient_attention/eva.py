@@ -129,7 +129,7 @@ class EVA(LocalAttention):
         if _recompute.needs_grad(packed, *params, *self._bias_sources()):
             # training (vit/engine.py:47-62): kernel forward, backward by recomputation (see _recompute.py)
             out = _recompute.eva_core(q, k, v, geometry=geometry, mu_coeff=0.5, params=params, pad_mask=key_padding_mask,
-                                      noise=noise, bias=self._local_bias(differentiable=True))
+                                      noise=noise, bias=self._local_bias(differentiable=True), packed=packed)
         else:
             out = _abi.eva_forward(q, k, v, geom, self._adaptive(), pad_mask=key_padding_mask, noise=noise,
                                    bias=self._local_bias())

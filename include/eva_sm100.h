@@ -120,9 +120,10 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
  * local_attention.py:134-182 with autograd).  float32 CUDA-core kernels for every geometry the forward accepts; the
  * probabilities are recomputed from q, k, v (nothing but the forward OUTPUT is kept between the two calls).
  *   out, grad_out  io_dtype [batch, tokens, heads*head_dim] contiguous: the forward result and the gradient arriving at it
- *   grad_qkv       float32 [3, batch, tokens, heads, head_dim] = dq | dk | dv, ZEROED by the caller (accumulated with atomics)
- *   grad_bias      float32, the shape of `bias`, zeroed by the caller; NULL: not wanted
- *   chunk_rows     float32 [12, batch, heads, C_n, head_dim], zeroed by the caller; NULL iff g->chunk == 0.  Slots on return:
+ *   grad_qkv       float32 [3, batch, tokens, heads, head_dim] = dq | dk | dv (need not be initialised: the call zeroes what it
+ *                  accumulates into)
+ *   grad_bias      float32, the shape of `bias`; NULL: not wanted
+ *   chunk_rows     float32 [12, batch, heads, C_n, head_dim]; NULL iff g->chunk == 0.  Slots on return:
  *                  0 k_bar | 1 beta (recomputed) | 2 d k_bar | 3 d beta | 4 dy_k | 5 dy_q (gradients at the adaptive Linear outputs) |
  *                  6 mean_k | 7 mean_q (the Linear inputs) | 8 n_k | 9 n_q (LayerNorm-normalised rows) | 10 dout_k | 11 dout_q
  *                  (gradients at the LayerNorm outputs).  The PARAMETER gradients are plain reductions over the chunk rows, left to
