@@ -235,6 +235,33 @@ def eva_core(q, k, v, *, geometry, mu_coeff, params, pad_mask=None, noise=None, 
     return EvaCoreFn.apply(q, k, v, noise, bias, *params, meta)
 
 
+class WindowCoreFn(torch.autograd.Function):
+    """Chunk-less window attention (local_attention.py:134-182; the dense softmax baseline abstract_attention.py:115-133 is the
+    one-window case): forward `eva_window_attention`, backward `eva_backward` of libeva_sm100."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bias, meta):
+        geom = _abi.eva_geometry(q, **meta['geometry'])
+        out = _abi.eva_window_attention(q, k, v, geom, pad_mask=meta['pad_mask'], bias=None if bias is None else bias.detach())
+        ctx.meta = meta
+        ctx.save_for_backward(q, k, v, bias, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, v, bias, out = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        geom = _abi.eva_geometry(q, **ctx.meta['geometry'])
+        gqkv, gbias, _ = _abi.eva_backward(q, k, v, geom, None, out, grad_out, pad_mask=ctx.meta['pad_mask'], bias=bias,
+                                           want_bias_grad=bias is not None and need[3])
+        return (gqkv[0].to(q.dtype) if need[0] else None, gqkv[1].to(k.dtype) if need[1] else None,
+                gqkv[2].to(v.dtype) if need[2] else None, None if gbias is None else gbias.to(bias.dtype), None)
+
+
+def window_core(q, k, v, *, geometry, pad_mask=None, bias=None):
+    return WindowCoreFn.apply(q, k, v, bias, dict(geometry=geometry, pad_mask=pad_mask))
+
+
 def needs_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 

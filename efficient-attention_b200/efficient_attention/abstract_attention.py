@@ -6,8 +6,7 @@ import math
 import torch
 import torch.nn as nn
 
-from . import _abi
-from .attn_utils import attach_forward_only
+from . import _abi, _recompute
 
 
 class MultiheadAttention(nn.Module):
@@ -58,9 +57,10 @@ class MultiheadAttention(nn.Module):
         if self.attn_drop.p > 0 and self.training:
             raise NotImplementedError('attention-probability dropout is not built into the sm_100a kernels')
         B, N, H, D = q.shape
-        geom = _abi.eva_geometry(q, seq_shape=(N,), window=N, ext=0, chunk=0, chunk_ext=0, mask_is_neg_inf=True)
-        out = _abi.eva_window_attention(q, k, v, geom, pad_mask=key_padding_mask)
-        return attach_forward_only(out, packed)
+        geometry = dict(seq_shape=(N,), window=N, ext=0, chunk=0, chunk_ext=0, mask_is_neg_inf=True)
+        if _recompute.needs_grad(packed):
+            return _recompute.window_core(q, k, v, geometry=geometry, pad_mask=key_padding_mask)
+        return _abi.eva_window_attention(q, k, v, _abi.eva_geometry(q, **geometry), pad_mask=key_padding_mask)
 
     def forward(self, x, key_padding_mask=None):
         B, *seq_shape, C = x.shape

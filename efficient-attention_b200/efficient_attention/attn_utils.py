@@ -29,26 +29,6 @@ class FlattenTranspose(nn.Module):
         return x.flatten(2).permute(0, 2, 1)
 
 
-class _ForwardOnly(torch.autograd.Function):
-    """Marks a kernel output as depending on its inputs; backward is a later round."""
-
-    @staticmethod
-    def forward(ctx, out, *deps):
-        return out.view_as(out)
-
-    @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(
-            'efficient_attention (B200 build): the attention core is forward-only in this release; '
-            'wrap evaluation in torch.no_grad() or detach the inputs.')
-
-
-def attach_forward_only(out, *deps):
-    if torch.is_grad_enabled() and any(d is not None and d.requires_grad for d in deps):
-        return _ForwardOnly.apply(out, *[d for d in deps if d is not None])
-    return out
-
-
 def t5_bucket_table(n_query, n_key, causal, num_buckets, max_distance):
     """LongTensor [n_query, n_key] of T5 relative-position buckets for rel = key - query
     (reference eva.py:31-55 / causal_eva.py:62-86).  float32 log like the reference."""

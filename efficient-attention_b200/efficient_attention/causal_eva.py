@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import _abi, _recompute
-from .attn_utils import attach_forward_only, pad_to_multiple, t5_bucket_table
+from .attn_utils import pad_to_multiple, t5_bucket_table
 
 
 class T5RelativePositionBias(nn.Module):

@@ -6,9 +6,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _abi
+from . import _abi, _recompute
 from .abstract_attention import MultiheadAttention
-from .attn_utils import attach_forward_only
 
 
 class LocalAttention(MultiheadAttention):
@@ -71,9 +70,12 @@ class LocalAttention(MultiheadAttention):
             else:
                 mask = key_padding_mask
             shape = (N + rem,)
-        geom = _abi.eva_geometry(q, seq_shape=shape, window=w, ext=e, chunk=0, chunk_ext=0)
-        out = _abi.eva_window_attention(q, k, v, geom, pad_mask=mask, bias=self._window_bias())
-        return attach_forward_only(out[:, :N], packed)
+        geometry = dict(seq_shape=shape, window=w, ext=e, chunk=0, chunk_ext=0)
+        if _recompute.needs_grad(packed, *((self.local_relative_position_bias_table,) if self.use_rpe else ())):
+            out = _recompute.window_core(q, k, v, geometry=geometry, pad_mask=mask, bias=self._window_bias(differentiable=True))
+        else:
+            out = _abi.eva_window_attention(q, k, v, _abi.eva_geometry(q, **geometry), pad_mask=mask, bias=self._window_bias())
+        return out[:, :N]
 
     @staticmethod
     def add_attn_specific_args(parent_parser, struct_name="attn_args", prefix=""):

@@ -164,6 +164,8 @@ def _grads_of(module, cfg, a, dev, dtype):
     noise = a['noise'].to(device=dev, dtype=torch.float32) if a['noise'] is not None else None
     if cfg['kind'] == 'causal_eva':
         y = module(x, x, x, key_padding_mask=mask, noise=noise)[0]
+    elif cfg['kind'] in ('local', 'softmax'):
+        y = module(x, mask)
     else:
         y = module(x, mask, noise=noise)
     w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(device=dev, dtype=y.dtype)
@@ -179,6 +181,10 @@ def _oracle_grads(cfg, sd, a):
         y = O.causal_eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
     elif cfg['kind'] == 'lara':
         y = O.lara_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
+    elif cfg['kind'] == 'local':
+        y = O.local_forward(sd64, cfg, x, pad_mask=a['mask'])
+    elif cfg['kind'] == 'softmax':
+        y = O.softmax_forward(sd64, cfg, x, pad_mask=a['mask'])
     else:
         y = O.eva_forward(sd64, cfg, x, pad_mask=a['mask'], noise=noise)
     w = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).double()
@@ -188,7 +194,8 @@ def _oracle_grads(cfg, sd, a):
 
 @pytest.mark.parametrize('name', ['eva_2d_train', 'eva_1d_train', 'eva_c1_train', 'eva_c3_train', 'causal_numchunks_train',
                                   'lara_c4_train', 'lara_2d_train_anti', 'lara_2d_train_multi', 'lara_1d_even', 'lara_1d_uneven_mask',
-                                  'lara_2d_dense', 'lara_2d_dense_vmixed', 'lara_2d_vmixed_biased'])
+                                  'lara_2d_dense', 'lara_2d_dense_vmixed', 'lara_2d_vmixed_biased', 'local_1d_mask', 'local_2d_rpe',
+                                  'softmax_mask'])
 def test_module_gradients_match_oracle_autograd_fp32(name):
     cfg, sd, a = load_golden(name, dtype=torch.float32)
     m = build_module(cfg)
