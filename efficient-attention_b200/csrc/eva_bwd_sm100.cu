@@ -34,9 +34,10 @@ using fused::tmem_ld_cols;
 using fused::ex2;
 
 constexpr int kThreads = 256;
-constexpr int kQ = 0, kG = 8192, kKx = 16384, kVx = 32768, kdS = 49152, kdSt = 65536, kPt = 81920, kMisc = 98304;
+constexpr int kQ = 0, kG = 8192, kKx = 16384, kVx = 32768, kdS = 49152, kP = 65536, kMisc = 81920;
 constexpr int kDelta = kMisc, kPm = kDelta + 256, kPl = kPm + 512, kBar = kPl + 512, kSlot = kBar + 16;
-constexpr int kSmemBytes = kSlot + 16 + 1024;   // + slack to align the tiles to 1024 B
+constexpr int kBias = kSlot + 16;                // [L][J] bias rows of the CTA's head, pre-multiplied by log2(e)
+constexpr int kSmemFixed = kBias + 1024;         // + slack to align the tiles to 1024 B; + L * J floats when there is a bias
 constexpr uint32_t kTmemCols = 256;
 
 struct Params {
@@ -47,13 +48,14 @@ struct Params {
   const void* out; const void* dout;
   float* dq; float* dk; float* dv; float* dkbar; float* dbeta; float* dbias;
   int total;
+  int trace;   // EVA_SM100_TRACE=1: CTA 0 prints the phase clocks of its second window
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 eva_window_bwd_tc_kernel(const Params p) {
   extern __shared__ uint8_t raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo& g = p.g;
   const int L = g.L, C = g.n_chunks;
@@ -63,6 +65,12 @@ eva_window_bwd_tc_kernel(const Params p) {
   float* delta = reinterpret_cast<float*>(sm + kDelta);
   float* pm = reinterpret_cast<float*>(sm + kPm);     // [2][64] row maxima of the two column halves (log2 domain)
   float* pl = reinterpret_cast<float*>(sm + kPl);     // [2][64] row sums
+  float* sbias = reinterpret_cast<float*>(sm + kBias);
+  // CTA -> one head (its bias table stays in shared memory), windows of that head strided over the CTAs of the head
+  const int h = blockIdx.x % g.H, cta_h = blockIdx.x / g.H, ctas_h = gridDim.x / g.H;
+  const int per_head = g.B * g.n_windows;
+  if (p.bias)
+    for (int i = tid; i < L * L; i += kThreads) sbias[i] = __ldg(p.bias + (long long)h * p.bias_sh + i) * kLog2e;
 
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(slot), kTmemCols);
   if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
@@ -74,7 +82,7 @@ eva_window_bwd_tc_kernel(const Params p) {
   constexpr uint32_t fmt = IoFmt<T>::kUmma;
   constexpr uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 64, 128);
   constexpr uint32_t id_dq = ptx::umma_idesc(fmt, fmt, 0, 1, 64, 64);
-  constexpr uint32_t id_dk = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+  constexpr uint32_t id_dk = ptx::umma_idesc(fmt, fmt, 1, 1, 128, 64);   // A = dS / P read MN-major (keys contiguous)
   const float scale = 0.125f, scale2 = 0.125f * kLog2e;
 
   const int qr = warp & 3, hf = warp >> 2;
@@ -82,9 +90,13 @@ eva_window_bwd_tc_kernel(const Params p) {
   const int r = 16 * qr + (lane & 15);            // row of the M = 64 accumulators this thread reads (lanes 0-15)
   const bool act = lane < 16;
 
-  for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
-    const int win = item % g.n_windows, bh = item / g.n_windows;
-    const int b = bh / g.H, h = bh % g.H;
+  long long tk[8];
+  int it = 0;
+#define EVA_MARK(i) if (p.trace && it == 1) tk[i] = clock64();
+  for (int item = cta_h; item < per_head; item += ctas_h, ++it) {
+    const int win = item % g.n_windows, b = item / g.n_windows;
+    const int bh = b * g.H + h;
+    EVA_MARK(0)
     // ---------------------------------------------- loads ------------------------------------------------------------
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
@@ -129,6 +141,7 @@ eva_window_bwd_tc_kernel(const Params p) {
       *reinterpret_cast<uint4*>(sm + kKx + offc) = ck;
       *reinterpret_cast<uint4*>(sm + kVx + offc) = cv;
     }
+    EVA_MARK(1)
     ptx::fence_proxy_async_smem();
     __syncthreads();
     const uint64_t dQd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kQ)), dGd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kG));
@@ -143,6 +156,7 @@ eva_window_bwd_tc_kernel(const Params p) {
     }
     ptx::mbar_wait(bar, 0);
     ptx::tc_fence_after();
+    EVA_MARK(2)
     // ---------------------------------------------- E 1 --------------------------------------------------------------
     {
       const bool row_live = act && r < L;
@@ -150,24 +164,25 @@ eva_window_bwd_tc_kernel(const Params p) {
       float s[64];
       tmem_ld_cols<64>(trow + 64 * hf, reinterpret_cast<uint32_t*>(s));
       ptx::tmem_ld_wait();
-      const float* brow = (p.bias && !hf && row_live) ? p.bias + (long long)h * p.bias_sh + (long long)r * g.J : nullptr;
+      const float* brow = (p.bias && !hf && row_live) ? sbias + r * L : nullptr;
       float mloc = kNegInf;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         float x = s[j] * scale2;
-        if (brow && j < ncol) x = fmaf(__ldg(brow + j), kLog2e, x);
+        if (brow && j < ncol) x += brow[j];
         x = j < ncol ? x : kNegInf;
         s[j] = x;
         mloc = fmaxf(mloc, x);
       }
       float lloc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) lloc += ex2(s[j] - mloc);
+      for (int j = 0; j < 64; ++j) { s[j] = ex2(s[j] - mloc); lloc += s[j]; }      // s <- exp2(logit - half maximum)
       if (act) { pm[hf * 64 + r] = mloc; pl[hf * 64 + r] = lloc; }
       __syncthreads();
       const float m0 = pm[r], m1 = pm[64 + r];
       const float mm = fmaxf(m0, m1);
       const float linv = 1.0f / (pl[r] * ex2(m0 - mm) + pl[64 + r] * ex2(m1 - mm));
+      const float pscale = row_live ? ex2(mloc - mm) * linv : 0.f;                  // dead rows: P = dS = 0
       const float dl = delta[r];
       float* dbrow = (p.dbias && !hf && row_live) ? p.dbias + (long long)h * p.bias_sh + (long long)r * g.J : nullptr;
 #pragma unroll
@@ -175,48 +190,50 @@ eva_window_bwd_tc_kernel(const Params p) {
         float dp[16];
         ptx::tmem_ld16(trow + 128 + 64 * hf + 16 * blk, reinterpret_cast<uint32_t*>(dp));
         ptx::tmem_ld_wait();
-        uint32_t pk[8];
+        uint32_t pk[8], pp[8];
 #pragma unroll
         for (int jj = 0; jj < 16; jj += 2) {
-          float pv[2], ds[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int j = 16 * blk + jj + u;
-            const bool live = row_live && j < ncol;
-            pv[u] = live ? ex2(s[j] - mm) * linv : 0.f;
-            ds[u] = pv[u] * (dp[jj + u] - dl);
-            if (dbrow && live) atomicAdd(dbrow + j, ds[u]);
-            if (act) {
-              *reinterpret_cast<uint16_t*>(sm + kdSt + tile_off(64 * hf + j, r)) = IoFmt<T>::one(ds[u]);
-              *reinterpret_cast<uint16_t*>(sm + kPt + tile_off(64 * hf + j, r)) = IoFmt<T>::one(pv[u]);
-            }
+          const int j = 16 * blk + jj;
+          const float p0 = s[j] * pscale, p1 = s[j + 1] * pscale;                  // dead columns: s = exp2(-inf) = 0
+          const float d0 = p0 * (dp[jj] - dl), d1 = p1 * (dp[jj + 1] - dl);
+          if (dbrow) {
+            if (j < ncol) atomicAdd(dbrow + j, d0);
+            if (j + 1 < ncol) atomicAdd(dbrow + j + 1, d1);
           }
-          pk[jj >> 1] = IoFmt<T>::pack2(ds[0], ds[1]);
+          pk[jj >> 1] = IoFmt<T>::pack2(d0, d1);
+          pp[jj >> 1] = IoFmt<T>::pack2(p0, p1);
         }
         if (act) {
-          *reinterpret_cast<uint4*>(sm + kdS + hf * 8192 + tile_off(r, 16 * blk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(sm + kdS + hf * 8192 + tile_off(r, 16 * blk + 8)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          const int o0 = hf * 8192 + tile_off(r, 16 * blk), o1 = hf * 8192 + tile_off(r, 16 * blk + 8);
+          *reinterpret_cast<uint4*>(sm + kdS + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(sm + kdS + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(sm + kP + o0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+          *reinterpret_cast<uint4*>(sm + kP + o1) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
         }
       }
     }
+    EVA_MARK(3)
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();
     __syncthreads();
+    EVA_MARK(4)
     if (tid == 0) {
       ptx::tc_fence_after();
-      const uint64_t dSd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kdS)), dStd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kdSt));
-      const uint64_t dPtd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kPt));
+      const uint64_t dSd = ptx::umma_desc_sw128(ptx::smem_u32(sm + kdS));
+      // the same row-major [64 rows][2 x 64 keys] tiles read as A^T: M = 128 keys (two 64-key atoms 8192 B apart), K = rows
+      const uint64_t dStd = ptx::umma_desc_sw128_mn(ptx::smem_u32(sm + kdS), 8192), dPtd = ptx::umma_desc_sw128_mn(ptx::smem_u32(sm + kP), 8192);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
         ptx::umma_ss(tmem, dSd + (uint64_t)((ks >> 2) * (8192 >> 4) + 2 * (ks & 3)), dKd + 128 * ks, id_dq, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 64, dStd + 2 * ks, dQd + 128 * ks, id_dk, ks > 0);
+      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 64, dStd + 128 * ks, dQd + 128 * ks, id_dk, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 128, dPtd + 2 * ks, dGd + 128 * ks, id_dk, ks > 0);
+      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + 128, dPtd + 128 * ks, dGd + 128 * ks, id_dk, ks > 0);
       ptx::umma_commit(bar);
     }
     ptx::mbar_wait(bar, 1);
     ptx::tc_fence_after();
+    EVA_MARK(5)
     // ---------------------------------------------- E 2 --------------------------------------------------------------
     {
       float y[32];
@@ -248,29 +265,41 @@ eva_window_bwd_tc_kernel(const Params p) {
       } else if (key - 64 < C) {
         const long long base = ((long long)bh * C + (key - 64)) * 64 + 32 * hf;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          atomicAdd(p.dkbar + base + i, y[i] * scale);
-          atomicAdd(p.dbeta + base + i, z[i]);
+        for (int i = 0; i < 32; i += 4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dkbar + base + i), "f"(y[i] * scale), "f"(y[i + 1] * scale),
+                       "f"(y[i + 2] * scale), "f"(y[i + 3] * scale) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dbeta + base + i), "f"(z[i]), "f"(z[i + 1]), "f"(z[i + 2]),
+                       "f"(z[i + 3]) : "memory");
         }
       }
     }
+    EVA_MARK(6)
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    EVA_MARK(7)
+    if (p.trace && it == 1 && blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 16))
+      printf("bwd tc trace tid %d: load %lld | sync+mma1 %lld | E1 %lld | sync %lld | mma2 %lld | E2 %lld | sync %lld | total %lld\n", tid,
+             tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], tk[7] - tk[0]);
   }
+#undef EVA_MARK
   if (warp == 0) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
 template <typename T>
 static cudaError_t launch_t(const Params& p, cudaStream_t st) {
   auto kern = eva_window_bwd_tc_kernel<T>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  const int smem = kSmemFixed + (p.bias ? p.g.L * p.g.L * (int)sizeof(float) : 0);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = p.total < 2 * sms ? p.total : 2 * sms;
-  kern<<<grid, kThreads, kSmemBytes, st>>>(p);
+  // a whole number of CTAs per head, two CTAs per SM
+  int per_head = (2 * sms) / p.g.H;
+  if (per_head < 1) per_head = 1;
+  if (per_head > p.g.B * p.g.n_windows) per_head = p.g.B * p.g.n_windows;
+  kern<<<per_head * p.g.H, kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -296,6 +325,8 @@ cudaError_t launch_window_bwd_tc(const Geo& g, int io_dtype, const View& q, cons
   p.out = out; p.dout = dout;
   p.dq = dq; p.dk = dk; p.dv = dv; p.dkbar = dkbar; p.dbeta = dbeta; p.dbias = dbias;
   p.total = g.B * g.H * g.n_windows;
+  static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.trace = trace;
   ++g_bwd_tc_count;
   return io_dtype == EVA_F16 ? bwdtc::launch_t<__half>(p, st) : bwdtc::launch_t<__nv_bfloat16>(p, st);
 }

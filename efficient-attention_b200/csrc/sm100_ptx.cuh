@@ -271,6 +271,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
   return d;
 }
+// MN-major tile wider than one 64-element swizzle atom: [K rows][64 MN elements] blocks, `lbo_bytes` apart along M / N
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next 64-element atom along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-row (K) group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1 };
 // kind::f16 instruction descriptor: fp32 accumulate, M x N tile
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t a_fmt, uint32_t b_fmt, uint32_t a_mn_major,
