@@ -34,7 +34,7 @@ using fused::tmem_ld_cols;
 using fused::ex2;
 
 constexpr int kThreads = 256;
-constexpr int kQ = 0, kG = 8192, kKx = 16384, kVx = 32768, kdS = 49152, kP = 65536, kMisc = 81920;
+constexpr int kQ = 0, kG = 8192, kKx = 16384, kVx = 32768, kdS = 49152, kP = 65536, kO = 81920, kMisc = 90112;
 constexpr int kDelta = kMisc, kPm = kDelta + 256, kPl = kPm + 512, kBar = kPl + 512, kSlot = kBar + 16;
 constexpr int kBias = kSlot + 16;                // [L][J] bias rows of the CTA's head, pre-multiplied by log2(e)
 constexpr int kSmemFixed = kBias + 1024;         // + slack to align the tiles to 1024 B; + L * J floats when there is a bias
@@ -53,7 +53,9 @@ struct Params {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
-eva_window_bwd_tc_kernel(const Params p) {
+eva_window_bwd_tc_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_constant__ CUtensorMap t_k,
+                         const __grid_constant__ CUtensorMap t_v, const __grid_constant__ CUtensorMap t_g,
+                         const __grid_constant__ CUtensorMap t_o, const Params p) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -61,7 +63,7 @@ eva_window_bwd_tc_kernel(const Params p) {
   const int L = g.L, C = g.n_chunks;
   const long long HD = (long long)g.H * 64;
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + kSlot);
-  const uint32_t bar = ptx::smem_u32(sm + kBar);
+  const uint32_t bar = ptx::smem_u32(sm + kBar), bar_in = bar + 8;
   float* delta = reinterpret_cast<float*>(sm + kDelta);
   float* pm = reinterpret_cast<float*>(sm + kPm);     // [2][64] row maxima of the two column halves (log2 domain)
   float* pl = reinterpret_cast<float*>(sm + kPl);     // [2][64] row sums
@@ -73,7 +75,20 @@ eva_window_bwd_tc_kernel(const Params p) {
     for (int i = tid; i < L * L; i += kThreads) sbias[i] = __ldg(p.bias + (long long)h * p.bias_sh + i) * kLog2e;
 
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(slot), kTmemCols);
-  if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::mbar_init(bar_in, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&t_q); ptx::prefetch_tmap(&t_k); ptx::prefetch_tmap(&t_v); ptx::prefetch_tmap(&t_g); ptx::prefetch_tmap(&t_o);
+  }
+  // rows L .. 63 of the row tiles are never written by the boxes: zero once
+  for (int i = tid; i < (64 - L) * 8; i += kThreads) {
+    const int off = tile_off(L + (i >> 3), 8 * (i & 7));
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sm + kQ + off) = z;  *reinterpret_cast<uint4*>(sm + kG + off) = z;
+    *reinterpret_cast<uint4*>(sm + kKx + off) = z; *reinterpret_cast<uint4*>(sm + kVx + off) = z;
+    *reinterpret_cast<uint4*>(sm + kO + off) = z;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -90,27 +105,54 @@ eva_window_bwd_tc_kernel(const Params p) {
   const int r = 16 * qr + (lane & 15);            // row of the M = 64 accumulators this thread reads (lanes 0-15)
   const bool act = lane < 16;
 
+  // contiguous runs of windows per CTA: the item's chunk rows (k_bar / beta) are re-staged only when the image changes
+  const int lo = (int)((long long)per_head * cta_h / ctas_h), hi = (int)((long long)per_head * (cta_h + 1) / ctas_h);
+  const int nwx = g.gw / g.window;                                 // windows per grid row (1-D: gw = N)
+  auto issue_loads = [&](int item) {                               // one thread: five boxes of L rows x 128 B
+    const int win = item % g.n_windows, b = item / g.n_windows;
+    const int x0 = (win % nwx) * g.window, y0 = g.dims == 2 ? (win / nwx) * g.window : 0;
+    ptx::mbar_arrive_expect_tx(bar_in, 5u * (uint32_t)L * 128u);
+    ptx::tma_load_5d(ptx::smem_u32(sm + kQ), &t_q, bar_in, 0, h, x0, y0, b);
+    ptx::tma_load_5d(ptx::smem_u32(sm + kKx), &t_k, bar_in, 0, h, x0, y0, b);
+    ptx::tma_load_5d(ptx::smem_u32(sm + kVx), &t_v, bar_in, 0, h, x0, y0, b);
+    ptx::tma_load_5d(ptx::smem_u32(sm + kG), &t_g, bar_in, 0, h, x0, y0, b);
+    ptx::tma_load_5d(ptx::smem_u32(sm + kO), &t_o, bar_in, 0, h, x0, y0, b);
+  };
+  if (tid == 0 && lo < hi) issue_loads(lo);
   long long tk[8];
-  int it = 0;
+  int it = 0, b_staged = -1;
 #define EVA_MARK(i) if (p.trace && it == 1) tk[i] = clock64();
-  for (int item = cta_h; item < per_head; item += ctas_h, ++it) {
+  for (int item = lo; item < hi; ++item, ++it) {
     const int win = item % g.n_windows, b = item / g.n_windows;
     const int bh = b * g.H + h;
     EVA_MARK(0)
     // ---------------------------------------------- loads ------------------------------------------------------------
+    if (b != b_staged) {                        // chunk keys / values of the item: float32 statistics -> the I/O format
+      b_staged = b;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int row = pass * 32 + (tid >> 3), ch = tid & 7;
-      const int tok = row < L ? group_token(g, win, row, g.window, 0) : -1;
-      uint4 zq = make_uint4(0, 0, 0, 0), zk = zq, zv = zq, zg = zq;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int row = pass * 32 + (tid >> 3), ch = tid & 7;
+        uint4 ck = make_uint4(0, 0, 0, 0), cv = ck;
+        if (row < C) {
+          const long long base = ((long long)bh * C + row) * 64 + 8 * ch;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.kbar + base)), a1 = __ldg(reinterpret_cast<const float4*>(p.kbar + base) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + base)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + base) + 1);
+          ck = make_uint4(IoFmt<T>::pack2(a0.x, a0.y), IoFmt<T>::pack2(a0.z, a0.w), IoFmt<T>::pack2(a1.x, a1.y), IoFmt<T>::pack2(a1.z, a1.w));
+          cv = make_uint4(IoFmt<T>::pack2(b0.x, b0.y), IoFmt<T>::pack2(b0.z, b0.w), IoFmt<T>::pack2(b1.x, b1.y), IoFmt<T>::pack2(b1.z, b1.w));
+        }
+        const int offc = tile_off(64 + row, 8 * ch);
+        *reinterpret_cast<uint4*>(sm + kKx + offc) = ck;
+        *reinterpret_cast<uint4*>(sm + kVx + offc) = cv;
+      }
+    }
+    ptx::mbar_wait(bar_in, it & 1);
+    {                                           // delta_r = <grad_out_r, out_r>: four threads per row, two 16-byte pieces each
+      const int row = tid >> 2, c0 = 2 * (tid & 3);
       float part = 0.f;
-      if (tok >= 0) {
-        zq = __ldg(reinterpret_cast<const uint4*>(p.q.row<T>(b, tok, h)) + ch);
-        zk = __ldg(reinterpret_cast<const uint4*>(p.k.row<T>(b, tok, h)) + ch);
-        zv = __ldg(reinterpret_cast<const uint4*>(p.v.row<T>(b, tok, h)) + ch);
-        const long long o = ((long long)b * g.N + tok) * HD + (long long)h * 64;
-        zg = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.dout) + o) + ch);
-        const uint4 zo = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.out) + o) + ch);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int off = tile_off(row, 8 * (c0 + cc));
+        const uint4 zg = *reinterpret_cast<const uint4*>(sm + kG + off), zo = *reinterpret_cast<const uint4*>(sm + kO + off);
         const uint32_t* a = reinterpret_cast<const uint32_t*>(&zg);
         const uint32_t* c = reinterpret_cast<const uint32_t*>(&zo);
 #pragma unroll
@@ -121,25 +163,7 @@ eva_window_bwd_tc_kernel(const Params p) {
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      if (ch == 0) delta[row] = part;
-      const int off = tile_off(row, 8 * ch);
-      *reinterpret_cast<uint4*>(sm + kQ + off) = zq;
-      *reinterpret_cast<uint4*>(sm + kG + off) = zg;
-      *reinterpret_cast<uint4*>(sm + kKx + off) = zk;
-      *reinterpret_cast<uint4*>(sm + kVx + off) = zv;
-      // chunk keys / values of the item: float32 statistics -> the I/O format
-      uint4 ck = make_uint4(0, 0, 0, 0), cv = ck;
-      if (row < C) {
-        const long long base = ((long long)bh * C + row) * 64 + 8 * ch;
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.kbar + base)), a1 = __ldg(reinterpret_cast<const float4*>(p.kbar + base) + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + base)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + base) + 1);
-        ck = make_uint4(IoFmt<T>::pack2(a0.x, a0.y), IoFmt<T>::pack2(a0.z, a0.w), IoFmt<T>::pack2(a1.x, a1.y), IoFmt<T>::pack2(a1.z, a1.w));
-        cv = make_uint4(IoFmt<T>::pack2(b0.x, b0.y), IoFmt<T>::pack2(b0.z, b0.w), IoFmt<T>::pack2(b1.x, b1.y), IoFmt<T>::pack2(b1.z, b1.w));
-      }
-      const int offc = tile_off(64 + row, 8 * ch);
-      *reinterpret_cast<uint4*>(sm + kKx + offc) = ck;
-      *reinterpret_cast<uint4*>(sm + kVx + offc) = cv;
+      if ((tid & 3) == 0) delta[row] = part;
     }
     EVA_MARK(1)
     ptx::fence_proxy_async_smem();
@@ -233,6 +257,7 @@ eva_window_bwd_tc_kernel(const Params p) {
     }
     ptx::mbar_wait(bar, 1);
     ptx::tc_fence_after();
+    if (tid == 0 && item + 1 < hi) issue_loads(item + 1);    // every tile is free again: the next window lands under E 2
     EVA_MARK(5)
     // ---------------------------------------------- E 2 --------------------------------------------------------------
     {
@@ -290,6 +315,17 @@ template <typename T>
 static cudaError_t launch_t(const Params& p, cudaStream_t st) {
   auto kern = eva_window_bwd_tc_kernel<T>;
   const int smem = kSmemFixed + (p.bias ? p.g.L * p.g.L * (int)sizeof(float) : 0);
+  const Geo& g = p.g;
+  const int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
+  const int bw = g.window, bh_ = g.dims == 2 ? g.window : 1;
+  View vo, vg;
+  vo.ptr = p.out;  vo.sb = (long long)g.N * g.H * 64; vo.sn = (long long)g.H * 64; vo.sh = 64;
+  vg = vo; vg.ptr = p.dout;
+  CUtensorMap tq, tk_, tv, tg, to;
+  if (!fused::make_box_map(&tq, p.q, g, io, bw, bh_) || !fused::make_box_map(&tk_, p.k, g, io, bw, bh_) ||
+      !fused::make_box_map(&tv, p.v, g, io, bw, bh_) || !fused::make_box_map(&tg, vg, g, io, bw, bh_) ||
+      !fused::make_box_map(&to, vo, g, io, bw, bh_))
+    return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 148;
@@ -299,7 +335,7 @@ static cudaError_t launch_t(const Params& p, cudaStream_t st) {
   int per_head = (2 * sms) / p.g.H;
   if (per_head < 1) per_head = 1;
   if (per_head > p.g.B * p.g.n_windows) per_head = p.g.B * p.g.n_windows;
-  kern<<<per_head * p.g.H, kThreads, smem, st>>>(p);
+  kern<<<per_head * p.g.H, kThreads, smem, st>>>(tq, tk_, tv, tg, to, p);
   return cudaGetLastError();
 }
 
