@@ -186,7 +186,7 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   char* ws = reinterpret_cast<char*>(workspace);
   float* k_bar = reinterpret_cast<float*>(ws);
   float* beta = reinterpret_cast<float*>(ws + stats);
-  if (eva::cluster_supported(g, gin->io_dtype, vq, vk, vv, pad_mask)) {
+  if (!gin->keep_stats && eva::cluster_supported(g, gin->io_dtype, vq, vk, vv, pad_mask)) {   // the cluster kernel keeps its statistics on chip
     const char* msg = "";
     const cudaError_t e = eva::launch_cluster(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out, ws + 2 * stats, st, &msg);
     if (path_taken) *path_taken = 3;
@@ -197,7 +197,7 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
   if (eva::fused_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, bias, bias_stride_h)) {
     const char* msg = "";
     const cudaError_t e = eva::launch_fused(g, gin->io_dtype, vq, vk, vv, *ada, noise, bias, bias_stride_h, out,
-                                            ws + 2 * stats, st, &msg);
+                                            ws + 2 * stats, st, &msg, gin->keep_stats ? k_bar : nullptr, gin->keep_stats ? beta : nullptr);
     if (path_taken) *path_taken = 1;
     ++g_path_count[1];
     if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(fused): %s: %s", msg, cudaGetErrorString(e));
@@ -251,7 +251,8 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
 
 int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, float* grad_qkv, float* grad_bias, float* chunk_rows, void* stream) {
+                 const void* out, const void* grad_out, const float* k_bar_in, const float* beta_in, float* grad_qkv, float* grad_bias,
+                 float* chunk_rows, void* stream) {
   eva::Geo g{};
   eva::View vq, vk, vv;
   int rc;
@@ -268,8 +269,11 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long slot = (long long)g.B * g.H * g.n_chunks * g.D;
   const long long tens = (long long)g.B * g.N * g.H * g.D;
-  float* kbar = chunk_rows;
-  float* beta = chunk_rows + slot;
+  if ((k_bar_in == nullptr) != (beta_in == nullptr)) return fail(EVA_ERR_INVALID, "k_bar and beta come together");
+  if (((reinterpret_cast<uintptr_t>(k_bar_in) | reinterpret_cast<uintptr_t>(beta_in)) & 15u) != 0)
+    return fail(EVA_ERR_INVALID, "k_bar / beta must be 16-byte aligned");
+  const float* kbar = k_bar_in ? k_bar_in : chunk_rows;
+  const float* beta = beta_in ? beta_in : chunk_rows + slot;
   // accumulation targets start from zero: d k_bar | d beta, the bias gradient, and -- unless the tcgen05 window kernel runs, which
   // writes every dq / dk / dv row exactly once before the chunk-statistics kernel adds to it -- dq | dk | dv
   cudaError_t ez = cudaSuccess;
@@ -279,8 +283,8 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   if (ez == cudaSuccess && !eva::window_bwd_tc_supported(g, gin->io_dtype, pad_mask))
     ez = cudaMemsetAsync(grad_qkv, 0, 3 * (size_t)tens * sizeof(float), st);
   if (ez != cudaSuccess) return cuda_fail(ez, "eva_backward(memset)");
-  if (g.n_chunks > 0) {
-    const cudaError_t e0 = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, kbar, beta, st);
+  if (g.n_chunks > 0 && !k_bar_in) {
+    const cudaError_t e0 = eva::launch_chunk_stats(g, gin->io_dtype, vq, vk, vv, pad_mask, *ada, noise, chunk_rows, chunk_rows + slot, st);
     if (e0 != cudaSuccess) return cuda_fail(e0, "eva_backward(chunk_stats)");
   }
   const cudaError_t e = eva::launch_eva_backward(g, gin->io_dtype, vq, vk, vv, pad_mask, ada, noise, kbar, beta, bias, bias_stride_h, out,

@@ -63,6 +63,8 @@ struct Params {
   int trace;
   int prefetch_rows;             // chunk-rows of the NEXT item to warm in L2 during phase B (tuning knob)
   int prefetch_v;                // warm L2 with v during pass 1
+  float* kbar_out;               // training: k_bar / beta of every item -> float32 [B, H, chunks, 64] (the backward reads them); or NULL
+  float* beta_out;
 };
 
 // G = chunk-rows per pass-1 / pass-2 tile: 1 on the 28-wide grid (112-token rows); 4 on the 14-wide grid, where a 28-token row
@@ -611,6 +613,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         tr(241);
         if (C::chunk_ok(i)) {
           uint8_t* const dst = (ws ? KBt : OMt) + i * 128;
+          if (ws == 1 && p.kbar_out) {
+            float4* kd = reinterpret_cast<float4*>(p.kbar_out + (((long long)b * p.H + h) * CN + (i >> 3) * NCX + (i & 7)) * 64);
+#pragma unroll
+            for (int e4 = 0; e4 < 16; ++e4) kd[e4] = make_float4(y[4 * e4], y[4 * e4 + 1], y[4 * e4 + 2], y[4 * e4 + 3]);
+          }
           if (ws == 0) {
             // q side: omega = mu_coeff (q_bar + k_bar) + noise is applied as  mu_coeff ((q_bar + noise / mu_coeff) + k_bar):
             // the phi-logit MMAs accumulate K_r q'^T and K_r k_bar^T, so the two halves never have to meet in a thread
@@ -741,6 +748,11 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
 #pragma unroll
           for (int cx = 0; cx < NCX; ++cx)
             *reinterpret_cast<uint16_t*>(BTt + tile_off(8 * r + cx, feat)) = IoFmt<T>::one(bt[cx]);
+          if (p.beta_out) {
+            float* bd = p.beta_out + (((long long)b * p.H + h) * CN + r * NCX) * 64 + feat;
+#pragma unroll
+            for (int cx = 0; cx < NCX; ++cx) bd[cx * 64] = bt[cx];
+          }
         }
       }
       ptx::fence_proxy_async_smem();
@@ -944,7 +956,7 @@ struct MapCache {
 template <typename T, int W, int GW, int CH, int NR, int G>
 static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const View& v, const EvaAdaptive& ada,
                             const float* noise, const float* bias, long long bias_sh, void* out, void* workspace,
-                            cudaStream_t st, const char** msg) {
+                            cudaStream_t st, const char** msg, float* kbar_out, float* beta_out) {
   using C = Cfg<W, GW, CH, NR, G>;
   constexpr int io = std::is_same<T, __half>::value ? EVA_F16 : EVA_BF16;
   __half* w16 = reinterpret_cast<__half*>(workspace);
@@ -993,6 +1005,7 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   static const int prefetch_v = env_int("EVA_SM100_PREFETCH_V", 0);         // measured: warming L2 with v during pass 1 costs 5 % (L2 is already full)
   p.prefetch_rows = prefetch_rows;
   p.prefetch_v = prefetch_v;
+  p.kbar_out = kbar_out; p.beta_out = beta_out;
   auto kern = p.trace ? eva_fused_kernel<T, W, GW, CH, NR, G, true> : eva_fused_kernel<T, W, GW, CH, NR, G, false>;
   static bool attr_set[2][kMaxDevices] = {};         // per (instantiation, traced or not, device): the attribute is sticky
   if (dev < 0 || dev >= kMaxDevices || !attr_set[p.trace ? 1 : 0][dev]) {
@@ -1063,14 +1076,14 @@ extern "C" int eva_debug_read_trace(unsigned long long* dst, int which, int n) {
 
 cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                          const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,
-                         void* out, void* workspace, cudaStream_t st, const char** msg) {
+                         void* out, void* workspace, cudaStream_t st, const char** msg, float* kbar_out, float* beta_out) {
   const int var = fused_variant(g);
   if (io_dtype == EVA_F16) {
-    if (var == 1) return fused::launch_t<__half, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
-    return fused::launch_t<__half, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+    if (var == 1) return fused::launch_t<__half, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg, kbar_out, beta_out);
+    return fused::launch_t<__half, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg, kbar_out, beta_out);
   }
-  if (var == 1) return fused::launch_t<__nv_bfloat16, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
-  return fused::launch_t<__nv_bfloat16, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg);
+  if (var == 1) return fused::launch_t<__nv_bfloat16, 7, 28, 4, 7, 1>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg, kbar_out, beta_out);
+  return fused::launch_t<__nv_bfloat16, 7, 14, 2, 7, kG14>(g, q, k, v, ada, noise, bias, bias_sh, out, workspace, st, msg, kbar_out, beta_out);
 }
 
 }  // namespace eva

@@ -23,7 +23,8 @@ size_t fused_workspace_bytes(const Geo& g);
 // returns cudaSuccess, or an error with *msg describing it
 cudaError_t launch_fused(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                          const EvaAdaptive& ada, const float* noise, const float* bias, long long bias_sh,
-                         void* out, void* workspace, cudaStream_t st, const char** msg);
+                         void* out, void* workspace, cudaStream_t st, const char** msg, float* kbar_out = nullptr,
+                         float* beta_out = nullptr);   // kbar_out / beta_out: also leave the chunk statistics in global memory (training)
 
 // Cluster-resident fused path (eva_cluster_sm100.cu): the c3 geometry (28 x 28 tokens, window 7, 4 x 4 chunks), one item per
 // two-CTA cluster with k / v resident in shared memory; same workspace layout as the streamed fused kernel

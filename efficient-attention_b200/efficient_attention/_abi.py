@@ -29,7 +29,7 @@ class EvaHeadsView(ctypes.Structure):
 class EvaGeometry(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         'batch', 'heads', 'tokens', 'head_dim', 'dims', 'grid_h', 'grid_w', 'window', 'ext', 'halo_left_only',
-        'chunk', 'chunk_ext', 'causal', 'mask_queries', 'mask_is_neg_inf', 'io_dtype', 'bias_toeplitz')]
+        'chunk', 'chunk_ext', 'causal', 'mask_queries', 'mask_is_neg_inf', 'io_dtype', 'bias_toeplitz', 'keep_stats')]
 
 
 class EvaAdaptive(ctypes.Structure):
@@ -73,7 +73,7 @@ def load():
         lib.eva_window_attention.argtypes = [G, V, V, V, P, P, P, P, I64, P, P]
         lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
-        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P]
+        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
@@ -184,12 +184,12 @@ def _stream(dev):
 
 
 def eva_geometry(q, *, seq_shape, window, ext, chunk, chunk_ext, causal=False, halo_left_only=False,
-                 mask_queries=False, mask_is_neg_inf=False, bias_toeplitz=False):
+                 mask_queries=False, mask_is_neg_inf=False, bias_toeplitz=False, keep_stats=False):
     B, N, H, D = q.shape
     two_d = len(seq_shape) == 2
     return EvaGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N,
                        window, ext, int(halo_left_only), chunk, chunk_ext, int(causal), int(mask_queries),
-                       int(mask_is_neg_inf), io_dtype(q), int(bias_toeplitz))
+                       int(mask_is_neg_inf), io_dtype(q), int(bias_toeplitz), int(keep_stats))
 
 
 def num_chunks(geom):
@@ -199,8 +199,9 @@ def num_chunks(geom):
     return n
 
 
-def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, return_path=False):
-    """q,k,v: [B,N,H,D] views.  Returns out [B,N,H*D] (same dtype)."""
+def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, return_path=False, return_stats=False):
+    """q,k,v: [B,N,H,D] views.  Returns out [B,N,H*D] (same dtype).  return_stats (geom.keep_stats must be set): also the forward's
+    chunk statistics (k_bar, beta), float32 [B, H, C, D] views of the call's workspace."""
     lib = load()
     _require_cuda(q, k, v, pad_mask, noise, bias)
     B, N, H, D = q.shape
@@ -220,10 +221,17 @@ def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, ret
                              bias_sh, _ptr(out), _ptr(ws), ws.numel(), ctypes.byref(path), _stream(q.device))
     _check(rc, 'eva_forward')
     del keep
+    if return_stats:
+        assert geom.keep_stats, 'return_stats needs a geometry built with keep_stats=True'
+        C = num_chunks(geom)
+        n = B * H * C * D
+        second = (n * 4 + 255) // 256 * 256
+        stats = (ws[:n * 4].view(torch.float32).view(B, H, C, D), ws[second:second + n * 4].view(torch.float32).view(B, H, C, D))
+        return (out, path.value, stats) if return_path else (out, stats)
     return (out, path.value) if return_path else out
 
 
-def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False):
+def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False, stats=None):
     """Gradients of eva_forward / eva_window_attention (`ada` None for chunk-less geometries).
     Returns (grad_qkv float32 [3, B, N, H, D], grad_bias float32 like bias or None, chunk_rows float32 [12, B, H, C, D] or None --
     the slots are listed at eva_backward in include/eva_sm100.h)."""
@@ -231,6 +239,8 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     _require_cuda(q, k, v, out, grad_out, pad_mask, noise, bias)
     B, N, H, D = q.shape
     C = num_chunks(geom) if geom.chunk > 0 else 0
+    k_bar, beta = stats if stats is not None else (None, None)
+    assert k_bar is None or (k_bar.dtype == torch.float32 and k_bar.is_contiguous() and beta.is_contiguous())
     mask = _mask_u8(pad_mask, B, N)
     noise = _f32(noise)
     bias = _f32(bias)
@@ -244,8 +254,8 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     with torch.cuda.device(q.device):
         rc = lib.eva_backward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
                               ctypes.byref(heads_view(v)), _ptr(mask), None if ada_s is None else ctypes.byref(ada_s), _ptr(noise),
-                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(grad_qkv), _ptr(grad_bias), _ptr(rows),
-                              _stream(q.device))
+                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(k_bar), _ptr(beta), _ptr(grad_qkv), _ptr(grad_bias),
+                              _ptr(rows), _stream(q.device))
     _check(rc, 'eva_backward')
     del keep
     return grad_qkv, grad_bias, rows

@@ -130,11 +130,12 @@ def eva_core_torch(q, k, v, *, seq_shape, window, ext, chunk, chunk_ext, wq, bq,
 def _cuda_backward(saved, meta, need, grad_out):
     """`eva_backward` on the saved (q, k, v, noise, bias, 8 parameters, out); need = needs_input_grad of (bias, 8 parameters).
     Returns (float32 [3, B, N, H, D] = dq | dk | dv, (d bias, 8 parameter gradients))."""
-    q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = saved
+    q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = saved[:14]
+    stats = tuple(saved[14:16]) if len(saved) >= 16 else None          # (k_bar, beta) kept by the forward
     geom = _abi.eva_geometry(q, **meta['geometry'])
     ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
     gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
-                                          want_bias_grad=bias is not None and need[0])
+                                          want_bias_grad=bias is not None and need[0], stats=stats)
     B, H, D = q.shape[0], q.shape[2], q.shape[-1]
     # per-chunk rows, grouped per (batch, head): the reductions over ~B*H*C rows run as B*H small GEMMs and one sum
     dyk, dyq, mk, mq, nk, nq, dok, doq = (rows[i].reshape(B * H, -1, D) for i in range(4, 12))
@@ -153,12 +154,12 @@ class EvaCoreFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, meta):
-        geom = _abi.eva_geometry(q, **meta['geometry'])
+        geom = _abi.eva_geometry(q, keep_stats=True, **meta['geometry'])
         ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
-        out = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise,
-                               bias=None if bias is None else bias.detach())
+        out, stats = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise,
+                                      bias=None if bias is None else bias.detach(), return_stats=True)
         ctx.meta = meta
-        ctx.save_for_backward(q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out)
+        ctx.save_for_backward(q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out, *stats)
         return out
 
     @staticmethod
@@ -173,7 +174,7 @@ class EvaCoreFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         if _BACKWARD_IMPL == 'cuda':
             return EvaCoreFn._backward_cuda(ctx, grad_out)
-        saved = ctx.saved_tensors[:13]
+        saved = ctx.saved_tensors[:13]          # the torch route recomputes everything from the inputs
         meta = ctx.meta
         need = ctx.needs_input_grad[:13]
         with torch.enable_grad():
@@ -206,11 +207,12 @@ class EvaCorePackedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, meta):
         q, k, v = packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]
-        geom = _abi.eva_geometry(q, **meta['geometry'])
+        geom = _abi.eva_geometry(q, keep_stats=True, **meta['geometry'])
         ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
-        out = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise, bias=None if bias is None else bias.detach())
+        out, stats = _abi.eva_forward(q, k, v, geom, ada, pad_mask=meta['pad_mask'], noise=noise,
+                                      bias=None if bias is None else bias.detach(), return_stats=True)
         ctx.meta = meta
-        ctx.save_for_backward(packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out)
+        ctx.save_for_backward(packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out, *stats)
         return out
 
     @staticmethod

@@ -74,6 +74,10 @@ typedef struct EvaGeometry {
   int32_t bias_toeplitz;                  /* (ABI v2) 1: the caller guarantees bias[i][j] depends on i - j only
                                              (T5 bucketed bias, eva.py:31-65, causal_eva.py:62-97); a hint that lets a
                                              kernel read one column of the table instead of all of it; 0 is always valid */
+  int32_t keep_stats;                     /* (ABI v3) 1: eva_forward leaves k_bar | beta (float32 [batch, heads, C_n, head_dim] each, the
+                                             second one 256-byte aligned after the first) at the start of its workspace, whatever
+                                             kernel runs -- eva_backward takes them back instead of recomputing them; 0: the
+                                             workspace contents are unspecified on return */
 } EvaGeometry;
 
 /* adaptive_mu_q / adaptive_mu_k = Linear(d,d) [+ LayerNorm(d)] shared by all heads
@@ -128,10 +132,13 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
  *                  6 mean_k | 7 mean_q (the Linear inputs) | 8 n_k | 9 n_q (LayerNorm-normalised rows) | 10 dout_k | 11 dout_q
  *                  (gradients at the LayerNorm outputs).  The PARAMETER gradients are plain reductions over the chunk rows, left to
  *                  the caller's library: dW = dy^T mean, db = sum dy, d gain = sum dout * n, d ln_bias = sum dout.
- *   ada            may be NULL iff g->chunk == 0. */
+ *   ada            may be NULL iff g->chunk == 0.
+ *   k_bar, beta    the forward's chunk statistics (eva_forward with g->keep_stats, or eva_chunk_stats), or both NULL: recomputed
+ *                  into slots 0 / 1. */
 int eva_backward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, float* grad_qkv, float* grad_bias, float* chunk_rows, void* stream);
+                 const void* out, const void* grad_out, const float* k_bar, const float* beta, float* grad_qkv, float* grad_bias,
+                 float* chunk_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LARA (lara.py).  Landmarks are the pooled q/k summaries; samples S = landmarks C, or 2C with

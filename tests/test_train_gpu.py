@@ -157,6 +157,32 @@ def test_tcgen05_backward_kernel_matches_the_cuda_core_kernel(seq_shape, window,
         assert rel_l2(a_.cpu(), b_.cpu()) < (3e-3 if dtype == torch.float16 else 1.2e-2), (n_, rel_l2(a_.cpu(), b_.cpu()))
 
 
+@pytest.mark.parametrize('seq_shape,window,chunk,dtype,expect_path', [
+    ((28, 28), 7, 4, torch.float16, 1), ((14, 14), 7, 2, torch.bfloat16, 1), ((96,), 16, 8, torch.float32, 0)])
+def test_forward_keeps_the_chunk_statistics_for_the_backward(seq_shape, window, chunk, dtype, expect_path):
+    """`EvaGeometry.keep_stats`: k_bar | beta left in the workspace by whichever forward kernel ran equal `eva_chunk_stats`."""
+    from efficient_attention import _abi, _recompute
+    from test_gpu_parity import _rand_ada
+    dev = _dev()
+    B, H, d = 3, 3, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dev, dtype)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    ada_t = {k_: v_.to(dev) for k_, v_ in _rand_ada(d, g).items()}
+    ada = _abi.adaptive(*[ada_t[n] for n in ('wq', 'bq', 'gq', 'betq', 'wk', 'bk', 'gk', 'betk')], mu_coeff=0.5)
+    noise = torch.randn(B, H, _recompute.num_chunks_of(seq_shape, chunk), d, generator=g).to(dev)
+    geometry = dict(seq_shape=seq_shape, window=window, ext=0, chunk=chunk, chunk_ext=0)
+    out, path, (k_bar, beta) = _abi.eva_forward(q, k, v, _abi.eva_geometry(q, keep_stats=True, **geometry), ada, noise=noise,
+                                                return_path=True, return_stats=True)
+    assert path == expect_path
+    ref_out = _abi.eva_forward(q, k, v, _abi.eva_geometry(q, **geometry), ada, noise=noise)
+    assert torch.equal(out, ref_out)
+    kb, bt = _abi.eva_chunk_stats(q, k, v, _abi.eva_geometry(q, **geometry), ada, noise=noise)
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    assert rel_l2(k_bar.cpu(), kb.cpu()) < tol and rel_l2(beta.cpu(), bt.cpu()) < tol, (rel_l2(k_bar.cpu(), kb.cpu()), rel_l2(beta.cpu(), bt.cpu()))
+
+
 def _grads_of(module, cfg, a, dev, dtype):
     """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
     x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
