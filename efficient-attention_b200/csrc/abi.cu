@@ -251,8 +251,8 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
 
 int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, const float* k_bar_in, const float* beta_in, float* grad_qkv, float* grad_bias,
-                 float* chunk_rows, void* stream) {
+                 const void* out, const void* grad_out, const float* k_bar_in, const float* beta_in, float* grad_qkv, void* grad_qkv_io,
+                 float* grad_bias, float* chunk_rows, void* stream) {
   eva::Geo g{};
   eva::View vq, vk, vv;
   int rc;
@@ -261,6 +261,8 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   if (g.n_chunks > 0 && (rc = check_ada(ada))) return rc;
   if (g.n_chunks > 0 && !chunk_rows) return fail(EVA_ERR_INVALID, "chunk_rows is NULL");
   if (!out || !grad_out || !grad_qkv) return fail(EVA_ERR_INVALID, "out / grad_out / grad_qkv is NULL");
+  if ((reinterpret_cast<uintptr_t>(grad_qkv) | reinterpret_cast<uintptr_t>(grad_qkv_io)) & 15u)
+    return fail(EVA_ERR_INVALID, "grad_qkv / grad_qkv_io must be 16-byte aligned");
   if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(chunk_rows)) & 15u) != 0)
     return fail(EVA_ERR_INVALID, "out / grad_out / chunk_rows must be 16-byte aligned");
   if (bias && bias_stride_h != 0 && bias_stride_h != (int64_t)g.L * g.J)
@@ -289,7 +291,7 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   }
   const cudaError_t e = eva::launch_eva_backward(g, gin->io_dtype, vq, vk, vv, pad_mask, ada, noise, kbar, beta, bias, bias_stride_h, out,
                                                  grad_out, grad_qkv, grad_qkv + tens, grad_qkv + 2 * tens, chunk_rows + 2 * slot,
-                                                 chunk_rows + 3 * slot, grad_bias, chunk_rows + 4 * slot, st);
+                                                 chunk_rows + 3 * slot, grad_bias, chunk_rows + 4 * slot, grad_qkv_io, st);
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_backward");
 }
 

@@ -593,12 +593,237 @@ chunk_stats_bwd_kernel(const Geo g, const View q, const View k, const View v, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Chunk-statistics gradient, fast case: head_dim 64, 16-bit I/O, chunks without halo of at most 32 tokens, no padding mask (the
+// DeiT geometries).  Every token then belongs to exactly one chunk, so the warp that owns a chunk also FINISHES the gradient of the
+// chunk's tokens: it adds the chunk-path terms to the window kernel's float32 dq / dk / dv rows and writes the result once -- no
+// atomics -- either back in place or, when `gio` is given, rounded to the I/O format in the packed [B, N, 3, H, 64] layout of the
+// qkv projection (the caller's convert-and-interleave pass disappears).  One warp per chunk; lane l owns features 2l, 2l + 1 of
+// every vector (4-byte loads of 16-bit rows); the per-token dot products run with lane = token on k / v rows staged in shared
+// memory, so the 2 x Jc warp reductions of chunk_stats_bwd_kernel become two.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCgMaxJc = 32;
+constexpr int kCgRow = 132;          // bytes per staged 16-bit row: 33 words, conflict-free for lane = token and for lane = feature pair
+
+template <typename T> struct Pair16;
+template <> struct Pair16<__half> {
+  static __device__ __forceinline__ float2 up(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+template <> struct Pair16<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 up(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+
+// y = W x + b, x / y distributed as (2 lane, 2 lane + 1); Wt[in][out] in shared memory
+__device__ __forceinline__ float2 pair_linear(const float* __restrict__ Wt, const float* __restrict__ bias, float2 x, int lane) {
+  float2 y = bias ? __ldg(reinterpret_cast<const float2*>(bias) + lane) : make_float2(0.f, 0.f);
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float x0 = __shfl_sync(0xffffffffu, x.x, j), x1 = __shfl_sync(0xffffffffu, x.y, j);
+    const float2 w0 = *reinterpret_cast<const float2*>(Wt + (2 * j) * 64 + 2 * lane);
+    const float2 w1 = *reinterpret_cast<const float2*>(Wt + (2 * j + 1) * 64 + 2 * lane);
+    y.x = fmaf(w0.x, x0, fmaf(w1.x, x1, y.x));
+    y.y = fmaf(w0.y, x0, fmaf(w1.y, x1, y.y));
+  }
+  return y;
+}
+// dx = W^T dy, W row-major [out][in] in global memory (L1)
+__device__ __forceinline__ float2 pair_linear_bwd(const float* __restrict__ W, float2 dy, int lane) {
+  float2 dx = make_float2(0.f, 0.f);
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float d0 = __shfl_sync(0xffffffffu, dy.x, j), d1 = __shfl_sync(0xffffffffu, dy.y, j);
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W + (2 * j) * 64) + lane);
+    const float2 w1 = __ldg(reinterpret_cast<const float2*>(W + (2 * j + 1) * 64) + lane);
+    dx.x = fmaf(w0.x, d0, fmaf(w1.x, d1, dx.x));
+    dx.y = fmaf(w0.y, d0, fmaf(w1.y, d1, dx.y));
+  }
+  return dx;
+}
+// LayerNorm over 64 features held as pairs: normalised row and 1 / sigma
+__device__ __forceinline__ float2 pair_ln(float2 y, float eps, float& inv) {
+  const float mean = warp_sum(y.x + y.y) * (1.0f / 64);
+  const float cx = y.x - mean, cy = y.y - mean;
+  inv = 1.0f / sqrtf(warp_sum(cx * cx + cy * cy) * (1.0f / 64) + eps);
+  return make_float2(cx * inv, cy * inv);
+}
+__device__ __forceinline__ float2 pair_ln_bwd(float2 dout, float2 n, float inv, const float* __restrict__ gain, int lane) {
+  if (!gain) return dout;
+  const float2 gg = __ldg(reinterpret_cast<const float2*>(gain) + lane);
+  const float dx = dout.x * gg.x, dy = dout.y * gg.y;
+  const float s1 = warp_sum(dx + dy) * (1.0f / 64);
+  const float s2 = warp_sum(dx * n.x + dy * n.y) * (1.0f / 64);
+  return make_float2(inv * (dx - s1 - n.x * s2), inv * (dy - s1 - n.y * s2));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_grad_fast_kernel(const Geo g, const View q, const View k, const View v, const EvaAdaptive ada, const float* __restrict__ noise,
+                       const float* __restrict__ beta_fw, const float* __restrict__ dkbar, const float* __restrict__ dbeta,
+                       float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ rows,
+                       T* __restrict__ gio) {
+  extern __shared__ float sm[];
+  float* WtK = sm;
+  float* WtQ = sm + 64 * 64;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int e = idx >> 6, i = idx & 63;
+    WtK[i * 64 + e] = __ldg(ada.w_k + idx);
+    if (ada.w_q) WtQ[i * 64 + e] = __ldg(ada.w_q + idx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int Jc = g.Jc;
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(sm + 2 * 64 * 64) + (size_t)warp * (2 * Jc * kCgRow + 512);
+  uint8_t* Kt = tiles;                                              // [Jc][kCgRow] k rows
+  uint8_t* Vt = tiles + Jc * kCgRow;                                // [Jc][kCgRow] v rows
+  float* vec = reinterpret_cast<float*>(tiles + 2 * Jc * kCgRow);   // omega [64] | d beta [64]
+  const float scale = 0.125f;
+  const float inv_cnt = 1.0f / (float)Jc;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  const long long slot = total * 64;
+  for (long long wg = (long long)blockIdx.x * wpb + warp; wg < total; wg += (long long)gridDim.x * wpb) {
+    const int c = (int)(wg % g.n_chunks);
+    const int h = (int)((wg / g.n_chunks) % g.H);
+    const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+    const long long obase = wg * 64;
+    const int my_tok = lane < Jc ? group_token(g, c, lane, g.chunk, 0) : 0;
+    // ---- stage the chunk's k / v rows; column sums of q and k ----
+    __syncwarp();
+    for (int idx = lane; idx < Jc * 8; idx += 32) {
+      const int t = idx >> 3, piece = idx & 7;
+      const int tok = __shfl_sync(0xffffffffu, my_tok, t);
+      const uint4 rk = __ldg(reinterpret_cast<const uint4*>(k.row<T>(b, tok, h)) + piece);
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(v.row<T>(b, tok, h)) + piece);
+      uint32_t* dk_ = reinterpret_cast<uint32_t*>(Kt + t * kCgRow + piece * 16);
+      uint32_t* dv_ = reinterpret_cast<uint32_t*>(Vt + t * kCgRow + piece * 16);
+      dk_[0] = rk.x; dk_[1] = rk.y; dk_[2] = rk.z; dk_[3] = rk.w;
+      dv_[0] = rv.x; dv_[1] = rv.y; dv_[2] = rv.z; dv_[3] = rv.w;
+    }
+    float2 sq = make_float2(0.f, 0.f), sk = sq;
+    for (int t = 0; t < Jc; ++t) {
+      const int tok = __shfl_sync(0xffffffffu, my_tok, t);
+      const float2 a = Pair16<T>::up(__ldg(reinterpret_cast<const uint32_t*>(q.row<T>(b, tok, h)) + lane));
+      const float2 c2 = Pair16<T>::up(__ldg(reinterpret_cast<const uint32_t*>(k.row<T>(b, tok, h)) + lane));
+      sq.x += a.x; sq.y += a.y; sk.x += c2.x; sk.y += c2.y;
+    }
+    sq.x *= inv_cnt; sq.y *= inv_cnt; sk.x *= inv_cnt; sk.y *= inv_cnt;
+    // ---- forward statistics: k_bar, omega ----
+    float inv_k = 1.f, inv_q = 1.f;
+    float2 nk = make_float2(0.f, 0.f), nq = nk, om = nk;
+    float2 kb = pair_linear(WtK, ada.b_k, sk, lane);
+    if (ada.ln_gain_k) {
+      nk = pair_ln(kb, ada.ln_eps, inv_k);
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_k) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_k) + lane);
+      kb = make_float2(fmaf(nk.x, gg.x, bb.x), fmaf(nk.y, gg.y, bb.y));
+    }
+    if (ada.w_q) {
+      float2 qb = pair_linear(WtQ, ada.b_q, sq, lane);
+      if (ada.ln_gain_q) {
+        nq = pair_ln(qb, ada.ln_eps, inv_q);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_q) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_q) + lane);
+        qb = make_float2(fmaf(nq.x, gg.x, bb.x), fmaf(nq.y, gg.y, bb.y));
+      }
+      om = make_float2(ada.mu_coeff * (qb.x + kb.x), ada.mu_coeff * (qb.y + kb.y));
+    }
+    if (noise) { const float2 z = __ldg(reinterpret_cast<const float2*>(noise + obase) + lane); om.x += z.x; om.y += z.y; }
+    const float2 db = *(reinterpret_cast<const float2*>(dbeta + obase) + lane);
+    const float2 dkb_in = *(reinterpret_cast<const float2*>(dkbar + obase) + lane);
+    const float2 bf = __ldg(reinterpret_cast<const float2*>(beta_fw + obase) + lane);
+    const float dsum = warp_sum(db.x * bf.x + db.y * bf.y);                  // <d beta, beta>
+    reinterpret_cast<float2*>(vec)[lane] = om;
+    reinterpret_cast<float2*>(vec + 64)[lane] = db;
+    __syncwarp();
+    // ---- lane = token: phi-logit and <d beta, v_t> ----
+    float p1 = 0.f, p2 = 0.f;
+    if (lane < Jc) {
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(Kt + lane * kCgRow);
+      const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + lane * kCgRow);
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const float2 kk = Pair16<T>::up(kr[i]), vv = Pair16<T>::up(vr[i]);
+        const float2 oo = reinterpret_cast<const float2*>(vec)[i], dd = reinterpret_cast<const float2*>(vec + 64)[i];
+        p1 = fmaf(kk.x, oo.x - 0.5f * kk.x, fmaf(kk.y, oo.y - 0.5f * kk.y, p1));
+        p2 = fmaf(dd.x, vv.x, fmaf(dd.y, vv.y, p2));
+      }
+    }
+    const float lg = lane < Jc ? scale * p1 : kNegInf;
+    const float mx = warp_max(lg);
+    const float e = exp_nonpos(lg - mx);
+    const float a = e / warp_sum(e);                                           // softmax over the chunk's tokens (0 on idle lanes)
+    const float dlg = scale * a * (p2 - dsum);
+    // ---- d omega = sum_t dlg_t k_t ----
+    float2 dom = make_float2(0.f, 0.f);
+    for (int t = 0; t < Jc; ++t) {
+      const float d = __shfl_sync(0xffffffffu, dlg, t);
+      const float2 kk = Pair16<T>::up(reinterpret_cast<const uint32_t*>(Kt + t * kCgRow)[lane]);
+      dom.x = fmaf(d, kk.x, dom.x); dom.y = fmaf(d, kk.y, dom.y);
+    }
+    // ---- omega -> LayerNorm -> Linear -> means ----
+    const float cq = ada.w_q ? ada.mu_coeff : 0.f;
+    const float2 dok = make_float2(dkb_in.x + cq * dom.x, dkb_in.y + cq * dom.y);
+    const float2 doq = make_float2(cq * dom.x, cq * dom.y);
+    const float2 dyk = pair_ln_bwd(dok, nk, inv_k, ada.ln_gain_k, lane);
+    const float2 dmk = pair_linear_bwd(ada.w_k, dyk, lane);
+    float2 dyq = make_float2(0.f, 0.f), dmq = dyq;
+    if (ada.w_q) {
+      dyq = pair_ln_bwd(doq, nq, inv_q, ada.ln_gain_q, lane);
+      dmq = pair_linear_bwd(ada.w_q, dyq, lane);
+    }
+    {
+      float2* r2 = reinterpret_cast<float2*>(rows + obase) + lane;
+      const long long s2 = slot / 2;
+      r2[0] = dyk; r2[s2] = dyq; r2[2 * s2] = sk; r2[3 * s2] = sq; r2[4 * s2] = nk; r2[5 * s2] = nq; r2[6 * s2] = dok; r2[7 * s2] = doq;
+    }
+    // ---- finish the chunk's tokens: window-path rows + chunk-path terms, written once ----
+    for (int t = 0; t < Jc; ++t) {
+      const int tok = __shfl_sync(0xffffffffu, my_tok, t);
+      const float at = __shfl_sync(0xffffffffu, a, t), dt = __shfl_sync(0xffffffffu, dlg, t);
+      const float2 kk = Pair16<T>::up(reinterpret_cast<const uint32_t*>(Kt + t * kCgRow)[lane]);
+      const long long base = (((long long)b * g.N + tok) * g.H + h) * 64;
+      float2* pq = reinterpret_cast<float2*>(dq + base) + lane;
+      float2* pk = reinterpret_cast<float2*>(dk + base) + lane;
+      float2* pv = reinterpret_cast<float2*>(dv + base) + lane;
+      float2 gq = *pq, gk = *pk, gv = *pv;
+      gq.x = fmaf(dmq.x, inv_cnt, gq.x); gq.y = fmaf(dmq.y, inv_cnt, gq.y);
+      gk.x += fmaf(dt, om.x - kk.x, dmk.x * inv_cnt); gk.y += fmaf(dt, om.y - kk.y, dmk.y * inv_cnt);
+      gv.x = fmaf(at, db.x, gv.x); gv.y = fmaf(at, db.y, gv.y);
+      if (gio) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(gio + ((((long long)b * g.N + tok) * 3) * g.H + h) * 64) + lane;
+        const long long plane = (long long)g.H * 32;       // one of q | k | v, in 32-bit words
+        o[0] = Pair16<T>::pk(gq.x, gq.y); o[plane] = Pair16<T>::pk(gk.x, gk.y); o[2 * plane] = Pair16<T>::pk(gv.x, gv.y);
+      } else {
+        *pq = gq; *pk = gk; *pv = gv;
+      }
+    }
+  }
+}
+
+// float32 [3, B, N, H, D] -> io format, packed [B, N, 3, H, D] (the cases the fast kernel above does not finish itself)
+template <typename T>
+__global__ void pack_grad_kernel(const float* __restrict__ g3, T* __restrict__ gio, long long tens, int HD, int N) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;      // 4 elements of one (which, b, n) row
+  if (i4 >= 3 * tens) return;
+  const long long which = i4 / tens, rem = i4 % tens;
+  const long long bn = rem / HD, e = rem % HD;
+  const float4 x = *reinterpret_cast<const float4*>(g3 + i4);
+  T* o = gio + (bn * 3 + which) * HD + e;
+  o[0] = from_f32<T>(x.x); o[1] = from_f32<T>(x.y); o[2] = from_f32<T>(x.z); o[3] = from_f32<T>(x.w);
+}
+
+// ------------------------------------------------------------------------------------------------
 template <typename T, int D>
 static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, cudaStream_t st) {
+                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st) {
   cudaError_t e;
+  const long long tens = (long long)g.B * g.N * g.H * g.D;
+  auto pack = [&]() -> cudaError_t {          // generic finish: convert and interleave
+    if (!gio) return cudaSuccess;
+    const long long n4 = (3 * tens + 3) / 4;
+    pack_grad_kernel<T><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(dq, reinterpret_cast<T*>(gio), tens, g.H * g.D, g.N);
+    return cudaGetLastError();
+  };
   if (window_bwd_tc_supported(g, io_dtype, mask)) {
     e = launch_window_bwd_tc(g, io_dtype, q, k, v, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
   } else {
@@ -612,7 +837,22 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
                                             reinterpret_cast<const T*>(dout), dq, dk, dv, dkbar, dbeta, dbias);
     e = cudaGetLastError();
   }
-  if (e != cudaSuccess || g.n_chunks == 0) return e;
+  if (e != cudaSuccess) return e;
+  if (g.n_chunks == 0) return pack();
+  if constexpr (D == 64 && sizeof(T) == 2) {
+    static const bool slow_only = [] { const char* e_ = getenv("EVA_SM100_CHUNK_BWD_GENERIC"); return e_ && e_[0] == '1'; }();
+    if (!slow_only && !mask && g.chunk_ext == 0 && g.Jc <= kCgMaxJc) {
+      auto kf = chunk_grad_fast_kernel<T>;
+      const size_t smf = 2 * 64 * 64 * sizeof(float) + 8 * ((size_t)2 * g.Jc * kCgRow + 512);
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
+      if (e != cudaSuccess) return e;
+      const long long total_f = (long long)g.B * g.H * g.n_chunks;
+      long long blocks_f = (total_f + 7) / 8;
+      if (blocks_f > 148LL * 12) blocks_f = 148LL * 12;
+      kf<<<(unsigned)blocks_f, 256, smf, st>>>(g, q, k, v, *ada, noise, beta, dkbar, dbeta, dq, dk, dv, rows, reinterpret_cast<T*>(gio));
+      return cudaGetLastError();
+    }
+  }
   auto kern2 = chunk_stats_bwd_kernel<T, D>;
   const size_t smem2 = 2 * (size_t)D * D * sizeof(float);
   e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
@@ -621,15 +861,16 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
   long long blocks = (total + 7) / 8;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   kern2<<<(unsigned)blocks, 256, smem2, st>>>(g, q, k, v, mask, *ada, noise, dkbar, dbeta, dq, dk, dv, rows);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  return e != cudaSuccess ? e : pack();
 }
 
 cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, cudaStream_t st) {
+                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st) {
 #define EVA_BWD_CASE(DT, TY, DD) \
-  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, io_dtype, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, st);
+  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, io_dtype, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, gio, st);
   switch (io_dtype * 256 + g.D) {
     EVA_BWD_CASE(EVA_F32, float, 16) EVA_BWD_CASE(EVA_F32, float, 32) EVA_BWD_CASE(EVA_F32, float, 64) EVA_BWD_CASE(EVA_F32, float, 128)
     EVA_BWD_CASE(EVA_F16, __half, 16) EVA_BWD_CASE(EVA_F16, __half, 32) EVA_BWD_CASE(EVA_F16, __half, 64) EVA_BWD_CASE(EVA_F16, __half, 128)

@@ -44,11 +44,13 @@ cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, cons
                                  const EvaAdaptive* ada = nullptr, const float* noise = nullptr, unsigned int* flags = nullptr);
 
 // Backward of the two generic stages (eva_backward.cu); kbar / beta are the forward statistics, dkbar / dbeta zeroed scratch,
-// rows = 8 per-chunk row slots (see chunk_stats_bwd_kernel); ada / noise / dkbar / dbeta / rows unused when g.n_chunks == 0
+// rows = 8 per-chunk row slots (see chunk_stats_bwd_kernel); ada / noise / dkbar / dbeta / rows unused when g.n_chunks == 0;
+// grad_io (optional): the final dq | dk | dv once more, rounded to the I/O format, packed [B, N, 3, H, D] (dq / dk / dv float32 are
+// then scratch: the kernel that finishes a token may skip writing them back)
 cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, cudaStream_t st);
+                                float* dbeta, float* dbias, float* rows, void* grad_io, cudaStream_t st);
 
 // tcgen05 window-attention backward (eva_bwd_sm100.cu): head_dim 64, 16-bit I/O, halo-free windows of <= 64 tokens, <= 64 chunks
 bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask);

@@ -73,7 +73,7 @@ def load():
         lib.eva_window_attention.argtypes = [G, V, V, V, P, P, P, P, I64, P, P]
         lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
-        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P]
+        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P, P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
@@ -231,10 +231,12 @@ def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, ret
     return (out, path.value) if return_path else out
 
 
-def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False, stats=None):
+def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False, stats=None,
+                 packed_out=False):
     """Gradients of eva_forward / eva_window_attention (`ada` None for chunk-less geometries).
     Returns (grad_qkv float32 [3, B, N, H, D], grad_bias float32 like bias or None, chunk_rows float32 [12, B, H, C, D] or None --
-    the slots are listed at eva_backward in include/eva_sm100.h)."""
+    the slots are listed at eva_backward in include/eva_sm100.h).  packed_out: grad_qkv is returned in q's dtype in the packed
+    [B, N, 3, H, D] layout instead (written by the kernels themselves)."""
     lib = load()
     _require_cuda(q, k, v, out, grad_out, pad_mask, noise, bias)
     B, N, H, D = q.shape
@@ -247,6 +249,7 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     out = out.detach().contiguous()
     grad_out = grad_out.detach().to(out.dtype).contiguous()
     grad_qkv = torch.empty(3, B, N, H, D, dtype=torch.float32, device=q.device)
+    grad_io = torch.empty(B, N, 3, H, D, dtype=q.dtype, device=q.device) if packed_out else None
     rows = torch.empty(12, B, H, C, D, dtype=torch.float32, device=q.device) if C > 0 else None
     grad_bias = torch.empty_like(bias) if (want_bias_grad and bias is not None) else None
     ada_s, keep = ada if ada is not None else (None, None)
@@ -254,11 +257,11 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     with torch.cuda.device(q.device):
         rc = lib.eva_backward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
                               ctypes.byref(heads_view(v)), _ptr(mask), None if ada_s is None else ctypes.byref(ada_s), _ptr(noise),
-                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(k_bar), _ptr(beta), _ptr(grad_qkv), _ptr(grad_bias),
-                              _ptr(rows), _stream(q.device))
+                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(k_bar), _ptr(beta), _ptr(grad_qkv), _ptr(grad_io),
+                              _ptr(grad_bias), _ptr(rows), _stream(q.device))
     _check(rc, 'eva_backward')
     del keep
-    return grad_qkv, grad_bias, rows
+    return (grad_io if packed_out else grad_qkv), grad_bias, rows
 
 
 def eva_chunk_stats(q, k, v, geom, ada, *, pad_mask=None, noise=None):

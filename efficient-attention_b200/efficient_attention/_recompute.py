@@ -127,15 +127,15 @@ def eva_core_torch(q, k, v, *, seq_shape, window, ext, chunk, chunk_ext, wq, bq,
     return out.reshape(B, N, H * d)
 
 
-def _cuda_backward(saved, meta, need, grad_out):
+def _cuda_backward(saved, meta, need, grad_out, packed_out=False):
     """`eva_backward` on the saved (q, k, v, noise, bias, 8 parameters, out); need = needs_input_grad of (bias, 8 parameters).
-    Returns (float32 [3, B, N, H, D] = dq | dk | dv, (d bias, 8 parameter gradients))."""
+    Returns (float32 [3, B, N, H, D] = dq | dk | dv -- or, packed_out, q's dtype [B, N, 3, H, D] --, (d bias, 8 parameter gradients))."""
     q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = saved[:14]
     stats = tuple(saved[14:16]) if len(saved) >= 16 else None          # (k_bar, beta) kept by the forward
     geom = _abi.eva_geometry(q, **meta['geometry'])
     ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
     gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
-                                          want_bias_grad=bias is not None and need[0], stats=stats)
+                                          want_bias_grad=bias is not None and need[0], stats=stats, packed_out=packed_out)
     B, H, D = q.shape[0], q.shape[2], q.shape[-1]
     # per-chunk rows, grouped per (batch, head): the reductions over ~B*H*C rows run as B*H small GEMMs and one sum
     dyk, dyq, mk, mq, nk, nq, dok, doq = (rows[i].reshape(B * H, -1, D) for i in range(4, 12))
@@ -201,8 +201,8 @@ class EvaCoreFn(torch.autograd.Function):
 
 class EvaCorePackedFn(torch.autograd.Function):
     """EvaCoreFn for q, k, v that are the three slices of one packed [B, N, 3, H, d] projection output (abstract_attention.py:72-78):
-    the gradient goes back as ONE tensor in that layout (a single convert-and-interleave pass over dq | dk | dv) instead of three
-    casts followed by autograd's three zero-filled `select` gradients and their sums."""
+    the gradient goes back as ONE tensor in that layout, written by the backward kernels themselves (`grad_qkv_io` of eva_backward),
+    instead of three casts followed by autograd's three zero-filled `select` gradients and their sums."""
 
     @staticmethod
     def forward(ctx, packed, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, meta):
@@ -220,12 +220,8 @@ class EvaCorePackedFn(torch.autograd.Function):
         packed = ctx.saved_tensors[0]
         need = ctx.needs_input_grad
         saved = (packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]) + tuple(ctx.saved_tensors[1:])
-        gqkv, rest = _cuda_backward(saved, ctx.meta, need[2:11], grad_out)
-        gp = None
-        if need[0]:
-            gp = torch.empty(packed.shape, dtype=packed.dtype, device=packed.device)
-            gp.copy_(gqkv.permute(1, 2, 0, 3, 4))
-        return (gp, None) + rest + (None,)
+        gp, rest = _cuda_backward(saved, ctx.meta, need[2:11], grad_out, packed_out=True)
+        return (gp if need[0] else None, None) + rest + (None,)
 
 
 def eva_core(q, k, v, *, geometry, mu_coeff, params, pad_mask=None, noise=None, bias=None, packed=None):

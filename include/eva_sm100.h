@@ -126,6 +126,9 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
  *   out, grad_out  io_dtype [batch, tokens, heads*head_dim] contiguous: the forward result and the gradient arriving at it
  *   grad_qkv       float32 [3, batch, tokens, heads, head_dim] = dq | dk | dv (need not be initialised: the call zeroes what it
  *                  accumulates into)
+ *   grad_qkv_io    optional: io_dtype [batch, tokens, 3, heads, head_dim] -- the layout of the packed qkv projection
+ *                  (abstract_attention.py:72-78).  When given, the final dq | dk | dv are written there rounded to io_dtype and the
+ *                  contents of grad_qkv are unspecified on return (scratch)
  *   grad_bias      float32, the shape of `bias`; NULL: not wanted
  *   chunk_rows     float32 [12, batch, heads, C_n, head_dim]; NULL iff g->chunk == 0.  Slots on return:
  *                  0 k_bar | 1 beta (recomputed) | 2 d k_bar | 3 d beta | 4 dy_k | 5 dy_q (gradients at the adaptive Linear outputs) |
@@ -137,8 +140,8 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
  *                  into slots 0 / 1. */
 int eva_backward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, const float* k_bar, const float* beta, float* grad_qkv, float* grad_bias,
-                 float* chunk_rows, void* stream);
+                 const void* out, const void* grad_out, const float* k_bar, const float* beta, float* grad_qkv, void* grad_qkv_io,
+                 float* grad_bias, float* chunk_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LARA (lara.py).  Landmarks are the pooled q/k summaries; samples S = landmarks C, or 2C with

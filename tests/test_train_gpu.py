@@ -145,7 +145,8 @@ def test_tcgen05_backward_kernel_matches_the_cuda_core_kernel(seq_shape, window,
             x = qkv.clone().requires_grad_(True)
             b_ = bias.clone().requires_grad_(True) if with_bias else None
             prm = [ada[n_].clone().requires_grad_(True) for n_ in names]
-            out = _recompute.eva_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, mu_coeff=0.5, params=prm, noise=noise, bias=b_)
+            out = _recompute.eva_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, mu_coeff=0.5, params=prm, noise=noise, bias=b_,
+                                      packed=x if mode else None)       # mode 1 also takes the packed-gradient route (grad_qkv_io)
             (out.float() * w).sum().backward()
             assert lib.eva_debug_bwd_tc_count() - before == mode
             return [x.grad.float()] + ([b_.grad] if with_bias else []) + [p_.grad for p_ in prm]
