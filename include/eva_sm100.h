@@ -1,5 +1,5 @@
 /* eva_sm100.h -- C ABI of libeva_sm100.so: the B200 (sm_100a) EVA / LARA / causal-EVA attention
- * forward core.
+ * core (forward; backward for the EVA family).
  *
  * The reference (HKUNLP/efficient-attention) is pure Python/PyTorch and has no native boundary of
  * its own; the seam is cut just below `module.forward`: everything between `proj_and_split_heads`
@@ -11,6 +11,8 @@
  *                          local_attention.py:134-182   abstract_attention.py:115-133   joint softmax, PV)
  *   eva_forward            eva.py:151-227 as one call (selects the fused sm_100a tcgen05/TMA kernel
  *                          when the geometry allows, else the two generic stages)
+ *   eva_backward           what autograd derives from eva.py:151-227 / causal_eva.py:676-783 / local_attention.py:134-182
+ *                          (vit/engine.py:47-62 trains through it): gradients of eva_forward / eva_window_attention
  *   lara_forward           lara.py:84-175          (landmark pooling, Linear+LN, mixing, proposal stats) and
  *                          lara.py:201-246         (phi-projections, kv statistics, MIS weights, SNIS) in one call
  *
