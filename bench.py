@@ -432,6 +432,33 @@ def deit_leg(dev, world, batch=128, warm=20, steps=100):
             del bare
         except Exception as e:
             out['attention_share_error'] = f'{type(e).__name__}: {e}'[:200]
+    # training step (vit/engine.py:47-62): forward + backward (this package's eva_backward kernels) + SGD, DDP gradient all-reduce at N > 1
+    try:
+        model.train()
+        net = model
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
+        opt = torch.optim.SGD(net.parameters(), lr=1e-4)
+        target = torch.randint(0, 1000, (batch,), device=dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast('cuda', dtype=torch.float16):
+                loss = torch.nn.functional.cross_entropy(net(x).float(), target)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        train_ms = reduce_max_ms(statistics.median(timed(train_step, max(10, steps // 5))), dev, world)
+        out['train'] = {'ms_per_step': train_ms, 'images_per_s': batch * world / (train_ms * 1e-3),
+                        'what': 'forward + backward + SGD step, autocast fp16, unscaled loss' + (', DDP all-reduce over NCCL' if world > 1 else '')}
+        model.eval()
+    except Exception as e:
+        out['train_error'] = f'{type(e).__name__}: {e}'[:300]
     best = min(eager_ms, graph_ms) if graph_ms is not None else eager_ms
     out.update(images_per_s=batch * world / (best * 1e-3), ms_per_step=best, unit='images/s',
                timing='median of per-forward CUDA-event times, max over ranks')

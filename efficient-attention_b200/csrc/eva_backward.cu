@@ -159,7 +159,10 @@ window_attn_bwd_kernel(const Geo g, const View q, const View k, const View v, co
   float m[kBRw], linv[kBRw];
 #pragma unroll
   for (int r = 0; r < kBRw; ++r) { m[r] = kNegInf; linv[r] = 0.f; }
+  // causal: a tile of local keys that lies entirely above the diagonal of this row block holds only masked logits (P = dS = 0)
+  const int last_visible = rb * kBR + kBR - 1 + g.ext;
   for (int kt0 = 0; kt0 < n_keys; kt0 += kBK) {
+    if (g.causal && kt0 > last_visible && kt0 + kBK <= g.J) continue;
     __syncthreads();
     load_tile(kt0, false);
     __syncthreads();
@@ -207,6 +210,7 @@ window_attn_bwd_kernel(const Geo g, const View q, const View k, const View v, co
     for (int i = 0; i < DPL; ++i) dqa[r][i] = 0.f;
 
   for (int kt0 = 0; kt0 < n_keys; kt0 += kBK) {
+    if (g.causal && kt0 > last_visible && kt0 + kBK <= g.J) continue;
     __syncthreads();
     load_tile(kt0, true);
     __syncthreads();

@@ -294,15 +294,17 @@ def _segment_means(t, n_lm):
 
 
 def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded, alpha_coeff,
-                    wq, bq, gq, betq, wk, bk, gk, betk, dense=False, ln_eps=1e-5, pad_mask=None, noise=None):
+                    wq, bq, gq, betq, wk, bk, gk, betk, dense=False, ln_eps=1e-5, pad_mask=None, noise=None, keep_dtype=False):
     """q, k, v [B, N, H, d] -> [B, N, H * d] float32: landmarks (pooled 2-D 'light' / 'dense', or 1-D segment means with optional
     per-token Linear + LayerNorm), optional landmark mixing, then the self-normalised importance-sampling estimator with the three
     MIS variants.  sample_mode: 0 one sample per landmark, 1 antithetic (noise [.., C, d] -> [mu + e ; mu - e]), 2 multi (noise [.., 2C, d])."""
     B, N, H, d = q.shape
     scale = d ** -0.5
-    qh, kh, vh = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))           # [B, H, N, d]
+    # keep_dtype: leave 16-bit q, k, v as they are -- the caller runs this under torch.autocast, i.e. with the numerics the reference
+    # itself trains with (matmuls in the 16-bit format, softmax / logsumexp / LayerNorm / sums in float32)
+    qh, kh, vh = ((t if keep_dtype else t.float()).permute(0, 2, 1, 3) for t in (q, k, v))           # [B, H, N, d]
     if zero_padded and pad_mask is not None:
-        keep = (~pad_mask.to(torch.bool)).to(torch.float32).view(B, 1, N, 1)
+        keep = (~pad_mask.to(torch.bool)).to(qh.dtype).view(B, 1, N, 1)
         qh, kh, vh = qh * keep, kh * keep, vh * keep
     two_d = len(seq_shape) == 2
     if two_d:
@@ -381,7 +383,8 @@ class LaraCoreFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         meta = ctx.meta
         need = list(ctx.needs_input_grad[:4]) + list(ctx.needs_input_grad[5:13])
-        with torch.enable_grad():
+        half = saved[0].dtype in (torch.float16, torch.bfloat16)       # 16-bit activations: differentiate under autocast, as the reference trains
+        with torch.enable_grad(), torch.autocast('cuda', dtype=saved[0].dtype if half else torch.float16, enabled=half):
             ins = [None if t is None else t.detach().requires_grad_(n and t.is_floating_point()) for t, n in zip(saved, need)]
             q, k, v, noise, wq, bq, gq, betq, wk, bk, gk, betk = ins
             kk = meta['kernel']
@@ -389,9 +392,9 @@ class LaraCoreFn(torch.autograd.Function):
                                   mixed=kk['mixed'], mis_type=kk['mis_type'], sample_mode=kk['sample_mode'],
                                   zero_padded=kk['zero_padded'], alpha_coeff=kk['alpha_coeff'], wq=wq, bq=bq, gq=gq, betq=betq,
                                   wk=wk, bk=bk, gk=gk, betk=betk, dense=meta['dense'], ln_eps=meta['ln_eps'],
-                                  pad_mask=meta['pad_mask'], noise=noise)
+                                  pad_mask=meta['pad_mask'], noise=noise, keep_dtype=half)
             wanted = [t for t in ins if t is not None and t.requires_grad]
-            grads = torch.autograd.grad(out, wanted, grad_out.float().reshape(out.shape), allow_unused=True)
+            grads = torch.autograd.grad(out, wanted, grad_out.to(out.dtype).reshape(out.shape), allow_unused=True)
         it = iter(grads)
         res = []
         for t, src in zip(ins, saved):

@@ -29,7 +29,42 @@ def timed(fn, n, warm=5):
     return statistics.median(a.elapsed_time(b) for a, b in evs)
 
 
-def arm(which):
+def causal_arm(which, ea, dev):
+    """BASELINE config c5: one CausalEVAttention layer (embed 512, 8 heads, window = chunk = 256, T5 bias), T = 4096, batch 16, fp16
+    autocast: forward (eval) and forward + backward (train)."""
+    import warnings
+    from argparse import Namespace
+    import bench
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        torch.manual_seed(0)
+        m = bench.lively_init(ea.CausalEVAttention(512, 8, self_attention=True, attn_args=Namespace(
+            adaptive_proj='qk', num_chunks=None, chunk_size=256, causal=True, use_t5_rpe=True, window_size=256,
+            overlap_window=False))).to(dev)
+    x = torch.randn(4096, 16, 512, device=dev)
+    out = {'arm': which, 'attn': 'causal', 'package': os.path.dirname(ea.__file__)}
+    m.eval()
+
+    def fwd():
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+            return m(x, x, x, need_weights=False)
+    out['layer_fwd_ms'] = timed(fwd, 20)
+    m.train()
+
+    def fwd_bwd():
+        xx = x.detach().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.float16):
+            y = m(xx, xx, xx, need_weights=False)[0]
+        y.float().pow(2).mean().backward()
+    try:
+        out['layer_fwd_bwd_ms'] = timed(fwd_bwd, 10, warm=3)
+        out['peak_gib'] = torch.cuda.max_memory_allocated() / 2 ** 30
+    except RuntimeError as e:
+        out['layer_fwd_bwd_ms'] = f'failed: {str(e)[:80]}'
+    print(json.dumps(out))
+
+
+def arm(which, attn='eva'):
     import bench
     from oracle import ref_loader
     dev = torch.device('cuda', 0)
@@ -38,15 +73,21 @@ def arm(which):
     else:
         bench.use_product_package()
         import efficient_attention as ea
-    out = {'arm': which, 'package': os.path.dirname(ea.__file__)}
+    out = {'arm': which, 'attn': attn, 'package': os.path.dirname(ea.__file__)}
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        torch.manual_seed(0)
-        layer = bench.lively_init(ea.AttentionFactory.build_attention('eva', dict(bench.EVA_ARGS))).to(dev).eval()
         vm = ref_loader.vit_models()
         torch.manual_seed(0)
-        model = vm.evit_tiny_p8(ref_loader.deit_args('eva')).to(dev)
-    for B in (128, 1024):
+        if attn == 'eva':
+            layer = bench.lively_init(ea.AttentionFactory.build_attention('eva', dict(bench.EVA_ARGS))).to(dev).eval()
+            model = vm.evit_tiny_p8(ref_loader.deit_args('eva')).to(dev)
+        elif attn == 'causal':
+            layer = model = None
+        else:                                     # LARA: BASELINE config c4 = DeiT-small-p16 (196 tokens, 384 channels, 6 heads)
+            layer = None
+            model = vm.evit_small_p16(ref_loader.deit_args('lara')).to(dev)
+        out['model'] = {'eva': 'evit_tiny_p8', 'lara': 'evit_small_p16'}.get(attn, 'CausalEVAttention layer')
+    for B in ((128, 1024) if layer is not None else ()):
         x = torch.randn(B, 28, 28, 192, device=dev)
 
         def layer_fwd():
@@ -60,6 +101,8 @@ def arm(which):
             out[f'layer_fwd_ms_B{B}'] = f'failed: {str(e)[:80]}'
         del x
         torch.cuda.empty_cache()
+    if attn == 'causal':
+        return causal_arm(which, ea, dev)
     img = torch.randn(128, 3, 224, 224, device=dev)
     model.eval()
 
@@ -87,10 +130,11 @@ def arm(which):
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1:
-        arm(sys.argv[1])
+    if len(sys.argv) > 1 and sys.argv[1] in ('reference', 'ours'):
+        arm(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else 'eva')
     else:
+        attn = sys.argv[1] if len(sys.argv) > 1 else 'eva'
         for which in ('reference', 'ours'):
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), which], capture_output=True, text=True, timeout=1200)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), which, attn], capture_output=True, text=True, timeout=1200)
             lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
             print(lines[-1] if lines else f'{which}: failed\n{r.stderr[-1500:]}')
