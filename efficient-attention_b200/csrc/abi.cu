@@ -142,8 +142,11 @@ int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const Ev
                                                      reinterpret_cast<cudaStream_t>(stream), &msg);
     return ec == cudaSuccess ? EVA_OK : fail(EVA_ERR_CUDA, "eva_window_attention(causal window): %s: %s", msg, cudaGetErrorString(ec));
   }
-  const cudaError_t e = eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias,
-                                                bias_stride_h, out, reinterpret_cast<cudaStream_t>(stream));
+  const cudaError_t e = eva::window_tc_supported(g, gin->io_dtype)
+                            ? eva::launch_window_tc(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out,
+                                                    reinterpret_cast<cudaStream_t>(stream))
+                            : eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out,
+                                                      reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_window_attention");
 }
 
@@ -242,7 +245,9 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
       e = eva::launch_causal_window(gs, gin->io_dtype, sq, sk, sv, k_bar + stat_off, beta + stat_off, bias, sout, st, &msg);
       if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal window): %s: %s", msg, cudaGetErrorString(e));
     } else {
-      e = eva::launch_window_attn(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st);
+      e = eva::window_tc_supported(gs, gin->io_dtype)
+              ? eva::launch_window_tc(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st)
+              : eva::launch_window_attn(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st);
       if (e != cudaSuccess) return cuda_fail(e, "eva_forward(window_attention)");
     }
   }

@@ -137,4 +137,20 @@ __device__ __forceinline__ int group_token(const Geo& g, int grp, int slot, int 
   return (p >= 0 && p < g.N) ? p : -1;
 }
 
+// logit of (query row li / token tq, key gj) after bias and masks, exactly as window_attn_kernel (eva_generic.cu); returns whether it still depends
+// on q . k (false: the forward overwrote it with a constant, so no gradient flows to q, k or the bias)
+__device__ __forceinline__ bool finish_logit(const Geo& g, float& sv, int flag, int gj, int li, int tq, int qpad,
+                                             const float* __restrict__ bias, long long bias_off) {
+  if (flag == 2) { sv = kNegInf; return false; }
+  if (gj < g.J) {
+    bool live = true;
+    if (bias) sv += __ldg(bias + bias_off + (long long)li * g.J + gj);
+    if (flag == 1 || (g.mask_queries && qpad)) { sv = g.mask_fill; live = false; }
+    if (g.causal && gj > li + g.ext) { sv = kMaskVal; live = false; }
+    return live;
+  }
+  if (g.causal && (gj - g.J) >= tq / g.chunk) { sv = kMaskVal; return false; }
+  return true;
+}
+
 }  // namespace eva

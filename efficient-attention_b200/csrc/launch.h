@@ -52,6 +52,11 @@ cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
                                 float* dbeta, float* dbias, float* rows, void* grad_io, cudaStream_t st);
 
+// Window attention on tcgen05 for any geometry with head_dim 64 and 16-bit I/O (eva_window_tc_sm100.cu); arguments as launch_window_attn
+bool window_tc_supported(const Geo& g, int io_dtype);
+cudaError_t launch_window_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                             const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st);
+
 // tcgen05 window-attention backward (eva_bwd_sm100.cu): head_dim 64, 16-bit I/O, halo-free windows of <= 64 tokens, <= 64 chunks
 bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask);
 cudaError_t launch_window_bwd_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,

@@ -830,3 +830,60 @@ def test_lara_core_many_items_vs_oracle_fp16():
         mean += float(per_item.sum()) / (B * H)
     assert mean < TOL_F16, mean
     assert worst < 1.5 * TOL_F16, worst          # worst of 384 items; the mean is the north_star figure
+
+
+@pytest.mark.parametrize('seq_shape,window,ext,chunk,causal,with_mask,dtype', [
+    ((14, 14), 7, 3, 2, False, False, torch.float16), ((28, 28), 7, 0, 4, False, False, torch.bfloat16),
+    ((96,), 16, 8, 12, False, True, torch.float16), ((512,), 128, 128, 64, True, True, torch.float16),
+    ((128,), 32, 0, 16, True, False, torch.bfloat16), ((14, 14), 7, 0, 0, False, False, torch.float16),
+    ((197,), 197, 0, 0, False, True, torch.float16), ((784,), 784, 0, 0, False, False, torch.float16),
+    ((640,), 320, 0, 64, True, False, torch.float16)])
+def test_tcgen05_window_kernel_matches_the_cuda_core_kernel(seq_shape, window, ext, chunk, causal, with_mask, dtype):
+    """eva_window_tc_sm100.cu (any geometry, head_dim 64, 16-bit) against window_attn_kernel of eva_generic.cu on identical
+    inputs through `eva_window_attention`, and against the float64 oracle; the dispatch counter proves which kernel ran."""
+    from efficient_attention import _abi
+    dev = torch.device('cuda', 0)
+    lib = _abi.load()
+    B, H, d = 2, 3, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + window + ext + chunk)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dtype)
+    two_d = len(seq_shape) == 2
+    L = window * window if two_d else window
+    J = (window + 2 * ext) ** 2 if two_d else window + (ext if causal else 2 * ext)
+    bias = 0.5 * torch.randn(H, L, J, generator=g) if L * J <= 1 << 16 else None
+    mask = None
+    if with_mask:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[1, N - 9:] = True
+    softmax_like = chunk == 0 and window == N
+    geometry = dict(seq_shape=seq_shape, window=window, ext=ext, chunk=chunk, chunk_ext=0 if causal else ext, causal=causal,
+                    halo_left_only=causal, mask_queries=causal, mask_is_neg_inf=softmax_like)
+    qd = qkv.to(dev)
+    q, k, v = qd[:, :, 0], qd[:, :, 1], qd[:, :, 2]
+    geom = _abi.eva_geometry(q, **geometry)
+    stats = {}
+    ada = None
+    if chunk:
+        ada = _rand_ada(d, g)
+        noise = torch.randn(B, H, _abi.num_chunks(geom), d, generator=g)
+        kb, bt = _abi.eva_chunk_stats(q, k, v, geom, _abi_ada(ada, dev, 1.0 if causal else 0.5), pad_mask=None if mask is None else mask.to(dev),
+                                      noise=noise.to(dev))
+        stats = dict(k_bar=kb, beta=bt)
+
+    def run(mode):
+        lib.eva_debug_set_window_tc(mode)
+        try:
+            before = lib.eva_debug_window_tc_count()
+            out = _abi.eva_window_attention(q, k, v, geom, pad_mask=None if mask is None else mask.to(dev),
+                                            bias=None if bias is None else bias.to(dev), **stats)
+            torch.cuda.synchronize()
+            assert lib.eva_debug_window_tc_count() - before == mode
+            return out.float().cpu()
+        finally:
+            lib.eva_debug_set_window_tc(-1)
+    got, want = run(1), run(0)
+    live = torch.ones(B, N, dtype=torch.bool) if (mask is None or not causal) else ~mask      # padded queries of the causal layer are don't-care rows
+    assert torch.isfinite(got[live]).all()
+    tol = 2e-3 if dtype == torch.float16 else 1.2e-2
+    assert rel_l2(got[live], want[live]) < tol, rel_l2(got[live], want[live])
