@@ -6,9 +6,9 @@
 // CTA iteration = (batch x head, window, block of 128 query rows); keys = [local window slots | chunk keys] in tiles of 128.
 //   rows -> Q tile (gathered with the window index arithmetic, 128-byte swizzle); per key tile: K / V rows (or k_bar / beta rows,
 //   float32 -> the I/O format) -> tiles, flags (live / masked / absent) -> shared memory
-//   pass 0 (only when there is more than one key tile): S = Q K^T per tile, row maxima of the finished logits
-//   pass 1: S = Q K^T, P = exp2(logit - max) as 16-bit pairs -> tensor memory, O += P V (A operand from tensor memory, V MN-major)
-//   epilogue: O / rowsum -> out
+//   per tile: S = Q K^T, finished logits, online softmax (running row maximum; the O row in tensor memory and the row sum are
+//   rescaled when it moves), P = exp2(logit - max) as 16-bit pairs -> tensor memory, O += P V (A operand from tensor memory,
+//   V MN-major); epilogue: O / rowsum -> out
 // TMEM lane = query row (M = 128); warps w and w + 4 share a lane quarter and split the 128 columns of a tile; the two partial
 // maxima / sums of a row meet in shared memory once per pass.  Bias, padding, causal and chunk-visibility rules are applied by
 // finish_logit (common.cuh), the same function the CUDA-core kernels use.
@@ -28,8 +28,8 @@ using fused::tmem_ld_cols;
 using fused::ex2;
 
 constexpr int kThreads = 256;
-constexpr int kQ = 0, kK = 16384, kV = 32768, kMisc = 49152;
-constexpr int kFlag = kMisc, kQtok = kFlag + 512, kQpad = kQtok + 512, kPm = kQpad + 512, kPl = kPm + 1024, kBar = kPl + 1024,
+constexpr int kQ = 0, kK = 16384, kV = 32768, kBuf = 32768, kMisc = 81920;   // K / V tiles of buffer 1 at + kBuf
+constexpr int kFlag = kMisc, kFac = kFlag + 1024, kQtok = kFac + 2048, kQpad = kQtok + 512, kPm = kQpad + 512, kPl = kPm + 1024, kBar = kPl + 1024,
               kSlot = kBar + 16, kSmemBytes = kSlot + 16 + 1024;
 constexpr uint32_t kTmemCols = 256, cS = 0, cP = 128, cO = 192;
 
@@ -51,7 +51,8 @@ eva_window_tc_kernel(const Params p) {
   uint8_t* sm = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo& g = p.g;
-  int* kflag = reinterpret_cast<int*>(sm + kFlag);     // [128] 0 live, 1 masked, 2 absent
+  int* kflag_all = reinterpret_cast<int*>(sm + kFlag); // [2][128] per buffer: 0 live, 1 masked, 2 absent
+  float2* kfac_all = reinterpret_cast<float2*>(sm + kFac);   // [2][128] the same as (multiplier, addend): logit = s * mul + add
   int* qtok = reinterpret_cast<int*>(sm + kQtok);      // [128] token of the row, -1: no such row
   int* qpad = reinterpret_cast<int*>(sm + kQpad);
   float* pm = reinterpret_cast<float*>(sm + kPm);      // [2][128]
@@ -67,8 +68,8 @@ eva_window_tc_kernel(const Params p) {
   constexpr uint32_t fmt = IoFmt<T>::kUmma;
   constexpr uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 128);
   constexpr uint32_t id_pv = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
-  const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(sm + kQ)), dK = ptx::umma_desc_sw128(ptx::smem_u32(sm + kK)),
-                 dV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV));
+  const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(sm + kQ)), dK0 = ptx::umma_desc_sw128(ptx::smem_u32(sm + kK)),
+                 dV0 = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV));
   const int qr = warp & 3, hf = warp >> 2;
   const int r = 32 * qr + lane;                        // query row of the block = TMEM lane
   const uint32_t trow = tmem + ((uint32_t)(32 * qr) << 16);
@@ -101,44 +102,50 @@ eva_window_tc_kernel(const Params p) {
     }
     const int last_visible = rb * 128 + 127 + g.ext;   // causal: local key tiles entirely above the diagonal are skipped
     auto skip_tile = [&](int kt0) { return g.causal && kt0 > last_visible && kt0 + 128 <= g.J; };
-    auto load_tile = [&](int kt0, bool with_v) -> int {
+    // K / V rows of one key tile -> buffer `buf`, asynchronously (cp.async, zero-filled where there is no row); the chunk rows are
+    // converted from float32 on the way.  Returns the OR of the flags this thread wrote.
+    auto load_tile = [&](int kt0, int buf) -> int {
       int flags = 0;
+      int* kflag = kflag_all + 128 * buf;
       for (int idx = tid; idx < 128 * 8; idx += kThreads) {
         const int j = idx >> 3, piece = idx & 7;
         const int gj = kt0 + j;
-        uint4 zk = make_uint4(0, 0, 0, 0), zv = zk;
+        const uint32_t dk = ptx::smem_u32(sm + kK + buf * kBuf + tile_off(j, 8 * piece)), dv = dk + (kV - kK);
         int flag = 0;
         if (gj < g.J) {
           const int tok = group_token(g, win, gj, g.window, g.ext);
-          if (tok >= 0) {
-            zk = __ldg(reinterpret_cast<const uint4*>(p.k.row<T>(b, tok, h)) + piece);
-            if (with_v) zv = __ldg(reinterpret_cast<const uint4*>(p.v.row<T>(b, tok, h)) + piece);
-            flag = (p.mask && p.mask[(long long)b * g.N + tok]) ? 1 : 0;
-          } else {
-            flag = 1;
-          }
+          const int sz = tok >= 0 ? 16 : 0;
+          const int tk_ = tok >= 0 ? tok : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(reinterpret_cast<const uint4*>(p.k.row<T>(b, tk_, h)) + piece), "r"(sz) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(reinterpret_cast<const uint4*>(p.v.row<T>(b, tk_, h)) + piece), "r"(sz) : "memory");
+          flag = tok >= 0 ? ((p.mask && p.mask[(long long)b * g.N + tok]) ? 1 : 0) : 1;
         } else if (gj < n_keys) {
           const long long base = ((long long)bh * g.n_chunks + (gj - g.J)) * 64 + 8 * piece;
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.kbar + base)), a1 = __ldg(reinterpret_cast<const float4*>(p.kbar + base) + 1);
-          zk = make_uint4(IoFmt<T>::pack2(a0.x, a0.y), IoFmt<T>::pack2(a0.z, a0.w), IoFmt<T>::pack2(a1.x, a1.y), IoFmt<T>::pack2(a1.z, a1.w));
-          if (with_v) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + base)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + base) + 1);
-            zv = make_uint4(IoFmt<T>::pack2(b0.x, b0.y), IoFmt<T>::pack2(b0.z, b0.w), IoFmt<T>::pack2(b1.x, b1.y), IoFmt<T>::pack2(b1.z, b1.w));
-          }
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + base)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + base) + 1);
+          *reinterpret_cast<uint4*>(sm + kK + buf * kBuf + tile_off(j, 8 * piece)) =
+              make_uint4(IoFmt<T>::pack2(a0.x, a0.y), IoFmt<T>::pack2(a0.z, a0.w), IoFmt<T>::pack2(a1.x, a1.y), IoFmt<T>::pack2(a1.z, a1.w));
+          *reinterpret_cast<uint4*>(sm + kV + buf * kBuf + tile_off(j, 8 * piece)) =
+              make_uint4(IoFmt<T>::pack2(b0.x, b0.y), IoFmt<T>::pack2(b0.z, b0.w), IoFmt<T>::pack2(b1.x, b1.y), IoFmt<T>::pack2(b1.z, b1.w));
         } else {
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sm + kK + buf * kBuf + tile_off(j, 8 * piece)) = z;
+          *reinterpret_cast<uint4*>(sm + kV + buf * kBuf + tile_off(j, 8 * piece)) = z;
           flag = 2;
         }
-        const int off = tile_off(j, 8 * piece);
-        *reinterpret_cast<uint4*>(sm + kK + off) = zk;
-        if (with_v) *reinterpret_cast<uint4*>(sm + kV + off) = zv;
-        if (piece == 0) kflag[j] = flag;
+        if (piece == 0) {
+          kflag[j] = flag;
+          kfac_all[128 * buf + j] = flag == 0 ? make_float2(1.f, 0.f) : make_float2(0.f, flag == 1 ? g.mask_fill : kNegInf);
+        }
         flags |= flag;
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       return flags;
     };
     // S = Q K^T of the staged tiles; every thread returns once it is in TMEM.  Returns whether ANY key of the tile needs more than
     // the scale (a mask flag; the block-wide OR rides on the barrier the MMA issue needs anyway)
-    auto mma_s = [&](int my_flags) -> bool {
+    auto mma_s = [&](int my_flags, int buf) -> bool {
+      const uint64_t dK = dK0 + (uint64_t)((buf * kBuf) >> 4);
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       const int any = __syncthreads_or(my_flags);
@@ -159,7 +166,8 @@ eva_window_tc_kernel(const Params p) {
     const int tq_chunk = (g.causal && g.chunk > 0 && tq_row >= 0) ? tq_row / g.chunk : 0;
     const float* brow = (p.bias && tq_row >= 0) ? p.bias + bias_off + (long long)li_row * g.J : nullptr;
     const bool rules = p.bias != nullptr || g.causal || g.mask_queries;       // anything beyond per-key flags
-    auto logits = [&](int kt0, bool tile_flags, float (&x)[64]) {
+    auto logits = [&](int kt0, bool tile_flags, int buf, float (&x)[64]) {
+      const int* kflag = kflag_all + 128 * buf;
       tmem_ld_cols<64>(trow + cS + 64 * hf, reinterpret_cast<uint32_t*>(x));
       ptx::tmem_ld_wait();
       if (!rules && !tile_flags) {                     // the common tile: every key live, no bias, no causal rule
@@ -168,11 +176,16 @@ eva_window_tc_kernel(const Params p) {
         return;
       }
       const int c0 = kt0 + 64 * hf;
-      // the 64 per-key flags of my columns as bit masks (one shared-memory read per lane instead of one per column)
-      const int fa = kflag[64 * hf + lane], fb = kflag[64 * hf + 32 + lane];
-      const uint32_t dead[2] = {__ballot_sync(0xffffffffu, fa == 1), __ballot_sync(0xffffffffu, fb == 1)};
-      const uint32_t gone[2] = {__ballot_sync(0xffffffffu, fa == 2), __ballot_sync(0xffffffffu, fb == 2)};
+      const float2* kf = kfac_all + 128 * buf + 64 * hf;       // per key: (1, 0) live | (0, mask_fill) masked | (0, -inf) absent
       const bool row_masked = g.mask_queries && qp_row;
+      if (!rules || (!brow && !g.causal && !row_masked)) {     // flags only: one broadcast read and two FMAs per column
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float2 f = kf[j];
+          x[j] = fmaf(x[j] * scale, f.x, f.y) * kLog2e;
+        }
+        return;
+      }
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         float bb[16];
@@ -184,54 +197,63 @@ eva_window_tc_kernel(const Params p) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int j = 16 * blk + e, gj = c0 + j;
-          float sv = fmaf(x[j], scale, bb[e]);
+          const float2 f = kf[j];
+          float sv = fmaf(fmaf(x[j], scale, bb[e]), f.x, f.y);
           if (gj < g.J) {
-            if (((dead[j >> 5] >> (j & 31)) & 1u) || row_masked) sv = g.mask_fill;
+            if (row_masked) sv = g.mask_fill;
             if (g.causal && gj > li_row + g.ext) sv = kMaskVal;
-          } else if (g.causal && (gj - g.J) >= tq_chunk) {
+          } else if (g.causal && gj < n_keys && (gj - g.J) >= tq_chunk) {
             sv = kMaskVal;
           }
-          if ((gone[j >> 5] >> (j & 31)) & 1u) sv = kNegInf;
           x[j] = sv * kLog2e;
         }
       }
     };
-    float mrow = kNegInf;
-    if (n_tiles > 1) {
-      for (int kt0 = 0; kt0 < n_keys; kt0 += 128) {
-        if (skip_tile(kt0)) continue;
-        __syncthreads();
-        const bool tf = mma_s(load_tile(kt0, false));
-        float x[64];
-        logits(kt0, tf, x);
-#pragma unroll
-        for (int j = 0; j < 64; ++j) mrow = fmaxf(mrow, x[j]);
-      }
-      pm[hf * 128 + r] = mrow;
-      __syncthreads();
-      mrow = fmaxf(pm[r], pm[128 + r]);
-    }
+    float mrow = kNegInf;                              // running row maximum (both column halves), log2 domain
     float lrow = 0.f;
     bool first = true;
     long long tk[6];
+    bool first_print = true;
     const bool tr_on = p.trace && item == blockIdx.x + gridDim.x;
-    for (int kt0 = 0; kt0 < n_keys; kt0 += 128) {
-      if (skip_tile(kt0)) continue;
-      __syncthreads();
+    auto next_live = [&](int kt) { while (kt < n_keys && skip_tile(kt)) kt += 128; return kt; };
+    int kt0 = next_live(0), buf = 0;
+    int flags_cur = load_tile(kt0, 0);                 // (every item has at least one live tile: the diagonal / the chunk keys)
+    for (; kt0 < n_keys;) {
+      const int kt_next = next_live(kt0 + 128);
       if (tr_on) tk[0] = clock64();
-      const int lf = load_tile(kt0, true);
+      int flags_next = 0;
+      if (kt_next < n_keys) {                          // the next tile travels while this one is computed
+        flags_next = load_tile(kt_next, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
       if (tr_on) tk[1] = clock64();
-      const bool tf = mma_s(lf);
+      const bool tf = mma_s(flags_cur, buf);
       if (tr_on) tk[2] = clock64();
       float x[64];
-      logits(kt0, tf, x);
+      logits(kt0, tf, buf, x);
       if (tr_on) tk[3] = clock64();
-      if (n_tiles == 1) {
+      // online softmax: new running maximum, the accumulated O row and sum are rescaled when it moves
+      {
+        float mloc = kNegInf;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) mrow = fmaxf(mrow, x[j]);
-        pm[hf * 128 + r] = mrow;
+        for (int j = 0; j < 64; ++j) mloc = fmaxf(mloc, x[j]);
+        pm[hf * 128 + r] = mloc;
         __syncthreads();
-        mrow = fmaxf(pm[r], pm[128 + r]);
+        const float mnew = fmaxf(mrow, fmaxf(pm[r], pm[128 + r]));
+        const float alpha = (mnew == kNegInf || mrow == mnew) ? 1.f : ex2(mrow - mnew);      // exp2(-inf) = 0 for the first live tile
+        mrow = mnew;
+        lrow *= alpha;
+        if (!first && __any_sync(0xffffffffu, alpha != 1.f)) {
+          float o[32];
+          tmem_ld_cols<32>(trow + cO + 32 * hf, reinterpret_cast<uint32_t*>(o));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= alpha;
+          ptx::tmem_st16(trow + cO + 32 * hf, reinterpret_cast<const uint32_t*>(o));
+          ptx::tmem_st16(trow + cO + 32 * hf + 16, reinterpret_cast<const uint32_t*>(o) + 16);
+        }
       }
       const bool row_ok = qtok[r] >= 0 && mrow != kNegInf;
 #pragma unroll
@@ -252,6 +274,8 @@ eva_window_tc_kernel(const Params p) {
       if (tid == 0) {
         ptx::tc_fence_after();
 #pragma unroll
+        const uint64_t dV = dV0 + (uint64_t)((buf * kBuf) >> 4);
+#pragma unroll
         for (int ks = 0; ks < 8; ++ks) ptx::umma_ts(tmem + cO, tmem + cP + 8 * ks, dV + 128 * ks, id_pv, (first ? 0u : 1u) | (ks > 0 ? 1u : 0u));
         ptx::umma_commit(bar);
       }
@@ -260,9 +284,11 @@ eva_window_tc_kernel(const Params p) {
       ptx::mbar_wait(bar, ph & 1);                     // the tiles and the P columns are free again
       ++ph;
       ptx::tc_fence_after();
-      if (tr_on && blockIdx.x == 0 && (tid == 0 || tid == 200) && kt0 == 0)
-        printf("window tc trace tid %d: load %lld | sync+S mma %lld | logits %lld | exp+P+sync %lld | O mma %lld\n", tid, tk[1] - tk[0],
+      if (tr_on && blockIdx.x == 0 && (tid == 0 || tid == 200) && first_print)
+        printf("window tc trace tid %d: issue next + wait %lld | sync+S mma %lld | logits %lld | exp+P+sync %lld | O mma %lld\n", tid, tk[1] - tk[0],
                tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], clock64() - tk[4]);
+      first_print = false;
+      kt0 = kt_next; buf ^= 1; flags_cur = flags_next;
     }
     pl[hf * 128 + r] = lrow;
     __syncthreads();
