@@ -20,12 +20,15 @@ run memcheck cluster   "test_fused_kernel_many_items_per_cta_fp16 and 28-4-200"
 run memcheck fused14   "test_fused_kernel_many_items_per_cta_fp16 and 14-2"
 run memcheck causal    "test_causal_tcgen05_many_windows_per_cta_fp16"
 run memcheck lara      "test_lara_core_many_items_vs_oracle_fp16"
+run memcheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel"
 run memcheck bwd_tc    "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel"
 run memcheck bwd_simt  "test_backward_kernels_equal_autograd_through_the_recomputation"
 run racecheck fused28  "test_fused_kernel_variants_fp16 and 28-4-False and default and True-True"
 run racecheck cluster  "test_fused_kernel_variants_fp16 and 28-4-True and default and True-True"
 run racecheck causal   "test_causal_tcgen05_window_kernel_vs_oracle and 256-True-True and dtype0"
 run racecheck lara     "test_lara_core_only_prequantised_fp16_vs_oracle and True-False"
+run racecheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel and seq_shape3"
+run synccheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel and seq_shape3"
 run racecheck bwd_tc   "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape0"
 run racecheck bwd_simt "test_backward_kernels_equal_autograd_through_the_recomputation and seq_shape2"
 run synccheck bwd_tc   "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape0"
