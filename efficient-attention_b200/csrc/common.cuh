@@ -137,6 +137,59 @@ __device__ __forceinline__ int group_token(const Geo& g, int grp, int slot, int 
   return (p >= 0 && p < g.N) ? p : -1;
 }
 
+// ---- head_dim 64 vectors held as feature pairs (2 lane, 2 lane + 1): 4-byte loads of 16-bit rows ----------------------
+template <typename T> struct Pair16;
+template <> struct Pair16<__half> {
+  static __device__ __forceinline__ float2 up(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+template <> struct Pair16<__nv_bfloat16> {
+  static __device__ __forceinline__ float2 up(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+};
+
+// y = W x + b, x / y distributed as (2 lane, 2 lane + 1); Wt[in][out] in shared memory
+__device__ __forceinline__ float2 pair_linear(const float* __restrict__ Wt, const float* __restrict__ bias, float2 x, int lane) {
+  float2 y = bias ? __ldg(reinterpret_cast<const float2*>(bias) + lane) : make_float2(0.f, 0.f);
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float x0 = __shfl_sync(0xffffffffu, x.x, j), x1 = __shfl_sync(0xffffffffu, x.y, j);
+    const float2 w0 = *reinterpret_cast<const float2*>(Wt + (2 * j) * 64 + 2 * lane);
+    const float2 w1 = *reinterpret_cast<const float2*>(Wt + (2 * j + 1) * 64 + 2 * lane);
+    y.x = fmaf(w0.x, x0, fmaf(w1.x, x1, y.x));
+    y.y = fmaf(w0.y, x0, fmaf(w1.y, x1, y.y));
+  }
+  return y;
+}
+// dx = W^T dy, W row-major [out][in] in global memory (L1)
+__device__ __forceinline__ float2 pair_linear_bwd(const float* __restrict__ W, float2 dy, int lane) {
+  float2 dx = make_float2(0.f, 0.f);
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    const float d0 = __shfl_sync(0xffffffffu, dy.x, j), d1 = __shfl_sync(0xffffffffu, dy.y, j);
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W + (2 * j) * 64) + lane);
+    const float2 w1 = __ldg(reinterpret_cast<const float2*>(W + (2 * j + 1) * 64) + lane);
+    dx.x = fmaf(w0.x, d0, fmaf(w1.x, d1, dx.x));
+    dx.y = fmaf(w0.y, d0, fmaf(w1.y, d1, dx.y));
+  }
+  return dx;
+}
+// LayerNorm over 64 features held as pairs: normalised row and 1 / sigma
+__device__ __forceinline__ float2 pair_ln(float2 y, float eps, float& inv) {
+  const float mean = warp_sum(y.x + y.y) * (1.0f / 64);
+  const float cx = y.x - mean, cy = y.y - mean;
+  inv = 1.0f / sqrtf(warp_sum(cx * cx + cy * cy) * (1.0f / 64) + eps);
+  return make_float2(cx * inv, cy * inv);
+}
+__device__ __forceinline__ float2 pair_ln_bwd(float2 dout, float2 n, float inv, const float* __restrict__ gain, int lane) {
+  if (!gain) return dout;
+  const float2 gg = __ldg(reinterpret_cast<const float2*>(gain) + lane);
+  const float dx = dout.x * gg.x, dy = dout.y * gg.y;
+  const float s1 = warp_sum(dx + dy) * (1.0f / 64);
+  const float s2 = warp_sum(dx * n.x + dy * n.y) * (1.0f / 64);
+  return make_float2(inv * (dx - s1 - n.x * s2), inv * (dy - s1 - n.y * s2));
+}
+
 // logit of (query row li / token tq, key gj) after bias and masks, exactly as window_attn_kernel (eva_generic.cu); returns whether it still depends
 // on q . k (false: the forward overwrote it with a constant, so no gradient flows to q, k or the bias)
 __device__ __forceinline__ bool finish_logit(const Geo& g, float& sv, int flag, int gj, int li, int tq, int qpad,

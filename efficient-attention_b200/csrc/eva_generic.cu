@@ -323,6 +323,171 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stage A for head_dim 64 with 16-bit I/O and chunks of at most 128 slots (any geometry: halo, padding, 1-D / 2-D).  Same
+// semantics as chunk_stats_kernel with an order of magnitude fewer instructions per chunk: the token index of a slot is computed
+// by ONE lane per slot (not by every lane for every slot and pass), vectors are held as feature pairs (4-byte loads of the
+// 16-bit rows), and the per-token phi-logits run with lane = token (a 64-term dot product from the token's own 128-byte row
+// against omega in shared memory) -- two warp reductions per chunk instead of one per token.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastMaxJc = 128;
+
+// 8 consecutive features per lane (piece p8 = lane & 7 of a 128-byte row), partial over the tokens of sub-index ts = lane >> 3:
+// sum over the four ts groups, then hand lane l its feature pair (2l, 2l + 1)
+__device__ __forceinline__ float2 pieces_to_pair(float (&a)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 8);
+    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 16);
+  }
+  float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float x = __shfl_sync(0xffffffffu, a[2 * u], lane >> 2), y = __shfl_sync(0xffffffffu, a[2 * u + 1], lane >> 2);
+    if ((lane & 3) == u) r = make_float2(x, y);
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void add8(const uint4& raw, float w, float (&a)[8]) {
+  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float2 f = Pair16<T>::up(w4[u]);
+    a[2 * u] = fmaf(w, f.x, a[2 * u]); a[2 * u + 1] = fmaf(w, f.y, a[2 * u + 1]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_stats_fast_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                        const EvaAdaptive ada, const float* __restrict__ noise, float* __restrict__ kbar_out,
+                        float* __restrict__ beta_out) {
+  extern __shared__ float sm[];
+  float* WtK = sm;
+  float* WtQ = sm + 64 * 64;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int e = idx >> 6, i = idx & 63;
+    WtK[i * 64 + e] = __ldg(ada.w_k + idx);
+    if (ada.w_q) WtQ[i * 64 + e] = __ldg(ada.w_q + idx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* omv = sm + 2 * 64 * 64 + warp * 64;          // omega of the warp's chunk
+  const float scale = 0.125f;
+  const float inv_cnt = 1.0f / (float)g.Jc;
+  const int n_rounds = (g.Jc + 31) >> 5;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  for (long long wg = (long long)blockIdx.x * wpb + warp; wg < total; wg += (long long)gridDim.x * wpb) {
+    const int c = (int)(wg % g.n_chunks);
+    const int h = (int)((wg / g.n_chunks) % g.H);
+    const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+    const long long obase = wg * 64;
+    // token of slot 32 rd + lane: -1 when off the sequence or padded (such slots count as zeros)
+    int tokr[4];
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      const int s = 32 * rd + lane;
+      int t = (rd < n_rounds && s < g.Jc) ? group_token(g, c, s, g.chunk, g.chunk_ext) : -1;
+      if (t >= 0 && mask && mask[(long long)b * g.N + t]) t = -1;
+      tokr[rd] = t;
+    }
+    // ---- chunk means: lane = (token sub-index ts, 16-byte piece p8), four tokens per load instruction ----
+    const int ts = lane >> 3, p8 = lane & 7;
+    float aq[8], ak[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aq[i] = ak[i] = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      if (rd >= n_rounds) break;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int t = __shfl_sync(0xffffffffu, tokr[rd], 4 * i + ts);
+        if (t < 0) continue;
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(q.row<T>(b, t, h)) + p8), 1.f, aq);
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + p8), 1.f, ak);
+      }
+    }
+    float2 sq = pieces_to_pair(aq, lane), sk = pieces_to_pair(ak, lane);
+    sq.x *= inv_cnt; sq.y *= inv_cnt; sk.x *= inv_cnt; sk.y *= inv_cnt;
+    // ---- k_bar, omega ----
+    float inv_unused;
+    float2 kb = pair_linear(WtK, ada.b_k, sk, lane);
+    if (ada.ln_gain_k) {
+      const float2 n = pair_ln(kb, ada.ln_eps, inv_unused);
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_k) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_k) + lane);
+      kb = make_float2(fmaf(n.x, gg.x, bb.x), fmaf(n.y, gg.y, bb.y));
+    }
+    float2 om = make_float2(0.f, 0.f);
+    if (ada.w_q) {
+      float2 qb = pair_linear(WtQ, ada.b_q, sq, lane);
+      if (ada.ln_gain_q) {
+        const float2 n = pair_ln(qb, ada.ln_eps, inv_unused);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_q) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_q) + lane);
+        qb = make_float2(fmaf(n.x, gg.x, bb.x), fmaf(n.y, gg.y, bb.y));
+      }
+      om = make_float2(ada.mu_coeff * (qb.x + kb.x), ada.mu_coeff * (qb.y + kb.y));
+    }
+    if (noise) { const float2 z = __ldg(reinterpret_cast<const float2*>(noise + obase) + lane); om.x += z.x; om.y += z.y; }
+    reinterpret_cast<float2*>(kbar_out + obase)[lane] = kb;
+    __syncwarp();
+    reinterpret_cast<float2*>(omv)[lane] = om;
+    __syncwarp();
+    // ---- phi-logits (lane = token): scale (omega . k - |k|^2 / 2); padded / off-sequence slots: -5e4 ----
+    float lg[4];
+    float mx = kNegInf;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      lg[rd] = kNegInf;
+      if (rd >= n_rounds) continue;
+      if (32 * rd + lane < g.Jc) {
+        lg[rd] = kMaskVal;
+        const int t = tokr[rd];
+        if (t >= 0) {
+          const uint4* kr = reinterpret_cast<const uint4*>(k.row<T>(b, t, h));
+          float part = 0.f;
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            const uint4 raw = __ldg(kr + pc);
+            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+            const float4 o0 = *reinterpret_cast<const float4*>(omv + 8 * pc), o1 = *reinterpret_cast<const float4*>(omv + 8 * pc + 4);
+            const float oo[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 kk = Pair16<T>::up(w4[u]);
+              part = fmaf(kk.x, oo[2 * u] - 0.5f * kk.x, fmaf(kk.y, oo[2 * u + 1] - 0.5f * kk.y, part));
+            }
+          }
+          lg[rd] = scale * part;
+        }
+      }
+      mx = fmaxf(mx, lg[rd]);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) { lg[rd] = exp_nonpos(lg[rd] - mx); den += lg[rd]; }     // exp(-inf) = 0 on slots that do not exist
+    const float inv_l = 1.0f / warp_sum(den);
+    // ---- beta = sum_t softmax_t v_t: same four-tokens-per-instruction layout ----
+    float av[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) av[i] = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      if (rd >= n_rounds) break;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int t = __shfl_sync(0xffffffffu, tokr[rd], 4 * i + ts);
+        const float a = __shfl_sync(0xffffffffu, lg[rd], 4 * i + ts);
+        if (t < 0) continue;
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(v.row<T>(b, t, h)) + p8), a, av);
+      }
+    }
+    const float2 acc = pieces_to_pair(av, lane);
+    reinterpret_cast<float2*>(beta_out + obase)[lane] = make_float2(acc.x * inv_l, acc.y * inv_l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stage B: CTA = (batch*head, window, block of 16 query rows); keys = local window slots followed by
 // the chunk keys (k_bar / beta); key tiles of 32 staged in smem, online softmax per query row.
 // ------------------------------------------------------------------------------------------------
@@ -505,6 +670,20 @@ static cudaError_t launch_chunk_stats_t(const Geo& g, const View& q, const View&
       }
       const long long total_cta = (long long)g.B * g.H * g.n_chunks;
       chunk_stats_cta_kernel<T><<<(unsigned)total_cta, 256, smem_cta, st>>>(g, q, k, v, ada, noise, kbar, beta);
+      return cudaGetLastError();
+    }
+  }
+  if constexpr (D == 64 && sizeof(T) == 2) {
+    static const bool slow_only = [] { const char* e = getenv("EVA_SM100_STATS_GENERIC"); return e && e[0] == '1'; }();
+    if (!slow_only && g.Jc <= kFastMaxJc) {
+      auto kf = chunk_stats_fast_kernel<T>;
+      const size_t smf = (2 * 64 * 64 + 8 * 64) * sizeof(float);
+      cudaError_t ef = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
+      if (ef != cudaSuccess) return ef;
+      const long long total_f = (long long)g.B * g.H * g.n_chunks;
+      long long blocks_f = (total_f + 7) / 8;
+      if (blocks_f > 148LL * 16) blocks_f = 148LL * 16;
+      kf<<<(unsigned)blocks_f, 256, smf, st>>>(g, q, k, v, mask, ada, noise, kbar, beta);
       return cudaGetLastError();
     }
   }

@@ -887,3 +887,36 @@ def test_tcgen05_window_kernel_matches_the_cuda_core_kernel(seq_shape, window, e
     assert torch.isfinite(got[live]).all()
     tol = 2e-3 if dtype == torch.float16 else 1.2e-2
     assert rel_l2(got[live], want[live]) < tol, rel_l2(got[live], want[live])
+
+
+@pytest.mark.parametrize('seq_shape,chunk,chunk_ext,causal,with_mask,dtype', [
+    ((14, 14), 2, 3, False, False, torch.float16), ((28, 28), 4, 3, False, False, torch.bfloat16), ((28, 28), 4, 0, False, False, torch.float16),
+    ((96,), 12, 8, False, True, torch.float16), ((1024,), 16, 32, False, True, torch.float16), ((128,), 16, 0, True, True, torch.bfloat16),
+    ((90,), 45, 40, False, True, torch.float16)])
+def test_fast_chunk_statistics_kernel_matches_the_generic_one(seq_shape, chunk, chunk_ext, causal, with_mask, dtype):
+    """chunk_stats_fast_kernel (head_dim 64, 16-bit I/O, <= 128 slots per chunk) against chunk_stats_kernel: the same 16-bit values
+    handed over as float32 take the generic kernel; both compute in float32."""
+    from efficient_attention import _abi
+    dev = torch.device('cuda', 0)
+    B, H, d = 3, 2, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + chunk + chunk_ext)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dtype).to(dev)
+    mask = None
+    if with_mask:
+        mask = torch.zeros(B, N, dtype=torch.bool, device=dev)
+        mask[1, N - 9:] = True
+        mask[2, :5] = True
+    ada = _abi_ada(_rand_ada(d, g), dev, 1.0 if causal else 0.5)
+    window = chunk * 2 if N % (chunk * 2) == 0 else chunk
+    geometry = dict(seq_shape=seq_shape, window=window if len(seq_shape) == 1 else 7, ext=0, chunk=chunk, chunk_ext=chunk_ext, causal=causal,
+                    halo_left_only=causal)
+    noise = None
+
+    def stats(x):
+        q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]
+        geom = _abi.eva_geometry(q, **geometry)
+        nz = torch.randn(B, H, _abi.num_chunks(geom), d, generator=torch.Generator().manual_seed(1)).to(dev)
+        return _abi.eva_chunk_stats(q, k, v, geom, ada, pad_mask=mask, noise=nz)
+    (kb, bt), (kb32, bt32) = stats(qkv), stats(qkv.float())
+    assert rel_l2(kb.cpu(), kb32.cpu()) < 1e-5 and rel_l2(bt.cpu(), bt32.cpu()) < 1e-5, (rel_l2(kb.cpu(), kb32.cpu()), rel_l2(bt.cpu(), bt32.cpu()))
