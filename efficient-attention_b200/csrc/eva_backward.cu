@@ -762,6 +762,8 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
   };
   if (window_bwd_tc_supported(g, io_dtype, mask)) {
     e = launch_window_bwd_tc(g, io_dtype, q, k, v, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
+  } else if (window_bwd_gen_supported(g, io_dtype)) {
+    e = launch_window_bwd_gen(g, io_dtype, q, k, v, mask, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
   } else {
     auto kern = window_attn_bwd_kernel<T, D>;
     const size_t smem = BwdSmem<D>::kBytes;

@@ -344,9 +344,14 @@ static cudaError_t launch_t(const Params& p, cudaStream_t st) {
 static int g_bwd_tc_count = 0;
 static int g_bwd_tc_mode = -1;   // -1: environment (EVA_SM100_BWD_SIMT=1 disables), 0: off, 1: on
 
-bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask) {
+bool bwd_tc_enabled() {
   static const bool env_off = [] { const char* e = getenv("EVA_SM100_BWD_SIMT"); return e && e[0] == '1'; }();
-  if (g_bwd_tc_mode == 0 || (g_bwd_tc_mode < 0 && env_off)) return false;
+  return !(g_bwd_tc_mode == 0 || (g_bwd_tc_mode < 0 && env_off));
+}
+void note_bwd_tc_launch() { ++g_bwd_tc_count; }
+
+bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask) {
+  if (!bwd_tc_enabled()) return false;
   return g.D == 64 && (io_dtype == EVA_F16 || io_dtype == EVA_BF16) && !mask && !g.causal && g.ext == 0 && g.chunk_ext == 0 &&
          g.L <= 64 && g.J == g.L && g.n_chunks >= 1 && g.n_chunks <= 64 &&
          (long long)g.B * g.H * g.n_windows <= 0x7fffffffLL;

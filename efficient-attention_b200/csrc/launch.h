@@ -63,6 +63,15 @@ cudaError_t launch_window_bwd_tc(const Geo& g, int io_dtype, const View& q, cons
                                  const float* beta, const float* bias, long long bias_sh, const void* out, const void* dout,
                                  float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias, cudaStream_t st);
 
+// tcgen05 window-attention backward for every other geometry with head_dim 64 and 16-bit I/O (eva_window_bwd_gen_sm100.cu)
+bool bwd_tc_enabled();
+void note_bwd_tc_launch();
+bool window_bwd_gen_supported(const Geo& g, int io_dtype);
+cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                                  const float* kbar, const float* beta, const float* bias, long long bias_sh, const void* out,
+                                  const void* dout, float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias,
+                                  cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

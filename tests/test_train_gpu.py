@@ -184,6 +184,67 @@ def test_forward_keeps_the_chunk_statistics_for_the_backward(seq_shape, window, 
     assert rel_l2(k_bar.cpu(), kb.cpu()) < tol and rel_l2(beta.cpu(), bt.cpu()) < tol, (rel_l2(k_bar.cpu(), kb.cpu()), rel_l2(beta.cpu(), bt.cpu()))
 
 
+@pytest.mark.parametrize('seq_shape,window,ext,chunk,causal,with_mask,dtype', [
+    ((14, 14), 7, 3, 2, False, False, torch.float16), ((96,), 16, 8, 12, False, True, torch.float16),
+    ((512,), 128, 128, 64, True, True, torch.float16), ((512,), 256, 0, 256, True, False, torch.bfloat16),
+    ((14, 14), 7, 0, 0, False, False, torch.float16), ((197,), 197, 0, 0, False, True, torch.float16),
+    ((400,), 400, 0, 0, False, False, torch.bfloat16), ((28, 28), 14, 0, 4, False, False, torch.float16)])
+def test_generic_tcgen05_backward_kernel_matches_the_cuda_core_kernel(seq_shape, window, ext, chunk, causal, with_mask, dtype):
+    """eva_window_bwd_gen_sm100.cu (any geometry, head_dim 64, 16-bit) against window_attn_bwd_kernel (float32 CUDA cores) on
+    identical 16-bit inputs: gradients of q, k, v, the bias table and (with chunks) the adaptive parameters."""
+    from efficient_attention import _abi, _recompute
+    from test_gpu_parity import _rand_ada
+    dev = _dev()
+    lib = _abi.load()
+    B, H, d = 2, 2, 64
+    N = math.prod(seq_shape)
+    g = torch.Generator().manual_seed(N + window + ext + chunk)
+    qkv = torch.randn(B, N, 3, H, d, generator=g).to(dev, dtype)
+    two_d = len(seq_shape) == 2
+    L = window * window if two_d else window
+    J = (window + 2 * ext) ** 2 if two_d else window + (ext if causal else 2 * ext)
+    bias = (0.5 * torch.randn(H, L, J, generator=g)).to(dev) if L * J <= 1 << 16 else None
+    mask = None
+    if with_mask:
+        mask = torch.zeros(B, N, dtype=torch.bool, device=dev)
+        mask[1, N - 9:] = True
+    names = ('wq', 'bq', 'gq', 'betq', 'wk', 'bk', 'gk', 'betk')
+    ada = {k_: v_.to(dev) for k_, v_ in _rand_ada(d, g).items()}
+    w = torch.randn(B, N, H * d, generator=g).to(dev)
+    if mask is not None and causal:
+        w = w * (~mask).unsqueeze(-1)                     # padded queries of the causal layer are don't-care rows
+    softmax_like = chunk == 0 and window == N
+    if chunk:
+        noise = torch.randn(B, H, _recompute.num_chunks_of(seq_shape, chunk), d, generator=g).to(dev)
+        geometry = dict(seq_shape=seq_shape, window=window, ext=ext, chunk=chunk, chunk_ext=0 if causal else ext, causal=causal,
+                        halo_left_only=causal, mask_queries=causal)
+    else:
+        geometry = dict(seq_shape=seq_shape, window=window, ext=ext, chunk=0, chunk_ext=0, mask_is_neg_inf=softmax_like)
+
+    def run(mode):
+        lib.eva_debug_set_bwd_tc(mode)
+        try:
+            before = lib.eva_debug_bwd_tc_count()
+            x = qkv.clone().requires_grad_(True)
+            b_ = bias.clone().requires_grad_(True) if bias is not None else None
+            prm = [ada[n_].clone().requires_grad_(True) for n_ in names]
+            if chunk:
+                out = _recompute.eva_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, mu_coeff=1.0 if causal else 0.5,
+                                          params=prm, pad_mask=mask, noise=noise, bias=b_)
+            else:
+                out = _recompute.window_core(x[:, :, 0], x[:, :, 1], x[:, :, 2], geometry=geometry, pad_mask=mask, bias=b_)
+            (out.float() * w).sum().backward()
+            assert lib.eva_debug_bwd_tc_count() - before == mode
+            return [x.grad.float()] + ([b_.grad] if b_ is not None else []) + ([p_.grad for p_ in prm] if chunk else [])
+        finally:
+            lib.eva_debug_set_bwd_tc(-1)
+    got, want = run(1), run(0)
+    labels = ('qkv',) + (('bias',) if bias is not None else ()) + (names if chunk else ())
+    for n_, a_, b_ in zip(labels, got, want):
+        assert torch.isfinite(a_).all(), n_
+        assert rel_l2(a_.cpu(), b_.cpu()) < (3e-3 if dtype == torch.float16 else 1.5e-2), (n_, rel_l2(a_.cpu(), b_.cpu()))
+
+
 def _grads_of(module, cfg, a, dev, dtype):
     """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
     x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
