@@ -31,8 +31,8 @@ using fused::ex2;
 
 constexpr int kThreads = 256;
 constexpr int kQ = 0, kG = 16384, kK = 32768, kV = 49152, kP = 65536, kdS = 98304, kMisc = 131072;
-constexpr int kFac = kMisc, kKtok = kFac + 1024, kQtok = kKtok + 512, kQpad = kQtok + 512, kDelta = kQpad + 512, kPm = kDelta + 512,
-              kPl = kPm + 1024, kBar = kPl + 1024, kSlot = kBar + 16, kSmemBytes = kSlot + 16 + 1024;
+constexpr int kFac = kMisc, kKtok = kFac + 2048, kQtok = kKtok + 512, kQpad = kQtok + 512, kDelta = kQpad + 512, kPm = kDelta + 512,
+              kPl = kPm + 1024, kBiasT = kPl + 1024, kBar = kBiasT + 8 * 32 * 17 * 4, kSlot = kBar + 16, kSmemBytes = kSlot + 16 + 1024;
 constexpr uint32_t kTmemCols = 512, cS = 0, cDP = 128, cDQ = 256, cDK = 320, cDV = 384;
 
 struct Params {
@@ -44,6 +44,7 @@ struct Params {
   const void* out; const void* dout;
   float* dq; float* dk; float* dv; float* dkbar; float* dbeta; float* dbias;
   long long total;
+  int trace;
 };
 
 template <typename T>
@@ -53,13 +54,16 @@ eva_window_bwd_gen_kernel(const Params p) {
   uint8_t* sm = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo& g = p.g;
-  float2* kfac = reinterpret_cast<float2*>(sm + kFac);   // [128] per key: (1, 0) live | (0, mask_fill) masked | (0, -inf) absent
+  // [128] per key: logit = s * mul + add with (1, 0) live | (0, mask_fill) masked | (0, -inf) absent, and the causal rule as two
+  // thresholds: overwritten by -5e4 when row index < thr_row (local keys: key slot - halo) or row chunk < thr_chunk (chunk keys: c + 1)
+  float4* kfac = reinterpret_cast<float4*>(sm + kFac);
   int* ktok = reinterpret_cast<int*>(sm + kKtok);        // [128] destination of a key's gradient: token >= 0 | -1 none | -2 - c chunk c
   int* qtok = reinterpret_cast<int*>(sm + kQtok);
   int* qpad = reinterpret_cast<int*>(sm + kQpad);
   float* delta = reinterpret_cast<float*>(sm + kDelta);
   float* pm = reinterpret_cast<float*>(sm + kPm);        // [2][128]
   float* pl = reinterpret_cast<float*>(sm + kPl);        // [2][128]
+  float* biasT = reinterpret_cast<float*>(sm + kBiasT);  // [8 warps][32][17] bias transposition
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + kSlot);
   const uint32_t bar = ptx::smem_u32(sm + kBar);
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(slot), kTmemCols);
@@ -160,7 +164,11 @@ eva_window_bwd_gen_kernel(const Params p) {
         if (with_v) *reinterpret_cast<uint4*>(sm + kV + off) = zv;
         if (piece == 0) {
           ktok[j] = dest;
-          kfac[j] = flag == 0 ? make_float2(1.f, 0.f) : make_float2(0.f, flag == 1 ? g.mask_fill : kNegInf);
+          const int never = -2147483647 - 1;
+          const int thr_row = (g.causal && gj < g.J) ? gj - g.ext : never;
+          const int thr_chunk = (g.causal && gj >= g.J && gj < n_keys) ? gj - g.J + 1 : never;
+          kfac[j] = make_float4(flag == 0 ? 1.f : 0.f, flag == 0 ? 0.f : (flag == 1 ? g.mask_fill : kNegInf), __int_as_float(thr_row),
+                                __int_as_float(thr_chunk));
         }
         flags |= flag;
       }
@@ -203,33 +211,50 @@ eva_window_bwd_gen_kernel(const Params p) {
         return;
       }
       const int c0 = kt0 + 64 * hf;
-      const float2* kf = kfac + 64 * hf;
+      const float4* kf = kfac + 64 * hf;
+      const bool any_row_masked = __any_sync(0xffffffffu, row_masked);
       live[0] = live[1] = 0u;
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         float bb[16];
+        if (p.bias) {                                  // coalesced: two rows x 16 columns per load instruction, transposed through
+          float* tb = biasT + warp * (32 * 17);        // shared memory (a per-thread row read would touch 32 lines per instruction)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int gj = c0 + 16 * blk + e;
-          bb[e] = (brow && gj < g.J) ? __ldg(brow + gj) : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            const int row = 2 * i + (lane >> 4), col = lane & 15;
+            const int li2 = rb * 128 + 32 * qr + row, gj = c0 + 16 * blk + col;
+            tb[row * 17 + col] = (li2 < g.L && gj < g.J) ? __ldg(p.bias + bias_off + (long long)li2 * g.J + gj) : 0.f;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bb[e] = tb[lane * 17 + e];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bb[e] = 0.f;
         }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int j = 16 * blk + e, gj = c0 + j;
-          const float2 f = kf[j];
+          const int j = 16 * blk + e;
+          const float4 f = kf[j];
           float sv = fmaf(fmaf(x[j], scale, bb[e]), f.x, f.y);
+          const bool cm = (li_row < __float_as_int(f.z)) | (tq_chunk < __float_as_int(f.w));
           bool lv = f.x != 0.f;
-          if (gj < g.J) {
-            if (row_masked) { sv = g.mask_fill; lv = false; }
-            if (g.causal && gj > li_row + g.ext) { sv = kMaskVal; lv = false; }
-          } else if (g.causal && gj < n_keys && (gj - g.J) >= tq_chunk) {
-            sv = kMaskVal; lv = false;
+          if (any_row_masked) {                        // padded query rows of the causal layer (warp-uniform branch)
+            const bool rm = row_masked && (c0 + j < g.J);
+            sv = rm ? g.mask_fill : sv;
+            lv = lv && !rm;
           }
+          sv = cm ? kMaskVal : sv;
+          lv = lv && !cm;
           x[j] = sv * kLog2e;
           live[j >> 5] |= (lv ? 1u : 0u) << (j & 31);
         }
       }
     };
+    long long tk[8];
+    const bool tr_on = p.trace && item == blockIdx.x + gridDim.x && blockIdx.x == 0;
+    if (tr_on) tk[0] = clock64();
     // ---- pass 0: lse of every row ----
     float mrow = kNegInf, lrow = 0.f;
     for (int kt0 = 0; kt0 < n_keys; kt0 += 128) {
@@ -262,13 +287,19 @@ eva_window_bwd_gen_kernel(const Params p) {
     float* dbrow = (p.dbias && tq_row >= 0) ? p.dbias + bias_off + (long long)li_row * g.J : nullptr;
     // ---- pass 1 ----
     bool first = true;
+    if (tr_on) tk[1] = clock64();
     for (int kt0 = 0; kt0 < n_keys; kt0 += 128) {
       if (skip_tile(kt0)) continue;
       __syncthreads();
-      const bool tf = mma_s(load_tile(kt0, true), true);
+      if (tr_on) tk[2] = clock64();
+      const int lf = load_tile(kt0, true);
+      if (tr_on) tk[3] = clock64();
+      const bool tf = mma_s(lf, true);
+      if (tr_on) tk[4] = clock64();
       float x[64];
       uint32_t live[2];
       logits(kt0, tf, x, live);
+      if (tr_on) tk[5] = clock64();
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         float dp[16];
@@ -295,6 +326,7 @@ eva_window_bwd_gen_kernel(const Params p) {
         *reinterpret_cast<uint4*>(sm + kP + o0) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
         *reinterpret_cast<uint4*>(sm + kP + o1) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
       }
+      if (tr_on) tk[6] = clock64();
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       __syncthreads();
@@ -313,6 +345,7 @@ eva_window_bwd_gen_kernel(const Params p) {
       ptx::mbar_wait(bar, ph & 1);
       ++ph;
       ptx::tc_fence_after();
+      if (tr_on) tk[7] = clock64();
       // dK / dV rows of the tile: lane = key row
       {
         float y[32], z[32];
@@ -339,6 +372,9 @@ eva_window_bwd_gen_kernel(const Params p) {
         }
       }
       ptx::tc_fence_before();
+      if (tr_on && (tid == 0 || tid == 200) && kt0 == 0)
+        printf("bwd gen trace tid %d: pass0 %lld | load %lld | S,dP mma %lld | logits %lld | P,dS %lld | mma2 %lld | dK,dV out %lld\n", tid,
+               tk[1] - tk[0], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], clock64() - tk[7]);
     }
     // ---- dQ rows ----
     {
@@ -375,6 +411,8 @@ cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, con
   p.out = out; p.dout = dout;
   p.dq = dq; p.dk = dk; p.dv = dv; p.dkbar = dkbar; p.dbeta = dbeta; p.dbias = dbias;
   p.total = (long long)((g.L + 127) / 128) * g.n_windows * g.B * g.H;
+  static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.trace = trace;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

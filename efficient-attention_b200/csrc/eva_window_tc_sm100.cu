@@ -29,7 +29,7 @@ using fused::ex2;
 
 constexpr int kThreads = 256;
 constexpr int kQ = 0, kK = 16384, kV = 32768, kBuf = 32768, kMisc = 81920;   // K / V tiles of buffer 1 at + kBuf
-constexpr int kFlag = kMisc, kFac = kFlag + 1024, kQtok = kFac + 2048, kQpad = kQtok + 512, kPm = kQpad + 512, kPl = kPm + 1024, kBar = kPl + 1024,
+constexpr int kFlag = kMisc, kFac = kFlag + 1024, kQtok = kFac + 4096, kQpad = kQtok + 512, kPm = kQpad + 512, kPl = kPm + 1024, kBiasT = kPl + 1024, kBar = kBiasT + 8 * 32 * 17 * 4,
               kSlot = kBar + 16, kSmemBytes = kSlot + 16 + 1024;
 constexpr uint32_t kTmemCols = 256, cS = 0, cP = 128, cO = 192;
 
@@ -52,11 +52,14 @@ eva_window_tc_kernel(const Params p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Geo& g = p.g;
   int* kflag_all = reinterpret_cast<int*>(sm + kFlag); // [2][128] per buffer: 0 live, 1 masked, 2 absent
-  float2* kfac_all = reinterpret_cast<float2*>(sm + kFac);   // [2][128] the same as (multiplier, addend): logit = s * mul + add
+  // [2][128] per key: logit = s * mul + add with (1, 0) live | (0, mask_fill) masked | (0, -inf) absent, and the causal rule as two
+  // thresholds: overwritten by -5e4 when row index < thr_row (local keys: key slot - halo) or row chunk < thr_chunk (chunk keys: c + 1)
+  float4* kfac_all = reinterpret_cast<float4*>(sm + kFac);
   int* qtok = reinterpret_cast<int*>(sm + kQtok);      // [128] token of the row, -1: no such row
   int* qpad = reinterpret_cast<int*>(sm + kQpad);
   float* pm = reinterpret_cast<float*>(sm + kPm);      // [2][128]
   float* pl = reinterpret_cast<float*>(sm + kPl);      // [2][128]
+  float* biasT = reinterpret_cast<float*>(sm + kBiasT);   // [8 warps][32][17] bias transposition
   uint32_t* slot = reinterpret_cast<uint32_t*>(sm + kSlot);
   const uint32_t bar = ptx::smem_u32(sm + kBar);
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(slot), kTmemCols);
@@ -135,7 +138,11 @@ eva_window_tc_kernel(const Params p) {
         }
         if (piece == 0) {
           kflag[j] = flag;
-          kfac_all[128 * buf + j] = flag == 0 ? make_float2(1.f, 0.f) : make_float2(0.f, flag == 1 ? g.mask_fill : kNegInf);
+          const int never = -2147483647 - 1;
+          const int thr_row = (g.causal && gj < g.J) ? gj - g.ext : never;
+          const int thr_chunk = (g.causal && gj >= g.J && gj < n_keys) ? gj - g.J + 1 : never;
+          kfac_all[128 * buf + j] = make_float4(flag == 0 ? 1.f : 0.f, flag == 0 ? 0.f : (flag == 1 ? g.mask_fill : kNegInf),
+                                                __int_as_float(thr_row), __int_as_float(thr_chunk));
         }
         flags |= flag;
       }
@@ -176,36 +183,44 @@ eva_window_tc_kernel(const Params p) {
         return;
       }
       const int c0 = kt0 + 64 * hf;
-      const float2* kf = kfac_all + 128 * buf + 64 * hf;       // per key: (1, 0) live | (0, mask_fill) masked | (0, -inf) absent
+      const float4* kf = kfac_all + 128 * buf + 64 * hf;
       const bool row_masked = g.mask_queries && qp_row;
-      if (!rules || (!brow && !g.causal && !row_masked)) {     // flags only: one broadcast read and two FMAs per column
+      if (!rules) {                                    // flags only (warp-uniform choice): one broadcast read and two FMAs per column
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-          const float2 f = kf[j];
+          const float4 f = kf[j];
           x[j] = fmaf(x[j] * scale, f.x, f.y) * kLog2e;
         }
         return;
       }
+      const bool any_row_masked = __any_sync(0xffffffffu, row_masked);
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         float bb[16];
+        if (p.bias) {                                  // coalesced: two rows x 16 columns per load instruction, transposed through
+          float* tb = biasT + warp * (32 * 17);        // shared memory (a per-thread row read would touch 32 lines per instruction)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {                 // independent loads first, the rules afterwards
-          const int gj = c0 + 16 * blk + e;
-          bb[e] = (brow && gj < g.J) ? __ldg(brow + gj) : 0.f;
+          for (int i = 0; i < 16; ++i) {
+            const int row = 2 * i + (lane >> 4), col = lane & 15;
+            const int li2 = rb * 128 + 32 * qr + row, gj = c0 + 16 * blk + col;
+            tb[row * 17 + col] = (li2 < g.L && gj < g.J) ? __ldg(p.bias + bias_off + (long long)li2 * g.J + gj) : 0.f;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bb[e] = tb[lane * 17 + e];
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bb[e] = 0.f;
         }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int j = 16 * blk + e, gj = c0 + j;
-          const float2 f = kf[j];
+          const int j = 16 * blk + e;
+          const float4 f = kf[j];
           float sv = fmaf(fmaf(x[j], scale, bb[e]), f.x, f.y);
-          if (gj < g.J) {
-            if (row_masked) sv = g.mask_fill;
-            if (g.causal && gj > li_row + g.ext) sv = kMaskVal;
-          } else if (g.causal && gj < n_keys && (gj - g.J) >= tq_chunk) {
-            sv = kMaskVal;
-          }
-          x[j] = sv * kLog2e;
+          const bool cm = (li_row < __float_as_int(f.z)) | (tq_chunk < __float_as_int(f.w));
+          if (any_row_masked) sv = (row_masked && (c0 + j < g.J)) ? g.mask_fill : sv;       // padded query rows of the causal layer
+          x[j] = (cm ? kMaskVal : sv) * kLog2e;
         }
       }
     };

@@ -26,7 +26,7 @@ def main():
     noise = torch.randn(B, H, N // w, d, generator=g).to(dev)
     bias = (0.1 * torch.randn(1, w, 2 * w, generator=g)).to(dev)
     ext = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # 0: overlap_window=False (the c5 configuration); 256: overlapping windows
-    bias = bias[:, :, :w + ext].contiguous()
+    bias = bias[:, :, :w + ext].contiguous() if os.environ.get('NO_BIAS') != '1' else None
     geometry = dict(seq_shape=(N,), window=w, ext=ext, chunk=w, chunk_ext=0, causal=True, halo_left_only=True, mask_queries=True)
     wgt = torch.randn(B, N, H * d, generator=g).to(dev, torch.float16)
     for impl in ('cuda', 'torch'):
