@@ -465,6 +465,59 @@ def deit_leg(dev, world, batch=128, warm=20, steps=100):
     return out
 
 
+def other_shapes_leg(dev):
+    """The other BASELINE.json configurations on THIS package (rank 0, one GPU): module forward (qkv / proj GEMMs + attention core, what
+    the reference's `module(x)` does) in fp16 with inputs resident in HBM, CUDA-event timed; `module_traffic_gbs_of_peak` relates the
+    module's algorithmic traffic (10 C x 2 bytes per token) to the measured HBM peak."""
+    import warnings
+    from argparse import Namespace
+    import efficient_attention as ea
+    from efficient_attention import _abi
+    peak, _ = peaks()
+    out = {}
+
+    def timed(fn, n=20, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.median(a.elapsed_time(b) for a, b in evs)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        torch.manual_seed(0)
+        eva = lively_init(ea.AttentionFactory.build_attention('eva', dict(EVA_ARGS))).to(dev).half().eval()
+        lara = lively_init(ea.AttentionFactory.build_attention('lara', dict(
+            dim=384, num_heads=6, num_landmarks=49, proposal_gen='pool-mixed', mis_type='mis-opt', alpha_coeff=2.0))).to(dev).half().eval()
+        causal = lively_init(ea.CausalEVAttention(512, 8, self_attention=True, attn_args=Namespace(
+            adaptive_proj='qk', num_chunks=None, chunk_size=256, causal=True, use_t5_rpe=True, window_size=256,
+            overlap_window=False))).to(dev).half().eval()
+    cases = [('c1', 'EVA N=196, C=192, batch 2 (the reference\'s CPU-runnable case)', lambda x: eva(x), (2, 14, 14, DIM), 196 * 2, DIM),
+             ('c2', 'EVA N=196, C=192, batch 2048 (DeiT-tiny-p16)', lambda x: eva(x), (2048, 14, 14, DIM), 196 * 2048, DIM),
+             ('c4', 'LARA N=196, C=384, h=6, batch 512 (DeiT-small-p16)', lambda x: lara(x), (512, 14, 14, 384), 196 * 512, 384),
+             ('c5', 'causal EVA T=4096, C=512, h=8, window = chunk = 256, batch 16', lambda x: causal(x, x, x, need_weights=False), (4096, 16, 512),
+              4096 * 16, 512)]
+    for tag, what, call, shape, tokens, C in cases:
+        try:
+            torch.manual_seed(1)
+            x = torch.randn(*shape, device=dev, dtype=torch.float16)
+            with torch.no_grad():
+                ms = timed(lambda: call(x))
+            out[tag] = {'what': what, 'module_ms': ms, 'module_tokens_per_s': tokens / (ms * 1e-3),
+                        'module_traffic_gbs_of_peak': (10 * C * 2 * tokens) / (ms * 1e-3) / 1e9 / peak}
+            del x
+        except Exception as e:
+            out[tag] = {'what': what, 'error': f'{type(e).__name__}: {e}'[:200]}
+    out['note'] = ('module = qkv Linear + attention core + proj Linear, fp16, inputs resident in HBM; module_traffic_gbs_of_peak = '
+                   '10 C x 2 bytes per token (x in, qkv out + in, o out + in, y out) / time / measured HBM peak')
+    return out
+
+
 def run_ours(args):
     use_product_package()
     import torch.distributed as dist
@@ -610,6 +663,12 @@ def run_ours(args):
         del q, k, v, x_dev
         torch.cuda.empty_cache()
         deit = deit_leg(dev, world, steps=args.deit_steps)
+    shapes = None
+    if rank == 0 and world == 1 and not args.no_deit:
+        try:
+            shapes = other_shapes_leg(dev)
+        except Exception as e:
+            shapes = {'error': f'{type(e).__name__}: {e}'[:300]}
 
     if rank == 0:
         tokens_per_step = aggregate_tokens(B, world)
@@ -656,6 +715,8 @@ def run_ours(args):
             out['sustained'] = sustained
         if deit is not None:
             out['deit_p8'] = deit
+        if shapes is not None:
+            out['other_shapes'] = shapes
         if world == 1 and not args.no_cpu:
             out['cpu_baseline'] = cpu_baseline_subprocess()
         print(json.dumps(out))

@@ -66,7 +66,14 @@ def _take_mask(mask, idx):
 
 def _linear_ln(x, w, b, g, beta, eps):
     y = F.linear(x, w, b)
-    return y if g is None else F.layer_norm(y, (y.shape[-1],), g, beta, eps)
+    if g is None:
+        return y
+    # LayerNorm spelled out: the gain / bias gradients then are plain sum reductions.  (F.layer_norm's weight-gradient kernel takes
+    # ~0.2 ms per call on the [B * H * C, 64] landmark rows -- 4 ms of a DeiT-small + LARA training step.)
+    yf = y.float()
+    mu = yf.mean(-1, keepdim=True)
+    var = yf.var(-1, unbiased=False, keepdim=True)
+    return (yf - mu) * torch.rsqrt(var + eps) * g.float() + beta.float()
 
 
 def eva_core_torch(q, k, v, *, seq_shape, window, ext, chunk, chunk_ext, wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff,

@@ -18,12 +18,13 @@ def main():
     from oracle import ref_loader
     bench.use_product_package()
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    attn = sys.argv[2] if len(sys.argv) > 2 else 'eva'          # eva (evit_tiny_p8) | lara (evit_small_p16) | softmax (evit_tiny_p8)
     dev = torch.device('cuda', 0)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         vm = ref_loader.vit_models()
         torch.manual_seed(0)
-        model = vm.evit_tiny_p8(ref_loader.deit_args('eva')).to(dev).train()
+        model = (vm.evit_small_p16 if attn == 'lara' else vm.evit_tiny_p8)(ref_loader.deit_args(attn)).to(dev).train()
     opt = torch.optim.SGD(model.parameters(), lr=1e-3)
     img = torch.randn(B, 3, 224, 224, device=dev)
     y = torch.randint(0, 1000, (B,), device=dev)
