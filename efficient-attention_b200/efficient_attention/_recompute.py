@@ -21,6 +21,7 @@ from . import _abi
 
 MASK_VAL = -5.0e4          # eva.py:139, causal_eva.py:488
 _BACKWARD_IMPL = os.environ.get('EVA_SM100_BACKWARD', 'cuda')
+_LARA_BACKWARD_IMPL = os.environ.get('EVA_SM100_LARA_BACKWARD', 'explicit')     # 'explicit' | 'autograd'
 
 
 def set_backward_impl(name):
@@ -300,11 +301,11 @@ def _segment_means(t, n_lm):
     return torch.cat([a, b], -2)
 
 
-def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded, alpha_coeff,
-                    wq, bq, gq, betq, wk, bk, gk, betk, dense=False, ln_eps=1e-5, pad_mask=None, noise=None, keep_dtype=False):
-    """q, k, v [B, N, H, d] -> [B, N, H * d] float32: landmarks (pooled 2-D 'light' / 'dense', or 1-D segment means with optional
-    per-token Linear + LayerNorm), optional landmark mixing, then the self-normalised importance-sampling estimator with the three
-    MIS variants.  sample_mode: 0 one sample per landmark, 1 antithetic (noise [.., C, d] -> [mu + e ; mu - e]), 2 multi (noise [.., 2C, d])."""
+def _lara_stage1(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, sample_mode, zero_padded, wq, bq, gq, betq, wk, bk, gk, betk,
+                 dense, ln_eps, pad_mask, noise, keep_dtype):
+    """Everything of LARA that lives on [B, H, C, d] tensors (lara.py:84-198): landmarks q_bar / k_bar (pooled 2-D 'light' / 'dense', or
+    1-D segment means with optional per-token Linear + LayerNorm), optional landmark mixing, mu, the proposal samples omega.
+    Returns (qh, kh, vh [B, H, N, d], q_bar, mu, omega, rep)."""
     B, N, H, d = q.shape
     scale = d ** -0.5
     # keep_dtype: leave 16-bit q, k, v as they are -- the caller runs this under torch.autocast, i.e. with the numerics the reference
@@ -349,6 +350,20 @@ def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis
         omega, rep = mu.repeat(1, 1, 2, 1) + noise.float(), 2
     else:
         omega = mu + noise.float()
+    return qh, kh, vh, q_bar, mu, omega, rep
+
+
+def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded, alpha_coeff,
+                    wq, bq, gq, betq, wk, bk, gk, betk, dense=False, ln_eps=1e-5, pad_mask=None, noise=None, keep_dtype=False):
+    """q, k, v [B, N, H, d] -> [B, N, H * d] float32: `_lara_stage1`, then the self-normalised importance-sampling estimator with the
+    three MIS variants (lara.py:201-246).  sample_mode: 0 one sample per landmark, 1 antithetic (noise [.., C, d] -> [mu + e ; mu - e]),
+    2 multi (noise [.., 2C, d])."""
+    B, N, H, d = q.shape
+    scale = d ** -0.5
+    qh, kh, vh, q_bar, mu, omega, rep = _lara_stage1(
+        q, k, v, seq_shape=seq_shape, landmarks=landmarks, per_token_proj=per_token_proj, mixed=mixed, sample_mode=sample_mode,
+        zero_padded=zero_padded, wq=wq, bq=bq, gq=gq, betq=betq, wk=wk, bk=bk, gk=gk, betk=betk, dense=dense, ln_eps=ln_eps,
+        pad_mask=pad_mask, noise=noise, keep_dtype=keep_dtype)
     A = _prm(qh, omega)                                                         # [B, H, S, N]
     Bk = _prm(kh, omega)
     if pad_mask is not None:
@@ -371,6 +386,42 @@ def lara_core_torch(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis
     return out.permute(0, 2, 1, 3).reshape(B, N, H * d)
 
 
+def _lara_stage2_backward(qf, kf, vf, gf, q_bar, omega, lp, bh, coeff):
+    """Explicit gradient of the mis-opt estimator (lara.py:201-246, one sample per landmark, no padding mask) with respect to
+    q, k, v [B, H, N, d] and to the small inputs q_bar, omega [B, H, C, d], lp, bh [B, H, C, 1]; everything float32.  The forward
+    quantities are recomputed here -- nothing of size [C, N] is kept between the forward kernel and this call.
+        A = s (omega q^T) - s |q|^2 / 2,   T = s q_bar q^T,  t = softmax_n T,   Bk = s (omega k^T) - s |k|^2 / 2,  Pk = softmax_m Bk,
+        kv = Pk v,  alpha = bh + coeff (t - mean_c t),  logw = log max(alpha, 1e-8) + A + lse_m Bk - lp,  W = softmax_c logw,  O = W^T kv"""
+    d = qf.shape[-1]
+    s = d ** -0.5
+    q2 = (0.5 * s) * (qf * qf).sum(-1).unsqueeze(-2)                            # [B, H, 1, N]
+    k2 = (0.5 * s) * (kf * kf).sum(-1).unsqueeze(-2)
+    A = s * (omega @ qf.transpose(-1, -2)) - q2                                # [B, H, C, N]
+    T = s * (q_bar @ qf.transpose(-1, -2))
+    Bk = s * (omega @ kf.transpose(-1, -2)) - k2
+    lseB = torch.logsumexp(Bk, -1, keepdim=True)
+    Pk = torch.exp(Bk - lseB)
+    t = torch.softmax(T, -1)
+    kv = Pk @ vf                                                                # [B, H, C, d]
+    alpha = bh + coeff * (t - t.mean(-2, keepdim=True))
+    W = torch.softmax(torch.log(alpha.clamp(min=1e-8)) + A + lseB - lp, -2)     # [B, H, C, N]
+    dW = kv @ gf.transpose(-1, -2)
+    dlw = W * (dW - (W * dW).sum(-2, keepdim=True))
+    dkv = W @ gf
+    dlseB = dlw.sum(-1, keepdim=True)
+    dalpha = torch.where(alpha > 1e-8, dlw / alpha, torch.zeros_like(dlw))
+    dbh = dalpha.sum(-1, keepdim=True)
+    dt = coeff * (dalpha - dalpha.mean(-2, keepdim=True))
+    dT = t * (dt - (t * dt).sum(-1, keepdim=True))
+    dBk = Pk * (dkv @ vf.transpose(-1, -2) - (dkv * kv).sum(-1, keepdim=True) + dlseB)
+    domega = s * (dlw @ qf + dBk @ kf)
+    dqbar = s * (dT @ qf)
+    dq = s * (dlw.transpose(-1, -2) @ omega + dT.transpose(-1, -2) @ q_bar - dlw.sum(-2).unsqueeze(-1) * qf)
+    dk = s * (dBk.transpose(-1, -2) @ omega - dBk.sum(-2).unsqueeze(-1) * kf)
+    dv = Pk.transpose(-1, -2) @ dkv
+    return dq, dk, dv, dqbar, domega, -dlseB, dbh
+
+
 class LaraCoreFn(torch.autograd.Function):
     """forward: `lara_forward` of libeva_sm100 (landmarks given by the caller when `dense`); backward: autograd through
     `lara_core_torch` on the saved inputs."""
@@ -386,10 +437,56 @@ class LaraCoreFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _backward_explicit(saved, meta, need, grad_out):
+        """mis-opt, one sample per landmark, no padding mask: the [C, N]-sized part of the estimator is differentiated by explicit
+        formulas (`_lara_stage2_backward`: batched GEMMs + row / column softmax algebra, float32), only the landmark stage
+        (`_lara_stage1`, tensors of size [C, d] plus the pooling) goes through autograd."""
+        kk = meta['kernel']
+        with torch.enable_grad():
+            ins = [None if t is None else t.detach().requires_grad_(n and t.is_floating_point()) for t, n in zip(saved, need)]
+            q, k, v, noise, wq, bq, gq, betq, wk, bk, gk, betk = ins
+            qh, kh, vh, q_bar, mu, omega, _ = _lara_stage1(
+                q, k, v, seq_shape=kk['seq_shape'], landmarks=kk['landmarks'], per_token_proj=kk['per_token_proj'], mixed=kk['mixed'],
+                sample_mode=kk['sample_mode'], zero_padded=False, wq=wq, bq=bq, gq=gq, betq=betq, wk=wk, bk=bk, gk=gk, betk=betk,
+                dense=meta['dense'], ln_eps=meta['ln_eps'], pad_mask=None, noise=noise, keep_dtype=False)
+            Lm = _prm(mu, omega)
+            lp = torch.diagonal(Lm, dim1=-1, dim2=-2).unsqueeze(-1)
+            bh = torch.exp(lp - torch.logsumexp(Lm, -1, keepdim=True))
+        B, N, H, d = saved[0].shape
+        with torch.no_grad():
+            gf = grad_out.reshape(B, N, H, d).permute(0, 2, 1, 3).float()
+            dq2, dk2, dv2, dqbar, domega, dlp, dbh = _lara_stage2_backward(
+                qh.detach().contiguous(), kh.detach().contiguous(), vh.detach().contiguous(), gf.contiguous(), q_bar.detach(),
+                omega.detach(), lp.detach(), bh.detach(), kk['alpha_coeff'])
+        wanted = [t for t in ins if t is not None and t.requires_grad]
+        g1 = torch.autograd.grad([q_bar, omega, lp, bh], wanted, [dqbar, domega, dlp, dbh], allow_unused=True)
+        direct = {id(q): dq2, id(k): dk2, id(v): dv2}
+        it = iter(g1)
+        res = []
+        for t, src in zip(ins, saved):
+            if t is not None and t.requires_grad:
+                gr = next(it)
+                extra = direct.get(id(t))
+                if extra is not None:
+                    extra = extra.permute(0, 2, 1, 3)                      # [B, H, N, d] -> [B, N, H, d]
+                    gr = extra if gr is None else gr + extra
+                res.append(None if gr is None else gr.to(src.dtype))
+            else:
+                res.append(None)
+        return tuple(res[:4]) + (None,) + tuple(res[4:]) + (None,)
+
+    @staticmethod
     def backward(ctx, grad_out):
         saved = ctx.saved_tensors
         meta = ctx.meta
         need = list(ctx.needs_input_grad[:4]) + list(ctx.needs_input_grad[5:13])
+        kk0 = meta['kernel']
+        # float32 activations: explicit float32 formulas for the [C, N]-sized part (exact, nothing of that size kept by autograd);
+        # 16-bit activations: autograd under autocast below is as fast (tensor-core GEMMs) and is what the reference trains with
+        # (measured, DeiT-small-p16 + LARA step at batch 128, fp16: 66.3 ms autograd / autocast, 68.0 ms explicit float32)
+        if (_LARA_BACKWARD_IMPL == 'explicit' and saved[0].dtype == torch.float32 and kk0['mis_type'] == 'mis-opt' and
+                meta['pad_mask'] is None and (saved[3] is None or kk0['sample_mode'] == _abi.LARA_SAMPLE_SINGLE)):
+            return LaraCoreFn._backward_explicit(saved, meta, need, grad_out)
         half = saved[0].dtype in (torch.float16, torch.bfloat16)       # 16-bit activations: differentiate under autocast, as the reference trains
         with torch.enable_grad(), torch.autocast('cuda', dtype=saved[0].dtype if half else torch.float16, enabled=half):
             ins = [None if t is None else t.detach().requires_grad_(n and t.is_floating_point()) for t, n in zip(saved, need)]
