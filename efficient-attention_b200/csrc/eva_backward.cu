@@ -734,6 +734,209 @@ chunk_grad_fast_kernel(const Geo g, const View q, const View k, const View v, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Chunk-statistics gradient for head_dim 64 with 16-bit I/O and chunks of at most 128 slots, ANY geometry (halo, padding, 1-D /
+// 2-D): the backward twin of chunk_stats_fast_kernel.  Tokens may belong to several chunks here, so the token gradients are
+// accumulated with vector reductions (red.global.add.v4.f32) instead of being finished in place; everything else follows the two
+// fast kernels: one token-index computation per slot, four tokens per 16-byte load instruction in the feature passes, lane = token
+// for the two per-token dot products (phi-logit, <d beta, v_t>).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
+                            const EvaAdaptive ada, const float* __restrict__ noise, const float* __restrict__ beta_fw,
+                            const float* __restrict__ dkbar, const float* __restrict__ dbeta, float* __restrict__ dq,
+                            float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ rows) {
+  extern __shared__ float sm[];
+  float* WtK = sm;
+  float* WtQ = sm + 64 * 64;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int e = idx >> 6, i = idx & 63;
+    WtK[i * 64 + e] = __ldg(ada.w_k + idx);
+    if (ada.w_q) WtQ[i * 64 + e] = __ldg(ada.w_q + idx);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* vec = sm + 2 * 64 * 64 + warp * 320;         // omega | d beta | dm_k / Jc | dm_q / Jc | (spare)   64 floats each
+  const float scale = 0.125f;
+  const float inv_cnt = 1.0f / (float)g.Jc;
+  const int n_rounds = (g.Jc + 31) >> 5;
+  const int ts = lane >> 3, p8 = lane & 7;
+  const long long total = (long long)g.B * g.H * g.n_chunks;
+  const long long slot = total * 64;
+  for (long long wg = (long long)blockIdx.x * wpb + warp; wg < total; wg += (long long)gridDim.x * wpb) {
+    const int c = (int)(wg % g.n_chunks);
+    const int h = (int)((wg / g.n_chunks) % g.H);
+    const int b = (int)(wg / ((long long)g.n_chunks * g.H));
+    const long long obase = wg * 64;
+    int tokr[4];
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      const int s = 32 * rd + lane;
+      int t = (rd < n_rounds && s < g.Jc) ? group_token(g, c, s, g.chunk, g.chunk_ext) : -1;
+      if (t >= 0 && mask && mask[(long long)b * g.N + t]) t = -1;
+      tokr[rd] = t;
+    }
+    // ---- forward statistics, recomputed ----
+    float aq[8], ak[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aq[i] = ak[i] = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      if (rd >= n_rounds) break;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int t = __shfl_sync(0xffffffffu, tokr[rd], 4 * i + ts);
+        if (t < 0) continue;
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(q.row<T>(b, t, h)) + p8), 1.f, aq);
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + p8), 1.f, ak);
+      }
+    }
+    float2 sq = pieces_to_pair(aq, lane), sk = pieces_to_pair(ak, lane);
+    sq.x *= inv_cnt; sq.y *= inv_cnt; sk.x *= inv_cnt; sk.y *= inv_cnt;
+    float inv_k = 1.f, inv_q = 1.f;
+    float2 nk = make_float2(0.f, 0.f), nq = nk, om = nk;
+    float2 kb = pair_linear(WtK, ada.b_k, sk, lane);
+    if (ada.ln_gain_k) {
+      nk = pair_ln(kb, ada.ln_eps, inv_k);
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_k) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_k) + lane);
+      kb = make_float2(fmaf(nk.x, gg.x, bb.x), fmaf(nk.y, gg.y, bb.y));
+    }
+    if (ada.w_q) {
+      float2 qb = pair_linear(WtQ, ada.b_q, sq, lane);
+      if (ada.ln_gain_q) {
+        nq = pair_ln(qb, ada.ln_eps, inv_q);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(ada.ln_gain_q) + lane), bb = __ldg(reinterpret_cast<const float2*>(ada.ln_bias_q) + lane);
+        qb = make_float2(fmaf(nq.x, gg.x, bb.x), fmaf(nq.y, gg.y, bb.y));
+      }
+      om = make_float2(ada.mu_coeff * (qb.x + kb.x), ada.mu_coeff * (qb.y + kb.y));
+    }
+    if (noise) { const float2 z = __ldg(reinterpret_cast<const float2*>(noise + obase) + lane); om.x += z.x; om.y += z.y; }
+    const float2 db = *(reinterpret_cast<const float2*>(dbeta + obase) + lane);
+    const float2 dkb_in = *(reinterpret_cast<const float2*>(dkbar + obase) + lane);
+    const float2 bf = __ldg(reinterpret_cast<const float2*>(beta_fw + obase) + lane);
+    const float dsum = warp_sum(db.x * bf.x + db.y * bf.y);                  // <d beta, beta>
+    __syncwarp();
+    reinterpret_cast<float2*>(vec)[lane] = om;
+    reinterpret_cast<float2*>(vec + 64)[lane] = db;
+    __syncwarp();
+    // ---- lane = token: phi-logit and <d beta, v_t> ----
+    float lg[4], p2[4];
+    float mx = kNegInf;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      lg[rd] = kNegInf; p2[rd] = 0.f;
+      if (rd >= n_rounds) continue;
+      if (32 * rd + lane < g.Jc) {
+        lg[rd] = kMaskVal;
+        const int t = tokr[rd];
+        if (t >= 0) {
+          const uint4* kr = reinterpret_cast<const uint4*>(k.row<T>(b, t, h));
+          const uint4* vr = reinterpret_cast<const uint4*>(v.row<T>(b, t, h));
+          float part = 0.f, pv = 0.f;
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            const uint4 rk = __ldg(kr + pc), rv = __ldg(vr + pc);
+            const uint32_t wk4[4] = {rk.x, rk.y, rk.z, rk.w}, wv4[4] = {rv.x, rv.y, rv.z, rv.w};
+            const float4 o0 = *reinterpret_cast<const float4*>(vec + 8 * pc), o1 = *reinterpret_cast<const float4*>(vec + 8 * pc + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(vec + 64 + 8 * pc), d1 = *reinterpret_cast<const float4*>(vec + 64 + 8 * pc + 4);
+            const float oo[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 kk = Pair16<T>::up(wk4[u]), vv = Pair16<T>::up(wv4[u]);
+              part = fmaf(kk.x, oo[2 * u] - 0.5f * kk.x, fmaf(kk.y, oo[2 * u + 1] - 0.5f * kk.y, part));
+              pv = fmaf(dd[2 * u], vv.x, fmaf(dd[2 * u + 1], vv.y, pv));
+            }
+          }
+          lg[rd] = scale * part;
+          p2[rd] = pv;
+        }
+      }
+      mx = fmaxf(mx, lg[rd]);
+    }
+    mx = warp_max(mx);
+    float den = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) { lg[rd] = exp_nonpos(lg[rd] - mx); den += lg[rd]; }
+    const float inv_l = 1.0f / warp_sum(den);
+    float dlg[4];
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      lg[rd] *= inv_l;                                                     // a_t
+      dlg[rd] = tokr[rd] >= 0 ? scale * lg[rd] * (p2[rd] - dsum) : 0.f;    // masked slots: constant logit, no gradient
+    }
+    // ---- d omega = sum_t dlg_t k_t ----
+    float ad[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ad[i] = 0.f;
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      if (rd >= n_rounds) break;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int t = __shfl_sync(0xffffffffu, tokr[rd], 4 * i + ts);
+        const float d = __shfl_sync(0xffffffffu, dlg[rd], 4 * i + ts);
+        if (t < 0) continue;
+        add8<T>(__ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + p8), d, ad);
+      }
+    }
+    const float2 dom = pieces_to_pair(ad, lane);
+    // ---- omega -> LayerNorm -> Linear -> means ----
+    const float cq = ada.w_q ? ada.mu_coeff : 0.f;
+    const float2 dok = make_float2(dkb_in.x + cq * dom.x, dkb_in.y + cq * dom.y);
+    const float2 doq = make_float2(cq * dom.x, cq * dom.y);
+    const float2 dyk = pair_ln_bwd(dok, nk, inv_k, ada.ln_gain_k, lane);
+    const float2 dmk = pair_linear_bwd(ada.w_k, dyk, lane);
+    float2 dyq = make_float2(0.f, 0.f), dmq = dyq;
+    if (ada.w_q) {
+      dyq = pair_ln_bwd(doq, nq, inv_q, ada.ln_gain_q, lane);
+      dmq = pair_linear_bwd(ada.w_q, dyq, lane);
+    }
+    {
+      float2* r2 = reinterpret_cast<float2*>(rows + obase) + lane;
+      const long long s2 = slot / 2;
+      r2[0] = dyk; r2[s2] = dyq; r2[2 * s2] = sk; r2[3 * s2] = sq; r2[4 * s2] = nk; r2[5 * s2] = nq; r2[6 * s2] = dok; r2[7 * s2] = doq;
+    }
+    reinterpret_cast<float2*>(vec + 128)[lane] = make_float2(dmk.x * inv_cnt, dmk.y * inv_cnt);
+    reinterpret_cast<float2*>(vec + 192)[lane] = make_float2(dmq.x * inv_cnt, dmq.y * inv_cnt);
+    __syncwarp();
+    // ---- token gradients: four tokens per instruction, 8 features per lane, vector reductions ----
+    float o8[8], d8[8], mk8[8], mq8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o8[i] = vec[8 * p8 + i]; d8[i] = vec[64 + 8 * p8 + i]; mk8[i] = vec[128 + 8 * p8 + i]; mq8[i] = vec[192 + 8 * p8 + i]; }
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+      if (rd >= n_rounds) break;
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int t = __shfl_sync(0xffffffffu, tokr[rd], 4 * i + ts);
+        const float at = __shfl_sync(0xffffffffu, lg[rd], 4 * i + ts), dt = __shfl_sync(0xffffffffu, dlg[rd], 4 * i + ts);
+        if (t < 0) continue;
+        const uint4 rk = __ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + p8);
+        const uint32_t w4[4] = {rk.x, rk.y, rk.z, rk.w};
+        float gk[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 kk = Pair16<T>::up(w4[u]);
+          gk[2 * u] = fmaf(dt, o8[2 * u] - kk.x, mk8[2 * u]);
+          gk[2 * u + 1] = fmaf(dt, o8[2 * u + 1] - kk.y, mk8[2 * u + 1]);
+        }
+        const long long base = (((long long)b * g.N + t) * g.H + h) * 64 + 8 * p8;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dk + base), "f"(gk[0]), "f"(gk[1]), "f"(gk[2]), "f"(gk[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dk + base + 4), "f"(gk[4]), "f"(gk[5]), "f"(gk[6]), "f"(gk[7]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dv + base), "f"(at * d8[0]), "f"(at * d8[1]), "f"(at * d8[2]), "f"(at * d8[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dv + base + 4), "f"(at * d8[4]), "f"(at * d8[5]), "f"(at * d8[6]), "f"(at * d8[7]) : "memory");
+        if (ada.w_q) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + base), "f"(mq8[0]), "f"(mq8[1]), "f"(mq8[2]), "f"(mq8[3]) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dq + base + 4), "f"(mq8[4]), "f"(mq8[5]), "f"(mq8[6]), "f"(mq8[7]) : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // float32 [3, B, N, H, D] -> io format, packed [B, N, 3, H, D] (the cases the fast kernel above does not finish itself)
 template <typename T>
 __global__ void pack_grad_kernel(const float* __restrict__ g3, T* __restrict__ gio, long long tens, int HD, int N) {
@@ -789,6 +992,21 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
       if (blocks_f > 148LL * 12) blocks_f = 148LL * 12;
       kf<<<(unsigned)blocks_f, 256, smf, st>>>(g, q, k, v, *ada, noise, beta, dkbar, dbeta, dq, dk, dv, rows, reinterpret_cast<T*>(gio));
       return cudaGetLastError();
+    }
+  }
+  if constexpr (D == 64 && sizeof(T) == 2) {
+    static const bool slow_only2 = [] { const char* e_ = getenv("EVA_SM100_CHUNK_BWD_GENERIC"); return e_ && e_[0] == '1'; }();
+    if (!slow_only2 && g.Jc <= 128) {
+      auto kf = chunk_stats_bwd_fast_kernel<T>;
+      const size_t smf = (2 * 64 * 64 + 8 * 320) * sizeof(float);
+      e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
+      if (e != cudaSuccess) return e;
+      const long long total_f = (long long)g.B * g.H * g.n_chunks;
+      long long blocks_f = (total_f + 7) / 8;
+      if (blocks_f > 148LL * 16) blocks_f = 148LL * 16;
+      kf<<<(unsigned)blocks_f, 256, smf, st>>>(g, q, k, v, mask, *ada, noise, beta, dkbar, dbeta, dq, dk, dv, rows);
+      e = cudaGetLastError();
+      return e != cudaSuccess ? e : pack();
     }
   }
   auto kern2 = chunk_stats_bwd_kernel<T, D>;

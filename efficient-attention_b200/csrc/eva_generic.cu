@@ -331,32 +331,6 @@ chunk_stats_cta_kernel(const Geo g, const View q, const View k, const View v, co
 // ------------------------------------------------------------------------------------------------
 constexpr int kFastMaxJc = 128;
 
-// 8 consecutive features per lane (piece p8 = lane & 7 of a 128-byte row), partial over the tokens of sub-index ts = lane >> 3:
-// sum over the four ts groups, then hand lane l its feature pair (2l, 2l + 1)
-__device__ __forceinline__ float2 pieces_to_pair(float (&a)[8], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 8);
-    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 16);
-  }
-  float2 r = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float x = __shfl_sync(0xffffffffu, a[2 * u], lane >> 2), y = __shfl_sync(0xffffffffu, a[2 * u + 1], lane >> 2);
-    if ((lane & 3) == u) r = make_float2(x, y);
-  }
-  return r;
-}
-template <typename T>
-__device__ __forceinline__ void add8(const uint4& raw, float w, float (&a)[8]) {
-  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float2 f = Pair16<T>::up(w4[u]);
-    a[2 * u] = fmaf(w, f.x, a[2 * u]); a[2 * u + 1] = fmaf(w, f.y, a[2 * u + 1]);
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 chunk_stats_fast_kernel(const Geo g, const View q, const View k, const View v, const uint8_t* __restrict__ mask,
