@@ -735,7 +735,7 @@ chunk_grad_fast_kernel(const Geo g, const View q, const View k, const View v, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Chunk-statistics gradient for head_dim 64 with 16-bit I/O and chunks of at most 128 slots, ANY geometry (halo, padding, 1-D /
+// Chunk-statistics gradient for head_dim 64 with 16-bit I/O and chunks of at most 256 slots, ANY geometry (halo, padding, 1-D /
 // 2-D): the backward twin of chunk_stats_fast_kernel.  Tokens may belong to several chunks here, so the token gradients are
 // accumulated with vector reductions (red.global.add.v4.f32) instead of being finished in place; everything else follows the two
 // fast kernels: one token-index computation per slot, four tokens per 16-byte load instruction in the feature passes, lane = token
@@ -769,9 +769,9 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
     const int h = (int)((wg / g.n_chunks) % g.H);
     const int b = (int)(wg / ((long long)g.n_chunks * g.H));
     const long long obase = wg * 64;
-    int tokr[4];
+    int tokr[8];
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       const int s = 32 * rd + lane;
       int t = (rd < n_rounds && s < g.Jc) ? group_token(g, c, s, g.chunk, g.chunk_ext) : -1;
       if (t >= 0 && mask && mask[(long long)b * g.N + t]) t = -1;
@@ -782,7 +782,7 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
 #pragma unroll
     for (int i = 0; i < 8; ++i) aq[i] = ak[i] = 0.f;
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       if (rd >= n_rounds) break;
 #pragma unroll 4
       for (int i = 0; i < 8; ++i) {
@@ -821,10 +821,10 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
     reinterpret_cast<float2*>(vec + 64)[lane] = db;
     __syncwarp();
     // ---- lane = token: phi-logit and <d beta, v_t> ----
-    float lg[4], p2[4];
+    float lg[8], p2[8];
     float mx = kNegInf;
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       lg[rd] = kNegInf; p2[rd] = 0.f;
       if (rd >= n_rounds) continue;
       if (32 * rd + lane < g.Jc) {
@@ -858,11 +858,11 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
     mx = warp_max(mx);
     float den = 0.f;
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) { lg[rd] = exp_nonpos(lg[rd] - mx); den += lg[rd]; }
+    for (int rd = 0; rd < 8; ++rd) { lg[rd] = exp_nonpos(lg[rd] - mx); den += lg[rd]; }
     const float inv_l = 1.0f / warp_sum(den);
-    float dlg[4];
+    float dlg[8];
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       lg[rd] *= inv_l;                                                     // a_t
       dlg[rd] = tokr[rd] >= 0 ? scale * lg[rd] * (p2[rd] - dsum) : 0.f;    // masked slots: constant logit, no gradient
     }
@@ -871,7 +871,7 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
 #pragma unroll
     for (int i = 0; i < 8; ++i) ad[i] = 0.f;
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       if (rd >= n_rounds) break;
 #pragma unroll 4
       for (int i = 0; i < 8; ++i) {
@@ -906,7 +906,7 @@ chunk_stats_bwd_fast_kernel(const Geo g, const View q, const View k, const View 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { o8[i] = vec[8 * p8 + i]; d8[i] = vec[64 + 8 * p8 + i]; mk8[i] = vec[128 + 8 * p8 + i]; mq8[i] = vec[192 + 8 * p8 + i]; }
 #pragma unroll
-    for (int rd = 0; rd < 4; ++rd) {
+    for (int rd = 0; rd < 8; ++rd) {
       if (rd >= n_rounds) break;
 #pragma unroll 2
       for (int i = 0; i < 8; ++i) {
@@ -996,7 +996,7 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
   }
   if constexpr (D == 64 && sizeof(T) == 2) {
     static const bool slow_only2 = [] { const char* e_ = getenv("EVA_SM100_CHUNK_BWD_GENERIC"); return e_ && e_[0] == '1'; }();
-    if (!slow_only2 && g.Jc <= 128) {
+    if (!slow_only2 && g.Jc <= 256) {
       auto kf = chunk_stats_bwd_fast_kernel<T>;
       const size_t smf = (2 * 64 * 64 + 8 * 320) * sizeof(float);
       e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf);
