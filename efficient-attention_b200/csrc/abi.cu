@@ -126,6 +126,13 @@ int eva_chunk_stats(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHead
 int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                          const uint8_t* pad_mask, const float* k_bar, const float* beta,
                          const float* bias, int64_t bias_stride_h, void* out, void* stream) {
+  return eva_window_attention_lse(gin, q, k, v, pad_mask, k_bar, beta, bias, bias_stride_h, out, nullptr, nullptr, stream);
+}
+
+int eva_window_attention_lse(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                             const uint8_t* pad_mask, const float* k_bar, const float* beta, const float* bias, int64_t bias_stride_h,
+                             void* out, float* lse, int32_t* lse_written, void* stream) {
+  if (lse_written) *lse_written = 0;
   eva::Geo g{};
   eva::View vq, vk, vv;
   int rc;
@@ -139,12 +146,14 @@ int eva_window_attention(const EvaGeometry* gin, const EvaHeadsView* q, const Ev
   if (g.n_chunks > 0 && eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias, bias_stride_h)) {
     const char* msg = "";
     const cudaError_t ec = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out,
-                                                     reinterpret_cast<cudaStream_t>(stream), &msg);
+                                                     reinterpret_cast<cudaStream_t>(stream), &msg, nullptr, nullptr, nullptr, lse);
+    if (lse && lse_written) *lse_written = 1;
     return ec == cudaSuccess ? EVA_OK : fail(EVA_ERR_CUDA, "eva_window_attention(causal window): %s: %s", msg, cudaGetErrorString(ec));
   }
+  if (lse && lse_written && eva::window_tc_supported(g, gin->io_dtype)) *lse_written = 1;
   const cudaError_t e = eva::window_tc_supported(g, gin->io_dtype)
                             ? eva::launch_window_tc(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out,
-                                                    reinterpret_cast<cudaStream_t>(stream))
+                                                    reinterpret_cast<cudaStream_t>(stream), lse)
                             : eva::launch_window_attn(g, gin->io_dtype, vq, vk, vv, pad_mask, k_bar, beta, bias, bias_stride_h, out,
                                                       reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_window_attention");
@@ -157,7 +166,9 @@ int eva_forward_workspace_bytes(const EvaGeometry* gin, size_t* bytes) {
   if (!bytes) return fail(EVA_ERR_INVALID, "bytes is NULL");
   const size_t stats = align256((size_t)g.B * g.H * g.n_chunks * g.D * sizeof(float));
   // k_bar | beta | fused-kernel scratch | per-window flags of the one-pass causal kernel
-  *bytes = 2 * stats + align256(eva::fused_workspace_bytes(g)) + align256((size_t)g.B * g.H * (g.n_windows > 0 ? g.n_windows : 1) * sizeof(unsigned int));
+  // k_bar | beta | fused-kernel scratch | per-window flags | (keep_stats) log-sum-exp of every query row
+  *bytes = 2 * stats + align256(eva::fused_workspace_bytes(g)) + align256((size_t)g.B * g.H * (g.n_windows > 0 ? g.n_windows : 1) * sizeof(unsigned int)) +
+           (gin->keep_stats ? align256((size_t)g.B * g.H * g.N * sizeof(float)) : 0);
   return EVA_OK;
 }
 
@@ -219,13 +230,19 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
     nb = (int)(fit < 1 ? 1 : (fit > g.B ? g.B : fit));
   }
   const bool causal_fast = eva::causal_window_supported(g, gin->io_dtype, vq, vk, vv, pad_mask, bias, bias_stride_h);
-  if (path_taken) *path_taken = causal_fast ? 2 : 0;
+  // training: the tcgen05 window kernels also leave the log-sum-exp of every query row (path_taken | 0x100 says so)
+  float* lse = gin->keep_stats ? reinterpret_cast<float*>(ws + 2 * stats + align256(eva::fused_workspace_bytes(g)) +
+                                                          align256((size_t)g.B * g.H * (g.n_windows > 0 ? g.n_windows : 1) * sizeof(unsigned int)))
+                               : nullptr;
+  const bool lse_kept = lse && nb == g.B && (causal_fast || eva::window_tc_supported(g, gin->io_dtype));
+  if (!lse_kept) lse = nullptr;
+  if (path_taken) *path_taken = (causal_fast ? 2 : 0) | (lse_kept ? 0x100 : 0);
   ++g_path_count[causal_fast ? 2 : 0];
   if (causal_fast && eva::causal_one_pass_supported(g, *ada)) {
     // one pass over q, k, v: the window kernel computes the chunk statistics itself
     unsigned int* flags = reinterpret_cast<unsigned int*>(ws + 2 * stats + align256(eva::fused_workspace_bytes(g)));
     const char* msg = "";
-    const cudaError_t e1 = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out, st, &msg, ada, noise, flags);
+    const cudaError_t e1 = eva::launch_causal_window(g, gin->io_dtype, vq, vk, vv, k_bar, beta, bias, out, st, &msg, ada, noise, flags, lse);
     if (e1 != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal one-pass): %s: %s", msg, cudaGetErrorString(e1));
     return EVA_OK;
   }
@@ -242,11 +259,11 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
     if (e != cudaSuccess) return cuda_fail(e, "eva_forward(chunk_stats)");
     if (causal_fast) {
       const char* msg = "";
-      e = eva::launch_causal_window(gs, gin->io_dtype, sq, sk, sv, k_bar + stat_off, beta + stat_off, bias, sout, st, &msg);
+      e = eva::launch_causal_window(gs, gin->io_dtype, sq, sk, sv, k_bar + stat_off, beta + stat_off, bias, sout, st, &msg, nullptr, nullptr, nullptr, lse);
       if (e != cudaSuccess) return fail(EVA_ERR_CUDA, "eva_forward(causal window): %s: %s", msg, cudaGetErrorString(e));
     } else {
       e = eva::window_tc_supported(gs, gin->io_dtype)
-              ? eva::launch_window_tc(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st)
+              ? eva::launch_window_tc(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st, lse)
               : eva::launch_window_attn(gs, gin->io_dtype, sq, sk, sv, smask, k_bar + stat_off, beta + stat_off, bias, bias_stride_h, sout, st);
       if (e != cudaSuccess) return cuda_fail(e, "eva_forward(window_attention)");
     }
@@ -256,8 +273,8 @@ int eva_forward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVie
 
 int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, const float* k_bar_in, const float* beta_in, float* grad_qkv, void* grad_qkv_io,
-                 float* grad_bias, float* chunk_rows, void* stream) {
+                 const void* out, const void* grad_out, const float* k_bar_in, const float* beta_in, const float* lse, float* grad_qkv,
+                 void* grad_qkv_io, float* grad_bias, float* chunk_rows, void* stream) {
   eva::Geo g{};
   eva::View vq, vk, vv;
   int rc;
@@ -296,7 +313,7 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   }
   const cudaError_t e = eva::launch_eva_backward(g, gin->io_dtype, vq, vk, vv, pad_mask, ada, noise, kbar, beta, bias, bias_stride_h, out,
                                                  grad_out, grad_qkv, grad_qkv + tens, grad_qkv + 2 * tens, chunk_rows + 2 * slot,
-                                                 chunk_rows + 3 * slot, grad_bias, chunk_rows + 4 * slot, grad_qkv_io, st);
+                                                 chunk_rows + 3 * slot, grad_bias, chunk_rows + 4 * slot, grad_qkv_io, st, lse);
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_backward");
 }
 

@@ -954,7 +954,7 @@ template <typename T, int D>
 static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st) {
+                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st, const float* lse) {
   cudaError_t e;
   const long long tens = (long long)g.B * g.N * g.H * g.D;
   auto pack = [&]() -> cudaError_t {          // generic finish: convert and interleave
@@ -966,7 +966,7 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
   if (window_bwd_tc_supported(g, io_dtype, mask)) {
     e = launch_window_bwd_tc(g, io_dtype, q, k, v, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
   } else if (window_bwd_gen_supported(g, io_dtype)) {
-    e = launch_window_bwd_gen(g, io_dtype, q, k, v, mask, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st);
+    e = launch_window_bwd_gen(g, io_dtype, q, k, v, mask, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, st, lse);
   } else {
     auto kern = window_attn_bwd_kernel<T, D>;
     const size_t smem = BwdSmem<D>::kBytes;
@@ -1024,9 +1024,9 @@ static cudaError_t launch_bwd_t(const Geo& g, int io_dtype, const View& q, const
 cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st) {
+                                float* dbeta, float* dbias, float* rows, void* gio, cudaStream_t st, const float* lse) {
 #define EVA_BWD_CASE(DT, TY, DD) \
-  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, io_dtype, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, gio, st);
+  case DT * 256 + DD: return launch_bwd_t<TY, DD>(g, io_dtype, q, k, v, mask, ada, noise, kbar, beta, bias, bias_sh, out, dout, dq, dk, dv, dkbar, dbeta, dbias, rows, gio, st, lse);
   switch (io_dtype * 256 + g.D) {
     EVA_BWD_CASE(EVA_F32, float, 16) EVA_BWD_CASE(EVA_F32, float, 32) EVA_BWD_CASE(EVA_F32, float, 64) EVA_BWD_CASE(EVA_F32, float, 128)
     EVA_BWD_CASE(EVA_F16, __half, 16) EVA_BWD_CASE(EVA_F16, __half, 32) EVA_BWD_CASE(EVA_F16, __half, 64) EVA_BWD_CASE(EVA_F16, __half, 128)

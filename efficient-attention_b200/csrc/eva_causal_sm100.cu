@@ -52,6 +52,7 @@ struct Params {
   const float *w_q, *b_q, *g_q, *beta_q, *w_k, *b_k, *g_k, *beta_k;
   float mu_coeff, ln_eps;
   const float* noise;            // [B, H, n_chunks, 64] or NULL
+  float* lse_out;                // training: log2-domain log-sum-exp of every query row -> float32 [B, H, N] (the backward reads it), or NULL
 };
 
 template <typename T> struct Fmt;
@@ -503,6 +504,7 @@ eva_causal_window_kernel(const __grid_constant__ CUtensorMap t_q, const __grid_c
       ptx::mbar_arrive(bar(kOFree0 + rb));
       const float inv = 1.0f / (s0 + s1);
       const int orow = 128 * rb + i;
+      if (p.lse_out) p.lse_out[((long long)b * p.H + h) * p.N + wi * kWin + orow] = log2f(s0 + s1) - nmx;
       if (p.fuse) ptx::mbar_wait(bar(kStatsDone0 + s), (it >> 1) & 1);   // the statistics warpgroup has read this stage's q tile
       uint8_t* row = stage_ptr(s) + orow * 128;
 #pragma unroll
@@ -560,7 +562,7 @@ static bool make_seq_map(CUtensorMap* tm, const void* ptr, long long sb, long lo
 template <typename T>
 static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar, const float* beta,
                             const float* bias, void* out, cudaStream_t st, const char** msg, const EvaAdaptive* ada, const float* noise,
-                            unsigned int* flags) {
+                            unsigned int* flags, float* lse_out) {
   CUtensorMap tq, tk, tv, to;
   bool swq = false, swk = false, swv = false;
   if (!make_seq_map(&tq, q.ptr, q.sb, q.sn, q.sh, g, io_dtype, kWin, &swq) || !make_seq_map(&tk, k.ptr, k.sb, k.sn, k.sh, g, io_dtype, kWin, &swk) ||
@@ -572,7 +574,7 @@ static cudaError_t launch_t(const Geo& g, int io_dtype, const View& q, const Vie
   Params p{};
   p.B = g.B; p.H = g.H; p.N = g.N; p.n_win = g.N / kWin; p.items = g.B * g.H * p.n_win;
   p.n_chunks = g.n_chunks; p.cnp = (g.n_chunks + 15) & ~15; p.chunk = g.chunk;
-  p.kbar = kbar; p.beta = beta; p.bias = bias;
+  p.kbar = kbar; p.beta = beta; p.bias = bias; p.lse_out = lse_out;
   p.swap = (swq ? 1 : 0) | (swk ? 2 : 0) | (swv ? 4 : 0);
   p.fuse = 0; p.cpw = kWin / (g.chunk > 0 ? g.chunk : kWin);
   if (ada && flags) {                                   // one-pass mode (see causal_one_pass_supported)
@@ -639,9 +641,9 @@ bool causal_one_pass_supported(const Geo& g, const EvaAdaptive& ada) {
 
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
                                  const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg,
-                                 const EvaAdaptive* ada, const float* noise, unsigned int* flags) {
-  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags);
-  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags);
+                                 const EvaAdaptive* ada, const float* noise, unsigned int* flags, float* lse_out) {
+  if (io_dtype == EVA_F16) return causal::launch_t<__half>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags, lse_out);
+  return causal::launch_t<__nv_bfloat16>(g, io_dtype, q, k, v, kbar, beta, bias, out, st, msg, ada, noise, flags, lse_out);
 }
 
 }  // namespace eva

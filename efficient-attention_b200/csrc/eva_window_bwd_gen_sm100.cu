@@ -42,6 +42,7 @@ struct Params {
   const float* kbar; const float* beta; const float* bias;
   long long bias_sh;
   const void* out; const void* dout;
+  const float* lse;              // log2-domain log-sum-exp per query row [B, H, N] kept by the forward, or NULL (recomputed: pass 0)
   float* dq; float* dk; float* dv; float* dkbar; float* dbeta; float* dbias;
   long long total;
   int trace;
@@ -255,9 +256,9 @@ eva_window_bwd_gen_kernel(const Params p) {
     long long tk[8];
     const bool tr_on = p.trace && item == blockIdx.x + gridDim.x && blockIdx.x == 0;
     if (tr_on) tk[0] = clock64();
-    // ---- pass 0: lse of every row ----
+    // ---- pass 0: lse of every row (skipped when the forward kept it) ----
     float mrow = kNegInf, lrow = 0.f;
-    for (int kt0 = 0; kt0 < n_keys; kt0 += 128) {
+    for (int kt0 = 0; kt0 < n_keys && !p.lse; kt0 += 128) {
       if (skip_tile(kt0)) continue;
       __syncthreads();
       const bool tf = mma_s(load_tile(kt0, false), false);
@@ -281,8 +282,12 @@ eva_window_bwd_gen_kernel(const Params p) {
     pl[hf * 128 + r] = lrow;
     __syncthreads();
     const float ltot = pl[r] + pl[128 + r];
-    const bool row_ok = tq_row >= 0 && mrow != kNegInf && ltot > 0.f;
-    const float lse = row_ok ? mrow + log2f(ltot) : 0.f;
+    bool row_ok = tq_row >= 0 && mrow != kNegInf && ltot > 0.f;
+    float lse = row_ok ? mrow + log2f(ltot) : 0.f;
+    if (p.lse) {
+      lse = tq_row >= 0 ? __ldg(p.lse + (long long)bh * g.N + tq_row) : 0.f;
+      row_ok = tq_row >= 0 && lse > -1e30f && lse < 1e30f;
+    }
     const float dl = delta[r];
     float* dbrow = (p.dbias && tq_row >= 0) ? p.dbias + bias_off + (long long)li_row * g.J : nullptr;
     // ---- pass 1 ----
@@ -404,11 +409,11 @@ bool window_bwd_gen_supported(const Geo& g, int io_dtype) {
 cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                   const float* kbar, const float* beta, const float* bias, long long bias_sh, const void* out,
                                   const void* dout, float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const float* lse) {
   bwdgen::Params p;
   p.g = g; p.q = q; p.k = k; p.v = v; p.mask = mask;
   p.kbar = kbar; p.beta = beta; p.bias = bias; p.bias_sh = bias_sh;
-  p.out = out; p.dout = dout;
+  p.out = out; p.dout = dout; p.lse = lse;
   p.dq = dq; p.dk = dk; p.dv = dv; p.dkbar = dkbar; p.dbeta = dbeta; p.dbias = dbias;
   p.total = (long long)((g.L + 127) / 128) * g.n_windows * g.B * g.H;
   static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();

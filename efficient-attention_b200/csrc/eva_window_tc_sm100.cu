@@ -40,6 +40,7 @@ struct Params {
   const float* kbar; const float* beta; const float* bias;
   long long bias_sh;
   void* out;
+  float* lse_out;                // training: log2-domain log-sum-exp per query row -> float32 [B, H, N], or NULL
   long long total;
   int trace;
 };
@@ -309,6 +310,7 @@ eva_window_tc_kernel(const Params p) {
     __syncthreads();
     {
       const float inv = 1.0f / (pl[r] + pl[128 + r]);
+      if (p.lse_out && hf == 0 && qtok[r] >= 0) p.lse_out[(long long)bh * g.N + qtok[r]] = mrow + log2f(pl[r] + pl[128 + r]);
       float o[32];
       tmem_ld_cols<32>(trow + cO + 32 * hf, reinterpret_cast<uint32_t*>(o));
       ptx::tmem_ld_wait();
@@ -343,10 +345,11 @@ bool window_tc_supported(const Geo& g, int io_dtype) {
 }
 
 cudaError_t launch_window_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                             const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st) {
+                             const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st,
+                             float* lse_out) {
   wintc::Params p;
   p.g = g; p.q = q; p.k = k; p.v = v; p.mask = mask;
-  p.kbar = kbar; p.beta = beta; p.bias = bias; p.bias_sh = bias_sh; p.out = out;
+  p.kbar = kbar; p.beta = beta; p.bias = bias; p.bias_sh = bias_sh; p.out = out; p.lse_out = lse_out;
   p.total = (long long)((g.L + 127) / 128) * g.n_windows * g.B * g.H;
   static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();
   p.trace = trace;

@@ -41,7 +41,8 @@ bool causal_window_supported(const Geo& g, int io_dtype, const View& q, const Vi
 bool causal_one_pass_supported(const Geo& g, const EvaAdaptive& ada);
 cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const float* kbar,
                                  const float* beta, const float* bias, void* out, cudaStream_t st, const char** msg,
-                                 const EvaAdaptive* ada = nullptr, const float* noise = nullptr, unsigned int* flags = nullptr);
+                                 const EvaAdaptive* ada = nullptr, const float* noise = nullptr, unsigned int* flags = nullptr,
+                                 float* lse_out = nullptr);   // lse_out: log2-domain log-sum-exp per query row [B, H, N] (training)
 
 // Backward of the two generic stages (eva_backward.cu); kbar / beta are the forward statistics, dkbar / dbeta zeroed scratch,
 // rows = 8 per-chunk row slots (see chunk_stats_bwd_kernel); ada / noise / dkbar / dbeta / rows unused when g.n_chunks == 0;
@@ -50,12 +51,13 @@ cudaError_t launch_causal_window(const Geo& g, int io_dtype, const View& q, cons
 cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                 const EvaAdaptive* ada, const float* noise, const float* kbar, const float* beta, const float* bias,
                                 long long bias_sh, const void* out, const void* dout, float* dq, float* dk, float* dv, float* dkbar,
-                                float* dbeta, float* dbias, float* rows, void* grad_io, cudaStream_t st);
+                                float* dbeta, float* dbias, float* rows, void* grad_io, cudaStream_t st, const float* lse = nullptr);
 
 // Window attention on tcgen05 for any geometry with head_dim 64 and 16-bit I/O (eva_window_tc_sm100.cu); arguments as launch_window_attn
 bool window_tc_supported(const Geo& g, int io_dtype);
 cudaError_t launch_window_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                             const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st);
+                             const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st,
+                             float* lse_out = nullptr);
 
 // tcgen05 window-attention backward (eva_bwd_sm100.cu): head_dim 64, 16-bit I/O, halo-free windows of <= 64 tokens, <= 64 chunks
 bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask);
@@ -70,7 +72,7 @@ bool window_bwd_gen_supported(const Geo& g, int io_dtype);
 cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                                   const float* kbar, const float* beta, const float* bias, long long bias_sh, const void* out,
                                   const void* dout, float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias,
-                                  cudaStream_t st);
+                                  cudaStream_t st, const float* lse = nullptr);
 
 // LARA (lara_generic.cu)
 struct LaraGeo {

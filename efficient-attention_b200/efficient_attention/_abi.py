@@ -71,14 +71,15 @@ def load():
         lib.eva_num_chunks.argtypes = [G]
         lib.eva_chunk_stats.argtypes = [G, V, V, V, P, A, P, P, P, P]
         lib.eva_window_attention.argtypes = [G, V, V, V, P, P, P, P, I64, P, P]
+        lib.eva_window_attention_lse.argtypes = [G, V, V, V, P, P, P, P, I64, P, P, ctypes.POINTER(ctypes.c_int32), P]
         lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
-        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P, P]
+        lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P, P, P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
-                   'eva_forward', 'eva_backward', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
+                   'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
             getattr(lib, fn).restype = ctypes.c_int
         if lib.eva_sm100_abi_version() != 3:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
@@ -221,18 +222,24 @@ def eva_forward(q, k, v, geom, ada, *, pad_mask=None, noise=None, bias=None, ret
                              bias_sh, _ptr(out), _ptr(ws), ws.numel(), ctypes.byref(path), _stream(q.device))
     _check(rc, 'eva_forward')
     del keep
+    path_id = path.value & 0xff
     if return_stats:
         assert geom.keep_stats, 'return_stats needs a geometry built with keep_stats=True'
         C = num_chunks(geom)
         n = B * H * C * D
         second = (n * 4 + 255) // 256 * 256
-        stats = (ws[:n * 4].view(torch.float32).view(B, H, C, D), ws[second:second + n * 4].view(torch.float32).view(B, H, C, D))
-        return (out, path.value, stats) if return_path else (out, stats)
-    return (out, path.value) if return_path else out
+        stats = [ws[:n * 4].view(torch.float32).view(B, H, C, D), ws[second:second + n * 4].view(torch.float32).view(B, H, C, D)]
+        if path.value & 0x100:               # the row log-sum-exp was kept too: the last region of the workspace
+            nl = B * H * N * 4
+            off = nbytes.value - (nl + 255) // 256 * 256
+            stats.append(ws[off:off + nl].view(torch.float32).view(B, H, N))
+        stats = tuple(stats)
+        return (out, path_id, stats) if return_path else (out, stats)
+    return (out, path_id) if return_path else out
 
 
 def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None, bias=None, want_bias_grad=False, stats=None,
-                 packed_out=False):
+                 packed_out=False, lse=None):
     """Gradients of eva_forward / eva_window_attention (`ada` None for chunk-less geometries).
     Returns (grad_qkv float32 [3, B, N, H, D], grad_bias float32 like bias or None, chunk_rows float32 [12, B, H, C, D] or None --
     the slots are listed at eva_backward in include/eva_sm100.h).  packed_out: grad_qkv is returned in q's dtype in the packed
@@ -241,7 +248,10 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     _require_cuda(q, k, v, out, grad_out, pad_mask, noise, bias)
     B, N, H, D = q.shape
     C = num_chunks(geom) if geom.chunk > 0 else 0
-    k_bar, beta = stats if stats is not None else (None, None)
+    k_bar, beta = stats[:2] if stats else (None, None)
+    if lse is None and stats and len(stats) > 2:
+        lse = stats[2]
+    assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous())
     assert k_bar is None or (k_bar.dtype == torch.float32 and k_bar.is_contiguous() and beta.is_contiguous())
     mask = _mask_u8(pad_mask, B, N)
     noise = _f32(noise)
@@ -257,7 +267,7 @@ def eva_backward(q, k, v, geom, ada, out, grad_out, *, pad_mask=None, noise=None
     with torch.cuda.device(q.device):
         rc = lib.eva_backward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
                               ctypes.byref(heads_view(v)), _ptr(mask), None if ada_s is None else ctypes.byref(ada_s), _ptr(noise),
-                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(k_bar), _ptr(beta), _ptr(grad_qkv), _ptr(grad_io),
+                              _ptr(bias), bias_sh, _ptr(out), _ptr(grad_out), _ptr(k_bar), _ptr(beta), _ptr(lse), _ptr(grad_qkv), _ptr(grad_io),
                               _ptr(grad_bias), _ptr(rows), _stream(q.device))
     _check(rc, 'eva_backward')
     del keep
@@ -283,7 +293,8 @@ def eva_chunk_stats(q, k, v, geom, ada, *, pad_mask=None, noise=None):
     return k_bar, beta
 
 
-def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None, bias=None):
+def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None, bias=None, return_lse=False):
+    """return_lse: also the row log-sum-exp [B, H, N] float32 the backward can reuse, or None when the kernel that ran keeps none."""
     lib = load()
     _require_cuda(q, k, v, pad_mask, k_bar, beta, bias)
     B, N, H, D = q.shape
@@ -292,11 +303,15 @@ def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None,
     k_bar, beta = _f32(k_bar), _f32(beta)
     out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
     bias_sh = 0 if bias is None or bias.shape[0] == 1 else bias.shape[1] * bias.shape[2]
+    lse = torch.empty(B, H, N, dtype=torch.float32, device=q.device) if return_lse else None
+    written = ctypes.c_int32(0)
     with torch.cuda.device(q.device):
-        rc = lib.eva_window_attention(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
-                                      ctypes.byref(heads_view(v)), _ptr(mask), _ptr(k_bar), _ptr(beta), _ptr(bias),
-                                      bias_sh, _ptr(out), _stream(q.device))
+        rc = lib.eva_window_attention_lse(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                          ctypes.byref(heads_view(v)), _ptr(mask), _ptr(k_bar), _ptr(beta), _ptr(bias),
+                                          bias_sh, _ptr(out), _ptr(lse), ctypes.byref(written), _stream(q.device))
     _check(rc, 'eva_window_attention')
+    if return_lse:
+        return out, (lse if written.value else None)
     return out
 
 

@@ -139,7 +139,7 @@ def _cuda_backward(saved, meta, need, grad_out, packed_out=False):
     """`eva_backward` on the saved (q, k, v, noise, bias, 8 parameters, out); need = needs_input_grad of (bias, 8 parameters).
     Returns (float32 [3, B, N, H, D] = dq | dk | dv -- or, packed_out, q's dtype [B, N, 3, H, D] --, (d bias, 8 parameter gradients))."""
     q, k, v, noise, bias, wq, bq, gq, betq, wk, bk, gk, betk, out = saved[:14]
-    stats = tuple(saved[14:16]) if len(saved) >= 16 else None          # (k_bar, beta) kept by the forward
+    stats = tuple(saved[14:]) if len(saved) >= 16 else None            # (k_bar, beta[, row log-sum-exp]) kept by the forward
     geom = _abi.eva_geometry(q, **meta['geometry'])
     ada = _abi.adaptive(wq, bq, gq, betq, wk, bk, gk, betk, mu_coeff=meta['mu_coeff'])
     gqkv, gbias, rows = _abi.eva_backward(q, k, v, geom, ada, out, grad_out, pad_mask=meta['pad_mask'], noise=noise, bias=bias,
@@ -248,18 +248,21 @@ class WindowCoreFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, bias, meta):
         geom = _abi.eva_geometry(q, **meta['geometry'])
-        out = _abi.eva_window_attention(q, k, v, geom, pad_mask=meta['pad_mask'], bias=None if bias is None else bias.detach())
+        out, lse = _abi.eva_window_attention(q, k, v, geom, pad_mask=meta['pad_mask'], bias=None if bias is None else bias.detach(),
+                                             return_lse=True)
         ctx.meta = meta
-        ctx.save_for_backward(q, k, v, bias, out)
+        ctx.has_lse = lse is not None
+        ctx.save_for_backward(q, k, v, bias, out, *(() if lse is None else (lse,)))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        q, k, v, bias, out = ctx.saved_tensors
+        q, k, v, bias, out = ctx.saved_tensors[:5]
+        lse = ctx.saved_tensors[5] if ctx.has_lse else None
         need = ctx.needs_input_grad
         geom = _abi.eva_geometry(q, **ctx.meta['geometry'])
         gqkv, gbias, _ = _abi.eva_backward(q, k, v, geom, None, out, grad_out, pad_mask=ctx.meta['pad_mask'], bias=bias,
-                                           want_bias_grad=bias is not None and need[3])
+                                           want_bias_grad=bias is not None and need[3], lse=lse)
         return (gqkv[0].to(q.dtype) if need[0] else None, gqkv[1].to(k.dtype) if need[1] else None,
                 gqkv[2].to(v.dtype) if need[2] else None, None if gbias is None else gbias.to(bias.dtype), None)
 

@@ -112,11 +112,20 @@ int eva_window_attention(const EvaGeometry* g, const EvaHeadsView* q, const EvaH
                          const uint8_t* pad_mask, const float* k_bar, const float* beta,
                          const float* bias, int64_t bias_stride_h, void* out, void* stream);
 
+/* eva_window_attention that also keeps, for the backward, the log-sum-exp of every query row (base-2 logarithm, logits multiplied by
+ * log2 e): lse float32 [batch, heads, tokens].  *lse_written = 1 when the kernel that ran wrote it (the tcgen05 kernels do; the
+ * CUDA-core kernel does not: eva_backward then recomputes it), else 0.  lse / lse_written may be NULL. */
+int eva_window_attention_lse(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
+                             const uint8_t* pad_mask, const float* k_bar, const float* beta, const float* bias, int64_t bias_stride_h,
+                             void* out, float* lse, int32_t* lse_written, void* stream);
+
 /* Bytes of scratch eva_forward needs (k_bar + beta + fast-path staging); 256-byte aligned. */
 int eva_forward_workspace_bytes(const EvaGeometry* g, size_t* bytes);
 
 /* Both stages in one call.  *path_taken (optional) receives 1 when the fused sm_100a kernel ran,
- * 2 when the generic statistics kernel + the tcgen05 causal window kernel ran, 0 when the generic two-stage path ran. */
+ * 2 when the generic statistics kernel + the tcgen05 causal window kernel ran, 0 when the generic two-stage path ran; with
+ * g->keep_stats, bit 0x100 is set in addition when the log-sum-exp of every query row (float32 [batch, heads, tokens], base 2) was
+ * left in the LAST align256(batch * heads * tokens * 4) bytes of the workspace. */
 int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                 const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise,
                 const float* bias, int64_t bias_stride_h, void* out, void* workspace, size_t workspace_bytes,
@@ -139,11 +148,12 @@ int eva_forward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
  *                  the caller's library: dW = dy^T mean, db = sum dy, d gain = sum dout * n, d ln_bias = sum dout.
  *   ada            may be NULL iff g->chunk == 0.
  *   k_bar, beta    the forward's chunk statistics (eva_forward with g->keep_stats, or eva_chunk_stats), or both NULL: recomputed
- *                  into slots 0 / 1. */
+ *                  into slots 0 / 1.
+ *   lse            the forward's row log-sum-exp (eva_forward: path_taken & 0x100; eva_window_attention_lse), or NULL: recomputed. */
 int eva_backward(const EvaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v,
                  const uint8_t* pad_mask, const EvaAdaptive* ada, const float* noise, const float* bias, int64_t bias_stride_h,
-                 const void* out, const void* grad_out, const float* k_bar, const float* beta, float* grad_qkv, void* grad_qkv_io,
-                 float* grad_bias, float* chunk_rows, void* stream);
+                 const void* out, const void* grad_out, const float* k_bar, const float* beta, const float* lse, float* grad_qkv,
+                 void* grad_qkv_io, float* grad_bias, float* chunk_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LARA (lara.py).  Landmarks are the pooled q/k summaries; samples S = landmarks C, or 2C with

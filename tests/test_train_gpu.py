@@ -174,8 +174,9 @@ def test_forward_keeps_the_chunk_statistics_for_the_backward(seq_shape, window, 
     ada = _abi.adaptive(*[ada_t[n] for n in ('wq', 'bq', 'gq', 'betq', 'wk', 'bk', 'gk', 'betk')], mu_coeff=0.5)
     noise = torch.randn(B, H, _recompute.num_chunks_of(seq_shape, chunk), d, generator=g).to(dev)
     geometry = dict(seq_shape=seq_shape, window=window, ext=0, chunk=chunk, chunk_ext=0)
-    out, path, (k_bar, beta) = _abi.eva_forward(q, k, v, _abi.eva_geometry(q, keep_stats=True, **geometry), ada, noise=noise,
-                                                return_path=True, return_stats=True)
+    out, path, stats = _abi.eva_forward(q, k, v, _abi.eva_geometry(q, keep_stats=True, **geometry), ada, noise=noise,
+                                        return_path=True, return_stats=True)
+    k_bar, beta = stats[:2]
     assert path == expect_path
     ref_out = _abi.eva_forward(q, k, v, _abi.eva_geometry(q, **geometry), ada, noise=noise)
     assert torch.equal(out, ref_out)
