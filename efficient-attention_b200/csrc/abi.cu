@@ -317,6 +317,20 @@ int eva_backward(const EvaGeometry* gin, const EvaHeadsView* q, const EvaHeadsVi
   return e == cudaSuccess ? EVA_OK : cuda_fail(e, "eva_backward");
 }
 
+int lara_backward_step(int32_t which, int32_t io_dtype, void* X, void* Y, const void* dW, void* M2, const float* v0, const float* v1,
+                       const float* v2, const float* v3, float* o0, float* o1, float* o2, int64_t x_item_stride, int64_t y_item_stride,
+                       int32_t items, int32_t landmarks, int32_t tokens, float scale, float alpha_coeff, void* stream) {
+  if (which < 0 || which > 2) return fail(EVA_ERR_INVALID, "which must be 0, 1 or 2");
+  if (io_dtype < EVA_F32 || io_dtype > EVA_BF16) return fail(EVA_ERR_INVALID, "unknown io_dtype %d", io_dtype);
+  if (items <= 0 || landmarks <= 0 || tokens <= 0) return fail(EVA_ERR_INVALID, "items / landmarks / tokens must be positive");
+  if (!X || !v0 || (which != 1 && !Y) || (which == 1 && (!dW || !M2 || !v1 || !v2 || !v3 || !o0 || !o1 || !o2)) || (which == 0 && (!o0 || !o1)))
+    return fail(EVA_ERR_INVALID, "lara_backward_step(%d): a required pointer is NULL", which);
+  if (which == 1 && items > 65535) return fail(EVA_ERR_UNSUPPORTED, "more than 65535 (batch x head) items in one call");
+  const cudaError_t e = eva::launch_lara_bwd(which, io_dtype, X, Y, dW, M2, v0, v1, v2, v3, o0, o1, o2, x_item_stride, y_item_stride, items,
+                                             landmarks, tokens, scale, alpha_coeff, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? EVA_OK : cuda_fail(e, "lara_backward_step");
+}
+
 // ---------------------------------------------------------------------------------------------
 static int make_lara_geo(const LaraGeometry* in, eva::LaraGeo* g) {
   if (!in) return fail(EVA_ERR_INVALID, "geometry is NULL");

@@ -92,4 +92,10 @@ cudaError_t launch_lara(const LaraGeo& g, int io_dtype, const View& q, const Vie
                         const uint8_t* mask, const EvaAdaptive& proj, const float* noise, void* out,
                         void* workspace, cudaStream_t st, const float* given_landmarks = nullptr);
 
+// LARA backward helpers (lara_backward.cu): which = 0 rows1 (X, Bm, v0 = k2s -> o0 = lse_B, o1 = lse_T), 1 cols (X, dW, M2, v0 = q2s, v1 = bh,
+// v2 = lp, v3 = lse_B -> o0 = d lse_B, o1 = d bh, o2 = R; zeroed by the caller), 2 row_affine (X <- Bm o (X - v0 + v1), item strides xs / ys)
+cudaError_t launch_lara_bwd(int which, int io_dtype, void* X, void* Bm, const void* dW, void* M2, const float* v0, const float* v1,
+                            const float* v2, const float* v3, float* o0, float* o1, float* o2, long long xs, long long ys, int BH, int C,
+                            int N, float s, float coeff, cudaStream_t st);
+
 }  // namespace eva

@@ -75,11 +75,13 @@ def load():
         lib.eva_forward_workspace_bytes.argtypes = [G, ctypes.POINTER(SZ)]
         lib.eva_forward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, SZ, ctypes.POINTER(ctypes.c_int32), P]
         lib.eva_backward.argtypes = [G, V, V, V, P, A, P, P, I64, P, P, P, P, P, P, P, P, P, P]
+        lib.lara_backward_step.argtypes = [ctypes.c_int32, ctypes.c_int32, P, P, P, P, P, P, P, P, P, P, P, I64, I64, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_float, ctypes.c_float, P]
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
-                   'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
+                   'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_backward_step', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
             getattr(lib, fn).restype = ctypes.c_int
         if lib.eva_sm100_abi_version() != 3:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
@@ -313,6 +315,18 @@ def eva_window_attention(q, k, v, geom, *, k_bar=None, beta=None, pad_mask=None,
     if return_lse:
         return out, (lse if written.value else None)
     return out
+
+
+def lara_backward_step(which, X, Y=None, *, dW=None, M2=None, v0=None, v1=None, v2=None, v3=None, o0=None, o1=None, o2=None,
+                       x_item_stride=0, y_item_stride=0, items, landmarks, tokens, scale, alpha_coeff=0.0):
+    """One of the three fused steps of the LARA backward (see lara_backward_step in include/eva_sm100.h)."""
+    lib = load()
+    _require_cuda(X, Y, dW, M2, v0, v1, v2, v3, o0, o1, o2)
+    with torch.cuda.device(X.device):
+        rc = lib.lara_backward_step(which, io_dtype(X), _ptr(X), _ptr(Y), _ptr(dW), _ptr(M2), _ptr(v0), _ptr(v1), _ptr(v2), _ptr(v3),
+                                    _ptr(o0), _ptr(o1), _ptr(o2), x_item_stride, y_item_stride, items, landmarks, tokens, scale,
+                                    alpha_coeff, _stream(X.device))
+    _check(rc, 'lara_backward_step')
 
 
 def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_type, sample_mode, zero_padded,

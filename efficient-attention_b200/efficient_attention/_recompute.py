@@ -21,7 +21,7 @@ from . import _abi
 
 MASK_VAL = -5.0e4          # eva.py:139, causal_eva.py:488
 _BACKWARD_IMPL = os.environ.get('EVA_SM100_BACKWARD', 'cuda')
-_LARA_BACKWARD_IMPL = os.environ.get('EVA_SM100_LARA_BACKWARD', 'explicit')     # 'explicit' | 'autograd'
+_LARA_BACKWARD_IMPL = os.environ.get('EVA_SM100_LARA_BACKWARD', 'fused')        # 'fused' | 'explicit' | 'autograd'
 
 
 def set_backward_impl(name):
@@ -425,6 +425,45 @@ def _lara_stage2_backward(qf, kf, vf, gf, q_bar, omega, lp, bh, coeff):
     return dq, dk, dv, dqbar, domega, -dlseB, dbh
 
 
+def _lara_stage2_backward_fused(qc, kc, vc, gc, q_bar, omega, lp, bh, coeff):
+    """`_lara_stage2_backward` with the row / column softmax algebra in three fused kernels (`lara_backward_step` of libeva_sm100)
+    and the GEMMs as batched library calls in the activation format.  qc, kc, vc, gc: [BH, N, d] contiguous (16-bit or float32);
+    q_bar, omega [BH, C, d], lp, bh [BH, C] float32.  Returns float32 (dq, dk, dv [BH, N, d], d q_bar, d omega [BH, C, d], d lp, d bh
+    [BH, C])."""
+    BH, N, d = qc.shape
+    C = omega.shape[1]
+    s = d ** -0.5
+    dt_ = qc.dtype
+    f32 = dict(dtype=torch.float32, device=qc.device)
+    OQ = torch.cat([omega, q_bar], 1).to(dt_)                                   # [BH, 2C, d]
+    om = OQ[:, :C]
+    X = OQ @ qc.transpose(1, 2)                                                 # [BH, 2C, N]: omega q^T | q_bar q^T
+    Bm = om @ kc.transpose(1, 2)                                                # [BH, C, N]:  omega k^T
+    q2s = (0.5 * s) * (qc.float() ** 2).sum(-1)
+    k2s = (0.5 * s) * (kc.float() ** 2).sum(-1)
+    lseB, lseT = torch.empty(BH, C, **f32), torch.empty(BH, C, **f32)
+    kw = dict(items=BH, landmarks=C, tokens=N, scale=s)
+    _abi.lara_backward_step(0, X, Bm, v0=k2s, o0=lseB, o1=lseT, **kw)           # X[:, C:] = t, Bm = Pk
+    kv = Bm @ vc                                                                # [BH, C, d]
+    dW = kv @ gc.transpose(1, 2)                                                # [BH, C, N]
+    M2 = torch.empty(BH, 2 * C, N, dtype=dt_, device=qc.device)
+    sums = torch.zeros(3, BH, C, **f32)                                         # d lse_B | d bh | R
+    _abi.lara_backward_step(1, X, None, dW=dW, M2=M2, v0=q2s, v1=bh.contiguous(), v2=lp.contiguous(), v3=lseB, o0=sums[0], o1=sums[1],
+                            o2=sums[2], alpha_coeff=coeff, **kw)                # X[:, :C] = W, M2 = [dlw ; dt]
+    dlseB, dbh, R = sums[0], sums[1], sums[2]
+    _abi.lara_backward_step(2, M2[:, C:], X[:, C:], v0=R, x_item_stride=2 * C * N, y_item_stride=2 * C * N, **kw)       # dT = t (dt - R)
+    dkv = X[:, :C] @ gc                                                         # [BH, C, d]
+    E = (dkv.float() * kv.float()).sum(-1)
+    dBk = dkv @ vc.transpose(1, 2)                                              # dPk, then dBk in place
+    _abi.lara_backward_step(2, dBk, Bm, v0=E, v1=dlseB, x_item_stride=C * N, y_item_stride=C * N, **kw)
+    dOQ = s * (M2 @ qc).float()                                                 # [BH, 2C, d]: d omega (A part) | d q_bar
+    domega = dOQ[:, :C] + s * (dBk @ kc).float()
+    dq = s * (M2.transpose(1, 2) @ OQ).float()                                  # the - sum_c dlw q_n term vanishes: columns of dlw sum to 0
+    dk = s * ((dBk.transpose(1, 2) @ om).float() - dBk.float().sum(1).unsqueeze(-1) * kc.float())
+    dv = (Bm.transpose(1, 2) @ dkv).float()
+    return dq, dk, dv, dOQ[:, C:], domega, -dlseB, dbh
+
+
 class LaraCoreFn(torch.autograd.Function):
     """forward: `lara_forward` of libeva_sm100 (landmarks given by the caller when `dense`); backward: autograd through
     `lara_core_torch` on the saved inputs."""
@@ -457,10 +496,21 @@ class LaraCoreFn(torch.autograd.Function):
             bh = torch.exp(lp - torch.logsumexp(Lm, -1, keepdim=True))
         B, N, H, d = saved[0].shape
         with torch.no_grad():
-            gf = grad_out.reshape(B, N, H, d).permute(0, 2, 1, 3).float()
-            dq2, dk2, dv2, dqbar, domega, dlp, dbh = _lara_stage2_backward(
-                qh.detach().contiguous(), kh.detach().contiguous(), vh.detach().contiguous(), gf.contiguous(), q_bar.detach(),
-                omega.detach(), lp.detach(), bh.detach(), kk['alpha_coeff'])
+            if _LARA_BACKWARD_IMPL == 'fused':
+                C = omega.shape[2]
+                flat = lambda t: t.detach().permute(0, 2, 1, 3).reshape(B * H, N, d).contiguous()          # [B, N, H, d] -> [BH, N, d]
+                gq = grad_out.reshape(B, N, H, d).to(saved[0].dtype)
+                r = _lara_stage2_backward_fused(flat(saved[0]), flat(saved[1]), flat(saved[2]), flat(gq), q_bar.detach().float().reshape(B * H, C, d),
+                                                omega.detach().float().reshape(B * H, C, d), lp.detach().float().reshape(B * H, C),
+                                                bh.detach().float().reshape(B * H, C), kk['alpha_coeff'])
+                dq2, dk2, dv2 = (t.view(B, H, N, d) for t in r[:3])
+                dqbar, domega = r[3].view(B, H, C, d), r[4].view(B, H, C, d)
+                dlp, dbh = r[5].view(B, H, C, 1), r[6].view(B, H, C, 1)
+            else:
+                gf = grad_out.reshape(B, N, H, d).permute(0, 2, 1, 3).float()
+                dq2, dk2, dv2, dqbar, domega, dlp, dbh = _lara_stage2_backward(
+                    qh.detach().contiguous(), kh.detach().contiguous(), vh.detach().contiguous(), gf.contiguous(), q_bar.detach(),
+                    omega.detach(), lp.detach(), bh.detach(), kk['alpha_coeff'])
         wanted = [t for t in ins if t is not None and t.requires_grad]
         g1 = torch.autograd.grad([q_bar, omega, lp, bh], wanted, [dqbar, domega, dlp, dbh], allow_unused=True)
         direct = {id(q): dq2, id(k): dk2, id(v): dv2}
@@ -487,8 +537,9 @@ class LaraCoreFn(torch.autograd.Function):
         # float32 activations: explicit float32 formulas for the [C, N]-sized part (exact, nothing of that size kept by autograd);
         # 16-bit activations: autograd under autocast below is as fast (tensor-core GEMMs) and is what the reference trains with
         # (measured, DeiT-small-p16 + LARA step at batch 128, fp16: 66.3 ms autograd / autocast, 68.0 ms explicit float32)
-        if (_LARA_BACKWARD_IMPL == 'explicit' and saved[0].dtype == torch.float32 and kk0['mis_type'] == 'mis-opt' and
-                meta['pad_mask'] is None and (saved[3] is None or kk0['sample_mode'] == _abi.LARA_SAMPLE_SINGLE)):
+        if (_LARA_BACKWARD_IMPL in ('explicit', 'fused') and (_LARA_BACKWARD_IMPL == 'fused' or saved[0].dtype == torch.float32) and
+                kk0['mis_type'] == 'mis-opt' and meta['pad_mask'] is None and
+                (saved[3] is None or kk0['sample_mode'] == _abi.LARA_SAMPLE_SINGLE)):
             return LaraCoreFn._backward_explicit(saved, meta, need, grad_out)
         half = saved[0].dtype in (torch.float16, torch.bfloat16)       # 16-bit activations: differentiate under autocast, as the reference trains
         with torch.enable_grad(), torch.autocast('cuda', dtype=saved[0].dtype if half else torch.float16, enabled=half):

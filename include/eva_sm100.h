@@ -192,6 +192,19 @@ int lara_forward_given_landmarks(const LaraGeometry* g, const EvaHeadsView* q, c
                                  const uint8_t* pad_mask, const float* landmarks, const float* noise,
                                  void* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* LARA backward (what autograd derives from lara.py:201-246, mis-opt estimator, one sample per landmark, no padding mask): the three
+ * fused steps BETWEEN the batched GEMMs of the explicit gradient.  Matrices are row-major [items][rows][tokens] in io_dtype
+ * (items = batch x heads); vectors float32.
+ *   which = 0  rows:  X [items, 2C, N] rows [C, 2C) = q_bar q^T in -> t = softmax_n(scale .) out;  Y [items, C, N] = omega k^T in ->
+ *              Pk = softmax_m(scale . - v0) out, v0 [items, N] = scale |k|^2 / 2;  o0 = lse_B, o1 = lse_T [items, C]
+ *   which = 1  columns:  X rows [0, C) = omega q^T in -> W = softmax_c(log w) out, rows [C, 2C) = t;  dW [items, C, N] = kv dO^T;
+ *              M2 [items, 2C, N] out: rows [0, C) = d log w, rows [C, 2C) = dt;  v0 [items, N] = scale |q|^2 / 2, v1 = bh, v2 = lp,
+ *              v3 = lse_B [items, C];  o0 += sum_n d log w, o1 += sum_n d alpha, o2 += sum_n t dt  [items, C], zeroed by the caller
+ *   which = 2  rows:  X <- Y o (X - v0 + v1), rows of X / Y at x_item_stride / y_item_stride elements per item; v1 may be NULL */
+int lara_backward_step(int32_t which, int32_t io_dtype, void* X, void* Y, const void* dW, void* M2, const float* v0, const float* v1,
+                       const float* v2, const float* v3, float* o0, float* o1, float* o2, int64_t x_item_stride, int64_t y_item_stride,
+                       int32_t items, int32_t landmarks, int32_t tokens, float scale, float alpha_coeff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
