@@ -484,13 +484,17 @@ class LaraCoreFn(torch.autograd.Function):
         formulas (`_lara_stage2_backward`: batched GEMMs + row / column softmax algebra, float32), only the landmark stage
         (`_lara_stage1`, tensors of size [C, d] plus the pooling) goes through autograd."""
         kk = meta['kernel']
-        with torch.enable_grad():
+        # 16-bit activations with the fused kernels: the landmark stage runs under autocast on the 16-bit q, k, v (no float32 copies of
+        # the activations); its outputs (LayerNorm / softmax results) are float32 either way
+        half = _LARA_BACKWARD_IMPL == 'fused' and saved[0].dtype in (torch.float16, torch.bfloat16)
+        with torch.enable_grad(), torch.autocast('cuda', dtype=saved[0].dtype if half else torch.float16, enabled=half):
             ins = [None if t is None else t.detach().requires_grad_(n and t.is_floating_point()) for t, n in zip(saved, need)]
             q, k, v, noise, wq, bq, gq, betq, wk, bk, gk, betk = ins
             qh, kh, vh, q_bar, mu, omega, _ = _lara_stage1(
                 q, k, v, seq_shape=kk['seq_shape'], landmarks=kk['landmarks'], per_token_proj=kk['per_token_proj'], mixed=kk['mixed'],
                 sample_mode=kk['sample_mode'], zero_padded=False, wq=wq, bq=bq, gq=gq, betq=betq, wk=wk, bk=bk, gk=gk, betk=betk,
-                dense=meta['dense'], ln_eps=meta['ln_eps'], pad_mask=None, noise=noise, keep_dtype=False)
+                dense=meta['dense'], ln_eps=meta['ln_eps'], pad_mask=None, noise=noise, keep_dtype=half)
+            q_bar, mu, omega = q_bar.float(), mu.float(), omega.float()
             Lm = _prm(mu, omega)
             lp = torch.diagonal(Lm, dim1=-1, dim2=-2).unsqueeze(-1)
             bh = torch.exp(lp - torch.logsumexp(Lm, -1, keepdim=True))
@@ -512,7 +516,8 @@ class LaraCoreFn(torch.autograd.Function):
                     qh.detach().contiguous(), kh.detach().contiguous(), vh.detach().contiguous(), gf.contiguous(), q_bar.detach(),
                     omega.detach(), lp.detach(), bh.detach(), kk['alpha_coeff'])
         wanted = [t for t in ins if t is not None and t.requires_grad]
-        g1 = torch.autograd.grad([q_bar, omega, lp, bh], wanted, [dqbar, domega, dlp, dbh], allow_unused=True)
+        g1 = torch.autograd.grad([q_bar, omega, lp, bh], wanted, [dqbar.to(q_bar.dtype), domega.to(omega.dtype), dlp.to(lp.dtype),
+                                                                   dbh.to(bh.dtype)], allow_unused=True)
         direct = {id(q): dq2, id(k): dk2, id(v): dv2}
         it = iter(g1)
         res = []

@@ -246,6 +246,28 @@ def test_generic_tcgen05_backward_kernel_matches_the_cuda_core_kernel(seq_shape,
         assert rel_l2(a_.cpu(), b_.cpu()) < (3e-3 if dtype == torch.float16 else 1.5e-2), (n_, rel_l2(a_.cpu(), b_.cpu()))
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.float16, 2e-2), (torch.bfloat16, 6e-2)])
+def test_lara_fused_backward_steps_match_the_explicit_formulas(dtype, tol):
+    """`_lara_stage2_backward_fused` (three `lara_backward_step` kernels between batched GEMMs in the activation format) against
+    `_lara_stage2_backward` (the same formulas in float32 PyTorch ops) on random inputs."""
+    from efficient_attention import _recompute
+    dev = _dev()
+    B, H, N, C, d = 2, 3, 196, 49, 64
+    g = torch.Generator().manual_seed(7)
+    q, k, v, go = (torch.randn(B, H, N, d, generator=g).to(dev) for _ in range(4))
+    q, k, v, go = (t.to(dtype).float() for t in (q, k, v, go))                     # identical values on both sides
+    q_bar, omega = (0.5 * torch.randn(B, H, C, d, generator=g).to(dev) for _ in range(2))
+    lp = torch.randn(B, H, C, 1, generator=g).to(dev)
+    bh = torch.softmax(torch.randn(B, H, C, 1, generator=g), 2).to(dev)
+    want = _recompute._lara_stage2_backward(q, k, v, go, q_bar, omega, lp, bh, 2.0)
+    flat = lambda t: t.reshape(B * H, *t.shape[2:]).contiguous()
+    got = _recompute._lara_stage2_backward_fused(flat(q).to(dtype), flat(k).to(dtype), flat(v).to(dtype), flat(go).to(dtype), flat(q_bar), flat(omega),
+                                                 flat(lp).squeeze(-1), flat(bh).squeeze(-1), 2.0)
+    for name, a_, b_ in zip(('dq', 'dk', 'dv', 'dq_bar', 'domega', 'dlp', 'dbh'), got, want):
+        assert torch.isfinite(a_).all(), name
+        assert rel_l2(a_.reshape(-1).cpu(), b_.reshape(-1).cpu()) < tol, (name, rel_l2(a_.reshape(-1).cpu(), b_.reshape(-1).cpu()))
+
+
 def _grads_of(module, cfg, a, dev, dtype):
     """loss = <y, w> for a fixed w; returns y, dL/dx and {name: dL/dparam}."""
     x = a['x'].to(device=dev, dtype=dtype).requires_grad_(True)
