@@ -109,8 +109,11 @@ template <int W, int GW, int CH, int NR, int G> struct Cfg {
   static constexpr int kShared = kP2Bytes > kOStageBytes ? (kP2Bytes > 8192 ? kP2Bytes : 8192) : (kOStageBytes > 8192 ? kOStageBytes : 8192);
   static constexpr int kLbuf = (kOm + kShared + 1023) & ~1023;   // NT x [128] fp32 logit exchange
   static constexpr int kPool = kLbuf + ((NT * 128 * 4 + 1023) & ~1023);   // KBLK x [CW][128 B] pooling weights (constant)
-  static constexpr int kBias = kPool + KBLK * kBlk;    // [L][LS] fp32, x log2(e)
-  static constexpr int kBiasSlab = (L * LS * 4 + 15) & ~15;
+  // bias slab: [L][LS] x log2(e), float32 -- except with four chunk-rows per tile, where a 16-bit slab frees the 4.8 KB the larger
+  // pooling / P2 tiles need (values ~1e-1 rounded to 11 bits: far below the 16-bit P the logits feed)
+  static constexpr bool kHalfBias = G == 4;
+  static constexpr int kBias = kPool + KBLK * kBlk;
+  static constexpr int kBiasSlab = (L * LS * (kHalfBias ? 2 : 4) + 15) & ~15;
   static constexpr int kZeroEnd = kBias + kBiasSlab;
   static constexpr int kLn = kZeroEnd;                 // [6][64] fp32: b_q, gain_q, beta_q, b_k, gain_k, beta_k
   static constexpr int kBars = (kLn + 6 * 64 * 4 + 7) & ~7;
@@ -775,6 +778,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         // Shift by M = scale*max_j(raw) + max_j(bias) >= true row max (softmax is shift invariant; M only has to
         // prevent overflow and sits within max|bias| of the true max, far inside fp16's range for P).
         const float* brow = bias2 + ic * LS;
+        const __half* hrow = reinterpret_cast<const __half*>(bias2) + ic * LS;       // (kHalfBias instantiations)
         float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
         for (int j = 0; j < L; ++j) {
@@ -788,7 +792,7 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
           if ((c & 3) == 0) r0 = fmaxf(r0, sr[c]); else if ((c & 3) == 1) r1 = fmaxf(r1, sr[c]);
           else if ((c & 3) == 2) r2 = fmaxf(r2, sr[c]); else r3 = fmaxf(r3, sr[c]);
         }
-        const float bmax = p.bias2 ? brow[L] : 0.f;
+        const float bmax = p.bias2 ? (C::kHalfBias ? __half2float(hrow[L]) : brow[L]) : 0.f;
         const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2 + bmax;
         const float mrfa = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)) * scale_log2;
         const float mx = fmaxf(mloc, mrfa);
@@ -803,7 +807,14 @@ eva_fused_kernel(const __grid_constant__ CUtensorMap tw_q, const __grid_constant
         uint64_t acc0 = pk2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
         for (int m4 = 0; m4 < (L + 3) / 4; ++m4) {          // four keys per 16-byte bias load
-          const float4 bq = *reinterpret_cast<const float4*>(brow + 4 * m4);
+          float4 bq;
+          if constexpr (C::kHalfBias) {
+            const uint2 hb = *reinterpret_cast<const uint2*>(hrow + 4 * m4);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hb.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&hb.y));
+            bq = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            bq = *reinterpret_cast<const float4*>(brow + 4 * m4);
+          }
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int m = 2 * m4 + hh;                      // P word: keys 2m, 2m+1
@@ -967,7 +978,8 @@ static cudaError_t launch_t(const Geo& g, const View& q, const View& k, const Vi
   static const int ctas_per_sm = env_int("EVA_SM100_CTAS_PER_SM", 2);   // tuning knob, read once; 2 = as many as fit
   const int max_ctas = ctas_per_sm * sm_count(dev);
   const int grid = items < max_ctas ? items : max_ctas;
-  pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / 4, next_item, (unsigned)grid);
+  pack_params<<<32, 256, 0, st>>>(ada.w_q, ada.w_k, w16, bias, bias_sh, bias2, g.H, C::L, C::LS, C::kBiasSlab / (C::kHalfBias ? 2 : 4), next_item,
+                                  (unsigned)grid, C::kHalfBias ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *msg = "pack_params launch"; return e; }
   static thread_local MapCache cache;
@@ -1038,10 +1050,10 @@ static bool fused_disabled() {
 
 // geometry families the fused kernel is instantiated for: window 7, 49 chunks on a 28-wide (chunk 4) or
 // 14-wide (chunk 2) grid -- DeiT-tiny/small p8 and p16 (BASELINE configs c2, c3)
-// chunk-rows per pass-1 / pass-2 tile on the 14-wide grid (see Cfg): 2 keeps the P2 / pooling tiles inside the 113 KB a CTA may use.
-// G = 4 (one 112-token box per 4 rows) measured 0.24 ms against 0.28 ms for c2, but its [32][112] P2 / pooling tiles need 4.8 KB
-// more than there is: 15 KB ring slots cannot hold the 16 KB [W_q ; W_k] tile (tried: the overflow corrupts the next slot)
-constexpr int kG14 = 2;
+// chunk-rows per pass-1 / pass-2 tile on the 14-wide grid (see Cfg): G = 4 (one 112-token box per 4 rows); its [32][112] P2 / pooling
+// tiles need 4.8 KB more than G = 2 -- paid for by the 16-bit bias slab of this instantiation (Cfg::kHalfBias).  Round 1 tried to
+// make room with 15 KB ring slots instead: they cannot hold the 16 KB [W_q ; W_k] tile (the overflow corrupted the next slot)
+constexpr int kG14 = 4;
 static int fused_variant(const Geo& g) {
   if (g.window != 7 || g.n_chunks != 49) return 0;
   if (g.gw == 28 && g.gh == 28 && g.chunk == 4) return 1;

@@ -79,7 +79,7 @@ __device__ __forceinline__ int ktile_off(int n, int t, int blk) { return (t >> 6
 // bias [H or 1][L][L] -> per-head slabs [L][LS] fp32 pre-multiplied by log2(e)
 static __global__ void pack_params(const float* __restrict__ wq, const float* __restrict__ wk, __half* __restrict__ w16,
                             const float* __restrict__ bias, long long bias_sh, float* __restrict__ bias2, int H, int L,
-                            int LS, int slab_floats, unsigned int* next_item, unsigned int first_free_item) {
+                            int LS, int slab_floats, unsigned int* next_item, unsigned int first_free_item, int half_bias = 0) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the fused kernel may begin its prologue and first loads now
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) *next_item = first_free_item;          // items 0 .. grid-1 are taken by blockIdx, the rest are handed out dynamically
@@ -96,9 +96,13 @@ static __global__ void pack_params(const float* __restrict__ wq, const float* __
         val = bias[(long long)h * bias_sh + r * L + c] * kLog2e;
       } else if (r < L && c == L) {      // row maximum: lets the softmax bound its max without touching the bias
         val = -INFINITY;
-        for (int cc = 0; cc < L; ++cc) val = fmaxf(val, bias[(long long)h * bias_sh + r * L + cc] * kLog2e);
+        for (int cc = 0; cc < L; ++cc) {
+          const float bv = bias[(long long)h * bias_sh + r * L + cc] * kLog2e;
+          val = fmaxf(val, half_bias ? __half2float(__float2half_rn(bv)) : bv);      // the maximum of the values as they are stored
+        }
       }
-      bias2[j] = val;
+      if (half_bias) reinterpret_cast<__half*>(bias2)[j] = __float2half_rn(val);     // slab_floats then counts 16-bit elements
+      else bias2[j] = val;
     }
   }
 }
