@@ -23,6 +23,9 @@ run memcheck lara      "test_lara_core_many_items_vs_oracle_fp16"
 run memcheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel"
 run memcheck bwd_tc    "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel"
 run memcheck bwd_simt  "test_backward_kernels_equal_autograd_through_the_recomputation"
+run memcheck bwd_gen   "test_generic_tcgen05_backward_kernel_matches_the_cuda_core_kernel"
+run memcheck stats_fast "test_fast_chunk_statistics_kernel_matches_the_generic_one"
+run memcheck lara_bwd  "test_lara_fused_backward_steps_match_the_explicit_formulas"
 run racecheck fused28  "test_fused_kernel_variants_fp16 and 28-4-False and default and True-True"
 run racecheck cluster  "test_fused_kernel_variants_fp16 and 28-4-True and default and True-True"
 run racecheck causal   "test_causal_tcgen05_window_kernel_vs_oracle and 256-True-True and dtype0"
@@ -31,6 +34,9 @@ run racecheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel
 run synccheck window_tc "test_tcgen05_window_kernel_matches_the_cuda_core_kernel and seq_shape3"
 run racecheck bwd_tc   "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape0"
 run racecheck bwd_simt "test_backward_kernels_equal_autograd_through_the_recomputation and seq_shape2"
+run racecheck bwd_gen  "test_generic_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape2"
+run racecheck lara_bwd "test_lara_fused_backward_steps_match_the_explicit_formulas and dtype1"
+run synccheck bwd_gen  "test_generic_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape2"
 run synccheck bwd_tc   "test_tcgen05_backward_kernel_matches_the_cuda_core_kernel and seq_shape0"
 run synccheck fused28  "test_fused_kernel_variants_fp16 and 28-4-False and default and True-True"
 run synccheck cluster  "test_fused_kernel_variants_fp16 and 28-4-True and default and True-True"
