@@ -513,8 +513,48 @@ def other_shapes_leg(dev):
             del x
         except Exception as e:
             out[tag] = {'what': what, 'error': f'{type(e).__name__}: {e}'[:200]}
+    # the attention CORE of the same shapes through the C ABI (q, k, v resident in HBM): 20 launches back to back, CUDA events;
+    # roofline = algorithmic bytes (q, k, v in + o out = 4 C x 2 bytes per token) / time / measured HBM peak
+    def core_time(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 20
+    try:
+        with torch.no_grad():
+            x = torch.randn(2048, 14, 14, DIM, device=dev, dtype=torch.float16)
+            q, k, v, _ = eva._qkv_heads(x.reshape(2048, 196, DIM))
+            geom = _abi.eva_geometry(q, seq_shape=(14, 14), window=7, ext=0, chunk=2, chunk_ext=0)
+            ada, bias = eva._adaptive(), eva._local_bias().float().contiguous()
+            ms = core_time(lambda: _abi.eva_forward(q, k, v, geom, ada, bias=bias))
+            out['c2'].update(core_ms=ms, core_roofline_frac=4 * DIM * 2 * 196 * 2048 / (ms * 1e-3) / 1e9 / peak)
+            del x, q, k, v
+            x = torch.randn(512, 14, 14, 384, device=dev, dtype=torch.float16)
+            q, k, v, _ = lara._qkv_heads(x.reshape(512, 196, 384))
+            ms = core_time(lambda: _abi.lara_forward(q, k, v, seq_shape=(14, 14), landmarks=49, per_token_proj=False, mixed=1, mis_type='mis-opt',
+                                                     sample_mode=_abi.LARA_SAMPLE_SINGLE, zero_padded=False, alpha_coeff=2.0,
+                                                     proj=lara._proj_params(True), pad_mask=None, noise=None))
+            out['c4'].update(core_ms=ms, core_roofline_frac=4 * 384 * 2 * 196 * 512 / (ms * 1e-3) / 1e9 / peak)
+            del x, q, k, v
+            qkv = torch.randn(16, 4096, 3, 8, 64, device=dev, dtype=torch.float16)
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+            geom = _abi.eva_geometry(q, seq_shape=(4096,), window=256, ext=0, chunk=256, chunk_ext=0, causal=True, halo_left_only=True,
+                                     mask_queries=True, bias_toeplitz=True)
+            ada = causal._adaptive()
+            tb = causal.rel_pos_bias.dense(256, 256).unsqueeze(0).detach().float().contiguous()
+            ms = core_time(lambda: _abi.eva_forward(q, k, v, geom, ada, bias=tb))
+            out['c5'].update(core_ms=ms, core_roofline_frac=4 * 512 * 2 * 4096 * 16 / (ms * 1e-3) / 1e9 / peak)
+    except Exception as e:
+        out['core_error'] = f'{type(e).__name__}: {e}'[:300]
     out['note'] = ('module = qkv Linear + attention core + proj Linear, fp16, inputs resident in HBM; module_traffic_gbs_of_peak = '
-                   '10 C x 2 bytes per token (x in, qkv out + in, o out + in, y out) / time / measured HBM peak')
+                   '10 C x 2 bytes per token (x in, qkv out + in, o out + in, y out) / time / measured HBM peak; core_* = the attention '
+                   'core alone through the C ABI, 4 C x 2 bytes per token')
     return out
 
 
