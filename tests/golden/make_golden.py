@@ -47,6 +47,8 @@ def _lively_init(module, seed):
         with torch.no_grad():
             if name.endswith('relative_attention_bias.weight') or 'bias_table' in name:
                 p.copy_(torch.randn(p.shape, generator=g) * 0.7)
+            elif p.dim() == 3:                       # learnable random-feature projections keep their orthogonal init
+                continue
             elif p.dim() == 2:
                 p.copy_(torch.randn(p.shape, generator=g) * (1.3 / math.sqrt(p.shape[1])))
             elif name.endswith('.weight'):           # LayerNorm gain
@@ -189,10 +191,120 @@ def gen_causal(ref, name, *, T, B, dim, heads, window, chunk_size=None, num_chun
     _save(name, cfg, m.float(), dict(x=x, mask=mask, noise=noise, y=y))
 
 
+def _tail_mask(B, n, mask_tail):
+    if mask_tail is None:
+        return None
+    mask = torch.zeros(B, n, dtype=torch.bool)
+    for b, t in enumerate(mask_tail):
+        if t:
+            mask[b, n - t:] = True
+    return mask
+
+
+def gen_performer(ref, name, *, B, shape, dim, heads, method='favorp', approx=64, cos=False, scheme='default', mask_tail=None,
+                  train_seed=None, seed=0):
+    """kernelized_attention.py.  Training mode with sample_scheme 'default' draws a fresh Gaussian projection with torch.randn as
+    the first use of the global RNG in forward: it is re-derived from the seed and stored as `proj`."""
+    cfg = dict(kind='performer', dim=dim, num_heads=heads, proj_method=method, approx_attn_dim=approx, cos_weighting=cos,
+               sample_scheme=scheme, qkv_bias=True)
+    m = ref.AttentionFactory.build_attention('performer', dict(
+        dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, approx_attn_dim=approx,
+        proj_method=method, cos_weighting=cos, sample_scheme=scheme))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    mask = _tail_mask(B, int(np.prod(shape)), mask_tail)
+    y = _run(m, lambda mod: mod(x.double(), mask), train_seed)
+    proj = None
+    if train_seed is not None and scheme == 'default' and method in ('favorp', 'relu', 'fourier'):
+        torch.manual_seed(train_seed)
+        proj = torch.randn(heads, approx, dim // heads, dtype=torch.float64)
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, proj=proj, y=y))
+
+
+def gen_ra(ref, name, *, B, shape, dim, heads, num_samples, train_seed=None, eval_seed=1234, seed=0):
+    """randomized_attention.py.  The key index drawn with torch.multinomial (and the Gaussian noise of training mode, drawn after
+    it) are re-derived from the seed with the module's own q, k and stored as `k_ind` / `noise`."""
+    cfg = dict(kind='ra', dim=dim, num_heads=heads, num_samples=num_samples, qkv_bias=True)
+    m = ref.AttentionFactory.build_attention('ra', dict(
+        dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, num_samples=num_samples))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    m = m.double()
+    m.train(train_seed is not None)
+    rng_seed = train_seed if train_seed is not None else eval_seed
+    with torch.no_grad():
+        torch.manual_seed(rng_seed)
+        y = m(x.double(), None)
+        q, k, v = m.proj_and_split_heads(x.double())
+        b, h, n, d = q.shape
+        torch.manual_seed(rng_seed)
+        k_ind = None
+        mu_like = q + k                      # same memory layout as the reference's mu (randn_like fills in memory order)
+        if num_samples not in (0, -1):
+            pi = torch.softmax(torch.einsum('...nd,...md->...nm', m.scale * q, k), dim=-1)
+            k_ind = torch.multinomial(pi.reshape(b * h * n, n), 1, replacement=True).reshape(b, h, n)
+            mu_like = q + torch.gather(k, 2, k_ind.unsqueeze(-1).expand(-1, -1, -1, d))
+        noise = torch.randn_like(mu_like).contiguous() if train_seed is not None else None
+    _save(name, cfg, m.float(), dict(x=x, mask=None, k_ind=k_ind, noise=noise, y=y))
+
+
+def gen_scatterbrain(ref, name, *, B, shape, dim, heads, window, attn_2d, overlap=False, use_rpe=False, approx=64,
+                     mask_tail=None, train_seed=None, seed=0):
+    cfg = dict(kind='scatterbrain', dim=dim, num_heads=heads, window_size=window, attn_2d=attn_2d, overlap_window=overlap,
+               use_rpe=use_rpe, approx_attn_dim=approx, proj_method='favorp', qkv_bias=True)
+    m = ref.AttentionFactory.build_attention('scatterbrain', dict(
+        dim=dim, num_heads=heads, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False, use_rpe=use_rpe, window_size=window,
+        attn_2d=attn_2d, overlap_window=overlap, approx_attn_dim=approx))
+    _lively_init(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn((B,) + tuple(shape) + (dim,), generator=g)
+    mask = _tail_mask(B, int(np.prod(shape)), mask_tail)
+    y = _run(m, lambda mod: mod(x.double(), mask), train_seed)
+    proj = None
+    if train_seed is not None:
+        torch.manual_seed(train_seed)
+        proj = torch.randn(heads, approx, dim // heads, dtype=torch.float64)
+    _save(name, cfg, m.float(), dict(x=x, mask=mask, proj=proj, y=y))
+
+
+def main_rfa(ref):
+    # --- Performer (kernelized_attention.py) ---
+    gen_performer(ref, 'perf_favorp_2d', B=2, shape=(14, 14), dim=128, heads=2, seed=81)
+    gen_performer(ref, 'perf_favorp_mask', B=3, shape=(45,), dim=64, heads=2, mask_tail=[0, 7, 20], seed=83)
+    gen_performer(ref, 'perf_favorp_train', B=2, shape=(40,), dim=128, heads=2, train_seed=85, seed=84)
+    gen_performer(ref, 'perf_favorp_cos', B=2, shape=(33,), dim=64, heads=2, cos=True, approx=32, seed=86)
+    gen_performer(ref, 'perf_relu_fixed', B=2, shape=(8, 8), dim=64, heads=2, method='relu', scheme='fixed', seed=87)
+    gen_performer(ref, 'perf_fourier_learn', B=2, shape=(31,), dim=64, heads=4, method='fourier', scheme='learnable', approx=24, mask_tail=[0, 4], seed=89)
+    gen_performer(ref, 'perf_dpfp', B=2, shape=(29,), dim=64, heads=2, method='dpfp', approx=128, seed=91)
+    gen_performer(ref, 'perf_relu_only_cos', B=1, shape=(50,), dim=64, heads=2, method='relu-only', cos=True, seed=93)
+    gen_performer(ref, 'perf_sigmoid_only', B=2, shape=(6, 6), dim=128, heads=2, method='sigmoid-only', mask_tail=[0, 5], seed=95)
+    gen_performer(ref, 'perf_mlp_fourier', B=2, shape=(27,), dim=64, heads=2, method='mlp-fourier', approx=64, seed=97)
+    # --- randomized attention (randomized_attention.py) ---
+    gen_ra(ref, 'ra_mean', B=2, shape=(37,), dim=64, heads=2, num_samples=0, seed=101)
+    gen_ra(ref, 'ra_expect_2d', B=1, shape=(8, 8), dim=128, heads=2, num_samples=-1, seed=103)
+    gen_ra(ref, 'ra_sample', B=2, shape=(41,), dim=64, heads=2, num_samples=1, seed=105)
+    gen_ra(ref, 'ra_sample_train', B=2, shape=(14, 14), dim=128, heads=2, num_samples=1, train_seed=109, seed=107)
+    # --- ScatterBrain (scatterbrain_attention.py) ---
+    gen_scatterbrain(ref, 'sb_2d_rpe', B=2, shape=(14, 14), dim=128, heads=2, window=7, attn_2d=True, use_rpe=True, seed=111)
+    # overlap_window=True is not pinned: the reference returns NaN there (the zero-padded halo slots carry log-feature 0, which
+    # makes the "local" log-sum-exp exceed the global one; log_add_exp(.., mask=(1, -1)) then takes the log of a negative number)
+    gen_scatterbrain(ref, 'sb_2d_small', B=1, shape=(8, 8), dim=64, heads=2, window=4, attn_2d=True, use_rpe=True, approx=32, seed=113)
+    gen_scatterbrain(ref, 'sb_1d_pad_mask', B=3, shape=(45,), dim=64, heads=2, window=8, attn_2d=False, use_rpe=True, mask_tail=[0, 6, 19], seed=115)
+    gen_scatterbrain(ref, 'sb_1d_norpe', B=2, shape=(48,), dim=64, heads=4, window=16, attn_2d=False, mask_tail=[3, 0], seed=117)
+    gen_scatterbrain(ref, 'sb_2d_train', B=2, shape=(14, 14), dim=128, heads=2, window=7, attn_2d=True, use_rpe=True, train_seed=121, seed=119)
+
+
 def main():
-    argparse.ArgumentParser(description=__doc__).parse_args()
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument('--only-rfa', action='store_true', help='only the performer / ra / scatterbrain fixtures')
+    args = ap.parse_args()
     ref = _import_reference()
     torch.set_num_threads(8)
+    main_rfa(ref)
+    if args.only_rfa:
+        return
     # --- EVA (eva.py) ---
     # BASELINE config c1, exact shape
     gen_eva(ref, 'eva_c1', B=2, shape=(14, 14), dim=192, heads=3, window=7, landmarks=49, attn_2d=True, use_rpe=True)

@@ -1,10 +1,11 @@
-"""Pin the CPU oracle (oracle/eva_oracle.py) against outputs of the reference itself
+"""Pin the CPU oracle (oracle/eva_oracle.py, oracle/rfa_oracle.py) against outputs of the reference itself
 (tests/golden/*.npz, produced by tests/golden/make_golden.py from /root/reference)."""
 import pytest
 import torch
 
 from conftest import golden_names, load_golden, rel_l2
 from oracle import eva_oracle as O
+from oracle import rfa_oracle as R
 
 FORWARD = {
     'eva': lambda cfg, sd, a: O.eva_forward(sd, cfg, a['x'], a['mask'], a['noise']),
@@ -12,6 +13,9 @@ FORWARD = {
     'softmax': lambda cfg, sd, a: O.softmax_forward(sd, cfg, a['x'], a['mask']),
     'lara': lambda cfg, sd, a: O.lara_forward(sd, cfg, a['x'], a['mask'], a['noise']),
     'causal_eva': lambda cfg, sd, a: O.causal_eva_forward(sd, cfg, a['x'], a['mask'], a['noise']),
+    'performer': lambda cfg, sd, a: R.performer_forward(sd, cfg, a['x'], a['mask'], a.get('proj'), f32_linear=True),
+    'ra': lambda cfg, sd, a: R.ra_forward(sd, cfg, a['x'], a['mask'], a.get('k_ind'), a['noise']),
+    'scatterbrain': lambda cfg, sd, a: R.scatterbrain_forward(sd, cfg, a['x'], a['mask'], a.get('proj')),
 }
 
 
@@ -20,8 +24,9 @@ def test_oracle_matches_reference_output(name):
     cfg, sd, a = load_golden(name)
     y = FORWARD[cfg['kind']](cfg, sd, a)
     assert y.shape == a['y'].shape
-    # both sides are float64 evaluations of the same float32-representable inputs
-    assert rel_l2(y, a['y']) < 1e-11, name
+    # both sides are float64 evaluations of the same float32-representable inputs -- except 'performer', whose reference casts to
+    # float32 for the linear-attention step whatever the module dtype (kernelized_attention.py:319): float32 rounding there
+    assert rel_l2(y, a['y']) < (2e-6 if cfg['kind'] == 'performer' else 1e-11), name
 
 
 def test_golden_set_covers_every_module_kind():
