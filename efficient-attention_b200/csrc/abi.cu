@@ -95,6 +95,12 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+namespace eva {
+int abi_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+int abi_cuda_fail(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+int abi_view(const EvaHeadsView* in, const char* name, View* v) { return make_view(in, name, v); }
+}  // namespace eva
+
 extern "C" {
 
 int eva_sm100_abi_version(void) { return EVA_SM100_ABI_VERSION; }

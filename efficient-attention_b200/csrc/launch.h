@@ -8,6 +8,11 @@
 
 namespace eva {
 
+// error plumbing of the C ABI (abi.cu), for the translation units that export entry points of their own (rfa_kernels.cu)
+int abi_fail(int code, const char* msg);
+int abi_cuda_fail(cudaError_t e, const char* what);
+int abi_view(const EvaHeadsView* in, const char* name, View* v);
+
 cudaError_t launch_chunk_stats(const Geo& g, int io_dtype, const View& q, const View& k, const View& v,
                                const uint8_t* mask, const EvaAdaptive& ada, const float* noise,
                                float* kbar, float* beta, cudaStream_t st);

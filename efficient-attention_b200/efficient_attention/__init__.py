@@ -6,8 +6,8 @@ Same import name and plugin surface as the reference (efficient_attention/__init
 own the same parameters under the same names (checkpoints load unchanged) but run the attention core
 as hand-written sm_100a CUDA kernels reached through the C ABI of libeva_sm100.so.
 
-Scope: 'eva', 'lara', 'causal_eva', and the 'local' / 'softmax' bases they are built
-on.  'performer', 'ra' and 'scatterbrain' are not part of the accelerated path and are not registered.
+Scope: 'eva', 'lara', 'causal_eva', the 'local' / 'softmax' bases they are built on, and (8f-4) the
+random-feature baselines of the registry: 'performer', 'ra', 'scatterbrain'.
 """
 import argparse
 from typing import Dict
@@ -54,7 +54,10 @@ class NestedNamespace(argparse.Namespace):
 
 from .abstract_attention import MultiheadAttention  # noqa: E402
 from .local_attention import LocalAttention  # noqa: E402
+from .kernelized_attention import KernelizedAttention  # noqa: E402
 from .lara import LinearRA  # noqa: E402
+from .randomized_attention import RandomizedAttention  # noqa: E402
+from .scatterbrain_attention import ScatterBrain  # noqa: E402
 from .eva import EVA  # noqa: E402
 from .causal_eva import CausalEVAttention  # noqa: E402
 from ._abi import invalidate_caches  # noqa: E402,F401
@@ -62,9 +65,12 @@ from ._abi import invalidate_caches  # noqa: E402,F401
 
 class AttentionFactory(object):
     attn_dict = {
+        'performer': KernelizedAttention,
         'softmax': MultiheadAttention,
         'local': LocalAttention,
         'lara': LinearRA,
+        'ra': RandomizedAttention,
+        'scatterbrain': ScatterBrain,
         'eva': EVA,
         'causal_eva': CausalEVAttention,
     }

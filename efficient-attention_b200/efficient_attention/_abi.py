@@ -43,6 +43,22 @@ class LaraGeometry(ctypes.Structure):
         'mis_type', 'sample_mode', 'zero_padded', 'io_dtype')] + [('alpha_coeff', ctypes.c_float)]
 
 
+class RfaGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        'batch', 'heads', 'tokens', 'head_dim', 'method', 'proj_dim', 'nu', 'feat_dim', 'cos_weighting', 'io_dtype')]
+
+
+class SbGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        'batch', 'heads', 'tokens', 'head_dim', 'dims', 'grid_h', 'grid_w', 'window', 'proj_dim', 'io_dtype')]
+
+
+class RaGeometry(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('batch', 'heads', 'tokens', 'head_dim', 'mode', 'io_dtype')]
+
+
+RFA_METHOD = {'favorp': 0, 'relu': 1, 'fourier': 2, 'dpfp': 3, 'relu-only': 4, 'sigmoid-only': 5, 'given': 6}
+
 _lib = None
 _lock = threading.Lock()
 
@@ -80,10 +96,20 @@ def load():
         lib.lara_forward_workspace_bytes.argtypes = [LG, ctypes.POINTER(SZ)]
         lib.lara_forward.argtypes = [LG, V, V, V, P, A, P, P, P, SZ, P]
         lib.lara_forward_given_landmarks.argtypes = [LG, V, V, V, P, P, P, P, P, SZ, P]
+        RG, SG, AG = ctypes.POINTER(RfaGeometry), ctypes.POINTER(SbGeometry), ctypes.POINTER(RaGeometry)
+        lib.rfa_feature_dim.argtypes = [RG]
+        lib.rfa_forward_workspace_bytes.argtypes = [RG, ctypes.POINTER(SZ)]
+        lib.rfa_forward.argtypes = [RG, V, V, V, P, P, P, P, P, P, SZ, P]
+        lib.scatterbrain_forward_workspace_bytes.argtypes = [SG, ctypes.POINTER(SZ)]
+        lib.scatterbrain_forward.argtypes = [SG, V, V, V, P, P, P, P, P, SZ, P]
+        lib.ra_forward.argtypes = [AG, V, V, V, P, P, P, P, P, SZ, P]
+        for fn in ('rfa_feature_dim', 'rfa_forward_workspace_bytes', 'rfa_forward', 'scatterbrain_forward_workspace_bytes',
+                   'scatterbrain_forward', 'ra_forward'):
+            getattr(lib, fn).restype = ctypes.c_int
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
                    'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_backward_step', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
             getattr(lib, fn).restype = ctypes.c_int
-        if lib.eva_sm100_abi_version() != 3:
+        if lib.eva_sm100_abi_version() != 4:
             raise RuntimeError('libeva_sm100.so ABI version mismatch; rebuild')
         _lib = lib
     return _lib
@@ -360,4 +386,68 @@ def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_ty
                                   _ptr(ws), ws.numel(), _stream(q.device))
     _check(rc, 'lara_forward')
     del keep
+    return out
+
+
+def rfa_forward(q, k, v, *, method, proj=None, nu=1, cos_weighting=False, pad_mask=None, q_feat=None, k_feat=None):
+    """Linear attention with the feature map `method` (kernelized_attention.py:301-320).  q, k, v: [B, N, H, D] views; proj float32
+    [H, m, D]; method 'given': q_feat / k_feat float32 [B, H, N, M] computed by the caller.  Returns [B, N, H*D] in q's dtype."""
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, proj, q_feat, k_feat)
+    B, N, H, D = q.shape
+    proj, q_feat, k_feat = _f32(proj), _f32(q_feat), _f32(k_feat)
+    geom = RfaGeometry(B, H, N, D, RFA_METHOD[method], 0 if proj is None else proj.shape[1], nu,
+                       0 if q_feat is None else q_feat.shape[-1], int(cos_weighting), io_dtype(q))
+    mask = _mask_u8(pad_mask, B, N)
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.rfa_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'rfa_forward_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.rfa_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)), ctypes.byref(heads_view(v)),
+                             _ptr(mask), _ptr(proj), _ptr(q_feat), _ptr(k_feat), _ptr(out), _ptr(ws), ws.numel(), _stream(q.device))
+    _check(rc, 'rfa_forward')
+    return out
+
+
+def scatterbrain_forward(q, k, v, *, seq_shape, window, proj, pad_mask=None, bias=None):
+    """ScatterBrain core (scatterbrain_attention.py:95-160): halo-free windows + random-feature keys for the rest of the sequence."""
+    lib = load()
+    _require_cuda(q, k, v, pad_mask, proj, bias)
+    B, N, H, D = q.shape
+    proj, bias = _f32(proj), _f32(bias)
+    two_d = len(seq_shape) == 2
+    geom = SbGeometry(B, H, N, D, 2 if two_d else 1, seq_shape[0] if two_d else 1, seq_shape[1] if two_d else N, window,
+                      proj.shape[1], io_dtype(q))
+    mask = _mask_u8(pad_mask, B, N)
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.scatterbrain_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'scatterbrain_forward_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.scatterbrain_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)),
+                                      ctypes.byref(heads_view(v)), _ptr(mask), _ptr(proj), _ptr(bias), _ptr(out), _ptr(ws), ws.numel(),
+                                      _stream(q.device))
+    _check(rc, 'scatterbrain_forward')
+    return out
+
+
+def ra_forward(q, k, v, *, mode, extra=None, k_ind=None, noise=None):
+    """Randomized attention core (randomized_attention.py:24-55).  mode 'mean' | 'given' (extra: [B, N, H*D] in q's dtype) |
+    'gather' (k_ind int64 [B, H, N]); noise float32 [B, H, N, D] or None."""
+    lib = load()
+    _require_cuda(q, k, v, extra, k_ind, noise)
+    B, N, H, D = q.shape
+    geom = RaGeometry(B, H, N, D, {'mean': 0, 'given': 1, 'gather': 2}[mode], io_dtype(q))
+    noise = _f32(noise)
+    if extra is not None:
+        extra = extra.detach().to(q.dtype).contiguous()
+    if k_ind is not None:
+        k_ind = k_ind.to(torch.int64).contiguous()
+    out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
+    ws = torch.empty(max(B * H * D * 4, 256), dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.ra_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)), ctypes.byref(heads_view(v)),
+                            _ptr(extra), _ptr(k_ind), _ptr(noise), _ptr(out), _ptr(ws), ws.numel(), _stream(q.device))
+    _check(rc, 'ra_forward')
     return out

@@ -13,6 +13,7 @@
  *                          when the geometry allows, else the two generic stages)
  *   eva_backward           what autograd derives from eva.py:151-227 / causal_eva.py:676-783 / local_attention.py:134-182
  *                          (vit/engine.py:47-62 trains through it): gradients of eva_forward / eva_window_attention
+ *   rfa_forward / scatterbrain_forward / ra_forward   kernelized_attention.py, scatterbrain_attention.py, randomized_attention.py
  *   lara_forward           lara.py:84-175          (landmark pooling, Linear+LN, mixing, proposal stats) and
  *                          lara.py:201-246         (phi-projections, kv statistics, MIS weights, SNIS) in one call
  *
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define EVA_SM100_ABI_VERSION 3
+#define EVA_SM100_ABI_VERSION 4
 
 enum EvaDtype { EVA_F32 = 0, EVA_F16 = 1, EVA_BF16 = 2 };
 
@@ -204,6 +205,67 @@ int lara_forward_given_landmarks(const LaraGeometry* g, const EvaHeadsView* q, c
 int lara_backward_step(int32_t which, int32_t io_dtype, void* X, void* Y, const void* dW, void* M2, const float* v0, const float* v1,
                        const float* v2, const float* v3, float* o0, float* o1, float* o2, int64_t x_item_stride, int64_t y_item_stride,
                        int32_t items, int32_t landmarks, int32_t tokens, float scale, float alpha_coeff, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (ABI v4) Random-feature modules of the registry (__init__.py:53-62): 'performer' (kernelized_attention.py), 'ra'
+ * (randomized_attention.py), 'scatterbrain' (scatterbrain_attention.py).  float32 math, q / k / v / out in io_dtype. */
+enum RfaMethod {
+  RFA_FAVORP = 0,        /* favorp_projection,       kernelized_attention.py:21-55  (positive random features, eps 1e-4)   */
+  RFA_RELU = 1,          /* generalized_projection + relu, :92-113 (eps 1e-3)                                              */
+  RFA_FOURIER = 2,       /* fourier_projection,      :57-87  (2 * proj_dim features)                                        */
+  RFA_DPFP = 3,          /* dpfp_projection,         :12-19  (2 * head_dim * nu features, no projection matrix)            */
+  RFA_RELU_ONLY = 4,     /* nonlinear_map(relu),     :89-90  (head_dim features, eps 0.1)                                   */
+  RFA_SIGMOID_ONLY = 5,  /* nonlinear_map(sigmoid)                                                                          */
+  RFA_GIVEN = 6          /* the caller computed phi(q), phi(k) itself ('mlp-fourier': a learnable Linear over all features,
+                            :155-178, is a library GEMM on the host side)                                                   */
+};
+
+typedef struct RfaGeometry {
+  int32_t batch, heads, tokens, head_dim;
+  int32_t method;        /* RfaMethod */
+  int32_t proj_dim;      /* rows of the projection matrix (approx_attn_dim) for FAVORP / RELU / FOURIER */
+  int32_t nu;            /* DPFP */
+  int32_t feat_dim;      /* GIVEN: width of q_feat / k_feat */
+  int32_t cos_weighting; /* cosFormer re-weighting, kernelized_attention.py:122-153 */
+  int32_t io_dtype;
+} RfaGeometry;
+
+/* Width of phi(.) after the optional cosFormer doubling, or a negative status. */
+int rfa_feature_dim(const RfaGeometry* g);
+int rfa_forward_workspace_bytes(const RfaGeometry* g, size_t* bytes);
+/* KernelizedAttention._apply_attention (kernelized_attention.py:301-320): out = phi(q) (phi(k)^T v) / max(phi(q) . sum phi(k), 1e-2).
+ * proj: float32 [heads, proj_dim, head_dim] (NULL for the methods without one); q_feat / k_feat: float32 [batch, heads, tokens,
+ * feat_dim], RFA_GIVEN only; pad_mask: [batch, tokens] bytes or NULL (padded keys' features are zeroed after the stabilisers, as
+ * the reference does).  out: io_dtype [batch, tokens, heads*head_dim]. */
+int rfa_forward(const RfaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const uint8_t* pad_mask,
+                const float* proj, const float* q_feat, const float* k_feat, void* out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ScatterBrain.forward between the qkv and the output projections (scatterbrain_attention.py:95-160), proj_method 'favorp':
+ * halo-free local windows (<= 64 tokens) + proj_dim random-feature keys per window that stand for everything outside it. */
+typedef struct SbGeometry {
+  int32_t batch, heads, tokens, head_dim;
+  int32_t dims, grid_h, grid_w, window;
+  int32_t proj_dim;
+  int32_t io_dtype;
+} SbGeometry;
+int scatterbrain_forward_workspace_bytes(const SbGeometry* g, size_t* bytes);
+/* proj: float32 [heads, proj_dim, head_dim]; bias: float32 [heads, L, L] added to the local logits, or NULL. */
+int scatterbrain_forward(const SbGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const uint8_t* pad_mask,
+                         const float* proj, const float* bias, void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* RandomizedAttention._apply_attention (randomized_attention.py:24-55): out_n = softmax_m(scale w_n . k_m - scale |k_m|^2 / 2) v_m,
+ * w_n = q_n + extra_n (+ noise_n).  mode 0: extra = mean of k (num_samples == 0; workspace: batch*heads*head_dim floats);
+ * mode 1: extra = caller-supplied rows, io_dtype [batch, tokens, heads*head_dim] (num_samples == -1: E_pi[k], i.e.
+ * eva_window_attention with v := k); mode 2: extra = k[k_ind[n]], k_ind int64 [batch, heads, tokens] (the multinomial draw).
+ * noise: float32 [batch, heads, tokens, head_dim] or NULL.  The reference ignores the padding mask here; so does this. */
+typedef struct RaGeometry {
+  int32_t batch, heads, tokens, head_dim;
+  int32_t mode;
+  int32_t io_dtype;
+} RaGeometry;
+int ra_forward(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const void* extra,
+               const int64_t* k_ind, const float* noise, void* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,8 @@ from efficient_attention.attn_utils import pad_to_multiple, t5_bucket_table
 
 
 def test_registry_names_and_errors():
-    assert set(ea.AttentionFactory.attn_dict) == {'softmax', 'local', 'lara', 'eva', 'causal_eva'}
+    # the reference registry, name for name (efficient_attention/__init__.py:53-62)
+    assert set(ea.AttentionFactory.attn_dict) == {'performer', 'softmax', 'local', 'lara', 'ra', 'scatterbrain', 'eva', 'causal_eva'}
     with pytest.raises(KeyError):
         ea.AttentionFactory.build_attention('nope', {})
     with pytest.raises(TypeError):
@@ -109,12 +110,13 @@ def test_t5_bucket_table_matches_oracle(geom, causal):
 def test_cabi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, 'include', 'eva_sm100.h')).read()
     header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
-    declared = set(re.findall(r'\b(?:int|const char\s*\*)\s+((?:eva|lara)_\w+)\s*\(', header))
-    assert {'eva_forward', 'eva_chunk_stats', 'eva_window_attention', 'lara_forward', 'eva_last_error'} <= declared
+    declared = set(re.findall(r'\b(?:int|const char\s*\*)\s+((?:eva|lara|rfa|ra|scatterbrain)_\w+)\s*\(', header))
+    assert {'eva_forward', 'eva_chunk_stats', 'eva_window_attention', 'lara_forward', 'eva_last_error', 'rfa_forward', 'ra_forward',
+            'scatterbrain_forward'} <= declared
     lib = ctypes.CDLL(_abi.LIB_PATH)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert _abi.load().eva_sm100_abi_version() == 3
+    assert _abi.load().eva_sm100_abi_version() == 4
 
 
 def test_cabi_rejects_bad_geometry_without_touching_the_gpu():
@@ -233,3 +235,89 @@ def test_integration_md_ctypes_stub_matches_the_abi():
     header = open(os.path.join(ROOT, 'include', 'eva_sm100.h')).read()
     for n, _ in _abi.EvaGeometry._fields_:
         assert re.search(r'\b%s\b' % n, header), n
+
+
+def test_random_feature_modules_cli_and_errors():
+    """'performer' / 'ra' / 'scatterbrain' argparse surface (kernelized_attention.py:322-330, randomized_attention.py:56-63,
+    scatterbrain_attention.py:166-180) and the two configurations that do not run in the reference either."""
+    p = argparse.ArgumentParser()
+    p = ea.AttentionFactory.add_attn_specific_args(p, 'performer')
+    ns = p.parse_args(['--approx-attn-dim', '32', '--proj-method', 'relu', '--cos-weighting'], namespace=ea.NestedNamespace())
+    assert vars(ns.attn_args) == dict(fp32=False, approx_attn_dim=32, proj_method='relu', cos_weighting=True, sample_scheme='default')
+    p = ea.AttentionFactory.add_attn_specific_args(argparse.ArgumentParser(), 'ra')
+    assert vars(p.parse_args([], namespace=ea.NestedNamespace()).attn_args) == dict(fp32=False, num_samples=1)
+    p = ea.AttentionFactory.add_attn_specific_args(argparse.ArgumentParser(), 'scatterbrain')
+    got = vars(p.parse_args(['--window-size', '7', '--attn-2d'], namespace=ea.NestedNamespace()).attn_args)
+    assert got == dict(fp32=False, use_rpe=False, window_size=7, attn_2d=True, overlap_window=False, approx_attn_dim=64,
+                       proj_method='favorp', cos_weighting=False, sample_scheme='default')
+    x = torch.zeros(1, 16, 64)
+    sb = ea.AttentionFactory.build_attention('scatterbrain', dict(dim=64, num_heads=2, window_size=4, overlap_window=True))
+    with pytest.raises(NotImplementedError, match='NaN'):
+        sb(x)
+    sb = ea.AttentionFactory.build_attention('scatterbrain', dict(dim=64, num_heads=2, window_size=4, proj_method='relu'))
+    with pytest.raises(NotImplementedError, match='favorp'):
+        sb(x)
+    with pytest.raises(NotImplementedError):
+        ea.AttentionFactory.build_attention('performer', dict(dim=64, num_heads=2, proj_method='bogus'))
+
+
+def test_orthogonal_projection_init():
+    """create_proj_matrix(ortho=True) (kernelized_attention.py:187-227): orthogonal directions inside each block of head_dim rows."""
+    from efficient_attention.kernelized_attention import create_proj_matrix
+    w = create_proj_matrix(3, 80, 32, ortho=True).double()
+    assert w.shape == (3, 80, 32)
+    unit = w / w.norm(dim=-1, keepdim=True)
+    for blk in (unit[:, :32], unit[:, 32:64], unit[:, 64:]):
+        gram = blk @ blk.transpose(-1, -2)
+        assert torch.allclose(gram, torch.eye(blk.shape[1], dtype=torch.float64).expand_as(gram), atol=1e-5)
+
+
+@pytest.mark.parametrize('name', golden_names(['perf_', 'ra_', 'sb_']))
+def test_backward_restatements_match_reference_output(name):
+    """The float32 PyTorch restatements the random-feature modules differentiate in training (`*_core_torch`) reproduce the
+    reference's forward on the fixtures (CPU): what the backward differentiates is the reference's function."""
+    from efficient_attention import kernelized_attention as KA, randomized_attention as RA, scatterbrain_attention as SB
+    from oracle import eva_oracle as O
+    cfg, sd, a = load_golden(name, dtype=torch.float32)
+    H = cfg['num_heads']
+    x = a['x']
+    B, C = x.shape[0], x.shape[-1]
+    shape = tuple(x.shape[1:-1])
+    mask = a['mask']
+    xf = x.reshape(B, -1, C)
+    w = cfg.get('window_size')
+    if cfg['kind'] == 'scatterbrain' and not cfg['attn_2d']:
+        xf, mask = O._pad_tokens(xf, mask, w)
+    N = xf.shape[1]
+    packed = (xf @ sd['qkv.weight'].t() + sd['qkv.bias']).view(B, N, 3, H, C // H)
+    q, k, v = packed[:, :, 0], packed[:, :, 1], packed[:, :, 2]
+    proj = a.get('proj')
+    if proj is None:
+        proj = sd.get('eval_proj', sd.get('random_proj'))
+    if cfg['kind'] == 'performer':
+        method = cfg['proj_method']
+        if method == 'mlp-fourier':
+            pytest.skip('features by library ops')
+        nu = (cfg['approx_attn_dim'] // (C // H)) // 2
+        o = KA.linear_attention_torch(KA.features_torch(q, method, True, proj, nu), KA.features_torch(k, method, False, proj, nu), v,
+                                      cfg['cos_weighting'], mask)
+    elif cfg['kind'] == 'ra':
+        ns = cfg['num_samples']
+        if ns == 0:
+            extra = k.mean(1, keepdim=True)
+        elif ns == -1:
+            pi = torch.softmax((C // H) ** -0.5 * torch.einsum('bnhd,bmhd->bhnm', q, k), -1)
+            extra = torch.einsum('bhnm,bmhd->bnhd', pi, k)
+        else:
+            extra = torch.gather(k, 1, a['k_ind'].transpose(1, 2).unsqueeze(-1).expand(B, N, H, C // H))
+        o = RA.ra_core_torch(q, k, v, extra, a['noise'], (C // H) ** -0.5)
+    else:
+        L = w * w if cfg['attn_2d'] else w
+        bias = O.local_bias_from_state(sd, dict(cfg, ext=0, use_t5_rpe=False), H, L, L, 1.0)
+        seq_shape = shape if cfg['attn_2d'] else (N,)
+        o = SB.scatterbrain_core_torch(q, k, v, proj, seq_shape=seq_shape, window=w, pad_mask=mask, bias=bias)
+    y = (o @ sd['proj.weight'].t() + sd['proj.bias']).view((B,) + ((N,) if len(shape) == 1 else shape) + (C,))
+    if len(shape) == 1:
+        y = y[:, :shape[0]]
+    err = float((y.double() - a['y'].double()).norm() / a['y'].double().norm())
+    assert err < 2e-5, (name, err)

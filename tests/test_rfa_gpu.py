@@ -1,0 +1,187 @@
+"""GPU parity tests (`-m gpu`) of the random-feature cores (csrc/rfa_kernels.cu) through the C ABI, against the float64 oracle
+(oracle/rfa_oracle.py) on identical, pre-quantised q / k / v, plus gradients of the modules against autograd through the oracle.
+
+Tolerances (relative L2, oracle in float64): float32 I/O 2e-5; float16 I/O 1e-3 (north_star); bfloat16 I/O 6e-3 (output rounding).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from helpers import build_module, set_draws
+from oracle import eva_oracle as O
+from oracle import rfa_oracle as R
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 2e-5, torch.float16: 1e-3, torch.bfloat16: 6e-3}
+
+
+def _dev():
+    return torch.device('cuda', 0)
+
+
+def _qkv(B, N, H, D, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    packed = (scale * torch.randn(B, N, 3, H, D, generator=g)).to(dtype)
+    dev = packed.to(_dev())
+    ref = [packed[:, :, i].double().transpose(1, 2) for i in range(3)]          # [B, H, N, D] float64 of the SAME rounded values
+    return (dev[:, :, 0], dev[:, :, 1], dev[:, :, 2]), ref
+
+
+def _heads(o, B, N, H, D):
+    return o.transpose(1, 2).reshape(B, N, H * D)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('method,m,cos', [('favorp', 64, False), ('favorp', 48, True), ('relu', 64, False), ('fourier', 32, False),
+                                          ('dpfp', 256, False), ('relu-only', 0, True), ('sigmoid-only', 0, False)])
+def test_performer_core_vs_oracle(dtype, method, m, cos):
+    from efficient_attention import _abi
+    B, N, H, D = 3, 203, 2, 64
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, dtype, 5)
+    g = torch.Generator().manual_seed(7)
+    proj = torch.randn(H, m, D, generator=g) if method in ('favorp', 'relu', 'fourier') else None
+    mask = torch.zeros(B, N, dtype=torch.bool)
+    mask[1, -17:] = True
+    nu = 2
+    out = _abi.rfa_forward(q, k, v, method=method, proj=None if proj is None else proj.to(_dev()), nu=nu, cos_weighting=cos,
+                           pad_mask=mask.to(_dev()))
+    ref = R.performer_core(qr, kr, vr, method=method, proj=None if proj is None else proj.double(), nu=nu, cos_weighting=cos,
+                           pad_mask=mask)
+    err = rel_l2(out.cpu(), _heads(ref, B, N, H, D))
+    assert err < TOL[dtype], (method, dtype, err)
+
+
+@pytest.mark.parametrize('D,m', [(16, 24), (32, 64), (128, 128)])
+def test_performer_core_other_head_dims(D, m):
+    from efficient_attention import _abi
+    B, N, H = 2, 77, 3
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, torch.float32, 9)
+    proj = torch.randn(H, m, D, generator=torch.Generator().manual_seed(1))
+    out = _abi.rfa_forward(q, k, v, method='favorp', proj=proj.to(_dev()))
+    ref = R.performer_core(qr, kr, vr, method='favorp', proj=proj.double())
+    assert rel_l2(out.cpu(), _heads(ref, B, N, H, D)) < 2e-5
+
+
+def test_performer_c3_shape_linearity_and_oracle_slice():
+    """BASELINE c3 shape (N = 784, h = 3, d = 64), batch 64, fp16: a slice of the batch against the oracle, and the size-independent
+    property out(v1 + v2) = out(v1) + out(v2) on the whole batch (the map is linear in v for fixed q, k)."""
+    from efficient_attention import _abi
+    B, N, H, D = 64, 784, 3, 64
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, torch.float16, 11)
+    proj = torch.randn(H, 64, D, generator=torch.Generator().manual_seed(2))
+    out = _abi.rfa_forward(q, k, v, method='favorp', proj=proj.to(_dev()))
+    ref = R.performer_core(qr[:2], kr[:2], vr[:2], method='favorp', proj=proj.double())
+    assert rel_l2(out[:2].cpu(), _heads(ref, 2, N, H, D)) < 1e-3
+    v2 = torch.randn_like(v)
+    o2 = _abi.rfa_forward(q, k, v2, method='favorp', proj=proj.to(_dev()))
+    o12 = _abi.rfa_forward(q, k, (v.float() + v2.float()).half(), method='favorp', proj=proj.to(_dev()))
+    assert rel_l2(o12.float().cpu(), (out.float() + o2.float()).cpu()) < 2e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('mode', ['mean', 'given', 'gather'])
+def test_ra_core_vs_oracle(dtype, mode):
+    from efficient_attention import _abi
+    B, N, H, D = 2, 150, 3, 64
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, dtype, 13, scale=0.7)
+    g = torch.Generator().manual_seed(3)
+    noise = 0.5 * torch.randn(B, H, N, D, generator=g)
+    k_ind = torch.randint(0, N, (B, H, N), generator=g)
+    if mode == 'given':
+        extra = torch.randn(B, N, H * D, generator=g).to(dtype)
+        ex_ref = extra.double().view(B, N, H, D).transpose(1, 2)
+        out = _abi.ra_forward(q, k, v, mode='given', extra=extra.to(_dev()), noise=noise.to(_dev()))
+        w_extra = ex_ref
+    elif mode == 'mean':
+        out = _abi.ra_forward(q, k, v, mode='mean', noise=noise.to(_dev()))
+        w_extra = kr.mean(-2, keepdim=True)
+    else:
+        out = _abi.ra_forward(q, k, v, mode='gather', k_ind=k_ind.to(_dev()), noise=noise.to(_dev()))
+        w_extra = torch.gather(kr, 2, k_ind.unsqueeze(-1).expand(-1, -1, -1, D))
+    s = D ** -0.5
+    w = qr + w_extra + noise.double()
+    ref = torch.softmax(s * (w @ kr.transpose(-1, -2)) - 0.5 * s * (kr * kr).sum(-1).unsqueeze(-2), -1) @ vr
+    err = rel_l2(out.cpu(), _heads(ref, B, N, H, D))
+    assert err < TOL[dtype], (mode, dtype, err)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('geom', ['2d_w7', '1d_w16_mask', '2d_w8_d32'])
+def test_scatterbrain_core_vs_oracle(dtype, geom):
+    from efficient_attention import _abi
+    if geom == '2d_w7':
+        B, H, D, shape, w, m = 2, 3, 64, (28, 28), 7, 64
+    elif geom == '1d_w16_mask':
+        B, H, D, shape, w, m = 3, 2, 64, (160,), 16, 48
+    else:
+        B, H, D, shape, w, m = 2, 2, 32, (16, 16), 8, 32
+    N = math.prod(shape)
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, dtype, 17, scale=0.8)
+    g = torch.Generator().manual_seed(4)
+    proj = torch.randn(H, m, D, generator=g)
+    L = w * w if len(shape) == 2 else w
+    bias = 0.5 * torch.randn(H, L, L, generator=g)
+    mask = None
+    if 'mask' in geom:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[1, -21:] = True
+        mask[2, 40:60] = True
+    out = _abi.scatterbrain_forward(q, k, v, seq_shape=shape, window=w, proj=proj.to(_dev()), bias=bias.to(_dev()),
+                                    pad_mask=None if mask is None else mask.to(_dev()))
+    ref = R.scatterbrain_core(qr, kr, vr, proj=proj.double(), seq_shape=shape, window=w, ext=0, pad_mask=mask, bias=bias.double())
+    err = rel_l2(out.cpu(), _heads(ref, B, N, H, D))
+    assert err < TOL[dtype], (geom, dtype, err)
+
+
+@pytest.mark.parametrize('name', ['perf_favorp_mask', 'perf_fourier_learn', 'perf_mlp_fourier', 'perf_relu_only_cos', 'ra_mean',
+                                  'ra_expect_2d', 'ra_sample_train', 'sb_2d_rpe', 'sb_1d_pad_mask'])
+def test_module_gradients_match_autograd_through_the_oracle(name):
+    """d loss / d x and d loss / d (every parameter) of the drop-in module (forward: CUDA kernels; backward: the module's float32
+    restatement) against autograd through the float64 oracle, loss = sum(y * fixed random tensor)."""
+    cfg, sd, a = load_golden(name, dtype=torch.float32)
+    m = build_module(cfg)
+    m.load_state_dict(sd)
+    m = m.to(_dev())
+    m.train()
+    set_draws(m, cfg, a, _dev())
+    if cfg['kind'] in ('performer', 'scatterbrain') and a.get('proj') is None and 'eval_proj' in sd:
+        m._proj_override = sd['eval_proj'].to(_dev())         # training mode would draw a fresh projection
+    if cfg['kind'] == 'ra' and a.get('noise') is None:
+        m._draw_override = (a['k_ind'].to(_dev()) if a.get('k_ind') is not None else None, None)
+    x = a['x'].to(_dev()).requires_grad_(True)
+    mask = a['mask'].to(_dev()) if a['mask'] is not None else None
+    y = m(x, mask)
+    gsel = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).to(_dev())
+    (y * gsel).sum().backward()
+    # oracle side, float64
+    sd64 = {k_: (v_.double().requires_grad_(True) if v_.is_floating_point() else v_) for k_, v_ in sd.items()}
+    x64 = a['x'].double().requires_grad_(True)
+    fwd = {'performer': lambda: R.performer_forward(sd64, cfg, x64, a['mask'], a.get('proj').double() if a.get('proj') is not None else None),
+           'ra': lambda: R.ra_forward(sd64, cfg, x64, a['mask'], a.get('k_ind'), a['noise'].double() if a.get('noise') is not None else None),
+           'scatterbrain': lambda: R.scatterbrain_forward(sd64, cfg, x64, a['mask'], a.get('proj').double() if a.get('proj') is not None else None)}
+    y64 = fwd[cfg['kind']]()
+    assert rel_l2(y.detach().cpu(), y64.detach()) < 5e-5
+    (y64 * gsel.cpu().double()).sum().backward()
+    assert rel_l2(x.grad.cpu(), x64.grad) < 2e-4, name
+    for pname, p in m.named_parameters():
+        ref_g = sd64[pname].grad
+        if ref_g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, pname
+            continue
+        assert p.grad is not None, pname
+        assert rel_l2(p.grad.cpu(), ref_g) < 5e-4, (name, pname)
+
+
+def test_ra_default_sampling_draws_from_pi():
+    """num_samples = 1 in eval mode without the test hook: the module draws one key per query from pi = softmax(scale q k^T)
+    (library ops, as the reference's torch.multinomial).  With a peaked pi the draw is (almost surely) the arg-max key."""
+    import efficient_attention as ea
+    torch.manual_seed(0)
+    m = ea.AttentionFactory.build_attention('ra', dict(dim=64, num_heads=1, num_samples=1)).to(_dev()).eval()
+    x = torch.randn(2, 40, 64, device=_dev())
+    with torch.no_grad():
+        m.qkv.weight.mul_(60.0)
+        y = m(x)
+    assert torch.isfinite(y).all() and y.shape == x.shape
