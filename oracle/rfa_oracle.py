@@ -48,11 +48,11 @@ def features(x, method: str, is_query: bool, proj=None, nu: int = 1, mlp_w=None,
         dd = torch.einsum('bhnd,hjd->bhnj', dn * x, proj)
         half_sq = 0.5 * dn * dn * (x * x).sum(-1, keepdim=True)
         if method == 'favorp':                                   # :21-55
-            stab = dd.amax(-1, keepdim=True) if is_query else dd.amax((-1, -2), keepdim=True)
+            stab = (dd.amax(-1, keepdim=True) if is_query else dd.amax((-1, -2), keepdim=True)).detach()   # detached in the reference too
             return m ** -0.5 * torch.exp(dd - half_sq - stab) + 1e-4
         if method == 'relu':                                     # :92-113 (generalized_projection, eps = 1e-3)
             return torch.relu(m ** -0.5 * dd) + 1e-3
-        hq = torch.exp(half_sq - half_sq.amax(-2, keepdim=True))  # :57-87: the max runs over the TOKENS
+        hq = torch.exp(half_sq - half_sq.amax(-2, keepdim=True).detach())  # :57-87: the max runs over the TOKENS
         return hq * (m ** -0.5) * torch.cat([torch.sin(dd), torch.cos(dd)], -1)
     if method == 'dpfp':                                         # :12-19
         x2 = torch.cat([torch.relu(x), torch.relu(-x)], -1)
@@ -142,7 +142,7 @@ def scatterbrain_core(q, k, v, *, proj, seq_shape, window, ext, pad_mask=None, b
         qi, ki = group_index_1d(N, window, 0, 0), group_index_1d(N, window, ext, ext)
     wq_, wk_, wv_ = take_groups(q, qi), take_groups(k, ki), take_groups(v, ki)
     wlq, wlk = take_groups(lq, qi), take_groups(lk, ki, fill=0.0)
-    mx = torch.maximum(lk.amax(-2), wlk.amax((-2, -3)))                     # [B, h, m]
+    mx = torch.maximum(lk.amax(-2), wlk.amax((-2, -3))).detach()                  # [B, h, m]
     pk = torch.exp(lk - mx.unsqueeze(-2))                                   # [B, h, N, m]
     wpk = torch.exp(wlk - mx.unsqueeze(-2).unsqueeze(-2))                   # [B, h, G, J, m]
     num = (pk.transpose(-1, -2) @ v).unsqueeze(2) - wpk.transpose(-1, -2) @ wv_          # [B, h, G, m, d]
