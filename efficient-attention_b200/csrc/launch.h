@@ -79,6 +79,11 @@ cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, con
                                   const void* dout, float* dq, float* dk, float* dv, float* dkbar, float* dbeta, float* dbias,
                                   cudaStream_t st, const float* lse = nullptr);
 
+// Performer / FAVOR+ on tcgen05 (rfa_tc_sm100.cu): 'favorp', 64 features, head_dim 64, 16-bit I/O
+bool rfa_tc_supported(int method, int D, int m, int cosw, int io_dtype, const View& q, const View& k, const View& v);
+cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                          const float* proj, void* out, cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

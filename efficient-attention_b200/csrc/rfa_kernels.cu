@@ -723,10 +723,14 @@ int rfa_forward(const RfaGeometry* g, const EvaHeadsView* q, const EvaHeadsView*
   if (p.method == RFA_GIVEN && (!q_feat || !k_feat)) return eva::abi_fail(EVA_ERR_INVALID, "RFA_GIVEN needs q_feat and k_feat");
   if (!out || !workspace) return eva::abi_fail(EVA_ERR_INVALID, "out / workspace is NULL");
   if (workspace_bytes < pl.ws_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return eva::abi_fail(EVA_ERR_INVALID, "workspace too small or not 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (eva::rfa_tc_supported(p.method, p.D, p.m, p.cosw, g->io_dtype, vq, vk, vv)) {      // tcgen05 path (rfa_tc_sm100.cu)
+    const cudaError_t e2 = eva::launch_rfa_tc(p.B, p.H, p.N, g->io_dtype, vq, vk, vv, pad_mask, proj, out, st);
+    return e2 == cudaSuccess ? EVA_OK : eva::abi_cuda_fail(e2, "rfa_forward (tcgen05)");
+  }
   p.proj = proj; p.qf = q_feat; p.kf = k_feat; p.mask = pad_mask;
   p.stab = reinterpret_cast<float*>(workspace);
   p.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((((size_t)p.B * p.H * 8) + 255) & ~(size_t)255));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
   if (g->io_dtype == EVA_F32) e = eva::rfa::run<float>(pl, vq, vk, vv, out, st);
   else if (g->io_dtype == EVA_F16) e = eva::rfa::run<__half>(pl, vq, vk, vv, out, st);

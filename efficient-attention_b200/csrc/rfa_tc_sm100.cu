@@ -1,0 +1,291 @@
+// Performer (FAVOR+) linear attention on tcgen05 / TMEM for sm_100a: the default configuration of the reference's 'performer'
+// (kernelized_attention.py:21-55, 115-120, 301-320: proj_method 'favorp', 64 random features) at head_dim 64 with 16-bit I/O.
+// Everything else (other feature maps / widths, float32 I/O, cosFormer re-weighting) stays on the CUDA-core kernels of
+// rfa_kernels.cu.
+//
+// One (batch, head) item per CTA iteration, 128 threads (thread t <-> TMEM lane t <-> token t of the 128-token tile), two or more
+// CTAs per SM (80 KB of tiles, 256 TMEM columns).  Per item, with W' = d^-1/4 W in 16 bits ([features][d], K-major):
+//   pass 1   per key tile:    DD = K W'^T (M = 128 tokens, N = 64 features)        -> running max = the key stabiliser
+//   pass 2   per key tile:    DD again; thread-local phi(k) = m^-1/2 exp(DD - |k|^2 d^-1/2 / 2 - stab) + 1e-4 (0 for padding)
+//                             -> 16-bit tile F [tokens][features];  KV (+)= F^T V  (A and B both MN-major, M = 64 features),
+//                             KS (+)= F^T 1  (the same MMA against a constant tile of ones: column sums without a reduction)
+//            KV -> 16-bit tile [features][d], KS column 0 -> ksum (float32)
+//   phase Q  per query tile:  DD = Q W'^T; phi(q) with the row's own max; den = phi(q) . ksum (float32, thread-local);
+//                             O = F KV (B MN-major) -> / max(den, 1e-2) -> 128-byte row stores
+// Loads are plain 16-byte global loads (8 lanes per 128-byte row) written with the 128-byte swizzle the UMMA descriptors expect.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "launch.h"
+#include "sm100_ptx.cuh"
+
+namespace eva {
+namespace rfatc {
+
+using fused::tmem_ld_cols;
+
+constexpr int kThreads = 128;
+constexpr int kTile = 128;
+constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cO = 160;     // TMEM columns
+// shared memory (bytes from the 1024-aligned base)
+constexpr int kX = 0, kV = 16384, kF = 32768, kOnes = 49152, kW = 65536, kKVt = 73728, kKsum = 81920, kRed = kKsum + 256,
+              kBar = kRed + 64, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
+
+struct Params {
+  int B, H, N, items;
+  const float* proj;        // [H, 64, 64]
+  const uint8_t* mask;      // [B, N] or NULL
+};
+
+template <typename T> struct Fmt;
+template <> struct Fmt<__half> { static constexpr uint32_t kUmma = ptx::kFmtF16; };
+template <> struct Fmt<__nv_bfloat16> { static constexpr uint32_t kUmma = ptx::kFmtBF16; };
+
+// rows n0 .. n0 + 128 of (b, h) -> swizzled [128][128 B] tile; rows past the sequence are zero
+template <typename T>
+__device__ __forceinline__ void load_tile(const View& x, int b, int h, int n0, int N, uint8_t* dst) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * kThreads + threadIdx.x, row = idx >> 3, ch = idx & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (n0 + row < N) val = __ldg(reinterpret_cast<const uint4*>(x.row<T>(b, n0 + row, h)) + ch);
+    *reinterpret_cast<uint4*>(dst + row * 128 + ((ch ^ (row & 7)) << 4)) = val;
+  }
+}
+
+// |x_row|^2 of the thread's own row of a swizzled tile
+template <typename T>
+__device__ __forceinline__ float row_sq(const uint8_t* tile, int row) {
+  float s = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4));
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float2 f = Pair16<T>::up(w4[u]); s = fmaf(f.x, f.x, fmaf(f.y, f.y, s)); }
+  }
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float (&f)[64]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4)) =
+        make_uint4(Pair16<T>::pk(f[8 * ch], f[8 * ch + 1]), Pair16<T>::pk(f[8 * ch + 2], f[8 * ch + 3]),
+                   Pair16<T>::pk(f[8 * ch + 4], f[8 * ch + 5]), Pair16<T>::pk(f[8 * ch + 6], f[8 * ch + 7]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = ptx::smem_u32(sm + kBar);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
+  float* const ksum = reinterpret_cast<float*>(sm + kKsum);
+  float* const red = reinterpret_cast<float*>(sm + kRed);
+  constexpr uint32_t fmt = Fmt<T>::kUmma;
+  constexpr uint32_t id_dd = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);     // X [128 x 64] . W'^T
+  constexpr uint32_t id_kv = ptx::umma_idesc(fmt, fmt, 1, 1, 64, 64);      // F^T [64 x 128] . V [128 x 64]
+  constexpr uint32_t id_ks = ptx::umma_idesc(fmt, fmt, 1, 1, 64, 16);      // F^T . ones
+  constexpr uint32_t id_o = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);      // F [128 x 64] . KV [64 x 64]
+  {
+    const uint32_t one2 = Pair16<T>::pk(1.0f, 1.0f);
+    for (int i = tid; i < 16384 / 16; i += kThreads) reinterpret_cast<uint4*>(sm + kOnes)[i] = make_uint4(one2, one2, one2, one2);
+  }
+  if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+  const uint64_t dX = ptx::umma_desc_sw128(ptx::smem_u32(sm + kX)), dV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV));
+  const uint64_t dF = ptx::umma_desc_sw128(ptx::smem_u32(sm + kF)), dOnes = ptx::umma_desc_sw128(ptx::smem_u32(sm + kOnes));
+  const uint64_t dW = ptx::umma_desc_sw128(ptx::smem_u32(sm + kW)), dKV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kKVt));
+  const float dn = 0.35355339059327373f;          // 64^-1/4
+  const float half_dn2 = 0.5f * dn * dn, ratio = 0.125f;   // m^-1/2, m = 64
+  uint32_t phase = 0;
+  auto mma_wait = [&]() { ptx::mbar_wait(bar, phase & 1); ++phase; ptx::tc_fence_after(); };
+  // smem tiles written by this thread -> visible to the tensor core; TMEM reads of this thread retired; then everyone
+  auto hand_over = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); __syncthreads(); };
+  auto issue_dd = [&]() {
+    if (warp == 0 && ptx::elect_one()) {
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cDD, dX + 2 * ks, dW + 2 * ks, id_dd, ks > 0);
+      ptx::umma_commit(bar);
+    }
+  };
+  const int tiles = (p.N + kTile - 1) / kTile;
+  int h_loaded = -1;
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int b = item / p.H, h = item % p.H;
+    if (h != h_loaded) {                            // W' = d^-1/4 W of this head, 16-bit, [feature][d] rows of 128 bytes
+      const float* W = p.proj + (long long)h * 4096;
+      for (int idx = tid; idx < 512; idx += kThreads) {
+        const int row = idx >> 3, ch = idx & 7;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(W + row * 64 + 8 * ch)), c = __ldg(reinterpret_cast<const float4*>(W + row * 64 + 8 * ch) + 1);
+        *reinterpret_cast<uint4*>(sm + kW + row * 128 + ((ch ^ (row & 7)) << 4)) =
+            make_uint4(Pair16<T>::pk(dn * a.x, dn * a.y), Pair16<T>::pk(dn * a.z, dn * a.w), Pair16<T>::pk(dn * c.x, dn * c.y), Pair16<T>::pk(dn * c.z, dn * c.w));
+      }
+      h_loaded = h;
+    }
+    // ---- pass 1: stabiliser of the keys = max over (token, feature) of DD (reference :48-51; padded keys count) ----
+    float mx = kNegInf;
+    for (int t = 0; t < tiles; ++t) {
+      load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
+      hand_over();
+      issue_dd();
+      mma_wait();
+      {
+        float dd[64], tmx = kNegInf;
+        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(dd));      // warp-collective: every lane, valid token or not
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) tmx = fmaxf(tmx, dd[j]);
+        if (t * kTile + tid < p.N) mx = fmaxf(mx, tmx);
+      }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    ptx::tc_fence_before();
+    __syncthreads();
+    const float stab = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    // ---- pass 2: KV = phi(K)^T V, KS = phi(K)^T 1 ----
+    for (int t = 0; t < tiles; ++t) {
+      load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
+      if (t > 0) mma_wait();                        // the previous tile's KV / KS MMAs have read F and V
+      load_tile<T>(v, b, h, t * kTile, p.N, sm + kV);
+      hand_over();
+      issue_dd();
+      mma_wait();
+      {
+        const int n = t * kTile + tid;
+        const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
+        float f[64];
+        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+        ptx::tmem_ld_wait();
+        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + stab;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = dead ? 0.f : fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+        store_row16<T>(sm + kF, tid, f);
+      }
+      hand_over();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKV, dF + 128 * ks, dV + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKS, dF + 128 * ks, dOnes + 128 * ks, id_ks, (t > 0 || ks > 0) ? 1u : 0u);
+        ptx::umma_commit(bar);
+      }
+    }
+    mma_wait();
+    {                                               // M = 64 accumulators: feature 16 w + l sits on lane l < 16 of quarter w
+      const int j = 16 * warp + (lane & 15);        // (tcgen05.ld is warp-collective: every lane issues the loads)
+      float kv[64];
+      uint32_t ks0;
+      tmem_ld_cols<64>(trow + cKV, reinterpret_cast<uint32_t*>(kv));
+      ptx::tmem_ld1(trow + cKS, ks0);
+      ptx::tmem_ld_wait();
+      if (lane < 16) {
+        store_row16<T>(sm + kKVt, j, kv);
+        ksum[j] = __uint_as_float(ks0);
+      }
+    }
+    // ---- phase Q ----
+    for (int t = 0; t < tiles; ++t) {
+      load_tile<T>(q, b, h, t * kTile, p.N, sm + kX);
+      hand_over();
+      issue_dd();
+      mma_wait();
+      float den = 0.f;
+      {
+        float f[64];
+        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+        ptx::tmem_ld_wait();
+        float rmx = kNegInf;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) rmx = fmaxf(rmx, f[j]);
+        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + rmx;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          f[j] = fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+          den = fmaf(f[j], ksum[j], den);
+        }
+        store_row16<T>(sm + kF, tid, f);
+      }
+      hand_over();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cO, dF + 2 * ks, dKV + 128 * ks, id_o, ks > 0);
+        ptx::umma_commit(bar);
+      }
+      mma_wait();
+      {
+        float o[64];
+        tmem_ld_cols<64>(trow + cO, reinterpret_cast<uint32_t*>(o));
+        ptx::tmem_ld_wait();
+        const int n = t * kTile + tid;
+        if (n < p.N) {
+          const float inv = 1.0f / fmaxf(den, 1e-2f);
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + n) * ((long long)p.H * 64) + (long long)h * 64);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            dst[ch] = make_uint4(Pair16<T>::pk(o[8 * ch] * inv, o[8 * ch + 1] * inv), Pair16<T>::pk(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                                 Pair16<T>::pk(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Pair16<T>::pk(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();                                // ksum / KV tile / W tile are rewritten by the next item
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+static int g_launches = 0;
+
+}  // namespace rfatc
+
+extern "C" int eva_debug_rfa_tc_launches(void) { return rfatc::g_launches; }
+
+bool rfa_tc_supported(int method, int D, int m, int cosw, int io_dtype, const View& q, const View& k, const View& v) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off) return false;
+  if (method != RFA_FAVORP || D != 64 || m != 64 || cosw) return false;
+  if (io_dtype != EVA_F16 && io_dtype != EVA_BF16) return false;
+  for (const View* x : {&q, &k, &v})
+    if (x->sh * 2 % 16 || x->sn * 2 % 16 || x->sb * 2 % 16 || reinterpret_cast<uintptr_t>(x->ptr) % 16) return false;
+  return true;
+}
+
+cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
+                          const float* proj, void* out, cudaStream_t st) {
+  rfatc::Params p{B, H, N, B * H, proj, mask};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int dyn = rfatc::kSmemBytes + 1024;
+  const int grid = p.items < 2 * sms ? p.items : 2 * sms;
+  ++rfatc::g_launches;
+  cudaError_t e;
+  if (io_dtype == EVA_F16) {
+    if ((e = cudaFuncSetAttribute(rfatc::rfa_favorp_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
+    rfatc::rfa_favorp_tc_kernel<__half><<<grid, rfatc::kThreads, dyn, st>>>(q, k, v, reinterpret_cast<__half*>(out), p);
+  } else {
+    if ((e = cudaFuncSetAttribute(rfatc::rfa_favorp_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
+    rfatc::rfa_favorp_tc_kernel<__nv_bfloat16><<<grid, rfatc::kThreads, dyn, st>>>(q, k, v, reinterpret_cast<__nv_bfloat16*>(out), p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace eva

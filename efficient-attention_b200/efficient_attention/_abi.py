@@ -389,6 +389,11 @@ def lara_forward(q, k, v, *, seq_shape, landmarks, per_token_proj, mixed, mis_ty
     return out
 
 
+def rfa_tc_launches():
+    """How many times the tcgen05 Performer kernel has been launched by this process (diagnostic; tests assert the path)."""
+    return load().eva_debug_rfa_tc_launches()
+
+
 def rfa_forward(q, k, v, *, method, proj=None, nu=1, cos_weighting=False, pad_mask=None, q_feat=None, k_feat=None):
     """Linear attention with the feature map `method` (kernelized_attention.py:301-320).  q, k, v: [B, N, H, D] views; proj float32
     [H, m, D]; method 'given': q_feat / k_feat float32 [B, H, N, M] computed by the caller.  Returns [B, N, H*D] in q's dtype."""

@@ -53,6 +53,31 @@ def test_performer_core_vs_oracle(dtype, method, m, cos):
     assert err < TOL[dtype], (method, dtype, err)
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('B,N,masked', [(2, 784, False), (3, 203, True), (1, 128, False), (120, 196, True)])
+def test_performer_tcgen05_path_vs_oracle(dtype, B, N, masked):
+    """'favorp', 64 features, head_dim 64, 16-bit: the tcgen05 kernel (launch counter), incl. ragged tiles, padded keys and more
+    items than resident CTAs (B = 120, h = 3: every CTA loops), against the float64 oracle on the same rounded q / k / v."""
+    from efficient_attention import _abi
+    H, D = 3, 64
+    (q, k, v), (qr, kr, vr) = _qkv(B, N, H, D, dtype, 21)
+    proj = torch.randn(H, 64, D, generator=torch.Generator().manual_seed(5))
+    mask = None
+    if masked:
+        mask = torch.zeros(B, N, dtype=torch.bool)
+        mask[B - 1, -37:] = True
+        mask[0, 5:9] = True
+    before = _abi.rfa_tc_launches()
+    out = _abi.rfa_forward(q, k, v, method='favorp', proj=proj.to(_dev()), pad_mask=None if mask is None else mask.to(_dev()))
+    assert _abi.rfa_tc_launches() == before + 1
+    worst = 0.0
+    for b0 in range(0, B, 8):                      # the oracle in slices of the batch
+        sl = slice(b0, min(B, b0 + 8))
+        ref = R.performer_core(qr[sl], kr[sl], vr[sl], method='favorp', proj=proj.double(), pad_mask=None if mask is None else mask[sl])
+        worst = max(worst, rel_l2(out[sl].cpu(), _heads(ref, ref.shape[0], N, H, D)))
+    assert worst < TOL[dtype], (dtype, B, N, worst)
+
+
 @pytest.mark.parametrize('D,m', [(16, 24), (32, 64), (128, 128)])
 def test_performer_core_other_head_dims(D, m):
     from efficient_attention import _abi
