@@ -41,6 +41,7 @@ struct Params {
   long long bias_sh;
   void* out;
   float* lse_out;                // training: log2-domain log-sum-exp per query row -> float32 [B, H, N], or NULL
+  const float* key_bias;         // float32 [B, H, N] added to the (scaled) logit of every live local key, or NULL (randomized attention)
   long long total;
   int trace;
 };
@@ -142,8 +143,12 @@ eva_window_tc_kernel(const Params p) {
           const int never = -2147483647 - 1;
           const int thr_row = (g.causal && gj < g.J) ? gj - g.ext : never;
           const int thr_chunk = (g.causal && gj >= g.J && gj < n_keys) ? gj - g.J + 1 : never;
-          kfac_all[128 * buf + j] = make_float4(flag == 0 ? 1.f : 0.f, flag == 0 ? 0.f : (flag == 1 ? g.mask_fill : kNegInf),
-                                                __int_as_float(thr_row), __int_as_float(thr_chunk));
+          float add = flag == 0 ? 0.f : (flag == 1 ? g.mask_fill : kNegInf);
+          if (p.key_bias && flag == 0 && gj < g.J) {     // (flag 0 and gj < J: the slot holds a token)
+            add = __ldg(p.key_bias + (long long)bh * g.N + group_token(g, win, gj, g.window, g.ext));
+            flags |= 4;                                  // the tile needs the per-key table
+          }
+          kfac_all[128 * buf + j] = make_float4(flag == 0 ? 1.f : 0.f, add, __int_as_float(thr_row), __int_as_float(thr_chunk));
         }
         flags |= flag;
       }
@@ -346,8 +351,9 @@ bool window_tc_supported(const Geo& g, int io_dtype) {
 
 cudaError_t launch_window_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                              const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st,
-                             float* lse_out) {
+                             float* lse_out, const float* key_bias) {
   wintc::Params p;
+  p.key_bias = key_bias;
   p.g = g; p.q = q; p.k = k; p.v = v; p.mask = mask;
   p.kbar = kbar; p.beta = beta; p.bias = bias; p.bias_sh = bias_sh; p.out = out; p.lse_out = lse_out;
   p.total = (long long)((g.L + 127) / 128) * g.n_windows * g.B * g.H;

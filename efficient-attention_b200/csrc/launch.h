@@ -62,7 +62,7 @@ cudaError_t launch_eva_backward(const Geo& g, int io_dtype, const View& q, const
 bool window_tc_supported(const Geo& g, int io_dtype);
 cudaError_t launch_window_tc(const Geo& g, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                              const float* kbar, const float* beta, const float* bias, long long bias_sh, void* out, cudaStream_t st,
-                             float* lse_out = nullptr);
+                             float* lse_out = nullptr, const float* key_bias = nullptr);   // key_bias: float32 [B, H, N] per-key logit addend
 
 // tcgen05 window-attention backward (eva_bwd_sm100.cu): head_dim 64, 16-bit I/O, halo-free windows of <= 64 tokens, <= 64 chunks
 bool window_bwd_tc_supported(const Geo& g, int io_dtype, const uint8_t* mask);

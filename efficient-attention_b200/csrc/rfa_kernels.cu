@@ -678,6 +678,61 @@ __global__ void __launch_bounds__(kThreads) ra_attn_kernel(const View q, const V
   }
 }
 
+
+// w = q + extra (+ noise) as a contiguous [B, N, H, D] tensor in the I/O format and kb[b, h, n] = -scale |k_n|^2 / 2: the inputs of the
+// tensor-core route (the dense tcgen05 window kernel with a per-key logit addend)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ra_prepare_kernel(const View q, const View k, const RaParams p, T* __restrict__ w, float* __restrict__ kb) {
+  const long long rows = (long long)p.B * p.N * p.H;
+  const float scale = rsqrtf((float)p.D);
+  const int pieces = p.D >> 3;
+  for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < rows * pieces; idx += (long long)gridDim.x * kThreads) {
+    const int pc = (int)(idx % pieces);
+    const long long row = idx / pieces;
+    const int h = (int)(row % p.H), n = (int)((row / p.H) % p.N), b = (int)(row / ((long long)p.H * p.N));
+    const int bh = b * p.H + h;
+    float x[8], e[8], kk[8];
+    load8<T>(q.row<T>(b, n, h) + 8 * pc, x);
+    load8<T>(k.row<T>(b, n, h) + 8 * pc, kk);
+    if (p.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = p.kmean[(long long)bh * p.D + 8 * pc + i];
+    } else if (p.mode == 1) {
+      load8<T>(reinterpret_cast<const T*>(p.extra) + ((long long)b * p.N + n) * ((long long)p.H * p.D) + (long long)h * p.D + 8 * pc, e);
+    } else {
+      load8<T>(k.row<T>(b, (int)p.k_ind[(long long)bh * p.N + n], h) + 8 * pc, e);
+    }
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      x[i] += e[i];
+      if (p.noise) x[i] += __ldg(p.noise + ((long long)bh * p.N + n) * p.D + 8 * pc + i);
+      sq = fmaf(kk[i], kk[i], sq);
+    }
+    T* dst = w + row * p.D + 8 * pc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = from_f32<T>(x[i]);
+    // the `pieces` lanes of a row are consecutive lanes of one warp (pieces divides 32 for D = 64)
+    const unsigned act = __activemask();              // groups of `pieces` lanes are active or inactive together
+    for (int o = pieces >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(act, sq, o);
+    if (pc == 0) kb[(long long)bh * p.N + n] = -0.5f * scale * sq;
+  }
+}
+
+template <typename T>
+static cudaError_t run_ra_tc(const RaParams& p, int io_dtype, const View& q, const View& k, const View& v, void* out, void* w16, float* kb,
+                             cudaStream_t st) {
+  if (p.mode == 0) ra_kmean_kernel<T><<<p.B * p.H, kThreads, 0, st>>>(k, p);
+  const long long work = (long long)p.B * p.N * p.H * (p.D >> 3);
+  const int grid = (int)((work + kThreads - 1) / kThreads < 148 * 8 ? (work + kThreads - 1) / kThreads : 148 * 8);
+  ra_prepare_kernel<T><<<grid, kThreads, 0, st>>>(q, k, p, reinterpret_cast<T*>(w16), kb);
+  Geo g{};
+  g.B = p.B; g.H = p.H; g.N = p.N; g.D = p.D; g.dims = 1; g.gh = 1; g.gw = p.N; g.window = p.N; g.n_windows = 1; g.L = p.N; g.J = p.N;
+  g.mask_fill = kNegInf;
+  View vw{w16, (long long)p.N * p.H * p.D, (long long)p.H * p.D, (long long)p.D};
+  return launch_window_tc(g, io_dtype, vw, k, v, nullptr, nullptr, nullptr, nullptr, 0, out, st, nullptr, kb);
+}
+
 template <typename T>
 static cudaError_t run_ra(const RaParams& p, const View& q, const View& k, const View& v, void* out, cudaStream_t st) {
   if (p.mode == 0) ra_kmean_kernel<T><<<p.B * p.H, kThreads, 0, st>>>(k, p);
@@ -814,6 +869,23 @@ int scatterbrain_forward(const SbGeometry* g, const EvaHeadsView* q, const EvaHe
 }
 
 /* ---- randomized attention ---- */
+static bool ra_uses_tensor_cores(const RaGeometry* g) {
+  if (g->head_dim != 64 || (g->io_dtype != EVA_F16 && g->io_dtype != EVA_BF16)) return false;
+  eva::Geo geo{};
+  geo.D = 64; geo.J = g->tokens;
+  return eva::window_tc_supported(geo, g->io_dtype);
+}
+
+int ra_forward_workspace_bytes(const RaGeometry* g, size_t* bytes) {
+  if (!g || !bytes) return eva::abi_fail(EVA_ERR_INVALID, "geometry / bytes is NULL");
+  size_t n = ((size_t)g->batch * g->heads * g->head_dim * 4 + 255) & ~(size_t)255;                 /* mean of k */
+  if (ra_uses_tensor_cores(g))
+    n += (((size_t)g->batch * g->tokens * g->heads * g->head_dim * 2 + 255) & ~(size_t)255) +       /* w, 16-bit */
+         (((size_t)g->batch * g->heads * g->tokens * 4 + 255) & ~(size_t)255);                      /* per-key addend */
+  *bytes = n;
+  return EVA_OK;
+}
+
 int ra_forward(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const void* extra,
                const int64_t* k_ind, const float* noise, void* out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!g) return eva::abi_fail(EVA_ERR_INVALID, "geometry is NULL");
@@ -828,13 +900,24 @@ int ra_forward(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k
   if (!out) return eva::abi_fail(EVA_ERR_INVALID, "out is NULL");
   if (g->mode == 1 && !extra) return eva::abi_fail(EVA_ERR_INVALID, "mode 1 needs the extra rows");
   if (g->mode == 2 && !k_ind) return eva::abi_fail(EVA_ERR_INVALID, "mode 2 needs k_ind");
-  if (g->mode == 0 && (!workspace || workspace_bytes < (size_t)g->batch * g->heads * g->head_dim * 4))
-    return eva::abi_fail(EVA_ERR_INVALID, "mode 0 needs batch * heads * head_dim floats of workspace");
+  size_t need = 0;
+  ra_forward_workspace_bytes(g, &need);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return eva::abi_fail(EVA_ERR_INVALID, "workspace too small (ra_forward_workspace_bytes) or not 256-byte aligned");
   eva::rfa::RaParams p{};
   p.B = g->batch; p.H = g->heads; p.N = g->tokens; p.D = g->head_dim; p.mode = g->mode;
   p.extra = extra; p.k_ind = reinterpret_cast<const long long*>(k_ind); p.noise = noise; p.kmean = reinterpret_cast<float*>(workspace);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
+  if (ra_uses_tensor_cores(g)) {      // prepare w, kb -> dense tcgen05 window kernel with a per-key addend (eva_window_tc_sm100.cu)
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    const size_t off_w = ((size_t)g->batch * g->heads * g->head_dim * 4 + 255) & ~(size_t)255;
+    const size_t off_kb = off_w + (((size_t)g->batch * g->tokens * g->heads * g->head_dim * 2 + 255) & ~(size_t)255);
+    if (g->io_dtype == EVA_F16) e = eva::rfa::run_ra_tc<__half>(p, g->io_dtype, vq, vk, vv, out, base + off_w, reinterpret_cast<float*>(base + off_kb), st);
+    else e = eva::rfa::run_ra_tc<__nv_bfloat16>(p, g->io_dtype, vq, vk, vv, out, base + off_w, reinterpret_cast<float*>(base + off_kb), st);
+    if (e != cudaSuccess) return eva::abi_cuda_fail(e, "ra_forward (tcgen05)");
+    return EVA_OK;
+  }
   if (g->io_dtype == EVA_F32) e = eva::rfa::run_ra<float>(p, vq, vk, vv, out, st);
   else if (g->io_dtype == EVA_F16) e = eva::rfa::run_ra<__half>(p, vq, vk, vv, out, st);
   else e = eva::rfa::run_ra<__nv_bfloat16>(p, vq, vk, vv, out, st);

@@ -103,8 +103,9 @@ def load():
         lib.scatterbrain_forward_workspace_bytes.argtypes = [SG, ctypes.POINTER(SZ)]
         lib.scatterbrain_forward.argtypes = [SG, V, V, V, P, P, P, P, P, SZ, P]
         lib.ra_forward.argtypes = [AG, V, V, V, P, P, P, P, P, SZ, P]
+        lib.ra_forward_workspace_bytes.argtypes = [AG, ctypes.POINTER(SZ)]
         for fn in ('rfa_feature_dim', 'rfa_forward_workspace_bytes', 'rfa_forward', 'scatterbrain_forward_workspace_bytes',
-                   'scatterbrain_forward', 'ra_forward'):
+                   'scatterbrain_forward', 'ra_forward', 'ra_forward_workspace_bytes'):
             getattr(lib, fn).restype = ctypes.c_int
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
                    'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_backward_step', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
@@ -450,7 +451,9 @@ def ra_forward(q, k, v, *, mode, extra=None, k_ind=None, noise=None):
     if k_ind is not None:
         k_ind = k_ind.to(torch.int64).contiguous()
     out = torch.empty(B, N, H * D, dtype=q.dtype, device=q.device)
-    ws = torch.empty(max(B * H * D * 4, 256), dtype=torch.uint8, device=q.device)
+    nbytes = ctypes.c_size_t(0)
+    _check(lib.ra_forward_workspace_bytes(ctypes.byref(geom), ctypes.byref(nbytes)), 'ra_forward_workspace_bytes')
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=q.device)
     with torch.cuda.device(q.device):
         rc = lib.ra_forward(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)), ctypes.byref(heads_view(v)),
                             _ptr(extra), _ptr(k_ind), _ptr(noise), _ptr(out), _ptr(ws), ws.numel(), _stream(q.device))

@@ -264,6 +264,7 @@ typedef struct RaGeometry {
   int32_t mode;
   int32_t io_dtype;
 } RaGeometry;
+int ra_forward_workspace_bytes(const RaGeometry* g, size_t* bytes);
 int ra_forward(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const void* extra,
                const int64_t* k_ind, const float* noise, void* out, void* workspace, size_t workspace_bytes, void* stream);
 

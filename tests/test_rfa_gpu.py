@@ -114,6 +114,7 @@ def test_ra_core_vs_oracle(dtype, mode):
     g = torch.Generator().manual_seed(3)
     noise = 0.5 * torch.randn(B, H, N, D, generator=g)
     k_ind = torch.randint(0, N, (B, H, N), generator=g)
+    tc_before = _abi.load().eva_debug_window_tc_count()
     if mode == 'given':
         extra = torch.randn(B, N, H * D, generator=g).to(dtype)
         ex_ref = extra.double().view(B, N, H, D).transpose(1, 2)
@@ -125,6 +126,8 @@ def test_ra_core_vs_oracle(dtype, mode):
     else:
         out = _abi.ra_forward(q, k, v, mode='gather', k_ind=k_ind.to(_dev()), noise=noise.to(_dev()))
         w_extra = torch.gather(kr, 2, k_ind.unsqueeze(-1).expand(-1, -1, -1, D))
+    if dtype != torch.float32:       # head_dim 64, 16-bit: the dense tcgen05 window kernel with a per-key addend did the softmax pass
+        assert _abi.load().eva_debug_window_tc_count() > tc_before
     s = D ** -0.5
     w = qr + w_extra + noise.double()
     ref = torch.softmax(s * (w @ kr.transpose(-1, -2)) - 0.5 * s * (kr * kr).sum(-1).unsqueeze(-2), -1) @ vr
