@@ -82,7 +82,9 @@ cudaError_t launch_window_bwd_gen(const Geo& g, int io_dtype, const View& q, con
 // Performer / FAVOR+ on tcgen05 (rfa_tc_sm100.cu): 'favorp', 64 features, head_dim 64, 16-bit I/O
 bool rfa_tc_supported(int method, int D, int m, int cosw, int io_dtype, const View& q, const View& k, const View& v);
 cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                          const float* proj, void* out, cudaStream_t st);
+                          const float* proj, void* out, cudaStream_t st, float* sb_stabv = nullptr, float* sb_part = nullptr);
+// sb_part != NULL: the ScatterBrain key statistics instead (per-feature maxima -> sb_stabv [items][64], KV | ksum -> sb_part
+// [items][64 * 64 + 64], float32); q / out unused
 
 // LARA (lara_generic.cu)
 struct LaraGeo {

@@ -545,14 +545,18 @@ __global__ void __launch_bounds__(kThreads) sb_window_kernel(const View q, const
 
 template <typename T>
 static cudaError_t run_sb(const Plan& pl, const SbParams& sp, size_t smem_win, int windows, const View& q, const View& k, const View& v,
-                          void* out, cudaStream_t st) {
+                          void* out, cudaStream_t st, bool sb_global_tc, int io_dtype) {
   const Params& p = pl.p;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(rfa_stab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_stab)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(rfa_kv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_kv)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(sb_window_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_win)) != cudaSuccess) return e;
-  rfa_stab_kernel<T><<<p.B * p.H, kThreads, pl.smem_stab, st>>>(k, k, p);
-  rfa_kv_kernel<T><<<dim3(p.B * p.H, p.S), kThreads, pl.smem_kv, st>>>(k, v, p);
+  if (sb_global_tc) {          // global key statistics on tcgen05 (rfa_tc_sm100.cu, kLogF); p.S == 1 there
+    if ((e = launch_rfa_tc(p.B, p.H, p.N, io_dtype, k, k, v, p.mask, p.proj, nullptr, st, p.stabv, p.part)) != cudaSuccess) return e;
+  } else {
+    rfa_stab_kernel<T><<<p.B * p.H, kThreads, pl.smem_stab, st>>>(k, k, p);
+    rfa_kv_kernel<T><<<dim3(p.B * p.H, p.S), kThreads, pl.smem_kv, st>>>(k, v, p);
+  }
   sb_window_kernel<T><<<dim3(p.B * p.H, windows), kThreads, smem_win, st>>>(q, k, v, reinterpret_cast<T*>(out), sp);
   return cudaGetLastError();
 }
@@ -858,12 +862,14 @@ int scatterbrain_forward(const SbGeometry* g, const EvaHeadsView* q, const EvaHe
   p.stabv = reinterpret_cast<float*>(workspace);
   p.stab = p.stabv;
   p.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t)p.B * p.H * p.m * 4 + 255) & ~(size_t)255));
+  const bool tc = eva::rfa_tc_supported(RFA_FAVORP, p.D, p.m, 0, g->io_dtype, vk, vk, vv);
+  if (tc) p.S = 1;                      // the tcgen05 statistics kernel writes one partial per item
   sp.r = p; sp.bias = bias;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (g->io_dtype == EVA_F32) e = eva::rfa::run_sb<float>(pl, sp, smem, windows, vq, vk, vv, out, st);
-  else if (g->io_dtype == EVA_F16) e = eva::rfa::run_sb<__half>(pl, sp, smem, windows, vq, vk, vv, out, st);
-  else e = eva::rfa::run_sb<__nv_bfloat16>(pl, sp, smem, windows, vq, vk, vv, out, st);
+  if (g->io_dtype == EVA_F32) e = eva::rfa::run_sb<float>(pl, sp, smem, windows, vq, vk, vv, out, st, false, g->io_dtype);
+  else if (g->io_dtype == EVA_F16) e = eva::rfa::run_sb<__half>(pl, sp, smem, windows, vq, vk, vv, out, st, tc, g->io_dtype);
+  else e = eva::rfa::run_sb<__nv_bfloat16>(pl, sp, smem, windows, vq, vk, vv, out, st, tc, g->io_dtype);
   if (e != cudaSuccess) return eva::abi_cuda_fail(e, "scatterbrain_forward");
   return EVA_OK;
 }

@@ -30,12 +30,14 @@ constexpr int kTile = 128;
 constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cO = 160;     // TMEM columns
 // shared memory (bytes from the 1024-aligned base)
 constexpr int kX = 0, kV = 16384, kF = 32768, kOnes = 49152, kW = 65536, kKVt = 73728, kKsum = 81920, kRed = kKsum + 256,
-              kBar = kRed + 64, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
+              kHs = kRed + 64, kMxs = kHs + 512, kBar = kMxs + 256, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
 
 struct Params {
   int B, H, N, items;
   const float* proj;        // [H, 64, 64]
   const uint8_t* mask;      // [B, N] or NULL
+  float* stabv;             // kLogF: [items][64] per-feature maxima of the keys' log-features
+  float* part;              // kLogF: [items][64 * 64 + 64] KV | ksum
 };
 
 template <typename T> struct Fmt;
@@ -77,7 +79,10 @@ __device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float 
                    Pair16<T>::pk(f[8 * ch + 4], f[8 * ch + 5]), Pair16<T>::pk(f[8 * ch + 6], f[8 * ch + 7]));
 }
 
-template <typename T>
+// kLogF: the key statistics of ScatterBrain instead (scatterbrain_attention.py:10-44, 107-121): features exp(log phi(k)_c - max_n log
+// phi(k_n)_c) with a PER-FEATURE maximum (pass 1 computes W' K^T, features on the TMEM lanes, so that the maximum over the tokens is
+// thread-local), no query phase; KV / ksum / the maxima go to global memory (float32) for sb_window_tc_kernel.
+template <typename T, bool kLogF>
 __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -86,6 +91,10 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
   float* const ksum = reinterpret_cast<float*>(sm + kKsum);
   float* const red = reinterpret_cast<float*>(sm + kRed);
+  float* const hs_s = reinterpret_cast<float*>(sm + kHs);       // kLogF: [128] |k|^2 term of the tile's tokens (-inf: dead token)
+  float* const mxs = reinterpret_cast<float*>(sm + kMxs);       // kLogF: [64] per-feature maxima
+  constexpr uint32_t id_ddt = ptx::umma_idesc(Fmt<T>::kUmma, Fmt<T>::kUmma, 0, 0, 64, 128);   // W' [64 x 64] . K^T -> [features x tokens]
+  const float hlm = 0.5f * 4.1588830833596715f;                 // log(64) / 2
   constexpr uint32_t fmt = Fmt<T>::kUmma;
   constexpr uint32_t id_dd = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);     // X [128 x 64] . W'^T
   constexpr uint32_t id_kv = ptx::umma_idesc(fmt, fmt, 1, 1, 64, 64);      // F^T [64 x 128] . V [128 x 64]
@@ -134,6 +143,42 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       }
       h_loaded = h;
     }
+    float stab = 0.f;
+    if constexpr (kLogF) {
+      // ---- pass 1: per-feature maximum over the live tokens of log phi(k)_c = DD - |k|^2 term - log(m) / 2 ----
+      float mxc = kNegInf;
+      for (int t = 0; t < tiles; ++t) {
+        load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncthreads();
+        {
+          const int n = t * kTile + tid;
+          const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
+          hs_s[tid] = dead ? __int_as_float(0x7f800000) : half_dn2 * row_sq<T>(sm + kX, tid);
+        }
+        if (warp == 0 && ptx::elect_one()) {
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cKV, dW + 2 * ks, dX + 2 * ks, id_ddt, ks > 0);
+          ptx::umma_commit(bar);
+        }
+        __syncthreads();                            // hs_s complete
+        mma_wait();
+#pragma unroll 1
+        for (int g8 = 0; g8 < 8; ++g8) {            // lanes < 16 of each warp hold a feature row; the loads are warp-collective
+          float dd[16];
+          ptx::tmem_ld16(trow + cKV + 16 * g8, reinterpret_cast<uint32_t*>(dd));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) mxc = fmaxf(mxc, dd[e] - hs_s[16 * g8 + e]);
+        }
+        ptx::tc_fence_before();
+        __syncthreads();                            // hs_s / the accumulator columns are rewritten by the next tile
+      }
+      if (lane < 16) mxs[16 * warp + lane] = mxc - hlm;
+      __syncthreads();
+    } else {
     // ---- pass 1: stabiliser of the keys = max over (token, feature) of DD (reference :48-51; padded keys count) ----
     float mx = kNegInf;
     for (int t = 0; t < tiles; ++t) {
@@ -154,7 +199,8 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
     if (lane == 0) red[warp] = mx;
     ptx::tc_fence_before();
     __syncthreads();
-    const float stab = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    stab = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    }
     // ---- pass 2: KV = phi(K)^T V, KS = phi(K)^T 1 ----
     for (int t = 0; t < tiles; ++t) {
       load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
@@ -169,9 +215,12 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
         float f[64];
         tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
-        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + stab;
+        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + (kLogF ? hlm : stab);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = dead ? 0.f : fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+        for (int j = 0; j < 64; ++j) {
+          if constexpr (kLogF) f[j] = dead ? 0.f : __expf(f[j] - sub - mxs[j]);
+          else f[j] = dead ? 0.f : fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+        }
         store_row16<T>(sm + kF, tid, f);
       }
       hand_over();
@@ -192,10 +241,23 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       tmem_ld_cols<64>(trow + cKV, reinterpret_cast<uint32_t*>(kv));
       ptx::tmem_ld1(trow + cKS, ks0);
       ptx::tmem_ld_wait();
-      if (lane < 16) {
+      if constexpr (kLogF) {
+        if (lane < 16) {
+          float* dst = p.part + (long long)item * (64 * 64 + 64);
+#pragma unroll
+          for (int d4 = 0; d4 < 16; ++d4) reinterpret_cast<float4*>(dst + j * 64)[d4] = make_float4(kv[4 * d4], kv[4 * d4 + 1], kv[4 * d4 + 2], kv[4 * d4 + 3]);
+          dst[64 * 64 + j] = __uint_as_float(ks0);
+          p.stabv[(long long)item * 64 + j] = mxs[j];
+        }
+      } else if (lane < 16) {
         store_row16<T>(sm + kKVt, j, kv);
         ksum[j] = __uint_as_float(ks0);
       }
+    }
+    if constexpr (kLogF) {
+      ptx::tc_fence_before();
+      __syncthreads();
+      continue;
     }
     // ---- phase Q ----
     for (int t = 0; t < tiles; ++t) {
@@ -269,23 +331,26 @@ bool rfa_tc_supported(int method, int D, int m, int cosw, int io_dtype, const Vi
 }
 
 cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
-                          const float* proj, void* out, cudaStream_t st) {
-  rfatc::Params p{B, H, N, B * H, proj, mask};
+                          const float* proj, void* out, cudaStream_t st, float* sb_stabv, float* sb_part) {
+  rfatc::Params p{B, H, N, B * H, proj, mask, sb_stabv, sb_part};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int dyn = rfatc::kSmemBytes + 1024;
   const int grid = p.items < 2 * sms ? p.items : 2 * sms;
   ++rfatc::g_launches;
-  cudaError_t e;
+  auto go = [&](auto kern, auto* o) -> cudaError_t {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, rfatc::kThreads, dyn, st>>>(q, k, v, o, p);
+    return cudaGetLastError();
+  };
   if (io_dtype == EVA_F16) {
-    if ((e = cudaFuncSetAttribute(rfatc::rfa_favorp_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
-    rfatc::rfa_favorp_tc_kernel<__half><<<grid, rfatc::kThreads, dyn, st>>>(q, k, v, reinterpret_cast<__half*>(out), p);
-  } else {
-    if ((e = cudaFuncSetAttribute(rfatc::rfa_favorp_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
-    rfatc::rfa_favorp_tc_kernel<__nv_bfloat16><<<grid, rfatc::kThreads, dyn, st>>>(q, k, v, reinterpret_cast<__nv_bfloat16*>(out), p);
+    __half* o = reinterpret_cast<__half*>(out);
+    return sb_part ? go(rfatc::rfa_favorp_tc_kernel<__half, true>, o) : go(rfatc::rfa_favorp_tc_kernel<__half, false>, o);
   }
-  return cudaGetLastError();
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  return sb_part ? go(rfatc::rfa_favorp_tc_kernel<__nv_bfloat16, true>, o) : go(rfatc::rfa_favorp_tc_kernel<__nv_bfloat16, false>, o);
 }
 
 }  // namespace eva
