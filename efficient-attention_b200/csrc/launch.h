@@ -86,6 +86,12 @@ cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, cons
 // sb_part != NULL: the ScatterBrain key statistics instead (per-feature maxima -> sb_stabv [items][64], KV | ksum -> sb_part
 // [items][64 * 64 + 64], float32); q / out unused
 
+// ScatterBrain window stage on tcgen05 (sb_window_tc_sm100.cu): 64 features, head_dim 64, 16-bit I/O, windows of <= 64 tokens
+bool sb_window_tc_supported(int D, int m, int L, int io_dtype);
+cudaError_t launch_sb_window_tc(int B, int H, int N, int dims, int gh, int gw, int w, int L, int n_windows, int io_dtype, const View& q,
+                                const View& k, const View& v, const uint8_t* mask, const float* proj, const float* bias,
+                                const float* stabv, const float* part, void* out, cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

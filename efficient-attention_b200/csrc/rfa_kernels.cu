@@ -557,6 +557,9 @@ static cudaError_t run_sb(const Plan& pl, const SbParams& sp, size_t smem_win, i
     rfa_stab_kernel<T><<<p.B * p.H, kThreads, pl.smem_stab, st>>>(k, k, p);
     rfa_kv_kernel<T><<<dim3(p.B * p.H, p.S), kThreads, pl.smem_kv, st>>>(k, v, p);
   }
+  if (sb_global_tc && sb_window_tc_supported(p.D, p.m, sp.L, io_dtype))
+    return launch_sb_window_tc(p.B, p.H, p.N, sp.dims, sp.gh, sp.gw, sp.w, sp.L, windows, io_dtype, q, k, v, p.mask, p.proj, sp.bias, p.stabv,
+                               p.part, out, st);
   sb_window_kernel<T><<<dim3(p.B * p.H, windows), kThreads, smem_win, st>>>(q, k, v, reinterpret_cast<T*>(out), sp);
   return cudaGetLastError();
 }

@@ -1,0 +1,322 @@
+// ScatterBrain window stage on tcgen05 / TMEM for sm_100a (scatterbrain_attention.py:95-160): 'favorp' log-features, 64 random
+// features, head_dim 64, 16-bit I/O, halo-free windows of at most 64 tokens.  The SIMT kernel of rfa_kernels.cu keeps everything else.
+//
+// One PAIR of windows of one (batch, head) item per iteration, 128 threads (thread r <-> TMEM lane r; rows 0-63 window a, 64-127
+// window b), with W' = d^-1/4 W in 16 bits and the item's global statistics G = sum_n phi(k_n) v_n, gs = sum_n phi(k_n), mx (per
+// feature; rfa_favorp_tc_kernel<kLogF>) in global memory:
+//   M1  DDk = [Ka ; Kb] W'^T                      E1  PK = exp(DDk - |k|^2 term - log(m)/2 - mx)  (0 for padding)      -> 16-bit tile
+//   M2  Lc_w = PK_w^T V_w, ls_w = PK_w^T 1 (w = a, b; M = 64 features), R = [Qa ; Qb] W'^T
+//                                                  E2  thread = feature: values (G - Lc_w) / max(gs - ls_w, 1e-3) -> 16-bit tile
+//                                                      KVS [a features ; b features][d], log-mass nl_w = log(sum outside the window)
+//   M3  S = [Qa ; Qb] [Ka ; Kb]^T (128 x 128; the diagonal blocks are used)
+//                                                  E3  thread = query row: local logits (scale, bias, -inf for padding) and feature
+//                                                      logits R - |q|^2 term - log(m)/2 + nl_w, ONE softmax over both, P (16-bit,
+//                                                      block-diagonal [local a, local b | features a, features b]) -> tensor memory
+//   M4  O = P [Va ; Vb ; KVS]  (A from tensor memory, K = 256)
+//                                                  E4  O / row sum -> 128-byte row stores
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "fused_common.cuh"
+#include "launch.h"
+#include "sm100_ptx.cuh"
+
+namespace eva {
+namespace sbtc {
+
+using fused::tmem_ld_cols;
+
+constexpr int kThreads = 128;
+constexpr uint32_t cDD = 0, cLa = 64, cLsa = 128, cLb = 144, cLsb = 208, cS = 64, cP = 64, cO = 192;
+constexpr int kQ = 0, kK = 16384, kV = 32768, kPK = 49152, kKVS = 65536, kW = 81920, kOnes = 90112, kNl = 98304, kMxs = kNl + 512,
+              kDead = kMxs + 256, kBar = kDead + 128, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
+
+struct Params {
+  int B, H, N, items;
+  int dims, gh, gw, w, L, n_windows;
+  const float* proj;       // [H, 64, 64]
+  const uint8_t* mask;     // [B, N] or NULL
+  const float* bias;       // [H, L, L] or NULL
+  const float* stabv;      // [items][64]
+  const float* part;       // [items][64 * 64 + 64]
+};
+
+template <typename T> struct Fmt;
+template <> struct Fmt<__half> { static constexpr uint32_t kUmma = ptx::kFmtF16; };
+template <> struct Fmt<__nv_bfloat16> { static constexpr uint32_t kUmma = ptx::kFmtBF16; };
+
+__device__ __forceinline__ int window_token(const Params& p, int g, int l) {
+  if (p.dims == 2) {
+    const int ngx = p.gw / p.w;
+    return ((g / ngx) * p.w + l / p.w) * p.gw + (g % ngx) * p.w + l % p.w;
+  }
+  return g * p.w + l;
+}
+
+template <typename T>
+__device__ __forceinline__ float row_sq(const uint8_t* tile, int row) {
+  float s = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4));
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float2 f = Pair16<T>::up(w4[u]); s = fmaf(f.x, f.x, fmaf(f.y, f.y, s)); }
+  }
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float (&f)[64]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4)) =
+        make_uint4(Pair16<T>::pk(f[8 * ch], f[8 * ch + 1]), Pair16<T>::pk(f[8 * ch + 2], f[8 * ch + 3]),
+                   Pair16<T>::pk(f[8 * ch + 4], f[8 * ch + 5]), Pair16<T>::pk(f[8 * ch + 6], f[8 * ch + 7]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar = ptx::smem_u32(sm + kBar);
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
+  float* const nl = reinterpret_cast<float*>(sm + kNl);          // [2][64]
+  float* const mxs = reinterpret_cast<float*>(sm + kMxs);        // [64]
+  uint8_t* const dead = sm + kDead;                              // [128] key row is padding / absent
+  float* const biasS = reinterpret_cast<float*>(sm + kBias);     // [L][L]
+  constexpr uint32_t fmt = Fmt<T>::kUmma;
+  constexpr uint32_t id_dd = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
+  constexpr uint32_t id_kv = ptx::umma_idesc(fmt, fmt, 1, 1, 64, 64);
+  constexpr uint32_t id_ks = ptx::umma_idesc(fmt, fmt, 1, 1, 64, 16);
+  constexpr uint32_t id_s = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 128);
+  constexpr uint32_t id_o = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);
+  {
+    const uint32_t one2 = Pair16<T>::pk(1.0f, 1.0f);
+    for (int i = tid; i < 8192 / 16; i += kThreads) reinterpret_cast<uint4*>(sm + kOnes)[i] = make_uint4(one2, one2, one2, one2);
+  }
+  if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+  const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(sm + kQ)), dK = ptx::umma_desc_sw128(ptx::smem_u32(sm + kK));
+  const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV)), dPK = ptx::umma_desc_sw128(ptx::smem_u32(sm + kPK));
+  const uint64_t dKVS = ptx::umma_desc_sw128(ptx::smem_u32(sm + kKVS)), dW = ptx::umma_desc_sw128(ptx::smem_u32(sm + kW));
+  const uint64_t dOnes = ptx::umma_desc_sw128(ptx::smem_u32(sm + kOnes));
+  const float dn = 0.35355339059327373f, half_dn2 = 0.5f * dn * dn, hlm = 0.5f * 4.1588830833596715f, scale = 0.125f;
+  uint32_t phase = 0;
+  auto mma_wait = [&]() { ptx::mbar_wait(bar, phase & 1); ++phase; ptx::tc_fence_after(); };
+  auto hand_over = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); __syncthreads(); };
+  const int L = p.L, pairs = (p.n_windows + 1) >> 1;
+  const int w2 = tid >> 6, li = tid & 63;                  // my row: window a / b of the pair, slot inside it
+  int h_loaded = -1;
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const int b = item / p.H, h = item % p.H;
+    if (h != h_loaded) {
+      const float* W = p.proj + (long long)h * 4096;
+      for (int idx = tid; idx < 512; idx += kThreads) {
+        const int row = idx >> 3, ch = idx & 7;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(W + row * 64 + 8 * ch)), c = __ldg(reinterpret_cast<const float4*>(W + row * 64 + 8 * ch) + 1);
+        *reinterpret_cast<uint4*>(sm + kW + row * 128 + ((ch ^ (row & 7)) << 4)) =
+            make_uint4(Pair16<T>::pk(dn * a.x, dn * a.y), Pair16<T>::pk(dn * a.z, dn * a.w), Pair16<T>::pk(dn * c.x, dn * c.y), Pair16<T>::pk(dn * c.z, dn * c.w));
+      }
+      for (int idx = tid; idx < L * L; idx += kThreads) biasS[idx] = p.bias ? __ldg(p.bias + (long long)h * L * L + idx) : 0.f;
+      h_loaded = h;
+    }
+    if (tid < 64) mxs[tid] = __ldg(p.stabv + (long long)item * 64 + tid);
+    const float* part = p.part + (long long)item * (64 * 64 + 64);
+    for (int pr = 0; pr < pairs; ++pr) {
+      const int win = 2 * pr + w2;
+      const bool have_row = win < p.n_windows && li < L;
+      const int tok = have_row ? window_token(p, win, li) : -1;
+      // ---- loads: rows of the two windows (8 lanes per 128-byte row), zero where there is no row ----
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * kThreads + tid, row = idx >> 3, ch = idx & 7;
+        const int rw = 2 * pr + (row >> 6), rl = row & 63;
+        uint4 zq = make_uint4(0, 0, 0, 0), zk = zq, zv = zq;
+        if (rw < p.n_windows && rl < L) {
+          const int t = window_token(p, rw, rl);
+          zq = __ldg(reinterpret_cast<const uint4*>(q.row<T>(b, t, h)) + ch);
+          zk = __ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + ch);
+          zv = __ldg(reinterpret_cast<const uint4*>(v.row<T>(b, t, h)) + ch);
+        }
+        const int off = row * 128 + ((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(sm + kQ + off) = zq;
+        *reinterpret_cast<uint4*>(sm + kK + off) = zk;
+        *reinterpret_cast<uint4*>(sm + kV + off) = zv;
+      }
+      dead[tid] = (!have_row || (p.mask && p.mask[(long long)b * p.N + tok])) ? 1 : 0;
+      hand_over();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cDD, dK + 2 * ks, dW + 2 * ks, id_dd, ks > 0);
+        ptx::umma_commit(bar);
+      }
+      mma_wait();
+      {   // E1: exp-features of my key row
+        float f[64];
+        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+        ptx::tmem_ld_wait();
+        const float sub = half_dn2 * row_sq<T>(sm + kK, tid) + hlm;
+        const bool dd_ = dead[tid] != 0;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = dd_ ? 0.f : __expf(f[j] - sub - mxs[j]);
+        store_row16<T>(sm + kPK, tid, f);
+      }
+      hand_over();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cLa, dPK + 128 * ks, dV + 128 * ks, id_kv, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cLsa, dPK + 128 * ks, dOnes + 128 * ks, id_ks, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cLb, dPK + 512 + 128 * ks, dV + 512 + 128 * ks, id_kv, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cLsb, dPK + 512 + 128 * ks, dOnes + 128 * ks, id_ks, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cDD, dQ + 2 * ks, dW + 2 * ks, id_dd, ks > 0);      // R (DDk is dead)
+        ptx::umma_commit(bar);
+      }
+      mma_wait();
+      {   // E2: thread = feature (lanes < 16 of each warp hold the M = 64 rows; the loads are warp-collective)
+        const int c = 16 * warp + (lane & 15);
+        const float gsum = __ldg(part + 64 * 64 + c);
+#pragma unroll 1
+        for (int ww = 0; ww < 2; ++ww) {
+          float lc[64];
+          uint32_t ls0;
+          tmem_ld_cols<64>(trow + (ww ? cLb : cLa), reinterpret_cast<uint32_t*>(lc));
+          ptx::tmem_ld1(trow + (ww ? cLsb : cLsa), ls0);
+          ptx::tmem_ld_wait();
+          if (lane < 16) {
+            const float ls = __uint_as_float(ls0);
+            const float inv = 1.0f / fmaxf(gsum - ls, 1e-3f);
+#pragma unroll
+            for (int d4 = 0; d4 < 16; ++d4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(part + c * 64) + d4);
+              lc[4 * d4] = (g4.x - lc[4 * d4]) * inv; lc[4 * d4 + 1] = (g4.y - lc[4 * d4 + 1]) * inv;
+              lc[4 * d4 + 2] = (g4.z - lc[4 * d4 + 2]) * inv; lc[4 * d4 + 3] = (g4.w - lc[4 * d4 + 3]) * inv;
+            }
+            store_row16<T>(sm + kKVS, 64 * ww + c, lc);
+            // log_add_exp(glse, llse, mask = (1, -1)) of attn_utils.py:44-51; both log-sums are relative to the per-feature maximum
+            const float glse = __logf(gsum), llse = __logf(ls), a = fmaxf(glse, llse);
+            nl[64 * ww + c] = mxs[c] + a + __logf(__expf(glse - a) - __expf(llse - a) + 1e-5f);
+          }
+        }
+      }
+      hand_over();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cS, dQ + 2 * ks, dK + 2 * ks, id_s, ks > 0);
+        ptx::umma_commit(bar);
+      }
+      mma_wait();
+      float rsum = 0.f;
+      {   // E3: joint softmax of my query row over [local keys of my window | the 64 feature keys]
+        float s[64], r[64];
+        tmem_ld_cols<64>(trow + cS + 64 * w2, reinterpret_cast<uint32_t*>(s));
+        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(r));
+        ptx::tmem_ld_wait();
+        const float qsub = half_dn2 * row_sq<T>(sm + kQ, tid) + hlm;
+        const float* brow = biasS + (li < L ? li : 0) * L;
+        float mx = kNegInf;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          s[j] = (j < L && !dead[64 * w2 + j]) ? fmaf(scale, s[j], brow[j < L ? j : 0]) : kNegInf;
+          r[j] = r[j] - qsub + nl[64 * w2 + j];
+          mx = fmaxf(mx, fmaxf(s[j], r[j]));
+        }
+        uint32_t pl[32], pr_[32];
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) {
+          const float e0 = __expf(s[j] - mx), e1 = __expf(s[j + 1] - mx), f0 = __expf(r[j] - mx), f1 = __expf(r[j + 1] - mx);
+          rsum += (e0 + e1) + (f0 + f1);
+          pl[j >> 1] = Pair16<T>::pk(e0, e1);
+          pr_[j >> 1] = Pair16<T>::pk(f0, f1);
+        }
+        uint32_t zero[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zero[j] = 0u;
+        // P row: 256 16-bit values = 128 columns: [local a | local b | features a | features b], mine in my window's blocks
+        fused::tmem_st_cols<32>(trow + cP + 32 * w2, pl);
+        fused::tmem_st_cols<32>(trow + cP + 32 * (1 - w2), zero);
+        fused::tmem_st_cols<32>(trow + cP + 64 + 32 * w2, pr_);
+        fused::tmem_st_cols<32>(trow + cP + 64 + 32 * (1 - w2), zero);
+        ptx::tmem_st_wait();
+      }
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (warp == 0 && ptx::elect_one()) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ts(tmem + cO, tmem + cP + 8 * ks, dV + 128 * ks, id_o, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ts(tmem + cO, tmem + cP + 64 + 8 * ks, dKVS + 128 * ks, id_o, 1);
+        ptx::umma_commit(bar);
+      }
+      mma_wait();
+      {   // E4
+        float o[64];
+        tmem_ld_cols<64>(trow + cO, reinterpret_cast<uint32_t*>(o));
+        ptx::tmem_ld_wait();
+        if (have_row) {
+          const float inv = 1.0f / rsum;
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + tok) * ((long long)p.H * 64) + (long long)h * 64);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            dst[ch] = make_uint4(Pair16<T>::pk(o[8 * ch] * inv, o[8 * ch + 1] * inv), Pair16<T>::pk(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
+                                 Pair16<T>::pk(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Pair16<T>::pk(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
+        }
+      }
+      ptx::tc_fence_before();
+      __syncthreads();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+static int g_launches = 0;
+
+}  // namespace sbtc
+
+extern "C" int eva_debug_sb_tc_launches(void) { return sbtc::g_launches; }
+
+bool sb_window_tc_supported(int D, int m, int L, int io_dtype) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("EVA_SM100_DISABLE_FUSED"); off = (e && e[0] == '1') ? 1 : 0; }
+  return !off && D == 64 && m == 64 && L <= 64 && (io_dtype == EVA_F16 || io_dtype == EVA_BF16);
+}
+
+cudaError_t launch_sb_window_tc(int B, int H, int N, int dims, int gh, int gw, int w, int L, int n_windows, int io_dtype, const View& q,
+                                const View& k, const View& v, const uint8_t* mask, const float* proj, const float* bias,
+                                const float* stabv, const float* part, void* out, cudaStream_t st) {
+  sbtc::Params p{B, H, N, B * H, dims, gh, gw, w, L, n_windows, proj, mask, bias, stabv, part};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int dyn = sbtc::kBias + L * L * 4 + 1024;
+  const int grid = p.items < 2 * sms ? p.items : 2 * sms;
+  ++sbtc::g_launches;
+  auto go = [&](auto kern, auto* o) -> cudaError_t {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, sbtc::kThreads, dyn, st>>>(q, k, v, o, p);
+    return cudaGetLastError();
+  };
+  if (io_dtype == EVA_F16) return go(sbtc::sb_window_tc_kernel<__half>, reinterpret_cast<__half*>(out));
+  return go(sbtc::sb_window_tc_kernel<__nv_bfloat16>, reinterpret_cast<__nv_bfloat16*>(out));
+}
+
+}  // namespace eva
