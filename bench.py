@@ -552,6 +552,36 @@ def other_shapes_leg(dev):
             out['c5'].update(core_ms=ms, core_roofline_frac=4 * 512 * 2 * 4096 * 16 / (ms * 1e-3) / 1e9 / peak)
     except Exception as e:
         out['core_error'] = f'{type(e).__name__}: {e}'[:300]
+    # the random-feature baselines of the registry on the c3 geometry, batch 256 (ra: 128): module forward and core
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            base = dict(dim=DIM, num_heads=3, qkv_bias=True, attn_drop=0., proj_drop=0., fp32=False)
+            mods = {'performer': ea.AttentionFactory.build_attention('performer', dict(base, approx_attn_dim=64, proj_method='favorp')),
+                    'scatterbrain': ea.AttentionFactory.build_attention('scatterbrain', dict(base, approx_attn_dim=64, window_size=7, attn_2d=True, use_rpe=True)),
+                    'ra': ea.AttentionFactory.build_attention('ra', dict(base, num_samples=-1))}
+        for name, m in mods.items():
+            m = lively_init(m).to(dev).half().eval()
+            bb = 128 if name == 'ra' else 256
+            with torch.no_grad():
+                x = torch.randn(bb, 28, 28, DIM, device=dev, dtype=torch.float16)
+                ms = timed(lambda: m(x))
+                q, k, v, _ = m._qkv_heads(x.reshape(bb, 784, DIM))
+                if name == 'performer':
+                    core = lambda: _abi.rfa_forward(q, k, v, method='favorp', proj=m.eval_proj.float())
+                elif name == 'scatterbrain':
+                    wb = m._window_bias()
+                    core = lambda: _abi.scatterbrain_forward(q, k, v, seq_shape=(28, 28), window=7, proj=m.eval_proj.float(), bias=wb)
+                else:
+                    ex = _abi.eva_window_attention(q, k, k, _abi.eva_geometry(q, seq_shape=(784,), window=784, ext=0, chunk=0, chunk_ext=0, mask_is_neg_inf=True))
+                    core = lambda: _abi.ra_forward(q, k, v, mode='given', extra=ex)
+                cms = core_time(core)
+            out[name] = {'what': f'{name} N=784, C=192, h=3, batch {bb} (registry baseline, SURVEY 8f-4)', 'module_ms': ms,
+                         'module_tokens_per_s': bb * 784 / (ms * 1e-3), 'core_ms': cms,
+                         'core_roofline_frac': 4 * DIM * 2 * 784 * bb / (cms * 1e-3) / 1e9 / peak}
+            del x, q, k, v
+    except Exception as e:
+        out['rfa_error'] = f'{type(e).__name__}: {e}'[:300]
     out['note'] = ('module = qkv Linear + attention core + proj Linear, fp16, inputs resident in HBM; module_traffic_gbs_of_peak = '
                    '10 C x 2 bytes per token (x in, qkv out + in, o out + in, y out) / time / measured HBM peak; core_* = the attention '
                    'core alone through the C ABI, 4 C x 2 bytes per token')
