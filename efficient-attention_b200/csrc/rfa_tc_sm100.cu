@@ -29,7 +29,7 @@ constexpr int kThreads = 128;
 constexpr int kTile = 128;
 constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cO = 160;     // TMEM columns
 // shared memory (bytes from the 1024-aligned base)
-constexpr int kX = 0, kV = 16384, kF = 32768, kOnes = 49152, kW = 65536, kKVt = 73728, kKsum = 81920, kRed = kKsum + 256,
+constexpr int kX = 0, kV = 32768, kF = 65536, kW = 81920, kKVt = 90112, kOnes = 98304, kKsum = 100352, kRed = kKsum + 256,   // X / V: two buffers of 16 KB
               kHs = kRed + 64, kMxs = kHs + 512, kBar = kMxs + 256, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
 
 struct Params {
@@ -44,15 +44,16 @@ template <typename T> struct Fmt;
 template <> struct Fmt<__half> { static constexpr uint32_t kUmma = ptx::kFmtF16; };
 template <> struct Fmt<__nv_bfloat16> { static constexpr uint32_t kUmma = ptx::kFmtBF16; };
 
-// rows n0 .. n0 + 128 of (b, h) -> swizzled [128][128 B] tile; rows past the sequence are zero
+// rows n0 .. n0 + 128 of (b, h) -> swizzled [128][128 B] tile, asynchronously (cp.async; rows past the sequence are zero-filled)
 template <typename T>
-__device__ __forceinline__ void load_tile(const View& x, int b, int h, int n0, int N, uint8_t* dst) {
+__device__ __forceinline__ void load_tile_async(const View& x, int b, int h, int n0, int N, uint8_t* dst) {
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int idx = it * kThreads + threadIdx.x, row = idx >> 3, ch = idx & 7;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (n0 + row < N) val = __ldg(reinterpret_cast<const uint4*>(x.row<T>(b, n0 + row, h)) + ch);
-    *reinterpret_cast<uint4*>(dst + row * 128 + ((ch ^ (row & 7)) << 4)) = val;
+    const bool ok = n0 + row < N;
+    const uint4* src = reinterpret_cast<const uint4*>(x.row<T>(b, ok ? n0 + row : 0, h)) + ch;
+    const uint32_t d = ptx::smem_u32(dst + row * 128 + ((ch ^ (row & 7)) << 4));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
   }
 }
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
   constexpr uint32_t id_o = ptx::umma_idesc(fmt, fmt, 0, 1, 128, 64);      // F [128 x 64] . KV [64 x 64]
   {
     const uint32_t one2 = Pair16<T>::pk(1.0f, 1.0f);
-    for (int i = tid; i < 16384 / 16; i += kThreads) reinterpret_cast<uint4*>(sm + kOnes)[i] = make_uint4(one2, one2, one2, one2);
+    for (int i = tid; i < 2048 / 16; i += kThreads) reinterpret_cast<uint4*>(sm + kOnes)[i] = make_uint4(one2, one2, one2, one2);   // 16 rows: every K step reads the same ones
   }
   if (tid == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
   if (warp == 0) ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr)), 256);
@@ -121,15 +122,38 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
   auto mma_wait = [&]() { ptx::mbar_wait(bar, phase & 1); ++phase; ptx::tc_fence_after(); };
   // smem tiles written by this thread -> visible to the tensor core; TMEM reads of this thread retired; then everyone
   auto hand_over = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); __syncthreads(); };
+  const int tiles = (p.N + kTile - 1) / kTile;
+  // The tiles of an item form a list of stages: [K tiles (pass 1)] [K + V tiles (pass 2)] [Q tiles].  Stage g of this CTA lives in
+  // buffer g & 1; its successor (possibly the first stage of the CTA's next item) is requested with cp.async before it is consumed.
+  const int stages_per_item = (kLogF ? 2 : 3) * tiles;
+  uint32_t gs = 0;                                  // stages consumed so far
+  int buf = 0;
+  auto stage_load = [&](int item_, int s_, int buf_) {
+    const int b_ = item_ / p.H, h_ = item_ % p.H, pass = s_ / tiles, t_ = s_ - pass * tiles;
+    load_tile_async<T>(pass == 2 ? q : k, b_, h_, t_ * kTile, p.N, sm + kX + buf_ * 16384);
+    if (pass == 1) load_tile_async<T>(v, b_, h_, t_ * kTile, p.N, sm + kV + buf_ * 16384);
+  };
+  // make stage (item_, s_) current: request its successor, wait for its own tiles
+  auto acquire = [&](int item_, int s_) {
+    buf = (int)(gs & 1);
+    int ni = item_, ns = s_ + 1;
+    if (ns == stages_per_item) { ni = item_ + (int)gridDim.x; ns = 0; }
+    if (ni < p.items) stage_load(ni, ns, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    ++gs;
+  };
   auto issue_dd = [&]() {
     if (warp == 0 && ptx::elect_one()) {
       ptx::tc_fence_after();
+      const uint64_t dXb = dX + (uint64_t)(buf * 1024);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cDD, dX + 2 * ks, dW + 2 * ks, id_dd, ks > 0);
+      for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cDD, dXb + 2 * ks, dW + 2 * ks, id_dd, ks > 0);
       ptx::umma_commit(bar);
     }
   };
-  const int tiles = (p.N + kTile - 1) / kTile;
+  if ((int)blockIdx.x < p.items) stage_load(blockIdx.x, 0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   int h_loaded = -1;
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int b = item / p.H, h = item % p.H;
@@ -148,19 +172,20 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       // ---- pass 1: per-feature maximum over the live tokens of log phi(k)_c = DD - |k|^2 term - log(m) / 2 ----
       float mxc = kNegInf;
       for (int t = 0; t < tiles; ++t) {
-        load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
+        acquire(item, t);
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncthreads();
         {
           const int n = t * kTile + tid;
           const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
-          hs_s[tid] = dead ? __int_as_float(0x7f800000) : half_dn2 * row_sq<T>(sm + kX, tid);
+          hs_s[tid] = dead ? __int_as_float(0x7f800000) : half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid);
         }
         if (warp == 0 && ptx::elect_one()) {
           ptx::tc_fence_after();
+          const uint64_t dXb = dX + (uint64_t)(buf * 1024);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cKV, dW + 2 * ks, dX + 2 * ks, id_ddt, ks > 0);
+          for (int ks = 0; ks < 4; ++ks) ptx::umma_ss(tmem + cKV, dW + 2 * ks, dXb + 2 * ks, id_ddt, ks > 0);
           ptx::umma_commit(bar);
         }
         __syncthreads();                            // hs_s complete
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
     // ---- pass 1: stabiliser of the keys = max over (token, feature) of DD (reference :48-51; padded keys count) ----
     float mx = kNegInf;
     for (int t = 0; t < tiles; ++t) {
-      load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
+      acquire(item, t);
       hand_over();
       issue_dd();
       mma_wait();
@@ -203,9 +228,8 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
     }
     // ---- pass 2: KV = phi(K)^T V, KS = phi(K)^T 1 ----
     for (int t = 0; t < tiles; ++t) {
-      load_tile<T>(k, b, h, t * kTile, p.N, sm + kX);
-      if (t > 0) mma_wait();                        // the previous tile's KV / KS MMAs have read F and V
-      load_tile<T>(v, b, h, t * kTile, p.N, sm + kV);
+      if (t > 0) mma_wait();                        // the previous tile's KV / KS MMAs have read F and its V buffer (the one the
+      acquire(item, tiles + t);                     // successor stage is loaded into)
       hand_over();
       issue_dd();
       mma_wait();
@@ -215,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
         float f[64];
         tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
-        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + (kLogF ? hlm : stab);
+        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid) + (kLogF ? hlm : stab);
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
           if constexpr (kLogF) f[j] = dead ? 0.f : __expf(f[j] - sub - mxs[j]);
@@ -227,9 +251,11 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKV, dF + 128 * ks, dV + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+        const uint64_t dVb = dV + (uint64_t)(buf * 1024);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKS, dF + 128 * ks, dOnes + 128 * ks, id_ks, (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKV, dF + 128 * ks, dVb + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKS, dF + 128 * ks, dOnes, id_ks, (t > 0 || ks > 0) ? 1u : 0u);
         ptx::umma_commit(bar);
       }
     }
@@ -261,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
     }
     // ---- phase Q ----
     for (int t = 0; t < tiles; ++t) {
-      load_tile<T>(q, b, h, t * kTile, p.N, sm + kX);
+      acquire(item, 2 * tiles + t);
       hand_over();
       issue_dd();
       mma_wait();
@@ -273,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
         float rmx = kNegInf;
 #pragma unroll
         for (int j = 0; j < 64; ++j) rmx = fmaxf(rmx, f[j]);
-        const float sub = half_dn2 * row_sq<T>(sm + kX, tid) + rmx;
+        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid) + rmx;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
           f[j] = fmaf(ratio, __expf(f[j] - sub), 1e-4f);
