@@ -14,6 +14,7 @@
 //                                                      block-diagonal [local a, local b | features a, features b]) -> tensor memory
 //   M4  O = P [Va ; Vb ; KVS]  (A from tensor memory, K = 256)
 //                                                  E4  O / row sum -> 128-byte row stores
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +30,7 @@ using fused::tmem_ld_cols;
 constexpr int kThreads = 128;
 constexpr uint32_t cDD = 0, cLa = 64, cLsa = 128, cLb = 144, cLsb = 208, cS = 64, cP = 64, cO = 192;
 constexpr int kQ = 0, kK = 16384, kV = 32768, kPK = 49152, kKVS = 65536, kW = 81920, kOnes = 90112, kNl = 98304, kMxs = kNl + 512,
-              kDead = kMxs + 256, kBar = kDead + 128, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
+              kDead = kMxs + 256, kBar = kDead + 256, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
 
 struct Params {
   int B, H, N, items;
@@ -39,6 +40,7 @@ struct Params {
   const float* bias;       // [H, L, L] or NULL
   const float* stabv;      // [items][64]
   const float* part;       // [items][64 * 64 + 64]
+  int trace;               // EVA_SM100_TRACE=1: phase clocks of one pair (block 0, thread 0)
 };
 
 template <typename T> struct Fmt;
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
   float* const nl = reinterpret_cast<float*>(sm + kNl);          // [2][64]
   float* const mxs = reinterpret_cast<float*>(sm + kMxs);        // [64]
-  uint8_t* const dead = sm + kDead;                              // [128] key row is padding / absent
+  uint8_t* const dead_all = sm + kDead;                          // [2][128] key row is padding / absent (per pair parity)
   float* const biasS = reinterpret_cast<float*>(sm + kBias);     // [L][L]
   constexpr uint32_t fmt = Fmt<T>::kUmma;
   constexpr uint32_t id_dd = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
@@ -114,6 +116,30 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
   auto hand_over = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); __syncthreads(); };
   const int L = p.L, pairs = (p.n_windows + 1) >> 1;
   const int w2 = tid >> 6, li = tid & 63;                  // my row: window a / b of the pair, slot inside it
+  // rows of the two windows of pair `pr_` of item `item_` -> tile `which` (0 q, 1 k, 2 v), cp.async with zero fill where there is no
+  // row; the key flags of that pair go to the parity buffer of pair counter `np_`
+  auto issue_rows = [&](int item_, int pr_, int which, uint32_t np_) {
+    const int b_ = item_ / p.H, h_ = item_ % p.H;
+    const View& x = which == 0 ? q : (which == 1 ? k : v);
+    uint8_t* const dst = sm + (which == 0 ? kQ : (which == 1 ? kK : kV));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * kThreads + tid, row = idx >> 3, ch = idx & 7;
+      const int rw = 2 * pr_ + (row >> 6), rl = row & 63;
+      const bool ok = rw < p.n_windows && rl < L;
+      const uint4* src = reinterpret_cast<const uint4*>(x.row<T>(b_, ok ? window_token(p, rw, rl) : 0, h_)) + ch;
+      const uint32_t d = ptx::smem_u32(dst + row * 128 + ((ch ^ (row & 7)) << 4));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    if (which == 1) {
+      const int rw = 2 * pr_ + w2;
+      const bool have = rw < p.n_windows && li < L;
+      dead_all[128 * (np_ & 1) + tid] = (!have || (p.mask && p.mask[(long long)b_ * p.N + window_token(p, rw, li)])) ? 1 : 0;
+    }
+  };
+  uint32_t np = 0;                                  // pairs processed by this CTA
+  long long tk[12];
+#define SB_MARK(i) if (p.trace && np == 5 && blockIdx.x == 0) tk[i] = clock64();
   int h_loaded = -1;
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int b = item / p.H, h = item % p.H;
@@ -130,29 +156,18 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
     }
     if (tid < 64) mxs[tid] = __ldg(p.stabv + (long long)item * 64 + tid);
     const float* part = p.part + (long long)item * (64 * 64 + 64);
-    for (int pr = 0; pr < pairs; ++pr) {
+    for (int pr = 0; pr < pairs; ++pr, ++np) {
       const int win = 2 * pr + w2;
       const bool have_row = win < p.n_windows && li < L;
       const int tok = have_row ? window_token(p, win, li) : -1;
-      // ---- loads: rows of the two windows (8 lanes per 128-byte row), zero where there is no row ----
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * kThreads + tid, row = idx >> 3, ch = idx & 7;
-        const int rw = 2 * pr + (row >> 6), rl = row & 63;
-        uint4 zq = make_uint4(0, 0, 0, 0), zk = zq, zv = zq;
-        if (rw < p.n_windows && rl < L) {
-          const int t = window_token(p, rw, rl);
-          zq = __ldg(reinterpret_cast<const uint4*>(q.row<T>(b, t, h)) + ch);
-          zk = __ldg(reinterpret_cast<const uint4*>(k.row<T>(b, t, h)) + ch);
-          zv = __ldg(reinterpret_cast<const uint4*>(v.row<T>(b, t, h)) + ch);
-        }
-        const int off = row * 128 + ((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(sm + kQ + off) = zq;
-        *reinterpret_cast<uint4*>(sm + kK + off) = zk;
-        *reinterpret_cast<uint4*>(sm + kV + off) = zv;
-      }
-      dead[tid] = (!have_row || (p.mask && p.mask[(long long)b * p.N + tok])) ? 1 : 0;
+      uint8_t* const dead = dead_all + 128 * (np & 1);
+      SB_MARK(0)
+      // ---- tiles of this pair: requested during the previous pair (q, k after its S MMA, v after its output MMA) ----
+      if (np == 0) { issue_rows(item, pr, 0, np); issue_rows(item, pr, 1, np); issue_rows(item, pr, 2, np); }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       hand_over();
+      SB_MARK(1)
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
 #pragma unroll
@@ -160,6 +175,8 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::umma_commit(bar);
       }
       mma_wait();
+      SB_MARK(2)
+      const float qsub = half_dn2 * row_sq<T>(sm + kQ, tid) + hlm;       // (the q tile is handed to the next pair after the S MMA)
       {   // E1: exp-features of my key row
         float f[64];
         tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
@@ -170,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         for (int j = 0; j < 64; ++j) f[j] = dd_ ? 0.f : __expf(f[j] - sub - mxs[j]);
         store_row16<T>(sm + kPK, tid, f);
       }
+      SB_MARK(3)
       hand_over();
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
@@ -186,6 +204,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::umma_commit(bar);
       }
       mma_wait();
+      SB_MARK(4)
       {   // E2: thread = feature (lanes < 16 of each warp hold the M = 64 rows; the loads are warp-collective)
         const int c = 16 * warp + (lane & 15);
         const float gsum = __ldg(part + 64 * 64 + c);
@@ -212,6 +231,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
           }
         }
       }
+      SB_MARK(5)
       hand_over();
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
@@ -220,13 +240,18 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::umma_commit(bar);
       }
       mma_wait();
+      // successor pair (possibly of the CTA's next item): its q and k rows travel under the softmax and the output MMA
+      int nitem = item, npr = pr + 1;
+      if (npr == pairs) { nitem = item + (int)gridDim.x; npr = 0; }
+      const bool more = nitem < p.items;
+      if (more) { issue_rows(nitem, npr, 0, np + 1); issue_rows(nitem, npr, 1, np + 1); }
+      SB_MARK(6)
       float rsum = 0.f;
       {   // E3: joint softmax of my query row over [local keys of my window | the 64 feature keys]
         float s[64], r[64];
         tmem_ld_cols<64>(trow + cS + 64 * w2, reinterpret_cast<uint32_t*>(s));
         tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(r));
         ptx::tmem_ld_wait();
-        const float qsub = half_dn2 * row_sq<T>(sm + kQ, tid) + hlm;
         const float* brow = biasS + (li < L ? li : 0) * L;
         float mx = kNegInf;
 #pragma unroll
@@ -253,6 +278,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         fused::tmem_st_cols<32>(trow + cP + 64 + 32 * (1 - w2), zero);
         ptx::tmem_st_wait();
       }
+      SB_MARK(7)
       ptx::tc_fence_before();
       __syncthreads();
       if (warp == 0 && ptx::elect_one()) {
@@ -264,6 +290,8 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::umma_commit(bar);
       }
       mma_wait();
+      SB_MARK(8)
+      if (more) issue_rows(nitem, npr, 2, np + 1);
       {   // E4
         float o[64];
         tmem_ld_cols<64>(trow + cO, reinterpret_cast<uint32_t*>(o));
@@ -277,8 +305,12 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
                                  Pair16<T>::pk(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Pair16<T>::pk(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
       }
+      SB_MARK(9)
       ptx::tc_fence_before();
       __syncthreads();
+      if (p.trace && np == 5 && blockIdx.x == 0 && tid == 0)
+        printf("sb pair trace (cycles): loads+wait %lld | sync %lld | M1 %lld | E1 %lld | sync+M2 %lld | E2 %lld | sync+M3 %lld | E3 %lld | sync+M4 %lld | E4 %lld\n",
+               tk[1] - tk[0], 0LL, tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4], tk[6] - tk[5], tk[7] - tk[6], tk[8] - tk[7], tk[9] - tk[8]);
     }
   }
   ptx::tc_fence_before();
@@ -302,7 +334,8 @@ bool sb_window_tc_supported(int D, int m, int L, int io_dtype) {
 cudaError_t launch_sb_window_tc(int B, int H, int N, int dims, int gh, int gw, int w, int L, int n_windows, int io_dtype, const View& q,
                                 const View& k, const View& v, const uint8_t* mask, const float* proj, const float* bias,
                                 const float* stabv, const float* part, void* out, cudaStream_t st) {
-  sbtc::Params p{B, H, N, B * H, dims, gh, gw, w, L, n_windows, proj, mask, bias, stabv, part};
+  static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();
+  sbtc::Params p{B, H, N, B * H, dims, gh, gw, w, L, n_windows, proj, mask, bias, stabv, part, trace};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

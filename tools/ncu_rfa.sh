@@ -18,6 +18,6 @@ for _ in range(2):
 torch.cuda.synchronize()
 PY
 for kern in rfa_favorp_tc_kernel sb_window_tc_kernel; do
-  timeout 600 ncu --set full --clock-control none -k regex:$kern -s 2 -c 1 --csv --page raw --log-file gpurun_out/ncu_raw_${kern}_B256.csv python /tmp/rfa_one.py > gpurun_out/ncu_${kern}.log 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:$kern -s 1 -c 1 --csv --page raw --log-file gpurun_out/ncu_raw_${kern}_B256.csv python /tmp/rfa_one.py > gpurun_out/ncu_${kern}.log 2>&1
   echo "$kern rc=$?"
 done
