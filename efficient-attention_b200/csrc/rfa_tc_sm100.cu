@@ -25,12 +25,12 @@ namespace rfatc {
 
 using fused::tmem_ld_cols;
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;       // warps w and w + 4 share a TMEM lane quarter and split the columns of every epilogue
 constexpr int kTile = 128;
 constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cO = 160;     // TMEM columns
 // shared memory (bytes from the 1024-aligned base)
 constexpr int kX = 0, kV = 32768, kF = 65536, kW = 81920, kKVt = 90112, kOnes = 98304, kKsum = 100352, kRed = kKsum + 256,   // X / V: two buffers of 16 KB
-              kHs = kRed + 64, kMxs = kHs + 512, kBar = kMxs + 256, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
+              kHs = kRed + 64, kMxs = kHs + 512, kPm = kMxs + 256, kPd = kPm + 1024, kMx2 = kPd + 1024, kBar = kMx2 + 512, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
 
 struct Params {
   int B, H, N, items;
@@ -48,7 +48,7 @@ template <> struct Fmt<__nv_bfloat16> { static constexpr uint32_t kUmma = ptx::k
 template <typename T>
 __device__ __forceinline__ void load_tile_async(const View& x, int b, int h, int n0, int N, uint8_t* dst) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
+  for (int it = 0; it < 1024 / kThreads; ++it) {
     const int idx = it * kThreads + threadIdx.x, row = idx >> 3, ch = idx & 7;
     const bool ok = n0 + row < N;
     const uint4* src = reinterpret_cast<const uint4*>(x.row<T>(b, ok ? n0 + row : 0, h)) + ch;
@@ -80,14 +80,28 @@ __device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float 
                    Pair16<T>::pk(f[8 * ch + 4], f[8 * ch + 5]), Pair16<T>::pk(f[8 * ch + 6], f[8 * ch + 7]));
 }
 
+// features [32 hf, 32 hf + 32) of a row -> chunks 4 hf .. 4 hf + 3 of the swizzled 16-bit tile
+template <typename T>
+__device__ __forceinline__ void store_half16(uint8_t* tile, int row, int hf, const float (&f)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + row * 128 + (((4 * hf + c) ^ (row & 7)) << 4)) =
+        make_uint4(Pair16<T>::pk(f[8 * c], f[8 * c + 1]), Pair16<T>::pk(f[8 * c + 2], f[8 * c + 3]),
+                   Pair16<T>::pk(f[8 * c + 4], f[8 * c + 5]), Pair16<T>::pk(f[8 * c + 6], f[8 * c + 7]));
+}
+
 // kLogF: the key statistics of ScatterBrain instead (scatterbrain_attention.py:10-44, 107-121): features exp(log phi(k)_c - max_n log
 // phi(k_n)_c) with a PER-FEATURE maximum (pass 1 computes W' K^T, features on the TMEM lanes, so that the maximum over the tokens is
 // thread-local), no query phase; KV / ksum / the maxima go to global memory (float32) for sb_window_tc_kernel.
 template <typename T, bool kLogF>
-__global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
+__global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qr = warp & 3, hf = warp >> 2, r = 32 * qr + lane;     // my TMEM lane quarter, column half, row of the tile
+  float* const pm = reinterpret_cast<float*>(sm + kPm);          // [2][128] partial row maxima of the two column halves
+  float* const pd = reinterpret_cast<float*>(sm + kPd);          // [2][128] partial denominators
+  float* const mx2 = reinterpret_cast<float*>(sm + kMx2);        // kLogF: [2][64] partial per-feature maxima
   const uint32_t bar = ptx::smem_u32(sm + kBar);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
   float* const ksum = reinterpret_cast<float*>(sm + kKsum);
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+  const uint32_t trow = tmem + ((uint32_t)(32 * qr) << 16);
   const uint64_t dX = ptx::umma_desc_sw128(ptx::smem_u32(sm + kX)), dV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV));
   const uint64_t dF = ptx::umma_desc_sw128(ptx::smem_u32(sm + kF)), dOnes = ptx::umma_desc_sw128(ptx::smem_u32(sm + kOnes));
   const uint64_t dW = ptx::umma_desc_sw128(ptx::smem_u32(sm + kW)), dKV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kKVt));
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncthreads();
-        {
+        if (tid < 128) {
           const int n = t * kTile + tid;
           const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
           hs_s[tid] = dead ? __int_as_float(0x7f800000) : half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid);
@@ -191,17 +205,19 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
         __syncthreads();                            // hs_s complete
         mma_wait();
 #pragma unroll 1
-        for (int g8 = 0; g8 < 8; ++g8) {            // lanes < 16 of each warp hold a feature row; the loads are warp-collective
-          float dd[16];
-          ptx::tmem_ld16(trow + cKV + 16 * g8, reinterpret_cast<uint32_t*>(dd));
+        for (int g8 = 0; g8 < 4; ++g8) {            // lanes < 16 of each warp hold a feature row (warp-collective loads); my half of
+          float dd[16];                             // the 128 token columns
+          ptx::tmem_ld16(trow + cKV + 64 * hf + 16 * g8, reinterpret_cast<uint32_t*>(dd));
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) mxc = fmaxf(mxc, dd[e] - hs_s[16 * g8 + e]);
+          for (int e = 0; e < 16; ++e) mxc = fmaxf(mxc, dd[e] - hs_s[64 * hf + 16 * g8 + e]);
         }
         ptx::tc_fence_before();
         __syncthreads();                            // hs_s / the accumulator columns are rewritten by the next tile
       }
-      if (lane < 16) mxs[16 * warp + lane] = mxc - hlm;
+      if (lane < 16) mx2[64 * hf + 16 * qr + lane] = mxc;
+      __syncthreads();
+      if (tid < 64) mxs[tid] = fmaxf(mx2[tid], mx2[64 + tid]) - hlm;
       __syncthreads();
     } else {
     // ---- pass 1: stabiliser of the keys = max over (token, feature) of DD (reference :48-51; padded keys count) ----
@@ -212,19 +228,19 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       issue_dd();
       mma_wait();
       {
-        float dd[64], tmx = kNegInf;
-        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(dd));      // warp-collective: every lane, valid token or not
+        float dd[32], tmx = kNegInf;
+        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(dd));      // warp-collective: every lane, valid token or not
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 64; ++j) tmx = fmaxf(tmx, dd[j]);
-        if (t * kTile + tid < p.N) mx = fmaxf(mx, tmx);
+        for (int j = 0; j < 32; ++j) tmx = fmaxf(tmx, dd[j]);
+        if (t * kTile + r < p.N) mx = fmaxf(mx, tmx);
       }
     }
     mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
     ptx::tc_fence_before();
     __syncthreads();
-    stab = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    stab = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
     }
     // ---- pass 2: KV = phi(K)^T V, KS = phi(K)^T 1 ----
     for (int t = 0; t < tiles; ++t) {
@@ -234,23 +250,22 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       issue_dd();
       mma_wait();
       {
-        const int n = t * kTile + tid;
+        const int n = t * kTile + r;
         const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
-        float f[64];
-        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+        float f[32];
+        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
-        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid) + (kLogF ? hlm : stab);
+        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + (kLogF ? hlm : stab);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          if constexpr (kLogF) f[j] = dead ? 0.f : __expf(f[j] - sub - mxs[j]);
+        for (int j = 0; j < 32; ++j) {
+          if constexpr (kLogF) f[j] = dead ? 0.f : __expf(f[j] - sub - mxs[32 * hf + j]);
           else f[j] = dead ? 0.f : fmaf(ratio, __expf(f[j] - sub), 1e-4f);
         }
-        store_row16<T>(sm + kF, tid, f);
+        store_half16<T>(sm + kF, r, hf, f);
       }
       hand_over();
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
-#pragma unroll
         const uint64_t dVb = dV + (uint64_t)(buf * 1024);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKV, dF + 128 * ks, dVb + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
@@ -260,24 +275,23 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       }
     }
     mma_wait();
-    {                                               // M = 64 accumulators: feature 16 w + l sits on lane l < 16 of quarter w
-      const int j = 16 * warp + (lane & 15);        // (tcgen05.ld is warp-collective: every lane issues the loads)
-      float kv[64];
+    {                                               // M = 64 accumulators: feature 16 qr + l sits on lane l < 16 of quarter qr;
+      const int j = 16 * qr + (lane & 15);          // my half of its 64 columns (tcgen05.ld is warp-collective: every lane loads)
+      float kv[32];
       uint32_t ks0;
-      tmem_ld_cols<64>(trow + cKV, reinterpret_cast<uint32_t*>(kv));
+      tmem_ld_cols<32>(trow + cKV + 32 * hf, reinterpret_cast<uint32_t*>(kv));
       ptx::tmem_ld1(trow + cKS, ks0);
       ptx::tmem_ld_wait();
       if constexpr (kLogF) {
         if (lane < 16) {
           float* dst = p.part + (long long)item * (64 * 64 + 64);
 #pragma unroll
-          for (int d4 = 0; d4 < 16; ++d4) reinterpret_cast<float4*>(dst + j * 64)[d4] = make_float4(kv[4 * d4], kv[4 * d4 + 1], kv[4 * d4 + 2], kv[4 * d4 + 3]);
-          dst[64 * 64 + j] = __uint_as_float(ks0);
-          p.stabv[(long long)item * 64 + j] = mxs[j];
+          for (int d4 = 0; d4 < 8; ++d4) reinterpret_cast<float4*>(dst + j * 64 + 32 * hf)[d4] = make_float4(kv[4 * d4], kv[4 * d4 + 1], kv[4 * d4 + 2], kv[4 * d4 + 3]);
+          if (hf == 0) { dst[64 * 64 + j] = __uint_as_float(ks0); p.stabv[(long long)item * 64 + j] = mxs[j]; }
         }
       } else if (lane < 16) {
-        store_row16<T>(sm + kKVt, j, kv);
-        ksum[j] = __uint_as_float(ks0);
+        store_half16<T>(sm + kKVt, j, hf, kv);
+        if (hf == 0) ksum[j] = __uint_as_float(ks0);
       }
     }
     if constexpr (kLogF) {
@@ -291,21 +305,25 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       hand_over();
       issue_dd();
       mma_wait();
-      float den = 0.f;
       {
-        float f[64];
-        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+        float f[32];
+        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
         float rmx = kNegInf;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) rmx = fmaxf(rmx, f[j]);
-        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, tid) + rmx;
+        for (int j = 0; j < 32; ++j) rmx = fmaxf(rmx, f[j]);
+        pm[128 * hf + r] = rmx;
+        __syncthreads();                            // the two column halves of a row meet
+        rmx = fmaxf(pm[r], pm[128 + r]);
+        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + rmx;
+        float den = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < 32; ++j) {
           f[j] = fmaf(ratio, __expf(f[j] - sub), 1e-4f);
-          den = fmaf(f[j], ksum[j], den);
+          den = fmaf(f[j], ksum[32 * hf + j], den);
         }
-        store_row16<T>(sm + kF, tid, f);
+        pd[128 * hf + r] = den;
+        store_half16<T>(sm + kF, r, hf, f);
       }
       hand_over();
       if (warp == 0 && ptx::elect_one()) {
@@ -316,15 +334,15 @@ __global__ void __launch_bounds__(kThreads) rfa_favorp_tc_kernel(const View q, c
       }
       mma_wait();
       {
-        float o[64];
-        tmem_ld_cols<64>(trow + cO, reinterpret_cast<uint32_t*>(o));
+        float o[32];
+        tmem_ld_cols<32>(trow + cO + 32 * hf, reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
-        const int n = t * kTile + tid;
+        const int n = t * kTile + r;
         if (n < p.N) {
-          const float inv = 1.0f / fmaxf(den, 1e-2f);
-          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + n) * ((long long)p.H * 64) + (long long)h * 64);
+          const float inv = 1.0f / fmaxf(pd[r] + pd[128 + r], 1e-2f);
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + n) * ((long long)p.H * 64) + (long long)h * 64) + 4 * hf;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
+          for (int ch = 0; ch < 4; ++ch)
             dst[ch] = make_uint4(Pair16<T>::pk(o[8 * ch] * inv, o[8 * ch + 1] * inv), Pair16<T>::pk(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
                                  Pair16<T>::pk(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Pair16<T>::pk(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
