@@ -30,7 +30,7 @@ using fused::tmem_ld_cols;
 constexpr int kThreads = 128;
 constexpr uint32_t cDD = 0, cLa = 64, cLsa = 128, cLb = 144, cLsb = 208, cS = 64, cP = 64, cO = 192;
 constexpr int kQ = 0, kK = 16384, kV = 32768, kPK = 49152, kKVS = 65536, kW = 81920, kOnes = 90112, kNl = 98304, kMxs = kNl + 512,
-              kDead = kMxs + 256, kBar = kDead + 256, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
+              kDead = kMxs + 256, kTok = kDead + 256, kDmask = kTok + 1024, kBar = kDmask + 16, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
 
 struct Params {
   int B, H, N, items;
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
   float* const nl = reinterpret_cast<float*>(sm + kNl);          // [2][64]
   float* const mxs = reinterpret_cast<float*>(sm + kMxs);        // [64]
   uint8_t* const dead_all = sm + kDead;                          // [2][128] key row is padding / absent (per pair parity)
+  int* const tokS = reinterpret_cast<int*>(sm + kTok);           // [2][128] token of every row of the pair (-1: no row), per pair parity
+  uint32_t* const dmask = reinterpret_cast<uint32_t*>(sm + kDmask);   // [4] the dead flags of the pair as one ballot per warp
   float* const biasS = reinterpret_cast<float*>(sm + kBias);     // [L][L]
   constexpr uint32_t fmt = Fmt<T>::kUmma;
   constexpr uint32_t id_dd = ptx::umma_idesc(fmt, fmt, 0, 0, 128, 64);
@@ -125,16 +127,15 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int idx = it * kThreads + tid, row = idx >> 3, ch = idx & 7;
-      const int rw = 2 * pr_ + (row >> 6), rl = row & 63;
-      const bool ok = rw < p.n_windows && rl < L;
-      const uint4* src = reinterpret_cast<const uint4*>(x.row<T>(b_, ok ? window_token(p, rw, rl) : 0, h_)) + ch;
+      const int tk_ = tokS[128 * (np_ & 1) + row];                 // (index arithmetic with divisions: once per row and pair)
+      const bool ok = tk_ >= 0;
+      const uint4* src = reinterpret_cast<const uint4*>(x.row<T>(b_, ok ? tk_ : 0, h_)) + ch;
       const uint32_t d = ptx::smem_u32(dst + row * 128 + ((ch ^ (row & 7)) << 4));
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
     if (which == 1) {
-      const int rw = 2 * pr_ + w2;
-      const bool have = rw < p.n_windows && li < L;
-      dead_all[128 * (np_ & 1) + tid] = (!have || (p.mask && p.mask[(long long)b_ * p.N + window_token(p, rw, li)])) ? 1 : 0;
+      const int tk_ = tokS[128 * (np_ & 1) + tid];
+      dead_all[128 * (np_ & 1) + tid] = (tk_ < 0 || (p.mask && p.mask[(long long)b_ * p.N + tk_])) ? 1 : 0;
     }
   };
   uint32_t np = 0;                                  // pairs processed by this CTA
@@ -157,9 +158,15 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
     if (tid < 64) mxs[tid] = __ldg(p.stabv + (long long)item * 64 + tid);
     const float* part = p.part + (long long)item * (64 * 64 + 64);
     for (int pr = 0; pr < pairs; ++pr, ++np) {
-      const int win = 2 * pr + w2;
-      const bool have_row = win < p.n_windows && li < L;
-      const int tok = have_row ? window_token(p, win, li) : -1;
+      auto pair_token = [&](int pr_) { const int win_ = 2 * pr_ + w2; return (win_ < p.n_windows && li < L) ? window_token(p, win_, li) : -1; };
+      if (np == 0) { tokS[tid] = pair_token(pr); __syncthreads(); }
+      // successor pair (possibly of the CTA's next item): its row tokens now, its rows under this pair's softmax / output MMA
+      int nitem = item, npr = pr + 1;
+      if (npr == pairs) { nitem = item + (int)gridDim.x; npr = 0; }
+      const bool more = nitem < p.items;
+      tokS[128 * ((np + 1) & 1) + tid] = more ? pair_token(npr) : -1;
+      const int tok = tokS[128 * (np & 1) + tid];
+      const bool have_row = tok >= 0;
       uint8_t* const dead = dead_all + 128 * (np & 1);
       SB_MARK(0)
       // ---- tiles of this pair: requested during the previous pair (q, k after its S MMA, v after its output MMA) ----
@@ -183,6 +190,8 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::tmem_ld_wait();
         const float sub = half_dn2 * row_sq<T>(sm + kK, tid) + hlm;
         const bool dd_ = dead[tid] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, dd_);
+        if (lane == 0) dmask[warp] = bal;
 #pragma unroll
         for (int j = 0; j < 64; ++j) f[j] = dd_ ? 0.f : __expf(f[j] - sub - mxs[j]);
         store_row16<T>(sm + kPK, tid, f);
@@ -240,11 +249,8 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         ptx::umma_commit(bar);
       }
       mma_wait();
-      // successor pair (possibly of the CTA's next item): its q and k rows travel under the softmax and the output MMA
-      int nitem = item, npr = pr + 1;
-      if (npr == pairs) { nitem = item + (int)gridDim.x; npr = 0; }
-      const bool more = nitem < p.items;
-      if (more) { issue_rows(nitem, npr, 0, np + 1); issue_rows(nitem, npr, 1, np + 1); }
+      if (more) {       // the successor's q and k rows travel under the softmax and the output MMA
+        issue_rows(nitem, npr, 0, np + 1); issue_rows(nitem, npr, 1, np + 1); }
       SB_MARK(6)
       float rsum = 0.f;
       {   // E3: joint softmax of my query row over [local keys of my window | the 64 feature keys]
@@ -253,10 +259,11 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(r));
         ptx::tmem_ld_wait();
         const float* brow = biasS + (li < L ? li : 0) * L;
+        const unsigned long long dm = (unsigned long long)dmask[2 * w2] | ((unsigned long long)dmask[2 * w2 + 1] << 32);
         float mx = kNegInf;
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
-          s[j] = (j < L && !dead[64 * w2 + j]) ? fmaf(scale, s[j], brow[j < L ? j : 0]) : kNegInf;
+          s[j] = (j < L && !((dm >> j) & 1ull)) ? fmaf(scale, s[j], brow[j < L ? j : 0]) : kNegInf;
           r[j] = r[j] - qsub + nl[64 * w2 + j];
           mx = fmaxf(mx, fmaxf(s[j], r[j]));
         }
