@@ -321,3 +321,30 @@ def test_backward_restatements_match_reference_output(name):
         y = y[:, :shape[0]]
     err = float((y.double() - a['y'].double()).norm() / a['y'].double().norm())
     assert err < 2e-5, (name, err)
+
+
+def test_rfa_cabi_rejects_bad_geometry_without_touching_the_gpu():
+    """The ABI v4 entry points validate before they enqueue anything (errno-style codes, message in eva_last_error)."""
+    lib = _abi.load()
+    sz = ctypes.c_size_t(0)
+    g = _abi.RfaGeometry(2, 3, 196, 64, _abi.RFA_METHOD['favorp'], 64, 1, 0, 0, _abi.EVA_F16)
+    assert lib.rfa_feature_dim(ctypes.byref(g)) == 64
+    assert lib.rfa_forward_workspace_bytes(ctypes.byref(g), ctypes.byref(sz)) == 0 and sz.value % 256 == 0 and sz.value > 0
+    g = _abi.RfaGeometry(2, 3, 196, 64, _abi.RFA_METHOD['fourier'], 24, 1, 0, 1, _abi.EVA_F32)      # cosFormer doubles 2 x 24
+    assert lib.rfa_feature_dim(ctypes.byref(g)) == 96
+    g = _abi.RfaGeometry(2, 3, 196, 60, _abi.RFA_METHOD['favorp'], 64, 1, 0, 0, _abi.EVA_F16)       # head_dim % 8
+    assert lib.rfa_feature_dim(ctypes.byref(g)) == -95
+    g = _abi.RfaGeometry(2, 3, 196, 64, 42, 64, 1, 0, 0, _abi.EVA_F16)                             # unknown feature map
+    assert lib.rfa_feature_dim(ctypes.byref(g)) == -22 and b'method' in lib.eva_last_error()
+    g = _abi.RfaGeometry(2, 3, 196, 128, _abi.RFA_METHOD['dpfp'], 0, 2, 0, 1, _abi.EVA_F16)         # 2 * 128 * 2 * 2 features
+    assert lib.rfa_feature_dim(ctypes.byref(g)) == -95
+    sg = _abi.SbGeometry(2, 3, 196, 64, 2, 14, 14, 5, 64, _abi.EVA_F16)                            # 14 % 5
+    assert lib.scatterbrain_forward_workspace_bytes(ctypes.byref(sg), ctypes.byref(sz)) == -22
+    sg = _abi.SbGeometry(2, 3, 1024, 64, 1, 1, 1024, 128, 64, _abi.EVA_F16)                        # windows of 128 tokens
+    assert lib.scatterbrain_forward_workspace_bytes(ctypes.byref(sg), ctypes.byref(sz)) == -95
+    sg = _abi.SbGeometry(2, 3, 196, 64, 2, 14, 14, 7, 64, _abi.EVA_F16)
+    assert lib.scatterbrain_forward_workspace_bytes(ctypes.byref(sg), ctypes.byref(sz)) == 0 and sz.value > 0
+    rg = _abi.RaGeometry(2, 3, 196, 64, 1, _abi.EVA_F16)
+    assert lib.ra_forward_workspace_bytes(ctypes.byref(rg), ctypes.byref(sz)) == 0 and sz.value >= 2 * 3 * 64 * 4
+    rg = _abi.RaGeometry(2, 3, 196, 64, 7, _abi.EVA_F16)                                           # unknown mode: no pointers are read
+    assert lib.ra_forward(ctypes.byref(rg), None, None, None, None, None, None, None, None, 0, None) == -22
