@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'libeva_sm100.so')
-SOURCES = ['abi.cu', 'eva_generic.cu', 'eva_backward.cu', 'eva_window_tc_sm100.cu', 'eva_bwd_sm100.cu', 'eva_window_bwd_gen_sm100.cu', 'lara_generic.cu', 'lara_backward.cu', 'rfa_kernels.cu', 'rfa_tc_sm100.cu', 'sb_window_tc_sm100.cu', 'eva_fused_sm100.cu', 'eva_cluster_sm100.cu', 'eva_causal_sm100.cu', 'lara_core_sm100.cu']
+SOURCES = ['abi.cu', 'eva_generic.cu', 'eva_backward.cu', 'eva_window_tc_sm100.cu', 'eva_bwd_sm100.cu', 'eva_window_bwd_gen_sm100.cu', 'lara_generic.cu', 'lara_backward.cu', 'rfa_kernels.cu', 'rfa_tc_sm100.cu', 'sb_window_tc_sm100.cu', 'ra_sample_tc_sm100.cu', 'eva_fused_sm100.cu', 'eva_cluster_sm100.cu', 'eva_causal_sm100.cu', 'lara_core_sm100.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '--use_fast_math=false', '-Xptxas', '-v']
 

@@ -92,6 +92,11 @@ cudaError_t launch_sb_window_tc(int B, int H, int N, int dims, int gh, int gw, i
                                 const View& k, const View& v, const uint8_t* mask, const float* proj, const float* bias,
                                 const float* stabv, const float* part, void* out, cudaStream_t st);
 
+// Key draw of randomized attention by Gumbel-max on tcgen05 (ra_sample_tc_sm100.cu): head_dim 64, 16-bit I/O
+bool ra_sample_tc_supported(int D, int io_dtype, const View& q, const View& k);
+cudaError_t launch_ra_sample_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, unsigned long long seed,
+                                const float* gumbel, long long* k_ind, cudaStream_t st);
+
 // LARA (lara_generic.cu)
 struct LaraGeo {
   int B, H, N, D;

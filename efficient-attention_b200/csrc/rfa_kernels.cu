@@ -885,6 +885,21 @@ static bool ra_uses_tensor_cores(const RaGeometry* g) {
   return eva::window_tc_supported(geo, g->io_dtype);
 }
 
+int ra_sample(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, uint64_t seed, const float* gumbel, int64_t* k_ind,
+              void* stream) {
+  if (!g) return eva::abi_fail(EVA_ERR_INVALID, "geometry is NULL");
+  if (g->batch <= 0 || g->heads <= 0 || g->tokens <= 0) return eva::abi_fail(EVA_ERR_INVALID, "batch / heads / tokens must be positive");
+  eva::View vq, vk;
+  int rc;
+  if ((rc = eva::abi_view(q, "q", &vq)) || (rc = eva::abi_view(k, "k", &vk))) return rc;
+  if (!k_ind) return eva::abi_fail(EVA_ERR_INVALID, "k_ind is NULL");
+  if (!eva::ra_sample_tc_supported(g->head_dim, g->io_dtype, vq, vk))
+    return eva::abi_fail(EVA_ERR_UNSUPPORTED, "ra_sample: head_dim 64 with 16-bit q / k only (draw with library ops otherwise)");
+  const cudaError_t e = eva::launch_ra_sample_tc(g->batch, g->heads, g->tokens, g->io_dtype, vq, vk, seed, gumbel,
+                                                 reinterpret_cast<long long*>(k_ind), reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? EVA_OK : eva::abi_cuda_fail(e, "ra_sample");
+}
+
 int ra_forward_workspace_bytes(const RaGeometry* g, size_t* bytes) {
   if (!g || !bytes) return eva::abi_fail(EVA_ERR_INVALID, "geometry / bytes is NULL");
   size_t n = ((size_t)g->batch * g->heads * g->head_dim * 4 + 255) & ~(size_t)255;                 /* mean of k */

@@ -104,8 +104,9 @@ def load():
         lib.scatterbrain_forward.argtypes = [SG, V, V, V, P, P, P, P, P, SZ, P]
         lib.ra_forward.argtypes = [AG, V, V, V, P, P, P, P, P, SZ, P]
         lib.ra_forward_workspace_bytes.argtypes = [AG, ctypes.POINTER(SZ)]
+        lib.ra_sample.argtypes = [AG, V, V, ctypes.c_uint64, P, P, P]
         for fn in ('rfa_feature_dim', 'rfa_forward_workspace_bytes', 'rfa_forward', 'scatterbrain_forward_workspace_bytes',
-                   'scatterbrain_forward', 'ra_forward', 'ra_forward_workspace_bytes'):
+                   'scatterbrain_forward', 'ra_forward', 'ra_forward_workspace_bytes', 'ra_sample'):
             getattr(lib, fn).restype = ctypes.c_int
         for fn in ('eva_num_chunks', 'eva_chunk_stats', 'eva_window_attention', 'eva_forward_workspace_bytes',
                    'eva_forward', 'eva_backward', 'eva_window_attention_lse', 'lara_backward_step', 'lara_forward_workspace_bytes', 'lara_forward', 'lara_forward_given_landmarks'):
@@ -459,3 +460,23 @@ def ra_forward(q, k, v, *, mode, extra=None, k_ind=None, noise=None):
                             _ptr(extra), _ptr(k_ind), _ptr(noise), _ptr(out), _ptr(ws), ws.numel(), _stream(q.device))
     _check(rc, 'ra_forward')
     return out
+
+
+def ra_sample_supported(q):
+    return q.shape[-1] == 64 and q.dtype in (torch.float16, torch.bfloat16)
+
+
+def ra_sample(q, k, *, seed=0, gumbel=None):
+    """One key index per query drawn from softmax(scale q k^T) by Gumbel-max (`ra_sample` in include/eva_sm100.h): int64 [B, H, N].
+    `gumbel`: explicit float32 [B, H, N, N] noise instead of the seeded hash (tests)."""
+    lib = load()
+    _require_cuda(q, k, gumbel)
+    B, N, H, D = q.shape
+    geom = RaGeometry(B, H, N, D, 2, io_dtype(q))
+    gumbel = _f32(gumbel)
+    k_ind = torch.empty(B, H, N, dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = lib.ra_sample(ctypes.byref(geom), ctypes.byref(heads_view(q)), ctypes.byref(heads_view(k)), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                           _ptr(gumbel), _ptr(k_ind), _stream(q.device))
+    _check(rc, 'ra_sample')
+    return k_ind

@@ -3,8 +3,10 @@
 out_n = softmax_m(scale w_n . k_m - scale |k_m|^2 / 2) v_m with w_n = mu_n (+ Gaussian noise in training mode) and
 mu_n = q_n + mean(k) (num_samples == 0) | q_n + E_pi[k] (num_samples == -1) | q_n + k[one index drawn from pi_n] (otherwise),
 pi = softmax(scale q k^T).  The softmax-over-keys pass with the key-norm bias is `ra_forward` (csrc/rfa_kernels.cu); E_pi[k] is the
-dense-softmax kernel of this library with v := k.  The draw from pi needs the [N, N] probabilities, exactly as in the reference; they
-are evaluated by library ops (`torch.multinomial` is the sampler there too).  The padding mask is ignored, as in the reference.
+dense-softmax kernel of this library with v := k.  The draw from pi: for head_dim 64 / 16-bit activations `ra_sample` draws it by
+Gumbel-max on tensor cores (argmax_m of scale q.k + Gumbel noise is distributed as pi: no [N, N] probabilities); otherwise the
+probabilities are evaluated by library ops and `torch.multinomial` draws, as in the reference.  The padding mask is ignored, as in the
+reference.
 """
 import torch
 
@@ -49,8 +51,13 @@ class RandomizedAttention(MultiheadAttention):
             mode, extra = 'gather', None
             if k_ind is None:
                 with torch.no_grad():   # reference :38-40: one key per query whatever num_samples says
-                    pi = torch.softmax(self.scale * torch.einsum('bnhd,bmhd->bhnm', q.float(), k.float()), dim=-1)
-                    k_ind = torch.multinomial(pi.reshape(B * H * N, N), 1, replacement=True).reshape(B, H, N)
+                    if _abi.ra_sample_supported(q):
+                        # Gumbel-max on tensor cores: the same distribution without the [N, N] probabilities; the seed comes from
+                        # PyTorch's CPU generator (torch.manual_seed governs it, no device synchronisation)
+                        k_ind = _abi.ra_sample(q, k, seed=int(torch.randint(0, 2 ** 62, (1,)).item()))
+                    else:
+                        pi = torch.softmax(self.scale * torch.einsum('bnhd,bmhd->bhnm', q.float(), k.float()), dim=-1)
+                        k_ind = torch.multinomial(pi.reshape(B * H * N, N), 1, replacement=True).reshape(B, H, N)
         if self.training and noise is None and self._draw_override is None:
             noise = torch.randn(B, H, N, D, device=q.device, dtype=torch.float32)
         scale = self.scale

@@ -265,6 +265,13 @@ typedef struct RaGeometry {
   int32_t io_dtype;
 } RaGeometry;
 int ra_forward_workspace_bytes(const RaGeometry* g, size_t* bytes);
+/* The draw of mode 2 (randomized_attention.py:36-40: one key index per query from pi_n = softmax_m(scale q_n . k_m), torch.multinomial
+ * in the reference) without the [tokens, tokens] probabilities: k_ind[b, h, n] = argmax_m (scale q_n . k_m + G_nm), G i.i.d. standard
+ * Gumbel (the Gumbel-max trick draws exactly from pi_n).  G comes from a counter-based hash of (seed, b, h, n, m), or from `gumbel`,
+ * float32 [batch, heads, tokens, tokens], when that is not NULL (tests).  head_dim 64 and 16-bit q / k only: EVA_ERR_UNSUPPORTED
+ * otherwise (the caller then draws with library ops, as the reference does).  g->mode is ignored. */
+int ra_sample(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, uint64_t seed, const float* gumbel, int64_t* k_ind,
+              void* stream);
 int ra_forward(const RaGeometry* g, const EvaHeadsView* q, const EvaHeadsView* k, const EvaHeadsView* v, const void* extra,
                const int64_t* k_ind, const float* noise, void* out, void* workspace, size_t workspace_bytes, void* stream);
 

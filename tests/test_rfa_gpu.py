@@ -217,6 +217,46 @@ def test_module_gradients_match_autograd_through_the_oracle(name):
         assert rel_l2(p.grad.cpu(), ref_g) < 5e-4, (name, pname)
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('B,N', [(2, 203), (40, 384)])
+def test_ra_sample_gumbel_max_vs_oracle(dtype, B, N):
+    """`ra_sample` with EXPLICIT Gumbel noise: k_ind[n] = argmax_m (scale q_n . k_m + G_nm) against the float64 evaluation on the same
+    rounded q / k.  Index work: exact, except where the two best candidates of a row are closer than the 16-bit MMA can resolve."""
+    from efficient_attention import _abi
+    H, D = 3, 64
+    (q, k, _), (qr, kr, _) = _qkv(B, N, H, D, dtype, 31)
+    u = torch.rand(B, H, N, N, generator=torch.Generator().manual_seed(9)).clamp(1e-7, 1 - 1e-7)
+    gum = -torch.log(-torch.log(u))
+    got = _abi.ra_sample(q, k, gumbel=gum.to(_dev())).cpu()
+    val = D ** -0.5 * (qr @ kr.transpose(-1, -2)) + gum.double()
+    want = val.argmax(-1)
+    assert got.shape == want.shape and int(got.min()) >= 0 and int(got.max()) < N
+    same = got == want
+    assert float(same.float().mean()) > 0.999, float(same.float().mean())
+    gap = val.max(-1).values - torch.gather(val, -1, got.unsqueeze(-1)).squeeze(-1)       # 0 where equal
+    assert float(gap.max()) < (2e-2 if dtype == torch.float16 else 1e-1), float(gap.max())
+
+
+def test_ra_sample_follows_pi():
+    """The seeded draw: with every query equal (one row of pi, 24 keys) the empirical frequencies over 6144 x 8 independent draws
+    match pi (total variation < 0.02; the expected TV of that many multinomial draws is ~0.01)."""
+    from efficient_attention import _abi
+    B, N, H, D = 8, 24, 1, 64
+    g = torch.Generator().manual_seed(3)
+    q1, k1 = 2.0 * torch.randn(D, generator=g), 1.5 * torch.randn(N, D, generator=g)
+    reps = 256
+    q = q1.view(1, 1, 1, D).expand(B, N, H, D).half().contiguous().to(_dev())
+    k = k1.view(1, N, 1, D).expand(B, N, H, D).half().contiguous().to(_dev())
+    pi = torch.softmax(D ** -0.5 * (q1.half().double() @ k1.half().double().t()), -1)
+    counts = torch.zeros(N, dtype=torch.float64)
+    for rep in range(reps):
+        idx = _abi.ra_sample(q, k, seed=1000 + rep).cpu().reshape(-1)
+        counts += torch.bincount(idx, minlength=N).double()
+    freq = counts / counts.sum()
+    tv = 0.5 * float((freq - pi).abs().sum())
+    assert tv < 0.02, (tv, freq, pi)
+
+
 def test_ra_default_sampling_draws_from_pi():
     """num_samples = 1 in eval mode without the test hook: the module draws one key per query from pi = softmax(scale q k^T)
     (library ops, as the reference's torch.multinomial).  With a peaked pi the draw is (almost surely) the arg-max key."""

@@ -21,6 +21,7 @@ SPECS = {
     'performer': dict(BASE, approx_attn_dim=64, proj_method='favorp'),
     'scatterbrain': dict(BASE, approx_attn_dim=64, window_size=7, attn_2d=True, use_rpe=True),
     'ra': dict(BASE, num_samples=-1),
+    'ra_sample': dict(BASE, num_samples=1),          # the registry default: one key drawn from pi per query (torch.multinomial)
 }
 
 
@@ -38,8 +39,8 @@ def arm(which, B):
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             torch.manual_seed(0)
-            layer = bench.lively_init(ea.AttentionFactory.build_attention(name, dict(spec))).to(dev).eval()
-        bb = B if name != 'ra' else min(B, 128)
+            layer = bench.lively_init(ea.AttentionFactory.build_attention(name.split('_')[0], dict(spec))).to(dev).eval()
+        bb = B if not name.startswith('ra') else min(B, 128)
         x = torch.randn(bb, 28, 28, 192, device=dev)
 
         def fwd():
@@ -50,7 +51,7 @@ def arm(which, B):
             out[name] = {'batch': bb, 'layer_fwd_ms': round(ms, 4), 'tokens_per_s': bb * 784 / (ms * 1e-3)}
         except RuntimeError as e:
             out[name] = {'batch': bb, 'failed': str(e)[:100]}
-        if which == 'ours':
+        if which == 'ours' and name != 'ra_sample':
             from efficient_attention import _abi
             xh = x.half()
             lh = layer.half()
