@@ -348,3 +348,12 @@ def test_rfa_cabi_rejects_bad_geometry_without_touching_the_gpu():
     assert lib.ra_forward_workspace_bytes(ctypes.byref(rg), ctypes.byref(sz)) == 0 and sz.value >= 2 * 3 * 64 * 4
     rg = _abi.RaGeometry(2, 3, 196, 64, 7, _abi.EVA_F16)                                           # unknown mode: no pointers are read
     assert lib.ra_forward(ctypes.byref(rg), None, None, None, None, None, None, None, None, 0, None) == -22
+
+
+def test_graft_entry_build_runs_here():
+    """The driver's "does it build" check: build() compiles (or finds up to date) the library, imports the package and loads it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('graft_entry_under_test', os.path.join(ROOT, '__graft_entry__.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
