@@ -3,8 +3,8 @@
 // Everything else (other feature maps / widths, float32 I/O, cosFormer re-weighting) stays on the CUDA-core kernels of
 // rfa_kernels.cu.
 //
-// One (batch, head) item per CTA iteration, 128 threads (thread t <-> TMEM lane t <-> token t of the 128-token tile), two or more
-// CTAs per SM (80 KB of tiles, 256 TMEM columns).  Per item, with W' = d^-1/4 W in 16 bits ([features][d], K-major):
+// One (batch, head) item per CTA iteration, 256 threads (TMEM lane = token of the 128-token tile; warps w and w + 4 share a lane
+// quarter and split the 64 feature columns of every epilogue), two CTAs per SM (100 KB of tiles, 256 TMEM columns).  Per item, with W' = d^-1/4 W in 16 bits ([features][d], K-major):
 //   pass 1   per key tile:    DD = K W'^T (M = 128 tokens, N = 64 features)        -> running max = the key stabiliser
 //   pass 2   per key tile:    DD again; thread-local phi(k) = m^-1/2 exp(DD - |k|^2 d^-1/2 / 2 - stab) + 1e-4 (0 for padding)
 //                             -> 16-bit tile F [tokens][features];  KV (+)= F^T V  (A and B both MN-major, M = 64 features),
@@ -12,7 +12,9 @@
 //            KV -> 16-bit tile [features][d], KS column 0 -> ksum (float32)
 //   phase Q  per query tile:  DD = Q W'^T; phi(q) with the row's own max; den = phi(q) . ksum (float32, thread-local);
 //                             O = F KV (B MN-major) -> / max(den, 1e-2) -> 128-byte row stores
-// Loads are plain 16-byte global loads (8 lanes per 128-byte row) written with the 128-byte swizzle the UMMA descriptors expect.
+// Loads: cp.async, 16 bytes per lane (8 lanes per 128-byte row), into 128-byte-swizzled tiles, two buffers: the tiles of an item form
+// a list of stages (pass 1 | pass 2 | queries) and the successor stage -- also across items -- is requested before the current one is
+// consumed.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -69,15 +71,6 @@ __device__ __forceinline__ float row_sq(const uint8_t* tile, int row) {
     for (int u = 0; u < 4; ++u) { const float2 f = Pair16<T>::up(w4[u]); s = fmaf(f.x, f.x, fmaf(f.y, f.y, s)); }
   }
   return s;
-}
-
-template <typename T>
-__device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float (&f)[64]) {
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch)
-    *reinterpret_cast<uint4*>(tile + row * 128 + ((ch ^ (row & 7)) << 4)) =
-        make_uint4(Pair16<T>::pk(f[8 * ch], f[8 * ch + 1]), Pair16<T>::pk(f[8 * ch + 2], f[8 * ch + 3]),
-                   Pair16<T>::pk(f[8 * ch + 4], f[8 * ch + 5]), Pair16<T>::pk(f[8 * ch + 6], f[8 * ch + 7]));
 }
 
 // features [32 hf, 32 hf + 32) of a row -> chunks 4 hf .. 4 hf + 3 of the swizzled 16-bit tile
