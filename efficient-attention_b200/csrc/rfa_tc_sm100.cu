@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
         const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + (kLogF ? hlm : stab);
+        const float live = dead ? 0.f : 1.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if constexpr (kLogF) f[j] = dead ? 0.f : __expf(f[j] - sub - mxs[32 * hf + j]);
-          else f[j] = dead ? 0.f : fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+        for (int j = 0; j < 32; ++j) {              // branch-free (a select around every exponential compiles to a divergence region)
+          if constexpr (kLogF) f[j] = live * __expf(fminf(f[j] - sub - mxs[32 * hf + j], 0.f));   // live rows: <= 0 by the definition of mxs
+          else f[j] = live * fmaf(ratio, __expf(f[j] - sub), 1e-4f);                              // <= 0 for every row: stab covers them all
         }
         store_half16<T>(sm + kF, r, hf, f);
       }

@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
         const bool dd_ = dead[tid] != 0;
         const unsigned bal = __ballot_sync(0xffffffffu, dd_);
         if (lane == 0) dmask[warp] = bal;
+        const float live = dd_ ? 0.f : 1.f;         // branch-free: a select around every exponential compiled to 64 divergence regions
 #pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = dd_ ? 0.f : __expf(f[j] - sub - mxs[j]);
+        for (int j = 0; j < 64; ++j) f[j] = live * __expf(fminf(f[j] - sub - mxs[j], 0.f));      // (live rows: <= 0 by the definition of mxs)
         store_row16<T>(sm + kPK, tid, f);
       }
       SB_MARK(3)
