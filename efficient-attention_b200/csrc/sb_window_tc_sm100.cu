@@ -27,10 +27,10 @@ namespace sbtc {
 
 using fused::tmem_ld_cols;
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;       // warps w and w + 4 share a TMEM lane quarter and split the columns of every epilogue
 constexpr uint32_t cDD = 0, cLa = 64, cLsa = 128, cLb = 144, cLsb = 208, cS = 64, cP = 64, cO = 192;
 constexpr int kQ = 0, kK = 16384, kV = 32768, kPK = 49152, kKVS = 65536, kW = 81920, kOnes = 90112, kNl = 98304, kMxs = kNl + 512,
-              kDead = kMxs + 256, kTok = kDead + 256, kDmask = kTok + 1024, kBar = kDmask + 16, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
+              kDead = kMxs + 256, kTok = kDead + 256, kDmask = kTok + 1024, kPm = kDmask + 16, kPd = kPm + 1024, kBar = kPd + 1024, kTmemPtr = kBar + 16, kBias = kTmemPtr + 16;     // bias: L * L floats at the end
 
 struct Params {
   int B, H, N, items;
@@ -78,10 +78,22 @@ __device__ __forceinline__ void store_row16(uint8_t* tile, int row, const float 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
+__device__ __forceinline__ void store_half16(uint8_t* tile, int row, int hf, const float (&f)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + row * 128 + (((4 * hf + c) ^ (row & 7)) << 4)) =
+        make_uint4(Pair16<T>::pk(f[8 * c], f[8 * c + 1]), Pair16<T>::pk(f[8 * c + 2], f[8 * c + 3]),
+                   Pair16<T>::pk(f[8 * c + 4], f[8 * c + 5]), Pair16<T>::pk(f[8 * c + 6], f[8 * c + 7]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2) sb_window_tc_kernel(const View q, const View k, const View v, T* __restrict__ out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* const sm = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qr = warp & 3, hf = warp >> 2, r = 32 * qr + lane;     // my TMEM lane quarter, column half, row of the pair's tile
+  float* const pm = reinterpret_cast<float*>(sm + kPm);          // [2][128] partial row maxima of the two column halves
+  float* const pd = reinterpret_cast<float*>(sm + kPd);          // [2][128] partial row sums
   const uint32_t bar = ptx::smem_u32(sm + kBar);
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTmemPtr);
   float* const nl = reinterpret_cast<float*>(sm + kNl);          // [2][64]
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);
+  const uint32_t trow = tmem + ((uint32_t)(32 * qr) << 16);
   const uint64_t dQ = ptx::umma_desc_sw128(ptx::smem_u32(sm + kQ)), dK = ptx::umma_desc_sw128(ptx::smem_u32(sm + kK));
   const uint64_t dV = ptx::umma_desc_sw128(ptx::smem_u32(sm + kV)), dPK = ptx::umma_desc_sw128(ptx::smem_u32(sm + kPK));
   const uint64_t dKVS = ptx::umma_desc_sw128(ptx::smem_u32(sm + kKVS)), dW = ptx::umma_desc_sw128(ptx::smem_u32(sm + kW));
@@ -117,7 +129,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
   auto mma_wait = [&]() { ptx::mbar_wait(bar, phase & 1); ++phase; ptx::tc_fence_after(); };
   auto hand_over = [&]() { ptx::fence_proxy_async_smem(); ptx::tc_fence_before(); __syncthreads(); };
   const int L = p.L, pairs = (p.n_windows + 1) >> 1;
-  const int w2 = tid >> 6, li = tid & 63;                  // my row: window a / b of the pair, slot inside it
+  const int w2 = r >> 6, li = r & 63;                      // my row: window a / b of the pair, slot inside it
   // rows of the two windows of pair `pr_` of item `item_` -> tile `which` (0 q, 1 k, 2 v), cp.async with zero fill where there is no
   // row; the key flags of that pair go to the parity buffer of pair counter `np_`
   auto issue_rows = [&](int item_, int pr_, int which, uint32_t np_) {
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
     const View& x = which == 0 ? q : (which == 1 ? k : v);
     uint8_t* const dst = sm + (which == 0 ? kQ : (which == 1 ? kK : kV));
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < 1024 / kThreads; ++it) {
       const int idx = it * kThreads + tid, row = idx >> 3, ch = idx & 7;
       const int tk_ = tokS[128 * (np_ & 1) + row];                 // (index arithmetic with divisions: once per row and pair)
       const bool ok = tk_ >= 0;
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
       const uint32_t d = ptx::smem_u32(dst + row * 128 + ((ch ^ (row & 7)) << 4));
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
-    if (which == 1) {
+    if (which == 1 && tid < 128) {
       const int tk_ = tokS[128 * (np_ & 1) + tid];
       dead_all[128 * (np_ & 1) + tid] = (tk_ < 0 || (p.mask && p.mask[(long long)b_ * p.N + tk_])) ? 1 : 0;
     }
@@ -159,13 +171,13 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
     const float* part = p.part + (long long)item * (64 * 64 + 64);
     for (int pr = 0; pr < pairs; ++pr, ++np) {
       auto pair_token = [&](int pr_) { const int win_ = 2 * pr_ + w2; return (win_ < p.n_windows && li < L) ? window_token(p, win_, li) : -1; };
-      if (np == 0) { tokS[tid] = pair_token(pr); __syncthreads(); }
+      if (np == 0) { if (hf == 0) tokS[r] = pair_token(pr); __syncthreads(); }
       // successor pair (possibly of the CTA's next item): its row tokens now, its rows under this pair's softmax / output MMA
       int nitem = item, npr = pr + 1;
       if (npr == pairs) { nitem = item + (int)gridDim.x; npr = 0; }
       const bool more = nitem < p.items;
-      tokS[128 * ((np + 1) & 1) + tid] = more ? pair_token(npr) : -1;
-      const int tok = tokS[128 * (np & 1) + tid];
+      if (hf == 0) tokS[128 * ((np + 1) & 1) + r] = more ? pair_token(npr) : -1;
+      const int tok = tokS[128 * (np & 1) + r];
       const bool have_row = tok >= 0;
       uint8_t* const dead = dead_all + 128 * (np & 1);
       SB_MARK(0)
@@ -183,19 +195,21 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
       }
       mma_wait();
       SB_MARK(2)
-      const float qsub = half_dn2 * row_sq<T>(sm + kQ, tid) + hlm;       // (the q tile is handed to the next pair after the S MMA)
-      {   // E1: exp-features of my key row
-        float f[64];
-        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(f));
+      const float qsub = half_dn2 * row_sq<T>(sm + kQ, r) + hlm;         // (the q tile is handed to the next pair after the S MMA)
+      {   // E1: exp-features of my key row, my half of the 64 features
+        float f[32];
+        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
-        const float sub = half_dn2 * row_sq<T>(sm + kK, tid) + hlm;
-        const bool dd_ = dead[tid] != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, dd_);
-        if (lane == 0) dmask[warp] = bal;
-        const float live = dd_ ? 0.f : 1.f;         // branch-free: a select around every exponential compiled to 64 divergence regions
+        const float sub = half_dn2 * row_sq<T>(sm + kK, r) + hlm;
+        const bool dd_ = dead[r] != 0;
+        if (hf == 0) {                              // (warp-uniform)
+          const unsigned bal = __ballot_sync(0xffffffffu, dd_);
+          if (lane == 0) dmask[qr] = bal;
+        }
+        const float live = dd_ ? 0.f : 1.f;         // branch-free: a select around every exponential compiled to a divergence region each
 #pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = live * __expf(fminf(f[j] - sub - mxs[j], 0.f));      // (live rows: <= 0 by the definition of mxs)
-        store_row16<T>(sm + kPK, tid, f);
+        for (int j = 0; j < 32; ++j) f[j] = live * __expf(fminf(f[j] - sub - mxs[32 * hf + j], 0.f));      // (live rows: <= 0 by the definition of mxs)
+        store_half16<T>(sm + kPK, r, hf, f);
       }
       SB_MARK(3)
       hand_over();
@@ -215,30 +229,28 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
       }
       mma_wait();
       SB_MARK(4)
-      {   // E2: thread = feature (lanes < 16 of each warp hold the M = 64 rows; the loads are warp-collective)
-        const int c = 16 * warp + (lane & 15);
+      {   // E2: thread = feature (lanes < 16 of each warp hold the M = 64 rows; the loads are warp-collective); warps 0-3 take
+        const int c = 16 * qr + (lane & 15);        // window a, warps 4-7 window b
+        const int ww = hf;
         const float gsum = __ldg(part + 64 * 64 + c);
-#pragma unroll 1
-        for (int ww = 0; ww < 2; ++ww) {
-          float lc[64];
-          uint32_t ls0;
-          tmem_ld_cols<64>(trow + (ww ? cLb : cLa), reinterpret_cast<uint32_t*>(lc));
-          ptx::tmem_ld1(trow + (ww ? cLsb : cLsa), ls0);
-          ptx::tmem_ld_wait();
-          if (lane < 16) {
-            const float ls = __uint_as_float(ls0);
-            const float inv = 1.0f / fmaxf(gsum - ls, 1e-3f);
+        float lc[64];
+        uint32_t ls0;
+        tmem_ld_cols<64>(trow + (ww ? cLb : cLa), reinterpret_cast<uint32_t*>(lc));
+        ptx::tmem_ld1(trow + (ww ? cLsb : cLsa), ls0);
+        ptx::tmem_ld_wait();
+        if (lane < 16) {
+          const float ls = __uint_as_float(ls0);
+          const float inv = 1.0f / fmaxf(gsum - ls, 1e-3f);
 #pragma unroll
-            for (int d4 = 0; d4 < 16; ++d4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(part + c * 64) + d4);
-              lc[4 * d4] = (g4.x - lc[4 * d4]) * inv; lc[4 * d4 + 1] = (g4.y - lc[4 * d4 + 1]) * inv;
-              lc[4 * d4 + 2] = (g4.z - lc[4 * d4 + 2]) * inv; lc[4 * d4 + 3] = (g4.w - lc[4 * d4 + 3]) * inv;
-            }
-            store_row16<T>(sm + kKVS, 64 * ww + c, lc);
-            // log_add_exp(glse, llse, mask = (1, -1)) of attn_utils.py:44-51; both log-sums are relative to the per-feature maximum
-            const float glse = __logf(gsum), llse = __logf(ls), a = fmaxf(glse, llse);
-            nl[64 * ww + c] = mxs[c] + a + __logf(__expf(glse - a) - __expf(llse - a) + 1e-5f);
+          for (int d4 = 0; d4 < 16; ++d4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(part + c * 64) + d4);
+            lc[4 * d4] = (g4.x - lc[4 * d4]) * inv; lc[4 * d4 + 1] = (g4.y - lc[4 * d4 + 1]) * inv;
+            lc[4 * d4 + 2] = (g4.z - lc[4 * d4 + 2]) * inv; lc[4 * d4 + 3] = (g4.w - lc[4 * d4 + 3]) * inv;
           }
+          store_row16<T>(sm + kKVS, 64 * ww + c, lc);
+          // log_add_exp(glse, llse, mask = (1, -1)) of attn_utils.py:44-51; both log-sums are relative to the per-feature maximum
+          const float glse = __logf(gsum), llse = __logf(ls), a = fmaxf(glse, llse);
+          nl[64 * ww + c] = mxs[c] + a + __logf(__expf(glse - a) - __expf(llse - a) + 1e-5f);
         }
       }
       SB_MARK(5)
@@ -253,37 +265,42 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
       if (more) {       // the successor's q and k rows travel under the softmax and the output MMA
         issue_rows(nitem, npr, 0, np + 1); issue_rows(nitem, npr, 1, np + 1); }
       SB_MARK(6)
-      float rsum = 0.f;
-      {   // E3: joint softmax of my query row over [local keys of my window | the 64 feature keys]
-        float s[64], r[64];
-        tmem_ld_cols<64>(trow + cS + 64 * w2, reinterpret_cast<uint32_t*>(s));
-        tmem_ld_cols<64>(trow + cDD, reinterpret_cast<uint32_t*>(r));
+      {   // E3: joint softmax of my query row over [local keys of my window | the 64 feature keys]; my half of either
+        float s[32], rr[32];
+        tmem_ld_cols<32>(trow + cS + 64 * w2 + 32 * hf, reinterpret_cast<uint32_t*>(s));
+        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(rr));
         ptx::tmem_ld_wait();
         const float* brow = biasS + (li < L ? li : 0) * L;
-        const unsigned long long dm = (unsigned long long)dmask[2 * w2] | ((unsigned long long)dmask[2 * w2 + 1] << 32);
+        const unsigned dm = dmask[2 * w2 + hf];     // the dead flags of my 32 local keys
         float mx = kNegInf;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          s[j] = (j < L && !((dm >> j) & 1ull)) ? fmaf(scale, s[j], brow[j < L ? j : 0]) : kNegInf;
-          r[j] = r[j] - qsub + nl[64 * w2 + j];
-          mx = fmaxf(mx, fmaxf(s[j], r[j]));
+        for (int j = 0; j < 32; ++j) {
+          const int jj = 32 * hf + j;
+          s[j] = (jj < L && !((dm >> j) & 1u)) ? fmaf(scale, s[j], brow[jj < L ? jj : 0]) : kNegInf;
+          rr[j] = rr[j] - qsub + nl[64 * w2 + jj];
+          mx = fmaxf(mx, fmaxf(s[j], rr[j]));
         }
-        uint32_t pl[32], pr_[32];
+        pm[128 * hf + r] = mx;
+        __syncthreads();                            // the two column halves of a row meet
+        mx = fmaxf(pm[r], pm[128 + r]);
+        float rsum = 0.f;
+        uint32_t pl[16], pr_[16];
 #pragma unroll
-        for (int j = 0; j < 64; j += 2) {
-          const float e0 = __expf(s[j] - mx), e1 = __expf(s[j + 1] - mx), f0 = __expf(r[j] - mx), f1 = __expf(r[j + 1] - mx);
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = __expf(s[j] - mx), e1 = __expf(s[j + 1] - mx), f0 = __expf(rr[j] - mx), f1 = __expf(rr[j + 1] - mx);
           rsum += (e0 + e1) + (f0 + f1);
           pl[j >> 1] = Pair16<T>::pk(e0, e1);
           pr_[j >> 1] = Pair16<T>::pk(f0, f1);
         }
-        uint32_t zero[32];
+        pd[128 * hf + r] = rsum;
+        uint32_t zero[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) zero[j] = 0u;
-        // P row: 256 16-bit values = 128 columns: [local a | local b | features a | features b], mine in my window's blocks
-        fused::tmem_st_cols<32>(trow + cP + 32 * w2, pl);
-        fused::tmem_st_cols<32>(trow + cP + 32 * (1 - w2), zero);
-        fused::tmem_st_cols<32>(trow + cP + 64 + 32 * w2, pr_);
-        fused::tmem_st_cols<32>(trow + cP + 64 + 32 * (1 - w2), zero);
+        for (int j = 0; j < 16; ++j) zero[j] = 0u;
+        // P row: 256 16-bit values = 128 columns: [local a | local b | features a | features b], mine in my window's blocks, my half
+        fused::tmem_st_cols<16>(trow + cP + 32 * w2 + 16 * hf, pl);
+        fused::tmem_st_cols<16>(trow + cP + 32 * (1 - w2) + 16 * hf, zero);
+        fused::tmem_st_cols<16>(trow + cP + 64 + 32 * w2 + 16 * hf, pr_);
+        fused::tmem_st_cols<16>(trow + cP + 64 + 32 * (1 - w2) + 16 * hf, zero);
         ptx::tmem_st_wait();
       }
       SB_MARK(7)
@@ -301,14 +318,14 @@ __global__ void __launch_bounds__(kThreads) sb_window_tc_kernel(const View q, co
       SB_MARK(8)
       if (more) issue_rows(nitem, npr, 2, np + 1);
       {   // E4
-        float o[64];
-        tmem_ld_cols<64>(trow + cO, reinterpret_cast<uint32_t*>(o));
+        float o[32];
+        tmem_ld_cols<32>(trow + cO + 32 * hf, reinterpret_cast<uint32_t*>(o));
         ptx::tmem_ld_wait();
         if (have_row) {
-          const float inv = 1.0f / rsum;
-          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + tok) * ((long long)p.H * 64) + (long long)h * 64);
+          const float inv = 1.0f / (pd[r] + pd[128 + r]);
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * p.N + tok) * ((long long)p.H * 64) + (long long)h * 64) + 4 * hf;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
+          for (int ch = 0; ch < 4; ++ch)
             dst[ch] = make_uint4(Pair16<T>::pk(o[8 * ch] * inv, o[8 * ch + 1] * inv), Pair16<T>::pk(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv),
                                  Pair16<T>::pk(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv), Pair16<T>::pk(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv));
         }
