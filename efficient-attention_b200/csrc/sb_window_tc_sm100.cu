@@ -1,8 +1,9 @@
 // ScatterBrain window stage on tcgen05 / TMEM for sm_100a (scatterbrain_attention.py:95-160): 'favorp' log-features, 64 random
 // features, head_dim 64, 16-bit I/O, halo-free windows of at most 64 tokens.  The SIMT kernel of rfa_kernels.cu keeps everything else.
 //
-// One PAIR of windows of one (batch, head) item per iteration, 256 threads (TMEM lane = row; warps w and w + 4 share a lane quarter and split the columns; rows 0-63 window a, 64-127
-// window b), with W' = d^-1/4 W in 16 bits and the item's global statistics G = sum_n phi(k_n) v_n, gs = sum_n phi(k_n), mx (per
+// One PAIR of windows of one (batch, head) item per iteration, 256 threads (TMEM lane = row of the pair's tile: rows 0-63 window a,
+// 64-127 window b; warps w and w + 4 share a lane quarter and split the columns of every epilogue), with W' = d^-1/4 W in 16 bits
+// and the item's global statistics G = sum_n phi(k_n) v_n, gs = sum_n phi(k_n), mx (per
 // feature; rfa_favorp_tc_kernel<kLogF>) in global memory:
 //   M1  DDk = [Ka ; Kb] W'^T                      E1  PK = exp(DDk - |k|^2 term - log(m)/2 - mx)  (0 for padding)      -> 16-bit tile
 //   M2  Lc_w = PK_w^T V_w, ls_w = PK_w^T 1 (w = a, b; M = 64 features), R = [Qa ; Qb] W'^T
