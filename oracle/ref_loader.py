@@ -61,6 +61,11 @@ def deit_args(attn_name='eva', num_classes=1000, input_size=224, **attn_kw):
     elif attn_name == 'lara':
         spec = dict(num_landmarks=49, kernel_size=None, proposal_gen='pool-mixed', use_antithetics=False, use_multisample=False,
                     pool_module_type='light', mis_type='mis-opt', alpha_coeff=2.0, fp32=False)
+    elif attn_name == 'performer':     # the defaults of kernelized_attention.py:322-330
+        spec = dict(fp32=False, approx_attn_dim=64, proj_method='favorp', cos_weighting=False, sample_scheme='default')
+    elif attn_name == 'scatterbrain':  # scatterbrain_attention.py:166-180 with the window flags of the DeiT + EVA command
+        spec = dict(fp32=False, use_rpe=True, window_size=7, attn_2d=True, overlap_window=False, approx_attn_dim=64,
+                    proj_method='favorp', cos_weighting=False, sample_scheme='default')
     else:
         spec = dict(fp32=False)
     spec.update(attn_kw)

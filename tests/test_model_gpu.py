@@ -20,6 +20,7 @@ from torch import nn
 
 from conftest import rel_l2
 from oracle import eva_oracle as O
+from oracle import rfa_oracle as R
 from oracle import ref_loader
 
 pytestmark = [pytest.mark.gpu,
@@ -59,6 +60,12 @@ class _OracleAttn(nn.Module):
         if kind == 'eva':
             self.cfg = dict(num_heads=mod.num_heads, window_size=mod.window_size, attn_2d=True, overlap_window=False,
                             adaptive_proj=mod.adaptive_proj, num_landmarks=mod.num_landmarks, use_rpe=mod.use_rpe, use_t5_rpe=False)
+        elif kind == 'performer':
+            self.cfg = dict(num_heads=mod.num_heads, proj_method=mod.proj_method, approx_attn_dim=mod.approx_attn_dim,
+                            cos_weighting=mod.cos_weighting)
+        elif kind == 'scatterbrain':
+            self.cfg = dict(num_heads=mod.num_heads, window_size=mod.window_size, attn_2d=mod.attn_2d, overlap_window=False,
+                            use_rpe=mod.use_rpe)
         else:
             self.cfg = dict(num_heads=mod.num_heads, num_landmarks=mod.num_landmarks, proposal_gen=mod.proposal_gen,
                             mis_type=mod.mis_type, alpha_coeff=mod.alpha_coeff)
@@ -66,6 +73,10 @@ class _OracleAttn(nn.Module):
     def forward(self, x):
         if self.kind == 'eva':
             return O.eva_forward(self.sd, self.cfg, x)
+        if self.kind == 'performer':
+            return R.performer_forward(self.sd, self.cfg, x)
+        if self.kind == 'scatterbrain':
+            return R.scatterbrain_forward(self.sd, self.cfg, x)
         return O.lara_forward(self.sd, self.cfg, x)
 
 
@@ -85,7 +96,8 @@ def _path_count(path):
 
 
 @pytest.mark.parametrize('name,attn,fast_paths', [('evit_tiny_p8', 'eva', (1, 3)), ('evit_tiny_p16', 'eva', (1, 3)),
-                                                  ('evit_small_p16', 'lara', None)])
+                                                  ('evit_small_p16', 'lara', None), ('evit_tiny_p16', 'performer', None),
+                                                  ('evit_tiny_p8', 'scatterbrain', None)])
 def test_reference_vit_with_dropin_attention_matches_oracle(name, attn, fast_paths):
     model = _build(name, attn)
     torch.manual_seed(2)
@@ -105,6 +117,11 @@ def test_reference_vit_with_dropin_attention_matches_oracle(name, attn, fast_pat
         after = [_path_count(p) for p in range(4)]
         err16 = rel_l2(got16, want16)
     assert err32 < 1e-4, (name, err32)
+    if attn in ('performer', 'scatterbrain'):          # the tcgen05 random-feature kernels took the fp16 layers
+        from efficient_attention import _abi
+        assert _abi.rfa_tc_launches() >= len(model.blocks)
+        if attn == 'scatterbrain':
+            assert _abi.load().eva_debug_sb_tc_launches() >= len(model.blocks)
     if fast_paths is not None:     # every layer must have taken a tcgen05 path, none the CUDA-core kernels
         assert after[0] == before[0] and sum(after[p] - before[p] for p in fast_paths) == len(model.blocks), (before, after)
     assert not torch.isnan(got16).any()
