@@ -48,13 +48,15 @@ class DeterministicLearnableFourierFeatures(nn.Module):
 
 
 def features_torch(x, method, is_query, proj=None, nu=1):
-    """Differentiable float32 restatement of the feature maps (reference :12-113) on [B, N, H, d] -> [B, H, N, M]."""
-    x = x.float().transpose(1, 2)
+    """Differentiable restatement of the feature maps (reference :12-113) on [B, N, H, d] -> [B, H, N, M], float32 except the
+    projection einsum, which runs in the activations' 16-bit format when there is one (as the reference does under autocast)."""
+    x = x.transpose(1, 2)
     d = x.shape[-1]
     dn = d ** -0.25
     if method in ('favorp', 'relu', 'fourier'):
         m = proj.shape[1]
-        dd = torch.einsum('bhnd,hjd->bhnj', dn * x, proj.float())
+        dd = torch.einsum('bhnd,hjd->bhnj', dn * x, proj.to(x.dtype)).float()
+        x = x.float()
         half_sq = 0.5 * dn * dn * (x * x).sum(-1, keepdim=True)
         if method == 'favorp':
             stab = (dd.amax(-1, keepdim=True) if is_query else dd.amax((-1, -2), keepdim=True)).detach()
@@ -63,6 +65,7 @@ def features_torch(x, method, is_query, proj=None, nu=1):
             return torch.relu(m ** -0.5 * dd) + 1e-3
         h = torch.exp(half_sq - half_sq.amax(-2, keepdim=True).detach())
         return h * (m ** -0.5) * torch.cat([torch.sin(dd), torch.cos(dd)], -1)
+    x = x.float()
     if method == 'dpfp':
         x2 = torch.cat([torch.relu(x), torch.relu(-x)], -1)
         return torch.cat([x2] * nu, -1) * torch.cat([x2.roll(shifts=j, dims=-1) for j in range(1, nu + 1)], -1)

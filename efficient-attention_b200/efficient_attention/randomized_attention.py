@@ -17,12 +17,15 @@ from .kernelized_attention import recompute_fn
 
 def ra_core_torch(q, k, v, extra, noise, scale):
     """float32 restatement on [B, N, H, d] views (what the backward differentiates).  extra: [B, N, H, d] or [1, 1, H, d]."""
-    q, k, v = (t.float().transpose(1, 2) for t in (q, k, v))
-    w = q + extra.float().transpose(1, 2)
+    lowp = q.dtype if q.dtype != torch.float32 else None      # 16-bit activations: the two [N, N] contractions run in that format
+    q, k, v = (t.transpose(1, 2) for t in (q, k, v))
+    w = q.float() + extra.float().transpose(1, 2)
     if noise is not None:
         w = w + noise
-    logits = scale * (w @ k.transpose(-1, -2)) - 0.5 * scale * (k * k).sum(-1).unsqueeze(-2)
-    o = torch.softmax(logits, -1) @ v
+    mm = (lambda a, b: (a.to(lowp) @ b.to(lowp)).float()) if lowp is not None else (lambda a, b: a.float() @ b.float())
+    kf = k.float()
+    logits = scale * mm(w, k.transpose(-1, -2)) - 0.5 * scale * (kf * kf).sum(-1).unsqueeze(-2)
+    o = mm(torch.softmax(logits, -1), v)
     return o.transpose(1, 2).reshape(o.shape[0], o.shape[2], -1)
 
 

@@ -22,14 +22,15 @@ def scatterbrain_core_torch(q, k, v, proj, *, seq_shape, window, pad_mask, bias)
     """float32 restatement on [B, N, H, d] views (halo-free windows); what the backward differentiates."""
     from ._recompute import _groups_1d, _groups_2d, _take
     B, N, H, d = q.shape
-    q, k, v = q.float(), k.float(), v.float()
-    proj = proj.float()
+    lowp = q.dtype if q.dtype != torch.float32 else None      # 16-bit activations: the big contractions run in that format
     m = proj.shape[1]
     dn = d ** -0.25
 
     def logf(x):
-        return (torch.einsum('bnhd,hjd->bnhj', dn * x, proj) - 0.5 * dn * dn * (x * x).sum(-1, keepdim=True) - 0.5 * math.log(m))
+        dd = torch.einsum('bnhd,hjd->bnhj', dn * x, proj.to(x.dtype)).float()
+        return dd - 0.5 * dn * dn * (x.float() * x.float()).sum(-1, keepdim=True) - 0.5 * math.log(m)
     lq, lk = logf(q), logf(k)
+    mm = (lambda a, b: (a.to(lowp) @ b.to(lowp)).float()) if lowp is not None else (lambda a, b: a @ b)
     if pad_mask is not None:
         lk = lk.masked_fill(pad_mask.to(torch.bool).view(B, N, 1, 1), float('-inf'))
     idx = _groups_2d(seq_shape[0], seq_shape[1], window, 0, q.device) if len(seq_shape) == 2 else _groups_1d(N, window, 0, 0, q.device)
@@ -40,21 +41,21 @@ def scatterbrain_core_torch(q, k, v, proj, *, seq_shape, window, pad_mask, bias)
     mx = lk.amax(1).detach()                                                     # [B, H, m]
     pk = torch.exp(lk - mx.unsqueeze(1))                                         # [B, N, H, m]
     wpk = torch.exp(wlk - mx.view(B, H, 1, 1, m))
-    num = torch.einsum('bnhm,bnhd->bhmd', pk, v).unsqueeze(2) - wpk.transpose(-1, -2) @ wv
+    num = mm(pk.permute(0, 2, 3, 1), v.permute(0, 2, 1, 3)).unsqueeze(2) - mm(wpk.transpose(-1, -2), wv)
     den = pk.sum(1).unsqueeze(2) - wpk.sum(-2)                                   # [B, H, G, m]
     kv_stats = num / den.unsqueeze(-1).clamp(min=1e-3)
     glse = torch.logsumexp(lk, 1).unsqueeze(2)
     llse = torch.logsumexp(wlk, -2)
     a = torch.maximum(glse, llse)
     nonlocal_lse = a + torch.log(torch.exp(glse - a) - torch.exp(llse - a) + 1e-5)
-    s = d ** -0.5 * (wq @ wk.transpose(-1, -2))
+    s = d ** -0.5 * mm(wq, wk.transpose(-1, -2))
     if bias is not None:
         s = s + bias.float().view(1, H, 1, L, L)
     if pad_mask is not None:
         wmask = pad_mask.to(torch.bool).index_select(1, flat).view(B, 1, G, 1, L)
         s = s.masked_fill(wmask, float('-inf'))
     p = torch.softmax(torch.cat([s, wlq + nonlocal_lse.unsqueeze(-2)], -1), -1)
-    o_w = p[..., :L] @ wv + p[..., L:] @ kv_stats                                 # [B, H, G, L, d]
+    o_w = mm(p[..., :L], wv) + mm(p[..., L:], kv_stats)                            # [B, H, G, L, d]
     o = torch.zeros(B, N, H, d, dtype=torch.float32, device=q.device)
     o = o.index_copy(1, flat, o_w.permute(0, 2, 3, 1, 4).reshape(B, G * L, H, d))
     return o.reshape(B, N, H * d)

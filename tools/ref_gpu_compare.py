@@ -86,10 +86,13 @@ def arm(which, attn='eva'):
         elif attn == 'softmax':                   # the dense baseline of the reference's ViT (abstract_attention.py), N = 784
             layer = None
             model = vm.evit_tiny_p8(ref_loader.deit_args('softmax')).to(dev)
+        elif attn in ('performer', 'scatterbrain', 'ra'):   # the random-feature baselines of the registry in DeiT-tiny-p8
+            layer = None
+            model = vm.evit_tiny_p8(ref_loader.deit_args(attn)).to(dev)
         else:                                     # LARA: BASELINE config c4 = DeiT-small-p16 (196 tokens, 384 channels, 6 heads)
             layer = None
             model = vm.evit_small_p16(ref_loader.deit_args('lara')).to(dev)
-        out['model'] = {'eva': 'evit_tiny_p8', 'lara': 'evit_small_p16', 'softmax': 'evit_tiny_p8'}.get(attn, 'CausalEVAttention layer')
+        out['model'] = {'eva': 'evit_tiny_p8', 'lara': 'evit_small_p16', 'softmax': 'evit_tiny_p8', 'performer': 'evit_tiny_p8', 'scatterbrain': 'evit_tiny_p8', 'ra': 'evit_tiny_p8'}.get(attn, 'CausalEVAttention layer')
     for B in ((128, 1024) if layer is not None else ()):
         x = torch.randn(B, 28, 28, 192, device=dev)
 
