@@ -5,16 +5,19 @@
 //
 // One (batch, head) item per CTA iteration, 256 threads (TMEM lane = token of the 128-token tile; warps w and w + 4 share a lane
 // quarter and split the 64 feature columns of every epilogue), two CTAs per SM (100 KB of tiles, 256 TMEM columns).  Per item, with W' = d^-1/4 W in 16 bits ([features][d], K-major):
-//   pass 1   per key tile:    DD = K W'^T (M = 128 tokens, N = 64 features)        -> running max = the key stabiliser
-//   pass 2   per key tile:    DD again; thread-local phi(k) = m^-1/2 exp(DD - |k|^2 d^-1/2 / 2 - stab) + 1e-4 (0 for padding)
-//                             -> 16-bit tile F [tokens][features];  KV (+)= F^T V  (A and B both MN-major, M = 64 features),
-//                             KS (+)= F^T 1  (the same MMA against a constant tile of ones: column sums without a reduction)
-//            KV -> 16-bit tile [features][d], KS column 0 -> ksum (float32)
+//   keys     per key tile:    DD = K W'^T (M = 128 tokens, N = 64 features); the key stabiliser of the reference (max over every token
+//                             and feature of DD) is a RUNNING maximum: phi~(k) = exp(DD - |k|^2 d^-1/2 / 2 - s_run) (0 for padding) ->
+//                             16-bit tile F [tokens][features];  KVe (+)= F^T V  (A and B both MN-major, M = 64 features),
+//                             KSe (+)= F^T 1  (the same MMA against a constant tile of ones: column sums without a reduction),
+//                             SV (+)= 1^T V;  when a tile raises the maximum the accumulators are rescaled in tensor memory
+//            KV = m^-1/2 KVe + 1e-4 SV -> 16-bit tile [features][d], ksum = m^-1/2 KSe + 1e-4 n_live (float32)
+//            (kLogF, ScatterBrain's statistics: a first pass W' K^T for the per-feature maxima instead, see below)
 //   phase Q  per query tile:  DD = Q W'^T; phi(q) with the row's own max; den = phi(q) . ksum (float32, thread-local);
 //                             O = F KV (B MN-major) -> / max(den, 1e-2) -> 128-byte row stores
 // Loads: cp.async, 16 bytes per lane (8 lanes per 128-byte row), into 128-byte-swizzled tiles, two buffers: the tiles of an item form
 // a list of stages (pass 1 | pass 2 | queries) and the successor stage -- also across items -- is requested before the current one is
 // consumed.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,7 +32,7 @@ using fused::tmem_ld_cols;
 
 constexpr int kThreads = 256;       // warps w and w + 4 share a TMEM lane quarter and split the columns of every epilogue
 constexpr int kTile = 128;
-constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cO = 160;     // TMEM columns
+constexpr uint32_t cDD = 0, cKV = 64, cKS = 128, cSV = 144, cO = 0;   // TMEM columns (O overlays DD: DD is in registers by then)
 // shared memory (bytes from the 1024-aligned base)
 constexpr int kX = 0, kV = 32768, kF = 65536, kW = 81920, kKVt = 90112, kOnes = 98304, kKsum = 100352, kRed = kKsum + 256,   // X / V: two buffers of 16 KB
               kHs = kRed + 64, kMxs = kHs + 512, kPm = kMxs + 256, kPd = kPm + 1024, kMx2 = kPd + 1024, kBar = kMx2 + 512, kTmemPtr = kBar + 16, kSmemBytes = kTmemPtr + 16;
@@ -40,6 +43,7 @@ struct Params {
   const uint8_t* mask;      // [B, N] or NULL
   float* stabv;             // kLogF: [items][64] per-feature maxima of the keys' log-features
   float* part;              // kLogF: [items][64 * 64 + 64] KV | ksum
+  int trace;                // EVA_SM100_TRACE=1: phase clocks of one key stage and one query stage (block 0, thread 0)
 };
 
 template <typename T> struct Fmt;
@@ -132,13 +136,19 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
   const int tiles = (p.N + kTile - 1) / kTile;
   // The tiles of an item form a list of stages: [K tiles (pass 1)] [K + V tiles (pass 2)] [Q tiles].  Stage g of this CTA lives in
   // buffer g & 1; its successor (possibly the first stage of the CTA's next item) is requested with cp.async before it is consumed.
-  const int stages_per_item = (kLogF ? 2 : 3) * tiles;
+  const int stages_per_item = 2 * tiles;           // kLogF: [K (maxima)] [K + V]; else: [K + V (online stabiliser)] [Q]
   uint32_t gs = 0;                                  // stages consumed so far
+  long long tk[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) tk[i] = 0;
+  const bool tr = p.trace && blockIdx.x == 0 && tid == 0;
+#define RFA_MARK(i, cond) if (tr && (cond)) tk[i] = clock64();
   int buf = 0;
   auto stage_load = [&](int item_, int s_, int buf_) {
     const int b_ = item_ / p.H, h_ = item_ % p.H, pass = s_ / tiles, t_ = s_ - pass * tiles;
-    load_tile_async<T>(pass == 2 ? q : k, b_, h_, t_ * kTile, p.N, sm + kX + buf_ * 16384);
-    if (pass == 1) load_tile_async<T>(v, b_, h_, t_ * kTile, p.N, sm + kV + buf_ * 16384);
+    const bool is_q = !kLogF && pass == 1, with_v = kLogF ? pass == 1 : pass == 0;
+    load_tile_async<T>(is_q ? q : k, b_, h_, t_ * kTile, p.N, sm + kX + buf_ * 16384);
+    if (with_v) load_tile_async<T>(v, b_, h_, t_ * kTile, p.N, sm + kV + buf_ * 16384);
   };
   // make stage (item_, s_) current: request its successor, wait for its own tiles
   auto acquire = [&](int item_, int s_) {
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
   int h_loaded = -1;
   for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
     const int b = item / p.H, h = item % p.H;
+    RFA_MARK(10, item == (int)blockIdx.x)
     if (h != h_loaded) {                            // W' = d^-1/4 W of this head, 16-bit, [feature][d] rows of 128 bytes
       const float* W = p.proj + (long long)h * 4096;
       for (int idx = tid; idx < 512; idx += kThreads) {
@@ -174,7 +185,6 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
       }
       h_loaded = h;
     }
-    float stab = 0.f;
     if constexpr (kLogF) {
       // ---- pass 1: per-feature maximum over the live tokens of log phi(k)_c = DD - |k|^2 term - log(m) / 2 ----
       float mxc = kNegInf;
@@ -212,52 +222,84 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
       __syncthreads();
       if (tid < 64) mxs[tid] = fmaxf(mx2[tid], mx2[64 + tid]) - hlm;
       __syncthreads();
-    } else {
-    // ---- pass 1: stabiliser of the keys = max over (token, feature) of DD (reference :48-51; padded keys count) ----
-    float mx = kNegInf;
-    for (int t = 0; t < tiles; ++t) {
-      acquire(item, t);
-      hand_over();
-      issue_dd();
-      mma_wait();
-      {
-        float dd[32], tmx = kNegInf;
-        tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(dd));      // warp-collective: every lane, valid token or not
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tmx = fmaxf(tmx, dd[j]);
-        if (t * kTile + r < p.N) mx = fmaxf(mx, tmx);
-      }
     }
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    ptx::tc_fence_before();
-    __syncthreads();
-    stab = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    // favorp: NO separate stabiliser pass.  The key stabiliser (max over every token and feature of DD, padded keys included,
+    // reference :48-51) is tracked as a running maximum s_run: features are exp(DD - |k|^2 term - s_run) WITHOUT the m^-1/2 factor and
+    // the 1e-4 (which must not be rescaled); when a tile raises the maximum the accumulators in tensor memory are multiplied by
+    // exp(s_old - s_new); at the end KV = m^-1/2 KVe + 1e-4 sum_n v_n (a third MMA, ones^T V), ksum = m^-1/2 KSe + 1e-4 n_live.
+    float s_run = kNegInf, n_live = (float)p.N;
+    if constexpr (!kLogF) {
+      if (p.mask) {
+        float c = 0.f;
+        for (int i = tid; i < p.N; i += kThreads) c += p.mask[(long long)b * p.N + i] ? 1.f : 0.f;
+        c = warp_sum(c);
+        if (lane == 0) red[8 + warp] = c;
+        __syncthreads();
+        n_live = (float)p.N - (red[8] + red[9] + red[10] + red[11] + red[12] + red[13] + red[14] + red[15]);
+      }
     }
     // ---- pass 2: KV = phi(K)^T V, KS = phi(K)^T 1 ----
     for (int t = 0; t < tiles; ++t) {
+      RFA_MARK(0, t == 2 && item == (int)blockIdx.x)
       if (t > 0) mma_wait();                        // the previous tile's KV / KS MMAs have read F and its V buffer (the one the
-      acquire(item, tiles + t);                     // successor stage is loaded into)
+      acquire(item, kLogF ? tiles + t : t);         // successor stage is loaded into)
+      if constexpr (!kLogF) {
+        if (p.mask) {                               // padded keys must not enter sum_n v_n: their v rows become zero
+          const int n = t * kTile + r;
+          if (n < p.N && p.mask[(long long)b * p.N + n]) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sm + kV + buf * 16384 + r * 128 + (((4 * hf + c) ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      RFA_MARK(1, t == 2 && item == (int)blockIdx.x)
       hand_over();
       issue_dd();
       mma_wait();
+      RFA_MARK(2, t == 2 && item == (int)blockIdx.x)
       {
         const int n = t * kTile + r;
         const bool dead = n >= p.N || (p.mask && p.mask[(long long)b * p.N + n]);
         float f[32];
         tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
         ptx::tmem_ld_wait();
-        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + (kLogF ? hlm : stab);
+        if constexpr (!kLogF) {                     // running stabiliser: this tile's maximum (every row of the sequence), rescale if it grew
+          float tmx = kNegInf;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tmx = fmaxf(tmx, f[j]);
+          tmx = warp_max(n < p.N ? tmx : kNegInf);
+          if (lane == 0) red[warp] = tmx;
+          __syncthreads();
+          const float s_new = fmaxf(s_run, fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7]))));
+          if (t > 0 && s_new > s_run) {             // (block-uniform) accumulators of the earlier tiles: x exp(s_old - s_new)
+            const float c = __expf(s_run - s_new);
+            float kv[32];
+            uint32_t ks4[4];
+            tmem_ld_cols<32>(trow + cKV + 32 * hf, reinterpret_cast<uint32_t*>(kv));
+            tmem_ld_cols<4>(trow + cKS, ks4);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) kv[j] *= c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ks4[j] = __float_as_uint(__uint_as_float(ks4[j]) * c);
+            fused::tmem_st_cols<32>(trow + cKV + 32 * hf, reinterpret_cast<const uint32_t*>(kv));
+            if (hf == 0) fused::tmem_st_cols<4>(trow + cKS, ks4);
+            ptx::tmem_st_wait();
+          }
+          s_run = s_new;
+        }
+        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + (kLogF ? hlm : s_run);
         const float live = dead ? 0.f : 1.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {              // branch-free (a select around every exponential compiles to a divergence region)
           if constexpr (kLogF) f[j] = live * __expf(fminf(f[j] - sub - mxs[32 * hf + j], 0.f));   // live rows: <= 0 by the definition of mxs
-          else f[j] = live * fmaf(ratio, __expf(f[j] - sub), 1e-4f);                              // <= 0 for every row: stab covers them all
+          else f[j] = live * __expf(f[j] - sub);                                                   // <= 0: s_run covers this tile
         }
         store_half16<T>(sm + kF, r, hf, f);
       }
+      RFA_MARK(3, t == 2 && item == (int)blockIdx.x)
       hand_over();
+      RFA_MARK(4, t == 2 && item == (int)blockIdx.x)
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
         const uint64_t dVb = dV + (uint64_t)(buf * 1024);
@@ -265,6 +307,10 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKV, dF + 128 * ks, dVb + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cKS, dF + 128 * ks, dOnes, id_ks, (t > 0 || ks > 0) ? 1u : 0u);
+        if constexpr (!kLogF) {                     // SV = ones^T V: every accumulator row holds sum_n v_n
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) ptx::umma_ss(tmem + cSV, dOnes, dVb + 128 * ks, id_kv, (t > 0 || ks > 0) ? 1u : 0u);
+        }
         ptx::umma_commit(bar);
       }
     }
@@ -283,9 +329,16 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
           for (int d4 = 0; d4 < 8; ++d4) reinterpret_cast<float4*>(dst + j * 64 + 32 * hf)[d4] = make_float4(kv[4 * d4], kv[4 * d4 + 1], kv[4 * d4 + 2], kv[4 * d4 + 3]);
           if (hf == 0) { dst[64 * 64 + j] = __uint_as_float(ks0); p.stabv[(long long)item * 64 + j] = mxs[j]; }
         }
-      } else if (lane < 16) {
-        store_half16<T>(sm + kKVt, j, hf, kv);
-        if (hf == 0) ksum[j] = __uint_as_float(ks0);
+      } else {
+        float sv[32];
+        tmem_ld_cols<32>(trow + cSV + 32 * hf, reinterpret_cast<uint32_t*>(sv));
+        ptx::tmem_ld_wait();
+        if (lane < 16) {
+#pragma unroll
+          for (int d = 0; d < 32; ++d) kv[d] = fmaf(ratio, kv[d], 1e-4f * sv[d]);
+          store_half16<T>(sm + kKVt, j, hf, kv);
+          if (hf == 0) ksum[j] = fmaf(ratio, __uint_as_float(ks0), 1e-4f * n_live);
+        }
       }
     }
     if constexpr (kLogF) {
@@ -295,10 +348,12 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
     }
     // ---- phase Q ----
     for (int t = 0; t < tiles; ++t) {
-      acquire(item, 2 * tiles + t);
+      RFA_MARK(5, t == 2 && item == (int)blockIdx.x)
+      acquire(item, tiles + t);
       hand_over();
       issue_dd();
       mma_wait();
+      RFA_MARK(6, t == 2 && item == (int)blockIdx.x)
       {
         float f[32];
         tmem_ld_cols<32>(trow + cDD + 32 * hf, reinterpret_cast<uint32_t*>(f));
@@ -319,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         pd[128 * hf + r] = den;
         store_half16<T>(sm + kF, r, hf, f);
       }
+      RFA_MARK(7, t == 2 && item == (int)blockIdx.x)
       hand_over();
       if (warp == 0 && ptx::elect_one()) {
         ptx::tc_fence_after();
@@ -327,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         ptx::umma_commit(bar);
       }
       mma_wait();
+      RFA_MARK(8, t == 2 && item == (int)blockIdx.x)
       {
         float o[32];
         tmem_ld_cols<32>(trow + cO + 32 * hf, reinterpret_cast<uint32_t*>(o));
@@ -342,6 +399,10 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         }
       }
     }
+    RFA_MARK(9, item == (int)blockIdx.x)
+    if (tr && item == (int)blockIdx.x)
+      printf("rfa trace (cycles): key stage: wait KV MMA + acquire %lld | sync + DD MMA %lld | epilogue %lld | sync %lld ; query stage: acquire + sync + DD MMA %lld | epilogue %lld | sync + O MMA %lld ; item total %lld\n",
+             tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[6] - tk[5], tk[7] - tk[6], tk[8] - tk[7], tk[9] - tk[10]);
     ptx::tc_fence_before();
     __syncthreads();                                // ksum / KV tile / W tile are rewritten by the next item
   }
@@ -370,7 +431,8 @@ bool rfa_tc_supported(int method, int D, int m, int cosw, int io_dtype, const Vi
 
 cudaError_t launch_rfa_tc(int B, int H, int N, int io_dtype, const View& q, const View& k, const View& v, const uint8_t* mask,
                           const float* proj, void* out, cudaStream_t st, float* sb_stabv, float* sb_part) {
-  rfatc::Params p{B, H, N, B * H, proj, mask, sb_stabv, sb_part};
+  static const int trace = [] { const char* e = getenv("EVA_SM100_TRACE"); return (e && e[0] == '1') ? 1 : 0; }();
+  rfatc::Params p{B, H, N, B * H, proj, mask, sb_stabv, sb_part, trace};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
