@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
       acquire(item, kLogF ? tiles + t : t);         // successor stage is loaded into)
       if constexpr (!kLogF) {
         if (p.mask) {                               // padded keys must not enter sum_n v_n: their v rows become zero
+          __syncthreads();                          // (a row's 16-byte pieces were copied by OTHER threads: their cp.async must have landed)
           const int n = t * kTile + r;
           if (n < p.N && p.mask[(long long)b * p.N + n]) {
 #pragma unroll

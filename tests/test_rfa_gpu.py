@@ -78,6 +78,31 @@ def test_performer_tcgen05_path_vs_oracle(dtype, B, N, masked):
     assert worst < TOL[dtype], (dtype, B, N, worst)
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+def test_performer_tcgen05_running_stabiliser_rescales(dtype):
+    """Keys whose magnitude grows along the sequence: the running maximum of the tcgen05 kernel rises at every 128-token tile, so the
+    accumulators in tensor memory are rescaled six times per item; padded keys (which still count for the stabiliser) carry the
+    largest rows.  Against the float64 oracle."""
+    from efficient_attention import _abi
+    B, N, H, D = 3, 784, 3, 64
+    g = torch.Generator().manual_seed(41)
+    packed = torch.randn(B, N, 3, H, D, generator=g)
+    packed[:, :, 1] *= (0.3 + 1.2 * torch.arange(N).float() / N).view(1, N, 1, 1)
+    packed = packed.to(dtype)
+    dev = packed.to(_dev())
+    q, k, v = dev[:, :, 0], dev[:, :, 1], dev[:, :, 2]
+    qr, kr, vr = (packed[:, :, i].double().transpose(1, 2) for i in range(3))
+    proj = torch.randn(H, 64, D, generator=torch.Generator().manual_seed(6))
+    mask = torch.zeros(B, N, dtype=torch.bool)
+    mask[1, -100:] = True
+    before = _abi.rfa_tc_launches()
+    out = _abi.rfa_forward(q, k, v, method='favorp', proj=proj.to(_dev()), pad_mask=mask.to(_dev()))
+    assert _abi.rfa_tc_launches() == before + 1
+    ref = R.performer_core(qr, kr, vr, method='favorp', proj=proj.double(), pad_mask=mask)
+    err = rel_l2(out.cpu(), _heads(ref, B, N, H, D))
+    assert err < TOL[dtype], (dtype, err)
+
+
 @pytest.mark.parametrize('D,m', [(16, 24), (32, 64), (128, 128)])
 def test_performer_core_other_head_dims(D, m):
     from efficient_attention import _abi
