@@ -97,10 +97,16 @@ eva_window_tc_kernel(const Params p) {
       qtok[tid] = tok;
       qpad[tid] = (tok >= 0 && p.mask) ? (int)p.mask[(long long)b * g.N + tok] : 0;
     }
-    for (int idx = tid; idx < 128 * 8; idx += kThreads) {
+    // The eight lanes that share a row compute its token ONCE: lane piece p < 4 of a group takes the group's row of iteration p
+    // (the window arithmetic has integer divisions; it used to run once per 16-byte piece), the others get it by shuffle.
+    int qtok_mine = -1;
+    if ((tid & 7) < 4) {
+      const int li = rb * 128 + (tid >> 3) + 32 * (tid & 7);
+      qtok_mine = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+    }
+    for (int idx = tid, it = 0; idx < 128 * 8; idx += kThreads, ++it) {
       const int row = idx >> 3, piece = idx & 7;
-      const int li = rb * 128 + row;
-      const int tok = li < g.L ? group_token(g, win, li, g.window, 0) : -1;
+      const int tok = __shfl_sync(0xffffffffu, qtok_mine, (lane & 24) + it);
       uint4 z = make_uint4(0, 0, 0, 0);
       if (tok >= 0) z = __ldg(reinterpret_cast<const uint4*>(p.q.row<T>(b, tok, h)) + piece);
       *reinterpret_cast<uint4*>(sm + kQ + tile_off(row, 8 * piece)) = z;
@@ -112,13 +118,19 @@ eva_window_tc_kernel(const Params p) {
     auto load_tile = [&](int kt0, int buf) -> int {
       int flags = 0;
       int* kflag = kflag_all + 128 * buf;
-      for (int idx = tid; idx < 128 * 8; idx += kThreads) {
+      int ktok_mine = -1;                            // token of the group's row of iteration p, computed by lane piece p < 4
+      if ((tid & 7) < 4) {
+        const int gj = kt0 + (tid >> 3) + 32 * (tid & 7);
+        if (gj < g.J) ktok_mine = group_token(g, win, gj, g.window, g.ext);
+      }
+      for (int idx = tid, it = 0; idx < 128 * 8; idx += kThreads, ++it) {
         const int j = idx >> 3, piece = idx & 7;
         const int gj = kt0 + j;
         const uint32_t dk = ptx::smem_u32(sm + kK + buf * kBuf + tile_off(j, 8 * piece)), dv = dk + (kV - kK);
+        const int tok_row = __shfl_sync(0xffffffffu, ktok_mine, (lane & 24) + it);
         int flag = 0;
         if (gj < g.J) {
-          const int tok = group_token(g, win, gj, g.window, g.ext);
+          const int tok = tok_row;
           const int sz = tok >= 0 ? 16 : 0;
           const int tk_ = tok >= 0 ? tok : 0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(reinterpret_cast<const uint4*>(p.k.row<T>(b, tk_, h)) + piece), "r"(sz) : "memory");
@@ -145,7 +157,7 @@ eva_window_tc_kernel(const Params p) {
           const int thr_chunk = (g.causal && gj >= g.J && gj < n_keys) ? gj - g.J + 1 : never;
           float add = flag == 0 ? 0.f : (flag == 1 ? g.mask_fill : kNegInf);
           if (p.key_bias && flag == 0 && gj < g.J) {     // (flag 0 and gj < J: the slot holds a token)
-            add = __ldg(p.key_bias + (long long)bh * g.N + group_token(g, win, gj, g.window, g.ext));
+            add = __ldg(p.key_bias + (long long)bh * g.N + tok_row);
             flags |= 4;                                  // the tile needs the per-key table
           }
           kfac_all[128 * buf + j] = make_float4(flag == 0 ? 1.f : 0.f, add, __int_as_float(thr_row), __int_as_float(thr_chunk));
