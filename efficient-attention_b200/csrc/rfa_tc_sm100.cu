@@ -29,6 +29,7 @@ namespace eva {
 namespace rfatc {
 
 using fused::tmem_ld_cols;
+using fused::ex2;
 
 constexpr int kThreads = 256;       // warps w and w + 4 share a TMEM lane quarter and split the columns of every epilogue
 constexpr int kTile = 128;
@@ -291,10 +292,11 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         }
         const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + (kLogF ? hlm : s_run);
         const float live = dead ? 0.f : 1.f;
+        const float sub2 = dead ? kNegInf : -sub * kLog2e;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {              // branch-free (a select around every exponential compiles to a divergence region)
           if constexpr (kLogF) f[j] = live * __expf(fminf(f[j] - sub - mxs[32 * hf + j], 0.f));   // live rows: <= 0 by the definition of mxs
-          else f[j] = live * __expf(f[j] - sub);                                                   // <= 0: s_run covers this tile
+          else f[j] = ex2(fmaf(f[j], kLog2e, sub2));        // one FMA + one MUFU per feature; <= 0: s_run covers this tile; dead rows: -inf
         }
         store_half16<T>(sm + kF, r, hf, f);
       }
@@ -365,11 +367,11 @@ __global__ void __launch_bounds__(kThreads, 2) rfa_favorp_tc_kernel(const View q
         pm[128 * hf + r] = rmx;
         __syncthreads();                            // the two column halves of a row meet
         rmx = fmaxf(pm[r], pm[128 + r]);
-        const float sub = half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + rmx;
+        const float sub2 = -(half_dn2 * row_sq<T>(sm + kX + buf * 16384, r) + rmx) * kLog2e;
         float den = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          f[j] = fmaf(ratio, __expf(f[j] - sub), 1e-4f);
+          f[j] = fmaf(ratio, ex2(fmaf(f[j], kLog2e, sub2)), 1e-4f);
           den = fmaf(f[j], ksum[32 * hf + j], den);
         }
         pd[128 * hf + r] = den;

@@ -27,6 +27,7 @@ namespace eva {
 namespace sbtc {
 
 using fused::tmem_ld_cols;
+using fused::ex2;
 
 constexpr int kThreads = 256;       // warps w and w + 4 share a TMEM lane quarter and split the columns of every epilogue
 constexpr uint32_t cDD = 0, cLa = 64, cLsa = 128, cLb = 144, cLsb = 208, cS = 64, cP = 64, cO = 192;
@@ -284,11 +285,12 @@ __global__ void __launch_bounds__(kThreads, 2) sb_window_tc_kernel(const View q,
         pm[128 * hf + r] = mx;
         __syncthreads();                            // the two column halves of a row meet
         mx = fmaxf(pm[r], pm[128 + r]);
+        const float mx2 = -mx * kLog2e;             // (every row has finite feature logits: mx is finite)
         float rsum = 0.f;
         uint32_t pl[16], pr_[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float e0 = __expf(s[j] - mx), e1 = __expf(s[j + 1] - mx), f0 = __expf(rr[j] - mx), f1 = __expf(rr[j + 1] - mx);
+          const float e0 = ex2(fmaf(s[j], kLog2e, mx2)), e1 = ex2(fmaf(s[j + 1], kLog2e, mx2)), f0 = ex2(fmaf(rr[j], kLog2e, mx2)), f1 = ex2(fmaf(rr[j + 1], kLog2e, mx2));
           rsum += (e0 + e1) + (f0 + f1);
           pl[j >> 1] = Pair16<T>::pk(e0, e1);
           pr_[j >> 1] = Pair16<T>::pk(f0, f1);
